@@ -1,0 +1,199 @@
+// ecg_point.cuh — Jacobian point arithmetic over a field policy F (FpK256 / FpP256).
+//
+// Replaces (same group law, different coordinates) the reference's homogeneous-projective complete
+// formulas: k256/src/arithmetic/projective.rs:96-131 (add), :142-176 (add_mixed), :189-217 (double)
+// and primeorder/src/point_arithmetic.rs:222-245, :254-280, :289-318 for a = -3.
+// Affine results are canonical, so any coordinate system gives bit-identical output after
+// normalisation (the reference itself only compares after to_affine).
+//
+// Conventions: a Jacobian point (X:Y:Z) is (X/Z^2, Y/Z^3); Z == 0 (mod p) is the identity.
+// Jacobian formulas are incomplete, so every exceptional case (identity operands, P == Q, P == -Q) is
+// detected and routed through a slow path; in the windowed loops they are unreachable for honest
+// inputs (a warp-uniform not-taken branch), but adversarial inputs must still give exact results.
+#pragma once
+#include "ecg_prim.cuh"
+
+namespace ecg {
+
+struct Jac {
+  Fe X, Y, Z;
+};
+struct Aff {
+  Fe x, y;
+};
+
+// a = c ? -a : a  (branch-free: lanes of a warp disagree on c)
+template <class F>
+ECG_D void fe_cneg(Fe& a, uint32_t c) {
+  Fe n;
+  F::neg(n, a);
+#pragma unroll
+  for (int i = 0; i < 8; i++) a.v[i] = c ? n.v[i] : a.v[i];
+}
+// r = c ? t : r
+ECG_D void jac_csel(Jac& r, const Jac& t, uint32_t c) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.X.v[i] = c ? t.X.v[i] : r.X.v[i];
+    r.Y.v[i] = c ? t.Y.v[i] : r.Y.v[i];
+    r.Z.v[i] = c ? t.Z.v[i] : r.Z.v[i];
+  }
+}
+
+// Doubling in "halved" form (Z3 = Y*Z, X3 = X3_std/4, Y3 = Y3_std/8): 3M+4S (a=0) / 4M+4S (a=-3),
+// 8 cheap linear ops.   L = (3X^2 + a Z^4)/2;  X3 = L^2 - 2XY^2;  Y3 = L(XY^2 - X3) - Y^4.
+template <class F, bool A_IS_MINUS3>
+ECG_D void jac_dbl(Jac& r, const Jac& p) {
+  Fe A, L, T, D, t;
+  F::sqr(A, p.Y);  // Y^2
+  if (A_IS_MINUS3) {
+    Fe zz, u, v;
+    F::sqr(zz, p.Z);
+    F::sub(u, p.X, zz);
+    F::add(v, p.X, zz);
+    F::mul(L, u, v);  // X^2 - Z^4
+  } else {
+    F::sqr(L, p.X);
+  }
+  F::mul_small(L, L, 3);
+  F::half(L, L);
+  F::mul(T, p.X, A);   // X*Y^2
+  F::mul(r.Z, p.Y, p.Z);
+  F::sqr(D, A);        // Y^4
+  F::sqr(r.X, L);
+  F::add(t, T, T);
+  F::sub(r.X, r.X, t);
+  F::sub(t, T, r.X);
+  F::mul(r.Y, L, t);
+  F::sub(r.Y, r.Y, D);
+}
+
+// 2*(x,y) for an affine input (Z = 1): saves the Z products.
+template <class F, bool A_IS_MINUS3>
+ECG_D void aff_dbl(Jac& r, const Aff& p) {
+  Jac j;
+  j.X = p.x;
+  j.Y = p.y;
+  F::set_one(j.Z);  // internal-form one
+  jac_dbl<F, A_IS_MINUS3>(r, j);
+}
+
+// Slow path of mixed addition: identity accumulator, or H == 0.
+template <class F, bool A_IS_MINUS3>
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+    void
+    jac_madd_slow(Jac& r, const Jac& p, const Aff& q, bool z1zero, bool rzero) {
+  if (z1zero) {  // O + Q = Q
+    r.X = q.x;
+    r.Y = q.y;
+    F::set_one(r.Z);
+  } else if (rzero) {  // P == Q
+    aff_dbl<F, A_IS_MINUS3>(r, q);
+  } else {  // P == -Q
+    F::set_zero(r.X);
+    F::set_one(r.Y);
+    F::set_zero(r.Z);
+  }
+}
+
+// r = p + q, q affine and not the identity.  8M+3S.  If zr != nullptr it receives Z3/Z1 (= H).
+template <class F, bool A_IS_MINUS3>
+ECG_D void jac_madd(Jac& r, const Jac& p, const Aff& q, Fe* zr = nullptr) {
+  Fe zz, u2, s2, H, R, hh, hhh, V, t;
+  F::sqr(zz, p.Z);
+  F::mul(u2, q.x, zz);
+  F::mul(s2, p.Z, zz);
+  F::mul(s2, s2, q.y);
+  F::sub(H, u2, p.X);
+  F::sub(R, s2, p.Y);
+  bool z1zero = F::is_zero(p.Z);
+  bool hzero = F::is_zero(H);
+  if (z1zero | hzero) {
+    jac_madd_slow<F, A_IS_MINUS3>(r, p, q, z1zero, F::is_zero(R));
+    if (zr) F::set_zero(*zr);
+    return;
+  }
+  F::sqr(hh, H);
+  F::mul(hhh, H, hh);
+  F::mul(V, p.X, hh);
+  F::mul(r.Z, p.Z, H);
+  if (zr) *zr = H;
+  F::sqr(t, R);
+  F::sub(t, t, hhh);
+  F::sub(t, t, V);
+  F::sub(r.X, t, V);
+  F::sub(t, V, r.X);
+  F::mul(t, t, R);
+  F::mul(hhh, hhh, p.Y);
+  F::sub(r.Y, t, hhh);
+}
+
+// r = p + q, both Jacobian.  12M+4S.
+template <class F, bool A_IS_MINUS3>
+ECG_D void jac_add(Jac& r, const Jac& p, const Jac& q) {
+  bool z1zero = F::is_zero(p.Z), z2zero = F::is_zero(q.Z);
+  if (z1zero) {
+    r = q;
+    return;
+  }
+  if (z2zero) {
+    r = p;
+    return;
+  }
+  Fe z1z1, z2z2, u1, u2, s1, s2, H, R, hh, hhh, V, t;
+  F::sqr(z1z1, p.Z);
+  F::sqr(z2z2, q.Z);
+  F::mul(u1, p.X, z2z2);
+  F::mul(u2, q.X, z1z1);
+  F::mul(s1, q.Z, z2z2);
+  F::mul(s1, s1, p.Y);
+  F::mul(s2, p.Z, z1z1);
+  F::mul(s2, s2, q.Y);
+  F::sub(H, u2, u1);
+  F::sub(R, s2, s1);
+  if (F::is_zero(H)) {
+    if (F::is_zero(R)) {
+      jac_dbl<F, A_IS_MINUS3>(r, p);
+    } else {
+      F::set_zero(r.X);
+      F::set_one(r.Y);
+      F::set_zero(r.Z);
+    }
+    return;
+  }
+  F::sqr(hh, H);
+  F::mul(hhh, H, hh);
+  F::mul(V, u1, hh);
+  F::mul(t, p.Z, q.Z);
+  F::mul(r.Z, t, H);
+  F::sqr(t, R);
+  F::sub(t, t, hhh);
+  F::sub(t, t, V);
+  F::sub(r.X, t, V);
+  F::sub(t, V, r.X);
+  F::mul(t, t, R);
+  F::mul(hhh, hhh, s1);
+  F::sub(r.Y, t, hhh);
+}
+
+// y^2 == x^3 + a x + b ?   (AffinePoint::from_coordinates on-curve check, k256/src/arithmetic/affine.rs:134-147)
+template <class F, bool A_IS_MINUS3>
+ECG_D bool aff_on_curve(const Aff& p, const Fe& b_internal) {
+  Fe l, r, t;
+  F::sqr(l, p.y);
+  F::sqr(r, p.x);
+  F::mul(r, r, p.x);
+  if (A_IS_MINUS3) {
+    F::mul_small(t, p.x, 3);
+    F::sub(r, r, t);
+  }
+  F::add(r, r, b_internal);
+  F::sub(l, l, r);
+  return F::is_zero(l);
+}
+
+}  // namespace ecg

@@ -1,0 +1,100 @@
+#!/usr/bin/env python3
+"""Extract the reference's golden vectors into tests/golden/*.json.
+
+Run once in the authoring container (needs /root/reference, which does NOT
+exist on the GPU box): `python oracle/extract_golden.py`.  The JSON files it
+writes are committed; tests read only those.
+
+Sources (relative to /root/reference):
+  k256/src/test_vectors/group.rs:9   ADD_TEST_VECTORS (k*G, k=1..20)
+  k256/src/test_vectors/group.rs:96  MUL_TEST_VECTORS (k, x, y)
+  p256/src/test_vectors/group.rs:8,95   same for P-256
+  {k256,p256}/src/test_vectors/field.rs:6  DBL_TEST_VECTORS (2^i, 32 B BE)
+  {k256,p256}/src/test_vectors/ecdsa.rs    d -> (q_x, q_y) pairs (a k*G fixture each)
+  {k256,p256}/benches/point.rs             the criterion bench scalars
+"""
+import json
+import os
+import re
+import sys
+
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+HEX = re.compile(r'hex!\(\s*"([0-9A-Fa-f]+)"\s*\)')
+
+
+def hexes(text):
+    return [h.lower() for h in HEX.findall(text)]
+
+
+def split_consts(text):
+    """Map const name -> text of its initialiser."""
+    out = {}
+    parts = re.split(r"pub const (\w+)", text)
+    for i in range(1, len(parts), 2):
+        out[parts[i]] = parts[i + 1]
+    return out
+
+
+def group_vectors(curve):
+    txt = open(f"{REF}/{curve}/src/test_vectors/group.rs").read()
+    c = split_consts(txt)
+    add = hexes(c["ADD_TEST_VECTORS"])
+    mul = hexes(c["MUL_TEST_VECTORS"])
+    assert len(add) % 2 == 0 and len(mul) % 3 == 0
+    return {
+        "source": f"{curve}/src/test_vectors/group.rs",
+        "add": [{"k": i // 2 + 1, "x": add[i], "y": add[i + 1]} for i in range(0, len(add), 2)],
+        "mul": [{"k": mul[i], "x": mul[i + 1], "y": mul[i + 2]} for i in range(0, len(mul), 3)],
+    }
+
+
+def field_vectors(curve):
+    txt = open(f"{REF}/{curve}/src/test_vectors/field.rs").read()
+    c = split_consts(txt)
+    return {"source": f"{curve}/src/test_vectors/field.rs", "dbl": hexes(c["DBL_TEST_VECTORS"])}
+
+
+def ecdsa_keypairs(curve):
+    txt = open(f"{REF}/{curve}/src/test_vectors/ecdsa.rs").read()
+    out = []
+    for m in re.finditer(r'd:\s*&hex!\("([0-9a-fA-F]+)"\),\s*q_x:\s*&hex!\("([0-9a-fA-F]+)"\),\s*q_y:\s*&hex!\("([0-9a-fA-F]+)"\)', txt):
+        out.append({"d": m.group(1).lower(), "x": m.group(2).lower(), "y": m.group(3).lower()})
+    return {"source": f"{curve}/src/test_vectors/ecdsa.rs", "keypairs": out}
+
+
+def bench_scalars(curve):
+    txt = open(f"{REF}/{curve}/benches/point.rs").read()
+    out = []
+    for m in re.finditer(r"fn (test_scalar_\w)\(\) -> Scalar \{(.*?)\n\}", txt, re.S):
+        body = m.group(2)
+        hx = hexes(body)
+        if hx:
+            out.append({"name": m.group(1), "k": hx[0]})
+        else:
+            b = re.findall(r"0x([0-9a-fA-F]{2})", body)
+            out.append({"name": m.group(1), "k": "".join(b).lower()})
+    return {"source": f"{curve}/benches/point.rs", "scalars": out}
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for curve in ("k256", "p256"):
+        data = {
+            "curve": curve,
+            "reference_commit": "739304e026fdf06cd1a31606e4db487d3f47c5ae",
+            "group": group_vectors(curve),
+            "field": field_vectors(curve),
+            "ecdsa": ecdsa_keypairs(curve),
+            "bench": bench_scalars(curve),
+        }
+        path = os.path.join(OUT, f"{curve}.json")
+        with open(path, "w") as f:
+            json.dump(data, f, indent=1)
+        print(path, len(data["group"]["add"]), len(data["group"]["mul"]), len(data["field"]["dbl"]),
+              len(data["ecdsa"]["keypairs"]), len(data["bench"]["scalars"]))
+
+
+if __name__ == "__main__":
+    main()

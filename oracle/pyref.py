@@ -1,0 +1,163 @@
+"""Big-integer ground truth for the k256 / p256 scalar-multiplication hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product path (libecgpu.so, the
+`ecgpu` package) may import this module; only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline leg do.
+
+This is the *mathematical* definition the reference's results must satisfy
+(affine chord-and-tangent arithmetic over exact Python integers).  The
+algorithm-faithful restatement of the reference's limb code lives in
+oracle/ecref.c; both are pinned against the reference's own golden vectors
+(tests/golden/*.json, extracted by oracle/extract_golden.py from
+k256/src/test_vectors/group.rs:9,96, p256/src/test_vectors/group.rs:8,95,
+*/src/test_vectors/field.rs:6).
+
+Curve constants as they appear in the reference:
+  k256  p  k256/src/arithmetic/field.rs:42       n  k256/src/lib.rs:71
+        G  k256/src/arithmetic/affine.rs:61-77   b=7  k256/src/arithmetic.rs:32-41
+        beta  k256/src/arithmetic/projective.rs:32-37   lambda  k256/src/arithmetic/mul.rs:4-5
+  p256  p  p256/src/arithmetic/field.rs:35       n  p256/src/lib.rs:60
+        a=-3, b, G  p256/src/arithmetic.rs:53-74
+"""
+from __future__ import annotations
+
+import hashlib
+from dataclasses import dataclass
+
+
+@dataclass(frozen=True)
+class Curve:
+    name: str
+    p: int
+    n: int
+    a: int
+    b: int
+    gx: int
+    gy: int
+
+
+K256 = Curve(
+    "k256",
+    p=2**256 - 2**32 - 977,
+    n=0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141,
+    a=0,
+    b=7,
+    gx=0x79BE667EF9DCBBAC55A06295CE870B07029BFCDB2DCE28D959F2815B16F81798,
+    gy=0x483ADA7726A3C4655DA4FBFC0E1108A8FD17B448A68554199C47D08FFB10D4B8,
+)
+P256 = Curve(
+    "p256",
+    p=0xFFFFFFFF00000001000000000000000000000000FFFFFFFFFFFFFFFFFFFFFFFF,
+    n=0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551,
+    a=-3,
+    b=0x5AC635D8AA3A93E7B3EBBD55769886BC651D06B0CC53B0F63BCE3C3E27D2604B,
+    gx=0x6B17D1F2E12C4247F8BCE6E563A440F277037D812DEB33A0F4A13945D898C296,
+    gy=0x4FE342E2FE1A7F9B8EE7EB4A7C0F9E162BCE33576B315ECECBB6406837BF51F5,
+)
+CURVES = {"k256": K256, "p256": P256, 0: K256, 1: P256}
+
+K256_BETA = 0x7AE96A2B657C07106E64479EAC3434E99CF0497512F58995C1396C28719501EE
+K256_LAMBDA = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
+
+# A point is None (identity) or an (x, y) tuple of ints in [0, p).
+
+
+def on_curve(c: Curve, P) -> bool:
+    if P is None:
+        return True
+    x, y = P
+    return 0 <= x < c.p and 0 <= y < c.p and (y * y - (x * x * x + c.a * x + c.b)) % c.p == 0
+
+
+def neg(c: Curve, P):
+    if P is None:
+        return None
+    return (P[0], (-P[1]) % c.p)
+
+
+def add(c: Curve, P, Q):
+    if P is None:
+        return Q
+    if Q is None:
+        return P
+    x1, y1 = P
+    x2, y2 = Q
+    if x1 == x2:
+        if (y1 + y2) % c.p == 0:
+            return None
+        lam = (3 * x1 * x1 + c.a) * pow(2 * y1, -1, c.p) % c.p
+    else:
+        lam = (y2 - y1) * pow(x2 - x1, -1, c.p) % c.p
+    x3 = (lam * lam - x1 - x2) % c.p
+    y3 = (lam * (x1 - x3) - y1) % c.p
+    return (x3, y3)
+
+
+def mul(c: Curve, k: int, P):
+    """k*P by plain double-and-add (k taken mod n)."""
+    k %= c.n
+    R = None
+    Q = P
+    while k:
+        if k & 1:
+            R = add(c, R, Q)
+        Q = add(c, Q, Q)
+        k >>= 1
+    return R
+
+
+def lincomb(c: Curve, ks, Ps):
+    R = None
+    for k, P in zip(ks, Ps):
+        R = add(c, R, mul(c, k, P))
+    return R
+
+
+def G(c: Curve):
+    return (c.gx, c.gy)
+
+
+# ---- canonical encodings used at the C-ABI boundary ----
+
+def enc_scalar(k: int) -> bytes:
+    return k.to_bytes(32, "big")
+
+
+def enc_point(P) -> tuple[bytes, int]:
+    """(x||y big-endian 64 B, inf flag). Identity = 64 zero bytes + flag 1
+    (AffinePoint::IDENTITY, k256/src/arithmetic/affine.rs:53-57)."""
+    if P is None:
+        return bytes(64), 1
+    return P[0].to_bytes(32, "big") + P[1].to_bytes(32, "big"), 0
+
+
+def dec_point(xy: bytes, inf: int):
+    if inf:
+        return None
+    return (int.from_bytes(xy[:32], "big"), int.from_bytes(xy[32:64], "big"))
+
+
+# ---- deterministic synthetic inputs ----
+
+def synth_scalar(c: Curve, seed: int, tag: bytes, i: int) -> int:
+    h = hashlib.sha256(seed.to_bytes(8, "little") + tag + i.to_bytes(8, "little")).digest()
+    return int.from_bytes(h, "big") % c.n
+
+
+def glv_split(k: int):
+    """Exact-integer GLV split used only to cross-check the device decomposition:
+    returns (k1, k2) signed with k1 + k2*lambda == k (mod n)
+    (constants: k256/src/arithmetic/mul.rs:7-35, mul/glv.rs:10-37,149-156)."""
+    n = K256.n
+    a1 = 0x3086D221A7D46BCDE86C90E49284EB15
+    b1 = -0xE4437ED6010E88286F547FA90ABFE4C3
+    a2 = 0x114CA50F7A8E2F3F657C1108D9D44CFD8
+    b2 = a1
+    g1 = 0x3086D221A7D46BCDE86C90E49284EB153DAA8A1471E8CA7FE893209A45DBB031
+    g2 = 0xE4437ED6010E88286F547FA90ABFE4C4221208AC9DF506C61571B4AE8AC47F71
+    c1 = (k * g1 + (1 << 383)) >> 384
+    c2 = (k * g2 + (1 << 383)) >> 384
+    k1 = k - c1 * a1 - c2 * a2
+    k2 = -c1 * b1 - c2 * b2
+    assert (k1 + k2 * K256_LAMBDA - k) % n == 0
+    return k1, k2

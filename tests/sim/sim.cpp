@@ -1,0 +1,94 @@
+// tests/sim/sim.cpp — HOST SIMULATION of the device arithmetic (test infrastructure only).
+// Compiles the very same .cuh headers the CUDA kernels use, with the PTX carry-chain primitives
+// replaced by their C emulation (ecg_prim.cuh, #else branch), so that field / point / scalar-mult logic
+// can be checked against the big-integer oracle in a container that has no GPU.  Never linked into
+// libecgpu.so; never used as a fallback.
+#include <cstring>
+#include <vector>
+#include "../../elliptic-curves_b200/csrc/ecg_mul.cuh"
+#include "../../elliptic-curves_b200/csrc/ecg_io.cuh"
+
+using namespace ecg;
+
+extern "C" {
+
+// op: 0 add 1 sub 2 mul 3 sqr 4 neg 5 half 6 mul3 7 inv 8 normalize 9 mul8   (canonical BE bytes in/out)
+int sim_k256_fe_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  typedef FpK256 F;
+  Fe x, y, r;
+  load_be32(x.v, a);
+  load_be32(y.v, b);
+  switch (op) {
+    case 0: F::add(r, x, y); break;
+    case 1: F::sub(r, x, y); break;
+    case 2: F::mul(r, x, y); break;
+    case 3: F::sqr(r, x); break;
+    case 4: F::neg(r, x); break;
+    case 5: F::half(r, x); break;
+    case 6: F::mul_small(r, x, 3); break;
+    case 7: F::inv(r, x); break;
+    case 8: r = x; break;
+    case 9: F::mul_small(r, x, 8); break;
+    default: return -1;
+  }
+  F::normalize(r, r);
+  store_be32(out, r.v);
+  return 0;
+}
+
+// raw (non-normalised) variant: inputs are arbitrary 256-bit values (exercise the weakly-reduced range)
+int sim_k256_fe_op_raw(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  return sim_k256_fe_op(op, a, b, out);
+}
+
+int sim_k256_glv(const uint8_t* k_be, uint8_t* out /* h1[16] LE, neg1, even1, h2[16], neg2, even2 */) {
+  uint32_t k[8];
+  load_be32(k, k_be);
+  GlvHalf g1, g2;
+  bool ok = glv_split_k256(g1, g2, k);
+  memcpy(out, g1.h, 16);
+  out[16] = (uint8_t)g1.neg;
+  out[17] = (uint8_t)g1.even;
+  memcpy(out + 18, g2.h, 16);
+  out[34] = (uint8_t)g2.neg;
+  out[35] = (uint8_t)g2.even;
+  return ok ? 0 : 1;
+}
+
+// full per-thread variable-base multiplication + per-point inversion
+int sim_k256_mul(const uint8_t* k_be, const uint8_t* P_xy, uint8_t* out_xy, uint8_t* out_inf) {
+  typedef FpK256 F;
+  uint32_t k[8];
+  load_be32(k, k_be);
+  Aff P;
+  load_be32(P.x.v, P_xy);
+  load_be32(P.y.v, P_xy + 32);
+  std::vector<uint32_t> tabmem(8 * 16);
+  TabRef tab{tabmem.data(), 1};
+  Jac r;
+  k256_mul_thread(r, k, P, tab);
+  if (F::is_zero(r.Z)) {
+    memset(out_xy, 0, 64);
+    *out_inf = 1;
+    return 0;
+  }
+  Fe zinv, x, y;
+  F::inv(zinv, r.Z);
+  jac_to_affine_canonical<F>(x, y, r, zinv);
+  store_be32(out_xy, x.v);
+  store_be32(out_xy + 32, y.v);
+  *out_inf = 0;
+  return 0;
+}
+
+int sim_k256_on_curve(const uint8_t* P_xy) {
+  typedef FpK256 F;
+  Aff P;
+  load_be32(P.x.v, P_xy);
+  load_be32(P.y.v, P_xy + 32);
+  Fe b;
+  F::set_zero(b);
+  b.v[0] = 7;
+  return aff_on_curve<F, false>(P, b) ? 1 : 0;
+}
+}
