@@ -1,0 +1,267 @@
+"""ecgpu — Python (ctypes) host-side mirror of the reference's operator surface over libecgpu.so.
+
+The shared library is the product; this module is the thinnest possible binding used by tests/ and
+bench.py.  It mirrors the reference's names for the hot path:
+
+    Engine.mul_batch(curve, k, P)              ProjectivePoint * Scalar over a batch     (k256/src/arithmetic/mul.rs:236-295)
+    Engine.mul_by_generator(curve, k)          ProjectivePoint::mul_by_generator         (mul.rs:180-232)
+    Engine.lincomb(curve, k, P)                LinearCombination::lincomb                (mul.rs:66-175)
+    Engine.mul_by_generator_and_mul_add(...)   MulByGeneratorVartime::..._and_mul_add    (mul.rs:303-310)
+    Engine.batch_normalize(curve, XYZ)         BatchNormalize::batch_normalize           (projective.rs:345-391)
+    Engine.field_op(curve, op, a, b)           FieldElement add/sub/neg/mul/square/invert
+
+Buffers are numpy uint8 arrays (host mode) or raw device pointers (device mode, ECG_FLAG_DEVICE_PTRS).
+There is NO CPU fallback: if libecgpu.so is missing, or no CUDA device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libecgpu.so")
+
+SECP256K1 = 0
+NISTP256 = 1
+CURVE_IDS = {"k256": SECP256K1, "secp256k1": SECP256K1, "p256": NISTP256, "nistp256": NISTP256, 0: 0, 1: 1}
+
+ECG_OK, ECG_EINVAL, ECG_ESCALAR_RANGE, ECG_ENOT_ON_CURVE, ECG_ECUDA, ECG_ENCCL, ECG_ENOMEM = range(7)
+FLAG_DEVICE_PTRS = 1
+FOP = {"add": 0, "sub": 1, "neg": 2, "mul": 3, "sqr": 4, "inv": 5}
+
+EXPORTS = [
+    "ecg_ctx_create", "ecg_ctx_destroy", "ecg_last_error", "ecg_last_error_index", "ecg_ctx_set_stream",
+    "ecg_mul_batch", "ecg_mul_gen_batch", "ecg_lincomb", "ecg_lincomb_partial", "ecg_point_sum",
+    "ecg_mul_gen_add_batch", "ecg_batch_normalize", "ecg_field_op_batch", "ecg_microbench",
+    "ecg_kernel_launches", "ecg_version",
+]
+
+
+class EcgError(RuntimeError):
+    def __init__(self, code: int, msg: str, index: int = -1):
+        super().__init__(f"ecgpu error {code}: {msg}" + (f" (first offending index {index})" if index >= 0 else ""))
+        self.code = code
+        self.index = index
+
+
+class ScalarRangeError(EcgError):
+    """Scalar::from_repr returned None in the reference (k >= n)."""
+
+
+class NotOnCurveError(EcgError):
+    """AffinePoint::from_coordinates returned None in the reference."""
+
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    """dlopen libecgpu.so (fails loudly if it has not been built: run `python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FileNotFoundError(f"{p} not found: the CUDA extension is not built (no CPU fallback exists)")
+    lib = ctypes.CDLL(p)
+    vp, sz, u8p = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p
+    lib.ecg_ctx_create.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_uint, ctypes.POINTER(vp)]
+    lib.ecg_ctx_create.restype = ctypes.c_int
+    lib.ecg_ctx_destroy.argtypes = [vp]
+    lib.ecg_ctx_destroy.restype = None
+    lib.ecg_last_error.argtypes = [vp]
+    lib.ecg_last_error.restype = ctypes.c_char_p
+    lib.ecg_last_error_index.argtypes = [vp]
+    lib.ecg_last_error_index.restype = sz
+    lib.ecg_ctx_set_stream.argtypes = [vp, vp]
+    lib.ecg_ctx_set_stream.restype = ctypes.c_int
+    lib.ecg_mul_batch.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p, u8p, u8p]
+    lib.ecg_mul_batch.restype = ctypes.c_int
+    lib.ecg_mul_gen_batch.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p]
+    lib.ecg_mul_gen_batch.restype = ctypes.c_int
+    lib.ecg_lincomb.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p, u8p, u8p]
+    lib.ecg_lincomb.restype = ctypes.c_int
+    lib.ecg_lincomb_partial.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p, u8p]
+    lib.ecg_lincomb_partial.restype = ctypes.c_int
+    lib.ecg_point_sum.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p]
+    lib.ecg_point_sum.restype = ctypes.c_int
+    lib.ecg_mul_gen_add_batch.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p, u8p, u8p, u8p]
+    lib.ecg_mul_gen_add_batch.restype = ctypes.c_int
+    lib.ecg_batch_normalize.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p]
+    lib.ecg_batch_normalize.restype = ctypes.c_int
+    lib.ecg_field_op_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, sz, u8p, u8p, u8p]
+    lib.ecg_field_op_batch.restype = ctypes.c_int
+    lib.ecg_microbench.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    lib.ecg_microbench.restype = ctypes.c_int
+    lib.ecg_kernel_launches.argtypes = [vp]
+    lib.ecg_kernel_launches.restype = ctypes.c_uint64
+    lib.ecg_version.argtypes = []
+    lib.ecg_version.restype = ctypes.c_char_p
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _u8(a, nbytes: int, name: str) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint8).reshape(-1)
+    if a.size != nbytes:
+        raise ValueError(f"{name}: expected {nbytes} bytes, got {a.size}")
+    return a
+
+
+def _ptr(a) -> ctypes.c_void_p:
+    if a is None:
+        return ctypes.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        return ctypes.c_void_p(a.ctypes.data)
+    return ctypes.c_void_p(int(a))  # raw device pointer
+
+
+class Engine:
+    """One ecg_ctx.  `devices=[0]` host-pointer mode by default; `device_ptrs=True` takes raw CUDA pointers."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None, device_ptrs: bool = False):
+        self.lib = load_library()
+        devs = list(devices) if devices else [0]
+        arr = (ctypes.c_int * len(devs))(*devs)
+        self._ctx = ctypes.c_void_p(0)
+        self.device_ptrs = device_ptrs
+        rc = self.lib.ecg_ctx_create(arr, len(devs), FLAG_DEVICE_PTRS if device_ptrs else 0, ctypes.byref(self._ctx))
+        if rc != ECG_OK:
+            raise EcgError(rc, "ecg_ctx_create failed (is a CUDA device visible? there is no CPU fallback)")
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self.lib.ecg_ctx_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc == ECG_OK:
+            return
+        msg = (self.lib.ecg_last_error(self._ctx) or b"").decode()
+        idx = int(self.lib.ecg_last_error_index(self._ctx))
+        if idx == 2**64 - 1:
+            idx = -1
+        if rc == ECG_ESCALAR_RANGE:
+            raise ScalarRangeError(rc, msg, idx)
+        if rc == ECG_ENOT_ON_CURVE:
+            raise NotOnCurveError(rc, msg, idx)
+        raise EcgError(rc, msg, idx)
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.ecg_ctx_set_stream(self._ctx, ctypes.c_void_p(cuda_stream)))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.ecg_kernel_launches(self._ctx))
+
+    # ---- host-pointer API (numpy) ----
+    def mul_batch(self, curve, k, P_xy, P_inf=None, out_xy=None, out_inf=None):
+        c = CURVE_IDS[curve]
+        n = np.asarray(k).size // 32
+        k = _u8(k, 32 * n, "k")
+        P_xy = _u8(P_xy, 64 * n, "P_xy")
+        if P_inf is not None:
+            P_inf = _u8(P_inf, n, "P_inf")
+        out_xy = np.empty(64 * n, np.uint8) if out_xy is None else out_xy
+        out_inf = np.empty(n, np.uint8) if out_inf is None else out_inf
+        self._check(self.lib.ecg_mul_batch(self._ctx, c, n, _ptr(k), _ptr(P_xy), _ptr(P_inf), _ptr(out_xy), _ptr(out_inf)))
+        return out_xy.reshape(n, 64), out_inf
+
+    def mul_by_generator(self, curve, k, out_xy=None, out_inf=None):
+        c = CURVE_IDS[curve]
+        n = np.asarray(k).size // 32
+        k = _u8(k, 32 * n, "k")
+        out_xy = np.empty(64 * n, np.uint8) if out_xy is None else out_xy
+        out_inf = np.empty(n, np.uint8) if out_inf is None else out_inf
+        self._check(self.lib.ecg_mul_gen_batch(self._ctx, c, n, _ptr(k), _ptr(out_xy), _ptr(out_inf)))
+        return out_xy.reshape(n, 64), out_inf
+
+    def lincomb(self, curve, k, P_xy, P_inf=None):
+        c = CURVE_IDS[curve]
+        n = np.asarray(k).size // 32
+        k = _u8(k, 32 * n, "k")
+        P_xy = _u8(P_xy, 64 * n, "P_xy")
+        if P_inf is not None:
+            P_inf = _u8(P_inf, n, "P_inf")
+        out_xy = np.zeros(64, np.uint8)
+        out_inf = np.zeros(1, np.uint8)
+        self._check(self.lib.ecg_lincomb(self._ctx, c, n, _ptr(k), _ptr(P_xy), _ptr(P_inf), _ptr(out_xy), _ptr(out_inf)))
+        return out_xy, int(out_inf[0])
+
+    def lincomb_partial(self, curve, k, P_xy, P_inf=None):
+        c = CURVE_IDS[curve]
+        n = np.asarray(k).size // 32
+        k = _u8(k, 32 * n, "k")
+        P_xy = _u8(P_xy, 64 * n, "P_xy")
+        if P_inf is not None:
+            P_inf = _u8(P_inf, n, "P_inf")
+        out = np.zeros(96, np.uint8)
+        self._check(self.lib.ecg_lincomb_partial(self._ctx, c, n, _ptr(k), _ptr(P_xy), _ptr(P_inf), _ptr(out)))
+        return out
+
+    def point_sum(self, curve, xyz):
+        c = CURVE_IDS[curve]
+        xyz = np.ascontiguousarray(xyz, dtype=np.uint8).reshape(-1)
+        m = xyz.size // 96
+        out_xy = np.zeros(64, np.uint8)
+        out_inf = np.zeros(1, np.uint8)
+        self._check(self.lib.ecg_point_sum(self._ctx, c, m, _ptr(xyz), _ptr(out_xy), _ptr(out_inf)))
+        return out_xy, int(out_inf[0])
+
+    def mul_by_generator_and_mul_add(self, curve, a, b, P_xy, P_inf=None):
+        c = CURVE_IDS[curve]
+        n = np.asarray(a).size // 32
+        a = _u8(a, 32 * n, "a")
+        b = _u8(b, 32 * n, "b")
+        P_xy = _u8(P_xy, 64 * n, "P_xy")
+        if P_inf is not None:
+            P_inf = _u8(P_inf, n, "P_inf")
+        out_xy = np.empty(64 * n, np.uint8)
+        out_inf = np.empty(n, np.uint8)
+        self._check(self.lib.ecg_mul_gen_add_batch(self._ctx, c, n, _ptr(a), _ptr(b), _ptr(P_xy), _ptr(P_inf), _ptr(out_xy), _ptr(out_inf)))
+        return out_xy.reshape(n, 64), out_inf
+
+    def batch_normalize(self, curve, xyz):
+        c = CURVE_IDS[curve]
+        xyz = np.ascontiguousarray(xyz, dtype=np.uint8).reshape(-1)
+        n = xyz.size // 96
+        out_xy = np.empty(64 * n, np.uint8)
+        out_inf = np.empty(n, np.uint8)
+        self._check(self.lib.ecg_batch_normalize(self._ctx, c, n, _ptr(xyz), _ptr(out_xy), _ptr(out_inf)))
+        return out_xy.reshape(n, 64), out_inf
+
+    def field_op(self, curve, op, a, b=None):
+        c = CURVE_IDS[curve]
+        n = np.asarray(a).size // 32
+        a = _u8(a, 32 * n, "a")
+        if b is not None:
+            b = _u8(b, 32 * n, "b")
+        out = np.empty(32 * n, np.uint8)
+        self._check(self.lib.ecg_field_op_batch(self._ctx, c, FOP[op] if isinstance(op, str) else op, n, _ptr(a), _ptr(b), _ptr(out)))
+        return out.reshape(n, 32)
+
+    # ---- raw-pointer API (device_ptrs=True): all arguments are integer CUDA device addresses ----
+    def mul_batch_ptr(self, curve, n, k, P_xy, P_inf, out_xy, out_inf):
+        self._check(self.lib.ecg_mul_batch(self._ctx, CURVE_IDS[curve], n, _ptr(k), _ptr(P_xy), _ptr(P_inf), _ptr(out_xy), _ptr(out_inf)))
+
+    def mul_gen_batch_ptr(self, curve, n, k, out_xy, out_inf):
+        self._check(self.lib.ecg_mul_gen_batch(self._ctx, CURVE_IDS[curve], n, _ptr(k), _ptr(out_xy), _ptr(out_inf)))
+
+    def lincomb_partial_ptr(self, curve, n, k, P_xy, P_inf, out_xyz):
+        self._check(self.lib.ecg_lincomb_partial(self._ctx, CURVE_IDS[curve], n, _ptr(k), _ptr(P_xy), _ptr(P_inf), _ptr(out_xyz)))
+
+    def microbench(self, which: int, iters: int = 2000):
+        ops = ctypes.c_double(0)
+        ms = ctypes.c_double(0)
+        self._check(self.lib.ecg_microbench(self._ctx, which, iters, ctypes.byref(ops), ctypes.byref(ms)))
+        return ops.value, ms.value

@@ -1,0 +1,137 @@
+/* ecgpu.h — C ABI of libecgpu.so: B200-native batched elliptic-curve scalar multiplication
+ * (secp256k1 / NIST P-256).
+ *
+ * The reference (RustCrypto/elliptic-curves @ 739304e) has NO FFI boundary; its seams are Rust traits.
+ * Each entry point below names the trait method(s) / function(s) it stands in for (paths relative to the
+ * reference checkout).  INTEGRATION.md shows the `extern "C"` block and the trait-shaped Rust wrappers a
+ * maintainer would add on the reference side.
+ *
+ * Conventions (mirroring the reference's: infallible arithmetic, fallible decoding):
+ *  - scalars   : 32-byte big-endian, must be < n      (Scalar::from_repr, k256/src/arithmetic/scalar.rs:310-316,
+ *                                                      p256/src/arithmetic/scalar.rs:306-312) else ECG_ESCALAR_RANGE
+ *  - points    : 64 bytes x||y, each 32-byte big-endian < p and on the curve
+ *                (AffinePoint::from_coordinates, k256/src/arithmetic/affine.rs:134-147) else ECG_ENOT_ON_CURVE;
+ *                identity = flag byte 1 (coordinates ignored on input, written as 64 zero bytes on output:
+ *                AffinePoint::IDENTITY, k256/src/arithmetic/affine.rs:53-57)
+ *  - field elts: 32-byte big-endian canonical (< p)   (FieldElement::to_bytes, k256/src/arithmetic/field.rs:110-112)
+ *  - caller owns every buffer; the library reads/writes them only during the call; no exceptions cross.
+ *  - a ctx is not safe for concurrent calls; distinct ctxs are independent.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry fails with ECG_ECUDA.
+ */
+#ifndef ECGPU_H
+#define ECGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ecg_ctx ecg_ctx;
+
+typedef enum {
+  ECG_OK = 0,
+  ECG_EINVAL = 1,        /* bad argument (null pointer, unknown curve/op, unsupported flag combination) */
+  ECG_ESCALAR_RANGE = 2, /* some scalar >= n */
+  ECG_ENOT_ON_CURVE = 3, /* some point coordinate >= p or point not on the curve */
+  ECG_ECUDA = 4,         /* CUDA runtime error (see ecg_last_error) */
+  ECG_ENCCL = 5,         /* reserved: collective error (the library itself issues no collectives) */
+  ECG_ENOMEM = 6
+} ecg_status;
+
+typedef enum { ECG_SECP256K1 = 0, ECG_NISTP256 = 1 } ecg_curve;
+
+typedef enum {
+  ECG_FOP_ADD = 0,
+  ECG_FOP_SUB = 1,
+  ECG_FOP_NEG = 2, /* b ignored */
+  ECG_FOP_MUL = 3,
+  ECG_FOP_SQR = 4, /* b ignored */
+  ECG_FOP_INV = 5  /* b ignored; inv(0) = 0 */
+} ecg_field_op;
+
+/* ctx flags */
+#define ECG_FLAG_DEVICE_PTRS 1u /* every data pointer is a device pointer on device_ids[0] (n_devices must be 1) */
+
+/* Create a context on the given CUDA devices (NULL/0 = device 0).  With several devices a host-pointer
+ * batch is split into contiguous index ranges, one per device; there is no
+ * inter-device traffic.  Replaces nothing in the reference (it has no runtime state except the lazily
+ * built generator table, primeorder/src/tables/basepoint.rs:29-31, which ctx creation uploads). */
+ecg_status ecg_ctx_create(const int* device_ids, int n_devices, unsigned flags, ecg_ctx** out);
+void ecg_ctx_destroy(ecg_ctx* ctx);
+const char* ecg_last_error(const ecg_ctx* ctx);
+/* index of the first offending element of the last failed call with ECG_ESCALAR_RANGE / ECG_ENOT_ON_CURVE */
+size_t ecg_last_error_index(const ecg_ctx* ctx);
+
+/* Run this ctx's work on a caller-provided cudaStream_t (e.g. PyTorch's current stream) instead of the
+ * ctx-owned stream; device 0 of the ctx only.  NULL restores the owned stream. */
+ecg_status ecg_ctx_set_stream(ecg_ctx* ctx, void* cuda_stream);
+
+/* out[i] = k[i] * P[i].
+ * Replaces `ProjectivePoint * Scalar` / `mul_vartime` for a batch of independent pairs:
+ *   k256/src/arithmetic/mul.rs:236-295 (Mul, MulVartime impls), primeorder/src/projective.rs:133-144, :847-858
+ * followed by to_affine (k256/src/arithmetic/projective.rs:64-75).
+ * k: n*32, P_xy: n*64, P_inf: n bytes or NULL (no identities), out_xy: n*64, out_inf: n bytes. */
+ecg_status ecg_mul_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
+                         const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
+
+/* out[i] = k[i] * G.
+ * Replaces ProjectivePoint::mul_by_generator[_vartime] (k256/src/arithmetic/mul.rs:180-232),
+ * BasepointTable::mul (primeorder/src/tables/basepoint.rs:82-125), MulBackend::mul_by_generator
+ * (primeorder/src/mul_backend.rs:11-29). */
+ecg_status ecg_mul_gen_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, uint8_t* out_xy,
+                             uint8_t* out_inf);
+
+/* out = sum_i k[i] * P[i]   (one point).
+ * Replaces LinearCombination::lincomb / lincomb_vartime (k256/src/arithmetic/mul.rs:66-175,
+ * primeorder/src/projective.rs:480-557). */
+ecg_status ecg_lincomb(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
+                       const uint8_t* P_inf, uint8_t out_xy[64], uint8_t* out_inf);
+
+/* Same sum, but the result is left un-normalised as X||Y||Z (3*32 bytes big-endian, Jacobian:
+ * x = X/Z^2, y = Y/Z^3, Z = 0 for the identity) so that partial sums from several ranks can be combined
+ * with ecg_point_sum after one small gather. */
+ecg_status ecg_lincomb_partial(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
+                               const uint8_t* P_inf, uint8_t out_xyz[96]);
+
+/* out = sum of m Jacobian points given as m*96 bytes (X||Y||Z), normalised to affine.  Always HOST
+ * pointers (m is the number of ranks). */
+ecg_status ecg_point_sum(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* xyz, uint8_t out_xy[64],
+                         uint8_t* out_inf);
+
+/* out[i] = a[i] * G + b[i] * P[i].
+ * Replaces MulByGeneratorVartime::mul_by_generator_and_mul_add_vartime (k256/src/arithmetic/mul.rs:303-310,
+ * primeorder/src/mul_backend.rs:31-40) — the ECDSA / BIP340 verification shape. */
+ecg_status ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, const uint8_t* b,
+                                 const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
+
+/* Projective (Jacobian X||Y||Z, n*96 bytes) -> affine, one shared inversion per thread-group
+ * (Montgomery's trick).  Replaces BatchNormalize::batch_normalize (k256/src/arithmetic/projective.rs:345-391,
+ * primeorder/src/projective.rs:435-478).  Coordinates must be < p. */
+ecg_status ecg_batch_normalize(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz, uint8_t* out_xy,
+                               uint8_t* out_inf);
+
+/* out[i] = a[i] op b[i] in F_p.
+ * Replaces FieldElement add/sub/neg/mul/square/invert: k256/src/arithmetic/field.rs:116-196 over
+ * field_5x52.rs:203-414; p256/src/arithmetic/field.rs:67-118 over field64.rs:7-144. */
+ecg_status ecg_field_op_batch(ecg_ctx* ctx, ecg_curve curve, int op, size_t n, const uint8_t* a,
+                              const uint8_t* b, uint8_t* out);
+
+/* ---- measurement helpers (not part of the reference-facing surface) ---- */
+
+/* Integer-pipe microbenchmark on device 0 of the ctx: which = 0 IMAD.WIDE.U32.X carry chains (the
+ * field-multiplier's instruction), 1 = IMAD (32-bit lo), 2 = IADD3 carry chains, 3 = fused field-mul
+ * throughput (secp256k1), 4 = same for P-256.  Returns operations per second (thread-level instructions
+ * of the named kind, or field multiplications for 3/4). */
+ecg_status ecg_microbench(ecg_ctx* ctx, int which, int iters, double* ops_per_s, double* elapsed_ms);
+
+/* number of CUDA kernels this ctx has launched since creation */
+uint64_t ecg_kernel_launches(const ecg_ctx* ctx);
+
+const char* ecg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECGPU_H */
