@@ -1,0 +1,119 @@
+"""ctypes loader for oracle/libecref.so (the C restatement of the reference's CPU path).
+TEST INFRASTRUCTURE ONLY — see the header of ecref.c."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(_HERE, "libecref.so")
+_lib = None
+
+
+def build(force=False):
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(os.path.join(_HERE, "ecref.c")):
+        # -march=native binaries must be rebuilt on the machine that runs them
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libecref.so"], stdout=subprocess.DEVNULL)
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        try:
+            _lib = ctypes.CDLL(LIB)
+            _lib.ecref_init()
+        except OSError:
+            build(force=True)
+            _lib = ctypes.CDLL(LIB)
+            _lib.ecref_init()
+        vp, sz = ctypes.c_void_p, ctypes.c_size_t
+        _lib.ecref_mul_batch.argtypes = [ctypes.c_int, sz, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int]
+        _lib.ecref_mul_gen_batch.argtypes = [ctypes.c_int, sz, vp, vp, vp, ctypes.c_int]
+        _lib.ecref_lincomb.argtypes = [ctypes.c_int, sz, vp, vp, vp, vp, vp, ctypes.c_int]
+        _lib.ecref_field_op.argtypes = [ctypes.c_int, ctypes.c_int, sz, vp, vp, vp]
+        _lib.ecref_radix16.argtypes = [vp, ctypes.c_int, vp]
+        _lib.ecref_wnaf.argtypes = [vp, sz, sz, ctypes.c_int, vp]
+        _lib.ecref_wnaf.restype = ctypes.c_int
+        _lib.ecref_glv.argtypes = [vp, vp, vp]
+    return _lib
+
+
+def _p(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else ctypes.c_void_p(0)
+
+
+CURVE = {"k256": 0, "p256": 1, 0: 0, 1: 1}
+
+
+def mul_batch(curve, k, pxy, pinf=None, nthreads=1, variant=0):
+    k = np.ascontiguousarray(k, np.uint8).reshape(-1)
+    n = k.size // 32
+    pxy = np.ascontiguousarray(pxy, np.uint8).reshape(-1)
+    if pinf is not None:
+        pinf = np.ascontiguousarray(pinf, np.uint8).reshape(-1)
+    oxy = np.zeros(64 * n, np.uint8)
+    oinf = np.zeros(n, np.uint8)
+    rc = lib().ecref_mul_batch(CURVE[curve], n, _p(k), _p(pxy), _p(pinf), _p(oxy), _p(oinf), nthreads, variant)
+    if rc:
+        raise ValueError(f"ecref_mul_batch rc={rc}")
+    return oxy.reshape(n, 64), oinf
+
+
+def mul_gen_batch(curve, k, nthreads=1):
+    k = np.ascontiguousarray(k, np.uint8).reshape(-1)
+    n = k.size // 32
+    oxy = np.zeros(64 * n, np.uint8)
+    oinf = np.zeros(n, np.uint8)
+    rc = lib().ecref_mul_gen_batch(CURVE[curve], n, _p(k), _p(oxy), _p(oinf), nthreads)
+    if rc:
+        raise ValueError(f"ecref_mul_gen_batch rc={rc}")
+    return oxy.reshape(n, 64), oinf
+
+
+def lincomb(curve, k, pxy, pinf=None, nthreads=1):
+    k = np.ascontiguousarray(k, np.uint8).reshape(-1)
+    n = k.size // 32
+    pxy = np.ascontiguousarray(pxy, np.uint8).reshape(-1)
+    if pinf is not None:
+        pinf = np.ascontiguousarray(pinf, np.uint8).reshape(-1)
+    oxy = np.zeros(64, np.uint8)
+    oinf = np.zeros(1, np.uint8)
+    rc = lib().ecref_lincomb(CURVE[curve], n, _p(k), _p(pxy), _p(pinf), _p(oxy), _p(oinf), nthreads)
+    if rc:
+        raise ValueError(f"ecref_lincomb rc={rc}")
+    return oxy, int(oinf[0])
+
+
+def field_op(curve, op, a, b=None):
+    a = np.ascontiguousarray(a, np.uint8).reshape(-1)
+    n = a.size // 32
+    if b is not None:
+        b = np.ascontiguousarray(b, np.uint8).reshape(-1)
+    out = np.zeros(32 * n, np.uint8)
+    lib().ecref_field_op(CURVE[curve], op, n, _p(a), _p(b), _p(out))
+    return out.reshape(n, 32)
+
+
+def radix16(k_be: bytes, nd: int):
+    kb = np.frombuffer(k_be, np.uint8).copy()
+    out = np.zeros(nd, np.int8)
+    lib().ecref_radix16(_p(kb), nd, _p(out))
+    return out
+
+
+def wnaf(le: bytes, bit_len: int, window: int):
+    b = np.frombuffer(le, np.uint8).copy()
+    out = np.zeros(bit_len + 8, np.int8)
+    n = lib().ecref_wnaf(_p(b), len(le), bit_len, window, _p(out))
+    return out[:n]
+
+
+def glv(k: int):
+    kb = np.frombuffer(k.to_bytes(32, "big"), np.uint8).copy()
+    r1 = np.zeros(32, np.uint8)
+    r2 = np.zeros(32, np.uint8)
+    lib().ecref_glv(_p(kb), _p(r1), _p(r2))
+    return int.from_bytes(r1.tobytes(), "big"), int.from_bytes(r2.tobytes(), "big")
