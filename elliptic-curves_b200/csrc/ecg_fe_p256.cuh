@@ -1,0 +1,225 @@
+// ecg_fe_p256.cuh — F_p for NIST P-256, p = 2^256 - 2^224 + 2^192 + 2^96 - 1, on 8 saturated 32-bit limbs.
+//
+// Replaces (same values, different representation) the reference's Montgomery-form field
+//   p256/src/arithmetic/field.rs:59-118 over p256/src/arithmetic/field/field64.rs:7-144 (add, sub,
+//   montgomery_reduce) and primefield/src/monty.rs:319-375.
+// Representation: plain integers (no Montgomery domain — there is no per-multiplication conversion to
+// pay for on a machine where the reduction is shifts and adds anyway), weakly reduced to [0, 2^256).
+// Reduction is the Solinas / FIPS 186-4 D.2.3 word recombination on 32-bit words followed by folding the
+// small signed overflow with 2^256 == K (mod p), K = 2^224 - 2^192 - 2^96 + 1.  No multiplier is used by
+// the reduction: the whole of it runs on the ALU pipe, concurrently with the next product's IMAD.WIDEs.
+#pragma once
+#include "ecg_prim.cuh"
+
+namespace ecg {
+
+struct FpP256 {
+  ECG_D static void set_zero(Fe& r) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = 0;
+  }
+  ECG_D static void set_one(Fe& r) {
+    set_zero(r);
+    r.v[0] = 1;
+  }
+
+  // r += c*K for c in {0,1}; returns the carry out of bit 256.  K = {1,0,0,~0,~0,~0,~0-1,0}
+  ECG_D static uint32_t add_K(uint32_t* r, uint32_t c) {
+    uint32_t m = 0u - c;
+    r[0] = add_cc(r[0], c);
+    r[1] = addc_cc(r[1], 0);
+    r[2] = addc_cc(r[2], 0);
+    r[3] = addc_cc(r[3], m);
+    r[4] = addc_cc(r[4], m);
+    r[5] = addc_cc(r[5], m);
+    r[6] = addc_cc(r[6], m & 0xFFFFFFFEu);
+    r[7] = addc_cc(r[7], 0);
+    return addc(0, 0);
+  }
+  // r -= c*K; returns the borrow
+  ECG_D static uint32_t sub_K(uint32_t* r, uint32_t c) {
+    uint32_t m = 0u - c;
+    r[0] = sub_cc(r[0], c);
+    r[1] = subc_cc(r[1], 0);
+    r[2] = subc_cc(r[2], 0);
+    r[3] = subc_cc(r[3], m);
+    r[4] = subc_cc(r[4], m);
+    r[5] = subc_cc(r[5], m);
+    r[6] = subc_cc(r[6], m & 0xFFFFFFFEu);
+    r[7] = subc_cc(r[7], 0);
+    return 0u - subc(0, 0);
+  }
+
+  // r (8 limbs) += o*K for a small signed o; signed carry propagation; returns the new signed overflow.
+  ECG_D static int32_t fold_signed(uint32_t* r, int32_t o) {
+    int64_t t = (int64_t)r[0] + o;
+    r[0] = (uint32_t)t;
+    t >>= 32;
+    t += r[1];
+    r[1] = (uint32_t)t;
+    t >>= 32;
+    t += r[2];
+    r[2] = (uint32_t)t;
+    t >>= 32;
+    t += (int64_t)r[3] - o;
+    r[3] = (uint32_t)t;
+    t >>= 32;
+    t += r[4];
+    r[4] = (uint32_t)t;
+    t >>= 32;
+    t += r[5];
+    r[5] = (uint32_t)t;
+    t >>= 32;
+    t += (int64_t)r[6] - o;
+    r[6] = (uint32_t)t;
+    t >>= 32;
+    t += (int64_t)r[7] + o;
+    r[7] = (uint32_t)t;
+    t >>= 32;
+    return (int32_t)t;
+  }
+
+  // 16-limb c -> r = c mod p (weakly reduced).  FIPS 186-4 D.2.3: s1 + 2 s2 + 2 s3 + s4 + s5 - s6 - s7 - s8 - s9,
+  // written per output word; every partial sum fits comfortably in a signed 64-bit accumulator.
+  ECG_D static void reduce16(Fe& r, const uint32_t* c) {
+    int64_t t;
+    uint32_t o[8];
+    t = (int64_t)c[0] + c[8] + c[9] - c[11] - c[12] - c[13] - c[14];
+    o[0] = (uint32_t)t;
+    t >>= 32;
+    t += (int64_t)c[1] + c[9] + c[10] - c[12] - c[13] - c[14] - c[15];
+    o[1] = (uint32_t)t;
+    t >>= 32;
+    t += (int64_t)c[2] + c[10] + c[11] - c[13] - c[14] - c[15];
+    o[2] = (uint32_t)t;
+    t >>= 32;
+    t += (int64_t)c[3] + 2 * ((int64_t)c[11] + c[12]) + c[13] - c[15] - c[8] - c[9];
+    o[3] = (uint32_t)t;
+    t >>= 32;
+    t += (int64_t)c[4] + 2 * ((int64_t)c[12] + c[13]) + c[14] - c[9] - c[10];
+    o[4] = (uint32_t)t;
+    t >>= 32;
+    t += (int64_t)c[5] + 2 * ((int64_t)c[13] + c[14]) + c[15] - c[10] - c[11];
+    o[5] = (uint32_t)t;
+    t >>= 32;
+    t += (int64_t)c[6] + 3 * (int64_t)c[14] + 2 * (int64_t)c[15] + c[13] - c[8] - c[9];
+    o[6] = (uint32_t)t;
+    t >>= 32;
+    t += (int64_t)c[7] + 3 * (int64_t)c[15] + c[8] - c[10] - c[11] - c[12] - c[13];
+    o[7] = (uint32_t)t;
+    t >>= 32;
+    int32_t ov = (int32_t)t;            // |ov| <= 6
+    ov = fold_signed(o, ov);             // now ov in {-1,0,1}
+    ov = fold_signed(o, ov);             // now 0
+    (void)ov;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = o[i];
+  }
+
+  ECG_D static void mul(Fe& r, const Fe& a, const Fe& b) {
+    uint32_t t[16];
+    mul8x8(t, a.v, b.v);
+    reduce16(r, t);
+  }
+  ECG_D static void sqr(Fe& r, const Fe& a) {
+    uint32_t t[16];
+    mul8x8(t, a.v, a.v);
+    reduce16(r, t);
+  }
+  ECG_D static void add(Fe& r, const Fe& a, const Fe& b) {
+    uint32_t c = add8(r.v, a.v, b.v);
+    uint32_t c2 = add_K(r.v, c);   // 2^256 == K
+    (void)add_K(r.v, c2);          // second wrap only if the first left less than K below 2^256
+  }
+  ECG_D static void sub(Fe& r, const Fe& a, const Fe& b) {
+    uint32_t bw = sub8(r.v, a.v, b.v);
+    uint32_t bw2 = sub_K(r.v, bw);
+    (void)sub_K(r.v, bw2);
+  }
+  ECG_D static void neg(Fe& r, const Fe& a) {
+    Fe z;
+    set_zero(z);
+    sub(r, z, a);
+  }
+  ECG_D static void mul_small(Fe& r, const Fe& a, uint32_t k) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      uint64_t t = (uint64_t)a.v[i] * k + c;
+      r.v[i] = (uint32_t)t;
+      c = (uint32_t)(t >> 32);
+    }
+    int32_t ov = fold_signed(r.v, (int32_t)c);
+    ov = fold_signed(r.v, ov);
+    (void)ov;
+  }
+  // r = a/2 mod p;  p limbs = {~0, ~0, ~0, 0, 0, 0, 1, ~0}
+  ECG_D static void half(Fe& r, const Fe& a) {
+    uint32_t m = 0u - (a.v[0] & 1u);
+    uint32_t t[8];
+    t[0] = add_cc(a.v[0], m);
+    t[1] = addc_cc(a.v[1], m);
+    t[2] = addc_cc(a.v[2], m);
+    t[3] = addc_cc(a.v[3], 0);
+    t[4] = addc_cc(a.v[4], 0);
+    t[5] = addc_cc(a.v[5], 0);
+    t[6] = addc_cc(a.v[6], m & 1u);
+    t[7] = addc_cc(a.v[7], m);
+    uint32_t c = addc(0, 0);
+#pragma unroll
+    for (int i = 0; i < 7; i++) r.v[i] = funnel_r(t[i], t[i + 1], 1);
+    r.v[7] = funnel_r(t[7], c, 1);
+  }
+  // canonical representative: a >= p  <=>  a + (2^256 - p) carries;  2^256 - p = K
+  ECG_D static void normalize(Fe& r, const Fe& a) {
+    uint32_t t[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) t[i] = a.v[i];
+    uint32_t ge = add_K(t, 1u);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = ge ? t[i] : a.v[i];
+  }
+  ECG_D static bool is_zero(const Fe& a) {
+    uint32_t o = a.v[0] | a.v[1] | a.v[2] | a.v[3] | a.v[4] | a.v[5] | a.v[6] | a.v[7];
+    uint32_t n = ~(a.v[0] & a.v[1] & a.v[2] & a.v[7]) | a.v[3] | a.v[4] | a.v[5] | (a.v[6] ^ 1u);
+    return (o == 0) | (n == 0);
+  }
+  ECG_D static void sqr_n(Fe& r, const Fe& a, int n) {
+    r = a;
+#pragma unroll 1
+    for (int i = 0; i < n; i++) sqr(r, r);
+  }
+  // a^(p-2): p-2 = [32 ones][31 zeros][1][96 zeros][94 ones][0][1]; 255 S + 13 M.  0 -> 0.
+  // (reference: FieldElement::invert -> crypto-bigint, p256/src/arithmetic/field.rs:111-118)
+  ECG_D static void inv(Fe& r, const Fe& a) {
+    Fe x2, x3, x6, x12, x15, x30, x32, t;
+    sqr(x2, a);
+    mul(x2, x2, a);
+    sqr(x3, x2);
+    mul(x3, x3, a);
+    sqr_n(x6, x3, 3);
+    mul(x6, x6, x3);
+    sqr_n(x12, x6, 6);
+    mul(x12, x12, x6);
+    sqr_n(x15, x12, 3);
+    mul(x15, x15, x3);
+    sqr_n(x30, x15, 15);
+    mul(x30, x30, x15);
+    sqr_n(x32, x30, 2);
+    mul(x32, x32, x2);
+    sqr_n(t, x32, 32);
+    mul(t, t, a);
+    sqr_n(t, t, 128);
+    mul(t, t, x32);
+    sqr_n(t, t, 32);
+    mul(t, t, x32);
+    sqr_n(t, t, 30);
+    mul(t, t, x30);
+    sqr_n(t, t, 2);
+    mul(r, t, a);
+  }
+  ECG_D static void from_canonical(Fe& r, const Fe& a) { r = a; }
+  ECG_D static void to_canonical(Fe& r, const Fe& a) { normalize(r, a); }
+};
+
+}  // namespace ecg

@@ -36,6 +36,27 @@ struct TabRef {
     }
   }
 };
+// Same, for Jacobian entries (24 words: X, Y, Z).
+struct TabRefJ {
+  uint32_t* base;
+  uint32_t stride;
+  ECG_D void store(int e, const Jac& p) const {
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      base[(e * 24 + w) * stride] = p.X.v[w];
+      base[(e * 24 + 8 + w) * stride] = p.Y.v[w];
+      base[(e * 24 + 16 + w) * stride] = p.Z.v[w];
+    }
+  }
+  ECG_D void load(int e, Jac& p) const {
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      p.X.v[w] = base[(e * 24 + w) * stride];
+      p.Y.v[w] = base[(e * 24 + 8 + w) * stride];
+      p.Z.v[w] = base[(e * 24 + 16 + w) * stride];
+    }
+  }
+};
 
 ECG_D void k256_beta(Fe& b) {
   // ENDOMORPHISM_BETA, k256/src/arithmetic/projective.rs:32-37
@@ -139,6 +160,51 @@ ECG_D void k256_mul_thread(Jac& r, const uint32_t* k, const Aff& P, const TabRef
   r.X = acc.X;
   r.Y = acc.Y;
   F::mul(r.Z, acc.Z, Zg);
+}
+
+// Generic prime-order curve without endomorphism (NIST P-256): r = k*P (Jacobian).
+// k: 8 LE limbs, k < n.  P: affine, on curve, not identity.  Signed-odd radix-16 recoding of the full
+// 256-bit scalar: implicit top digit +1, then 64 windows of (4 dbl + 1 add) against a table of the eight
+// odd multiples kept in Jacobian form (the shared-denominator trick of build_table_iso_a0 needs a = 0).
+// Replaces primeorder ProjectivePoint::mul / mul_vartime (primeorder/src/projective.rs:133-144, :532-557).
+template <class F, bool A_IS_MINUS3>
+ECG_D void generic_mul_thread(Jac& r, const uint32_t* k, const Aff& P, const TabRefJ& tab) {
+  FullRecode rc;
+  recode_full(rc, k);
+  Jac d, cur, acc;
+  aff_dbl<F, A_IS_MINUS3>(d, P);
+  cur.X = P.x;
+  cur.Y = P.y;
+  F::set_one(cur.Z);
+  acc = cur;  // top digit (+1) * P
+  tab.store(0, cur);
+  jac_madd<F, A_IS_MINUS3>(cur, d, P);  // 3P
+  tab.store(1, cur);
+#pragma unroll 1
+  for (int i = 2; i < 8; i++) {
+    jac_add<F, A_IS_MINUS3>(cur, cur, d);
+    tab.store(i, cur);
+  }
+#pragma unroll 1
+  for (int i = 0; i < 64; i++) {
+#pragma unroll 1
+    for (int j = 0; j < 4; j++) jac_dbl<F, A_IS_MINUS3>(acc, acc);
+    uint32_t n = next_window8(rc.h);
+    uint32_t pos = n >> 3;
+    uint32_t idx = pos ? (n & 7u) : (7u - n);
+    Jac e;
+    tab.load((int)idx, e);
+    fe_cneg<F>(e.Y, pos ^ 1u);
+    jac_add<F, A_IS_MINUS3>(acc, acc, e);
+  }
+  // parity correction: the loop computed (k+1)*P when k was even
+  Aff np;
+  np.x = P.x;
+  F::neg(np.y, P.y);
+  Jac t;
+  jac_madd<F, A_IS_MINUS3>(t, acc, np);
+  jac_csel(acc, t, rc.even);
+  r = acc;
 }
 
 }  // namespace ecg

@@ -97,6 +97,207 @@ __global__ void __launch_bounds__(BLOCK, MINBLK)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Generic prime-order curve (P-256) variable-base: Jacobian window table in shared memory (768 B / thread).
+template <class C, int BLOCK, int MINBLK>
+__global__ void __launch_bounds__(BLOCK, MINBLK)
+    generic_varbase_kernel(const uint8_t* __restrict__ kb, const uint8_t* __restrict__ pxy,
+                           const uint8_t* __restrict__ pinf, size_t n, uint32_t* __restrict__ jac,
+                           uint32_t* __restrict__ status) {
+  typedef typename C::F F;
+  extern __shared__ uint32_t smem[];
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n) return;
+  uint32_t k[8];
+  Aff P;
+  bool inf;
+  uint32_t err = load_pair<C>(k, P, inf, kb, pxy, pinf, idx);
+  if (err) report_error(status, err, idx);
+  TabRefJ tab{smem + threadIdx.x, (uint32_t)BLOCK};
+  Jac r;
+  generic_mul_thread<F, C::A_IS_MINUS3>(r, k, P, tab);
+  if (inf || err) F::set_zero(r.Z);
+  soa_store<8>(jac, n, idx, r.X.v, 0);
+  soa_store<8>(jac, n, idx, r.Y.v, 8);
+  soa_store<8>(jac, n, idx, r.Z.v, 16);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fixed-base k*G from a device-resident table of affine odd multiples.
+//   table layout: window i (0..FB_WINDOWS-1), entry j (0..2^(FB_W-1)-1) = (2j+1) * 2^(FB_W*i) * G, 16 words
+//   (x[8], y[8], internal form); one extra entry at the end = 2^256 * G (the recoding's implicit top digit).
+// Replaces BasepointTable (primeorder/src/tables/basepoint.rs:41-125; k256/src/arithmetic/tables.rs:12-22):
+// same idea (precomputed multiples of G, only additions at run time), sized for a 126 MB L2 instead of a
+// 30 KiB L1: 16 sixteen-bit windows -> 17 mixed additions and no doubling per scalar.
+#define FB_W 16
+#define FB_WINDOWS 16
+#define FB_ENTRIES (1u << (FB_W - 1))
+#define FB_TABLE_POINTS ((size_t)FB_WINDOWS * FB_ENTRIES + 1)
+
+__device__ __forceinline__ void fb_load_entry(Aff& e, const uint32_t* __restrict__ table, size_t point) {
+  const uint4* p = reinterpret_cast<const uint4*>(table + point * 16);
+  uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+  e.x.v[0] = a.x; e.x.v[1] = a.y; e.x.v[2] = a.z; e.x.v[3] = a.w;
+  e.x.v[4] = b.x; e.x.v[5] = b.y; e.x.v[6] = b.z; e.x.v[7] = b.w;
+  e.y.v[0] = c.x; e.y.v[1] = c.y; e.y.v[2] = c.z; e.y.v[3] = c.w;
+  e.y.v[4] = d.x; e.y.v[5] = d.y; e.y.v[6] = d.z; e.y.v[7] = d.w;
+}
+
+// acc += k*G (acc Jacobian on the true curve; pass Z = 0 to start from the identity)
+template <class C, bool FROM_IDENTITY>
+__device__ __forceinline__ void fixedbase_accumulate(Jac& acc, const uint32_t* k, const uint32_t* __restrict__ table) {
+  typedef typename C::F F;
+  FullRecode rc;
+  recode_full(rc, k);
+  Aff e;
+  fb_load_entry(e, table, (size_t)FB_WINDOWS * FB_ENTRIES);  // 2^256 * G
+  if (FROM_IDENTITY) {
+    acc.X = e.x;
+    acc.Y = e.y;
+    F::set_one(acc.Z);
+  } else {
+    jac_madd<F, C::A_IS_MINUS3>(acc, acc, e);
+  }
+#pragma unroll 1
+  for (int i = 0; i < FB_WINDOWS; i++) {
+    uint32_t w = rc.h[0] & 0xFFFFu;
+#pragma unroll
+    for (int j = 0; j < 7; j++) rc.h[j] = funnel_r(rc.h[j], rc.h[j + 1], 16);
+    rc.h[7] >>= 16;
+    uint32_t pos = w >> (FB_W - 1);
+    uint32_t idx = pos ? (w & (FB_ENTRIES - 1)) : (FB_ENTRIES - 1 - w);
+    fb_load_entry(e, table, (size_t)i * FB_ENTRIES + idx);
+    fe_cneg<F>(e.y, pos ^ 1u);
+    jac_madd<F, C::A_IS_MINUS3>(acc, acc, e);
+  }
+  // parity correction: subtract G if k was even
+  fb_load_entry(e, table, 0);
+  F::neg(e.y, e.y);
+  Jac t;
+  jac_madd<F, C::A_IS_MINUS3>(t, acc, e);
+  jac_csel(acc, t, rc.even);
+}
+
+template <class C>
+__global__ void __launch_bounds__(128, 4)
+    fixedbase_kernel(const uint8_t* __restrict__ kb, size_t n, const uint32_t* __restrict__ table,
+                     uint32_t* __restrict__ jac, uint32_t* __restrict__ status) {
+  typedef typename C::F F;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  uint32_t k[8];
+  load_be32(k, kb + 32 * idx);
+  bool bad = !lt8(k, C::N());
+  if (bad) {
+    report_error(status, ERRF_SCALAR, idx);
+#pragma unroll
+    for (int i = 0; i < 8; i++) k[i] = (i == 0);
+  }
+  Jac acc;
+  fixedbase_accumulate<C, true>(acc, k, table);
+  if (bad) F::set_zero(acc.Z);
+  soa_store<8>(jac, n, idx, acc.X.v, 0);
+  soa_store<8>(jac, n, idx, acc.Y.v, 8);
+  soa_store<8>(jac, n, idx, acc.Z.v, 16);
+}
+
+// a*G + b*P : variable-base thread routine, then the fixed-base accumulation on the same accumulator.
+// Replaces mul_by_generator_and_mul_add_vartime (k256/src/arithmetic/mul.rs:303-310, primeorder/src/mul_backend.rs:31-40).
+template <class C, int BLOCK, int MINBLK, bool IS_K256>
+__global__ void __launch_bounds__(BLOCK, MINBLK)
+    mul_gen_add_kernel(const uint8_t* __restrict__ ab, const uint8_t* __restrict__ kb,
+                       const uint8_t* __restrict__ pxy, const uint8_t* __restrict__ pinf, size_t n,
+                       const uint32_t* __restrict__ table, uint32_t* __restrict__ jac, uint32_t* __restrict__ status) {
+  typedef typename C::F F;
+  extern __shared__ uint32_t smem[];
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n) return;
+  uint32_t k[8], a[8];
+  Aff P;
+  bool inf;
+  uint32_t err = load_pair<C>(k, P, inf, kb, pxy, pinf, idx);
+  load_be32(a, ab + 32 * idx);
+  if (!lt8(a, C::N())) err |= ERRF_SCALAR;
+  if (err) report_error(status, err, idx);
+  Jac r;
+  if (IS_K256) {
+    TabRef tab{smem + threadIdx.x, (uint32_t)BLOCK};
+    k256_mul_thread(r, k, P, tab);
+  } else {
+    TabRefJ tab{smem + threadIdx.x, (uint32_t)BLOCK};
+    generic_mul_thread<F, C::A_IS_MINUS3>(r, k, P, tab);
+  }
+  if (inf) F::set_zero(r.Z);  // b * O = O, the sum is a*G
+  if (err) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = (i == 0);
+  }
+  fixedbase_accumulate<C, false>(r, a, table);
+  if (err) F::set_zero(r.Z);
+  soa_store<8>(jac, n, idx, r.X.v, 0);
+  soa_store<8>(jac, n, idx, r.Y.v, 8);
+  soa_store<8>(jac, n, idx, r.Z.v, 16);
+}
+
+// canonical affine big-endian bytes (n*64) -> table words (internal form); used once, when a table is built
+template <class C>
+__global__ void __launch_bounds__(256)
+    affine_to_table_kernel(const uint8_t* __restrict__ xy, size_t n, uint32_t* __restrict__ table) {
+  typedef typename C::F F;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  Fe x, y;
+  load_be32(x.v, xy + 64 * idx);
+  load_be32(y.v, xy + 64 * idx + 32);
+  F::from_canonical(x, x);
+  F::from_canonical(y, y);
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    table[idx * 16 + w] = x.v[w];
+    table[idx * 16 + 8 + w] = y.v[w];
+  }
+}
+
+// Sum of Jacobian points: thread t adds elements t, t+T, t+2T, ... of `in` (SoA, n_in) and writes partial t of
+// `out` (SoA, n_out = T).  Applied repeatedly until one point is left (lincomb's final reduction).
+template <class C>
+__global__ void __launch_bounds__(128)
+    jac_sum_kernel(const uint32_t* __restrict__ in, size_t n_in, uint32_t* __restrict__ out, size_t n_out) {
+  typedef typename C::F F;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_out) return;
+  Jac acc;
+  F::set_zero(acc.X);
+  F::set_one(acc.Y);
+  F::set_zero(acc.Z);
+  for (size_t idx = t; idx < n_in; idx += n_out) {
+    Jac p;
+    soa_load<8>(p.X.v, in, n_in, idx, 0);
+    soa_load<8>(p.Y.v, in, n_in, idx, 8);
+    soa_load<8>(p.Z.v, in, n_in, idx, 16);
+    jac_add<F, C::A_IS_MINUS3>(acc, acc, p);
+  }
+  soa_store<8>(out, n_out, t, acc.X.v, 0);
+  soa_store<8>(out, n_out, t, acc.Y.v, 8);
+  soa_store<8>(out, n_out, t, acc.Z.v, 16);
+}
+
+// SoA internal Jacobian -> AoS canonical big-endian X||Y||Z (96 bytes per point)
+template <class C>
+__global__ void __launch_bounds__(128)
+    export_jac_kernel(const uint32_t* __restrict__ jac, size_t n, uint8_t* __restrict__ xyz) {
+  typedef typename C::F F;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+#pragma unroll 1
+  for (int c = 0; c < 3; c++) {
+    Fe v;
+    soa_load<8>(v.v, jac, n, idx, 8 * c);
+    F::to_canonical(v, v);
+    store_be32(xyz + 96 * idx + 32 * c, v.v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Jacobian (SoA) -> canonical affine bytes with Montgomery's trick along each thread's strided slice:
 // thread t owns elements t, t+T, t+2T, ... ; one field inversion per thread, 7 field multiplications per
 // element.  Replaces batch_normalize / BatchInvert (k256/src/arithmetic/projective.rs:367-391,
@@ -286,18 +487,19 @@ __global__ void __launch_bounds__(256) mb_fmul_kernel(uint32_t* out, int iters, 
 // host side
 struct DevState {
   int dev = 0;
-  cudaStream_t stream = nullptr;      // owned
-  cudaStream_t user_stream = nullptr; // optional override
+  cudaStream_t stream = nullptr;       // owned
+  cudaStream_t user_stream = nullptr;  // optional override (ecg_ctx_set_stream)
   bool use_user_stream = false;
   // grow-only device buffers
-  void* buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  uint32_t* status = nullptr;  // 2 words
+  void* buf[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t cap[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t* status = nullptr;    // 2 words
   uint32_t* h_status = nullptr;  // pinned
+  uint32_t* fb_table[2] = {nullptr, nullptr};  // per curve, built lazily (like the reference's LazyLock table)
   int sm_count = 148;
   cudaStream_t s() const { return use_user_stream ? user_stream : stream; }
 };
-enum { B_K = 0, B_P = 1, B_INF = 2, B_JAC = 3, B_SCR = 4, B_OUT = 5, B_OINF = 6, B_AUX = 7 };
+enum { B_K = 0, B_P = 1, B_INF = 2, B_JAC = 3, B_SCR = 4, B_OUT = 5, B_OINF = 6, B_AUX = 7, B_A = 8, B_JAC2 = 9 };
 
 struct ecg_ctx {
   std::vector<DevState> devs;
@@ -307,20 +509,28 @@ struct ecg_ctx {
   uint64_t launches = 0;
 };
 
-#define CU_TRY(ctx, call)                                                                   \
-  do {                                                                                      \
-    cudaError_t e_ = (call);                                                                \
-    if (e_ != cudaSuccess) {                                                                \
-      char m_[512];                                                                         \
-      snprintf(m_, sizeof m_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-      (ctx)->err = m_;                                                                      \
-      return e_ == cudaErrorMemoryAllocation ? ECG_ENOMEM : ECG_ECUDA;                      \
-    }                                                                                       \
+#define CU_TRY(ctx, call)                                                                                    \
+  do {                                                                                                       \
+    cudaError_t e_ = (call);                                                                                 \
+    if (e_ != cudaSuccess) {                                                                                 \
+      char m_[512];                                                                                          \
+      snprintf(m_, sizeof m_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);  \
+      (ctx)->err = m_;                                                                                       \
+      return e_ == cudaErrorMemoryAllocation ? ECG_ENOMEM : ECG_ECUDA;                                       \
+    }                                                                                                        \
+  } while (0)
+#define ST_TRY(expr)                     \
+  do {                                   \
+    ecg_status st_ = (expr);             \
+    if (st_ != ECG_OK) return st_;       \
   } while (0)
 
 static ecg_status ensure(ecg_ctx* ctx, DevState& d, int which, size_t bytes) {
   if (bytes <= d.cap[which]) return ECG_OK;
-  if (d.buf[which]) CU_TRY(ctx, cudaFree(d.buf[which]));
+  if (d.buf[which]) {
+    CU_TRY(ctx, cudaStreamSynchronize(d.s()));
+    CU_TRY(ctx, cudaFree(d.buf[which]));
+  }
   d.buf[which] = nullptr;
   d.cap[which] = 0;
   size_t want = bytes + bytes / 8 + 256;
@@ -329,7 +539,7 @@ static ecg_status ensure(ecg_ctx* ctx, DevState& d, int which, size_t bytes) {
   return ECG_OK;
 }
 
-extern "C" const char* ecg_version(void) { return "ecgpu 0.1 (sm_100a)"; }
+extern "C" const char* ecg_version(void) { return "ecgpu 0.2 (sm_100a)"; }
 
 extern "C" ecg_status ecg_ctx_create(const int* device_ids, int n_devices, unsigned flags, ecg_ctx** out) {
   if (!out) return ECG_EINVAL;
@@ -370,8 +580,10 @@ extern "C" void ecg_ctx_destroy(ecg_ctx* ctx) {
       cudaStreamSynchronize(d.stream);
       cudaStreamDestroy(d.stream);
     }
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < 10; i++)
       if (d.buf[i]) cudaFree(d.buf[i]);
+    for (int i = 0; i < 2; i++)
+      if (d.fb_table[i]) cudaFree(d.fb_table[i]);
     if (d.status) cudaFree(d.status);
     if (d.h_status) cudaFreeHost(d.h_status);
   }
@@ -405,55 +617,40 @@ static std::vector<Shard> make_shards(size_t n, size_t ndev) {
   return v;
 }
 
+// device-side views of one shard's operands
 struct DevPtrs {
   const uint8_t *k = nullptr, *p = nullptr, *inf = nullptr, *a = nullptr;
   uint8_t *out = nullptr, *oinf = nullptr;
 };
 
-// Stage inputs (host mode: async H2D into ctx buffers; device mode: use the caller's pointers).
-static ecg_status stage_in(ecg_ctx* ctx, DevState& d, const Shard& sh, const uint8_t* k, size_t kstride,
-                           const uint8_t* p, size_t pstride, const uint8_t* inf, DevPtrs& dp) {
-  bool devptr = ctx->flags & ECG_FLAG_DEVICE_PTRS;
-  if (devptr) {
-    dp.k = k ? k + sh.off * kstride : nullptr;
-    dp.p = p ? p + sh.off * pstride : nullptr;
-    dp.inf = inf ? inf + sh.off : nullptr;
+static ecg_status stage_one(ecg_ctx* ctx, DevState& d, int slot, const uint8_t* src, size_t off, size_t cnt,
+                            size_t stride, const uint8_t** dst) {
+  if (!src) {
+    *dst = nullptr;
     return ECG_OK;
   }
-  ecg_status st;
-  if (k) {
-    if ((st = ensure(ctx, d, B_K, sh.cnt * kstride)) != ECG_OK) return st;
-    CU_TRY(ctx, cudaMemcpyAsync(d.buf[B_K], k + sh.off * kstride, sh.cnt * kstride, cudaMemcpyHostToDevice, d.s()));
-    dp.k = (const uint8_t*)d.buf[B_K];
+  if (ctx->flags & ECG_FLAG_DEVICE_PTRS) {
+    *dst = src + off * stride;
+    return ECG_OK;
   }
-  if (p) {
-    if ((st = ensure(ctx, d, B_P, sh.cnt * pstride)) != ECG_OK) return st;
-    CU_TRY(ctx, cudaMemcpyAsync(d.buf[B_P], p + sh.off * pstride, sh.cnt * pstride, cudaMemcpyHostToDevice, d.s()));
-    dp.p = (const uint8_t*)d.buf[B_P];
-  }
-  if (inf) {
-    if ((st = ensure(ctx, d, B_INF, sh.cnt)) != ECG_OK) return st;
-    CU_TRY(ctx, cudaMemcpyAsync(d.buf[B_INF], inf + sh.off, sh.cnt, cudaMemcpyHostToDevice, d.s()));
-    dp.inf = (const uint8_t*)d.buf[B_INF];
-  }
+  ST_TRY(ensure(ctx, d, slot, cnt * stride));
+  CU_TRY(ctx, cudaMemcpyAsync(d.buf[slot], src + off * stride, cnt * stride, cudaMemcpyHostToDevice, d.s()));
+  *dst = (const uint8_t*)d.buf[slot];
   return ECG_OK;
 }
 static ecg_status stage_out(ecg_ctx* ctx, DevState& d, const Shard& sh, uint8_t* out, size_t ostride,
                             uint8_t* oinf, DevPtrs& dp) {
-  bool devptr = ctx->flags & ECG_FLAG_DEVICE_PTRS;
-  if (devptr) {
+  if (ctx->flags & ECG_FLAG_DEVICE_PTRS) {
     dp.out = out + sh.off * ostride;
     dp.oinf = oinf ? oinf + sh.off : nullptr;
     if (!dp.oinf) {
-      ecg_status st = ensure(ctx, d, B_OINF, sh.cnt);
-      if (st != ECG_OK) return st;
+      ST_TRY(ensure(ctx, d, B_OINF, sh.cnt));
       dp.oinf = (uint8_t*)d.buf[B_OINF];
     }
     return ECG_OK;
   }
-  ecg_status st;
-  if ((st = ensure(ctx, d, B_OUT, sh.cnt * ostride)) != ECG_OK) return st;
-  if ((st = ensure(ctx, d, B_OINF, sh.cnt)) != ECG_OK) return st;
+  ST_TRY(ensure(ctx, d, B_OUT, sh.cnt * ostride));
+  ST_TRY(ensure(ctx, d, B_OINF, sh.cnt));
   dp.out = (uint8_t*)d.buf[B_OUT];
   dp.oinf = (uint8_t*)d.buf[B_OINF];
   return ECG_OK;
@@ -466,8 +663,8 @@ static ecg_status copy_back(ecg_ctx* ctx, DevState& d, const Shard& sh, uint8_t*
   return ECG_OK;
 }
 static ecg_status reset_status(ecg_ctx* ctx, DevState& d) {
-  static const uint32_t init[2] = {0u, 0xFFFFFFFFu};
-  CU_TRY(ctx, cudaMemcpyAsync(d.status, init, 8, cudaMemcpyHostToDevice, d.s()));
+  CU_TRY(ctx, cudaMemsetAsync(d.status, 0, 4, d.s()));
+  CU_TRY(ctx, cudaMemsetAsync(d.status + 1, 0xFF, 4, d.s()));
   return ECG_OK;
 }
 // Wait for every device, fold the validation status into a return code.
@@ -485,10 +682,7 @@ static ecg_status finish(ecg_ctx* ctx, const std::vector<Shard>& shards) {
       size_t idx = shards[i].off + d.h_status[1];
       if (idx < first) {
         first = idx;
-        rc = (d.h_status[0] & ERRF_SCALAR) && !(d.h_status[0] & ERRF_POINT) ? ECG_ESCALAR_RANGE
-             : (d.h_status[0] & ERRF_POINT) && !(d.h_status[0] & ERRF_SCALAR) ? ECG_ENOT_ON_CURVE
-                                                                             : ECG_ESCALAR_RANGE;
-        if ((d.h_status[0] & (ERRF_POINT | ERRF_SCALAR)) == (ERRF_POINT | ERRF_SCALAR)) rc = ECG_ENOT_ON_CURVE;
+        rc = (d.h_status[0] & ERRF_POINT) ? ECG_ENOT_ON_CURVE : ECG_ESCALAR_RANGE;
       }
     }
   }
@@ -500,47 +694,59 @@ static ecg_status finish(ecg_ctx* ctx, const std::vector<Shard>& shards) {
 }
 
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+#define LAUNCHED(ctx)                  \
+  do {                                 \
+    (ctx)->launches++;                 \
+    CU_TRY(ctx, cudaGetLastError());   \
+  } while (0)
 
 template <class F>
 static ecg_status launch_normalize(ecg_ctx* ctx, DevState& d, size_t n, const uint32_t* jac, uint8_t* out, uint8_t* oinf) {
-  ecg_status st = ensure(ctx, d, B_SCR, n * 32);
-  if (st != ECG_OK) return st;
-  // ~32 elements per thread amortise the per-thread inversion; never fewer threads than one per SM-warp slot
+  ST_TRY(ensure(ctx, d, B_SCR, n * 32));
+  // ~32 elements per thread amortise the per-thread inversion, but never leave SMs idle for small batches
   size_t want_threads = std::max<size_t>((n + 31) / 32, std::min<size_t>(n, (size_t)d.sm_count * 256));
   unsigned blocks = grid_for(want_threads, 256);
   normalize_kernel<F><<<blocks, 256, 0, d.s()>>>(jac, n, (uint32_t*)d.buf[B_SCR], out, oinf);
-  ctx->launches++;
-  CU_TRY(ctx, cudaGetLastError());
+  LAUNCHED(ctx);
   return ECG_OK;
 }
 
-static const int VB_BLOCK = 128, VB_MINBLK = 3;
+// launch geometry of the variable-base kernels
+static const int K_BLOCK = 128, K_MINBLK = 3;   // secp256k1: 512 B smem/thread  -> 3 x 64 KiB per SM
+static const int P_BLOCK = 128, P_MINBLK = 2;   // P-256   : 768 B smem/thread  -> 2 x 96 KiB per SM
 
-static ecg_status mul_batch_dev(ecg_ctx* ctx, DevState& d, ecg_curve curve, size_t n, const DevPtrs& dp) {
-  ecg_status st = ensure(ctx, d, B_JAC, n * 96);
-  if (st != ECG_OK) return st;
-  uint32_t* jac = (uint32_t*)d.buf[B_JAC];
-  if (curve == ECG_SECP256K1) {
-    size_t smem = (size_t)VB_BLOCK * 8 * 16 * 4;
-    static bool attr_set[64] = {false};
-    if (!attr_set[d.dev & 63]) {
-      CU_TRY(ctx, cudaFuncSetAttribute(k256_varbase_kernel<VB_BLOCK, VB_MINBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set[d.dev & 63] = true;
-    }
-    k256_varbase_kernel<VB_BLOCK, VB_MINBLK><<<grid_for(n, VB_BLOCK), VB_BLOCK, smem, d.s()>>>(dp.k, dp.p, dp.inf, n, jac, d.status);
-    ctx->launches++;
-    CU_TRY(ctx, cudaGetLastError());
-    return launch_normalize<FpK256>(ctx, d, n, jac, dp.out, dp.oinf);
-  }
-  ctx->err = "curve not implemented yet";
-  return ECG_EINVAL;
+template <class KernelT>
+static ecg_status set_smem(ecg_ctx* ctx, KernelT kernel, size_t smem) {
+  CU_TRY(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return ECG_OK;
 }
+
+// k*P for one shard -> Jacobian SoA in `jac`
+static ecg_status launch_varbase(ecg_ctx* ctx, DevState& d, ecg_curve curve, size_t n, const DevPtrs& dp, uint32_t* jac) {
+  if (curve == ECG_SECP256K1) {
+    size_t smem = (size_t)K_BLOCK * 8 * 16 * 4;
+    ST_TRY(set_smem(ctx, k256_varbase_kernel<K_BLOCK, K_MINBLK>, smem));
+    k256_varbase_kernel<K_BLOCK, K_MINBLK><<<grid_for(n, K_BLOCK), K_BLOCK, smem, d.s()>>>(dp.k, dp.p, dp.inf, n, jac, d.status);
+  } else {
+    size_t smem = (size_t)P_BLOCK * 8 * 24 * 4;
+    ST_TRY(set_smem(ctx, generic_varbase_kernel<CurveP256, P_BLOCK, P_MINBLK>, smem));
+    generic_varbase_kernel<CurveP256, P_BLOCK, P_MINBLK><<<grid_for(n, P_BLOCK), P_BLOCK, smem, d.s()>>>(dp.k, dp.p, dp.inf, n, jac, d.status);
+  }
+  LAUNCHED(ctx);
+  return ECG_OK;
+}
+static ecg_status launch_norm(ecg_ctx* ctx, DevState& d, ecg_curve curve, size_t n, const uint32_t* jac, uint8_t* out, uint8_t* oinf) {
+  return curve == ECG_SECP256K1 ? launch_normalize<FpK256>(ctx, d, n, jac, out, oinf)
+                                : launch_normalize<FpP256>(ctx, d, n, jac, out, oinf);
+}
+
+static bool curve_ok(ecg_curve c) { return c == ECG_SECP256K1 || c == ECG_NISTP256; }
 
 extern "C" ecg_status ecg_mul_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
                                     const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf) {
   if (!ctx) return ECG_EINVAL;
   if (n == 0) return ECG_OK;
-  if (!k || !P_xy || !out_xy || (curve != ECG_SECP256K1 && curve != ECG_NISTP256)) {
+  if (!k || !P_xy || !out_xy || !curve_ok(curve)) {
     ctx->err = "ecg_mul_batch: null pointer or unknown curve";
     return ECG_EINVAL;
   }
@@ -551,21 +757,129 @@ extern "C" ecg_status ecg_mul_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, con
     const Shard& sh = shards[i];
     if (sh.cnt == 0) continue;
     CU_TRY(ctx, cudaSetDevice(d.dev));
-    ecg_status st;
-    if ((st = reset_status(ctx, d)) != ECG_OK) return st;
-    if ((st = stage_in(ctx, d, sh, k, 32, P_xy, 64, P_inf, dps[i])) != ECG_OK) return st;
-    if ((st = stage_out(ctx, d, sh, out_xy, 64, out_inf, dps[i])) != ECG_OK) return st;
-    if ((st = mul_batch_dev(ctx, d, curve, sh.cnt, dps[i])) != ECG_OK) return st;
-    if ((st = copy_back(ctx, d, sh, out_xy, 64, out_inf, dps[i])) != ECG_OK) return st;
+    ST_TRY(reset_status(ctx, d));
+    ST_TRY(stage_one(ctx, d, B_K, k, sh.off, sh.cnt, 32, &dps[i].k));
+    ST_TRY(stage_one(ctx, d, B_P, P_xy, sh.off, sh.cnt, 64, &dps[i].p));
+    ST_TRY(stage_one(ctx, d, B_INF, P_inf, sh.off, sh.cnt, 1, &dps[i].inf));
+    ST_TRY(stage_out(ctx, d, sh, out_xy, 64, out_inf, dps[i]));
+    ST_TRY(ensure(ctx, d, B_JAC, sh.cnt * 96));
+    ST_TRY(launch_varbase(ctx, d, curve, sh.cnt, dps[i], (uint32_t*)d.buf[B_JAC]));
+    ST_TRY(launch_norm(ctx, d, curve, sh.cnt, (uint32_t*)d.buf[B_JAC], dps[i].out, dps[i].oinf));
+    ST_TRY(copy_back(ctx, d, sh, out_xy, 64, out_inf, dps[i]));
   }
   return finish(ctx, shards);
 }
 
-extern "C" ecg_status ecg_batch_normalize(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz,
-                                          uint8_t* out_xy, uint8_t* out_inf) {
+// ---- fixed-base table ------------------------------------------------------------------------------
+// Built on the device with the variable-base kernel itself: entry (i, j) = ((2j+1) << 16 i mod n) * G.
+static void scalar_be_from_shifted(uint8_t* out, uint64_t odd, int shift_bits, const uint32_t* n_le) {
+  // v = odd << shift_bits  (< 2^257), reduced once by n (v < 2n always holds: n > 2^255 for both curves)
+  uint32_t v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int w = shift_bits / 32, b = shift_bits % 32;
+  uint64_t lo = odd << b;  // odd < 2^17, b < 32
+  v[w] = (uint32_t)lo;
+  if (w + 1 < 10) v[w + 1] = (uint32_t)(lo >> 32);
+  // compare/subtract n on 9 limbs
+  uint32_t nn[9];
+  for (int i = 0; i < 8; i++) nn[i] = n_le[i];
+  nn[8] = 0;
+  bool ge = true;
+  for (int i = 8; i >= 0; i--) {
+    if (v[i] != nn[i]) {
+      ge = v[i] > nn[i];
+      break;
+    }
+  }
+  if (ge) {
+    uint64_t borrow = 0;
+    for (int i = 0; i < 9; i++) {
+      uint64_t t = (uint64_t)v[i] - nn[i] - borrow;
+      v[i] = (uint32_t)t;
+      borrow = (t >> 63) & 1;
+    }
+  }
+  for (int i = 0; i < 8; i++) {
+    out[31 - 4 * i] = (uint8_t)v[i];
+    out[30 - 4 * i] = (uint8_t)(v[i] >> 8);
+    out[29 - 4 * i] = (uint8_t)(v[i] >> 16);
+    out[28 - 4 * i] = (uint8_t)(v[i] >> 24);
+  }
+}
+static const uint32_t H_K256_N[8] = {0xD0364141u, 0xBFD25E8Cu, 0xAF48A03Bu, 0xBAAEDCE6u, 0xFFFFFFFEu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+static const uint32_t H_P256_N[8] = {0xFC632551u, 0xF3B9CAC2u, 0xA7179E84u, 0xBCE6FAADu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x00000000u, 0xFFFFFFFFu};
+static const uint8_t H_K256_G[64] = {
+    0x79, 0xBE, 0x66, 0x7E, 0xF9, 0xDC, 0xBB, 0xAC, 0x55, 0xA0, 0x62, 0x95, 0xCE, 0x87, 0x0B, 0x07, 0x02, 0x9B, 0xFC, 0xDB, 0x2D, 0xCE,
+    0x28, 0xD9, 0x59, 0xF2, 0x81, 0x5B, 0x16, 0xF8, 0x17, 0x98, 0x48, 0x3A, 0xDA, 0x77, 0x26, 0xA3, 0xC4, 0x65, 0x5D, 0xA4, 0xFB, 0xFC,
+    0x0E, 0x11, 0x08, 0xA8, 0xFD, 0x17, 0xB4, 0x48, 0xA6, 0x85, 0x54, 0x19, 0x9C, 0x47, 0xD0, 0x8F, 0xFB, 0x10, 0xD4, 0xB8};
+static const uint8_t H_P256_G[64] = {
+    0x6B, 0x17, 0xD1, 0xF2, 0xE1, 0x2C, 0x42, 0x47, 0xF8, 0xBC, 0xE6, 0xE5, 0x63, 0xA4, 0x40, 0xF2, 0x77, 0x03, 0x7D, 0x81, 0x2D, 0xEB,
+    0x33, 0xA0, 0xF4, 0xA1, 0x39, 0x45, 0xD8, 0x98, 0xC2, 0x96, 0x4F, 0xE3, 0x42, 0xE2, 0xFE, 0x1A, 0x7F, 0x9B, 0x8E, 0xE7, 0xEB, 0x4A,
+    0x7C, 0x0F, 0x9E, 0x16, 0x2B, 0xCE, 0x33, 0x57, 0x6B, 0x31, 0x5E, 0xCE, 0xCB, 0xB6, 0x40, 0x68, 0x37, 0xBF, 0x51, 0xF5};
+
+static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
+  if (d.fb_table[curve]) return ECG_OK;
+  const size_t np = FB_TABLE_POINTS;
+  std::vector<uint8_t> hk(np * 32), hp(np * 64);
+  const uint32_t* n_le = curve == ECG_SECP256K1 ? H_K256_N : H_P256_N;
+  const uint8_t* g = curve == ECG_SECP256K1 ? H_K256_G : H_P256_G;
+  for (int i = 0; i < FB_WINDOWS; i++)
+    for (uint32_t j = 0; j < FB_ENTRIES; j++) scalar_be_from_shifted(&hk[((size_t)i * FB_ENTRIES + j) * 32], 2ull * j + 1, FB_W * i, n_le);
+  scalar_be_from_shifted(&hk[(np - 1) * 32], 1, 256, n_le);  // 2^256 mod n
+  for (size_t i = 0; i < np; i++) memcpy(&hp[i * 64], g, 64);
+  uint8_t *dk = nullptr, *dpnt = nullptr, *dxy = nullptr, *dinf = nullptr;
+  uint32_t *jac = nullptr, *scr = nullptr, *table = nullptr;
+  CU_TRY(ctx, cudaMalloc((void**)&dk, np * 32));
+  CU_TRY(ctx, cudaMalloc((void**)&dpnt, np * 64));
+  CU_TRY(ctx, cudaMalloc((void**)&dxy, np * 64));
+  CU_TRY(ctx, cudaMalloc((void**)&dinf, np));
+  CU_TRY(ctx, cudaMalloc((void**)&jac, np * 96));
+  CU_TRY(ctx, cudaMalloc((void**)&scr, np * 32));
+  CU_TRY(ctx, cudaMalloc((void**)&table, np * 64));
+  CU_TRY(ctx, cudaMemcpyAsync(dk, hk.data(), np * 32, cudaMemcpyHostToDevice, d.s()));
+  CU_TRY(ctx, cudaMemcpyAsync(dpnt, hp.data(), np * 64, cudaMemcpyHostToDevice, d.s()));
+  DevPtrs dp;
+  dp.k = dk;
+  dp.p = dpnt;
+  // a private status word: building the table must not disturb the caller's validation state
+  uint32_t* st = nullptr;
+  CU_TRY(ctx, cudaMalloc((void**)&st, 8));
+  CU_TRY(ctx, cudaMemsetAsync(st, 0, 8, d.s()));
+  uint32_t* saved = d.status;
+  d.status = st;
+  ecg_status rc = launch_varbase(ctx, d, curve, np, dp, jac);
+  d.status = saved;
+  if (rc != ECG_OK) return rc;
+  size_t want_threads = std::max<size_t>((np + 31) / 32, std::min<size_t>(np, (size_t)d.sm_count * 256));
+  if (curve == ECG_SECP256K1) {
+    normalize_kernel<FpK256><<<grid_for(want_threads, 256), 256, 0, d.s()>>>(jac, np, scr, dxy, dinf);
+    LAUNCHED(ctx);
+    affine_to_table_kernel<CurveK256><<<grid_for(np, 256), 256, 0, d.s()>>>(dxy, np, table);
+  } else {
+    normalize_kernel<FpP256><<<grid_for(want_threads, 256), 256, 0, d.s()>>>(jac, np, scr, dxy, dinf);
+    LAUNCHED(ctx);
+    affine_to_table_kernel<CurveP256><<<grid_for(np, 256), 256, 0, d.s()>>>(dxy, np, table);
+  }
+  LAUNCHED(ctx);
+  CU_TRY(ctx, cudaStreamSynchronize(d.s()));
+  cudaFree(dk);
+  cudaFree(dpnt);
+  cudaFree(dxy);
+  cudaFree(dinf);
+  cudaFree(jac);
+  cudaFree(scr);
+  cudaFree(st);
+  d.fb_table[curve] = table;
+  return ECG_OK;
+}
+
+extern "C" ecg_status ecg_mul_gen_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, uint8_t* out_xy,
+                                        uint8_t* out_inf) {
   if (!ctx) return ECG_EINVAL;
   if (n == 0) return ECG_OK;
-  if (!xyz || !out_xy || (curve != ECG_SECP256K1 && curve != ECG_NISTP256)) return ECG_EINVAL;
+  if (!k || !out_xy || !curve_ok(curve)) {
+    ctx->err = "ecg_mul_gen_batch: null pointer or unknown curve";
+    return ECG_EINVAL;
+  }
   std::vector<Shard> shards = make_shards(n, ctx->devs.size());
   std::vector<DevPtrs> dps(ctx->devs.size());
   for (size_t i = 0; i < ctx->devs.size(); i++) {
@@ -573,22 +887,260 @@ extern "C" ecg_status ecg_batch_normalize(ecg_ctx* ctx, ecg_curve curve, size_t 
     const Shard& sh = shards[i];
     if (sh.cnt == 0) continue;
     CU_TRY(ctx, cudaSetDevice(d.dev));
-    ecg_status st;
-    if ((st = reset_status(ctx, d)) != ECG_OK) return st;
-    if ((st = stage_in(ctx, d, sh, nullptr, 0, xyz, 96, nullptr, dps[i])) != ECG_OK) return st;
-    if ((st = stage_out(ctx, d, sh, out_xy, 64, out_inf, dps[i])) != ECG_OK) return st;
-    if ((st = ensure(ctx, d, B_JAC, sh.cnt * 96)) != ECG_OK) return st;
+    ST_TRY(ensure_fb_table(ctx, d, curve));
+    ST_TRY(reset_status(ctx, d));
+    ST_TRY(stage_one(ctx, d, B_K, k, sh.off, sh.cnt, 32, &dps[i].k));
+    ST_TRY(stage_out(ctx, d, sh, out_xy, 64, out_inf, dps[i]));
+    ST_TRY(ensure(ctx, d, B_JAC, sh.cnt * 96));
+    uint32_t* jac = (uint32_t*)d.buf[B_JAC];
+    if (curve == ECG_SECP256K1)
+      fixedbase_kernel<CurveK256><<<grid_for(sh.cnt, 128), 128, 0, d.s()>>>(dps[i].k, sh.cnt, d.fb_table[curve], jac, d.status);
+    else
+      fixedbase_kernel<CurveP256><<<grid_for(sh.cnt, 128), 128, 0, d.s()>>>(dps[i].k, sh.cnt, d.fb_table[curve], jac, d.status);
+    LAUNCHED(ctx);
+    ST_TRY(launch_norm(ctx, d, curve, sh.cnt, jac, dps[i].out, dps[i].oinf));
+    ST_TRY(copy_back(ctx, d, sh, out_xy, 64, out_inf, dps[i]));
+  }
+  return finish(ctx, shards);
+}
+
+extern "C" ecg_status ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, const uint8_t* b,
+                                            const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf) {
+  if (!ctx) return ECG_EINVAL;
+  if (n == 0) return ECG_OK;
+  if (!a || !b || !P_xy || !out_xy || !curve_ok(curve)) {
+    ctx->err = "ecg_mul_gen_add_batch: null pointer or unknown curve";
+    return ECG_EINVAL;
+  }
+  std::vector<Shard> shards = make_shards(n, ctx->devs.size());
+  std::vector<DevPtrs> dps(ctx->devs.size());
+  for (size_t i = 0; i < ctx->devs.size(); i++) {
+    DevState& d = ctx->devs[i];
+    const Shard& sh = shards[i];
+    if (sh.cnt == 0) continue;
+    CU_TRY(ctx, cudaSetDevice(d.dev));
+    ST_TRY(ensure_fb_table(ctx, d, curve));
+    ST_TRY(reset_status(ctx, d));
+    ST_TRY(stage_one(ctx, d, B_A, a, sh.off, sh.cnt, 32, &dps[i].a));
+    ST_TRY(stage_one(ctx, d, B_K, b, sh.off, sh.cnt, 32, &dps[i].k));
+    ST_TRY(stage_one(ctx, d, B_P, P_xy, sh.off, sh.cnt, 64, &dps[i].p));
+    ST_TRY(stage_one(ctx, d, B_INF, P_inf, sh.off, sh.cnt, 1, &dps[i].inf));
+    ST_TRY(stage_out(ctx, d, sh, out_xy, 64, out_inf, dps[i]));
+    ST_TRY(ensure(ctx, d, B_JAC, sh.cnt * 96));
     uint32_t* jac = (uint32_t*)d.buf[B_JAC];
     if (curve == ECG_SECP256K1) {
-      import_jac_kernel<CurveK256><<<grid_for(sh.cnt, 256), 256, 0, d.s()>>>(dps[i].p, sh.cnt, jac, d.status);
-      ctx->launches++;
-      CU_TRY(ctx, cudaGetLastError());
-      if ((st = launch_normalize<FpK256>(ctx, d, sh.cnt, jac, dps[i].out, dps[i].oinf)) != ECG_OK) return st;
+      size_t smem = (size_t)K_BLOCK * 8 * 16 * 4;
+      ST_TRY(set_smem(ctx, mul_gen_add_kernel<CurveK256, K_BLOCK, K_MINBLK, true>, smem));
+      mul_gen_add_kernel<CurveK256, K_BLOCK, K_MINBLK, true><<<grid_for(sh.cnt, K_BLOCK), K_BLOCK, smem, d.s()>>>(
+          dps[i].a, dps[i].k, dps[i].p, dps[i].inf, sh.cnt, d.fb_table[curve], jac, d.status);
     } else {
-      ctx->err = "curve not implemented yet";
-      return ECG_EINVAL;
+      size_t smem = (size_t)P_BLOCK * 8 * 24 * 4;
+      ST_TRY(set_smem(ctx, mul_gen_add_kernel<CurveP256, P_BLOCK, P_MINBLK, false>, smem));
+      mul_gen_add_kernel<CurveP256, P_BLOCK, P_MINBLK, false><<<grid_for(sh.cnt, P_BLOCK), P_BLOCK, smem, d.s()>>>(
+          dps[i].a, dps[i].k, dps[i].p, dps[i].inf, sh.cnt, d.fb_table[curve], jac, d.status);
     }
-    if ((st = copy_back(ctx, d, sh, out_xy, 64, out_inf, dps[i])) != ECG_OK) return st;
+    LAUNCHED(ctx);
+    ST_TRY(launch_norm(ctx, d, curve, sh.cnt, jac, dps[i].out, dps[i].oinf));
+    ST_TRY(copy_back(ctx, d, sh, out_xy, 64, out_inf, dps[i]));
+  }
+  return finish(ctx, shards);
+}
+
+// ---- lincomb ----------------------------------------------------------------------------------------
+// Reduce n Jacobian points (SoA in `a`) to one, ping-ponging between a and b; returns the buffer holding it.
+template <class C>
+static ecg_status reduce_points(ecg_ctx* ctx, DevState& d, uint32_t* a, uint32_t* b, size_t n, uint32_t** result) {
+  while (n > 1) {
+    size_t m = (n + 31) / 32;
+    jac_sum_kernel<C><<<grid_for(m, 128), 128, 0, d.s()>>>(a, n, b, m);
+    LAUNCHED(ctx);
+    std::swap(a, b);
+    n = m;
+  }
+  *result = a;
+  return ECG_OK;
+}
+static ecg_status reduce_points_c(ecg_ctx* ctx, DevState& d, ecg_curve curve, uint32_t* a, uint32_t* b, size_t n, uint32_t** result) {
+  return curve == ECG_SECP256K1 ? reduce_points<CurveK256>(ctx, d, a, b, n, result) : reduce_points<CurveP256>(ctx, d, a, b, n, result);
+}
+
+// one shard -> one Jacobian point left in *result (SoA with n = 1, i.e. 24 consecutive words)
+static ecg_status lincomb_shard(ecg_ctx* ctx, DevState& d, ecg_curve curve, const Shard& sh, const uint8_t* k,
+                                const uint8_t* P_xy, const uint8_t* P_inf, uint32_t** result) {
+  DevPtrs dp;
+  ST_TRY(reset_status(ctx, d));
+  ST_TRY(stage_one(ctx, d, B_K, k, sh.off, sh.cnt, 32, &dp.k));
+  ST_TRY(stage_one(ctx, d, B_P, P_xy, sh.off, sh.cnt, 64, &dp.p));
+  ST_TRY(stage_one(ctx, d, B_INF, P_inf, sh.off, sh.cnt, 1, &dp.inf));
+  ST_TRY(ensure(ctx, d, B_JAC, sh.cnt * 96));
+  ST_TRY(ensure(ctx, d, B_JAC2, ((sh.cnt + 31) / 32) * 96 + 96));
+  ST_TRY(launch_varbase(ctx, d, curve, sh.cnt, dp, (uint32_t*)d.buf[B_JAC]));
+  return reduce_points_c(ctx, d, curve, (uint32_t*)d.buf[B_JAC], (uint32_t*)d.buf[B_JAC2], sh.cnt, result);
+}
+
+static ecg_status export_point(ecg_ctx* ctx, DevState& d, ecg_curve curve, const uint32_t* jac1, uint8_t* dev_xyz) {
+  if (curve == ECG_SECP256K1)
+    export_jac_kernel<CurveK256><<<1, 128, 0, d.s()>>>(jac1, 1, dev_xyz);
+  else
+    export_jac_kernel<CurveP256><<<1, 128, 0, d.s()>>>(jac1, 1, dev_xyz);
+  LAUNCHED(ctx);
+  return ECG_OK;
+}
+
+extern "C" ecg_status ecg_lincomb_partial(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
+                                          const uint8_t* P_inf, uint8_t* out_xyz) {
+  if (!ctx) return ECG_EINVAL;
+  if (!out_xyz || !curve_ok(curve) || (n > 0 && (!k || !P_xy))) {
+    ctx->err = "ecg_lincomb_partial: null pointer or unknown curve";
+    return ECG_EINVAL;
+  }
+  if (ctx->devs.size() != 1) {
+    ctx->err = "ecg_lincomb_partial: single-device ctx only (use ecg_lincomb for a multi-device ctx)";
+    return ECG_EINVAL;
+  }
+  DevState& d = ctx->devs[0];
+  CU_TRY(ctx, cudaSetDevice(d.dev));
+  bool devptr = ctx->flags & ECG_FLAG_DEVICE_PTRS;
+  if (n == 0) {  // empty sum = identity (0 : 1 : 0)
+    uint8_t z[96];
+    memset(z, 0, sizeof z);
+    z[63] = 1;
+    if (devptr)
+      CU_TRY(ctx, cudaMemcpy(out_xyz, z, 96, cudaMemcpyHostToDevice));
+    else
+      memcpy(out_xyz, z, 96);
+    return ECG_OK;
+  }
+  std::vector<Shard> shards = make_shards(n, 1);
+  uint32_t* res = nullptr;
+  ST_TRY(lincomb_shard(ctx, d, curve, shards[0], k, P_xy, P_inf, &res));
+  uint8_t* dst = out_xyz;
+  if (!devptr) {
+    ST_TRY(ensure(ctx, d, B_AUX, 256));
+    dst = (uint8_t*)d.buf[B_AUX];
+  }
+  ST_TRY(export_point(ctx, d, curve, res, dst));
+  if (!devptr) CU_TRY(ctx, cudaMemcpyAsync(out_xyz, dst, 96, cudaMemcpyDeviceToHost, d.s()));
+  return finish(ctx, shards);
+}
+
+// m Jacobian points as host bytes -> affine sum (device 0 of the ctx)
+static ecg_status point_sum_host(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* xyz, uint8_t* out_xy, uint8_t* out_inf) {
+  DevState& d = ctx->devs[0];
+  CU_TRY(ctx, cudaSetDevice(d.dev));
+  std::vector<Shard> one = make_shards(m, 1);
+  ST_TRY(reset_status(ctx, d));
+  ST_TRY(ensure(ctx, d, B_AUX, m * 96 + 256));
+  ST_TRY(ensure(ctx, d, B_JAC, m * 96 + 96));
+  ST_TRY(ensure(ctx, d, B_JAC2, ((m + 31) / 32) * 96 + 96));
+  ST_TRY(ensure(ctx, d, B_OUT, 64));
+  ST_TRY(ensure(ctx, d, B_OINF, 1));
+  uint8_t* dxyz = (uint8_t*)d.buf[B_AUX];
+  CU_TRY(ctx, cudaMemcpyAsync(dxyz, xyz, m * 96, cudaMemcpyHostToDevice, d.s()));
+  uint32_t* jac = (uint32_t*)d.buf[B_JAC];
+  if (curve == ECG_SECP256K1)
+    import_jac_kernel<CurveK256><<<grid_for(m, 256), 256, 0, d.s()>>>(dxyz, m, jac, d.status);
+  else
+    import_jac_kernel<CurveP256><<<grid_for(m, 256), 256, 0, d.s()>>>(dxyz, m, jac, d.status);
+  LAUNCHED(ctx);
+  uint32_t* res = nullptr;
+  ST_TRY(reduce_points_c(ctx, d, curve, jac, (uint32_t*)d.buf[B_JAC2], m, &res));
+  ST_TRY(launch_norm(ctx, d, curve, 1, res, (uint8_t*)d.buf[B_OUT], (uint8_t*)d.buf[B_OINF]));
+  CU_TRY(ctx, cudaMemcpyAsync(out_xy, d.buf[B_OUT], 64, cudaMemcpyDeviceToHost, d.s()));
+  CU_TRY(ctx, cudaMemcpyAsync(out_inf, d.buf[B_OINF], 1, cudaMemcpyDeviceToHost, d.s()));
+  return finish(ctx, one);
+}
+
+extern "C" ecg_status ecg_point_sum(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* xyz, uint8_t* out_xy,
+                                    uint8_t* out_inf) {
+  if (!ctx) return ECG_EINVAL;
+  if (!out_xy || !out_inf || !curve_ok(curve) || (m > 0 && !xyz)) return ECG_EINVAL;
+  if (m == 0) {
+    memset(out_xy, 0, 64);
+    *out_inf = 1;
+    return ECG_OK;
+  }
+  return point_sum_host(ctx, curve, m, xyz, out_xy, out_inf);
+}
+
+extern "C" ecg_status ecg_lincomb(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
+                                  const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf) {
+  if (!ctx) return ECG_EINVAL;
+  if (!out_xy || !out_inf || !curve_ok(curve) || (n > 0 && (!k || !P_xy))) {
+    ctx->err = "ecg_lincomb: null pointer or unknown curve";
+    return ECG_EINVAL;
+  }
+  bool devptr = ctx->flags & ECG_FLAG_DEVICE_PTRS;
+  if (n == 0) {
+    uint8_t z[65];
+    memset(z, 0, sizeof z);
+    if (devptr) {
+      CU_TRY(ctx, cudaMemcpy(out_xy, z, 64, cudaMemcpyHostToDevice));
+      z[0] = 1;
+      CU_TRY(ctx, cudaMemcpy(out_inf, z, 1, cudaMemcpyHostToDevice));
+    } else {
+      memcpy(out_xy, z, 64);
+      *out_inf = 1;
+    }
+    return ECG_OK;
+  }
+  size_t nd = ctx->devs.size();
+  std::vector<Shard> shards = make_shards(n, nd);
+  if (nd == 1) {
+    DevState& d = ctx->devs[0];
+    CU_TRY(ctx, cudaSetDevice(d.dev));
+    uint32_t* res = nullptr;
+    ST_TRY(lincomb_shard(ctx, d, curve, shards[0], k, P_xy, P_inf, &res));
+    DevPtrs dp;
+    Shard one = {0, 1};
+    ST_TRY(stage_out(ctx, d, one, out_xy, 64, out_inf, dp));
+    ST_TRY(launch_norm(ctx, d, curve, 1, res, dp.out, dp.oinf));
+    ST_TRY(copy_back(ctx, d, one, out_xy, 64, out_inf, dp));
+    return finish(ctx, shards);
+  }
+  // several devices: one partial point per device, gathered through the host (96 B each), summed on device 0
+  std::vector<uint8_t> partial(nd * 96, 0);
+  std::vector<uint8_t*> dsts(nd, nullptr);
+  for (size_t i = 0; i < nd; i++) {
+    DevState& d = ctx->devs[i];
+    partial[i * 96 + 63] = 1;  // identity (0:1:0) for empty shards
+    if (shards[i].cnt == 0) continue;
+    CU_TRY(ctx, cudaSetDevice(d.dev));
+    uint32_t* res = nullptr;
+    ST_TRY(lincomb_shard(ctx, d, curve, shards[i], k, P_xy, P_inf, &res));
+    ST_TRY(ensure(ctx, d, B_AUX, 256));
+    ST_TRY(export_point(ctx, d, curve, res, (uint8_t*)d.buf[B_AUX]));
+    CU_TRY(ctx, cudaMemcpyAsync(&partial[i * 96], d.buf[B_AUX], 96, cudaMemcpyDeviceToHost, d.s()));
+  }
+  ecg_status rc = finish(ctx, shards);
+  if (rc != ECG_OK) return rc;
+  return point_sum_host(ctx, curve, nd, partial.data(), out_xy, out_inf);
+}
+
+extern "C" ecg_status ecg_batch_normalize(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz,
+                                          uint8_t* out_xy, uint8_t* out_inf) {
+  if (!ctx) return ECG_EINVAL;
+  if (n == 0) return ECG_OK;
+  if (!xyz || !out_xy || !curve_ok(curve)) return ECG_EINVAL;
+  std::vector<Shard> shards = make_shards(n, ctx->devs.size());
+  std::vector<DevPtrs> dps(ctx->devs.size());
+  for (size_t i = 0; i < ctx->devs.size(); i++) {
+    DevState& d = ctx->devs[i];
+    const Shard& sh = shards[i];
+    if (sh.cnt == 0) continue;
+    CU_TRY(ctx, cudaSetDevice(d.dev));
+    ST_TRY(reset_status(ctx, d));
+    ST_TRY(stage_one(ctx, d, B_P, xyz, sh.off, sh.cnt, 96, &dps[i].p));
+    ST_TRY(stage_out(ctx, d, sh, out_xy, 64, out_inf, dps[i]));
+    ST_TRY(ensure(ctx, d, B_JAC, sh.cnt * 96));
+    uint32_t* jac = (uint32_t*)d.buf[B_JAC];
+    if (curve == ECG_SECP256K1)
+      import_jac_kernel<CurveK256><<<grid_for(sh.cnt, 256), 256, 0, d.s()>>>(dps[i].p, sh.cnt, jac, d.status);
+    else
+      import_jac_kernel<CurveP256><<<grid_for(sh.cnt, 256), 256, 0, d.s()>>>(dps[i].p, sh.cnt, jac, d.status);
+    LAUNCHED(ctx);
+    ST_TRY(launch_norm(ctx, d, curve, sh.cnt, jac, dps[i].out, dps[i].oinf));
+    ST_TRY(copy_back(ctx, d, sh, out_xy, 64, out_inf, dps[i]));
   }
   return finish(ctx, shards);
 }
@@ -598,8 +1150,7 @@ extern "C" ecg_status ecg_field_op_batch(ecg_ctx* ctx, ecg_curve curve, int op, 
   if (!ctx) return ECG_EINVAL;
   if (n == 0) return ECG_OK;
   bool binary = (op == ECG_FOP_ADD || op == ECG_FOP_SUB || op == ECG_FOP_MUL);
-  if (!a || !out || (binary && !b) || op < 0 || op > ECG_FOP_INV || (curve != ECG_SECP256K1 && curve != ECG_NISTP256))
-    return ECG_EINVAL;
+  if (!a || !out || (binary && !b) || op < 0 || op > ECG_FOP_INV || !curve_ok(curve)) return ECG_EINVAL;
   std::vector<Shard> shards = make_shards(n, ctx->devs.size());
   std::vector<DevPtrs> dps(ctx->devs.size());
   for (size_t i = 0; i < ctx->devs.size(); i++) {
@@ -607,20 +1158,16 @@ extern "C" ecg_status ecg_field_op_batch(ecg_ctx* ctx, ecg_curve curve, int op, 
     const Shard& sh = shards[i];
     if (sh.cnt == 0) continue;
     CU_TRY(ctx, cudaSetDevice(d.dev));
-    ecg_status st;
-    if ((st = reset_status(ctx, d)) != ECG_OK) return st;
-    // a -> B_K slot, b -> B_P slot (both 32-byte strides)
-    if ((st = stage_in(ctx, d, sh, a, 32, binary ? b : nullptr, 32, nullptr, dps[i])) != ECG_OK) return st;
-    if ((st = stage_out(ctx, d, sh, out, 32, nullptr, dps[i])) != ECG_OK) return st;
-    if (curve == ECG_SECP256K1) {
-      field_op_kernel<CurveK256><<<grid_for(sh.cnt, 256), 256, 0, d.s()>>>(op, sh.cnt, dps[i].k, dps[i].p, dps[i].out, d.status);
-    } else {
-      ctx->err = "curve not implemented yet";
-      return ECG_EINVAL;
-    }
-    ctx->launches++;
-    CU_TRY(ctx, cudaGetLastError());
-    if ((st = copy_back(ctx, d, sh, out, 32, nullptr, dps[i])) != ECG_OK) return st;
+    ST_TRY(reset_status(ctx, d));
+    ST_TRY(stage_one(ctx, d, B_K, a, sh.off, sh.cnt, 32, &dps[i].k));
+    ST_TRY(stage_one(ctx, d, B_A, binary ? b : nullptr, sh.off, sh.cnt, 32, &dps[i].a));
+    ST_TRY(stage_out(ctx, d, sh, out, 32, nullptr, dps[i]));
+    if (curve == ECG_SECP256K1)
+      field_op_kernel<CurveK256><<<grid_for(sh.cnt, 256), 256, 0, d.s()>>>(op, sh.cnt, dps[i].k, dps[i].a, dps[i].out, d.status);
+    else
+      field_op_kernel<CurveP256><<<grid_for(sh.cnt, 256), 256, 0, d.s()>>>(op, sh.cnt, dps[i].k, dps[i].a, dps[i].out, d.status);
+    LAUNCHED(ctx);
+    ST_TRY(copy_back(ctx, d, sh, out, 32, nullptr, dps[i]));
   }
   return finish(ctx, shards);
 }
@@ -629,8 +1176,7 @@ extern "C" ecg_status ecg_microbench(ecg_ctx* ctx, int which, int iters, double*
   if (!ctx || !ops_per_s || iters <= 0) return ECG_EINVAL;
   DevState& d = ctx->devs[0];
   CU_TRY(ctx, cudaSetDevice(d.dev));
-  ecg_status st = ensure(ctx, d, B_AUX, 256);
-  if (st != ECG_OK) return st;
+  ST_TRY(ensure(ctx, d, B_AUX, 256));
   uint32_t* out = (uint32_t*)d.buf[B_AUX];
   unsigned blocks = (unsigned)d.sm_count * 8, threads = 256;
   double per_thread_iter = 0;
@@ -645,6 +1191,7 @@ extern "C" ecg_status ecg_microbench(ecg_ctx* ctx, int which, int iters, double*
       case 1: mb_imad_kernel<<<blocks, threads, 0, d.s()>>>(out, iters, 12345u + rep); per_thread_iter = 64; break;
       case 2: mb_iadd_kernel<<<blocks, threads, 0, d.s()>>>(out, iters, 12345u + rep); per_thread_iter = 64; break;
       case 3: mb_fmul_kernel<FpK256><<<blocks, threads, 0, d.s()>>>(out, iters, 12345u + rep); per_thread_iter = 2; break;
+      case 4: mb_fmul_kernel<FpP256><<<blocks, threads, 0, d.s()>>>(out, iters, 12345u + rep); per_thread_iter = 2; break;
       default:
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
@@ -663,26 +1210,4 @@ extern "C" ecg_status ecg_microbench(ecg_ctx* ctx, int which, int iters, double*
   *ops_per_s = (double)blocks * threads * (double)iters * per_thread_iter / (best * 1e-3);
   if (elapsed_ms) *elapsed_ms = best;
   return ECG_OK;
-}
-
-// ---- not yet implemented entries (filled in below as the build widens) ------------------------------
-extern "C" ecg_status ecg_mul_gen_batch(ecg_ctx* ctx, ecg_curve, size_t, const uint8_t*, uint8_t*, uint8_t*) {
-  if (ctx) ctx->err = "ecg_mul_gen_batch: not implemented";
-  return ECG_EINVAL;
-}
-extern "C" ecg_status ecg_lincomb(ecg_ctx* ctx, ecg_curve, size_t, const uint8_t*, const uint8_t*, const uint8_t*, uint8_t*, uint8_t*) {
-  if (ctx) ctx->err = "ecg_lincomb: not implemented";
-  return ECG_EINVAL;
-}
-extern "C" ecg_status ecg_lincomb_partial(ecg_ctx* ctx, ecg_curve, size_t, const uint8_t*, const uint8_t*, const uint8_t*, uint8_t*) {
-  if (ctx) ctx->err = "ecg_lincomb_partial: not implemented";
-  return ECG_EINVAL;
-}
-extern "C" ecg_status ecg_point_sum(ecg_ctx* ctx, ecg_curve, size_t, const uint8_t*, uint8_t*, uint8_t*) {
-  if (ctx) ctx->err = "ecg_point_sum: not implemented";
-  return ECG_EINVAL;
-}
-extern "C" ecg_status ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve, size_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, uint8_t*, uint8_t*) {
-  if (ctx) ctx->err = "ecg_mul_gen_add_batch: not implemented";
-  return ECG_EINVAL;
 }

@@ -11,10 +11,27 @@ LIB = os.path.join(_HERE, "libecref.so")
 _lib = None
 
 
+def _host_tag():
+    """-march=native binaries must be rebuilt on the machine that runs them: tag the build with the CPU flags."""
+    import hashlib
+
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((ln for ln in f if ln.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    return hashlib.sha1(flags.encode()).hexdigest()
+
+
 def build(force=False):
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(os.path.join(_HERE, "ecref.c")):
-        # -march=native binaries must be rebuilt on the machine that runs them
+    tagf = LIB + ".host"
+    tag = _host_tag()
+    stale = (not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(os.path.join(_HERE, "ecref.c"))
+             or not os.path.exists(tagf) or open(tagf).read().strip() != tag)
+    if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-B", "libecref.so"], stdout=subprocess.DEVNULL)
+        with open(tagf, "w") as f:
+            f.write(tag)
     return LIB
 
 

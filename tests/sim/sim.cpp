@@ -5,6 +5,7 @@
 // libecgpu.so; never used as a fallback.
 #include <cstring>
 #include <vector>
+#include "../../elliptic-curves_b200/csrc/ecg_curves.cuh"
 #include "../../elliptic-curves_b200/csrc/ecg_mul.cuh"
 #include "../../elliptic-curves_b200/csrc/ecg_io.cuh"
 
@@ -90,5 +91,71 @@ int sim_k256_on_curve(const uint8_t* P_xy) {
   F::set_zero(b);
   b.v[0] = 7;
   return aff_on_curve<F, false>(P, b) ? 1 : 0;
+}
+
+// ---- P-256 -----------------------------------------------------------------------------------
+int sim_p256_fe_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  typedef FpP256 F;
+  Fe x, y, r;
+  load_be32(x.v, a);
+  load_be32(y.v, b);
+  switch (op) {
+    case 0: F::add(r, x, y); break;
+    case 1: F::sub(r, x, y); break;
+    case 2: F::mul(r, x, y); break;
+    case 3: F::sqr(r, x); break;
+    case 4: F::neg(r, x); break;
+    case 5: F::half(r, x); break;
+    case 6: F::mul_small(r, x, 3); break;
+    case 7: F::inv(r, x); break;
+    case 8: r = x; break;
+    case 9: F::mul_small(r, x, 8); break;
+    default: return -1;
+  }
+  F::normalize(r, r);
+  store_be32(out, r.v);
+  return 0;
+}
+}  // extern "C"
+template <class F, bool AM3>
+static int sim_generic_mul(const uint8_t* k_be, const uint8_t* P_xy, uint8_t* out_xy, uint8_t* out_inf) {
+  uint32_t k[8];
+  load_be32(k, k_be);
+  Aff P;
+  load_be32(P.x.v, P_xy);
+  load_be32(P.y.v, P_xy + 32);
+  std::vector<uint32_t> tabmem(8 * 24);
+  TabRefJ tab{tabmem.data(), 1};
+  Jac r;
+  generic_mul_thread<F, AM3>(r, k, P, tab);
+  if (F::is_zero(r.Z)) {
+    memset(out_xy, 0, 64);
+    *out_inf = 1;
+    return 0;
+  }
+  Fe zinv, x, y;
+  F::inv(zinv, r.Z);
+  jac_to_affine_canonical<F>(x, y, r, zinv);
+  store_be32(out_xy, x.v);
+  store_be32(out_xy + 32, y.v);
+  *out_inf = 0;
+  return 0;
+}
+extern "C" {
+int sim_p256_mul(const uint8_t* k_be, const uint8_t* P_xy, uint8_t* out_xy, uint8_t* out_inf) {
+  return sim_generic_mul<FpP256, true>(k_be, P_xy, out_xy, out_inf);
+}
+// generic (no-endomorphism) path instantiated for secp256k1 as a cross-check of the shared code
+int sim_k256_mul_generic(const uint8_t* k_be, const uint8_t* P_xy, uint8_t* out_xy, uint8_t* out_inf) {
+  return sim_generic_mul<FpK256, false>(k_be, P_xy, out_xy, out_inf);
+}
+int sim_p256_on_curve(const uint8_t* P_xy) {
+  typedef FpP256 F;
+  Aff P;
+  load_be32(P.x.v, P_xy);
+  load_be32(P.y.v, P_xy + 32);
+  Fe b;
+  CurveP256::b_internal(b);
+  return aff_on_curve<F, true>(P, b) ? 1 : 0;
 }
 }

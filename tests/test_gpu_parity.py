@@ -1,0 +1,327 @@
+"""GPU parity through the C ABI (libecgpu.so) vs the oracle: the reference's golden vectors, the big-integer
+model, and the C restatement of the reference's CPU path (bit-exact on every output)."""
+import random
+
+import numpy as np
+import pytest
+
+import ecref
+import pyref
+from helpers import edge_scalars, golden, pack_points, pack_scalars, random_points, unpack_points
+
+pytestmark = pytest.mark.gpu
+CURVES = ["k256", "p256"]
+
+
+def ints(out):
+    return [int.from_bytes(o.tobytes(), "big") for o in np.asarray(out).reshape(-1, 32)]
+
+
+# ---------------------------------------------------------------- field layer
+@pytest.mark.parametrize("curve", CURVES)
+def test_field_ops_vs_bigint_and_oracle(engine, curve):
+    p = pyref.CURVES[curve].p
+    rng = random.Random(11)
+    edge = [0, 1, 2, p - 1, p - 2, (p + 1) // 2, 2**256 - p, 2**256 - p - 1, 2**255, 2**128, 2**224, 2**96]
+    a = edge + [rng.randrange(p) for _ in range(4000)]
+    b = [rng.choice(edge) for _ in edge] + [rng.randrange(p) for _ in range(4000)]
+    A, B = pack_scalars(a), pack_scalars(b)
+    model = {"add": lambda x, y: (x + y) % p, "sub": lambda x, y: (x - y) % p, "mul": lambda x, y: x * y % p,
+             "neg": lambda x, y: (-x) % p, "sqr": lambda x, y: x * x % p, "inv": lambda x, y: pow(x, -1, p) if x else 0}
+    ops = {"add": 0, "sub": 1, "neg": 2, "mul": 3, "sqr": 4, "inv": 5}
+    for op, f in model.items():
+        bb = B if op in ("add", "sub", "mul") else None
+        out = engine.field_op(curve, op, A, bb)
+        assert ints(out) == [f(x, y) for x, y in zip(a, b)], op
+        assert np.array_equal(out, ecref.field_op(curve, ops[op], A, bb)), op
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_field_golden_doubling_chain(engine, curve):
+    # DBL_TEST_VECTORS ({k256,p256}/src/test_vectors/field.rs:6): 2^i as 32-byte BE
+    dbl = [int(h, 16) for h in golden(curve)["field"]["dbl"]]
+    A = pack_scalars(dbl[:-1])
+    assert ints(engine.field_op(curve, "add", A, A)) == dbl[1:]
+    assert ints(engine.field_op(curve, "mul", A, pack_scalars([2] * (len(dbl) - 1)))) == dbl[1:]
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_field_rejects_noncanonical(engine, curve):
+    import ecgpu
+
+    p = pyref.CURVES[curve].p
+    with pytest.raises(ecgpu.NotOnCurveError):
+        engine.field_op(curve, "add", pack_scalars([1, p]), pack_scalars([1, 1]))
+
+
+# ---------------------------------------------------------------- variable base (rows a4-a10, a12, a13)
+@pytest.mark.parametrize("curve", CURVES)
+def test_golden_mul_vectors(engine, curve):
+    c = pyref.CURVES[curve]
+    g = golden(curve)
+    ks = [v["k"] for v in g["group"]["add"]] + [int(v["k"], 16) for v in g["group"]["mul"]]
+    exp = [(int(v["x"], 16), int(v["y"], 16)) for v in g["group"]["add"] + g["group"]["mul"]]
+    ks += [int(v["d"], 16) for v in g["ecdsa"]["keypairs"]]
+    exp += [(int(v["x"], 16), int(v["y"], 16)) for v in g["ecdsa"]["keypairs"]]
+    G = pyref.G(c)
+    xy, inf = pack_points([G] * len(ks))
+    out_xy, out_inf = engine.mul_batch(curve, pack_scalars(ks), xy, inf)
+    assert unpack_points(out_xy, out_inf) == exp
+    out_xy, out_inf = engine.mul_by_generator(curve, pack_scalars(ks))
+    assert unpack_points(out_xy, out_inf) == exp
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_varbase_random_and_edges_bit_exact_vs_oracle(engine, curve):
+    c = pyref.CURVES[curve]
+    rng = random.Random(2024)
+    bench_ks = [int(v["k"], 16) for v in golden(curve)["bench"]["scalars"]]
+    ks = edge_scalars(c) + bench_ks + [rng.randrange(c.n) for _ in range(1500)]
+    base = random_points(c, 48, seed=5)
+    Ps = [base[i % 48] for i in range(len(ks))]
+    Ps[3] = None  # identity inputs (k256/src/arithmetic/mul.rs:356-365)
+    Ps[10] = None
+    xy, inf = pack_points(Ps)
+    K = pack_scalars(ks)
+    out_xy, out_inf = engine.mul_batch(curve, K, xy, inf)
+    for variant in (0, 1):  # the reference's constant-time `*` and mul_vartime must both agree
+        ref_xy, ref_inf = ecref.mul_batch(curve, K, xy, inf, nthreads=8, variant=variant)
+        assert np.array_equal(np.asarray(out_xy).reshape(-1), ref_xy.reshape(-1))
+        assert np.array_equal(out_inf, ref_inf)
+    got = unpack_points(out_xy, out_inf)
+    for i in list(range(40)) + list(range(40, len(ks), 97)):
+        assert got[i] == pyref.mul(c, ks[i], Ps[i])
+    assert got[0] is None and int(out_inf[0]) == 1 and not np.asarray(out_xy)[0].any()
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_ragged_sizes_and_empty(engine, curve):
+    c = pyref.CURVES[curve]
+    rng = random.Random(77)
+    G = pyref.G(c)
+    for n in (1, 2, 31, 33, 127, 129, 385):
+        ks = [rng.randrange(c.n) for _ in range(n)]
+        xy, inf = pack_points([G] * n)
+        K = pack_scalars(ks)
+        out_xy, out_inf = engine.mul_batch(curve, K, xy, inf)
+        ref_xy, ref_inf = ecref.mul_gen_batch(curve, K, nthreads=4)
+        assert np.array_equal(np.asarray(out_xy).reshape(-1), ref_xy.reshape(-1)) and np.array_equal(out_inf, ref_inf)
+        g_xy, g_inf = engine.mul_by_generator(curve, K)
+        assert np.array_equal(np.asarray(g_xy).reshape(-1), ref_xy.reshape(-1)) and np.array_equal(g_inf, ref_inf)
+    out_xy, out_inf = engine.mul_batch(curve, np.zeros(0, np.uint8), np.zeros(0, np.uint8), None)
+    assert out_xy.shape[0] == 0
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_rejects_bad_inputs(engine, curve):
+    import ecgpu
+
+    c = pyref.CURVES[curve]
+    G = pyref.G(c)
+    xy, inf = pack_points([G, G, G])
+    with pytest.raises(ecgpu.ScalarRangeError) as ei:
+        engine.mul_batch(curve, pack_scalars([1, c.n, 5]), xy, inf)
+    assert ei.value.index == 1
+    with pytest.raises(ecgpu.ScalarRangeError):
+        engine.mul_by_generator(curve, pack_scalars([1, 2, 2**256 - 1]))
+    bad = xy.copy()
+    bad[2 * 64 + 63] ^= 1  # off-curve
+    with pytest.raises(ecgpu.NotOnCurveError) as ei:
+        engine.mul_batch(curve, pack_scalars([1, 2, 3]), bad, inf)
+    assert ei.value.index == 2
+    bad = xy.copy()
+    bad[0:32] = 0xFF  # x >= p
+    with pytest.raises(ecgpu.NotOnCurveError):
+        engine.mul_batch(curve, pack_scalars([1, 2, 3]), bad, inf)
+    # the engine stays usable after an error
+    out_xy, out_inf = engine.mul_batch(curve, pack_scalars([1, 2, 3]), xy, inf)
+    assert unpack_points(out_xy, out_inf) == [pyref.mul(c, k, G) for k in (1, 2, 3)]
+
+
+# ---------------------------------------------------------------- fixed base (row a11)
+@pytest.mark.parametrize("curve", CURVES)
+def test_mul_by_generator_vs_oracle(engine, curve):
+    c = pyref.CURVES[curve]
+    rng = random.Random(31)
+    ks = edge_scalars(c) + [rng.randrange(c.n) for _ in range(3000)]
+    # every 16-bit window value at least once in some position: structured scalars
+    ks += [(0xFFFF << s) % c.n for s in range(0, 256, 16)] + [(0x8000 << s) % c.n for s in range(0, 256, 16)]
+    ks += [(0x7FFF << s) % c.n for s in range(0, 256, 16)] + [(1 << s) % c.n for s in range(0, 256, 7)]
+    K = pack_scalars(ks)
+    out_xy, out_inf = engine.mul_by_generator(curve, K)
+    ref_xy, ref_inf = ecref.mul_gen_batch(curve, K, nthreads=8)
+    assert np.array_equal(np.asarray(out_xy).reshape(-1), ref_xy.reshape(-1)) and np.array_equal(out_inf, ref_inf)
+    got = unpack_points(out_xy, out_inf)
+    G = pyref.G(c)
+    for i in range(0, len(ks), 211):
+        assert got[i] == pyref.mul(c, ks[i], G)
+
+
+# ---------------------------------------------------------------- a*G + b*P  (MulByGeneratorVartime)
+@pytest.mark.parametrize("curve", CURVES)
+def test_mul_gen_add(engine, curve):
+    c = pyref.CURVES[curve]
+    rng = random.Random(57)
+    n = 200
+    base = random_points(c, 16, seed=4)
+    Ps = [base[i % 16] for i in range(n)]
+    a = [rng.randrange(c.n) for _ in range(n)]
+    b = [rng.randrange(c.n) for _ in range(n)]
+    a[0], b[0] = 0, 0
+    a[1], b[1] = 5, 0
+    a[2], b[2] = 0, 7
+    Ps[4] = None
+    # a*G + b*P = O : P = G, b = n - a
+    Ps[5] = pyref.G(c)
+    b[5] = c.n - a[5]
+    # a*G == b*P (forces the doubling branch of the final addition): P = G, a = b
+    Ps[6] = pyref.G(c)
+    b[6] = a[6]
+    xy, inf = pack_points(Ps)
+    out_xy, out_inf = engine.mul_by_generator_and_mul_add(curve, pack_scalars(a), pack_scalars(b), xy, inf)
+    got = unpack_points(out_xy, out_inf)
+    G = pyref.G(c)
+    for i in range(n):
+        assert got[i] == pyref.add(c, pyref.mul(c, a[i], G), pyref.mul(c, b[i], Ps[i])), i
+
+
+# ---------------------------------------------------------------- lincomb (rows a7, a8, a12)
+@pytest.mark.parametrize("curve", CURVES)
+def test_lincomb_vs_oracle(engine, curve):
+    c = pyref.CURVES[curve]
+    rng = random.Random(8)
+    for n in (1, 2, 3, 33, 1000, 5000):
+        base = random_points(c, min(n, 24), seed=n)
+        Ps = [base[i % len(base)] for i in range(n)]
+        ks = [rng.randrange(c.n) for _ in range(n)]
+        if n >= 33:
+            Ps[7] = None
+            ks[9] = 0
+        xy, inf = pack_points(Ps)
+        K = pack_scalars(ks)
+        out_xy, out_inf = engine.lincomb(curve, K, xy, inf)
+        ref_xy, ref_inf = ecref.lincomb(curve, K, xy, inf, nthreads=8)
+        assert np.array_equal(out_xy, ref_xy) and out_inf == ref_inf
+        if n <= 33:
+            assert pyref.dec_point(out_xy.tobytes(), out_inf) == pyref.lincomb(c, ks, Ps)
+    # sum that cancels to the identity: k*P + (n-k)*P
+    P = random_points(c, 1, seed=99)[0]
+    xy, inf = pack_points([P, P])
+    out_xy, out_inf = engine.lincomb(curve, pack_scalars([1234567, c.n - 1234567]), xy, inf)
+    assert out_inf == 1 and not out_xy.any()
+    # empty sum
+    out_xy, out_inf = engine.lincomb(curve, np.zeros(0, np.uint8), np.zeros(0, np.uint8), None)
+    assert out_inf == 1
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_lincomb_partial_and_point_sum(engine, curve):
+    """config-5 shape: per-rank partial sums (Jacobian, 96 B) combined by ecg_point_sum == one big lincomb."""
+    c = pyref.CURVES[curve]
+    rng = random.Random(15)
+    n = 600
+    base = random_points(c, 20, seed=6)
+    Ps = [base[i % 20] for i in range(n)]
+    ks = [rng.randrange(c.n) for _ in range(n)]
+    xy, inf = pack_points(Ps)
+    K = pack_scalars(ks)
+    parts = []
+    for lo, hi in ((0, 150), (150, 151), (151, 600), (600, 600)):
+        parts.append(engine.lincomb_partial(curve, K[32 * lo:32 * hi], xy[64 * lo:64 * hi], inf[lo:hi]))
+    s_xy, s_inf = engine.point_sum(curve, np.concatenate(parts))
+    ref_xy, ref_inf = ecref.lincomb(curve, K, xy, inf, nthreads=8)
+    assert np.array_equal(s_xy, ref_xy) and s_inf == ref_inf
+
+
+# ---------------------------------------------------------------- batch normalisation (row a5)
+@pytest.mark.parametrize("curve", CURVES)
+def test_batch_normalize(engine, curve):
+    c = pyref.CURVES[curve]
+    p = c.p
+    rng = random.Random(3)
+    Ps = random_points(c, 70, seed=21)
+    xyz = bytearray()
+    exp = []
+    for i, P in enumerate(Ps):
+        if i % 7 == 3:
+            xyz += rng.randrange(p).to_bytes(32, "big") + rng.randrange(p).to_bytes(32, "big") + bytes(32)
+            exp.append(None)
+            continue
+        z = rng.randrange(1, p)
+        xyz += (P[0] * z * z % p).to_bytes(32, "big") + (P[1] * z * z * z % p).to_bytes(32, "big") + z.to_bytes(32, "big")
+        exp.append(P)
+    out_xy, out_inf = engine.batch_normalize(curve, np.frombuffer(bytes(xyz), dtype=np.uint8))
+    assert unpack_points(out_xy, out_inf) == exp
+
+
+# ---------------------------------------------------------------- size-independent properties at scale
+@pytest.mark.parametrize("curve,logn", [("k256", 17), ("p256", 16)])
+def test_large_batch_properties(engine, curve, logn):
+    """k*P and (n-k)*P must be negatives of each other; sample checked against the oracle;
+    lincomb of the whole batch must be the identity."""
+    c = pyref.CURVES[curve]
+    rng = random.Random(99)
+    n = 1 << logn
+    h = n // 2
+    base = random_points(c, 64, seed=33)
+    ks = [rng.randrange(1, c.n) for _ in range(h)]
+    ks = ks + [c.n - k for k in ks]
+    Ps = [base[i % 64] for i in range(h)] * 2
+    xy, inf = pack_points(Ps)
+    K = pack_scalars(ks)
+    out_xy, out_inf = engine.mul_batch(curve, K, xy, None)
+    out_xy = np.asarray(out_xy).reshape(n, 64)
+    assert not out_inf.any()
+    assert (out_xy[:h, :32] == out_xy[h:, :32]).all()
+    for i in range(0, h, 1013):
+        ya = int.from_bytes(out_xy[i, 32:].tobytes(), "big")
+        yb = int.from_bytes(out_xy[h + i, 32:].tobytes(), "big")
+        assert (ya + yb) % c.p == 0
+    idx = list(range(0, n, 2003))
+    sub_xy, sub_inf = ecref.mul_batch(curve, K.reshape(n, 32)[idx], xy.reshape(n, 64)[idx], None, nthreads=8)
+    assert np.array_equal(out_xy[idx], sub_xy)
+    l_xy, l_inf = engine.lincomb(curve, K, xy, None)
+    assert l_inf == 1 and not l_xy.any()
+
+
+def test_multi_engine_independence():
+    """distinct ctxs are independent (include/ecgpu.h contract)."""
+    import ecgpu
+
+    c = pyref.K256
+    e1, e2 = ecgpu.Engine([0]), ecgpu.Engine([0])
+    G = pyref.G(c)
+    xy, inf = pack_points([G] * 4)
+    a, _ = e1.mul_batch("k256", pack_scalars([1, 2, 3, 4]), xy, inf)
+    b, _ = e2.mul_batch("k256", pack_scalars([1, 2, 3, 4]), xy, inf)
+    assert np.array_equal(a, b)
+    assert e1.kernel_launches >= 2 and e2.kernel_launches >= 2
+    e1.close()
+    e2.close()
+
+
+def test_device_pointer_mode():
+    """ECG_FLAG_DEVICE_PTRS: operands already resident in HBM (torch owns the memory)."""
+    import torch
+
+    import ecgpu
+
+    c = pyref.K256
+    eng = ecgpu.Engine([0], device_ptrs=True)
+    n = 1000
+    rng = random.Random(1)
+    ks = [rng.randrange(c.n) for _ in range(n)]
+    base = random_points(c, 8, seed=2)
+    Ps = [base[i % 8] for i in range(n)]
+    xy, inf = pack_points(Ps)
+    K = pack_scalars(ks)
+    dev = torch.device("cuda:0")
+    kd = torch.from_numpy(K).to(dev)
+    pd = torch.from_numpy(xy).to(dev)
+    oxy = torch.empty(n * 64, dtype=torch.uint8, device=dev)
+    oinf = torch.empty(n, dtype=torch.uint8, device=dev)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    eng.mul_batch_ptr("k256", n, kd.data_ptr(), pd.data_ptr(), 0, oxy.data_ptr(), oinf.data_ptr())
+    ref_xy, ref_inf = ecref.mul_batch("k256", K, xy, None, nthreads=8)
+    assert np.array_equal(oxy.cpu().numpy(), ref_xy.reshape(-1)) and np.array_equal(oinf.cpu().numpy(), ref_inf)
+    eng.close()

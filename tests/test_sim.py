@@ -1,0 +1,112 @@
+"""CPU-only: the device arithmetic headers compiled for the host (PTX carry flags emulated) vs the big-int model.
+This exercises exactly the code the CUDA kernels run — field ops on the weakly-reduced range, GLV split,
+signed-odd recoding, window tables, exceptional cases — without a GPU.  tests/sim is test infrastructure."""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+
+import pyref
+from helpers import edge_scalars, golden, random_points
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SIM_SO = os.path.join(HERE, "sim", "libecgsim.so")
+
+
+@pytest.fixture(scope="module")
+def sim():
+    src = os.path.join(HERE, "sim", "sim.cpp")
+    csrc = os.path.join(HERE, "..", "elliptic-curves_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc)]
+    if not os.path.exists(SIM_SO) or any(os.path.getmtime(d) > os.path.getmtime(SIM_SO) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-shared", "-fPIC", "-o", SIM_SO, src])
+    return ctypes.CDLL(SIM_SO)
+
+
+def _feop(sim, curve, op, a, b=0):
+    out = ctypes.create_string_buffer(32)
+    getattr(sim, f"sim_{curve}_fe_op")(op, a.to_bytes(32, "big"), b.to_bytes(32, "big"), out)
+    return int.from_bytes(out.raw, "big")
+
+
+@pytest.mark.parametrize("curve", ["k256", "p256"])
+def test_field_ops_full_256bit_range(sim, curve):
+    p = pyref.CURVES[curve].p
+    rng = random.Random(7)
+    edge = [0, 1, 2, p - 1, p, p + 1, 2**256 - 1, 2**256 - 2, 2**256 - p, 2**256 - p - 1, p - 2, (p + 1) // 2,
+            2**255, 2**128, 2**224, 2**192, 2**96, 2**224 - 1, 2**256 - 2**224]
+    vals = edge + [rng.randrange(2**256) for _ in range(150)]
+    for a in vals:
+        for b in rng.sample(vals, 8) + edge[:8]:
+            assert _feop(sim, curve, 0, a, b) == (a + b) % p
+            assert _feop(sim, curve, 1, a, b) == (a - b) % p
+            assert _feop(sim, curve, 2, a, b) == a * b % p
+        assert _feop(sim, curve, 3, a) == a * a % p
+        assert _feop(sim, curve, 4, a) == (-a) % p
+        assert _feop(sim, curve, 5, a) == a * pow(2, -1, p) % p
+        assert _feop(sim, curve, 6, a) == 3 * a % p
+        assert _feop(sim, curve, 9, a) == 8 * a % p
+        assert _feop(sim, curve, 8, a) == a % p
+    for a in vals[:30]:
+        assert _feop(sim, curve, 7, a) == (pow(a % p, -1, p) if a % p else 0)
+
+
+def test_field_mul_extremes(sim):
+    # all-ones style operands maximise every carry chain
+    xs = [2**256 - 1, 2**256 - 2**32, 0xFFFFFFFF << 224, (2**256 - 1) ^ (0xFFFFFFFF << 96), int("f0" * 32, 16), int("0f" * 32, 16)]
+    for a in xs:
+        for b in xs:
+            assert _feop(sim, "k256", 2, a, b) == a * b % pyref.K256.p
+            assert _feop(sim, "p256", 2, a, b) == a * b % pyref.P256.p
+
+
+def test_glv_split_matches_reference_definition(sim):
+    rng = random.Random(2)
+    n = pyref.K256.n
+    for k in [0, 1, 2, n - 1, n - 2, pyref.K256_LAMBDA] + [rng.randrange(n) for _ in range(1500)]:
+        out = ctypes.create_string_buffer(36)
+        assert sim.sim_k256_glv(k.to_bytes(32, "big"), out) == 0
+        k1, k2 = pyref.glv_split(k)
+        for off, kk in ((0, k1), (18, k2)):
+            h = int.from_bytes(out.raw[off:off + 16], "little")
+            neg, ev = out.raw[off + 16], out.raw[off + 17]
+            m = abs(kk)
+            assert m < 2**128 and neg == (1 if kk < 0 else 0) and ev == 1 - (m & 1) and h == (m + ev) >> 1
+
+
+def _mul(sim, fn, c, k, P):
+    xy, _ = pyref.enc_point(P)
+    out = ctypes.create_string_buffer(64)
+    inf = ctypes.create_string_buffer(1)
+    getattr(sim, fn)(k.to_bytes(32, "big"), xy, out, inf)
+    return pyref.dec_point(out.raw, inf.raw[0])
+
+
+@pytest.mark.parametrize("curve,fn", [("k256", "sim_k256_mul"), ("p256", "sim_p256_mul"), ("k256", "sim_k256_mul_generic")])
+def test_scalar_mul_thread_routine(sim, curve, fn):
+    c = pyref.CURVES[curve]
+    G = pyref.G(c)
+    rng = random.Random(13)
+    g = golden(curve)["group"]
+    for v in g["mul"]:
+        assert _mul(sim, fn, c, int(v["k"], 16), G) == (int(v["x"], 16), int(v["y"], 16))
+    for v in g["add"]:
+        assert _mul(sim, fn, c, v["k"], G) == (int(v["x"], 16), int(v["y"], 16))
+    Ps = random_points(c, 6, seed=3)
+    for i, k in enumerate(edge_scalars(c) + [rng.randrange(c.n) for _ in range(25)]):
+        P = Ps[i % 6]
+        assert _mul(sim, fn, c, k, P) == pyref.mul(c, k, P), hex(k)
+
+
+def test_on_curve_check(sim):
+    for curve in ("k256", "p256"):
+        c = pyref.CURVES[curve]
+        P = pyref.mul(c, 12345, pyref.G(c))
+        xy, _ = pyref.enc_point(P)
+        f = getattr(sim, f"sim_{curve}_on_curve")
+        assert f(xy) == 1
+        bad = bytearray(xy)
+        bad[40] ^= 4
+        assert f(bytes(bad)) == 0
