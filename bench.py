@@ -1,0 +1,416 @@
+#!/usr/bin/env python3
+"""bench.py — the measurement contract for the batched scalar-multiplication hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm  (libecgpu.so, sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU restatement of the
+                                                             # reference's own algorithm on the host cores
+  N > 1 is launched by `python -m torch.distributed.run --nproc-per-node N ...` (one rank per GPU).
+
+A "step" = one pass of the hot path over one batch: BASELINE.json configs[1], secp256k1 variable-base
+scalar multiplication of 2^20 (scalar, point) pairs per GPU (weak scaling: each rank owns its own 2^20 pairs,
+no data-path collective).  Other workloads (--workload) are the remaining BASELINE configs; they print the
+same JSON line but are not the headline.
+
+Timed regions
+  value : inputs/outputs resident in HBM (ECG_FLAG_DEVICE_PTRS), CUDA events on the launching stream,
+          K steps between barrier+synchronize, max over ranks.
+  e2e   : same metric through the host-buffer C ABI call: pinned host inputs -> H2D -> kernels -> D2H of the
+          affine results inside the timed region.
+  roofline / cpu_baseline : see DESIGN.md section "Measurement".
+"""
+import argparse
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "elliptic-curves_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np
+
+WORKLOADS = {
+    # name: (curve, op, log2 batch per GPU, BASELINE.json config index, unit noun)
+    "k256_varbase": ("k256", "mul", 20, 1, "scalar-mults/s"),
+    "p256_varbase": ("p256", "mul", 20, 2, "scalar-mults/s"),
+    "k256_fixedbase": ("k256", "mulgen", 22, 3, "scalar-mults/s"),
+    "k256_lincomb": ("k256", "lincomb", 21, 4, "terms/s"),
+}
+SEEDS = {"k256_varbase": 0xB2000001, "p256_varbase": 0xB2000002, "k256_fixedbase": 0xB2000003, "k256_lincomb": 0xB2000004}
+ALGO_BYTES = {"mul": 160, "mulgen": 96, "lincomb": 96}  # algorithmic bytes per unit
+# IMAD.WIDE (32x32->64 multiply-accumulate) instructions per unit of work, counted from the kernels' operation
+# schedule (DESIGN.md "integer roofline"): field mul/sqr = 64 product + 8 reduction (k256) / 64 (p256, the
+# Solinas reduction uses no multiplier)
+IMADW_PER_UNIT = {("k256", "mul"): 130_400, ("p256", "mul"): 206_900, ("k256", "mulgen"): 13_500, ("k256", "lincomb"): 130_400}
+
+
+def synth_scalars(curve, seed, start, count):
+    """k_i = SHA-256(seed || "k" || LE64(i)) mod n   """
+    import pyref
+
+    n = pyref.CURVES[curve].n
+    out = bytearray(32 * count)
+    pre = seed.to_bytes(8, "little")
+    for j in range(count):
+        i = start + j
+        h = hashlib.sha256(pre + b"k" + i.to_bytes(8, "little")).digest()
+        v = int.from_bytes(h, "big")
+        if v >= n:
+            v -= n
+        out[32 * j:32 * j + 32] = v.to_bytes(32, "big")
+    return np.frombuffer(bytes(out), dtype=np.uint8).copy()
+
+
+def synth_point_scalars(curve, seed, start, count):
+    """t_i = SHA-256(seed || "p" || LE64(i)) mod n, t_i != 0 ; P_i = t_i * G"""
+    import pyref
+
+    n = pyref.CURVES[curve].n
+    out = bytearray(32 * count)
+    pre = seed.to_bytes(8, "little")
+    for j in range(count):
+        i = start + j
+        h = hashlib.sha256(pre + b"p" + i.to_bytes(8, "little")).digest()
+        v = int.from_bytes(h, "big") % n
+        if v == 0:
+            v = 1
+        out[32 * j:32 * j + 32] = v.to_bytes(32, "big")
+    return np.frombuffer(bytes(out), dtype=np.uint8).copy()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(mx), "power_w_max": max(power), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    return world, rank, local
+
+
+def barrier_sync(world):
+    import torch
+
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    import torch
+
+    if world == 1:
+        return x
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_ours(args):
+    import torch
+
+    import ecgpu
+    import pyref
+
+    curve, op, logn, cfg_idx, unit = WORKLOADS[args.workload]
+    if args.log2_batch:
+        logn = args.log2_batch
+    n = 1 << logn
+    world, rank, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    seed = SEEDS[args.workload]
+    start = rank * n
+
+    # ---- synthetic inputs: scalars hashed on the host, points P_i = t_i*G made with the fixed-base kernel
+    k_host = torch.from_numpy(synth_scalars(curve, seed, start, n)).pin_memory()
+    host_eng = ecgpu.Engine([local])
+    if op != "mulgen":
+        t_host = synth_point_scalars(curve, seed, start, n)
+        pxy, pinf = host_eng.mul_by_generator(curve, t_host)
+        assert not pinf.any()
+        p_host = torch.from_numpy(np.ascontiguousarray(pxy).reshape(-1)).pin_memory()
+    else:
+        p_host = None
+    out_host = torch.empty(64 * n if op != "lincomb" else 64, dtype=torch.uint8).pin_memory()
+    oinf_host = torch.empty(n if op != "lincomb" else 1, dtype=torch.uint8).pin_memory()
+
+    kd = k_host.to(dev)
+    pd = p_host.to(dev) if p_host is not None else None
+    oxy = torch.empty(64 * n if op != "lincomb" else 64, dtype=torch.uint8, device=dev)
+    oinf = torch.empty(n if op != "lincomb" else 1, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    eng = ecgpu.Engine([local], device_ptrs=True)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def step_dev():
+        flush.zero_()  # L2 flush between timed iterations
+        if op == "mul":
+            eng.mul_batch_ptr(curve, n, kd.data_ptr(), pd.data_ptr(), 0, oxy.data_ptr(), oinf.data_ptr())
+        elif op == "mulgen":
+            eng.mul_gen_batch_ptr(curve, n, kd.data_ptr(), oxy.data_ptr(), oinf.data_ptr())
+        else:
+            eng.lincomb_ptr(curve, n, kd.data_ptr(), pd.data_ptr(), 0, oxy.data_ptr(), oinf.data_ptr())
+
+    def step_host():
+        k_np, o_np, oi_np = k_host.numpy(), out_host.numpy(), oinf_host.numpy()
+        if op == "mul":
+            host_eng.mul_batch(curve, k_np, p_host.numpy(), None, o_np, oi_np)
+        elif op == "mulgen":
+            host_eng.mul_by_generator(curve, k_np, o_np, oi_np)
+        else:
+            xy, inf = host_eng.lincomb(curve, k_np, p_host.numpy(), None)
+            o_np[:] = xy
+            oi_np[0] = inf
+
+    # ---- device-resident timing (the `value`)
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    eng.timing_enable(True)
+    launches0 = eng.kernel_launches
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier_sync(world)
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_dev()
+    ev1.record()
+    barrier_sync(world)
+    clocks = sampler.stop() if sampler else None
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1), world)
+    launches = eng.kernel_launches - launches0
+    dom_ms, dom_calls = eng.timing_read()
+    eng.timing_enable(False)
+    ms_per_step = ms_total / args.steps
+    value = world * n * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end through the host-buffer ABI (pinned host memory, H2D + D2H inside the timed region)
+    for _ in range(2):
+        step_host()
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier_sync(world)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    e2e_value = world * n * args.steps / e2e_s
+    h2d = 32 * n + (64 * n if op != "mulgen" else 0)
+    d2h = (65 * n) if op != "lincomb" else 65
+
+    # ---- device result of the last device step == host-API result (same inputs)?
+    same = bool(np.array_equal(oxy.cpu().numpy(), out_host.numpy())) and bool(np.array_equal(oinf.cpu().numpy(), oinf_host.numpy()))
+
+    line = None
+    if rank == 0:
+        # ---- integer-pipe peak measured live on this GPU
+        imadw_peak, _ = eng.microbench(0, 4000)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            hbm_peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        else:
+            hbm_peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+        dom_avg_ms = dom_ms / max(dom_calls, 1)
+        achieved_gbs = ALGO_BYTES[op] * n / (dom_avg_ms * 1e-3) / 1e9
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(prof):
+            traffic = json.load(open(prof)).get(args.workload)
+        imadw_unit = IMADW_PER_UNIT.get((curve, op))
+        roofline_int = None
+        if imadw_unit:
+            ach = imadw_unit * n / (dom_avg_ms * 1e-3)
+            roofline_int = {"bound": "int32 multiply issue (IMAD.WIDE.U32, half-rate FMA pipe)", "achieved": ach, "peak": imadw_peak,
+                            "unit": "IMAD.WIDE/s", "frac": ach / imadw_peak, "imad_wide_per_unit": imadw_unit,
+                            "peak_source": "ecg_microbench(0) in this run"}
+
+        # ---- CPU baseline: the oracle (C restatement of the reference path) on all host cores, bounded sample
+        import ecref
+
+        cores = os.cpu_count() or 1
+        ns = min(n, 1 << 18) if op != "mulgen" else min(n, 1 << 19)
+        k_s = k_host.numpy()[:32 * ns]
+        t0 = time.perf_counter()
+        if op == "mul":
+            r_xy, r_inf = ecref.mul_batch(curve, k_s, p_host.numpy()[:64 * ns], None, nthreads=cores, variant=0)
+        elif op == "mulgen":
+            r_xy, r_inf = ecref.mul_gen_batch(curve, k_s, nthreads=cores)
+        else:
+            r_xy, r_inf = ecref.lincomb(curve, k_s, p_host.numpy()[:64 * ns], None, nthreads=cores)
+        cpu_s = time.perf_counter() - t0
+        if op != "lincomb":
+            bit_exact = bool(np.array_equal(out_host.numpy()[:64 * ns], r_xy.reshape(-1))) and bool(np.array_equal(oinf_host.numpy()[:ns], r_inf))
+        else:
+            sub_xy, sub_inf = host_eng.lincomb(curve, k_s, p_host.numpy()[:64 * ns], None)
+            bit_exact = bool(np.array_equal(sub_xy, r_xy)) and sub_inf == r_inf
+        cpu_baseline = {"value": ns / cpu_s, "unit": unit, "cores": cores, "kind": "port",
+                        "sample": f"first 2^{ns.bit_length() - 1} units of the same workload, constant-time `*` path (oracle/ecref.c), {cores} threads",
+                        "bit_exact_vs_gpu": bit_exact}
+
+        line = {
+            "metric": "scalar-mults/sec (var-base, batch) at 1/2/4/8 B200 vs reference Rust CPU" if op == "mul" else f"{unit} ({args.workload})",
+            "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"BASELINE.json configs[{cfg_idx}]: {args.workload}, batch 2^{logn} per GPU", "curve": curve,
+                       "batch_per_gpu": n, "inputs": "k_i, t_i = SHA-256(seed||tag||LE64(i)) mod n; P_i = t_i*G (SURVEY 8(d))",
+                       "l2": "256 MiB buffer written between timed iterations (L2 flush); working set 288 MiB > L2",
+                       "parallelism": f"batch sharded over {world} rank(s), no data-path collective"},
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "host-buffer C ABI call, pinned host memory, copies inside the timed region", "matches_device_path": same},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel_ms": dom_avg_ms,
+                         "note": "this path is integer-issue bound, not HBM bound (160 B per 1.3e5 multiplies); see roofline_int"},
+            "roofline_int": roofline_int,
+            "cpu_baseline": cpu_baseline,
+        }
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU algorithm (C restatement, oracle/ecref.c — the Rust crate cannot be
+    built here: no rustc/cargo) on all host cores; each step = a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import ecref
+    import pyref
+
+    curve, op, logn, cfg_idx, unit = WORKLOADS[args.workload]
+    seed = SEEDS[args.workload]
+    cores = os.cpu_count() or 1
+    ns = 1 << 16  # units per step
+    k = synth_scalars(curve, seed, 0, ns)
+    if op != "mulgen":
+        t = synth_point_scalars(curve, seed, 0, ns)
+        pxy, _ = ecref.mul_gen_batch(curve, t, nthreads=cores)
+        pxy = np.ascontiguousarray(pxy).reshape(-1)
+
+    def step():
+        if op == "mul":
+            ecref.mul_batch(curve, k, pxy, None, nthreads=cores, variant=0)
+        elif op == "mulgen":
+            ecref.mul_gen_batch(curve, k, nthreads=cores)
+        else:
+            ecref.lincomb(curve, k, pxy, None, nthreads=cores)
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = ns * args.steps / dt
+    sample = f"2^16 units per step of the same workload, constant-time `*` path, {cores} threads"
+    line = {
+        "impl": "reference",
+        "metric": "scalar-mults/sec (var-base, batch) at 1/2/4/8 B200 vs reference Rust CPU" if op == "mul" else f"{unit} ({args.workload})",
+        "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"BASELINE.json configs[{cfg_idx}]: {args.workload}, batch 2^{logn} per GPU", "curve": curve,
+                   "step_sample": sample},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="k256_varbase", choices=sorted(WORKLOADS))
+    ap.add_argument("--log2-batch", type=int, default=0, help="override the per-GPU batch (development only)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

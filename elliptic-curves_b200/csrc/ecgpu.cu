@@ -496,6 +496,8 @@ struct DevState {
   uint32_t* status = nullptr;    // 2 words
   uint32_t* h_status = nullptr;  // pinned
   uint32_t* fb_table[2] = {nullptr, nullptr};  // per curve, built lazily (like the reference's LazyLock table)
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;    // bracket the dominant kernel of the last call (ecg_timing)
+  bool ev_pending = false;
   int sm_count = 148;
   cudaStream_t s() const { return use_user_stream ? user_stream : stream; }
 };
@@ -507,6 +509,9 @@ struct ecg_ctx {
   std::string err;
   size_t err_index = (size_t)-1;
   uint64_t launches = 0;
+  bool timing = false;        // ecg_timing_enable
+  double dom_ms_sum = 0;      // accumulated device time of the dominant kernel (max over devices per call)
+  uint64_t dom_calls = 0;
 };
 
 #define CU_TRY(ctx, call)                                                                                    \
@@ -561,7 +566,8 @@ extern "C" ecg_status ecg_ctx_create(const int* device_ids, int n_devices, unsig
       return ECG_EINVAL;
     }
     if (cudaSetDevice(d.dev) != cudaSuccess || cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc((void**)&d.status, 8) != cudaSuccess || cudaMallocHost((void**)&d.h_status, 8) != cudaSuccess) {
+        cudaMalloc((void**)&d.status, 8) != cudaSuccess || cudaMallocHost((void**)&d.h_status, 8) != cudaSuccess ||
+        cudaEventCreate(&d.ev0) != cudaSuccess || cudaEventCreate(&d.ev1) != cudaSuccess) {
       delete ctx;
       return ECG_ECUDA;
     }
@@ -586,6 +592,8 @@ extern "C" void ecg_ctx_destroy(ecg_ctx* ctx) {
       if (d.fb_table[i]) cudaFree(d.fb_table[i]);
     if (d.status) cudaFree(d.status);
     if (d.h_status) cudaFreeHost(d.h_status);
+    if (d.ev0) cudaEventDestroy(d.ev0);
+    if (d.ev1) cudaEventDestroy(d.ev1);
   }
   delete ctx;
 }
@@ -593,6 +601,20 @@ extern "C" void ecg_ctx_destroy(ecg_ctx* ctx) {
 extern "C" const char* ecg_last_error(const ecg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 extern "C" size_t ecg_last_error_index(const ecg_ctx* ctx) { return ctx ? ctx->err_index : (size_t)-1; }
 extern "C" uint64_t ecg_kernel_launches(const ecg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" ecg_status ecg_timing_enable(ecg_ctx* ctx, int on) {
+  if (!ctx) return ECG_EINVAL;
+  ctx->timing = on != 0;
+  ctx->dom_ms_sum = 0;
+  ctx->dom_calls = 0;
+  return ECG_OK;
+}
+extern "C" ecg_status ecg_timing_read(const ecg_ctx* ctx, double* dominant_kernel_ms_sum, uint64_t* calls) {
+  if (!ctx || !dominant_kernel_ms_sum || !calls) return ECG_EINVAL;
+  *dominant_kernel_ms_sum = ctx->dom_ms_sum;
+  *calls = ctx->dom_calls;
+  return ECG_OK;
+}
 
 extern "C" ecg_status ecg_ctx_set_stream(ecg_ctx* ctx, void* cuda_stream) {
   if (!ctx) return ECG_EINVAL;
@@ -671,6 +693,8 @@ static ecg_status reset_status(ecg_ctx* ctx, DevState& d) {
 static ecg_status finish(ecg_ctx* ctx, const std::vector<Shard>& shards) {
   ecg_status rc = ECG_OK;
   size_t first = (size_t)-1;
+  float dom_ms = 0;
+  bool any_timed = false;
   for (size_t i = 0; i < ctx->devs.size(); i++) {
     DevState& d = ctx->devs[i];
     if (shards[i].cnt == 0) continue;
@@ -678,6 +702,12 @@ static ecg_status finish(ecg_ctx* ctx, const std::vector<Shard>& shards) {
     CU_TRY(ctx, cudaMemcpyAsync(d.h_status, d.status, 8, cudaMemcpyDeviceToHost, d.s()));
     CU_TRY(ctx, cudaStreamSynchronize(d.s()));
     CU_TRY(ctx, cudaGetLastError());
+    if (d.ev_pending) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, d.ev0, d.ev1) == cudaSuccess && ms > dom_ms) dom_ms = ms;
+      d.ev_pending = false;
+      any_timed = true;
+    }
     if (d.h_status[0]) {
       size_t idx = shards[i].off + d.h_status[1];
       if (idx < first) {
@@ -685,6 +715,10 @@ static ecg_status finish(ecg_ctx* ctx, const std::vector<Shard>& shards) {
         rc = (d.h_status[0] & ERRF_POINT) ? ECG_ENOT_ON_CURVE : ECG_ESCALAR_RANGE;
       }
     }
+  }
+  if (any_timed) {
+    ctx->dom_ms_sum += dom_ms;
+    ctx->dom_calls++;
   }
   if (rc != ECG_OK) {
     ctx->err_index = first;
@@ -698,6 +732,19 @@ static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n
   do {                                 \
     (ctx)->launches++;                 \
     CU_TRY(ctx, cudaGetLastError());   \
+  } while (0)
+
+// CUDA events around the dominant kernel of a call, on the launching stream (bench.py's roofline numerator)
+#define DOM_BEGIN(ctx, d)                                           \
+  do {                                                              \
+    if ((ctx)->timing) CU_TRY(ctx, cudaEventRecord((d).ev0, (d).s())); \
+  } while (0)
+#define DOM_END(ctx, d)                                             \
+  do {                                                              \
+    if ((ctx)->timing) {                                            \
+      CU_TRY(ctx, cudaEventRecord((d).ev1, (d).s()));               \
+      (d).ev_pending = true;                                        \
+    }                                                               \
   } while (0)
 
 template <class F>
@@ -723,6 +770,7 @@ static ecg_status set_smem(ecg_ctx* ctx, KernelT kernel, size_t smem) {
 
 // k*P for one shard -> Jacobian SoA in `jac`
 static ecg_status launch_varbase(ecg_ctx* ctx, DevState& d, ecg_curve curve, size_t n, const DevPtrs& dp, uint32_t* jac) {
+  DOM_BEGIN(ctx, d);
   if (curve == ECG_SECP256K1) {
     size_t smem = (size_t)K_BLOCK * 8 * 16 * 4;
     ST_TRY(set_smem(ctx, k256_varbase_kernel<K_BLOCK, K_MINBLK>, smem));
@@ -733,6 +781,7 @@ static ecg_status launch_varbase(ecg_ctx* ctx, DevState& d, ecg_curve curve, siz
     generic_varbase_kernel<CurveP256, P_BLOCK, P_MINBLK><<<grid_for(n, P_BLOCK), P_BLOCK, smem, d.s()>>>(dp.k, dp.p, dp.inf, n, jac, d.status);
   }
   LAUNCHED(ctx);
+  DOM_END(ctx, d);
   return ECG_OK;
 }
 static ecg_status launch_norm(ecg_ctx* ctx, DevState& d, ecg_curve curve, size_t n, const uint32_t* jac, uint8_t* out, uint8_t* oinf) {
@@ -845,9 +894,12 @@ static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
   CU_TRY(ctx, cudaMalloc((void**)&st, 8));
   CU_TRY(ctx, cudaMemsetAsync(st, 0, 8, d.s()));
   uint32_t* saved = d.status;
+  bool saved_timing = ctx->timing;
+  ctx->timing = false;
   d.status = st;
   ecg_status rc = launch_varbase(ctx, d, curve, np, dp, jac);
   d.status = saved;
+  ctx->timing = saved_timing;
   if (rc != ECG_OK) return rc;
   size_t want_threads = std::max<size_t>((np + 31) / 32, std::min<size_t>(np, (size_t)d.sm_count * 256));
   if (curve == ECG_SECP256K1) {
@@ -893,11 +945,13 @@ extern "C" ecg_status ecg_mul_gen_batch(ecg_ctx* ctx, ecg_curve curve, size_t n,
     ST_TRY(stage_out(ctx, d, sh, out_xy, 64, out_inf, dps[i]));
     ST_TRY(ensure(ctx, d, B_JAC, sh.cnt * 96));
     uint32_t* jac = (uint32_t*)d.buf[B_JAC];
+    DOM_BEGIN(ctx, d);
     if (curve == ECG_SECP256K1)
       fixedbase_kernel<CurveK256><<<grid_for(sh.cnt, 128), 128, 0, d.s()>>>(dps[i].k, sh.cnt, d.fb_table[curve], jac, d.status);
     else
       fixedbase_kernel<CurveP256><<<grid_for(sh.cnt, 128), 128, 0, d.s()>>>(dps[i].k, sh.cnt, d.fb_table[curve], jac, d.status);
     LAUNCHED(ctx);
+    DOM_END(ctx, d);
     ST_TRY(launch_norm(ctx, d, curve, sh.cnt, jac, dps[i].out, dps[i].oinf));
     ST_TRY(copy_back(ctx, d, sh, out_xy, 64, out_inf, dps[i]));
   }

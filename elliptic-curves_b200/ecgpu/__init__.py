@@ -36,7 +36,7 @@ EXPORTS = [
     "ecg_ctx_create", "ecg_ctx_destroy", "ecg_last_error", "ecg_last_error_index", "ecg_ctx_set_stream",
     "ecg_mul_batch", "ecg_mul_gen_batch", "ecg_lincomb", "ecg_lincomb_partial", "ecg_point_sum",
     "ecg_mul_gen_add_batch", "ecg_batch_normalize", "ecg_field_op_batch", "ecg_microbench",
-    "ecg_kernel_launches", "ecg_version",
+    "ecg_kernel_launches", "ecg_version", "ecg_timing_enable", "ecg_timing_read",
 ]
 
 
@@ -98,6 +98,10 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.ecg_microbench.restype = ctypes.c_int
     lib.ecg_kernel_launches.argtypes = [vp]
     lib.ecg_kernel_launches.restype = ctypes.c_uint64
+    lib.ecg_timing_enable.argtypes = [vp, ctypes.c_int]
+    lib.ecg_timing_enable.restype = ctypes.c_int
+    lib.ecg_timing_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
+    lib.ecg_timing_read.restype = ctypes.c_int
     lib.ecg_version.argtypes = []
     lib.ecg_version.restype = ctypes.c_char_p
     if path is None:
@@ -259,6 +263,19 @@ class Engine:
 
     def lincomb_partial_ptr(self, curve, n, k, P_xy, P_inf, out_xyz):
         self._check(self.lib.ecg_lincomb_partial(self._ctx, CURVE_IDS[curve], n, _ptr(k), _ptr(P_xy), _ptr(P_inf), _ptr(out_xyz)))
+
+    def lincomb_ptr(self, curve, n, k, P_xy, P_inf, out_xy, out_inf):
+        self._check(self.lib.ecg_lincomb(self._ctx, CURVE_IDS[curve], n, _ptr(k), _ptr(P_xy), _ptr(P_inf), _ptr(out_xy), _ptr(out_inf)))
+
+    def timing_enable(self, on: bool = True):
+        self._check(self.lib.ecg_timing_enable(self._ctx, 1 if on else 0))
+
+    def timing_read(self):
+        """(accumulated ms of the dominant kernel, number of calls) since timing_enable"""
+        ms = ctypes.c_double(0)
+        calls = ctypes.c_uint64(0)
+        self._check(self.lib.ecg_timing_read(self._ctx, ctypes.byref(ms), ctypes.byref(calls)))
+        return ms.value, int(calls.value)
 
     def microbench(self, which: int, iters: int = 2000):
         ops = ctypes.c_double(0)

@@ -126,6 +126,12 @@ ecg_status ecg_field_op_batch(ecg_ctx* ctx, ecg_curve curve, int op, size_t n, c
  * of the named kind, or field multiplications for 3/4). */
 ecg_status ecg_microbench(ecg_ctx* ctx, int which, int iters, double* ops_per_s, double* elapsed_ms);
 
+/* When enabled, every call brackets its dominant kernel (variable-base / fixed-base scalar multiplication)
+ * with CUDA events on the launching stream; ecg_timing_read returns the accumulated device milliseconds
+ * (max over the ctx's devices per call) and the number of calls since ecg_timing_enable. */
+ecg_status ecg_timing_enable(ecg_ctx* ctx, int on);
+ecg_status ecg_timing_read(const ecg_ctx* ctx, double* dominant_kernel_ms_sum, uint64_t* calls);
+
 /* number of CUDA kernels this ctx has launched since creation */
 uint64_t ecg_kernel_launches(const ecg_ctx* ctx);
 
