@@ -43,10 +43,12 @@ WORKLOADS = {
 }
 SEEDS = {"k256_varbase": 0xB2000001, "p256_varbase": 0xB2000002, "k256_fixedbase": 0xB2000003, "k256_lincomb": 0xB2000004}
 ALGO_BYTES = {"mul": 160, "mulgen": 96, "lincomb": 96}  # algorithmic bytes per unit
-# IMAD.WIDE (32x32->64 multiply-accumulate) instructions per unit of work, counted from the kernels' operation
-# schedule (DESIGN.md "integer roofline"): field mul/sqr = 64 product + 8 reduction (k256) / 64 (p256, the
-# Solinas reduction uses no multiplier)
-IMADW_PER_UNIT = {("k256", "mul"): 130_400, ("p256", "mul"): 206_900, ("k256", "mulgen"): 13_500, ("k256", "lincomb"): 130_400}
+# IMAD.WIDE (32x32->64 multiply-accumulate) instructions per unit of work in the dominant kernel, counted from
+# the kernels' operation schedule (derivation: DESIGN.md "Integer roofline"):
+#   k256: M = 64 + 8 (product + reduction), S = 36 + 8;  var-base = 1046 M + 748 S + 129 mul_small*8 + GLV ~200
+#   p256: M = 64, S = 36 (Solinas reduction uses no multiplier); var-base = 1885 M + 1316 S + 258*8
+#   k256 fixed-base: 17 mixed additions = 136 M + 51 S
+IMADW_PER_UNIT = {("k256", "mul"): 109_500, ("p256", "mul"): 170_100, ("k256", "mulgen"): 12_000, ("k256", "lincomb"): 109_500}
 
 
 def synth_scalars(curve, seed, start, count):
@@ -95,6 +97,10 @@ class ClockSampler:
         self.proc = None
         self.thread = None
 
+    def mark(self):
+        """index of the next sample (call at the start / end of the timed region)"""
+        return len(self.rows)
+
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -109,7 +115,7 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
-    def stop(self):
+    def stop(self, lo=0, hi=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -118,7 +124,8 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
-        for r in self.rows:
+        rows = self.rows[lo:hi] if (hi is not None and hi - lo >= 3) else self.rows
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -235,21 +242,22 @@ def run_ours(args):
             oi_np[0] = inf
 
     # ---- device-resident timing (the `value`)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_dev()
     eng.timing_enable(True)
     launches0 = eng.kernel_launches
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier_sync(world)
-    if sampler:
-        sampler.start()
+    m0 = sampler.mark() if sampler else 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
         step_dev()
     ev1.record()
     barrier_sync(world)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(m0, sampler.mark()) if sampler else None
     ms_total = max_over_ranks(ev0.elapsed_time(ev1), world)
     launches = eng.kernel_launches - launches0
     dom_ms, dom_calls = eng.timing_read()
@@ -400,7 +408,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="k256_varbase", choices=sorted(WORKLOADS))

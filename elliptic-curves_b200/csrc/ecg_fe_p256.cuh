@@ -13,7 +13,19 @@
 
 namespace ecg {
 
-struct FpP256 {
+#ifndef ECG_P256_OPT
+#define ECG_P256_OPT 3  // bit 0: dedicated squaring; bit 1: mul/sqr as real device functions (see ecg_fe_k256.cuh)
+#endif
+#ifndef ECG_NOINLINE_D
+#if defined(__CUDA_ARCH__) || defined(__CUDACC__)
+#define ECG_NOINLINE_D __device__ __noinline__
+#else
+#define ECG_NOINLINE_D
+#endif
+#endif
+
+template <int OPT>
+struct FpP256T {
   ECG_D static void set_zero(Fe& r) {
 #pragma unroll
     for (int i = 0; i < 8; i++) r.v[i] = 0;
@@ -116,15 +128,40 @@ struct FpP256 {
     for (int i = 0; i < 8; i++) r.v[i] = o[i];
   }
 
-  ECG_D static void mul(Fe& r, const Fe& a, const Fe& b) {
+  ECG_D static void mul_body(Fe& r, const Fe& a, const Fe& b) {
     uint32_t t[16];
     mul8x8(t, a.v, b.v);
     reduce16(r, t);
   }
-  ECG_D static void sqr(Fe& r, const Fe& a) {
+  ECG_D static void sqr_body(Fe& r, const Fe& a) {
     uint32_t t[16];
-    mul8x8(t, a.v, a.v);
+    if (OPT & 1)
+      sqr8(t, a.v);
+    else
+      mul8x8(t, a.v, a.v);
     reduce16(r, t);
+  }
+  static ECG_NOINLINE_D Fe mul_call(Fe a, Fe b) {
+    Fe r;
+    mul_body(r, a, b);
+    return r;
+  }
+  static ECG_NOINLINE_D Fe sqr_call(Fe a) {
+    Fe r;
+    sqr_body(r, a);
+    return r;
+  }
+  ECG_D static void mul(Fe& r, const Fe& a, const Fe& b) {
+    if (OPT & 2)
+      r = mul_call(a, b);
+    else
+      mul_body(r, a, b);
+  }
+  ECG_D static void sqr(Fe& r, const Fe& a) {
+    if (OPT & 2)
+      r = sqr_call(a);
+    else
+      sqr_body(r, a);
   }
   ECG_D static void add(Fe& r, const Fe& a, const Fe& b) {
     uint32_t c = add8(r.v, a.v, b.v);
@@ -221,5 +258,7 @@ struct FpP256 {
   ECG_D static void from_canonical(Fe& r, const Fe& a) { r = a; }
   ECG_D static void to_canonical(Fe& r, const Fe& a) { normalize(r, a); }
 };
+
+typedef FpP256T<ECG_P256_OPT> FpP256;
 
 }  // namespace ecg

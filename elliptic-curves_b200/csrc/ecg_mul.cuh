@@ -110,8 +110,8 @@ ECG_D void build_table_iso_a0(const TabRef& tab, Fe& Zg, const Aff& P) {
 // secp256k1: r = k*P (Jacobian, true curve).  k: 8 LE limbs, k < n.  P: affine, on curve, not identity.
 // GLV split -> two 128-bit halves -> 32 shared windows of (4 dbl + 2 madd); the lambda-half reuses the
 // same table through (x,y) -> (beta x, y) (ProjectivePoint::endomorphism, projective.rs:241-247).
+template <class F = FpK256>
 ECG_D void k256_mul_thread(Jac& r, const uint32_t* k, const Aff& P, const TabRef& tab) {
-  typedef FpK256 F;
   GlvHalf g1, g2;
   glv_split_k256(g1, g2, k);
   Fe Zg, beta;

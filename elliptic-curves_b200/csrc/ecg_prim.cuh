@@ -75,6 +75,12 @@ ECG_D void madc_wide_top(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
                : "+r"(lo), "=r"(hi)
                : "r"(a), "r"(b));
 }
+// lo += lo32(a*b) ; hi = hi32(a*b) + carry       (one-product chain on a live low limb and a fresh top limb)
+ECG_D void mad_wide_top(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, 0;"
+               : "+r"(lo), "=r"(hi)
+               : "r"(a), "r"(b));
+}
 // lo = lo32(a*b) + CF ; hi = hi32(a*b) + carry    (both limbs fresh)
 ECG_D void madc_wide_new(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
   asm volatile("madc.lo.cc.u32 %0, %2, %3, 0;\n\tmadc.hi.u32 %1, %2, %3, 0;"
@@ -82,6 +88,7 @@ ECG_D void madc_wide_new(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
                : "r"(a), "r"(b));
 }
 ECG_D uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
+ECG_D uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_l(lo, hi, s); }
 ECG_D uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
 
 #else  // ---------------------------------------------------------------- host emulation (tests only)
@@ -143,9 +150,19 @@ inline void madc_wide_new(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
   lo = (uint32_t)s0;
   hi = (uint32_t)(p >> 32) + (uint32_t)(s0 >> 32);
 }
+inline void mad_wide_top(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  uint64_t p = (uint64_t)a * b;
+  uint64_t s0 = (uint64_t)lo + (uint32_t)p;
+  lo = (uint32_t)s0;
+  hi = (uint32_t)(p >> 32) + (uint32_t)(s0 >> 32);
+}
 inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
   s &= 31;
   return s ? (lo >> s) | (hi << (32 - s)) : lo;
+}
+inline uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) {  // high word of ((hi:lo) << s)
+  s &= 31;
+  return s ? (hi << s) | (lo >> (32 - s)) : hi;
 }
 inline uint32_t bswap32(uint32_t x) { return __builtin_bswap32(x); }
 
@@ -219,6 +236,72 @@ ECG_D void mul8x8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 #pragma unroll
   for (int k = 2; k < 15; k++) r[k] = addc_cc(E[k], O[k - 1]);
   r[15] = addc(E[15], O[14]);
+}
+
+// 8-limb square -> 16 limbs: the 28 cross products a_i*a_j (i<j) once, in the same even/odd pair layout
+// (rows are triangular, so chains shorten), doubled by a 1-bit funnel shift, and the 8 diagonal squares
+// accumulated on top with one IMAD.WIDE.X chain.  36 IMAD.WIDE instead of 64.
+ECG_D void sqr8(uint32_t* r, const uint32_t* a) {
+  uint32_t E[14], O[14];
+  // row 0: a0 * a[1..7]  (all limbs fresh, independent products)
+  mul_wide(O[0], O[1], a[0], a[1]);
+  mul_wide(E[2], E[3], a[0], a[2]);
+  mul_wide(O[2], O[3], a[0], a[3]);
+  mul_wide(E[4], E[5], a[0], a[4]);
+  mul_wide(O[4], O[5], a[0], a[5]);
+  mul_wide(E[6], E[7], a[0], a[6]);
+  mul_wide(O[6], O[7], a[0], a[7]);
+  // row 1: a1 * a[2..7]: odd positions 3,5,7 -> O[2..7]; even positions 4,6,8 -> E[4..9]
+  mad_wide_cc(O[2], O[3], a[1], a[2]);
+  madc_wide_cc(O[4], O[5], a[1], a[4]);
+  madc_wide_cc(O[6], O[7], a[1], a[6]);
+  O[8] = addc(0, 0);
+  mad_wide_cc(E[4], E[5], a[1], a[3]);
+  madc_wide_cc(E[6], E[7], a[1], a[5]);
+  madc_wide_new(E[8], E[9], a[1], a[7]);
+  // row 2: a2 * a[3..7]: odd positions 5,7,9 -> O[4..9]; even positions 6,8 -> E[6..9]
+  mad_wide_cc(O[4], O[5], a[2], a[3]);
+  madc_wide_cc(O[6], O[7], a[2], a[5]);
+  madc_wide_top(O[8], O[9], a[2], a[7]);
+  mad_wide_cc(E[6], E[7], a[2], a[4]);
+  madc_wide_cc(E[8], E[9], a[2], a[6]);
+  E[10] = addc(0, 0);
+  // row 3: a3 * a[4..7]: odd positions 7,9 -> O[6..9]; even positions 8,10 -> E[8..11]
+  mad_wide_cc(O[6], O[7], a[3], a[4]);
+  madc_wide_cc(O[8], O[9], a[3], a[6]);
+  O[10] = addc(0, 0);
+  mad_wide_cc(E[8], E[9], a[3], a[5]);
+  madc_wide_top(E[10], E[11], a[3], a[7]);
+  // row 4: a4 * a[5..7]: odd positions 9,11 -> O[8..11]; even position 10 -> E[10..11]
+  mad_wide_cc(O[8], O[9], a[4], a[5]);
+  madc_wide_top(O[10], O[11], a[4], a[7]);
+  mad_wide_cc(E[10], E[11], a[4], a[6]);
+  E[12] = addc(0, 0);
+  // row 5: a5 * a[6..7]: odd position 11 -> O[10..11]; even position 12 -> E[12..13]
+  mad_wide_cc(O[10], O[11], a[5], a[6]);
+  O[12] = addc(0, 0);
+  mad_wide_top(E[12], E[13], a[5], a[7]);
+  // row 6: a6 * a7: odd position 13 -> O[12..13]
+  mad_wide_top(O[12], O[13], a[6], a[7]);
+  // merge: S = E + (O << 32), limbs 1..14  (S[0] = 0, E[0] = E[1] = 0)
+  uint32_t S[16];
+  S[0] = 0;
+  S[1] = O[0];
+  S[2] = add_cc(E[2], O[1]);
+#pragma unroll
+  for (int k = 3; k < 14; k++) S[k] = addc_cc(E[k], O[k - 1]);
+  S[14] = addc(0, O[13]);
+  // double (1-bit left funnel) and add the diagonal squares with one carry chain of IMAD.WIDE.X
+  uint32_t T[16];
+  T[15] = S[14] >> 31;
+#pragma unroll
+  for (int k = 14; k >= 1; k--) T[k] = funnel_l(S[k - 1], S[k], 1);
+  T[0] = 0;
+  mad_wide_cc(T[0], T[1], a[0], a[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) madc_wide_cc(T[2 * i], T[2 * i + 1], a[i], a[i]);
+#pragma unroll
+  for (int k = 0; k < 16; k++) r[k] = T[k];
 }
 
 }  // namespace ecg

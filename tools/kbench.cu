@@ -1,0 +1,136 @@
+// tools/kbench.cu — development harness: times kernel variants of the secp256k1 variable-base path on one GPU
+// and cross-checks that every variant produces identical Jacobian words.  Not part of the product or of bench.py.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tools/kbench tools/kbench.cu
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+#define ECG_K256_OPT 3
+#include "../elliptic-curves_b200/csrc/ecg_curves.cuh"
+#include "../elliptic-curves_b200/csrc/ecg_io.cuh"
+#include "../elliptic-curves_b200/csrc/ecg_mul.cuh"
+using namespace ecg;
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+__device__ __forceinline__ void make_inputs(uint32_t* k, Aff& P, size_t idx) {
+  // deterministic pseudo-random scalar < 2^255 ; P = G
+  uint32_t s = (uint32_t)idx * 2654435761u + 12345u;
+  for (int i = 0; i < 8; i++) { s = s * 1664525u + 1013904223u; k[i] = s ^ (s >> 15); }
+  k[7] &= 0x7FFFFFFFu;
+  CurveK256::generator(P);
+}
+
+template <class F, int BLOCK, int MINBLK, bool GLOBAL_TAB>
+__global__ void __launch_bounds__(BLOCK, MINBLK) kb_varbase(size_t n, uint32_t* __restrict__ jac, uint32_t* __restrict__ gtab) {
+  extern __shared__ uint32_t smem[];
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n) return;
+  uint32_t k[8];
+  Aff P;
+  make_inputs(k, P, idx);
+  Jac r;
+  if (GLOBAL_TAB) {
+    // per-resident-thread table slot in global memory (L2-resident): [entry*16+word][thread] layout per block slot
+    size_t slot = ((size_t)blockIdx.x % (148 * 8)) * BLOCK;  // NOTE: timing experiment only (slots may alias across waves)
+    TabRef tab{gtab + slot * 128 + threadIdx.x, (uint32_t)BLOCK};
+    k256_mul_thread<F>(r, k, P, tab);
+  } else {
+    TabRef tab{smem + threadIdx.x, (uint32_t)BLOCK};
+    k256_mul_thread<F>(r, k, P, tab);
+  }
+  for (int w = 0; w < 8; w++) {
+    jac[(size_t)w * n + idx] = r.X.v[w];
+    jac[(size_t)(8 + w) * n + idx] = r.Y.v[w];
+    jac[(size_t)(16 + w) * n + idx] = r.Z.v[w];
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) kb_fmul(uint32_t* out, int iters, uint32_t seed, int mode) {
+  Fe a, b;
+  for (int i = 0; i < 8; i++) { a.v[i] = seed * (i + 1) + threadIdx.x; b.v[i] = (seed ^ 0x9E3779B9u) * (i + 3) + blockIdx.x; }
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    if (mode == 0) { F::mul(a, a, b); F::mul(b, b, a); }
+    else { F::sqr(a, a); F::sqr(b, b); }
+  }
+  uint32_t s = 0;
+  for (int i = 0; i < 8; i++) s ^= a.v[i] ^ b.v[i];
+  if (s == 0x12345678u) out[0] = s;
+}
+
+static uint64_t checksum(const std::vector<uint32_t>& v) {
+  uint64_t h = 1469598103934665603ull;
+  for (uint32_t x : v) { h ^= x; h *= 1099511628211ull; }
+  return h;
+}
+
+template <class F, int BLOCK, int MINBLK, bool GLOBAL_TAB>
+static void run(const char* name, size_t n, uint32_t* jac, uint32_t* gtab) {
+  size_t smem = GLOBAL_TAB ? 0 : (size_t)BLOCK * 128 * 4;
+  auto kern = kb_varbase<F, BLOCK, MINBLK, GLOBAL_TAB>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, kern));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem));
+  unsigned grid = (unsigned)((n + BLOCK - 1) / BLOCK);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(e0));
+    kern<<<grid, BLOCK, smem>>>(n, jac, gtab);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  std::vector<uint32_t> h(24 * 4096);
+  // sample: first 4096 elements of each word row
+  for (int w = 0; w < 24; w++) CK(cudaMemcpy(&h[w * 4096], jac + (size_t)w * n, 4096 * 4, cudaMemcpyDeviceToHost));
+  printf("%-34s regs %3d  blocks/SM %d  warps/SM %2d  %8.3f ms  %.4g mults/s  chk %016llx\n", name, fa.numRegs, occ, occ * BLOCK / 32, best,
+         n / (best * 1e-3), (unsigned long long)checksum(h));
+}
+
+template <class F>
+static void run_fmul(const char* name) {
+  uint32_t* out; CK(cudaMalloc(&out, 256));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int mode = 0; mode < 2; mode++) {
+    float best = 1e30f; int iters = 4000; unsigned blocks = 148 * 8;
+    for (int rep = 0; rep < 3; rep++) {
+      CK(cudaEventRecord(e0));
+      kb_fmul<F><<<blocks, 256>>>(out, iters, 777u + rep, mode);
+      CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+      float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+      if (rep > 0 && ms < best) best = ms;
+    }
+    printf("%-34s %s: %.4g field-ops/s\n", name, mode ? "sqr" : "mul", (double)blocks * 256 * iters * 2 / (best * 1e-3));
+  }
+}
+
+int main(int argc, char** argv) {
+  size_t n = (size_t)1 << (argc > 1 ? atoi(argv[1]) : 20);
+  uint32_t *jac, *gtab;
+  CK(cudaMalloc(&jac, n * 96));
+  CK(cudaMalloc(&gtab, (size_t)148 * 8 * 256 * 128 * 4));
+  printf("n = %zu\n", n);
+  run_fmul<FpK256T<0>>("fmul inline mul8x8");
+  run_fmul<FpK256T<1>>("fmul inline sqr8");
+  run_fmul<FpK256T<3>>("fmul call sqr8");
+  run<FpK256T<0>, 128, 3, false>("v0 inline, sqr=mul   (128,3) smem", n, jac, gtab);
+  run<FpK256T<1>, 128, 3, false>("v1 inline, sqr8      (128,3) smem", n, jac, gtab);
+  run<FpK256T<2>, 128, 3, false>("v2 call,   sqr=mul   (128,3) smem", n, jac, gtab);
+  run<FpK256T<3>, 128, 3, false>("v3 call,   sqr8      (128,3) smem", n, jac, gtab);
+  run<FpK256T<3>, 192, 2, false>("v3 call,   sqr8      (192,2) smem", n, jac, gtab);
+  run<FpK256T<3>, 96, 4, false>("v3 call,   sqr8      (96,4)  smem", n, jac, gtab);
+  run<FpK256T<3>, 64, 7, false>("v3 call,   sqr8      (64,7)  smem", n, jac, gtab);
+  run<FpK256T<3>, 128, 4, true>("v3 call,   sqr8      (128,4) gtab", n, jac, gtab);
+  run<FpK256T<3>, 128, 5, true>("v3 call,   sqr8      (128,5) gtab", n, jac, gtab);
+  run<FpK256T<3>, 256, 2, true>("v3 call,   sqr8      (256,2) gtab", n, jac, gtab);
+  run<FpK256T<1>, 128, 4, true>("v1 inline, sqr8      (128,4) gtab", n, jac, gtab);
+  return 0;
+}
