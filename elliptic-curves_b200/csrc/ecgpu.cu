@@ -78,7 +78,7 @@ template <int BLOCK, int MINBLK>
 __global__ void __launch_bounds__(BLOCK, MINBLK)
     k256_varbase_kernel(const uint8_t* __restrict__ kb, const uint8_t* __restrict__ pxy,
                         const uint8_t* __restrict__ pinf, size_t n, uint32_t* __restrict__ jac,
-                        uint32_t* __restrict__ status) {
+                        uint32_t* __restrict__ status, size_t base) {
   extern __shared__ uint32_t smem[];
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   if (idx >= n) return;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(BLOCK, MINBLK)
   Aff P;
   bool inf;
   uint32_t err = load_pair<CurveK256>(k, P, inf, kb, pxy, pinf, idx);
-  if (err) report_error(status, err, idx);
+  if (err) report_error(status, err, base + idx);
   TabRef tab{smem + threadIdx.x, (uint32_t)BLOCK};
   Jac r;
   k256_mul_thread(r, k, P, tab);
@@ -102,7 +102,7 @@ template <class C, int BLOCK, int MINBLK>
 __global__ void __launch_bounds__(BLOCK, MINBLK)
     generic_varbase_kernel(const uint8_t* __restrict__ kb, const uint8_t* __restrict__ pxy,
                            const uint8_t* __restrict__ pinf, size_t n, uint32_t* __restrict__ jac,
-                           uint32_t* __restrict__ status) {
+                           uint32_t* __restrict__ status, size_t base) {
   typedef typename C::F F;
   extern __shared__ uint32_t smem[];
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(BLOCK, MINBLK)
   Aff P;
   bool inf;
   uint32_t err = load_pair<C>(k, P, inf, kb, pxy, pinf, idx);
-  if (err) report_error(status, err, idx);
+  if (err) report_error(status, err, base + idx);
   TabRefJ tab{smem + threadIdx.x, (uint32_t)BLOCK};
   Jac r;
   generic_mul_thread<F, C::A_IS_MINUS3>(r, k, P, tab);
@@ -180,7 +180,7 @@ __device__ __forceinline__ void fixedbase_accumulate(Jac& acc, const uint32_t* k
 template <class C>
 __global__ void __launch_bounds__(128, 4)
     fixedbase_kernel(const uint8_t* __restrict__ kb, size_t n, const uint32_t* __restrict__ table,
-                     uint32_t* __restrict__ jac, uint32_t* __restrict__ status) {
+                     uint32_t* __restrict__ jac, uint32_t* __restrict__ status, size_t base) {
   typedef typename C::F F;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(128, 4)
   load_be32(k, kb + 32 * idx);
   bool bad = !lt8(k, C::N());
   if (bad) {
-    report_error(status, ERRF_SCALAR, idx);
+    report_error(status, ERRF_SCALAR, base + idx);
 #pragma unroll
     for (int i = 0; i < 8; i++) k[i] = (i == 0);
   }
@@ -206,7 +206,7 @@ template <class C, int BLOCK, int MINBLK, bool IS_K256>
 __global__ void __launch_bounds__(BLOCK, MINBLK)
     mul_gen_add_kernel(const uint8_t* __restrict__ ab, const uint8_t* __restrict__ kb,
                        const uint8_t* __restrict__ pxy, const uint8_t* __restrict__ pinf, size_t n,
-                       const uint32_t* __restrict__ table, uint32_t* __restrict__ jac, uint32_t* __restrict__ status) {
+                       const uint32_t* __restrict__ table, uint32_t* __restrict__ jac, uint32_t* __restrict__ status, size_t base) {
   typedef typename C::F F;
   extern __shared__ uint32_t smem[];
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(BLOCK, MINBLK)
   uint32_t err = load_pair<C>(k, P, inf, kb, pxy, pinf, idx);
   load_be32(a, ab + 32 * idx);
   if (!lt8(a, C::N())) err |= ERRF_SCALAR;
-  if (err) report_error(status, err, idx);
+  if (err) report_error(status, err, base + idx);
   Jac r;
   if (IS_K256) {
     TabRef tab{smem + threadIdx.x, (uint32_t)BLOCK};
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(256)
 template <class C>
 __global__ void __launch_bounds__(256)
     import_jac_kernel(const uint8_t* __restrict__ xyz, size_t n, uint32_t* __restrict__ jac,
-                      uint32_t* __restrict__ status) {
+                      uint32_t* __restrict__ status, size_t base) {
   typedef typename C::F F;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(256)
   for (int c = 0; c < 3; c++) {
     Fe v, w;
     load_be32(v.v, xyz + 96 * idx + 32 * c);
-    if (!lt8(v.v, C::P())) report_error(status, ERRF_POINT, idx);
+    if (!lt8(v.v, C::P())) report_error(status, ERRF_POINT, base + idx);
     F::from_canonical(w, v);
     soa_store<8>(jac, n, idx, w.v, 8 * c);
   }
@@ -369,18 +369,18 @@ __global__ void __launch_bounds__(256)
 template <class C>
 __global__ void __launch_bounds__(256)
     field_op_kernel(int op, size_t n, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
-                    uint8_t* __restrict__ out, uint32_t* __restrict__ status) {
+                    uint8_t* __restrict__ out, uint32_t* __restrict__ status, size_t base) {
   typedef typename C::F F;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   Fe x, y, r;
   load_be32(x.v, a + 32 * idx);
-  if (!lt8(x.v, C::P())) report_error(status, ERRF_POINT, idx);
+  if (!lt8(x.v, C::P())) report_error(status, ERRF_POINT, base + idx);
   F::from_canonical(x, x);
   bool binary = (op == ECG_FOP_ADD || op == ECG_FOP_SUB || op == ECG_FOP_MUL);
   if (binary) {
     load_be32(y.v, b + 32 * idx);
-    if (!lt8(y.v, C::P())) report_error(status, ERRF_POINT, idx);
+    if (!lt8(y.v, C::P())) report_error(status, ERRF_POINT, base + idx);
     F::from_canonical(y, y);
   } else {
     y = x;
@@ -485,23 +485,33 @@ __global__ void __launch_bounds__(256) mb_fmul_kernel(uint32_t* out, int iters, 
 
 // ------------------------------------------------------------------------------------------------
 // host side
-struct DevState {
-  int dev = 0;
+//
+// A ctx owns, per device, two "lanes" (stream + grow-only device buffers + status words).  Device-pointer
+// mode uses lane 0 only (optionally on the caller's stream).  Host-pointer mode cuts every per-element batch
+// into chunks and alternates lanes, so the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the
+// kernels of chunk c (PCIe is the only thing between the caller's buffers and the SMs).
+enum { B_K = 0, B_P = 1, B_INF = 2, B_JAC = 3, B_SCR = 4, B_OUT = 5, B_OINF = 6, B_AUX = 7, B_A = 8, B_JAC2 = 9, B_COUNT = 10 };
+static const size_t HOST_CHUNK = (size_t)1 << 18;  // elements per pipelined chunk in host-pointer mode
+
+struct Lane {
   cudaStream_t stream = nullptr;       // owned
-  cudaStream_t user_stream = nullptr;  // optional override (ecg_ctx_set_stream)
+  cudaStream_t user_stream = nullptr;  // optional override (lane 0, ecg_ctx_set_stream)
   bool use_user_stream = false;
-  // grow-only device buffers
-  void* buf[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t cap[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  uint32_t* status = nullptr;    // 2 words
+  void* buf[B_COUNT] = {nullptr};
+  size_t cap[B_COUNT] = {0};
+  uint32_t* status = nullptr;    // 2 words: error flags, smallest offending index
   uint32_t* h_status = nullptr;  // pinned
-  uint32_t* fb_table[2] = {nullptr, nullptr};  // per curve, built lazily (like the reference's LazyLock table)
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;    // bracket the dominant kernel of the last call (ecg_timing)
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // bracket the dominant kernel of the last call (ecg_timing)
   bool ev_pending = false;
-  int sm_count = 148;
+  bool used = false;  // touched by the current call
   cudaStream_t s() const { return use_user_stream ? user_stream : stream; }
 };
-enum { B_K = 0, B_P = 1, B_INF = 2, B_JAC = 3, B_SCR = 4, B_OUT = 5, B_OINF = 6, B_AUX = 7, B_A = 8, B_JAC2 = 9 };
+struct DevState {
+  int dev = 0;
+  Lane lane[2];
+  uint32_t* fb_table[2] = {nullptr, nullptr};  // per curve, built lazily (like the reference's LazyLock table)
+  int sm_count = 148;
+};
 
 struct ecg_ctx {
   std::vector<DevState> devs;
@@ -509,9 +519,10 @@ struct ecg_ctx {
   std::string err;
   size_t err_index = (size_t)-1;
   uint64_t launches = 0;
-  bool timing = false;        // ecg_timing_enable
-  double dom_ms_sum = 0;      // accumulated device time of the dominant kernel (max over devices per call)
+  bool timing = false;    // ecg_timing_enable
+  double dom_ms_sum = 0;  // accumulated device time of the dominant kernel (max over devices per call)
   uint64_t dom_calls = 0;
+  bool devptr() const { return (flags & ECG_FLAG_DEVICE_PTRS) != 0; }
 };
 
 #define CU_TRY(ctx, call)                                                                                    \
@@ -524,27 +535,44 @@ struct ecg_ctx {
       return e_ == cudaErrorMemoryAllocation ? ECG_ENOMEM : ECG_ECUDA;                                       \
     }                                                                                                        \
   } while (0)
-#define ST_TRY(expr)                     \
-  do {                                   \
-    ecg_status st_ = (expr);             \
-    if (st_ != ECG_OK) return st_;       \
+#define ST_TRY(expr)               \
+  do {                             \
+    ecg_status st_ = (expr);       \
+    if (st_ != ECG_OK) return st_; \
+  } while (0)
+#define LAUNCHED(ctx)                \
+  do {                               \
+    (ctx)->launches++;               \
+    CU_TRY(ctx, cudaGetLastError()); \
+  } while (0)
+// CUDA events around the dominant kernel of a call, on the launching stream (bench.py's roofline numerator)
+#define DOM_BEGIN(ctx, L)                                              \
+  do {                                                                 \
+    if ((ctx)->timing) CU_TRY(ctx, cudaEventRecord((L).ev0, (L).s())); \
+  } while (0)
+#define DOM_END(ctx, L)                                  \
+  do {                                                   \
+    if ((ctx)->timing) {                                 \
+      CU_TRY(ctx, cudaEventRecord((L).ev1, (L).s()));    \
+      (L).ev_pending = true;                             \
+    }                                                    \
   } while (0)
 
-static ecg_status ensure(ecg_ctx* ctx, DevState& d, int which, size_t bytes) {
-  if (bytes <= d.cap[which]) return ECG_OK;
-  if (d.buf[which]) {
-    CU_TRY(ctx, cudaStreamSynchronize(d.s()));
-    CU_TRY(ctx, cudaFree(d.buf[which]));
+static ecg_status ensure(ecg_ctx* ctx, Lane& L, int which, size_t bytes) {
+  if (bytes <= L.cap[which]) return ECG_OK;
+  if (L.buf[which]) {
+    CU_TRY(ctx, cudaStreamSynchronize(L.s()));
+    CU_TRY(ctx, cudaFree(L.buf[which]));
   }
-  d.buf[which] = nullptr;
-  d.cap[which] = 0;
+  L.buf[which] = nullptr;
+  L.cap[which] = 0;
   size_t want = bytes + bytes / 8 + 256;
-  CU_TRY(ctx, cudaMalloc(&d.buf[which], want));
-  d.cap[which] = want;
+  CU_TRY(ctx, cudaMalloc(&L.buf[which], want));
+  L.cap[which] = want;
   return ECG_OK;
 }
 
-extern "C" const char* ecg_version(void) { return "ecgpu 0.2 (sm_100a)"; }
+extern "C" const char* ecg_version(void) { return "ecgpu 0.3 (sm_100a)"; }
 
 extern "C" ecg_status ecg_ctx_create(const int* device_ids, int n_devices, unsigned flags, ecg_ctx** out) {
   if (!out) return ECG_EINVAL;
@@ -562,13 +590,18 @@ extern "C" ecg_status ecg_ctx_create(const int* device_ids, int n_devices, unsig
     DevState& d = ctx->devs[i];
     d.dev = (device_ids && n_devices > 0) ? device_ids[i] : 0;
     if (d.dev < 0 || d.dev >= count) {
-      delete ctx;
+      ecg_ctx_destroy(ctx);
       return ECG_EINVAL;
     }
-    if (cudaSetDevice(d.dev) != cudaSuccess || cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc((void**)&d.status, 8) != cudaSuccess || cudaMallocHost((void**)&d.h_status, 8) != cudaSuccess ||
-        cudaEventCreate(&d.ev0) != cudaSuccess || cudaEventCreate(&d.ev1) != cudaSuccess) {
-      delete ctx;
+    bool ok = cudaSetDevice(d.dev) == cudaSuccess;
+    for (int l = 0; ok && l < 2; l++) {
+      Lane& L = d.lane[l];
+      ok = cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaMalloc((void**)&L.status, 8) == cudaSuccess && cudaMallocHost((void**)&L.h_status, 8) == cudaSuccess &&
+           cudaEventCreate(&L.ev0) == cudaSuccess && cudaEventCreate(&L.ev1) == cudaSuccess;
+    }
+    if (!ok) {
+      ecg_ctx_destroy(ctx);
       return ECG_ECUDA;
     }
     cudaDeviceProp prop;
@@ -582,18 +615,21 @@ extern "C" void ecg_ctx_destroy(ecg_ctx* ctx) {
   if (!ctx) return;
   for (DevState& d : ctx->devs) {
     cudaSetDevice(d.dev);
-    if (d.stream) {
-      cudaStreamSynchronize(d.stream);
-      cudaStreamDestroy(d.stream);
+    for (int l = 0; l < 2; l++) {
+      Lane& L = d.lane[l];
+      if (L.stream) {
+        cudaStreamSynchronize(L.stream);
+        cudaStreamDestroy(L.stream);
+      }
+      for (int i = 0; i < B_COUNT; i++)
+        if (L.buf[i]) cudaFree(L.buf[i]);
+      if (L.status) cudaFree(L.status);
+      if (L.h_status) cudaFreeHost(L.h_status);
+      if (L.ev0) cudaEventDestroy(L.ev0);
+      if (L.ev1) cudaEventDestroy(L.ev1);
     }
-    for (int i = 0; i < 10; i++)
-      if (d.buf[i]) cudaFree(d.buf[i]);
     for (int i = 0; i < 2; i++)
       if (d.fb_table[i]) cudaFree(d.fb_table[i]);
-    if (d.status) cudaFree(d.status);
-    if (d.h_status) cudaFreeHost(d.h_status);
-    if (d.ev0) cudaEventDestroy(d.ev0);
-    if (d.ev1) cudaEventDestroy(d.ev1);
   }
   delete ctx;
 }
@@ -618,13 +654,13 @@ extern "C" ecg_status ecg_timing_read(const ecg_ctx* ctx, double* dominant_kerne
 
 extern "C" ecg_status ecg_ctx_set_stream(ecg_ctx* ctx, void* cuda_stream) {
   if (!ctx) return ECG_EINVAL;
-  DevState& d = ctx->devs[0];
-  d.user_stream = (cudaStream_t)cuda_stream;
-  d.use_user_stream = cuda_stream != nullptr;
+  Lane& L = ctx->devs[0].lane[0];
+  L.user_stream = (cudaStream_t)cuda_stream;
+  L.use_user_stream = cuda_stream != nullptr;
   return ECG_OK;
 }
 
-// Shard [0,n) into contiguous per-device ranges (SURVEY.md §8(e)).
+// Shard [0,n) into contiguous per-device ranges (SURVEY.md section 8(e)).
 struct Shard {
   size_t off, cnt;
 };
@@ -639,82 +675,88 @@ static std::vector<Shard> make_shards(size_t n, size_t ndev) {
   return v;
 }
 
-// device-side views of one shard's operands
+// operands of one chunk as seen by the kernels
 struct DevPtrs {
   const uint8_t *k = nullptr, *p = nullptr, *inf = nullptr, *a = nullptr;
   uint8_t *out = nullptr, *oinf = nullptr;
 };
 
-static ecg_status stage_one(ecg_ctx* ctx, DevState& d, int slot, const uint8_t* src, size_t off, size_t cnt,
-                            size_t stride, const uint8_t** dst) {
+// Make elements [off, off+cnt) of `src` (stride bytes each) available on the lane: in device-pointer mode that is
+// pointer arithmetic, in host mode an async H2D copy into the lane's slot.
+static ecg_status stage_in(ecg_ctx* ctx, Lane& L, int slot, const uint8_t* src, size_t off, size_t cnt, size_t stride,
+                           const uint8_t** dst) {
   if (!src) {
     *dst = nullptr;
     return ECG_OK;
   }
-  if (ctx->flags & ECG_FLAG_DEVICE_PTRS) {
+  if (ctx->devptr()) {
     *dst = src + off * stride;
     return ECG_OK;
   }
-  ST_TRY(ensure(ctx, d, slot, cnt * stride));
-  CU_TRY(ctx, cudaMemcpyAsync(d.buf[slot], src + off * stride, cnt * stride, cudaMemcpyHostToDevice, d.s()));
-  *dst = (const uint8_t*)d.buf[slot];
+  ST_TRY(ensure(ctx, L, slot, cnt * stride));
+  CU_TRY(ctx, cudaMemcpyAsync(L.buf[slot], src + off * stride, cnt * stride, cudaMemcpyHostToDevice, L.s()));
+  *dst = (const uint8_t*)L.buf[slot];
   return ECG_OK;
 }
-static ecg_status stage_out(ecg_ctx* ctx, DevState& d, const Shard& sh, uint8_t* out, size_t ostride,
-                            uint8_t* oinf, DevPtrs& dp) {
-  if (ctx->flags & ECG_FLAG_DEVICE_PTRS) {
-    dp.out = out + sh.off * ostride;
-    dp.oinf = oinf ? oinf + sh.off : nullptr;
+static ecg_status stage_out(ecg_ctx* ctx, Lane& L, size_t off, size_t cnt, uint8_t* out, size_t ostride, uint8_t* oinf,
+                            DevPtrs& dp) {
+  if (ctx->devptr()) {
+    dp.out = out + off * ostride;
+    dp.oinf = oinf ? oinf + off : nullptr;
     if (!dp.oinf) {
-      ST_TRY(ensure(ctx, d, B_OINF, sh.cnt));
-      dp.oinf = (uint8_t*)d.buf[B_OINF];
+      ST_TRY(ensure(ctx, L, B_OINF, cnt));
+      dp.oinf = (uint8_t*)L.buf[B_OINF];
     }
     return ECG_OK;
   }
-  ST_TRY(ensure(ctx, d, B_OUT, sh.cnt * ostride));
-  ST_TRY(ensure(ctx, d, B_OINF, sh.cnt));
-  dp.out = (uint8_t*)d.buf[B_OUT];
-  dp.oinf = (uint8_t*)d.buf[B_OINF];
+  ST_TRY(ensure(ctx, L, B_OUT, cnt * ostride));
+  ST_TRY(ensure(ctx, L, B_OINF, cnt));
+  dp.out = (uint8_t*)L.buf[B_OUT];
+  dp.oinf = (uint8_t*)L.buf[B_OINF];
   return ECG_OK;
 }
-static ecg_status copy_back(ecg_ctx* ctx, DevState& d, const Shard& sh, uint8_t* out, size_t ostride,
-                            uint8_t* oinf, const DevPtrs& dp) {
-  if (ctx->flags & ECG_FLAG_DEVICE_PTRS) return ECG_OK;
-  CU_TRY(ctx, cudaMemcpyAsync(out + sh.off * ostride, dp.out, sh.cnt * ostride, cudaMemcpyDeviceToHost, d.s()));
-  if (oinf) CU_TRY(ctx, cudaMemcpyAsync(oinf + sh.off, dp.oinf, sh.cnt, cudaMemcpyDeviceToHost, d.s()));
+static ecg_status copy_back(ecg_ctx* ctx, Lane& L, size_t off, size_t cnt, uint8_t* out, size_t ostride, uint8_t* oinf,
+                            const DevPtrs& dp) {
+  if (ctx->devptr()) return ECG_OK;
+  CU_TRY(ctx, cudaMemcpyAsync(out + off * ostride, dp.out, cnt * ostride, cudaMemcpyDeviceToHost, L.s()));
+  if (oinf) CU_TRY(ctx, cudaMemcpyAsync(oinf + off, dp.oinf, cnt, cudaMemcpyDeviceToHost, L.s()));
   return ECG_OK;
 }
-static ecg_status reset_status(ecg_ctx* ctx, DevState& d) {
-  CU_TRY(ctx, cudaMemsetAsync(d.status, 0, 4, d.s()));
-  CU_TRY(ctx, cudaMemsetAsync(d.status + 1, 0xFF, 4, d.s()));
+static ecg_status begin_lane(ecg_ctx* ctx, Lane& L) {
+  if (L.used) return ECG_OK;
+  CU_TRY(ctx, cudaMemsetAsync(L.status, 0, 4, L.s()));
+  CU_TRY(ctx, cudaMemsetAsync(L.status + 1, 0xFF, 4, L.s()));
+  L.used = true;
   return ECG_OK;
 }
-// Wait for every device, fold the validation status into a return code.
-static ecg_status finish(ecg_ctx* ctx, const std::vector<Shard>& shards) {
+// Wait for every lane touched by this call; fold validation status and kernel timing into the ctx.
+static ecg_status finish(ecg_ctx* ctx) {
   ecg_status rc = ECG_OK;
   size_t first = (size_t)-1;
   float dom_ms = 0;
   bool any_timed = false;
-  for (size_t i = 0; i < ctx->devs.size(); i++) {
-    DevState& d = ctx->devs[i];
-    if (shards[i].cnt == 0) continue;
-    CU_TRY(ctx, cudaSetDevice(d.dev));
-    CU_TRY(ctx, cudaMemcpyAsync(d.h_status, d.status, 8, cudaMemcpyDeviceToHost, d.s()));
-    CU_TRY(ctx, cudaStreamSynchronize(d.s()));
-    CU_TRY(ctx, cudaGetLastError());
-    if (d.ev_pending) {
-      float ms = 0;
-      if (cudaEventElapsedTime(&ms, d.ev0, d.ev1) == cudaSuccess && ms > dom_ms) dom_ms = ms;
-      d.ev_pending = false;
-      any_timed = true;
-    }
-    if (d.h_status[0]) {
-      size_t idx = shards[i].off + d.h_status[1];
-      if (idx < first) {
-        first = idx;
-        rc = (d.h_status[0] & ERRF_POINT) ? ECG_ENOT_ON_CURVE : ECG_ESCALAR_RANGE;
+  for (DevState& d : ctx->devs) {
+    float dev_ms = 0;
+    for (int l = 0; l < 2; l++) {
+      Lane& L = d.lane[l];
+      if (!L.used) continue;
+      L.used = false;
+      CU_TRY(ctx, cudaSetDevice(d.dev));
+      CU_TRY(ctx, cudaMemcpyAsync(L.h_status, L.status, 8, cudaMemcpyDeviceToHost, L.s()));
+      CU_TRY(ctx, cudaStreamSynchronize(L.s()));
+      CU_TRY(ctx, cudaGetLastError());
+      if (L.ev_pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, L.ev0, L.ev1) == cudaSuccess) dev_ms += ms;
+        L.ev_pending = false;
+        any_timed = true;
+      }
+      if (L.h_status[0] && (size_t)L.h_status[1] < first) {
+        first = L.h_status[1];
+        rc = (L.h_status[0] & ERRF_POINT) ? ECG_ENOT_ON_CURVE : ECG_ESCALAR_RANGE;
       }
     }
+    if (dev_ms > dom_ms) dom_ms = dev_ms;
   }
   if (any_timed) {
     ctx->dom_ms_sum += dom_ms;
@@ -726,41 +768,41 @@ static ecg_status finish(ecg_ctx* ctx, const std::vector<Shard>& shards) {
   }
   return rc;
 }
+// abandon a call after a host-side failure: drain what was enqueued so buffers can be reused
+static ecg_status fail(ecg_ctx* ctx, ecg_status rc) {
+  std::string saved = ctx->err;
+  for (DevState& d : ctx->devs)
+    for (int l = 0; l < 2; l++)
+      if (d.lane[l].used) {
+        cudaSetDevice(d.dev);
+        cudaStreamSynchronize(d.lane[l].s());
+        d.lane[l].used = false;
+        d.lane[l].ev_pending = false;
+      }
+  ctx->err = saved;
+  return rc;
+}
 
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
-#define LAUNCHED(ctx)                  \
-  do {                                 \
-    (ctx)->launches++;                 \
-    CU_TRY(ctx, cudaGetLastError());   \
-  } while (0)
-
-// CUDA events around the dominant kernel of a call, on the launching stream (bench.py's roofline numerator)
-#define DOM_BEGIN(ctx, d)                                           \
-  do {                                                              \
-    if ((ctx)->timing) CU_TRY(ctx, cudaEventRecord((d).ev0, (d).s())); \
-  } while (0)
-#define DOM_END(ctx, d)                                             \
-  do {                                                              \
-    if ((ctx)->timing) {                                            \
-      CU_TRY(ctx, cudaEventRecord((d).ev1, (d).s()));               \
-      (d).ev_pending = true;                                        \
-    }                                                               \
-  } while (0)
 
 template <class F>
-static ecg_status launch_normalize(ecg_ctx* ctx, DevState& d, size_t n, const uint32_t* jac, uint8_t* out, uint8_t* oinf) {
-  ST_TRY(ensure(ctx, d, B_SCR, n * 32));
+static ecg_status launch_normalize(ecg_ctx* ctx, DevState& d, Lane& L, size_t n, const uint32_t* jac, uint8_t* out, uint8_t* oinf) {
+  ST_TRY(ensure(ctx, L, B_SCR, n * 32));
   // ~32 elements per thread amortise the per-thread inversion, but never leave SMs idle for small batches
   size_t want_threads = std::max<size_t>((n + 31) / 32, std::min<size_t>(n, (size_t)d.sm_count * 256));
-  unsigned blocks = grid_for(want_threads, 256);
-  normalize_kernel<F><<<blocks, 256, 0, d.s()>>>(jac, n, (uint32_t*)d.buf[B_SCR], out, oinf);
+  normalize_kernel<F><<<grid_for(want_threads, 256), 256, 0, L.s()>>>(jac, n, (uint32_t*)L.buf[B_SCR], out, oinf);
   LAUNCHED(ctx);
   return ECG_OK;
 }
+static ecg_status launch_norm(ecg_ctx* ctx, DevState& d, Lane& L, ecg_curve curve, size_t n, const uint32_t* jac, uint8_t* out,
+                              uint8_t* oinf) {
+  return curve == ECG_SECP256K1 ? launch_normalize<FpK256>(ctx, d, L, n, jac, out, oinf)
+                                : launch_normalize<FpP256>(ctx, d, L, n, jac, out, oinf);
+}
 
 // launch geometry of the variable-base kernels
-static const int K_BLOCK = 128, K_MINBLK = 3;   // secp256k1: 512 B smem/thread  -> 3 x 64 KiB per SM
-static const int P_BLOCK = 128, P_MINBLK = 2;   // P-256   : 768 B smem/thread  -> 2 x 96 KiB per SM
+static const int K_BLOCK = 128, K_MINBLK = 3;  // secp256k1: 512 B smem/thread  -> 3 x 64 KiB per SM
+static const int P_BLOCK = 128, P_MINBLK = 2;  // P-256   : 768 B smem/thread  -> 2 x 96 KiB per SM
 
 template <class KernelT>
 static ecg_status set_smem(ecg_ctx* ctx, KernelT kernel, size_t smem) {
@@ -768,56 +810,25 @@ static ecg_status set_smem(ecg_ctx* ctx, KernelT kernel, size_t smem) {
   return ECG_OK;
 }
 
-// k*P for one shard -> Jacobian SoA in `jac`
-static ecg_status launch_varbase(ecg_ctx* ctx, DevState& d, ecg_curve curve, size_t n, const DevPtrs& dp, uint32_t* jac) {
-  DOM_BEGIN(ctx, d);
+// k*P for one chunk -> Jacobian SoA in `jac`; `status` / `base` locate validation errors
+static ecg_status launch_varbase(ecg_ctx* ctx, Lane& L, ecg_curve curve, size_t n, const DevPtrs& dp, uint32_t* jac,
+                                 uint32_t* status, size_t base) {
+  DOM_BEGIN(ctx, L);
   if (curve == ECG_SECP256K1) {
     size_t smem = (size_t)K_BLOCK * 8 * 16 * 4;
     ST_TRY(set_smem(ctx, k256_varbase_kernel<K_BLOCK, K_MINBLK>, smem));
-    k256_varbase_kernel<K_BLOCK, K_MINBLK><<<grid_for(n, K_BLOCK), K_BLOCK, smem, d.s()>>>(dp.k, dp.p, dp.inf, n, jac, d.status);
+    k256_varbase_kernel<K_BLOCK, K_MINBLK><<<grid_for(n, K_BLOCK), K_BLOCK, smem, L.s()>>>(dp.k, dp.p, dp.inf, n, jac, status, base);
   } else {
     size_t smem = (size_t)P_BLOCK * 8 * 24 * 4;
     ST_TRY(set_smem(ctx, generic_varbase_kernel<CurveP256, P_BLOCK, P_MINBLK>, smem));
-    generic_varbase_kernel<CurveP256, P_BLOCK, P_MINBLK><<<grid_for(n, P_BLOCK), P_BLOCK, smem, d.s()>>>(dp.k, dp.p, dp.inf, n, jac, d.status);
+    generic_varbase_kernel<CurveP256, P_BLOCK, P_MINBLK><<<grid_for(n, P_BLOCK), P_BLOCK, smem, L.s()>>>(dp.k, dp.p, dp.inf, n, jac, status, base);
   }
   LAUNCHED(ctx);
-  DOM_END(ctx, d);
+  DOM_END(ctx, L);
   return ECG_OK;
-}
-static ecg_status launch_norm(ecg_ctx* ctx, DevState& d, ecg_curve curve, size_t n, const uint32_t* jac, uint8_t* out, uint8_t* oinf) {
-  return curve == ECG_SECP256K1 ? launch_normalize<FpK256>(ctx, d, n, jac, out, oinf)
-                                : launch_normalize<FpP256>(ctx, d, n, jac, out, oinf);
 }
 
 static bool curve_ok(ecg_curve c) { return c == ECG_SECP256K1 || c == ECG_NISTP256; }
-
-extern "C" ecg_status ecg_mul_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
-                                    const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf) {
-  if (!ctx) return ECG_EINVAL;
-  if (n == 0) return ECG_OK;
-  if (!k || !P_xy || !out_xy || !curve_ok(curve)) {
-    ctx->err = "ecg_mul_batch: null pointer or unknown curve";
-    return ECG_EINVAL;
-  }
-  std::vector<Shard> shards = make_shards(n, ctx->devs.size());
-  std::vector<DevPtrs> dps(ctx->devs.size());
-  for (size_t i = 0; i < ctx->devs.size(); i++) {
-    DevState& d = ctx->devs[i];
-    const Shard& sh = shards[i];
-    if (sh.cnt == 0) continue;
-    CU_TRY(ctx, cudaSetDevice(d.dev));
-    ST_TRY(reset_status(ctx, d));
-    ST_TRY(stage_one(ctx, d, B_K, k, sh.off, sh.cnt, 32, &dps[i].k));
-    ST_TRY(stage_one(ctx, d, B_P, P_xy, sh.off, sh.cnt, 64, &dps[i].p));
-    ST_TRY(stage_one(ctx, d, B_INF, P_inf, sh.off, sh.cnt, 1, &dps[i].inf));
-    ST_TRY(stage_out(ctx, d, sh, out_xy, 64, out_inf, dps[i]));
-    ST_TRY(ensure(ctx, d, B_JAC, sh.cnt * 96));
-    ST_TRY(launch_varbase(ctx, d, curve, sh.cnt, dps[i], (uint32_t*)d.buf[B_JAC]));
-    ST_TRY(launch_norm(ctx, d, curve, sh.cnt, (uint32_t*)d.buf[B_JAC], dps[i].out, dps[i].oinf));
-    ST_TRY(copy_back(ctx, d, sh, out_xy, 64, out_inf, dps[i]));
-  }
-  return finish(ctx, shards);
-}
 
 // ---- fixed-base table ------------------------------------------------------------------------------
 // Built on the device with the variable-base kernel itself: entry (i, j) = ((2j+1) << 16 i mod n) * G.
@@ -828,7 +839,6 @@ static void scalar_be_from_shifted(uint8_t* out, uint64_t odd, int shift_bits, c
   uint64_t lo = odd << b;  // odd < 2^17, b < 32
   v[w] = (uint32_t)lo;
   if (w + 1 < 10) v[w + 1] = (uint32_t)(lo >> 32);
-  // compare/subtract n on 9 limbs
   uint32_t nn[9];
   for (int i = 0; i < 8; i++) nn[i] = n_le[i];
   nn[8] = 0;
@@ -867,6 +877,7 @@ static const uint8_t H_P256_G[64] = {
 
 static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
   if (d.fb_table[curve]) return ECG_OK;
+  Lane& L = d.lane[0];
   const size_t np = FB_TABLE_POINTS;
   std::vector<uint8_t> hk(np * 32), hp(np * 64);
   const uint32_t* n_le = curve == ECG_SECP256K1 ? H_K256_N : H_P256_N;
@@ -876,7 +887,7 @@ static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
   scalar_be_from_shifted(&hk[(np - 1) * 32], 1, 256, n_le);  // 2^256 mod n
   for (size_t i = 0; i < np; i++) memcpy(&hp[i * 64], g, 64);
   uint8_t *dk = nullptr, *dpnt = nullptr, *dxy = nullptr, *dinf = nullptr;
-  uint32_t *jac = nullptr, *scr = nullptr, *table = nullptr;
+  uint32_t *jac = nullptr, *scr = nullptr, *table = nullptr, *st = nullptr;
   CU_TRY(ctx, cudaMalloc((void**)&dk, np * 32));
   CU_TRY(ctx, cudaMalloc((void**)&dpnt, np * 64));
   CU_TRY(ctx, cudaMalloc((void**)&dxy, np * 64));
@@ -884,35 +895,30 @@ static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
   CU_TRY(ctx, cudaMalloc((void**)&jac, np * 96));
   CU_TRY(ctx, cudaMalloc((void**)&scr, np * 32));
   CU_TRY(ctx, cudaMalloc((void**)&table, np * 64));
-  CU_TRY(ctx, cudaMemcpyAsync(dk, hk.data(), np * 32, cudaMemcpyHostToDevice, d.s()));
-  CU_TRY(ctx, cudaMemcpyAsync(dpnt, hp.data(), np * 64, cudaMemcpyHostToDevice, d.s()));
+  CU_TRY(ctx, cudaMalloc((void**)&st, 8));  // private status: building the table must not disturb a caller's validation state
+  CU_TRY(ctx, cudaMemsetAsync(st, 0, 8, L.s()));
+  CU_TRY(ctx, cudaMemcpyAsync(dk, hk.data(), np * 32, cudaMemcpyHostToDevice, L.s()));
+  CU_TRY(ctx, cudaMemcpyAsync(dpnt, hp.data(), np * 64, cudaMemcpyHostToDevice, L.s()));
   DevPtrs dp;
   dp.k = dk;
   dp.p = dpnt;
-  // a private status word: building the table must not disturb the caller's validation state
-  uint32_t* st = nullptr;
-  CU_TRY(ctx, cudaMalloc((void**)&st, 8));
-  CU_TRY(ctx, cudaMemsetAsync(st, 0, 8, d.s()));
-  uint32_t* saved = d.status;
   bool saved_timing = ctx->timing;
   ctx->timing = false;
-  d.status = st;
-  ecg_status rc = launch_varbase(ctx, d, curve, np, dp, jac);
-  d.status = saved;
+  ecg_status rc = launch_varbase(ctx, L, curve, np, dp, jac, st, 0);
   ctx->timing = saved_timing;
   if (rc != ECG_OK) return rc;
   size_t want_threads = std::max<size_t>((np + 31) / 32, std::min<size_t>(np, (size_t)d.sm_count * 256));
   if (curve == ECG_SECP256K1) {
-    normalize_kernel<FpK256><<<grid_for(want_threads, 256), 256, 0, d.s()>>>(jac, np, scr, dxy, dinf);
+    normalize_kernel<FpK256><<<grid_for(want_threads, 256), 256, 0, L.s()>>>(jac, np, scr, dxy, dinf);
     LAUNCHED(ctx);
-    affine_to_table_kernel<CurveK256><<<grid_for(np, 256), 256, 0, d.s()>>>(dxy, np, table);
+    affine_to_table_kernel<CurveK256><<<grid_for(np, 256), 256, 0, L.s()>>>(dxy, np, table);
   } else {
-    normalize_kernel<FpP256><<<grid_for(want_threads, 256), 256, 0, d.s()>>>(jac, np, scr, dxy, dinf);
+    normalize_kernel<FpP256><<<grid_for(want_threads, 256), 256, 0, L.s()>>>(jac, np, scr, dxy, dinf);
     LAUNCHED(ctx);
-    affine_to_table_kernel<CurveP256><<<grid_for(np, 256), 256, 0, d.s()>>>(dxy, np, table);
+    affine_to_table_kernel<CurveP256><<<grid_for(np, 256), 256, 0, L.s()>>>(dxy, np, table);
   }
   LAUNCHED(ctx);
-  CU_TRY(ctx, cudaStreamSynchronize(d.s()));
+  CU_TRY(ctx, cudaStreamSynchronize(L.s()));
   cudaFree(dk);
   cudaFree(dpnt);
   cudaFree(dxy);
@@ -920,8 +926,139 @@ static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
   cudaFree(jac);
   cudaFree(scr);
   cudaFree(st);
+  // lane 1 (and any caller stream) may use the table from now on: it was completed with a full synchronize
   d.fb_table[curve] = table;
   return ECG_OK;
+}
+
+// ---- per-element batch driver ------------------------------------------------------------------------
+// What one chunk does is the only thing that differs between ecg_mul_batch, ecg_mul_gen_batch, ecg_mul_gen_add_batch,
+// ecg_batch_normalize and ecg_field_op_batch:
+struct BatchOp {
+  enum Kind { MUL, MULGEN, MULGENADD, NORMALIZE, FIELD } kind;
+  ecg_curve curve;
+  int fop = 0;
+  const uint8_t *k = nullptr, *a = nullptr, *p = nullptr, *inf = nullptr;  // host or device, per ctx flags
+  size_t pstride = 64;
+  uint8_t *out = nullptr, *oinf = nullptr;
+  size_t ostride = 64;
+};
+
+static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& op, size_t off, size_t cnt) {
+  DevPtrs dp;
+  ST_TRY(begin_lane(ctx, L));
+  ST_TRY(stage_in(ctx, L, B_K, op.k, off, cnt, 32, &dp.k));
+  ST_TRY(stage_in(ctx, L, B_A, op.a, off, cnt, 32, &dp.a));
+  ST_TRY(stage_in(ctx, L, B_P, op.p, off, cnt, op.pstride, &dp.p));
+  ST_TRY(stage_in(ctx, L, B_INF, op.inf, off, cnt, 1, &dp.inf));
+  ST_TRY(stage_out(ctx, L, off, cnt, op.out, op.ostride, op.oinf, dp));
+  uint32_t* jac = nullptr;
+  if (op.kind != BatchOp::FIELD) {
+    ST_TRY(ensure(ctx, L, B_JAC, cnt * 96));
+    jac = (uint32_t*)L.buf[B_JAC];
+  }
+  const bool k1 = op.curve == ECG_SECP256K1;
+  switch (op.kind) {
+    case BatchOp::MUL:
+      ST_TRY(launch_varbase(ctx, L, op.curve, cnt, dp, jac, L.status, off));
+      break;
+    case BatchOp::MULGEN:
+      DOM_BEGIN(ctx, L);
+      if (k1)
+        fixedbase_kernel<CurveK256><<<grid_for(cnt, 128), 128, 0, L.s()>>>(dp.k, cnt, d.fb_table[op.curve], jac, L.status, off);
+      else
+        fixedbase_kernel<CurveP256><<<grid_for(cnt, 128), 128, 0, L.s()>>>(dp.k, cnt, d.fb_table[op.curve], jac, L.status, off);
+      LAUNCHED(ctx);
+      DOM_END(ctx, L);
+      break;
+    case BatchOp::MULGENADD:
+      DOM_BEGIN(ctx, L);
+      if (k1) {
+        size_t smem = (size_t)K_BLOCK * 8 * 16 * 4;
+        ST_TRY(set_smem(ctx, mul_gen_add_kernel<CurveK256, K_BLOCK, K_MINBLK, true>, smem));
+        mul_gen_add_kernel<CurveK256, K_BLOCK, K_MINBLK, true><<<grid_for(cnt, K_BLOCK), K_BLOCK, smem, L.s()>>>(
+            dp.a, dp.k, dp.p, dp.inf, cnt, d.fb_table[op.curve], jac, L.status, off);
+      } else {
+        size_t smem = (size_t)P_BLOCK * 8 * 24 * 4;
+        ST_TRY(set_smem(ctx, mul_gen_add_kernel<CurveP256, P_BLOCK, P_MINBLK, false>, smem));
+        mul_gen_add_kernel<CurveP256, P_BLOCK, P_MINBLK, false><<<grid_for(cnt, P_BLOCK), P_BLOCK, smem, L.s()>>>(
+            dp.a, dp.k, dp.p, dp.inf, cnt, d.fb_table[op.curve], jac, L.status, off);
+      }
+      LAUNCHED(ctx);
+      DOM_END(ctx, L);
+      break;
+    case BatchOp::NORMALIZE:
+      if (k1)
+        import_jac_kernel<CurveK256><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, cnt, jac, L.status, off);
+      else
+        import_jac_kernel<CurveP256><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, cnt, jac, L.status, off);
+      LAUNCHED(ctx);
+      break;
+    case BatchOp::FIELD:
+      if (k1)
+        field_op_kernel<CurveK256><<<grid_for(cnt, 256), 256, 0, L.s()>>>(op.fop, cnt, dp.k, dp.a, dp.out, L.status, off);
+      else
+        field_op_kernel<CurveP256><<<grid_for(cnt, 256), 256, 0, L.s()>>>(op.fop, cnt, dp.k, dp.a, dp.out, L.status, off);
+      LAUNCHED(ctx);
+      break;
+  }
+  if (op.kind != BatchOp::FIELD) ST_TRY(launch_norm(ctx, d, L, op.curve, cnt, jac, dp.out, dp.oinf));
+  return copy_back(ctx, L, off, cnt, op.out, op.ostride, op.oinf, dp);
+}
+
+static ecg_status run_batch(ecg_ctx* ctx, const BatchOp& op, size_t n) {
+  std::vector<Shard> shards = make_shards(n, ctx->devs.size());
+  bool need_table = op.kind == BatchOp::MULGEN || op.kind == BatchOp::MULGENADD;
+  for (size_t i = 0; i < ctx->devs.size(); i++) {
+    if (shards[i].cnt == 0) continue;
+    DevState& d = ctx->devs[i];
+    CU_TRY(ctx, cudaSetDevice(d.dev));
+    if (need_table) {
+      ecg_status st = ensure_fb_table(ctx, d, op.curve);
+      if (st != ECG_OK) return fail(ctx, st);
+    }
+  }
+  if (ctx->devptr()) {
+    DevState& d = ctx->devs[0];
+    ecg_status st = run_chunk(ctx, d, d.lane[0], op, 0, n);
+    if (st != ECG_OK) return fail(ctx, st);
+    return finish(ctx);
+  }
+  // host mode: interleave chunks across devices and lanes so copies and kernels of different chunks overlap
+  size_t maxchunks = 0;
+  for (const Shard& sh : shards) maxchunks = std::max(maxchunks, (sh.cnt + HOST_CHUNK - 1) / HOST_CHUNK);
+  for (size_t c = 0; c < maxchunks; c++) {
+    for (size_t i = 0; i < ctx->devs.size(); i++) {
+      const Shard& sh = shards[i];
+      size_t lo = c * HOST_CHUNK;
+      if (lo >= sh.cnt) continue;
+      size_t cnt = std::min(HOST_CHUNK, sh.cnt - lo);
+      DevState& d = ctx->devs[i];
+      CU_TRY(ctx, cudaSetDevice(d.dev));
+      ecg_status st = run_chunk(ctx, d, d.lane[c & 1], op, sh.off + lo, cnt);
+      if (st != ECG_OK) return fail(ctx, st);
+    }
+  }
+  return finish(ctx);
+}
+
+extern "C" ecg_status ecg_mul_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
+                                    const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf) {
+  if (!ctx) return ECG_EINVAL;
+  if (n == 0) return ECG_OK;
+  if (!k || !P_xy || !out_xy || !curve_ok(curve)) {
+    ctx->err = "ecg_mul_batch: null pointer or unknown curve";
+    return ECG_EINVAL;
+  }
+  BatchOp op;
+  op.kind = BatchOp::MUL;
+  op.curve = curve;
+  op.k = k;
+  op.p = P_xy;
+  op.inf = P_inf;
+  op.out = out_xy;
+  op.oinf = out_inf;
+  return run_batch(ctx, op, n);
 }
 
 extern "C" ecg_status ecg_mul_gen_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, uint8_t* out_xy,
@@ -932,30 +1069,13 @@ extern "C" ecg_status ecg_mul_gen_batch(ecg_ctx* ctx, ecg_curve curve, size_t n,
     ctx->err = "ecg_mul_gen_batch: null pointer or unknown curve";
     return ECG_EINVAL;
   }
-  std::vector<Shard> shards = make_shards(n, ctx->devs.size());
-  std::vector<DevPtrs> dps(ctx->devs.size());
-  for (size_t i = 0; i < ctx->devs.size(); i++) {
-    DevState& d = ctx->devs[i];
-    const Shard& sh = shards[i];
-    if (sh.cnt == 0) continue;
-    CU_TRY(ctx, cudaSetDevice(d.dev));
-    ST_TRY(ensure_fb_table(ctx, d, curve));
-    ST_TRY(reset_status(ctx, d));
-    ST_TRY(stage_one(ctx, d, B_K, k, sh.off, sh.cnt, 32, &dps[i].k));
-    ST_TRY(stage_out(ctx, d, sh, out_xy, 64, out_inf, dps[i]));
-    ST_TRY(ensure(ctx, d, B_JAC, sh.cnt * 96));
-    uint32_t* jac = (uint32_t*)d.buf[B_JAC];
-    DOM_BEGIN(ctx, d);
-    if (curve == ECG_SECP256K1)
-      fixedbase_kernel<CurveK256><<<grid_for(sh.cnt, 128), 128, 0, d.s()>>>(dps[i].k, sh.cnt, d.fb_table[curve], jac, d.status);
-    else
-      fixedbase_kernel<CurveP256><<<grid_for(sh.cnt, 128), 128, 0, d.s()>>>(dps[i].k, sh.cnt, d.fb_table[curve], jac, d.status);
-    LAUNCHED(ctx);
-    DOM_END(ctx, d);
-    ST_TRY(launch_norm(ctx, d, curve, sh.cnt, jac, dps[i].out, dps[i].oinf));
-    ST_TRY(copy_back(ctx, d, sh, out_xy, 64, out_inf, dps[i]));
-  }
-  return finish(ctx, shards);
+  BatchOp op;
+  op.kind = BatchOp::MULGEN;
+  op.curve = curve;
+  op.k = k;
+  op.out = out_xy;
+  op.oinf = out_inf;
+  return run_batch(ctx, op, n);
 }
 
 extern "C" ecg_status ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, const uint8_t* b,
@@ -966,47 +1086,57 @@ extern "C" ecg_status ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve curve, size_
     ctx->err = "ecg_mul_gen_add_batch: null pointer or unknown curve";
     return ECG_EINVAL;
   }
-  std::vector<Shard> shards = make_shards(n, ctx->devs.size());
-  std::vector<DevPtrs> dps(ctx->devs.size());
-  for (size_t i = 0; i < ctx->devs.size(); i++) {
-    DevState& d = ctx->devs[i];
-    const Shard& sh = shards[i];
-    if (sh.cnt == 0) continue;
-    CU_TRY(ctx, cudaSetDevice(d.dev));
-    ST_TRY(ensure_fb_table(ctx, d, curve));
-    ST_TRY(reset_status(ctx, d));
-    ST_TRY(stage_one(ctx, d, B_A, a, sh.off, sh.cnt, 32, &dps[i].a));
-    ST_TRY(stage_one(ctx, d, B_K, b, sh.off, sh.cnt, 32, &dps[i].k));
-    ST_TRY(stage_one(ctx, d, B_P, P_xy, sh.off, sh.cnt, 64, &dps[i].p));
-    ST_TRY(stage_one(ctx, d, B_INF, P_inf, sh.off, sh.cnt, 1, &dps[i].inf));
-    ST_TRY(stage_out(ctx, d, sh, out_xy, 64, out_inf, dps[i]));
-    ST_TRY(ensure(ctx, d, B_JAC, sh.cnt * 96));
-    uint32_t* jac = (uint32_t*)d.buf[B_JAC];
-    if (curve == ECG_SECP256K1) {
-      size_t smem = (size_t)K_BLOCK * 8 * 16 * 4;
-      ST_TRY(set_smem(ctx, mul_gen_add_kernel<CurveK256, K_BLOCK, K_MINBLK, true>, smem));
-      mul_gen_add_kernel<CurveK256, K_BLOCK, K_MINBLK, true><<<grid_for(sh.cnt, K_BLOCK), K_BLOCK, smem, d.s()>>>(
-          dps[i].a, dps[i].k, dps[i].p, dps[i].inf, sh.cnt, d.fb_table[curve], jac, d.status);
-    } else {
-      size_t smem = (size_t)P_BLOCK * 8 * 24 * 4;
-      ST_TRY(set_smem(ctx, mul_gen_add_kernel<CurveP256, P_BLOCK, P_MINBLK, false>, smem));
-      mul_gen_add_kernel<CurveP256, P_BLOCK, P_MINBLK, false><<<grid_for(sh.cnt, P_BLOCK), P_BLOCK, smem, d.s()>>>(
-          dps[i].a, dps[i].k, dps[i].p, dps[i].inf, sh.cnt, d.fb_table[curve], jac, d.status);
-    }
-    LAUNCHED(ctx);
-    ST_TRY(launch_norm(ctx, d, curve, sh.cnt, jac, dps[i].out, dps[i].oinf));
-    ST_TRY(copy_back(ctx, d, sh, out_xy, 64, out_inf, dps[i]));
-  }
-  return finish(ctx, shards);
+  BatchOp op;
+  op.kind = BatchOp::MULGENADD;
+  op.curve = curve;
+  op.a = a;
+  op.k = b;
+  op.p = P_xy;
+  op.inf = P_inf;
+  op.out = out_xy;
+  op.oinf = out_inf;
+  return run_batch(ctx, op, n);
+}
+
+extern "C" ecg_status ecg_batch_normalize(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz, uint8_t* out_xy,
+                                          uint8_t* out_inf) {
+  if (!ctx) return ECG_EINVAL;
+  if (n == 0) return ECG_OK;
+  if (!xyz || !out_xy || !curve_ok(curve)) return ECG_EINVAL;
+  BatchOp op;
+  op.kind = BatchOp::NORMALIZE;
+  op.curve = curve;
+  op.p = xyz;
+  op.pstride = 96;
+  op.out = out_xy;
+  op.oinf = out_inf;
+  return run_batch(ctx, op, n);
+}
+
+extern "C" ecg_status ecg_field_op_batch(ecg_ctx* ctx, ecg_curve curve, int fop, size_t n, const uint8_t* a, const uint8_t* b,
+                                         uint8_t* out) {
+  if (!ctx) return ECG_EINVAL;
+  if (n == 0) return ECG_OK;
+  bool binary = (fop == ECG_FOP_ADD || fop == ECG_FOP_SUB || fop == ECG_FOP_MUL);
+  if (!a || !out || (binary && !b) || fop < 0 || fop > ECG_FOP_INV || !curve_ok(curve)) return ECG_EINVAL;
+  BatchOp op;
+  op.kind = BatchOp::FIELD;
+  op.curve = curve;
+  op.fop = fop;
+  op.k = a;
+  op.a = binary ? b : nullptr;
+  op.out = out;
+  op.ostride = 32;
+  return run_batch(ctx, op, n);
 }
 
 // ---- lincomb ----------------------------------------------------------------------------------------
-// Reduce n Jacobian points (SoA in `a`) to one, ping-ponging between a and b; returns the buffer holding it.
+// Reduce n Jacobian points (SoA in `a`) to one, ping-ponging between a and b; *result = buffer holding it.
 template <class C>
-static ecg_status reduce_points(ecg_ctx* ctx, DevState& d, uint32_t* a, uint32_t* b, size_t n, uint32_t** result) {
+static ecg_status reduce_points(ecg_ctx* ctx, Lane& L, uint32_t* a, uint32_t* b, size_t n, uint32_t** result) {
   while (n > 1) {
     size_t m = (n + 31) / 32;
-    jac_sum_kernel<C><<<grid_for(m, 128), 128, 0, d.s()>>>(a, n, b, m);
+    jac_sum_kernel<C><<<grid_for(m, 128), 128, 0, L.s()>>>(a, n, b, m);
     LAUNCHED(ctx);
     std::swap(a, b);
     n = m;
@@ -1014,29 +1144,30 @@ static ecg_status reduce_points(ecg_ctx* ctx, DevState& d, uint32_t* a, uint32_t
   *result = a;
   return ECG_OK;
 }
-static ecg_status reduce_points_c(ecg_ctx* ctx, DevState& d, ecg_curve curve, uint32_t* a, uint32_t* b, size_t n, uint32_t** result) {
-  return curve == ECG_SECP256K1 ? reduce_points<CurveK256>(ctx, d, a, b, n, result) : reduce_points<CurveP256>(ctx, d, a, b, n, result);
+static ecg_status reduce_points_c(ecg_ctx* ctx, Lane& L, ecg_curve curve, uint32_t* a, uint32_t* b, size_t n, uint32_t** result) {
+  return curve == ECG_SECP256K1 ? reduce_points<CurveK256>(ctx, L, a, b, n, result) : reduce_points<CurveP256>(ctx, L, a, b, n, result);
 }
 
-// one shard -> one Jacobian point left in *result (SoA with n = 1, i.e. 24 consecutive words)
+// one shard -> one Jacobian point left in *result (SoA with n = 1, i.e. 24 consecutive words), on lane 0
 static ecg_status lincomb_shard(ecg_ctx* ctx, DevState& d, ecg_curve curve, const Shard& sh, const uint8_t* k,
                                 const uint8_t* P_xy, const uint8_t* P_inf, uint32_t** result) {
+  Lane& L = d.lane[0];
   DevPtrs dp;
-  ST_TRY(reset_status(ctx, d));
-  ST_TRY(stage_one(ctx, d, B_K, k, sh.off, sh.cnt, 32, &dp.k));
-  ST_TRY(stage_one(ctx, d, B_P, P_xy, sh.off, sh.cnt, 64, &dp.p));
-  ST_TRY(stage_one(ctx, d, B_INF, P_inf, sh.off, sh.cnt, 1, &dp.inf));
-  ST_TRY(ensure(ctx, d, B_JAC, sh.cnt * 96));
-  ST_TRY(ensure(ctx, d, B_JAC2, ((sh.cnt + 31) / 32) * 96 + 96));
-  ST_TRY(launch_varbase(ctx, d, curve, sh.cnt, dp, (uint32_t*)d.buf[B_JAC]));
-  return reduce_points_c(ctx, d, curve, (uint32_t*)d.buf[B_JAC], (uint32_t*)d.buf[B_JAC2], sh.cnt, result);
+  ST_TRY(begin_lane(ctx, L));
+  ST_TRY(stage_in(ctx, L, B_K, k, sh.off, sh.cnt, 32, &dp.k));
+  ST_TRY(stage_in(ctx, L, B_P, P_xy, sh.off, sh.cnt, 64, &dp.p));
+  ST_TRY(stage_in(ctx, L, B_INF, P_inf, sh.off, sh.cnt, 1, &dp.inf));
+  ST_TRY(ensure(ctx, L, B_JAC, sh.cnt * 96));
+  ST_TRY(ensure(ctx, L, B_JAC2, ((sh.cnt + 31) / 32) * 96 + 96));
+  ST_TRY(launch_varbase(ctx, L, curve, sh.cnt, dp, (uint32_t*)L.buf[B_JAC], L.status, sh.off));
+  return reduce_points_c(ctx, L, curve, (uint32_t*)L.buf[B_JAC], (uint32_t*)L.buf[B_JAC2], sh.cnt, result);
 }
 
-static ecg_status export_point(ecg_ctx* ctx, DevState& d, ecg_curve curve, const uint32_t* jac1, uint8_t* dev_xyz) {
+static ecg_status export_point(ecg_ctx* ctx, Lane& L, ecg_curve curve, const uint32_t* jac1, uint8_t* dev_xyz) {
   if (curve == ECG_SECP256K1)
-    export_jac_kernel<CurveK256><<<1, 128, 0, d.s()>>>(jac1, 1, dev_xyz);
+    export_jac_kernel<CurveK256><<<1, 128, 0, L.s()>>>(jac1, 1, dev_xyz);
   else
-    export_jac_kernel<CurveP256><<<1, 128, 0, d.s()>>>(jac1, 1, dev_xyz);
+    export_jac_kernel<CurveP256><<<1, 128, 0, L.s()>>>(jac1, 1, dev_xyz);
   LAUNCHED(ctx);
   return ECG_OK;
 }
@@ -1053,56 +1184,57 @@ extern "C" ecg_status ecg_lincomb_partial(ecg_ctx* ctx, ecg_curve curve, size_t 
     return ECG_EINVAL;
   }
   DevState& d = ctx->devs[0];
+  Lane& L = d.lane[0];
   CU_TRY(ctx, cudaSetDevice(d.dev));
-  bool devptr = ctx->flags & ECG_FLAG_DEVICE_PTRS;
   if (n == 0) {  // empty sum = identity (0 : 1 : 0)
     uint8_t z[96];
     memset(z, 0, sizeof z);
     z[63] = 1;
-    if (devptr)
+    if (ctx->devptr())
       CU_TRY(ctx, cudaMemcpy(out_xyz, z, 96, cudaMemcpyHostToDevice));
     else
       memcpy(out_xyz, z, 96);
     return ECG_OK;
   }
-  std::vector<Shard> shards = make_shards(n, 1);
+  Shard sh = {0, n};
   uint32_t* res = nullptr;
-  ST_TRY(lincomb_shard(ctx, d, curve, shards[0], k, P_xy, P_inf, &res));
+  ecg_status st = lincomb_shard(ctx, d, curve, sh, k, P_xy, P_inf, &res);
+  if (st != ECG_OK) return fail(ctx, st);
   uint8_t* dst = out_xyz;
-  if (!devptr) {
-    ST_TRY(ensure(ctx, d, B_AUX, 256));
-    dst = (uint8_t*)d.buf[B_AUX];
+  if (!ctx->devptr()) {
+    if ((st = ensure(ctx, L, B_AUX, 256)) != ECG_OK) return fail(ctx, st);
+    dst = (uint8_t*)L.buf[B_AUX];
   }
-  ST_TRY(export_point(ctx, d, curve, res, dst));
-  if (!devptr) CU_TRY(ctx, cudaMemcpyAsync(out_xyz, dst, 96, cudaMemcpyDeviceToHost, d.s()));
-  return finish(ctx, shards);
+  if ((st = export_point(ctx, L, curve, res, dst)) != ECG_OK) return fail(ctx, st);
+  if (!ctx->devptr()) CU_TRY(ctx, cudaMemcpyAsync(out_xyz, dst, 96, cudaMemcpyDeviceToHost, L.s()));
+  return finish(ctx);
 }
 
-// m Jacobian points as host bytes -> affine sum (device 0 of the ctx)
+// m Jacobian points as host bytes -> affine sum (device 0 of the ctx, lane 0)
 static ecg_status point_sum_host(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* xyz, uint8_t* out_xy, uint8_t* out_inf) {
   DevState& d = ctx->devs[0];
+  Lane& L = d.lane[0];
   CU_TRY(ctx, cudaSetDevice(d.dev));
-  std::vector<Shard> one = make_shards(m, 1);
-  ST_TRY(reset_status(ctx, d));
-  ST_TRY(ensure(ctx, d, B_AUX, m * 96 + 256));
-  ST_TRY(ensure(ctx, d, B_JAC, m * 96 + 96));
-  ST_TRY(ensure(ctx, d, B_JAC2, ((m + 31) / 32) * 96 + 96));
-  ST_TRY(ensure(ctx, d, B_OUT, 64));
-  ST_TRY(ensure(ctx, d, B_OINF, 1));
-  uint8_t* dxyz = (uint8_t*)d.buf[B_AUX];
-  CU_TRY(ctx, cudaMemcpyAsync(dxyz, xyz, m * 96, cudaMemcpyHostToDevice, d.s()));
-  uint32_t* jac = (uint32_t*)d.buf[B_JAC];
+  ST_TRY(begin_lane(ctx, L));
+  ST_TRY(ensure(ctx, L, B_AUX, m * 96 + 256));
+  ST_TRY(ensure(ctx, L, B_JAC, m * 96 + 96));
+  ST_TRY(ensure(ctx, L, B_JAC2, ((m + 31) / 32) * 96 + 96));
+  ST_TRY(ensure(ctx, L, B_OUT, 64));
+  ST_TRY(ensure(ctx, L, B_OINF, 1));
+  uint8_t* dxyz = (uint8_t*)L.buf[B_AUX];
+  CU_TRY(ctx, cudaMemcpyAsync(dxyz, xyz, m * 96, cudaMemcpyHostToDevice, L.s()));
+  uint32_t* jac = (uint32_t*)L.buf[B_JAC];
   if (curve == ECG_SECP256K1)
-    import_jac_kernel<CurveK256><<<grid_for(m, 256), 256, 0, d.s()>>>(dxyz, m, jac, d.status);
+    import_jac_kernel<CurveK256><<<grid_for(m, 256), 256, 0, L.s()>>>(dxyz, m, jac, L.status, 0);
   else
-    import_jac_kernel<CurveP256><<<grid_for(m, 256), 256, 0, d.s()>>>(dxyz, m, jac, d.status);
+    import_jac_kernel<CurveP256><<<grid_for(m, 256), 256, 0, L.s()>>>(dxyz, m, jac, L.status, 0);
   LAUNCHED(ctx);
   uint32_t* res = nullptr;
-  ST_TRY(reduce_points_c(ctx, d, curve, jac, (uint32_t*)d.buf[B_JAC2], m, &res));
-  ST_TRY(launch_norm(ctx, d, curve, 1, res, (uint8_t*)d.buf[B_OUT], (uint8_t*)d.buf[B_OINF]));
-  CU_TRY(ctx, cudaMemcpyAsync(out_xy, d.buf[B_OUT], 64, cudaMemcpyDeviceToHost, d.s()));
-  CU_TRY(ctx, cudaMemcpyAsync(out_inf, d.buf[B_OINF], 1, cudaMemcpyDeviceToHost, d.s()));
-  return finish(ctx, one);
+  ST_TRY(reduce_points_c(ctx, L, curve, jac, (uint32_t*)L.buf[B_JAC2], m, &res));
+  ST_TRY(launch_norm(ctx, d, L, curve, 1, res, (uint8_t*)L.buf[B_OUT], (uint8_t*)L.buf[B_OINF]));
+  CU_TRY(ctx, cudaMemcpyAsync(out_xy, L.buf[B_OUT], 64, cudaMemcpyDeviceToHost, L.s()));
+  CU_TRY(ctx, cudaMemcpyAsync(out_inf, L.buf[B_OINF], 1, cudaMemcpyDeviceToHost, L.s()));
+  return finish(ctx);
 }
 
 extern "C" ecg_status ecg_point_sum(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* xyz, uint8_t* out_xy,
@@ -1114,7 +1246,8 @@ extern "C" ecg_status ecg_point_sum(ecg_ctx* ctx, ecg_curve curve, size_t m, con
     *out_inf = 1;
     return ECG_OK;
   }
-  return point_sum_host(ctx, curve, m, xyz, out_xy, out_inf);
+  ecg_status st = point_sum_host(ctx, curve, m, xyz, out_xy, out_inf);
+  return st == ECG_OK ? st : fail(ctx, st);
 }
 
 extern "C" ecg_status ecg_lincomb(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
@@ -1124,11 +1257,10 @@ extern "C" ecg_status ecg_lincomb(ecg_ctx* ctx, ecg_curve curve, size_t n, const
     ctx->err = "ecg_lincomb: null pointer or unknown curve";
     return ECG_EINVAL;
   }
-  bool devptr = ctx->flags & ECG_FLAG_DEVICE_PTRS;
   if (n == 0) {
     uint8_t z[65];
     memset(z, 0, sizeof z);
-    if (devptr) {
+    if (ctx->devptr()) {
       CU_TRY(ctx, cudaMemcpy(out_xy, z, 64, cudaMemcpyHostToDevice));
       z[0] = 1;
       CU_TRY(ctx, cudaMemcpy(out_inf, z, 1, cudaMemcpyHostToDevice));
@@ -1140,98 +1272,45 @@ extern "C" ecg_status ecg_lincomb(ecg_ctx* ctx, ecg_curve curve, size_t n, const
   }
   size_t nd = ctx->devs.size();
   std::vector<Shard> shards = make_shards(n, nd);
+  ecg_status st;
   if (nd == 1) {
     DevState& d = ctx->devs[0];
+    Lane& L = d.lane[0];
     CU_TRY(ctx, cudaSetDevice(d.dev));
     uint32_t* res = nullptr;
-    ST_TRY(lincomb_shard(ctx, d, curve, shards[0], k, P_xy, P_inf, &res));
+    if ((st = lincomb_shard(ctx, d, curve, shards[0], k, P_xy, P_inf, &res)) != ECG_OK) return fail(ctx, st);
     DevPtrs dp;
-    Shard one = {0, 1};
-    ST_TRY(stage_out(ctx, d, one, out_xy, 64, out_inf, dp));
-    ST_TRY(launch_norm(ctx, d, curve, 1, res, dp.out, dp.oinf));
-    ST_TRY(copy_back(ctx, d, one, out_xy, 64, out_inf, dp));
-    return finish(ctx, shards);
+    if ((st = stage_out(ctx, L, 0, 1, out_xy, 64, out_inf, dp)) != ECG_OK) return fail(ctx, st);
+    if ((st = launch_norm(ctx, d, L, curve, 1, res, dp.out, dp.oinf)) != ECG_OK) return fail(ctx, st);
+    if ((st = copy_back(ctx, L, 0, 1, out_xy, 64, out_inf, dp)) != ECG_OK) return fail(ctx, st);
+    return finish(ctx);
   }
   // several devices: one partial point per device, gathered through the host (96 B each), summed on device 0
   std::vector<uint8_t> partial(nd * 96, 0);
-  std::vector<uint8_t*> dsts(nd, nullptr);
   for (size_t i = 0; i < nd; i++) {
     DevState& d = ctx->devs[i];
+    Lane& L = d.lane[0];
     partial[i * 96 + 63] = 1;  // identity (0:1:0) for empty shards
     if (shards[i].cnt == 0) continue;
     CU_TRY(ctx, cudaSetDevice(d.dev));
     uint32_t* res = nullptr;
-    ST_TRY(lincomb_shard(ctx, d, curve, shards[i], k, P_xy, P_inf, &res));
-    ST_TRY(ensure(ctx, d, B_AUX, 256));
-    ST_TRY(export_point(ctx, d, curve, res, (uint8_t*)d.buf[B_AUX]));
-    CU_TRY(ctx, cudaMemcpyAsync(&partial[i * 96], d.buf[B_AUX], 96, cudaMemcpyDeviceToHost, d.s()));
+    if ((st = lincomb_shard(ctx, d, curve, shards[i], k, P_xy, P_inf, &res)) != ECG_OK) return fail(ctx, st);
+    if ((st = ensure(ctx, L, B_AUX, 256)) != ECG_OK) return fail(ctx, st);
+    if ((st = export_point(ctx, L, curve, res, (uint8_t*)L.buf[B_AUX])) != ECG_OK) return fail(ctx, st);
+    CU_TRY(ctx, cudaMemcpyAsync(&partial[i * 96], L.buf[B_AUX], 96, cudaMemcpyDeviceToHost, L.s()));
   }
-  ecg_status rc = finish(ctx, shards);
-  if (rc != ECG_OK) return rc;
-  return point_sum_host(ctx, curve, nd, partial.data(), out_xy, out_inf);
-}
-
-extern "C" ecg_status ecg_batch_normalize(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz,
-                                          uint8_t* out_xy, uint8_t* out_inf) {
-  if (!ctx) return ECG_EINVAL;
-  if (n == 0) return ECG_OK;
-  if (!xyz || !out_xy || !curve_ok(curve)) return ECG_EINVAL;
-  std::vector<Shard> shards = make_shards(n, ctx->devs.size());
-  std::vector<DevPtrs> dps(ctx->devs.size());
-  for (size_t i = 0; i < ctx->devs.size(); i++) {
-    DevState& d = ctx->devs[i];
-    const Shard& sh = shards[i];
-    if (sh.cnt == 0) continue;
-    CU_TRY(ctx, cudaSetDevice(d.dev));
-    ST_TRY(reset_status(ctx, d));
-    ST_TRY(stage_one(ctx, d, B_P, xyz, sh.off, sh.cnt, 96, &dps[i].p));
-    ST_TRY(stage_out(ctx, d, sh, out_xy, 64, out_inf, dps[i]));
-    ST_TRY(ensure(ctx, d, B_JAC, sh.cnt * 96));
-    uint32_t* jac = (uint32_t*)d.buf[B_JAC];
-    if (curve == ECG_SECP256K1)
-      import_jac_kernel<CurveK256><<<grid_for(sh.cnt, 256), 256, 0, d.s()>>>(dps[i].p, sh.cnt, jac, d.status);
-    else
-      import_jac_kernel<CurveP256><<<grid_for(sh.cnt, 256), 256, 0, d.s()>>>(dps[i].p, sh.cnt, jac, d.status);
-    LAUNCHED(ctx);
-    ST_TRY(launch_norm(ctx, d, curve, sh.cnt, jac, dps[i].out, dps[i].oinf));
-    ST_TRY(copy_back(ctx, d, sh, out_xy, 64, out_inf, dps[i]));
-  }
-  return finish(ctx, shards);
-}
-
-extern "C" ecg_status ecg_field_op_batch(ecg_ctx* ctx, ecg_curve curve, int op, size_t n, const uint8_t* a,
-                                         const uint8_t* b, uint8_t* out) {
-  if (!ctx) return ECG_EINVAL;
-  if (n == 0) return ECG_OK;
-  bool binary = (op == ECG_FOP_ADD || op == ECG_FOP_SUB || op == ECG_FOP_MUL);
-  if (!a || !out || (binary && !b) || op < 0 || op > ECG_FOP_INV || !curve_ok(curve)) return ECG_EINVAL;
-  std::vector<Shard> shards = make_shards(n, ctx->devs.size());
-  std::vector<DevPtrs> dps(ctx->devs.size());
-  for (size_t i = 0; i < ctx->devs.size(); i++) {
-    DevState& d = ctx->devs[i];
-    const Shard& sh = shards[i];
-    if (sh.cnt == 0) continue;
-    CU_TRY(ctx, cudaSetDevice(d.dev));
-    ST_TRY(reset_status(ctx, d));
-    ST_TRY(stage_one(ctx, d, B_K, a, sh.off, sh.cnt, 32, &dps[i].k));
-    ST_TRY(stage_one(ctx, d, B_A, binary ? b : nullptr, sh.off, sh.cnt, 32, &dps[i].a));
-    ST_TRY(stage_out(ctx, d, sh, out, 32, nullptr, dps[i]));
-    if (curve == ECG_SECP256K1)
-      field_op_kernel<CurveK256><<<grid_for(sh.cnt, 256), 256, 0, d.s()>>>(op, sh.cnt, dps[i].k, dps[i].a, dps[i].out, d.status);
-    else
-      field_op_kernel<CurveP256><<<grid_for(sh.cnt, 256), 256, 0, d.s()>>>(op, sh.cnt, dps[i].k, dps[i].a, dps[i].out, d.status);
-    LAUNCHED(ctx);
-    ST_TRY(copy_back(ctx, d, sh, out, 32, nullptr, dps[i]));
-  }
-  return finish(ctx, shards);
+  if ((st = finish(ctx)) != ECG_OK) return st;
+  st = point_sum_host(ctx, curve, nd, partial.data(), out_xy, out_inf);
+  return st == ECG_OK ? st : fail(ctx, st);
 }
 
 extern "C" ecg_status ecg_microbench(ecg_ctx* ctx, int which, int iters, double* ops_per_s, double* elapsed_ms) {
   if (!ctx || !ops_per_s || iters <= 0) return ECG_EINVAL;
   DevState& d = ctx->devs[0];
+  Lane& L = d.lane[0];
   CU_TRY(ctx, cudaSetDevice(d.dev));
-  ST_TRY(ensure(ctx, d, B_AUX, 256));
-  uint32_t* out = (uint32_t*)d.buf[B_AUX];
+  ST_TRY(ensure(ctx, L, B_AUX, 256));
+  uint32_t* out = (uint32_t*)L.buf[B_AUX];
   unsigned blocks = (unsigned)d.sm_count * 8, threads = 256;
   double per_thread_iter = 0;
   cudaEvent_t e0, e1;
@@ -1239,20 +1318,20 @@ extern "C" ecg_status ecg_microbench(ecg_ctx* ctx, int which, int iters, double*
   CU_TRY(ctx, cudaEventCreate(&e1));
   float best = 1e30f;
   for (int rep = 0; rep < 4; rep++) {  // rep 0 = warm-up
-    CU_TRY(ctx, cudaEventRecord(e0, d.s()));
+    CU_TRY(ctx, cudaEventRecord(e0, L.s()));
     switch (which) {
-      case 0: mb_imad_wide_kernel<<<blocks, threads, 0, d.s()>>>(out, iters, 12345u + rep); per_thread_iter = 32; break;
-      case 1: mb_imad_kernel<<<blocks, threads, 0, d.s()>>>(out, iters, 12345u + rep); per_thread_iter = 64; break;
-      case 2: mb_iadd_kernel<<<blocks, threads, 0, d.s()>>>(out, iters, 12345u + rep); per_thread_iter = 64; break;
-      case 3: mb_fmul_kernel<FpK256><<<blocks, threads, 0, d.s()>>>(out, iters, 12345u + rep); per_thread_iter = 2; break;
-      case 4: mb_fmul_kernel<FpP256><<<blocks, threads, 0, d.s()>>>(out, iters, 12345u + rep); per_thread_iter = 2; break;
+      case 0: mb_imad_wide_kernel<<<blocks, threads, 0, L.s()>>>(out, iters, 12345u + rep); per_thread_iter = 32; break;
+      case 1: mb_imad_kernel<<<blocks, threads, 0, L.s()>>>(out, iters, 12345u + rep); per_thread_iter = 64; break;
+      case 2: mb_iadd_kernel<<<blocks, threads, 0, L.s()>>>(out, iters, 12345u + rep); per_thread_iter = 64; break;
+      case 3: mb_fmul_kernel<FpK256><<<blocks, threads, 0, L.s()>>>(out, iters, 12345u + rep); per_thread_iter = 2; break;
+      case 4: mb_fmul_kernel<FpP256><<<blocks, threads, 0, L.s()>>>(out, iters, 12345u + rep); per_thread_iter = 2; break;
       default:
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
         return ECG_EINVAL;
     }
     ctx->launches++;
-    CU_TRY(ctx, cudaEventRecord(e1, d.s()));
+    CU_TRY(ctx, cudaEventRecord(e1, L.s()));
     CU_TRY(ctx, cudaEventSynchronize(e1));
     CU_TRY(ctx, cudaGetLastError());
     float ms = 0;

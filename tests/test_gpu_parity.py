@@ -255,7 +255,7 @@ def test_batch_normalize(engine, curve):
 
 
 # ---------------------------------------------------------------- size-independent properties at scale
-@pytest.mark.parametrize("curve,logn", [("k256", 17), ("p256", 16)])
+@pytest.mark.parametrize("curve,logn", [("k256", 19), ("p256", 16)])
 def test_large_batch_properties(engine, curve, logn):
     """k*P and (n-k)*P must be negatives of each other; sample checked against the oracle;
     lincomb of the whole batch must be the identity."""
@@ -282,6 +282,68 @@ def test_large_batch_properties(engine, curve, logn):
     assert np.array_equal(out_xy[idx], sub_xy)
     l_xy, l_inf = engine.lincomb(curve, K, xy, None)
     assert l_inf == 1 and not l_xy.any()
+
+
+def test_pipelined_host_chunks_report_global_error_index(engine):
+    """host mode cuts batches into 2^18-element chunks on alternating lanes: results and error indices are global."""
+    import ecgpu
+
+    c = pyref.K256
+    n = (1 << 18) + 777
+    rng = random.Random(4)
+    base = random_points(c, 16, seed=8)
+    xy1, _ = pack_points(base)
+    xy = np.tile(xy1.reshape(16, 64), (n // 16 + 1, 1))[:n].reshape(-1).copy()
+    K = np.frombuffer(rng.randbytes(32 * n), dtype=np.uint8).copy().reshape(n, 32)
+    K[:, 0] &= 0x7F
+    out_xy, out_inf = engine.mul_batch("k256", K, xy, None)
+    idx = [0, 1, (1 << 18) - 1, 1 << 18, (1 << 18) + 1, n - 1] + [rng.randrange(n) for _ in range(200)]
+    ref_xy, ref_inf = ecref.mul_batch("k256", K[idx], xy.reshape(n, 64)[idx], None, nthreads=8)
+    assert np.array_equal(np.asarray(out_xy).reshape(n, 64)[idx], ref_xy)
+    bad = K.copy()
+    bad[(1 << 18) + 5] = 0xFF
+    with pytest.raises(ecgpu.ScalarRangeError) as ei:
+        engine.mul_batch("k256", bad, xy, None)
+    assert ei.value.index == (1 << 18) + 5
+    bad[12345] = 0xFF
+    with pytest.raises(ecgpu.ScalarRangeError) as ei:
+        engine.mul_batch("k256", bad, xy, None)
+    assert ei.value.index == 12345
+
+
+def test_multi_device_ctx_shards_the_batch():
+    """one ctx over several devices: contiguous shards, same bytes as a single-device ctx."""
+    import torch
+
+    import ecgpu
+
+    nd = torch.cuda.device_count()
+    if nd < 2:
+        pytest.skip("needs >= 2 GPUs")
+    c = pyref.K256
+    rng = random.Random(12)
+    n = 5003
+    base = random_points(c, 16, seed=18)
+    Ps = [base[i % 16] for i in range(n)]
+    ks = [rng.randrange(c.n) for _ in range(n)]
+    xy, inf = pack_points(Ps)
+    K = pack_scalars(ks)
+    multi = ecgpu.Engine(list(range(nd)))
+    out_xy, out_inf = multi.mul_batch("k256", K, xy, inf)
+    ref_xy, ref_inf = ecref.mul_batch("k256", K, xy, inf, nthreads=8)
+    assert np.array_equal(np.asarray(out_xy).reshape(-1), ref_xy.reshape(-1)) and np.array_equal(out_inf, ref_inf)
+    g_xy, g_inf = multi.mul_by_generator("k256", K)
+    r_xy, r_inf = ecref.mul_gen_batch("k256", K, nthreads=8)
+    assert np.array_equal(np.asarray(g_xy).reshape(-1), r_xy.reshape(-1))
+    l_xy, l_inf = multi.lincomb("k256", K, xy, inf)
+    e_xy, e_inf = ecref.lincomb("k256", K, xy, inf, nthreads=8)
+    assert np.array_equal(l_xy, e_xy) and l_inf == e_inf
+    bad = K.copy()
+    bad[32 * (n - 3):32 * (n - 3) + 32] = 0xFF
+    with pytest.raises(ecgpu.ScalarRangeError) as ei:
+        multi.mul_batch("k256", bad, xy, inf)
+    assert ei.value.index == n - 3
+    multi.close()
 
 
 def test_multi_engine_independence():
