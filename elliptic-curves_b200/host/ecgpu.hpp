@@ -1,0 +1,139 @@
+// ecgpu.hpp — C++ host-side mirror of the reference's operator surface for the scalar-multiplication path,
+// header-only, over the C ABI in include/ecgpu.h.  (The reference is Rust; this image has no Rust toolchain, so the
+// host layer above the ABI is C++; INTEGRATION.md shows the equivalent Rust shim.)
+//
+// Names follow the reference's traits so that call sites read the same:
+//   Engine::mul(points, scalars)                      <->  ProjectivePoint * Scalar            (k256/src/arithmetic/mul.rs:249-274)
+//   Engine::mul_vartime(...)                          <->  MulVartime::mul_vartime             (mul.rs:276-295)   [same kernel]
+//   Engine::mul_by_generator(scalars)                 <->  ProjectivePoint::mul_by_generator   (mul.rs:180-232)
+//   Engine::lincomb(points, scalars)                  <->  LinearCombination::lincomb          (mul.rs:66-109)
+//   Engine::mul_by_generator_and_mul_add_vartime(...) <->  MulByGeneratorVartime::...          (mul.rs:303-310)
+//   Engine::batch_normalize(jacobian)                 <->  BatchNormalize::batch_normalize     (projective.rs:345-365)
+// Fallible decoding mirrors CtOption/Result: out-of-range scalars / off-curve points throw DecodeError carrying the
+// index of the first offender; arithmetic itself is total.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/ecgpu.h"
+
+namespace ecgpu {
+
+using Scalar = std::array<uint8_t, 32>;  // big-endian, < n          (Scalar::to_bytes)
+struct AffinePoint {                     // AffinePoint { x, y, infinity } (k256/src/arithmetic/affine.rs:37-49)
+  std::array<uint8_t, 32> x{}, y{};
+  uint8_t infinity = 0;
+  static AffinePoint identity() {
+    AffinePoint p;
+    p.infinity = 1;
+    return p;
+  }
+};
+struct JacobianPoint {  // X, Y, Z big-endian; Z = 0 is the identity
+  std::array<uint8_t, 32> X{}, Y{}, Z{};
+};
+
+struct Error : std::runtime_error {
+  ecg_status code;
+  Error(ecg_status c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+struct DecodeError : Error {  // Scalar::from_repr / AffinePoint::from_coordinates returned None in the reference
+  size_t index;
+  DecodeError(ecg_status c, const std::string& m, size_t i) : Error(c, m), index(i) {}
+};
+
+class Engine {
+ public:
+  explicit Engine(ecg_curve curve, const std::vector<int>& devices = {0}) : curve_(curve) {
+    ecg_status st = ecg_ctx_create(devices.data(), (int)devices.size(), 0, &ctx_);
+    if (st != ECG_OK) throw Error(st, "ecg_ctx_create failed (no CUDA device? there is no CPU fallback)");
+  }
+  ~Engine() { ecg_ctx_destroy(ctx_); }
+  Engine(const Engine&) = delete;
+  Engine& operator=(const Engine&) = delete;
+
+  std::vector<AffinePoint> mul(const std::vector<AffinePoint>& points, const std::vector<Scalar>& scalars) {
+    size_t n = check_sizes(points.size(), scalars.size());
+    pack(points);
+    std::vector<uint8_t> out(64 * n), oinf(n);
+    check(ecg_mul_batch(ctx_, curve_, n, flat(scalars), xy_.data(), inf_.data(), out.data(), oinf.data()));
+    return unpack(out, oinf);
+  }
+  std::vector<AffinePoint> mul_vartime(const std::vector<AffinePoint>& p, const std::vector<Scalar>& k) { return mul(p, k); }
+
+  std::vector<AffinePoint> mul_by_generator(const std::vector<Scalar>& scalars) {
+    size_t n = scalars.size();
+    std::vector<uint8_t> out(64 * n), oinf(n);
+    check(ecg_mul_gen_batch(ctx_, curve_, n, flat(scalars), out.data(), oinf.data()));
+    return unpack(out, oinf);
+  }
+  std::vector<AffinePoint> mul_by_generator_vartime(const std::vector<Scalar>& k) { return mul_by_generator(k); }
+
+  AffinePoint lincomb(const std::vector<AffinePoint>& points, const std::vector<Scalar>& scalars) {
+    size_t n = check_sizes(points.size(), scalars.size());
+    pack(points);
+    std::vector<uint8_t> out(64), oinf(1);
+    check(ecg_lincomb(ctx_, curve_, n, flat(scalars), xy_.data(), inf_.data(), out.data(), oinf.data()));
+    return unpack(out, oinf)[0];
+  }
+  AffinePoint lincomb_vartime(const std::vector<AffinePoint>& p, const std::vector<Scalar>& k) { return lincomb(p, k); }
+
+  // a[i]*G + b[i]*P[i]
+  std::vector<AffinePoint> mul_by_generator_and_mul_add_vartime(const std::vector<Scalar>& a, const std::vector<Scalar>& b,
+                                                                const std::vector<AffinePoint>& points) {
+    size_t n = check_sizes(points.size(), a.size());
+    check_sizes(n, b.size());
+    pack(points);
+    std::vector<uint8_t> out(64 * n), oinf(n);
+    check(ecg_mul_gen_add_batch(ctx_, curve_, n, flat(a), flat(b), xy_.data(), inf_.data(), out.data(), oinf.data()));
+    return unpack(out, oinf);
+  }
+
+  std::vector<AffinePoint> batch_normalize(const std::vector<JacobianPoint>& pts) {
+    size_t n = pts.size();
+    std::vector<uint8_t> out(64 * n), oinf(n);
+    check(ecg_batch_normalize(ctx_, curve_, n, reinterpret_cast<const uint8_t*>(pts.data()), out.data(), oinf.data()));
+    return unpack(out, oinf);
+  }
+
+  uint64_t kernel_launches() const { return ecg_kernel_launches(ctx_); }
+
+ private:
+  static size_t check_sizes(size_t a, size_t b) {
+    if (a != b) throw Error(ECG_EINVAL, "points/scalars length mismatch");
+    return a;
+  }
+  static const uint8_t* flat(const std::vector<Scalar>& s) { return reinterpret_cast<const uint8_t*>(s.data()); }
+  void pack(const std::vector<AffinePoint>& pts) {
+    xy_.resize(64 * pts.size());
+    inf_.resize(pts.size());
+    for (size_t i = 0; i < pts.size(); i++) {
+      std::copy(pts[i].x.begin(), pts[i].x.end(), xy_.begin() + 64 * i);
+      std::copy(pts[i].y.begin(), pts[i].y.end(), xy_.begin() + 64 * i + 32);
+      inf_[i] = pts[i].infinity;
+    }
+  }
+  static std::vector<AffinePoint> unpack(const std::vector<uint8_t>& xy, const std::vector<uint8_t>& inf) {
+    std::vector<AffinePoint> r(inf.size());
+    for (size_t i = 0; i < r.size(); i++) {
+      std::copy(xy.begin() + 64 * i, xy.begin() + 64 * i + 32, r[i].x.begin());
+      std::copy(xy.begin() + 64 * i + 32, xy.begin() + 64 * i + 64, r[i].y.begin());
+      r[i].infinity = inf[i];
+    }
+    return r;
+  }
+  void check(ecg_status st) {
+    if (st == ECG_OK) return;
+    std::string m = ecg_last_error(ctx_);
+    if (st == ECG_ESCALAR_RANGE || st == ECG_ENOT_ON_CURVE) throw DecodeError(st, m, ecg_last_error_index(ctx_));
+    throw Error(st, m);
+  }
+  ecg_curve curve_;
+  ecg_ctx* ctx_ = nullptr;
+  std::vector<uint8_t> xy_, inf_;
+};
+
+}  // namespace ecgpu

@@ -1,0 +1,39 @@
+"""CPU-only: the C++ host mirror (host/ecgpu.hpp) compiles against include/ecgpu.h and links libecgpu.so."""
+import os
+import subprocess
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SRC = r"""
+#include "ecgpu.hpp"
+#include <cstdio>
+int main() {
+  try {
+    ecgpu::Engine eng(ECG_SECP256K1);
+    std::vector<ecgpu::Scalar> k(1);
+    k[0][31] = 1;
+    auto r = eng.mul_by_generator(k);
+    std::printf("gx0=%02x launches=%llu\n", r[0].x[0], (unsigned long long)eng.kernel_launches());
+    return r[0].x[0] == 0x79 ? 0 : 2;
+  } catch (const ecgpu::Error& e) {
+    std::printf("error %d\n", (int)e.code);
+    return e.code == ECG_ECUDA ? 42 : 3;   // 42: no GPU here -> loud failure, no CPU fallback
+  }
+}
+"""
+
+
+def test_cpp_mirror_compiles_and_links():
+    lib = os.path.join(ROOT, "elliptic-curves_b200", "libecgpu.so")
+    assert os.path.exists(lib)
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "t.cpp")
+        exe = os.path.join(td, "t")
+        open(src, "w").write(SRC)
+        subprocess.check_call(["g++", "-std=c++17", "-I", os.path.join(ROOT, "elliptic-curves_b200", "host"), src, lib,
+                               "-Wl,-rpath," + os.path.dirname(lib), "-o", exe])
+        rc = subprocess.call([exe])
+        import torch
+
+        assert rc == (0 if torch.cuda.is_available() else 42)
