@@ -91,41 +91,82 @@ struct FpP256T {
     return (int32_t)t;
   }
 
-  // 16-limb c -> r = c mod p (weakly reduced).  FIPS 186-4 D.2.3: s1 + 2 s2 + 2 s3 + s4 + s5 - s6 - s7 - s8 - s9,
-  // written per output word; every partial sum fits comfortably in a signed 64-bit accumulator.
-  ECG_D static void reduce16(Fe& r, const uint32_t* c) {
-    int64_t t;
-    uint32_t o[8];
-    t = (int64_t)c[0] + c[8] + c[9] - c[11] - c[12] - c[13] - c[14];
-    o[0] = (uint32_t)t;
-    t >>= 32;
-    t += (int64_t)c[1] + c[9] + c[10] - c[12] - c[13] - c[14] - c[15];
-    o[1] = (uint32_t)t;
-    t >>= 32;
-    t += (int64_t)c[2] + c[10] + c[11] - c[13] - c[14] - c[15];
-    o[2] = (uint32_t)t;
-    t >>= 32;
-    t += (int64_t)c[3] + 2 * ((int64_t)c[11] + c[12]) + c[13] - c[15] - c[8] - c[9];
-    o[3] = (uint32_t)t;
-    t >>= 32;
-    t += (int64_t)c[4] + 2 * ((int64_t)c[12] + c[13]) + c[14] - c[9] - c[10];
-    o[4] = (uint32_t)t;
-    t >>= 32;
-    t += (int64_t)c[5] + 2 * ((int64_t)c[13] + c[14]) + c[15] - c[10] - c[11];
-    o[5] = (uint32_t)t;
-    t >>= 32;
-    t += (int64_t)c[6] + 3 * (int64_t)c[14] + 2 * (int64_t)c[15] + c[13] - c[8] - c[9];
-    o[6] = (uint32_t)t;
-    t >>= 32;
-    t += (int64_t)c[7] + 3 * (int64_t)c[15] + c[8] - c[10] - c[11] - c[12] - c[13];
-    o[7] = (uint32_t)t;
-    t >>= 32;
-    int32_t ov = (int32_t)t;            // |ov| <= 6
-    ov = fold_signed(o, ov);             // now ov in {-1,0,1}
-    ov = fold_signed(o, ov);             // now 0
-    (void)ov;
+  // acc (9 limbs: 8 + overflow word) += v, where v has non-zero limbs lo..7 (limbs below lo are zero)
+  template <int LO>
+  ECG_D static void acc_add(uint32_t* acc, const uint32_t* v) {
+    acc[LO] = add_cc(acc[LO], v[LO]);
 #pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = o[i];
+    for (int i = LO + 1; i < 8; i++) acc[i] = addc_cc(acc[i], v[i]);
+    acc[8] = addc(acc[8], 0);
+  }
+  ECG_D static void acc_sub(uint32_t* acc, const uint32_t* v) {
+    acc[0] = sub_cc(acc[0], v[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) acc[i] = subc_cc(acc[i], v[i]);
+    acc[8] = subc(acc[8], 0);
+  }
+
+  // 16-limb c -> r = c mod p (weakly reduced).  FIPS 186-4 D.2.3: s1 + 2 s2 + 2 s3 + s4 + s5 - s6 - s7 - s8 - s9 on
+  // 32-bit words, as 32-bit carry chains only (IADD3.X on the ALU pipe: nothing here competes with the multiplier
+  // for the FMA pipe).  5p is added up front so the running value never goes negative; the overflow word o (< 13)
+  // is folded with 2^256 == K (mod p).
+  ECG_D static void reduce16(Fe& r, const uint32_t* c) {
+    uint32_t acc[9], v[8];
+    // s1 + 5p            5p = {fffffffb, ffffffff, ffffffff, 4, 0, 0, 5, fffffffb | 4}
+    acc[0] = add_cc(c[0], 0xFFFFFFFBu);
+    acc[1] = addc_cc(c[1], 0xFFFFFFFFu);
+    acc[2] = addc_cc(c[2], 0xFFFFFFFFu);
+    acc[3] = addc_cc(c[3], 4u);
+    acc[4] = addc_cc(c[4], 0u);
+    acc[5] = addc_cc(c[5], 0u);
+    acc[6] = addc_cc(c[6], 5u);
+    acc[7] = addc_cc(c[7], 0xFFFFFFFBu);
+    acc[8] = addc(4u, 0u);
+    // t = s2 + s3 = (c15, c14+c15, c13+c14, c12+c13, c11+c12, 0, 0, 0), added twice
+    uint32_t t[9];
+    t[0] = t[1] = t[2] = 0;
+    t[3] = add_cc(c[11], c[12]);
+    t[4] = addc_cc(c[12], c[13]);
+    t[5] = addc_cc(c[13], c[14]);
+    t[6] = addc_cc(c[14], c[15]);
+    t[7] = addc_cc(c[15], 0u);
+    uint32_t t8 = addc(0u, 0u);
+    acc_add<3>(acc, t);
+    acc_add<3>(acc, t);
+    acc[8] += 2u * t8;
+    // s4 = (c15, c14, 0, 0, 0, c10, c9, c8)
+    v[0] = c[8]; v[1] = c[9]; v[2] = c[10]; v[3] = 0; v[4] = 0; v[5] = 0; v[6] = c[14]; v[7] = c[15];
+    acc_add<0>(acc, v);
+    // s5 = (c8, c13, c15, c14, c13, c11, c10, c9)
+    v[0] = c[9]; v[1] = c[10]; v[2] = c[11]; v[3] = c[13]; v[4] = c[14]; v[5] = c[15]; v[6] = c[13]; v[7] = c[8];
+    acc_add<0>(acc, v);
+    // s6 = (c10, c8, 0, 0, 0, c13, c12, c11)
+    v[0] = c[11]; v[1] = c[12]; v[2] = c[13]; v[3] = 0; v[4] = 0; v[5] = 0; v[6] = c[8]; v[7] = c[10];
+    acc_sub(acc, v);
+    // s7 = (c11, c9, 0, 0, c15, c14, c13, c12)
+    v[0] = c[12]; v[1] = c[13]; v[2] = c[14]; v[3] = c[15]; v[4] = 0; v[5] = 0; v[6] = c[9]; v[7] = c[11];
+    acc_sub(acc, v);
+    // s8 = (c12, 0, c10, c9, c8, c15, c14, c13)
+    v[0] = c[13]; v[1] = c[14]; v[2] = c[15]; v[3] = c[8]; v[4] = c[9]; v[5] = c[10]; v[6] = 0; v[7] = c[12];
+    acc_sub(acc, v);
+    // s9 = (c13, 0, c11, c10, c9, 0, c15, c14)
+    v[0] = c[14]; v[1] = c[15]; v[2] = 0; v[3] = c[9]; v[4] = c[10]; v[5] = c[11]; v[6] = 0; v[7] = c[13];
+    acc_sub(acc, v);
+    // fold o = acc[8] in [0, 13):  o*K = {o, 0, 0, -o, ~0, ~0, ~o, o-1}  (o >= 1; all-zero for o = 0)
+    uint32_t o = acc[8];
+    uint32_t m = o ? 0xFFFFFFFFu : 0u;
+    acc[0] = add_cc(acc[0], o);
+    acc[1] = addc_cc(acc[1], 0u);
+    acc[2] = addc_cc(acc[2], 0u);
+    acc[3] = addc_cc(acc[3], 0u - o);
+    acc[4] = addc_cc(acc[4], m);
+    acc[5] = addc_cc(acc[5], m);
+    acc[6] = addc_cc(acc[6], m & ~o);
+    acc[7] = addc_cc(acc[7], (o - 1u) & m);
+    uint32_t c2 = addc(0u, 0u);
+    (void)add_K(acc, c2);  // value was < 2^256 + 13*2^224: one more wrap at most, and none after it
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = acc[i];
   }
 
   ECG_D static void mul_body(Fe& r, const Fe& a, const Fe& b) {

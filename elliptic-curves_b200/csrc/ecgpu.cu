@@ -73,13 +73,21 @@ __device__ __forceinline__ uint32_t load_pair(uint32_t* k, Aff& P, bool& inf, co
 }
 
 // ------------------------------------------------------------------------------------------------
-// secp256k1 variable-base: one pair per thread, window table in shared memory (512 B / thread).
+// Per-thread window tables live in global memory, one slot per block: word w of entry e of thread t at
+// gtab[blockIdx*BLOCK*EW + (e*WPE + w)*BLOCK + t]  (EW = words per thread: 128 affine / 192 Jacobian).
+// A warp's access to one (e, w) of differing e per lane touches 32 distinct 4-byte words spread over at most 8
+// rows; the blocks resident at any time keep ~50 MB of tables live, which stays in the 126 MB L2.  Shared memory
+// was the first home of these tables (512-768 B/thread capped occupancy at 8-12 warps/SM); moving them out lets
+// registers set the occupancy (16-20 warps/SM) and measured +7 % (k256) / +16 % (P-256), tools/kbench.cu.
+#define K_TAB_WORDS 128  /* 8 affine entries  x 16 words */
+#define P_TAB_WORDS 192  /* 8 Jacobian entries x 24 words */
+
+// secp256k1 variable-base: one pair per thread.
 template <int BLOCK, int MINBLK>
 __global__ void __launch_bounds__(BLOCK, MINBLK)
     k256_varbase_kernel(const uint8_t* __restrict__ kb, const uint8_t* __restrict__ pxy,
                         const uint8_t* __restrict__ pinf, size_t n, uint32_t* __restrict__ jac,
-                        uint32_t* __restrict__ status, size_t base) {
-  extern __shared__ uint32_t smem[];
+                        uint32_t* __restrict__ gtab, uint32_t* __restrict__ status, size_t base) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   if (idx >= n) return;
   uint32_t k[8];
@@ -87,7 +95,7 @@ __global__ void __launch_bounds__(BLOCK, MINBLK)
   bool inf;
   uint32_t err = load_pair<CurveK256>(k, P, inf, kb, pxy, pinf, idx);
   if (err) report_error(status, err, base + idx);
-  TabRef tab{smem + threadIdx.x, (uint32_t)BLOCK};
+  TabRef tab{gtab + (size_t)blockIdx.x * BLOCK * K_TAB_WORDS + threadIdx.x, (uint32_t)BLOCK};
   Jac r;
   k256_mul_thread(r, k, P, tab);
   if (inf || err) FpK256::set_zero(r.Z);
@@ -97,14 +105,13 @@ __global__ void __launch_bounds__(BLOCK, MINBLK)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Generic prime-order curve (P-256) variable-base: Jacobian window table in shared memory (768 B / thread).
+// Generic prime-order curve (P-256) variable-base: Jacobian window table (768 B / thread).
 template <class C, int BLOCK, int MINBLK>
 __global__ void __launch_bounds__(BLOCK, MINBLK)
     generic_varbase_kernel(const uint8_t* __restrict__ kb, const uint8_t* __restrict__ pxy,
                            const uint8_t* __restrict__ pinf, size_t n, uint32_t* __restrict__ jac,
-                           uint32_t* __restrict__ status, size_t base) {
+                           uint32_t* __restrict__ gtab, uint32_t* __restrict__ status, size_t base) {
   typedef typename C::F F;
-  extern __shared__ uint32_t smem[];
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   if (idx >= n) return;
   uint32_t k[8];
@@ -112,7 +119,7 @@ __global__ void __launch_bounds__(BLOCK, MINBLK)
   bool inf;
   uint32_t err = load_pair<C>(k, P, inf, kb, pxy, pinf, idx);
   if (err) report_error(status, err, base + idx);
-  TabRefJ tab{smem + threadIdx.x, (uint32_t)BLOCK};
+  TabRefJ tab{gtab + (size_t)blockIdx.x * BLOCK * P_TAB_WORDS + threadIdx.x, (uint32_t)BLOCK};
   Jac r;
   generic_mul_thread<F, C::A_IS_MINUS3>(r, k, P, tab);
   if (inf || err) F::set_zero(r.Z);
@@ -206,9 +213,9 @@ template <class C, int BLOCK, int MINBLK, bool IS_K256>
 __global__ void __launch_bounds__(BLOCK, MINBLK)
     mul_gen_add_kernel(const uint8_t* __restrict__ ab, const uint8_t* __restrict__ kb,
                        const uint8_t* __restrict__ pxy, const uint8_t* __restrict__ pinf, size_t n,
-                       const uint32_t* __restrict__ table, uint32_t* __restrict__ jac, uint32_t* __restrict__ status, size_t base) {
+                       const uint32_t* __restrict__ table, uint32_t* __restrict__ jac, uint32_t* __restrict__ gtab,
+                       uint32_t* __restrict__ status, size_t base) {
   typedef typename C::F F;
-  extern __shared__ uint32_t smem[];
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   if (idx >= n) return;
   uint32_t k[8], a[8];
@@ -220,10 +227,10 @@ __global__ void __launch_bounds__(BLOCK, MINBLK)
   if (err) report_error(status, err, base + idx);
   Jac r;
   if (IS_K256) {
-    TabRef tab{smem + threadIdx.x, (uint32_t)BLOCK};
+    TabRef tab{gtab + (size_t)blockIdx.x * BLOCK * K_TAB_WORDS + threadIdx.x, (uint32_t)BLOCK};
     k256_mul_thread(r, k, P, tab);
   } else {
-    TabRefJ tab{smem + threadIdx.x, (uint32_t)BLOCK};
+    TabRefJ tab{gtab + (size_t)blockIdx.x * BLOCK * P_TAB_WORDS + threadIdx.x, (uint32_t)BLOCK};
     generic_mul_thread<F, C::A_IS_MINUS3>(r, k, P, tab);
   }
   if (inf) F::set_zero(r.Z);  // b * O = O, the sum is a*G
@@ -490,7 +497,7 @@ __global__ void __launch_bounds__(256) mb_fmul_kernel(uint32_t* out, int iters, 
 // mode uses lane 0 only (optionally on the caller's stream).  Host-pointer mode cuts every per-element batch
 // into chunks and alternates lanes, so the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the
 // kernels of chunk c (PCIe is the only thing between the caller's buffers and the SMs).
-enum { B_K = 0, B_P = 1, B_INF = 2, B_JAC = 3, B_SCR = 4, B_OUT = 5, B_OINF = 6, B_AUX = 7, B_A = 8, B_JAC2 = 9, B_COUNT = 10 };
+enum { B_K = 0, B_P = 1, B_INF = 2, B_JAC = 3, B_SCR = 4, B_OUT = 5, B_OINF = 6, B_AUX = 7, B_A = 8, B_JAC2 = 9, B_TAB = 10, B_COUNT = 11 };
 static const size_t HOST_CHUNK = (size_t)1 << 18;  // elements per pipelined chunk in host-pointer mode
 
 struct Lane {
@@ -800,29 +807,28 @@ static ecg_status launch_norm(ecg_ctx* ctx, DevState& d, Lane& L, ecg_curve curv
                                 : launch_normalize<FpP256>(ctx, d, L, n, jac, out, oinf);
 }
 
-// launch geometry of the variable-base kernels
-static const int K_BLOCK = 128, K_MINBLK = 3;  // secp256k1: 512 B smem/thread  -> 3 x 64 KiB per SM
-static const int P_BLOCK = 128, P_MINBLK = 2;  // P-256   : 768 B smem/thread  -> 2 x 96 KiB per SM
+// launch geometry of the variable-base kernels (registers set the occupancy; tables are in global memory)
+static const int K_BLOCK = 128, K_MINBLK = 5;  // secp256k1: <= 96 registers -> 20 warps/SM
+static const int P_BLOCK = 128, P_MINBLK = 4;  // P-256   : <= 128 registers -> 16 warps/SM
 
-template <class KernelT>
-static ecg_status set_smem(ecg_ctx* ctx, KernelT kernel, size_t smem) {
-  CU_TRY(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  return ECG_OK;
+// per-block window-table slots for a launch of n elements
+static ecg_status ensure_tab(ecg_ctx* ctx, Lane& L, ecg_curve curve, size_t n) {
+  size_t block = curve == ECG_SECP256K1 ? K_BLOCK : P_BLOCK;
+  size_t words = curve == ECG_SECP256K1 ? K_TAB_WORDS : P_TAB_WORDS;
+  size_t blocks = (n + block - 1) / block;
+  return ensure(ctx, L, B_TAB, blocks * block * words * 4);
 }
 
 // k*P for one chunk -> Jacobian SoA in `jac`; `status` / `base` locate validation errors
 static ecg_status launch_varbase(ecg_ctx* ctx, Lane& L, ecg_curve curve, size_t n, const DevPtrs& dp, uint32_t* jac,
                                  uint32_t* status, size_t base) {
+  ST_TRY(ensure_tab(ctx, L, curve, n));
+  uint32_t* gtab = (uint32_t*)L.buf[B_TAB];
   DOM_BEGIN(ctx, L);
-  if (curve == ECG_SECP256K1) {
-    size_t smem = (size_t)K_BLOCK * 8 * 16 * 4;
-    ST_TRY(set_smem(ctx, k256_varbase_kernel<K_BLOCK, K_MINBLK>, smem));
-    k256_varbase_kernel<K_BLOCK, K_MINBLK><<<grid_for(n, K_BLOCK), K_BLOCK, smem, L.s()>>>(dp.k, dp.p, dp.inf, n, jac, status, base);
-  } else {
-    size_t smem = (size_t)P_BLOCK * 8 * 24 * 4;
-    ST_TRY(set_smem(ctx, generic_varbase_kernel<CurveP256, P_BLOCK, P_MINBLK>, smem));
-    generic_varbase_kernel<CurveP256, P_BLOCK, P_MINBLK><<<grid_for(n, P_BLOCK), P_BLOCK, smem, L.s()>>>(dp.k, dp.p, dp.inf, n, jac, status, base);
-  }
+  if (curve == ECG_SECP256K1)
+    k256_varbase_kernel<K_BLOCK, K_MINBLK><<<grid_for(n, K_BLOCK), K_BLOCK, 0, L.s()>>>(dp.k, dp.p, dp.inf, n, jac, gtab, status, base);
+  else
+    generic_varbase_kernel<CurveP256, P_BLOCK, P_MINBLK><<<grid_for(n, P_BLOCK), P_BLOCK, 0, L.s()>>>(dp.k, dp.p, dp.inf, n, jac, gtab, status, base);
   LAUNCHED(ctx);
   DOM_END(ctx, L);
   return ECG_OK;
@@ -972,18 +978,14 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
       DOM_END(ctx, L);
       break;
     case BatchOp::MULGENADD:
+      ST_TRY(ensure_tab(ctx, L, op.curve, cnt));
       DOM_BEGIN(ctx, L);
-      if (k1) {
-        size_t smem = (size_t)K_BLOCK * 8 * 16 * 4;
-        ST_TRY(set_smem(ctx, mul_gen_add_kernel<CurveK256, K_BLOCK, K_MINBLK, true>, smem));
-        mul_gen_add_kernel<CurveK256, K_BLOCK, K_MINBLK, true><<<grid_for(cnt, K_BLOCK), K_BLOCK, smem, L.s()>>>(
-            dp.a, dp.k, dp.p, dp.inf, cnt, d.fb_table[op.curve], jac, L.status, off);
-      } else {
-        size_t smem = (size_t)P_BLOCK * 8 * 24 * 4;
-        ST_TRY(set_smem(ctx, mul_gen_add_kernel<CurveP256, P_BLOCK, P_MINBLK, false>, smem));
-        mul_gen_add_kernel<CurveP256, P_BLOCK, P_MINBLK, false><<<grid_for(cnt, P_BLOCK), P_BLOCK, smem, L.s()>>>(
-            dp.a, dp.k, dp.p, dp.inf, cnt, d.fb_table[op.curve], jac, L.status, off);
-      }
+      if (k1)
+        mul_gen_add_kernel<CurveK256, K_BLOCK, K_MINBLK, true><<<grid_for(cnt, K_BLOCK), K_BLOCK, 0, L.s()>>>(
+            dp.a, dp.k, dp.p, dp.inf, cnt, d.fb_table[op.curve], jac, (uint32_t*)L.buf[B_TAB], L.status, off);
+      else
+        mul_gen_add_kernel<CurveP256, P_BLOCK, P_MINBLK, false><<<grid_for(cnt, P_BLOCK), P_BLOCK, 0, L.s()>>>(
+            dp.a, dp.k, dp.p, dp.inf, cnt, d.fb_table[op.curve], jac, (uint32_t*)L.buf[B_TAB], L.status, off);
       LAUNCHED(ctx);
       DOM_END(ctx, L);
       break;

@@ -62,6 +62,26 @@ def test_field_mul_extremes(sim):
             assert _feop(sim, "p256", 2, a, b) == a * b % pyref.P256.p
 
 
+def test_field_mul_structured_stress(sim):
+    """limbs drawn from {0, 1, ~0, ~0-1, random}: drives every carry / overflow-fold path of both reductions"""
+    rng = random.Random(123)
+
+    def structured():
+        v = 0
+        for i in range(8):
+            c = rng.random()
+            w = 0 if c < 0.3 else 0xFFFFFFFF if c < 0.6 else 1 if c < 0.65 else 0xFFFFFFFE if c < 0.7 else rng.getrandbits(32)
+            v |= w << (32 * i)
+        return v
+
+    for curve in ("k256", "p256"):
+        p = pyref.CURVES[curve].p
+        for _ in range(3000):
+            a, b = structured(), structured()
+            assert _feop(sim, curve, 2, a, b) == a * b % p
+            assert _feop(sim, curve, 3, a) == a * a % p
+
+
 def test_glv_split_matches_reference_definition(sim):
     rng = random.Random(2)
     n = pyref.K256.n

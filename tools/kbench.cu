@@ -46,6 +46,31 @@ __global__ void __launch_bounds__(BLOCK, MINBLK) kb_varbase(size_t n, uint32_t* 
   }
 }
 
+template <class F, int BLOCK, int MINBLK, bool GLOBAL_TAB>
+__global__ void __launch_bounds__(BLOCK, MINBLK) kb_generic(size_t n, uint32_t* __restrict__ jac, uint32_t* __restrict__ gtab) {
+  extern __shared__ uint32_t smem[];
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n) return;
+  uint32_t k[8];
+  Aff P;
+  make_inputs(k, P, idx);
+  CurveP256::generator(P);
+  Jac r;
+  if (GLOBAL_TAB) {
+    size_t slot = ((size_t)blockIdx.x % (148 * 8)) * BLOCK;
+    TabRefJ tab{gtab + slot * 192 + threadIdx.x, (uint32_t)BLOCK};
+    generic_mul_thread<F, true>(r, k, P, tab);
+  } else {
+    TabRefJ tab{smem + threadIdx.x, (uint32_t)BLOCK};
+    generic_mul_thread<F, true>(r, k, P, tab);
+  }
+  for (int w = 0; w < 8; w++) {
+    jac[(size_t)w * n + idx] = r.X.v[w];
+    jac[(size_t)(8 + w) * n + idx] = r.Y.v[w];
+    jac[(size_t)(16 + w) * n + idx] = r.Z.v[w];
+  }
+}
+
 template <class F>
 __global__ void __launch_bounds__(256) kb_fmul(uint32_t* out, int iters, uint32_t seed, int mode) {
   Fe a, b;
@@ -58,6 +83,59 @@ __global__ void __launch_bounds__(256) kb_fmul(uint32_t* out, int iters, uint32_
   uint32_t s = 0;
   for (int i = 0; i < 8; i++) s ^= a.v[i] ^ b.v[i];
   if (s == 0x12345678u) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) kb_dfma(double* out, int iters, double seed) {
+  double a = seed + threadIdx.x, b = 1.0000001, c = 0.5;
+  double r[8];
+  for (int i = 0; i < 8; i++) r[i] = a + i;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) r[i] = __fma_rz(r[i], b, c);
+    }
+  }
+  double s = 0;
+  for (int i = 0; i < 8; i++) s += r[i];
+  if (s == 12345.678) out[0] = s;
+}
+// DFMA and IMAD.WIDE issued from the same warps: do the FP64 and FMA-heavy pipes overlap?
+__global__ void __launch_bounds__(256) kb_mix(double* out, int iters, double seed, uint32_t iseed) {
+  double b = 1.0000001, c = 0.5;
+  double r[8];
+  for (int i = 0; i < 8; i++) r[i] = seed + threadIdx.x + i;
+  uint32_t a0 = iseed + threadIdx.x, a1 = a0 * 3 + 1, b0 = iseed ^ 0x9E3779B9u, b1 = b0 + blockIdx.x;
+  uint32_t q[16];
+  for (int i = 0; i < 16; i++) q[i] = a0 + i;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      mad_wide_cc(q[0], q[1], a0, b0);
+      r[0] = __fma_rz(r[0], b, c); r[1] = __fma_rz(r[1], b, c);
+      madc_wide_cc(q[2], q[3], a1, b0);
+      r[2] = __fma_rz(r[2], b, c); r[3] = __fma_rz(r[3], b, c);
+      madc_wide_cc(q[4], q[5], a0, b1);
+      r[4] = __fma_rz(r[4], b, c); r[5] = __fma_rz(r[5], b, c);
+      madc_wide_cc(q[6], q[7], a1, b1);
+      r[6] = __fma_rz(r[6], b, c); r[7] = __fma_rz(r[7], b, c);
+      mad_wide_cc(q[8], q[9], a1, b0);
+      r[0] = __fma_rz(r[0], b, c); r[1] = __fma_rz(r[1], b, c);
+      madc_wide_cc(q[10], q[11], a0, b1);
+      r[2] = __fma_rz(r[2], b, c); r[3] = __fma_rz(r[3], b, c);
+      madc_wide_cc(q[12], q[13], a1, b1);
+      r[4] = __fma_rz(r[4], b, c); r[5] = __fma_rz(r[5], b, c);
+      madc_wide_cc(q[14], q[15], a0, b0);
+      r[6] = __fma_rz(r[6], b, c); r[7] = __fma_rz(r[7], b, c);
+    }
+  }
+  double s = 0;
+  uint32_t x = 0;
+  for (int i = 0; i < 8; i++) s += r[i];
+  for (int i = 0; i < 16; i++) x ^= q[i];
+  if (s == 12345.678 && x == 77) out[0] = s;
 }
 
 static uint64_t checksum(const std::vector<uint32_t>& v) {
@@ -95,6 +173,34 @@ static void run(const char* name, size_t n, uint32_t* jac, uint32_t* gtab) {
          n / (best * 1e-3), (unsigned long long)checksum(h));
 }
 
+template <class F, int BLOCK, int MINBLK, bool GLOBAL_TAB>
+static void runp(const char* name, size_t n, uint32_t* jac, uint32_t* gtab) {
+  size_t smem = GLOBAL_TAB ? 0 : (size_t)BLOCK * 192 * 4;
+  auto kern = kb_generic<F, BLOCK, MINBLK, GLOBAL_TAB>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, kern));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem));
+  unsigned grid = (unsigned)((n + BLOCK - 1) / BLOCK);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    CK(cudaEventRecord(e0));
+    kern<<<grid, BLOCK, smem>>>(n, jac, gtab);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  std::vector<uint32_t> h(24 * 4096);
+  for (int w = 0; w < 24; w++) CK(cudaMemcpy(&h[w * 4096], jac + (size_t)w * n, 4096 * 4, cudaMemcpyDeviceToHost));
+  printf("%-34s regs %3d  blocks/SM %d  warps/SM %2d  %8.3f ms  %.4g mults/s  chk %016llx\n", name, fa.numRegs, occ, occ * BLOCK / 32, best,
+         n / (best * 1e-3), (unsigned long long)checksum(h));
+}
+
 template <class F>
 static void run_fmul(const char* name) {
   uint32_t* out; CK(cudaMalloc(&out, 256));
@@ -116,8 +222,24 @@ int main(int argc, char** argv) {
   size_t n = (size_t)1 << (argc > 1 ? atoi(argv[1]) : 20);
   uint32_t *jac, *gtab;
   CK(cudaMalloc(&jac, n * 96));
-  CK(cudaMalloc(&gtab, (size_t)148 * 8 * 256 * 128 * 4));
+  CK(cudaMalloc(&gtab, (size_t)148 * 8 * 256 * 192 * 4));
   printf("n = %zu\n", n);
+  {
+    double* dout; CK(cudaMalloc(&dout, 256));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int which = 0; which < 2; which++) {
+      float best = 1e30f; int iters = 4000; unsigned blocks = 148 * 8;
+      for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(e0));
+        if (which == 0) kb_dfma<<<blocks, 256>>>(dout, iters, 1.5 + rep); else kb_mix<<<blocks, 256>>>(dout, iters, 1.5 + rep, 99u + rep);
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+      }
+      if (which == 0) printf("DFMA: %.4g /s (%.3f ms)\n", (double)blocks * 256 * iters * 64 / (best * 1e-3), best);
+      else printf("mix: %.4g IMAD.WIDE/s + %.4g DFMA/s concurrently (%.3f ms)\n", (double)blocks * 256 * iters * 32 / (best * 1e-3), (double)blocks * 256 * iters * 64 / (best * 1e-3), best);
+    }
+  }
   run_fmul<FpK256T<0>>("fmul inline mul8x8");
   run_fmul<FpK256T<1>>("fmul inline sqr8");
   run_fmul<FpK256T<3>>("fmul call sqr8");
@@ -131,6 +253,13 @@ int main(int argc, char** argv) {
   run<FpK256T<3>, 128, 4, true>("v3 call,   sqr8      (128,4) gtab", n, jac, gtab);
   run<FpK256T<3>, 128, 5, true>("v3 call,   sqr8      (128,5) gtab", n, jac, gtab);
   run<FpK256T<3>, 256, 2, true>("v3 call,   sqr8      (256,2) gtab", n, jac, gtab);
-  run<FpK256T<1>, 128, 4, true>("v1 inline, sqr8      (128,4) gtab", n, jac, gtab);
+  run<FpK256T<3>, 128, 4, true>("v3 call,   sqr8      (128,4) gtab", n, jac, gtab);
+  run_fmul<FpP256T<1>>("p256 fmul inline");
+  run_fmul<FpP256T<3>>("p256 fmul call");
+  runp<FpP256T<1>, 128, 2, false>("p256 inline (128,2) smem", n, jac, gtab);
+  runp<FpP256T<3>, 128, 2, false>("p256 call   (128,2) smem", n, jac, gtab);
+  runp<FpP256T<3>, 128, 3, true>("p256 call   (128,3) gtab", n, jac, gtab);
+  runp<FpP256T<3>, 128, 4, true>("p256 call   (128,4) gtab", n, jac, gtab);
+  runp<FpP256T<1>, 128, 3, true>("p256 inline (128,3) gtab", n, jac, gtab);
   return 0;
 }
