@@ -1,0 +1,325 @@
+// ecg_msm.cuh — bucket-method (Pippenger) multi-scalar multiplication kernels: sum_i k_i * P_i for large n.
+//
+// Replaces LinearCombination::lincomb / lincomb_vartime for big slices (k256/src/arithmetic/mul.rs:66-175,
+// primeorder/src/projective.rs:480-557).  The reference walks all terms through shared doublings (Straus, 2 KiB of
+// tables per term); with 2^21 terms per GPU the bucket method needs ~16 mixed additions per term instead of a full
+// scalar multiplication:
+//   1. msm_prep_kernel      validate, GLV-split (secp256k1), cut every half-scalar into c-bit signed digits, count
+//                           how many points fall in each (window, |digit|) bucket             [atomics on counters]
+//   2. msm_scan_kernel      exclusive prefix sum of the counters                              [one block]
+//   3. msm_scatter_kernel   write each (point, sign) reference into its bucket's slice        [counting sort]
+//   4. msm_bucket_kernel    one thread per bucket: gather its points, mixed-add them           [the hot kernel]
+//   5. msm_wreduce_kernel   per window sum_j j*B_j by chunked running sums (recursive on the chunk totals)
+//   6. msm_horner_kernel    result = sum_w 2^(c w) R_w
+// Everything is order-independent group arithmetic, so the (affine, canonical) result is bit-identical to the
+// reference's whatever order the atomics produce.
+#pragma once
+#include "ecg_curves.cuh"
+#include "ecg_mul.cuh"
+
+namespace ecg {
+
+struct MsmGeom {
+  int c;          // window bits
+  int W;          // windows per sub-scalar
+  int nbits;      // bits per sub-scalar magnitude (128 with GLV, 256 without)
+  uint32_t nbw;   // bucket slots per window: digits 0 .. 2^(c+1)+1 (slot 0 unused)
+};
+
+// bits [pos, pos+width) of an up-to-288-bit little-endian limb array (9 limbs), width <= 17
+ECG_D uint32_t msm_bits(const uint32_t* m, int pos, int width) {
+  int w = pos >> 5, b = pos & 31;
+  uint64_t lo = m[w];
+  uint64_t hi = (w + 1 < 9) ? m[w + 1] : 0;
+  uint64_t v = (lo | (hi << 32)) >> b;
+  return (uint32_t)(v & ((1u << width) - 1u));
+}
+
+// Signed c-bit digits of a magnitude m (9 limbs, < 2^nbits (+1 bit of slack)): windows 0..W-2 in
+// [-2^(c-1)+1, 2^(c-1)], the top window unsigned (absorbs the carry and any slack bit).  out[w] = digit.
+ECG_D void msm_recode(int32_t* out, const uint32_t* m, const MsmGeom& g) {
+  uint32_t carry = 0;
+  const uint32_t half = 1u << (g.c - 1);
+  for (int w = 0; w < g.W - 1; w++) {
+    uint32_t v = msm_bits(m, g.c * w, g.c) + carry;
+    if (v > half) {
+      out[w] = (int32_t)v - (int32_t)(1u << g.c);
+      carry = 1;
+    } else {
+      out[w] = (int32_t)v;
+      carry = 0;
+    }
+  }
+  int top = g.c * (g.W - 1);
+  int width = g.nbits + 1 - top;  // one slack bit
+  if (width > 17) width = 17;
+  out[g.W - 1] = (int32_t)(msm_bits(m, top, width) + carry);
+}
+
+#if defined(__CUDACC__)
+
+// pts: sub-point j at pts[j*16 .. j*16+15] (x[8], y[8], internal form).  digits: sub-term j, window w at
+// digits[w * nsub + j] (signed, the sub-scalar's own sign already folded in; 0 = nothing to add).
+template <class C, bool GLV>
+__global__ void __launch_bounds__(128)
+    msm_prep_kernel(const uint8_t* __restrict__ kb, const uint8_t* __restrict__ pxy, const uint8_t* __restrict__ pinf,
+                    size_t n, MsmGeom g, uint32_t* __restrict__ pts, int32_t* __restrict__ digits,
+                    uint32_t* __restrict__ count, uint32_t* __restrict__ status, size_t base) {
+  typedef typename C::F F;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const size_t nsub = GLV ? 2 * n : n;
+  uint32_t k[8], m[9];
+  Aff P;
+  bool skip = false;
+  {
+    uint32_t err = 0;
+    load_be32(k, kb + 32 * idx);
+    if (!lt8(k, C::N())) err |= 1u;
+    bool inf = pinf != nullptr && pinf[idx] != 0;
+    Fe x, y;
+    load_be32(x.v, pxy + 64 * idx);
+    load_be32(y.v, pxy + 64 * idx + 32);
+    F::from_canonical(P.x, x);
+    F::from_canonical(P.y, y);
+    if (!inf) {
+      bool ok = lt8(x.v, C::P()) && lt8(y.v, C::P());
+      if (ok) {
+        Fe b;
+        C::b_internal(b);
+        ok = aff_on_curve<F, C::A_IS_MINUS3>(P, b);
+      }
+      if (!ok) err |= 2u;
+    }
+    if (err) {
+      atomicOr(&status[0], err);
+      size_t gi = base + idx;
+      atomicMin(&status[1], (uint32_t)(gi > 0xFFFFFFFEull ? 0xFFFFFFFEull : gi));
+    }
+    skip = inf || err != 0;
+  }
+  int32_t dg[33];
+  const int nh = GLV ? 2 : 1;
+  GlvHalf h1, h2;
+  if (GLV) {
+    // magnitudes are recovered from the signed-odd form kept by glv_split_k256: |k_i| = 2h + 1 - even
+    glv_split_k256(h1, h2, k);
+  }
+  for (int half = 0; half < nh; half++) {
+    size_t j = GLV ? 2 * idx + half : idx;
+    uint32_t neg = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) m[i] = 0;
+    if (GLV) {
+      const GlvHalf& h = half ? h2 : h1;
+      // m = 2h + 1 - even
+      uint32_t t[5];
+      t[0] = (h.h[0] << 1) | 1u;
+      t[1] = (h.h[1] << 1) | (h.h[0] >> 31);
+      t[2] = (h.h[2] << 1) | (h.h[1] >> 31);
+      t[3] = (h.h[3] << 1) | (h.h[2] >> 31);
+      t[4] = h.h[3] >> 31;
+      m[0] = sub_cc(t[0], h.even);
+      m[1] = subc_cc(t[1], 0);
+      m[2] = subc_cc(t[2], 0);
+      m[3] = subc_cc(t[3], 0);
+      m[4] = subc(t[4], 0);
+      neg = h.neg;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) m[i] = k[i];
+    }
+    // sub-point: P or (beta x, y)
+    Fe px = P.x;
+    if (GLV && half) {
+      Fe beta;
+      k256_beta(beta);
+      F::mul(px, px, beta);
+    }
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      pts[j * 16 + w] = px.v[w];
+      pts[j * 16 + 8 + w] = P.y.v[w];
+    }
+    msm_recode(dg, m, g);
+    for (int w = 0; w < g.W; w++) {
+      int32_t d = skip ? 0 : dg[w];
+      if (neg) d = -d;
+      digits[(size_t)w * nsub + j] = d;
+      if (d != 0) {
+        uint32_t a = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+        atomicAdd(&count[(size_t)w * g.nbw + a], 1u);
+      }
+    }
+  }
+}
+
+// exclusive scan of count[0..m) into offset[0..m]; one block of 1024 threads, serial over chunks
+__global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restrict__ count, uint32_t* __restrict__ offset, size_t m) {
+  __shared__ uint32_t part[1024];
+  size_t per = (m + 1023) / 1024;
+  size_t lo = threadIdx.x * per, hi = lo + per < m ? lo + per : m;
+  uint32_t s = 0;
+  for (size_t i = lo; i < hi; i++) s += count[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int i = 0; i < 1024; i++) {
+      uint32_t t = part[i];
+      part[i] = run;
+      run += t;
+    }
+    offset[m] = run;
+  }
+  __syncthreads();
+  uint32_t run = part[threadIdx.x];
+  for (size_t i = lo; i < hi; i++) {
+    offset[i] = run;
+    run += count[i];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    msm_scatter_kernel(const int32_t* __restrict__ digits, size_t nsub, MsmGeom g, const uint32_t* __restrict__ offset,
+                       uint32_t* __restrict__ cursor, uint32_t* __restrict__ list) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nsub) return;
+  for (int w = 0; w < g.W; w++) {
+    int32_t d = digits[(size_t)w * nsub + j];
+    if (d == 0) continue;
+    uint32_t a = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    size_t key = (size_t)w * g.nbw + a;
+    uint32_t pos = atomicAdd(&cursor[key], 1u);
+    list[offset[key] + pos] = ((uint32_t)j << 1) | (d < 0 ? 1u : 0u);
+  }
+}
+
+__device__ __forceinline__ void msm_load_point(Aff& e, const uint32_t* __restrict__ pts, uint32_t j) {
+  const uint4* p = reinterpret_cast<const uint4*>(pts + (size_t)j * 16);
+  uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+  e.x.v[0] = a.x; e.x.v[1] = a.y; e.x.v[2] = a.z; e.x.v[3] = a.w;
+  e.x.v[4] = b.x; e.x.v[5] = b.y; e.x.v[6] = b.z; e.x.v[7] = b.w;
+  e.y.v[0] = c.x; e.y.v[1] = c.y; e.y.v[2] = c.z; e.y.v[3] = c.w;
+  e.y.v[4] = d.x; e.y.v[5] = d.y; e.y.v[6] = d.z; e.y.v[7] = d.w;
+}
+
+// One thread per bucket: B = sum of its (signed) points.  bkt: SoA Jacobian over nb = W*nbw buckets.
+template <class C>
+__global__ void __launch_bounds__(128, 4)
+    msm_bucket_kernel(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ list, const uint32_t* __restrict__ offset,
+                      size_t nb, uint32_t* __restrict__ bkt) {
+  typedef typename C::F F;
+  size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  uint32_t lo = offset[b], hi = offset[b + 1];
+  Jac acc;
+  F::set_zero(acc.X);
+  F::set_one(acc.Y);
+  F::set_zero(acc.Z);
+  if (lo < hi) {
+    uint32_t ent = list[lo];
+    Aff e;
+    msm_load_point(e, pts, ent >> 1);
+    fe_cneg<F>(e.y, ent & 1u);
+    acc.X = e.x;
+    acc.Y = e.y;
+    F::set_one(acc.Z);
+#pragma unroll 1
+    for (uint32_t i = lo + 1; i < hi; i++) {
+      ent = list[i];
+      msm_load_point(e, pts, ent >> 1);
+      fe_cneg<F>(e.y, ent & 1u);
+      jac_madd<F, C::A_IS_MINUS3>(acc, acc, e);
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    bkt[(size_t)w * nb + b] = acc.X.v[w];
+    bkt[(size_t)(8 + w) * nb + b] = acc.Y.v[w];
+    bkt[(size_t)(16 + w) * nb + b] = acc.Z.v[w];
+  }
+}
+
+__device__ __forceinline__ void msm_jload(Jac& p, const uint32_t* __restrict__ a, size_t n, size_t i) {
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    p.X.v[w] = a[(size_t)w * n + i];
+    p.Y.v[w] = a[(size_t)(8 + w) * n + i];
+    p.Z.v[w] = a[(size_t)(16 + w) * n + i];
+  }
+}
+__device__ __forceinline__ void msm_jstore(uint32_t* __restrict__ a, size_t n, size_t i, const Jac& p) {
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    a[(size_t)w * n + i] = p.X.v[w];
+    a[(size_t)(8 + w) * n + i] = p.Y.v[w];
+    a[(size_t)(16 + w) * n + i] = p.Z.v[w];
+  }
+}
+
+// Weighted reduction level.  Input: W rows of `len` Jacobian points (element (w, j) at index w*stride_in + off + j,
+// weight j+1).  Thread (w, ch) covers j in [ch*CH, min(len, (ch+1)*CH)) from the top down with the running-sum
+// trick and writes  T = sum (j - ch*CH + 1) A_j  and  S = sum A_j  at index w*nch + ch of outT / outS.
+#define MSM_CH 64
+template <class C>
+__global__ void __launch_bounds__(128)
+    msm_wreduce_kernel(const uint32_t* __restrict__ in, size_t n_in, size_t stride_in, size_t off, size_t len, int W, size_t nch,
+                       uint32_t* __restrict__ outT, uint32_t* __restrict__ outS) {
+  typedef typename C::F F;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)W * nch) return;
+  size_t w = t / nch, ch = t % nch;
+  size_t lo = ch * MSM_CH, hi = lo + MSM_CH < len ? lo + MSM_CH : len;
+  Jac S, T, p;
+  F::set_zero(S.X);
+  F::set_one(S.Y);
+  F::set_zero(S.Z);
+  T = S;
+  for (size_t j = hi; j > lo; j--) {
+    msm_jload(p, in, n_in, w * stride_in + off + (j - 1));
+    jac_add<F, C::A_IS_MINUS3>(S, S, p);
+    jac_add<F, C::A_IS_MINUS3>(T, T, S);
+  }
+  size_t n_out = (size_t)W * nch;
+  msm_jstore(outT, n_out, t, T);
+  msm_jstore(outS, n_out, t, S);
+}
+
+// R[w] = sumT[w] + CH * (Rnext[w] - Stot[w])     (combine one recursion level; all arrays have W entries)
+template <class C>
+__global__ void __launch_bounds__(32)
+    msm_combine_kernel(const uint32_t* __restrict__ sumT, const uint32_t* __restrict__ Rnext, const uint32_t* __restrict__ Stot, int W,
+                       uint32_t* __restrict__ R) {
+  typedef typename C::F F;
+  int w = threadIdx.x;
+  if (w >= W) return;
+  Jac a, b, s;
+  msm_jload(a, sumT, W, w);
+  msm_jload(b, Rnext, W, w);
+  msm_jload(s, Stot, W, w);
+  F::neg(s.Y, s.Y);
+  jac_add<F, C::A_IS_MINUS3>(b, b, s);
+  for (int i = 0; i < 6; i++) jac_dbl<F, C::A_IS_MINUS3>(b, b);  // x MSM_CH = 2^6
+  jac_add<F, C::A_IS_MINUS3>(a, a, b);
+  msm_jstore(R, W, w, a);
+}
+
+// out (n = 1 SoA) = sum_w 2^(c w) R[w]
+template <class C>
+__global__ void __launch_bounds__(32) msm_horner_kernel(const uint32_t* __restrict__ R, int W, int c, uint32_t* __restrict__ out) {
+  typedef typename C::F F;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Jac acc, p;
+  msm_jload(acc, R, W, W - 1);
+  for (int w = W - 2; w >= 0; w--) {
+    for (int i = 0; i < c; i++) jac_dbl<F, C::A_IS_MINUS3>(acc, acc);
+    msm_jload(p, R, W, w);
+    jac_add<F, C::A_IS_MINUS3>(acc, acc, p);
+  }
+  msm_jstore(out, 1, 0, acc);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace ecg

@@ -14,6 +14,7 @@
 #include "ecg_curves.cuh"
 #include "ecg_io.cuh"
 #include "ecg_mul.cuh"
+#include "ecg_msm.cuh"
 
 using namespace ecg;
 
@@ -497,7 +498,7 @@ __global__ void __launch_bounds__(256) mb_fmul_kernel(uint32_t* out, int iters, 
 // mode uses lane 0 only (optionally on the caller's stream).  Host-pointer mode cuts every per-element batch
 // into chunks and alternates lanes, so the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the
 // kernels of chunk c (PCIe is the only thing between the caller's buffers and the SMs).
-enum { B_K = 0, B_P = 1, B_INF = 2, B_JAC = 3, B_SCR = 4, B_OUT = 5, B_OINF = 6, B_AUX = 7, B_A = 8, B_JAC2 = 9, B_TAB = 10, B_COUNT = 11 };
+enum { B_K = 0, B_P = 1, B_INF = 2, B_JAC = 3, B_SCR = 4, B_OUT = 5, B_OINF = 6, B_AUX = 7, B_A = 8, B_JAC2 = 9, B_TAB = 10, B_MSM = 11, B_COUNT = 12 };
 static const size_t HOST_CHUNK = (size_t)1 << 18;  // elements per pipelined chunk in host-pointer mode
 
 struct Lane {
@@ -1150,6 +1151,146 @@ static ecg_status reduce_points_c(ecg_ctx* ctx, Lane& L, ecg_curve curve, uint32
   return curve == ECG_SECP256K1 ? reduce_points<CurveK256>(ctx, L, a, b, n, result) : reduce_points<CurveP256>(ctx, L, a, b, n, result);
 }
 
+// ---- bucket-method lincomb (ecg_msm.cuh) ------------------------------------------------------------
+static const size_t MSM_MIN_TERMS = (size_t)1 << 13;   // below this the per-term kernel + tree sum is faster
+static const size_t MSM_MAX_TERMS = (size_t)1 << 24;   // per call (32-bit list offsets); larger shards are cut
+
+// out[w*out_len + q] = sum of in[w*row_len + q*64 .. +64)   (plain row sums of Jacobian points, W rows)
+template <class C>
+__global__ void __launch_bounds__(128)
+    msm_rowsum_kernel(const uint32_t* __restrict__ in, size_t row_len, int W, uint32_t* __restrict__ out, size_t out_len) {
+  typedef typename C::F F;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)W * out_len) return;
+  size_t w = t / out_len, q = t % out_len;
+  size_t lo = q * 64, hi = lo + 64 < row_len ? lo + 64 : row_len;
+  Jac acc, p;
+  F::set_zero(acc.X);
+  F::set_one(acc.Y);
+  F::set_zero(acc.Z);
+  size_t n_in = (size_t)W * row_len;
+  for (size_t j = lo; j < hi; j++) {
+    msm_jload(p, in, n_in, w * row_len + j);
+    jac_add<F, C::A_IS_MINUS3>(acc, acc, p);
+  }
+  msm_jstore(out, (size_t)W * out_len, t, acc);
+}
+
+static MsmGeom msm_geometry(ecg_curve curve, size_t n) {
+  MsmGeom g;
+  bool glv = curve == ECG_SECP256K1;
+  size_t nsub = glv ? 2 * n : n;
+  int lg = 0;
+  while (((size_t)1 << (lg + 1)) <= nsub) lg++;
+  g.c = std::min(16, std::max(8, lg - 5));
+  g.nbits = glv ? 128 : 256;
+  g.W = (g.nbits + g.c - 1) / g.c;
+  g.nbw = ((uint32_t)1 << (g.c + 1)) + 2;
+  return g;
+}
+
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  template <class T>
+  T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+template <class C, bool GLV>
+static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, size_t base, const MsmGeom& g, uint32_t** result) {
+  const size_t nsub = GLV ? 2 * n : n;
+  const size_t nb = (size_t)g.W * g.nbw;
+  // recursion geometry of the weighted reduction
+  std::vector<size_t> lens, nchs;
+  size_t len = g.nbw - 1;
+  for (;;) {
+    size_t nch = (len + MSM_CH - 1) / MSM_CH;
+    lens.push_back(len);
+    nchs.push_back(nch);
+    if (nch == 1) break;
+    len = nch;
+  }
+  const int levels = (int)lens.size();
+  // carve the scratch arena (first pass sizes it, second pass hands out pointers)
+  uint32_t *pts = nullptr, *count = nullptr, *cursor = nullptr, *offset = nullptr, *list = nullptr, *bkt = nullptr, *res = nullptr;
+  int32_t* digits = nullptr;
+  std::vector<uint32_t*> T(levels), S(levels), sumT(levels), tmp(levels), R(levels);
+  for (int pass = 0; pass < 2; pass++) {
+    Carver cv{pass ? (uint8_t*)L.buf[B_MSM] : nullptr};
+    pts = cv.take<uint32_t>(nsub * 16);
+    digits = cv.take<int32_t>(nsub * (size_t)g.W);
+    count = cv.take<uint32_t>(2 * nb + 2);  // count | cursor, cleared together
+    cursor = count ? count + nb + 1 : nullptr;
+    offset = cv.take<uint32_t>(nb + 1);
+    list = cv.take<uint32_t>(nsub * (size_t)g.W);
+    bkt = cv.take<uint32_t>(nb * 24);
+    for (int l = 0; l < levels; l++) {
+      T[l] = cv.take<uint32_t>((size_t)g.W * nchs[l] * 24);
+      S[l] = cv.take<uint32_t>((size_t)g.W * nchs[l] * 24);
+      sumT[l] = cv.take<uint32_t>((size_t)g.W * 24);
+      tmp[l] = cv.take<uint32_t>((size_t)g.W * ((nchs[l] + 63) / 64) * 24);
+      R[l] = cv.take<uint32_t>((size_t)g.W * 24);
+    }
+    res = cv.take<uint32_t>(24);
+    if (pass == 0) ST_TRY(ensure(ctx, L, B_MSM, cv.off + 256));
+  }
+  CU_TRY(ctx, cudaMemsetAsync(count, 0, (2 * nb + 2) * 4, L.s()));
+  msm_prep_kernel<C, GLV><<<grid_for(n, 128), 128, 0, L.s()>>>(dp.k, dp.p, dp.inf, n, g, pts, digits, count, L.status, base);
+  LAUNCHED(ctx);
+  msm_scan_kernel<<<1, 1024, 0, L.s()>>>(count, offset, nb);
+  LAUNCHED(ctx);
+  msm_scatter_kernel<<<grid_for(nsub, 256), 256, 0, L.s()>>>(digits, nsub, g, offset, cursor, list);
+  LAUNCHED(ctx);
+  DOM_BEGIN(ctx, L);
+  msm_bucket_kernel<C><<<grid_for(nb, 128), 128, 0, L.s()>>>(pts, list, offset, nb, bkt);
+  LAUNCHED(ctx);
+  DOM_END(ctx, L);
+  // weighted reduction, level by level
+  for (int l = 0; l < levels; l++) {
+    const uint32_t* in = l == 0 ? bkt : S[l - 1];
+    size_t n_in = l == 0 ? nb : (size_t)g.W * nchs[l - 1];
+    size_t stride = l == 0 ? g.nbw : nchs[l - 1];
+    size_t off = l == 0 ? 1 : 0;
+    msm_wreduce_kernel<C><<<grid_for((size_t)g.W * nchs[l], 128), 128, 0, L.s()>>>(in, n_in, stride, off, lens[l], g.W, nchs[l], T[l], S[l]);
+    LAUNCHED(ctx);
+    // sumT[l][w] = sum_ch T[l][w][ch]
+    const uint32_t* cur = T[l];
+    size_t row = nchs[l];
+    if (row == 1) {
+      sumT[l] = T[l];
+    } else {
+      while (row > 1) {
+        size_t out_len = (row + 63) / 64;
+        uint32_t* dst = out_len == 1 ? sumT[l] : tmp[l];
+        msm_rowsum_kernel<C><<<grid_for((size_t)g.W * out_len, 128), 128, 0, L.s()>>>(cur, row, g.W, dst, out_len);
+        LAUNCHED(ctx);
+        if (out_len > 1 && cur == tmp[l]) {  // would need a third pass (row > 4096): not reachable for c <= 16
+          ctx->err = "msm: weighted-reduction row too long";
+          return ECG_EINVAL;
+        }
+        cur = dst;
+        row = out_len;
+      }
+    }
+  }
+  // unwind: R[last] = sumT[last]; R[l] = sumT[l] + CH * (R[l+1] - Btot),  Btot = S[last]
+  uint32_t* Rcur = sumT[levels - 1];
+  for (int l = levels - 2; l >= 0; l--) {
+    msm_combine_kernel<C><<<1, 32, 0, L.s()>>>(sumT[l], Rcur, S[levels - 1], g.W, R[l]);
+    LAUNCHED(ctx);
+    Rcur = R[l];
+  }
+  msm_horner_kernel<C><<<1, 32, 0, L.s()>>>(Rcur, g.W, g.c, res);
+  LAUNCHED(ctx);
+  *result = res;
+  return ECG_OK;
+}
+
 // one shard -> one Jacobian point left in *result (SoA with n = 1, i.e. 24 consecutive words), on lane 0
 static ecg_status lincomb_shard(ecg_ctx* ctx, DevState& d, ecg_curve curve, const Shard& sh, const uint8_t* k,
                                 const uint8_t* P_xy, const uint8_t* P_inf, uint32_t** result) {
@@ -1159,6 +1300,34 @@ static ecg_status lincomb_shard(ecg_ctx* ctx, DevState& d, ecg_curve curve, cons
   ST_TRY(stage_in(ctx, L, B_K, k, sh.off, sh.cnt, 32, &dp.k));
   ST_TRY(stage_in(ctx, L, B_P, P_xy, sh.off, sh.cnt, 64, &dp.p));
   ST_TRY(stage_in(ctx, L, B_INF, P_inf, sh.off, sh.cnt, 1, &dp.inf));
+  if (sh.cnt >= MSM_MIN_TERMS) {
+    // bucket method, in pieces of at most MSM_MAX_TERMS terms whose partial sums are added at the end
+    size_t pieces = (sh.cnt + MSM_MAX_TERMS - 1) / MSM_MAX_TERMS;
+    ST_TRY(ensure(ctx, L, B_JAC, pieces * 96 + 96));
+    ST_TRY(ensure(ctx, L, B_JAC2, pieces * 96 + 96));
+    uint32_t* parts = (uint32_t*)L.buf[B_JAC];
+    for (size_t pc = 0; pc < pieces; pc++) {
+      size_t lo = pc * MSM_MAX_TERMS, cnt = std::min(MSM_MAX_TERMS, sh.cnt - lo);
+      DevPtrs q;
+      q.k = dp.k + 32 * lo;
+      q.p = dp.p + 64 * lo;
+      q.inf = dp.inf ? dp.inf + lo : nullptr;
+      MsmGeom g = msm_geometry(curve, cnt);
+      uint32_t* r1 = nullptr;
+      if (curve == ECG_SECP256K1)
+        ST_TRY((msm_run<CurveK256, true>(ctx, L, q, cnt, sh.off + lo, g, &r1)));
+      else
+        ST_TRY((msm_run<CurveP256, false>(ctx, L, q, cnt, sh.off + lo, g, &r1)));
+      if (pieces == 1) {
+        *result = r1;
+        return ECG_OK;
+      }
+      // gather piece results into an SoA array of `pieces` points (24 strided 4-byte copies)
+      for (int w = 0; w < 24; w++)
+        CU_TRY(ctx, cudaMemcpyAsync(parts + (size_t)w * pieces + pc, r1 + w, 4, cudaMemcpyDeviceToDevice, L.s()));
+    }
+    return reduce_points_c(ctx, L, curve, parts, (uint32_t*)L.buf[B_JAC2], pieces, result);
+  }
   ST_TRY(ensure(ctx, L, B_JAC, sh.cnt * 96));
   ST_TRY(ensure(ctx, L, B_JAC2, ((sh.cnt + 31) / 32) * 96 + 96));
   ST_TRY(launch_varbase(ctx, L, curve, sh.cnt, dp, (uint32_t*)L.buf[B_JAC], L.status, sh.off));

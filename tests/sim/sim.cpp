@@ -8,6 +8,7 @@
 #include "../../elliptic-curves_b200/csrc/ecg_curves.cuh"
 #include "../../elliptic-curves_b200/csrc/ecg_mul.cuh"
 #include "../../elliptic-curves_b200/csrc/ecg_io.cuh"
+#include "../../elliptic-curves_b200/csrc/ecg_msm.cuh"
 
 using namespace ecg;
 
@@ -157,5 +158,18 @@ int sim_p256_on_curve(const uint8_t* P_xy) {
   Fe b;
   CurveP256::b_internal(b);
   return aff_on_curve<F, true>(P, b) ? 1 : 0;
+}
+
+// bucket-method digit recoding (ecg_msm.cuh): m little-endian 36 bytes -> W signed digits
+int sim_msm_recode(const uint8_t* m_le36, int c, int nbits, int32_t* out) {
+  uint32_t m[9];
+  memcpy(m, m_le36, 36);
+  MsmGeom g;
+  g.c = c;
+  g.nbits = nbits;
+  g.W = (nbits + c - 1) / c;
+  g.nbw = (1u << (c + 1)) + 2;
+  msm_recode(out, m, g);
+  return g.W;
 }
 }

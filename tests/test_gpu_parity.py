@@ -215,6 +215,48 @@ def test_lincomb_vs_oracle(engine, curve):
 
 
 @pytest.mark.parametrize("curve", CURVES)
+def test_lincomb_bucket_method_vs_oracle(engine, curve):
+    """n >= 2^13 takes the bucket-method (Pippenger) path: same bytes as the reference's lincomb."""
+    import ecgpu
+
+    c = pyref.CURVES[curve]
+    rng = random.Random(81)
+    for n in ((1 << 13), (1 << 14) + 37, 1 << 17):
+        base = random_points(c, 40, seed=n % 1000)
+        bxy, _ = pack_points(base)
+        pick = [rng.randrange(40) for _ in range(n)]
+        xy = bxy.reshape(40, 64)[pick].reshape(-1).copy()
+        inf = np.zeros(n, np.uint8)
+        K = np.frombuffer(rng.randbytes(32 * n), dtype=np.uint8).copy().reshape(n, 32)
+        K[:, 0] &= 0x7F
+        # identities, zero scalars, tiny scalars, n-1, and a run of identical (k, P) terms (equal points meet in a
+        # bucket: exercises the doubling branch of the mixed addition)
+        inf[5] = 1
+        K[7] = 0
+        K[8] = 0
+        K[8, 31] = 1
+        K[9] = np.frombuffer((c.n - 1).to_bytes(32, "big"), np.uint8)
+        K[100:140] = K[100]
+        xy.reshape(n, 64)[100:140] = xy.reshape(n, 64)[100]
+        out_xy, out_inf = engine.lincomb(curve, K, xy, inf)
+        ref_xy, ref_inf = ecref.lincomb(curve, K, xy, inf, nthreads=8)
+        assert np.array_equal(out_xy, ref_xy) and out_inf == ref_inf, n
+        part = engine.lincomb_partial(curve, K, xy, inf)
+        s_xy, s_inf = engine.point_sum(curve, part)
+        assert np.array_equal(s_xy, ref_xy) and s_inf == ref_inf
+    bad = K.copy()
+    bad[n - 9] = 0xFF
+    with pytest.raises(ecgpu.ScalarRangeError) as ei:
+        engine.lincomb(curve, bad, xy, inf)
+    assert ei.value.index == n - 9
+    badp = xy.copy()
+    badp[64 * 4321 + 1] ^= 0x40
+    with pytest.raises(ecgpu.NotOnCurveError) as ei:
+        engine.lincomb(curve, K, badp, inf)
+    assert ei.value.index == 4321
+
+
+@pytest.mark.parametrize("curve", CURVES)
 def test_lincomb_partial_and_point_sum(engine, curve):
     """config-5 shape: per-rank partial sums (Jacobian, 96 B) combined by ecg_point_sum == one big lincomb."""
     c = pyref.CURVES[curve]

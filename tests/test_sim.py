@@ -120,6 +120,24 @@ def test_scalar_mul_thread_routine(sim, curve, fn):
         assert _mul(sim, fn, c, k, P) == pyref.mul(c, k, P), hex(k)
 
 
+def test_msm_digit_recoding(sim):
+    """bucket-method recoding: digits reconstruct the scalar, non-top digits in (-2^(c-1), 2^(c-1)], top fits its slots"""
+    import ctypes as ct
+
+    rng = random.Random(44)
+    for nbits in (128, 256):
+        for c in range(8, 17):
+            W = (nbits + c - 1) // c
+            for trial in range(60):
+                m = rng.getrandbits(nbits) if trial > 6 else [0, 1, 2**nbits - 1, 2**(nbits - 1), 2**nbits, (1 << (c - 1)), (1 << c) - 1][trial]
+                out = (ct.c_int32 * 40)()
+                assert sim.sim_msm_recode(m.to_bytes(36, "little"), c, nbits, out) == W
+                d = [out[i] for i in range(W)]
+                assert sum(x << (c * i) for i, x in enumerate(d)) == m
+                assert all(-(1 << (c - 1)) < x <= (1 << (c - 1)) for x in d[:-1])
+                assert 0 <= d[-1] <= (1 << (c + 1)) + 1
+
+
 def test_on_curve_check(sim):
     for curve in ("k256", "p256"):
         c = pyref.CURVES[curve]
