@@ -48,7 +48,8 @@ ALGO_BYTES = {"mul": 160, "mulgen": 96, "lincomb": 96}
 #   k256: M = 64 + 8 (product + reduction), S = 36 + 8;  var-base = 1046 M + 748 S + 129 mul_small*8 + GLV ~200
 #   p256: M = 64, S = 36 (Solinas reduction uses no multiplier); var-base = 1885 M + 1316 S + 258*8
 #   k256 fixed-base: 17 mixed additions = 136 M + 51 S
-IMADW_PER_UNIT = {("k256", "mul"): 109_500, ("p256", "mul"): 170_100, ("k256", "mulgen"): 12_000, ("k256", "lincomb"): 109_500}
+#   k256 lincomb (bucket kernel, c = 16): 2 halves x 8 windows mixed additions = 128 M + 48 S per term
+IMADW_PER_UNIT = {("k256", "mul"): 109_500, ("p256", "mul"): 170_100, ("k256", "mulgen"): 12_000, ("k256", "lincomb"): 11_300}
 
 
 def synth_scalars(curve, seed, start, count):

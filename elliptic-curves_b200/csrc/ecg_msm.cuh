@@ -154,13 +154,21 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-// exclusive scan of count[0..m) into offset[0..m]; one block of 1024 threads, serial over chunks
-__global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restrict__ count, uint32_t* __restrict__ offset, size_t m) {
+// exclusive scan of count[0..m) into offset[0..m]; one block of 1024 threads, serial over chunks.
+// *maxcnt receives the largest bucket population (the host falls back to the per-term kernel when one bucket
+// would serialise the accumulation: many identical (scalar, point) terms).
+__global__ void __launch_bounds__(1024)
+    msm_scan_kernel(const uint32_t* __restrict__ count, uint32_t* __restrict__ offset, size_t m, uint32_t* __restrict__ maxcnt) {
   __shared__ uint32_t part[1024];
   size_t per = (m + 1023) / 1024;
   size_t lo = threadIdx.x * per, hi = lo + per < m ? lo + per : m;
-  uint32_t s = 0;
-  for (size_t i = lo; i < hi; i++) s += count[i];
+  uint32_t s = 0, mx = 0;
+  for (size_t i = lo; i < hi; i++) {
+    uint32_t cnt = count[i];
+    s += cnt;
+    mx = cnt > mx ? cnt : mx;
+  }
+  atomicMax(maxcnt, mx);
   part[threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.x == 0) {

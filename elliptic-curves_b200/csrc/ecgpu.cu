@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(256) mb_fmul_kernel(uint32_t* out, int iters, 
 // mode uses lane 0 only (optionally on the caller's stream).  Host-pointer mode cuts every per-element batch
 // into chunks and alternates lanes, so the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the
 // kernels of chunk c (PCIe is the only thing between the caller's buffers and the SMs).
-enum { B_K = 0, B_P = 1, B_INF = 2, B_JAC = 3, B_SCR = 4, B_OUT = 5, B_OINF = 6, B_AUX = 7, B_A = 8, B_JAC2 = 9, B_TAB = 10, B_MSM = 11, B_COUNT = 12 };
+enum { B_K = 0, B_P = 1, B_INF = 2, B_JAC = 3, B_SCR = 4, B_OUT = 5, B_OINF = 6, B_AUX = 7, B_A = 8, B_JAC2 = 9, B_TAB = 10, B_MSM = 11, B_FB1 = 12, B_FB2 = 13, B_COUNT = 14 };
 static const size_t HOST_CHUNK = (size_t)1 << 18;  // elements per pipelined chunk in host-pointer mode
 
 struct Lane {
@@ -1201,6 +1201,7 @@ struct Carver {
   }
 };
 
+// *result == nullptr on return means "input too skewed for the bucket method, use the per-term path".
 template <class C, bool GLV>
 static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, size_t base, const MsmGeom& g, uint32_t** result) {
   const size_t nsub = GLV ? 2 * n : n;
@@ -1224,7 +1225,7 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
     Carver cv{pass ? (uint8_t*)L.buf[B_MSM] : nullptr};
     pts = cv.take<uint32_t>(nsub * 16);
     digits = cv.take<int32_t>(nsub * (size_t)g.W);
-    count = cv.take<uint32_t>(2 * nb + 2);  // count | cursor, cleared together
+    count = cv.take<uint32_t>(2 * nb + 4);  // count | cursor | maxcnt, cleared together
     cursor = count ? count + nb + 1 : nullptr;
     offset = cv.take<uint32_t>(nb + 1);
     list = cv.take<uint32_t>(nsub * (size_t)g.W);
@@ -1239,11 +1240,23 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
     res = cv.take<uint32_t>(24);
     if (pass == 0) ST_TRY(ensure(ctx, L, B_MSM, cv.off + 256));
   }
-  CU_TRY(ctx, cudaMemsetAsync(count, 0, (2 * nb + 2) * 4, L.s()));
+  uint32_t* maxcnt = count + 2 * nb + 3;
+  CU_TRY(ctx, cudaMemsetAsync(count, 0, (2 * nb + 4) * 4, L.s()));
   msm_prep_kernel<C, GLV><<<grid_for(n, 128), 128, 0, L.s()>>>(dp.k, dp.p, dp.inf, n, g, pts, digits, count, L.status, base);
   LAUNCHED(ctx);
-  msm_scan_kernel<<<1, 1024, 0, L.s()>>>(count, offset, nb);
+  msm_scan_kernel<<<1, 1024, 0, L.s()>>>(count, offset, nb, maxcnt);
   LAUNCHED(ctx);
+  {
+    // one bucket thread adds its points serially: refuse pathologically skewed inputs (e.g. thousands of identical
+    // terms) and let the caller use the per-term kernel, whose cost does not depend on the data
+    CU_TRY(ctx, cudaMemcpyAsync(L.h_status, maxcnt, 4, cudaMemcpyDeviceToHost, L.s()));
+    CU_TRY(ctx, cudaStreamSynchronize(L.s()));
+    size_t avg = nsub / ((size_t)1 << (g.c - 1)) + 1;
+    if ((size_t)L.h_status[0] > 4096 && (size_t)L.h_status[0] > 32 * avg) {
+      *result = nullptr;
+      return ECG_OK;
+    }
+  }
   msm_scatter_kernel<<<grid_for(nsub, 256), 256, 0, L.s()>>>(digits, nsub, g, offset, cursor, list);
   LAUNCHED(ctx);
   DOM_BEGIN(ctx, L);
@@ -1318,6 +1331,12 @@ static ecg_status lincomb_shard(ecg_ctx* ctx, DevState& d, ecg_curve curve, cons
         ST_TRY((msm_run<CurveK256, true>(ctx, L, q, cnt, sh.off + lo, g, &r1)));
       else
         ST_TRY((msm_run<CurveP256, false>(ctx, L, q, cnt, sh.off + lo, g, &r1)));
+      if (r1 == nullptr) {  // skewed input: per-term path for this piece
+        ST_TRY(ensure(ctx, L, B_FB1, cnt * 96));
+        ST_TRY(ensure(ctx, L, B_FB2, ((cnt + 31) / 32) * 96 + 256));
+        ST_TRY(launch_varbase(ctx, L, curve, cnt, q, (uint32_t*)L.buf[B_FB1], L.status, sh.off + lo));
+        ST_TRY(reduce_points_c(ctx, L, curve, (uint32_t*)L.buf[B_FB1], (uint32_t*)L.buf[B_FB2], cnt, &r1));
+      }
       if (pieces == 1) {
         *result = r1;
         return ECG_OK;

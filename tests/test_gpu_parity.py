@@ -244,6 +244,14 @@ def test_lincomb_bucket_method_vs_oracle(engine, curve):
         part = engine.lincomb_partial(curve, K, xy, inf)
         s_xy, s_inf = engine.point_sum(curve, part)
         assert np.array_equal(s_xy, ref_xy) and s_inf == ref_inf
+    # pathologically skewed input (all terms identical): must still be exact (per-term fallback inside the library)
+    ns = 1 << 14
+    Ks = np.tile(K[1], (ns, 1))
+    xys = np.tile(xy.reshape(n, 64)[1], (ns, 1)).reshape(-1)
+    out_xy, out_inf = engine.lincomb(curve, Ks, xys, None)
+    k1 = int.from_bytes(K[1].tobytes(), "big")
+    P1 = base[pick[1]]
+    assert pyref.dec_point(out_xy.tobytes(), out_inf) == pyref.mul(c, k1 * ns % c.n, P1)
     bad = K.copy()
     bad[n - 9] = 0xFF
     with pytest.raises(ecgpu.ScalarRangeError) as ei:
