@@ -437,3 +437,42 @@ def test_device_pointer_mode():
     ref_xy, ref_inf = ecref.mul_batch("k256", K, xy, None, nthreads=8)
     assert np.array_equal(oxy.cpu().numpy(), ref_xy.reshape(-1)) and np.array_equal(oinf.cpu().numpy(), ref_inf)
     eng.close()
+
+
+# ---------------------------------------------------------------- the reference's proptest properties, restated
+@pytest.mark.parametrize("curve", CURVES)
+def test_reference_proptest_properties(engine, curve):
+    """k256/tests/projective.rs:75-140, p256/tests/projective.rs:54-149 against the C ABI:
+    lincomb == sum of p_i*s_i; mul_by_generator == G*s; mul_by_generator_and_mul_add == a*G + b*P;
+    batch_normalize == to_affine."""
+    c = pyref.CURVES[curve]
+    rng = random.Random(2718)
+    n = 64
+    ts = [rng.randrange(1, c.n) for _ in range(n)]
+    ss = [rng.randrange(c.n) for _ in range(n)]
+    aa = [rng.randrange(c.n) for _ in range(n)]
+    G = pyref.G(c)
+    gxy, ginf = pack_points([G] * n)
+    # points = mul_by_generator(t)   (the reference builds its test points the same way)
+    p_xy, p_inf = engine.mul_by_generator(curve, pack_scalars(ts))
+    q_xy, q_inf = engine.mul_batch(curve, pack_scalars(ts), gxy, ginf)
+    assert np.array_equal(p_xy, q_xy) and np.array_equal(p_inf, q_inf)               # mul_by_generator == G * s
+    prods_xy, prods_inf = engine.mul_batch(curve, pack_scalars(ss), p_xy, p_inf)     # p_i * s_i
+    # lincomb == sum(p_i * s_i): add the products with unit scalars through the same engine
+    l_xy, l_inf = engine.lincomb(curve, pack_scalars(ss), p_xy, p_inf)
+    s_xy, s_inf = engine.lincomb(curve, pack_scalars([1] * n), prods_xy, prods_inf)
+    assert np.array_equal(l_xy, s_xy) and l_inf == s_inf
+    tot = sum(t * s for t, s in zip(ts, ss)) % c.n
+    assert pyref.dec_point(l_xy.tobytes(), l_inf) == pyref.mul(c, tot, G)
+    # a*G + b*P
+    m_xy, m_inf = engine.mul_by_generator_and_mul_add(curve, pack_scalars(aa), pack_scalars(ss), p_xy, p_inf)
+    e_xy, e_inf = engine.mul_by_generator(curve, pack_scalars([(a + t * s) % c.n for a, t, s in zip(aa, ts, ss)]))
+    assert np.array_equal(m_xy, e_xy) and np.array_equal(m_inf, e_inf)
+    # batch_normalize(Jacobian lift) == the affine points
+    xyz = bytearray()
+    pts = unpack_points(p_xy, p_inf)
+    for P in pts:
+        z = rng.randrange(1, c.p)
+        xyz += (P[0] * z * z % c.p).to_bytes(32, "big") + (P[1] * z * z * z % c.p).to_bytes(32, "big") + z.to_bytes(32, "big")
+    b_xy, b_inf = engine.batch_normalize(curve, np.frombuffer(bytes(xyz), np.uint8))
+    assert np.array_equal(np.asarray(b_xy).reshape(-1), np.asarray(p_xy).reshape(-1)) and not b_inf.any()
