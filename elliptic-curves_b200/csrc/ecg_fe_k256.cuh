@@ -118,7 +118,7 @@ struct FpK256T {
       mul_body(r, a, b);
   }
   ECG_D static void sqr(Fe& r, const Fe& a) {
-    if (OPT & 2)
+    if ((OPT & 2) && !(OPT & 4))  // OPT bit 2: keep the (smaller) squaring inlined even when mul is a call
       r = sqr_call(a);
     else
       sqr_body(r, a);

@@ -250,16 +250,21 @@ int main(int argc, char** argv) {
   run<FpK256T<3>, 192, 2, false>("v3 call,   sqr8      (192,2) smem", n, jac, gtab);
   run<FpK256T<3>, 96, 4, false>("v3 call,   sqr8      (96,4)  smem", n, jac, gtab);
   run<FpK256T<3>, 64, 7, false>("v3 call,   sqr8      (64,7)  smem", n, jac, gtab);
-  run<FpK256T<3>, 128, 4, true>("v3 call,   sqr8      (128,4) gtab", n, jac, gtab);
+  run<FpK256T<7>, 128, 5, true>("v7 mul call, sqr inl (128,5) gtab", n, jac, gtab);
+  run<FpK256T<7>, 128, 4, true>("v7 mul call, sqr inl (128,4) gtab", n, jac, gtab);
+  run<FpK256T<1>, 128, 5, true>("v1 inline, sqr8      (128,5) gtab", n, jac, gtab);
   run<FpK256T<3>, 128, 5, true>("v3 call,   sqr8      (128,5) gtab", n, jac, gtab);
   run<FpK256T<3>, 256, 2, true>("v3 call,   sqr8      (256,2) gtab", n, jac, gtab);
-  run<FpK256T<3>, 128, 4, true>("v3 call,   sqr8      (128,4) gtab", n, jac, gtab);
+  run<FpK256T<7>, 128, 5, true>("v7 mul call, sqr inl (128,5) gtab", n, jac, gtab);
+  run<FpK256T<7>, 128, 4, true>("v7 mul call, sqr inl (128,4) gtab", n, jac, gtab);
+  run<FpK256T<1>, 128, 5, true>("v1 inline, sqr8      (128,5) gtab", n, jac, gtab);
   run_fmul<FpP256T<1>>("p256 fmul inline");
   run_fmul<FpP256T<3>>("p256 fmul call");
   runp<FpP256T<1>, 128, 2, false>("p256 inline (128,2) smem", n, jac, gtab);
   runp<FpP256T<3>, 128, 2, false>("p256 call   (128,2) smem", n, jac, gtab);
   runp<FpP256T<3>, 128, 3, true>("p256 call   (128,3) gtab", n, jac, gtab);
   runp<FpP256T<3>, 128, 4, true>("p256 call   (128,4) gtab", n, jac, gtab);
-  runp<FpP256T<1>, 128, 3, true>("p256 inline (128,3) gtab", n, jac, gtab);
+  runp<FpP256T<7>, 128, 4, true>("p256 mul call, sqr inl (128,4) gtab", n, jac, gtab);
+  runp<FpP256T<7>, 128, 3, true>("p256 mul call, sqr inl (128,3) gtab", n, jac, gtab);
   return 0;
 }
