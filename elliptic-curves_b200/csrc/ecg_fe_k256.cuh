@@ -16,7 +16,7 @@ namespace ecg {
 // OPT bit 1: mul / sqr are real (non-inlined) device functions taking and returning Fe by value in registers:
 //            the kernels shrink ~3x and fit the instruction cache (ncu: `no_instruction` stalls)
 #ifndef ECG_K256_OPT
-#define ECG_K256_OPT 3
+#define ECG_K256_OPT 7
 #endif
 #if defined(__CUDA_ARCH__) || defined(__CUDACC__)
 #define ECG_NOINLINE_D __device__ __noinline__

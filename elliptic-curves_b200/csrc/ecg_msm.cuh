@@ -154,21 +154,48 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-// exclusive scan of count[0..m) into offset[0..m]; one block of 1024 threads, serial over chunks.
-// *maxcnt receives the largest bucket population (the host falls back to the per-term kernel when one bucket
-// would serialise the accumulation: many identical (scalar, point) terms).
-__global__ void __launch_bounds__(1024)
-    msm_scan_kernel(const uint32_t* __restrict__ count, uint32_t* __restrict__ offset, size_t m, uint32_t* __restrict__ maxcnt) {
-  __shared__ uint32_t part[1024];
-  size_t per = (m + 1023) / 1024;
-  size_t lo = threadIdx.x * per, hi = lo + per < m ? lo + per : m;
+// Exclusive scan of count[0..m) into offset[0..m] in three small kernels (4096 counters per block):
+//   msm_scan_partial_kernel  per-block totals + the largest bucket population (*maxcnt; the host falls back to the
+//                            per-term kernel when one bucket would serialise the accumulation)
+//   msm_scan_top_kernel      exclusive scan of the block totals (one block), offset[m] = grand total
+//   msm_scan_final_kernel    per-block scan + block offset
+#define MSM_SCAN_BLOCK 256
+#define MSM_SCAN_PER_THREAD 16
+#define MSM_SCAN_CHUNK (MSM_SCAN_BLOCK * MSM_SCAN_PER_THREAD)
+__global__ void __launch_bounds__(MSM_SCAN_BLOCK)
+    msm_scan_partial_kernel(const uint32_t* __restrict__ count, size_t m, uint32_t* __restrict__ blocksum, uint32_t* __restrict__ maxcnt) {
+  __shared__ uint32_t ssum[MSM_SCAN_BLOCK], smax[MSM_SCAN_BLOCK];
+  size_t lo = (size_t)blockIdx.x * MSM_SCAN_CHUNK + (size_t)threadIdx.x * MSM_SCAN_PER_THREAD;
   uint32_t s = 0, mx = 0;
-  for (size_t i = lo; i < hi; i++) {
-    uint32_t cnt = count[i];
-    s += cnt;
-    mx = cnt > mx ? cnt : mx;
+  for (int i = 0; i < MSM_SCAN_PER_THREAD; i++)
+    if (lo + i < m) {
+      uint32_t c = count[lo + i];
+      s += c;
+      mx = c > mx ? c : mx;
+    }
+  ssum[threadIdx.x] = s;
+  smax[threadIdx.x] = mx;
+  __syncthreads();
+  for (int st = MSM_SCAN_BLOCK / 2; st > 0; st >>= 1) {
+    if ((int)threadIdx.x < st) {
+      ssum[threadIdx.x] += ssum[threadIdx.x + st];
+      smax[threadIdx.x] = smax[threadIdx.x] > smax[threadIdx.x + st] ? smax[threadIdx.x] : smax[threadIdx.x + st];
+    }
+    __syncthreads();
   }
-  atomicMax(maxcnt, mx);
+  if (threadIdx.x == 0) {
+    blocksum[blockIdx.x] = ssum[0];
+    atomicMax(maxcnt, smax[0]);
+  }
+}
+__global__ void __launch_bounds__(1024)
+    msm_scan_top_kernel(uint32_t* __restrict__ blocksum, size_t nblocks, uint32_t* __restrict__ offset, size_t m) {
+  // nblocks <= a few thousand: serial per-thread chunks + one serial pass over 1024 partials
+  __shared__ uint32_t part[1024];
+  size_t per = (nblocks + 1023) / 1024;
+  size_t lo = threadIdx.x * per, hi = lo + per < nblocks ? lo + per : nblocks;
+  uint32_t s = 0;
+  for (size_t i = lo; i < hi; i++) s += blocksum[i];
   part[threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -183,9 +210,36 @@ __global__ void __launch_bounds__(1024)
   __syncthreads();
   uint32_t run = part[threadIdx.x];
   for (size_t i = lo; i < hi; i++) {
-    offset[i] = run;
-    run += count[i];
+    uint32_t t = blocksum[i];
+    blocksum[i] = run;
+    run += t;
   }
+}
+__global__ void __launch_bounds__(MSM_SCAN_BLOCK)
+    msm_scan_final_kernel(const uint32_t* __restrict__ count, size_t m, const uint32_t* __restrict__ blockoff, uint32_t* __restrict__ offset) {
+  __shared__ uint32_t ssum[MSM_SCAN_BLOCK];
+  size_t lo = (size_t)blockIdx.x * MSM_SCAN_CHUNK + (size_t)threadIdx.x * MSM_SCAN_PER_THREAD;
+  uint32_t c[MSM_SCAN_PER_THREAD];
+  uint32_t s = 0;
+  for (int i = 0; i < MSM_SCAN_PER_THREAD; i++) {
+    c[i] = lo + i < m ? count[lo + i] : 0;
+    s += c[i];
+  }
+  ssum[threadIdx.x] = s;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over the 256 thread totals
+  for (int st = 1; st < MSM_SCAN_BLOCK; st <<= 1) {
+    uint32_t v = (int)threadIdx.x >= st ? ssum[threadIdx.x - st] : 0;
+    __syncthreads();
+    ssum[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = blockoff[blockIdx.x] + ssum[threadIdx.x] - s;
+  for (int i = 0; i < MSM_SCAN_PER_THREAD; i++)
+    if (lo + i < m) {
+      offset[lo + i] = run;
+      run += c[i];
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -227,16 +281,24 @@ __global__ void __launch_bounds__(128, 4)
   F::set_zero(acc.Z);
   if (lo < hi) {
     uint32_t ent = list[lo];
-    Aff e;
+    Aff e, nx;
     msm_load_point(e, pts, ent >> 1);
     fe_cneg<F>(e.y, ent & 1u);
     acc.X = e.x;
     acc.Y = e.y;
     F::set_one(acc.Z);
+    // software pipeline: the gather of point i+1 (a random 64-byte read, usually an L2 miss) is issued before the
+    // mixed addition of point i
+    uint32_t nent = lo + 1 < hi ? list[lo + 1] : 0;
+    if (lo + 1 < hi) msm_load_point(nx, pts, nent >> 1);
 #pragma unroll 1
     for (uint32_t i = lo + 1; i < hi; i++) {
-      ent = list[i];
-      msm_load_point(e, pts, ent >> 1);
+      e = nx;
+      ent = nent;
+      if (i + 1 < hi) {
+        nent = list[i + 1];
+        msm_load_point(nx, pts, nent >> 1);
+      }
       fe_cneg<F>(e.y, ent & 1u);
       jac_madd<F, C::A_IS_MINUS3>(acc, acc, e);
     }
@@ -269,7 +331,8 @@ __device__ __forceinline__ void msm_jstore(uint32_t* __restrict__ a, size_t n, s
 // Weighted reduction level.  Input: W rows of `len` Jacobian points (element (w, j) at index w*stride_in + off + j,
 // weight j+1).  Thread (w, ch) covers j in [ch*CH, min(len, (ch+1)*CH)) from the top down with the running-sum
 // trick and writes  T = sum (j - ch*CH + 1) A_j  and  S = sum A_j  at index w*nch + ch of outT / outS.
-#define MSM_CH 64
+#define MSM_CH 16
+#define MSM_CH_LOG2 4
 template <class C>
 __global__ void __launch_bounds__(128)
     msm_wreduce_kernel(const uint32_t* __restrict__ in, size_t n_in, size_t stride_in, size_t off, size_t len, int W, size_t nch,
@@ -308,7 +371,7 @@ __global__ void __launch_bounds__(32)
   msm_jload(s, Stot, W, w);
   F::neg(s.Y, s.Y);
   jac_add<F, C::A_IS_MINUS3>(b, b, s);
-  for (int i = 0; i < 6; i++) jac_dbl<F, C::A_IS_MINUS3>(b, b);  // x MSM_CH = 2^6
+  for (int i = 0; i < MSM_CH_LOG2; i++) jac_dbl<F, C::A_IS_MINUS3>(b, b);  // x MSM_CH
   jac_add<F, C::A_IS_MINUS3>(a, a, b);
   msm_jstore(R, W, w, a);
 }

@@ -809,7 +809,7 @@ static ecg_status launch_norm(ecg_ctx* ctx, DevState& d, Lane& L, ecg_curve curv
 }
 
 // launch geometry of the variable-base kernels (registers set the occupancy; tables are in global memory)
-static const int K_BLOCK = 128, K_MINBLK = 5;  // secp256k1: <= 96 registers -> 20 warps/SM
+static const int K_BLOCK = 128, K_MINBLK = 4;  // secp256k1: <= 128 registers -> 16 warps/SM (mul = call, sqr inlined: OPT 7)
 static const int P_BLOCK = 128, P_MINBLK = 4;  // P-256   : <= 128 registers -> 16 warps/SM
 
 // per-block window-table slots for a launch of n elements
@@ -1219,14 +1219,16 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
   const int levels = (int)lens.size();
   // carve the scratch arena (first pass sizes it, second pass hands out pointers)
   uint32_t *pts = nullptr, *count = nullptr, *cursor = nullptr, *offset = nullptr, *list = nullptr, *bkt = nullptr, *res = nullptr;
+  uint32_t* blocksum = nullptr;
   int32_t* digits = nullptr;
-  std::vector<uint32_t*> T(levels), S(levels), sumT(levels), tmp(levels), R(levels);
+  std::vector<uint32_t*> T(levels), S(levels), sumT(levels), tmp(levels), tmp2(levels), R(levels);
   for (int pass = 0; pass < 2; pass++) {
     Carver cv{pass ? (uint8_t*)L.buf[B_MSM] : nullptr};
     pts = cv.take<uint32_t>(nsub * 16);
     digits = cv.take<int32_t>(nsub * (size_t)g.W);
     count = cv.take<uint32_t>(2 * nb + 4);  // count | cursor | maxcnt, cleared together
     cursor = count ? count + nb + 1 : nullptr;
+    blocksum = cv.take<uint32_t>((nb + MSM_SCAN_CHUNK - 1) / MSM_SCAN_CHUNK + 1);
     offset = cv.take<uint32_t>(nb + 1);
     list = cv.take<uint32_t>(nsub * (size_t)g.W);
     bkt = cv.take<uint32_t>(nb * 24);
@@ -1235,6 +1237,7 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
       S[l] = cv.take<uint32_t>((size_t)g.W * nchs[l] * 24);
       sumT[l] = cv.take<uint32_t>((size_t)g.W * 24);
       tmp[l] = cv.take<uint32_t>((size_t)g.W * ((nchs[l] + 63) / 64) * 24);
+      tmp2[l] = cv.take<uint32_t>((size_t)g.W * ((nchs[l] + 4095) / 4096) * 24);
       R[l] = cv.take<uint32_t>((size_t)g.W * 24);
     }
     res = cv.take<uint32_t>(24);
@@ -1244,8 +1247,15 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
   CU_TRY(ctx, cudaMemsetAsync(count, 0, (2 * nb + 4) * 4, L.s()));
   msm_prep_kernel<C, GLV><<<grid_for(n, 128), 128, 0, L.s()>>>(dp.k, dp.p, dp.inf, n, g, pts, digits, count, L.status, base);
   LAUNCHED(ctx);
-  msm_scan_kernel<<<1, 1024, 0, L.s()>>>(count, offset, nb, maxcnt);
-  LAUNCHED(ctx);
+  {
+    unsigned sb = (unsigned)((nb + MSM_SCAN_CHUNK - 1) / MSM_SCAN_CHUNK);
+    msm_scan_partial_kernel<<<sb, MSM_SCAN_BLOCK, 0, L.s()>>>(count, nb, blocksum, maxcnt);
+    LAUNCHED(ctx);
+    msm_scan_top_kernel<<<1, 1024, 0, L.s()>>>(blocksum, sb, offset, nb);
+    LAUNCHED(ctx);
+    msm_scan_final_kernel<<<sb, MSM_SCAN_BLOCK, 0, L.s()>>>(count, nb, blocksum, offset);
+    LAUNCHED(ctx);
+  }
   {
     // one bucket thread adds its points serially: refuse pathologically skewed inputs (e.g. thousands of identical
     // terms) and let the caller use the per-term kernel, whose cost does not depend on the data
@@ -1277,17 +1287,19 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
     if (row == 1) {
       sumT[l] = T[l];
     } else {
+      int pass_no = 0;
       while (row > 1) {
         size_t out_len = (row + 63) / 64;
-        uint32_t* dst = out_len == 1 ? sumT[l] : tmp[l];
-        msm_rowsum_kernel<C><<<grid_for((size_t)g.W * out_len, 128), 128, 0, L.s()>>>(cur, row, g.W, dst, out_len);
-        LAUNCHED(ctx);
-        if (out_len > 1 && cur == tmp[l]) {  // would need a third pass (row > 4096): not reachable for c <= 16
+        uint32_t* dst = out_len == 1 ? sumT[l] : (pass_no == 0 ? tmp[l] : tmp2[l]);
+        if (out_len > 1 && pass_no >= 2) {  // a fourth pass would need rows > 64^3
           ctx->err = "msm: weighted-reduction row too long";
           return ECG_EINVAL;
         }
+        msm_rowsum_kernel<C><<<grid_for((size_t)g.W * out_len, 128), 128, 0, L.s()>>>(cur, row, g.W, dst, out_len);
+        LAUNCHED(ctx);
         cur = dst;
         row = out_len;
+        pass_no++;
       }
     }
   }

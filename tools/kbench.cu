@@ -5,7 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <vector>
-#define ECG_K256_OPT 3
+#define ECG_K256_OPT 7
 #include "../elliptic-curves_b200/csrc/ecg_curves.cuh"
 #include "../elliptic-curves_b200/csrc/ecg_io.cuh"
 #include "../elliptic-curves_b200/csrc/ecg_mul.cuh"
