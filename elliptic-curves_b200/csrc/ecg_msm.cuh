@@ -10,7 +10,7 @@
 //   3. msm_scatter_kernel   write each (point, sign) reference into its bucket's slice        [counting sort]
 //   4. msm_bucket_kernel    one thread per bucket: gather its points, mixed-add them           [the hot kernel]
 //   5. msm_wreduce_kernel   per window sum_j j*B_j by chunked running sums (recursive on the chunk totals)
-//   6. msm_horner_kernel    result = sum_w 2^(c w) R_w
+//   6. msm_final_kernel     undo the recursion's bias, result = sum_w 2^(c w) R_w
 // Everything is order-independent group arithmetic, so the (affine, canonical) result is bit-identical to the
 // reference's whatever order the atomics produce.
 #pragma once
@@ -328,67 +328,86 @@ __device__ __forceinline__ void msm_jstore(uint32_t* __restrict__ a, size_t n, s
   }
 }
 
-// Weighted reduction level.  Input: W rows of `len` Jacobian points (element (w, j) at index w*stride_in + off + j,
-// weight j+1).  Thread (w, ch) covers j in [ch*CH, min(len, (ch+1)*CH)) from the top down with the running-sum
-// trick and writes  T = sum (j - ch*CH + 1) A_j  and  S = sum A_j  at index w*nch + ch of outT / outS.
+// Weighted reduction of every window's buckets, R_w = sum_{j>=1} j * B_{w,j}, by recursive chunking.
+// Level l reads W rows of `len` points A_j (level 0: the buckets, weight j+1 for element j; level l>0: the chunk
+// totals S of level l-1).  Thread (w, ch) walks its chunk of MSM_CH elements from the top with the running-sum trick
+//     S  = sum A_j                      (chunk total   -> input of level l+1)
+//     T  = sum (j - ch*CH + 1) A_j      (chunk-local weighted sum)
+// and carries the plain sum of everything the lower levels produced:
+//     X_l[ch] = sum_{ch' in chunk} X_{l-1}[ch']  +  CH^l * T          (X_{-1} = nothing)
+// At the last level (one chunk per row)  X_L = R_w + Btot * (CH + CH^2 + ... + CH^L),  Btot = S_L, which
+// msm_final_kernel undoes before the Horner combination of the windows.
 #define MSM_CH 16
 #define MSM_CH_LOG2 4
 template <class C>
 __global__ void __launch_bounds__(128)
     msm_wreduce_kernel(const uint32_t* __restrict__ in, size_t n_in, size_t stride_in, size_t off, size_t len, int W, size_t nch,
-                       uint32_t* __restrict__ outT, uint32_t* __restrict__ outS) {
+                       const uint32_t* __restrict__ Xprev, int level, uint32_t* __restrict__ outS, uint32_t* __restrict__ outX) {
   typedef typename C::F F;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)W * nch) return;
   size_t w = t / nch, ch = t % nch;
   size_t lo = ch * MSM_CH, hi = lo + MSM_CH < len ? lo + MSM_CH : len;
-  Jac S, T, p;
+  Jac S, T, X, p;
   F::set_zero(S.X);
   F::set_one(S.Y);
   F::set_zero(S.Z);
   T = S;
+  X = S;
   for (size_t j = hi; j > lo; j--) {
     msm_jload(p, in, n_in, w * stride_in + off + (j - 1));
     jac_add<F, C::A_IS_MINUS3>(S, S, p);
     jac_add<F, C::A_IS_MINUS3>(T, T, S);
+    if (Xprev != nullptr) {
+      msm_jload(p, Xprev, n_in, w * stride_in + (j - 1));
+      jac_add<F, C::A_IS_MINUS3>(X, X, p);
+    }
   }
+  for (int i = 0; i < MSM_CH_LOG2 * level; i++) jac_dbl<F, C::A_IS_MINUS3>(T, T);
+  jac_add<F, C::A_IS_MINUS3>(X, X, T);
   size_t n_out = (size_t)W * nch;
-  msm_jstore(outT, n_out, t, T);
   msm_jstore(outS, n_out, t, S);
+  msm_jstore(outX, n_out, t, X);
 }
 
-// R[w] = sumT[w] + CH * (Rnext[w] - Stot[w])     (combine one recursion level; all arrays have W entries)
+// R_w = X_L[w] - k * Btot[w],  k = CH + CH^2 + ... + CH^L;  then out = sum_w 2^(c w) R_w  (Horner, thread 0).
 template <class C>
 __global__ void __launch_bounds__(32)
-    msm_combine_kernel(const uint32_t* __restrict__ sumT, const uint32_t* __restrict__ Rnext, const uint32_t* __restrict__ Stot, int W,
-                       uint32_t* __restrict__ R) {
+    msm_final_kernel(const uint32_t* __restrict__ XL, const uint32_t* __restrict__ SL, int W, int c, int levels,
+                     uint32_t* __restrict__ R, uint32_t* __restrict__ out) {
   typedef typename C::F F;
   int w = threadIdx.x;
-  if (w >= W) return;
-  Jac a, b, s;
-  msm_jload(a, sumT, W, w);
-  msm_jload(b, Rnext, W, w);
-  msm_jload(s, Stot, W, w);
-  F::neg(s.Y, s.Y);
-  jac_add<F, C::A_IS_MINUS3>(b, b, s);
-  for (int i = 0; i < MSM_CH_LOG2; i++) jac_dbl<F, C::A_IS_MINUS3>(b, b);  // x MSM_CH
-  jac_add<F, C::A_IS_MINUS3>(a, a, b);
-  msm_jstore(R, W, w, a);
-}
-
-// out (n = 1 SoA) = sum_w 2^(c w) R[w]
-template <class C>
-__global__ void __launch_bounds__(32) msm_horner_kernel(const uint32_t* __restrict__ R, int W, int c, uint32_t* __restrict__ out) {
-  typedef typename C::F F;
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  Jac acc, p;
-  msm_jload(acc, R, W, W - 1);
-  for (int w = W - 2; w >= 0; w--) {
-    for (int i = 0; i < c; i++) jac_dbl<F, C::A_IS_MINUS3>(acc, acc);
-    msm_jload(p, R, W, w);
-    jac_add<F, C::A_IS_MINUS3>(acc, acc, p);
+  if (w < W) {
+    Jac x, s, ks, t;
+    msm_jload(x, XL, W, w);
+    msm_jload(s, SL, W, w);
+    // ks = k * s by Horner over the base-CH digits 1,1,...,1,0  (k = CH * (1 + CH * (1 + ...)))
+    ks = s;
+    for (int l = 1; l < levels; l++) {
+      for (int i = 0; i < MSM_CH_LOG2; i++) jac_dbl<F, C::A_IS_MINUS3>(ks, ks);
+      jac_add<F, C::A_IS_MINUS3>(ks, ks, s);
+    }
+    for (int i = 0; i < MSM_CH_LOG2; i++) jac_dbl<F, C::A_IS_MINUS3>(ks, ks);
+    if (levels == 0) {
+      F::set_zero(ks.X);
+      F::set_one(ks.Y);
+      F::set_zero(ks.Z);
+    }
+    F::neg(ks.Y, ks.Y);
+    jac_add<F, C::A_IS_MINUS3>(t, x, ks);
+    msm_jstore(R, W, w, t);
   }
-  msm_jstore(out, 1, 0, acc);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Jac acc, p;
+    msm_jload(acc, R, W, W - 1);
+    for (int ww = W - 2; ww >= 0; ww--) {
+      for (int i = 0; i < c; i++) jac_dbl<F, C::A_IS_MINUS3>(acc, acc);
+      msm_jload(p, R, W, ww);
+      jac_add<F, C::A_IS_MINUS3>(acc, acc, p);
+    }
+    msm_jstore(out, 1, 0, acc);
+  }
 }
 
 #endif  // __CUDACC__

@@ -1155,27 +1155,6 @@ static ecg_status reduce_points_c(ecg_ctx* ctx, Lane& L, ecg_curve curve, uint32
 static const size_t MSM_MIN_TERMS = (size_t)1 << 13;   // below this the per-term kernel + tree sum is faster
 static const size_t MSM_MAX_TERMS = (size_t)1 << 24;   // per call (32-bit list offsets); larger shards are cut
 
-// out[w*out_len + q] = sum of in[w*row_len + q*64 .. +64)   (plain row sums of Jacobian points, W rows)
-template <class C>
-__global__ void __launch_bounds__(128)
-    msm_rowsum_kernel(const uint32_t* __restrict__ in, size_t row_len, int W, uint32_t* __restrict__ out, size_t out_len) {
-  typedef typename C::F F;
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (size_t)W * out_len) return;
-  size_t w = t / out_len, q = t % out_len;
-  size_t lo = q * 64, hi = lo + 64 < row_len ? lo + 64 : row_len;
-  Jac acc, p;
-  F::set_zero(acc.X);
-  F::set_one(acc.Y);
-  F::set_zero(acc.Z);
-  size_t n_in = (size_t)W * row_len;
-  for (size_t j = lo; j < hi; j++) {
-    msm_jload(p, in, n_in, w * row_len + j);
-    jac_add<F, C::A_IS_MINUS3>(acc, acc, p);
-  }
-  msm_jstore(out, (size_t)W * out_len, t, acc);
-}
-
 static MsmGeom msm_geometry(ecg_curve curve, size_t n) {
   MsmGeom g;
   bool glv = curve == ECG_SECP256K1;
@@ -1221,7 +1200,8 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
   uint32_t *pts = nullptr, *count = nullptr, *cursor = nullptr, *offset = nullptr, *list = nullptr, *bkt = nullptr, *res = nullptr;
   uint32_t* blocksum = nullptr;
   int32_t* digits = nullptr;
-  std::vector<uint32_t*> T(levels), S(levels), sumT(levels), tmp(levels), tmp2(levels), R(levels);
+  std::vector<uint32_t*> S(levels), X(levels);
+  uint32_t* Rw = nullptr;
   for (int pass = 0; pass < 2; pass++) {
     Carver cv{pass ? (uint8_t*)L.buf[B_MSM] : nullptr};
     pts = cv.take<uint32_t>(nsub * 16);
@@ -1233,13 +1213,10 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
     list = cv.take<uint32_t>(nsub * (size_t)g.W);
     bkt = cv.take<uint32_t>(nb * 24);
     for (int l = 0; l < levels; l++) {
-      T[l] = cv.take<uint32_t>((size_t)g.W * nchs[l] * 24);
       S[l] = cv.take<uint32_t>((size_t)g.W * nchs[l] * 24);
-      sumT[l] = cv.take<uint32_t>((size_t)g.W * 24);
-      tmp[l] = cv.take<uint32_t>((size_t)g.W * ((nchs[l] + 63) / 64) * 24);
-      tmp2[l] = cv.take<uint32_t>((size_t)g.W * ((nchs[l] + 4095) / 4096) * 24);
-      R[l] = cv.take<uint32_t>((size_t)g.W * 24);
+      X[l] = cv.take<uint32_t>((size_t)g.W * nchs[l] * 24);
     }
+    Rw = cv.take<uint32_t>((size_t)g.W * 24);
     res = cv.take<uint32_t>(24);
     if (pass == 0) ST_TRY(ensure(ctx, L, B_MSM, cv.off + 256));
   }
@@ -1273,44 +1250,17 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
   msm_bucket_kernel<C><<<grid_for(nb, 128), 128, 0, L.s()>>>(pts, list, offset, nb, bkt);
   LAUNCHED(ctx);
   DOM_END(ctx, L);
-  // weighted reduction, level by level
+  // weighted reduction, level by level (ecg_msm.cuh)
   for (int l = 0; l < levels; l++) {
     const uint32_t* in = l == 0 ? bkt : S[l - 1];
     size_t n_in = l == 0 ? nb : (size_t)g.W * nchs[l - 1];
     size_t stride = l == 0 ? g.nbw : nchs[l - 1];
     size_t off = l == 0 ? 1 : 0;
-    msm_wreduce_kernel<C><<<grid_for((size_t)g.W * nchs[l], 128), 128, 0, L.s()>>>(in, n_in, stride, off, lens[l], g.W, nchs[l], T[l], S[l]);
+    msm_wreduce_kernel<C><<<grid_for((size_t)g.W * nchs[l], 128), 128, 0, L.s()>>>(in, n_in, stride, off, lens[l], g.W, nchs[l],
+                                                                                 l == 0 ? nullptr : X[l - 1], l, S[l], X[l]);
     LAUNCHED(ctx);
-    // sumT[l][w] = sum_ch T[l][w][ch]
-    const uint32_t* cur = T[l];
-    size_t row = nchs[l];
-    if (row == 1) {
-      sumT[l] = T[l];
-    } else {
-      int pass_no = 0;
-      while (row > 1) {
-        size_t out_len = (row + 63) / 64;
-        uint32_t* dst = out_len == 1 ? sumT[l] : (pass_no == 0 ? tmp[l] : tmp2[l]);
-        if (out_len > 1 && pass_no >= 2) {  // a fourth pass would need rows > 64^3
-          ctx->err = "msm: weighted-reduction row too long";
-          return ECG_EINVAL;
-        }
-        msm_rowsum_kernel<C><<<grid_for((size_t)g.W * out_len, 128), 128, 0, L.s()>>>(cur, row, g.W, dst, out_len);
-        LAUNCHED(ctx);
-        cur = dst;
-        row = out_len;
-        pass_no++;
-      }
-    }
   }
-  // unwind: R[last] = sumT[last]; R[l] = sumT[l] + CH * (R[l+1] - Btot),  Btot = S[last]
-  uint32_t* Rcur = sumT[levels - 1];
-  for (int l = levels - 2; l >= 0; l--) {
-    msm_combine_kernel<C><<<1, 32, 0, L.s()>>>(sumT[l], Rcur, S[levels - 1], g.W, R[l]);
-    LAUNCHED(ctx);
-    Rcur = R[l];
-  }
-  msm_horner_kernel<C><<<1, 32, 0, L.s()>>>(Rcur, g.W, g.c, res);
+  msm_final_kernel<C><<<1, 32, 0, L.s()>>>(X[levels - 1], S[levels - 1], g.W, g.c, levels - 1, Rw, res);
   LAUNCHED(ctx);
   *result = res;
   return ECG_OK;
