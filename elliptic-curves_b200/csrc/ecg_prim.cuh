@@ -238,6 +238,94 @@ ECG_D void mul8x8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   r[15] = addc(E[15], O[14]);
 }
 
+// 4x4 -> 8 limb product in the even/odd pair layout (16 IMAD.WIDE + 3 ADDC + 7 merge adds).
+ECG_D void mul4x4(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint32_t E[8], O[7];
+  mul_wide(E[0], E[1], a[0], b[0]);
+  mul_wide(E[2], E[3], a[2], b[0]);
+  mul_wide(O[0], O[1], a[1], b[0]);
+  mul_wide(O[2], O[3], a[3], b[0]);
+  // row 1: a_even*b1 -> odd positions 1,3 ; a_odd*b1 -> even positions 2,4
+  mad_wide_cc(O[0], O[1], a[0], b[1]);
+  madc_wide_cc(O[2], O[3], a[2], b[1]);
+  O[4] = addc(0, 0);
+  mad_wide_cc(E[2], E[3], a[1], b[1]);
+  madc_wide_new(E[4], E[5], a[3], b[1]);
+  // row 2: a_even*b2 -> even positions 2,4 ; a_odd*b2 -> odd positions 3,5
+  mad_wide_cc(E[2], E[3], a[0], b[2]);
+  madc_wide_cc(E[4], E[5], a[2], b[2]);
+  E[6] = addc(0, 0);
+  mad_wide_cc(O[2], O[3], a[1], b[2]);
+  madc_wide_top(O[4], O[5], a[3], b[2]);
+  // row 3: a_even*b3 -> odd positions 3,5 ; a_odd*b3 -> even positions 4,6
+  mad_wide_cc(O[2], O[3], a[0], b[3]);
+  madc_wide_cc(O[4], O[5], a[2], b[3]);
+  O[6] = addc(0, 0);
+  mad_wide_cc(E[4], E[5], a[1], b[3]);
+  madc_wide_top(E[6], E[7], a[3], b[3]);
+  r[0] = E[0];
+  r[1] = add_cc(E[1], O[0]);
+#pragma unroll
+  for (int k = 2; k < 7; k++) r[k] = addc_cc(E[k], O[k - 1]);
+  r[7] = addc(E[7], O[6]);
+}
+
+// 8x8 -> 16 limb product by one level of Karatsuba on 4-limb halves: 48 IMAD.WIDE instead of 64, paid for with
+// ~60 more carry-chain adds (ALU pipe).  a = a0 + a1 B^4, b = b0 + b1 B^4:
+//   z0 = a0 b0, z2 = a1 b1, zm = (a0 + a1)(b0 + b1), z1 = zm - z0 - z2,  r = z0 + z1 B^4 + z2 B^8.
+ECG_D void mul8x8_kara(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint32_t z0[8], z2[8], zm[9], sa[4], sb[4];
+  mul4x4(z0, a, b);
+  mul4x4(z2, a + 4, b + 4);
+  sa[0] = add_cc(a[0], a[4]);
+  sa[1] = addc_cc(a[1], a[5]);
+  sa[2] = addc_cc(a[2], a[6]);
+  sa[3] = addc_cc(a[3], a[7]);
+  uint32_t ca = addc(0, 0);
+  sb[0] = add_cc(b[0], b[4]);
+  sb[1] = addc_cc(b[1], b[5]);
+  sb[2] = addc_cc(b[2], b[6]);
+  sb[3] = addc_cc(b[3], b[7]);
+  uint32_t cb = addc(0, 0);
+  mul4x4(zm, sa, sb);
+  // (sa + ca B^4)(sb + cb B^4) = sa sb + (ca sb + cb sa) B^4 + ca cb B^8
+  uint32_t ma = 0u - ca, mb = 0u - cb;
+  zm[4] = add_cc(zm[4], sb[0] & ma);
+  zm[5] = addc_cc(zm[5], sb[1] & ma);
+  zm[6] = addc_cc(zm[6], sb[2] & ma);
+  zm[7] = addc_cc(zm[7], sb[3] & ma);
+  zm[8] = addc(ca & cb, 0);
+  zm[4] = add_cc(zm[4], sa[0] & mb);
+  zm[5] = addc_cc(zm[5], sa[1] & mb);
+  zm[6] = addc_cc(zm[6], sa[2] & mb);
+  zm[7] = addc_cc(zm[7], sa[3] & mb);
+  zm[8] = addc(zm[8], 0);
+  // z1 = zm - z0 - z2   (non-negative, < 2^258)
+  zm[0] = sub_cc(zm[0], z0[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) zm[i] = subc_cc(zm[i], z0[i]);
+  zm[8] = subc(zm[8], 0);
+  zm[0] = sub_cc(zm[0], z2[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) zm[i] = subc_cc(zm[i], z2[i]);
+  zm[8] = subc(zm[8], 0);
+  // r = z0 + z1 B^4 + z2 B^8
+#pragma unroll
+  for (int i = 0; i < 4; i++) r[i] = z0[i];
+  r[4] = add_cc(z0[4], zm[0]);
+  r[5] = addc_cc(z0[5], zm[1]);
+  r[6] = addc_cc(z0[6], zm[2]);
+  r[7] = addc_cc(z0[7], zm[3]);
+  r[8] = addc_cc(z2[0], zm[4]);
+  r[9] = addc_cc(z2[1], zm[5]);
+  r[10] = addc_cc(z2[2], zm[6]);
+  r[11] = addc_cc(z2[3], zm[7]);
+  r[12] = addc_cc(z2[4], zm[8]);
+  r[13] = addc_cc(z2[5], 0);
+  r[14] = addc_cc(z2[6], 0);
+  r[15] = addc(z2[7], 0);
+}
+
 // 8-limb square -> 16 limbs: the 28 cross products a_i*a_j (i<j) once, in the same even/odd pair layout
 // (rows are triangular, so chains shorten), doubled by a 1-bit funnel shift, and the 8 diagonal squares
 // accumulated on top with one IMAD.WIDE.X chain.  36 IMAD.WIDE instead of 64.

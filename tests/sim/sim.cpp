@@ -160,6 +160,21 @@ int sim_p256_on_curve(const uint8_t* P_xy) {
   return aff_on_curve<F, true>(P, b) ? 1 : 0;
 }
 
+// Karatsuba variant of the field multiplication (OPT bit 3)
+int sim_fe_mul_kara(int curve, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  Fe x, y, r;
+  load_be32(x.v, a);
+  load_be32(y.v, b);
+  if (curve == 0) {
+    FpK256T<9>::mul(r, x, y);
+    FpK256T<9>::normalize(r, r);
+  } else {
+    FpP256T<9>::mul(r, x, y);
+    FpP256T<9>::normalize(r, r);
+  }
+  store_be32(out, r.v);
+  return 0;
+}
 // bucket-method digit recoding (ecg_msm.cuh): m little-endian 36 bytes -> W signed digits
 int sim_msm_recode(const uint8_t* m_le36, int c, int nbits, int32_t* out) {
   uint32_t m[9];

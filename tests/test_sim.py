@@ -82,6 +82,26 @@ def test_field_mul_structured_stress(sim):
             assert _feop(sim, curve, 3, a) == a * a % p
 
 
+def test_karatsuba_multiplier_variant(sim):
+    rng = random.Random(321)
+
+    def structured():
+        v = 0
+        for i in range(8):
+            c = rng.random()
+            w = 0 if c < 0.3 else 0xFFFFFFFF if c < 0.6 else 1 if c < 0.65 else 0xFFFFFFFE if c < 0.7 else rng.getrandbits(32)
+            v |= w << (32 * i)
+        return v
+
+    for ci, curve in enumerate(("k256", "p256")):
+        p = pyref.CURVES[curve].p
+        for i in range(4000):
+            a, b = (structured(), structured()) if i % 2 else (rng.getrandbits(256), rng.getrandbits(256))
+            out = ctypes.create_string_buffer(32)
+            sim.sim_fe_mul_kara(ci, a.to_bytes(32, "big"), b.to_bytes(32, "big"), out)
+            assert int.from_bytes(out.raw, "big") == a * b % p
+
+
 def test_glv_split_matches_reference_definition(sim):
     rng = random.Random(2)
     n = pyref.K256.n

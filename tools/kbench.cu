@@ -243,6 +243,8 @@ int main(int argc, char** argv) {
   run_fmul<FpK256T<0>>("fmul inline mul8x8");
   run_fmul<FpK256T<1>>("fmul inline sqr8");
   run_fmul<FpK256T<3>>("fmul call sqr8");
+  run_fmul<FpK256T<9>>("fmul inline kara");
+  run_fmul<FpK256T<11>>("fmul call kara");
   run<FpK256T<0>, 128, 3, false>("v0 inline, sqr=mul   (128,3) smem", n, jac, gtab);
   run<FpK256T<1>, 128, 3, false>("v1 inline, sqr8      (128,3) smem", n, jac, gtab);
   run<FpK256T<2>, 128, 3, false>("v2 call,   sqr=mul   (128,3) smem", n, jac, gtab);
@@ -250,11 +252,17 @@ int main(int argc, char** argv) {
   run<FpK256T<3>, 192, 2, false>("v3 call,   sqr8      (192,2) smem", n, jac, gtab);
   run<FpK256T<3>, 96, 4, false>("v3 call,   sqr8      (96,4)  smem", n, jac, gtab);
   run<FpK256T<3>, 64, 7, false>("v3 call,   sqr8      (64,7)  smem", n, jac, gtab);
+  run<FpK256T<15>, 128, 4, true>("v15 kara call, sqr inl (128,4) gtab", n, jac, gtab);
+  run<FpK256T<11>, 128, 4, true>("v11 kara call, sqr call(128,4) gtab", n, jac, gtab);
+  run<FpK256T<11>, 128, 5, true>("v11 kara call, sqr call(128,5) gtab", n, jac, gtab);
   run<FpK256T<7>, 128, 5, true>("v7 mul call, sqr inl (128,5) gtab", n, jac, gtab);
   run<FpK256T<7>, 128, 4, true>("v7 mul call, sqr inl (128,4) gtab", n, jac, gtab);
   run<FpK256T<1>, 128, 5, true>("v1 inline, sqr8      (128,5) gtab", n, jac, gtab);
   run<FpK256T<3>, 128, 5, true>("v3 call,   sqr8      (128,5) gtab", n, jac, gtab);
   run<FpK256T<3>, 256, 2, true>("v3 call,   sqr8      (256,2) gtab", n, jac, gtab);
+  run<FpK256T<15>, 128, 4, true>("v15 kara call, sqr inl (128,4) gtab", n, jac, gtab);
+  run<FpK256T<11>, 128, 4, true>("v11 kara call, sqr call(128,4) gtab", n, jac, gtab);
+  run<FpK256T<11>, 128, 5, true>("v11 kara call, sqr call(128,5) gtab", n, jac, gtab);
   run<FpK256T<7>, 128, 5, true>("v7 mul call, sqr inl (128,5) gtab", n, jac, gtab);
   run<FpK256T<7>, 128, 4, true>("v7 mul call, sqr inl (128,4) gtab", n, jac, gtab);
   run<FpK256T<1>, 128, 5, true>("v1 inline, sqr8      (128,5) gtab", n, jac, gtab);
@@ -264,6 +272,7 @@ int main(int argc, char** argv) {
   runp<FpP256T<3>, 128, 2, false>("p256 call   (128,2) smem", n, jac, gtab);
   runp<FpP256T<3>, 128, 3, true>("p256 call   (128,3) gtab", n, jac, gtab);
   runp<FpP256T<3>, 128, 4, true>("p256 call   (128,4) gtab", n, jac, gtab);
+  runp<FpP256T<11>, 128, 4, true>("p256 kara call (128,4) gtab", n, jac, gtab);
   runp<FpP256T<7>, 128, 4, true>("p256 mul call, sqr inl (128,4) gtab", n, jac, gtab);
   runp<FpP256T<7>, 128, 3, true>("p256 mul call, sqr inl (128,3) gtab", n, jac, gtab);
   return 0;
