@@ -5,7 +5,8 @@
 // `LookupTable` (primeorder/src/tables/lookup.rs:30-81) and `wnaf_table` (wnaf/src/lib.rs:55-65).
 //
 // Everything here is per-thread straight-line work on registers plus a per-thread window table behind
-// the `Tab` accessor (shared memory in the kernels, a plain array in the host simulation).  All threads
+// the `TabRef` accessors (a per-block slot of global memory in the kernels — see ecgpu.cu —, a plain array in the
+// host simulation).  All threads
 // of a warp execute the same operation sequence (fixed windows, every digit non-zero), so there is no
 // divergence outside the never-taken exceptional-case branches.
 #pragma once
@@ -16,8 +17,8 @@
 namespace ecg {
 
 // Window-table accessor: entry e (0..7), word w (0..15: x[0..7], y[0..7]) lives at base[(e*16+w)*stride].
-// In the kernels base = smem + threadIdx.x and stride = blockDim.x, so a warp's accesses hit 32 distinct
-// banks whatever entry each lane selects (conflict-free data-dependent lookups).
+// In the kernels base = slot + threadIdx.x and stride = blockDim.x: the 32 lanes of a warp touch 32 consecutive
+// words of each row they select (coalesced when lanes agree on the entry, at worst 8 rows when they do not).
 struct TabRef {
   uint32_t* base;
   uint32_t stride;
