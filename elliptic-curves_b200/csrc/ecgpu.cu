@@ -15,6 +15,7 @@
 #include "ecg_io.cuh"
 #include "ecg_mul.cuh"
 #include "ecg_msm.cuh"
+#include "ecg_verify.cuh"
 
 using namespace ecg;
 
@@ -244,6 +245,182 @@ __global__ void __launch_bounds__(BLOCK, MINBLK)
   soa_store<8>(jac, n, idx, r.X.v, 0);
   soa_store<8>(jac, n, idx, r.Y.v, 8);
   soa_store<8>(jac, n, idx, r.Z.v, 16);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Signature verification front ends (ecg_verify.cuh).  Both reduce to a*G + b*P through mul_gen_add_kernel; the
+// kernels here prepare (a, b, P) and judge the result.  Invalid encodings never raise an API error: they are
+// marked not-ok, replaced by harmless operands (a = b = 1, P = G) so warps stay converged, and reported as
+// valid[i] = 0 — the reference returns Err(Error) per signature, not a batch failure.
+__device__ __forceinline__ void store_scalar_be(uint8_t* dst, const uint32_t* limbs) { store_be32(dst, limbs); }
+
+// BIP340: pk (x only), 32-byte message, signature r || s.
+__global__ void __launch_bounds__(128)
+    schnorr_prep_kernel(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, const uint8_t* __restrict__ sig, size_t n,
+                        uint8_t* __restrict__ pxy, uint8_t* __restrict__ a_out, uint8_t* __restrict__ b_out, uint8_t* __restrict__ ok_out) {
+  typedef FpK256 F;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  uint32_t x[8], r[8], sv[8], e[8];
+  load_be32(x, pk + 32 * idx);
+  load_be32(r, sig + 64 * idx);
+  load_be32(sv, sig + 64 * idx + 32);
+  Aff P;
+  bool ok = k256_lift_x<F>(P, x);                    // VerifyingKey::from_bytes (schnorr/verifying.rs:36-52)
+  ok = ok && lt8(r, K256_P);                           // Signature::try_from: r is a field element,
+  ok = ok && lt8(sv, K256_N) && !FnMont<CurveK256>::is_zero(sv);  //   s a non-zero scalar (schnorr.rs:150-170)
+  bip340_challenge(e, sig + 64 * idx, pk + 32 * idx, msg + 32 * idx);
+  if (!lt8(e, K256_N)) {  // Reduce<FieldBytes>: one conditional subtraction (2^256 < 2n)
+    uint32_t t[8];
+    sub8(t, e, K256_N);
+#pragma unroll
+    for (int i = 0; i < 8; i++) e[i] = t[i];
+  }
+  // b = -e mod n
+  uint32_t ne[8];
+  if (FnMont<CurveK256>::is_zero(e)) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) ne[i] = 0;
+  } else {
+    sub8(ne, K256_N, e);
+  }
+  if (!ok) {
+    CurveK256::generator(P);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      sv[i] = (i == 0);
+      ne[i] = (i == 0);
+    }
+  }
+  Fe cx, cy;
+  F::to_canonical(cx, P.x);
+  F::to_canonical(cy, P.y);
+  store_be32(pxy + 64 * idx, cx.v);
+  store_be32(pxy + 64 * idx + 32, cy.v);
+  store_scalar_be(a_out + 32 * idx, sv);
+  store_scalar_be(b_out + 32 * idx, ne);
+  ok_out[idx] = ok ? 1 : 0;
+}
+__global__ void __launch_bounds__(256)
+    schnorr_check_kernel(const uint8_t* __restrict__ sig, const uint8_t* __restrict__ rxy, const uint8_t* __restrict__ rinf,
+                         const uint8_t* __restrict__ ok, size_t n, uint8_t* __restrict__ valid) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(sig + 64 * idx);
+  const uint32_t* x = reinterpret_cast<const uint32_t*>(rxy + 64 * idx);
+  bool same = true;
+#pragma unroll
+  for (int i = 0; i < 8; i++) same = same && (r[i] == x[i]);
+  bool y_even = (rxy[64 * idx + 63] & 1u) == 0;
+  valid[idx] = (ok[idx] && !rinf[idx] && y_even && same) ? 1 : 0;  // verifying.rs:94
+}
+
+// ECDSA: z (32-byte hash), signature r || s, public key Q (x || y).  One modular inversion per thread slice
+// (Montgomery's trick over s_i, as in normalize_kernel); scr: 8*n words.
+template <class C>
+__global__ void __launch_bounds__(128)
+    ecdsa_prep_kernel(const uint8_t* __restrict__ zb, const uint8_t* __restrict__ sig, const uint8_t* __restrict__ qxy, size_t n,
+                      int low_s_only, uint32_t* __restrict__ scr, uint8_t* __restrict__ pxy, uint8_t* __restrict__ a_out,
+                      uint8_t* __restrict__ b_out, uint8_t* __restrict__ ok_out) {
+  typedef typename C::F F;
+  typedef FnMont<C> N;
+  size_t T = (size_t)gridDim.x * blockDim.x;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  uint32_t acc[8], sm[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = C::N_ONE()[i];
+  size_t last = t;
+  // forward: validate, prefix products of the (Montgomery-form) s_i
+  for (size_t idx = t; idx < n; idx += T) {
+    uint32_t r[8], sv[8];
+    load_be32(r, sig + 64 * idx);
+    load_be32(sv, sig + 64 * idx + 32);
+    bool ok = lt8(r, C::N()) && !N::is_zero(r) && lt8(sv, C::N()) && !N::is_zero(sv);
+    if (ok && low_s_only) {  // EcdsaCurve::NORMALIZE_S (k256/src/ecdsa.rs:104-106): reject s > n/2
+      uint32_t twice[8];
+      uint32_t c = add8(twice, sv, sv);
+      ok = !c && lt8(twice, C::N());
+    }
+    Aff Q;
+    Fe qx, qy;
+    load_be32(qx.v, qxy + 64 * idx);
+    load_be32(qy.v, qxy + 64 * idx + 32);
+    bool qok = lt8(qx.v, C::P()) && lt8(qy.v, C::P());
+    F::from_canonical(Q.x, qx);
+    F::from_canonical(Q.y, qy);
+    if (qok) {
+      Fe b;
+      C::b_internal(b);
+      qok = aff_on_curve<F, C::A_IS_MINUS3>(Q, b);
+    }
+    ok = ok && qok;
+    ok_out[idx] = ok ? 1 : 0;
+    if (!ok) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) sv[i] = (i == 0);
+    }
+    N::to_mont(sm, sv);
+    soa_store<8>(scr, n, idx, acc, 0);
+    N::mul(acc, acc, sm);
+    last = idx;
+  }
+  uint32_t inv[8];
+  N::inv(inv, acc);
+  for (size_t idx = last;; idx -= T) {
+    uint32_t r[8], sv[8], z[8], pre[8], w[8], u1[8], u2[8];
+    bool ok = ok_out[idx] != 0;
+    load_be32(r, sig + 64 * idx);
+    load_be32(sv, sig + 64 * idx + 32);
+    load_be32(z, zb + 32 * idx);
+    if (!ok) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) sv[i] = (i == 0);
+    }
+    N::to_mont(sm, sv);
+    soa_load<8>(pre, scr, n, idx, 0);
+    N::mul(w, inv, pre);   // w = s^-1 (Montgomery form)
+    N::mul(inv, inv, sm);
+    N::cond_sub_n(z, N::ge_n(z));  // bits2field + reduce for 256-bit curves
+    // u1 = z*w, u2 = r*w: mont_mul(plain, mont) = plain product
+    N::mul(u1, z, w);
+    N::mul(u2, r, w);
+    if (!ok) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        u1[i] = (i == 0);
+        u2[i] = (i == 0);
+      }
+      Aff G;
+      C::generator(G);
+      Fe gx, gy;
+      F::to_canonical(gx, G.x);
+      F::to_canonical(gy, G.y);
+      store_be32(pxy + 64 * idx, gx.v);
+      store_be32(pxy + 64 * idx + 32, gy.v);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; i++) reinterpret_cast<uint32_t*>(pxy + 64 * idx)[i] = reinterpret_cast<const uint32_t*>(qxy + 64 * idx)[i];
+    }
+    store_scalar_be(a_out + 32 * idx, u1);
+    store_scalar_be(b_out + 32 * idx, u2);
+    if (idx < T) break;
+  }
+}
+template <class C>
+__global__ void __launch_bounds__(256)
+    ecdsa_check_kernel(const uint8_t* __restrict__ sig, const uint8_t* __restrict__ rxy, const uint8_t* __restrict__ rinf,
+                       const uint8_t* __restrict__ ok, size_t n, uint8_t* __restrict__ valid) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  uint32_t r[8], x[8];
+  load_be32(r, sig + 64 * idx);
+  load_be32(x, rxy + 64 * idx);
+  FnMont<C>::cond_sub_n(x, FnMont<C>::ge_n(x));  // x(R) mod n  (p < 2n)
+  bool same = true;
+#pragma unroll
+  for (int i = 0; i < 8; i++) same = same && (r[i] == x[i]);
+  valid[idx] = (ok[idx] && !rinf[idx] && same) ? 1 : 0;
 }
 
 // canonical affine big-endian bytes (n*64) -> table words (internal form); used once, when a table is built
@@ -498,7 +675,7 @@ __global__ void __launch_bounds__(256) mb_fmul_kernel(uint32_t* out, int iters, 
 // mode uses lane 0 only (optionally on the caller's stream).  Host-pointer mode cuts every per-element batch
 // into chunks and alternates lanes, so the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the
 // kernels of chunk c (PCIe is the only thing between the caller's buffers and the SMs).
-enum { B_K = 0, B_P = 1, B_INF = 2, B_JAC = 3, B_SCR = 4, B_OUT = 5, B_OINF = 6, B_AUX = 7, B_A = 8, B_JAC2 = 9, B_TAB = 10, B_MSM = 11, B_FB1 = 12, B_FB2 = 13, B_COUNT = 14 };
+enum { B_K = 0, B_P = 1, B_INF = 2, B_JAC = 3, B_SCR = 4, B_OUT = 5, B_OINF = 6, B_AUX = 7, B_A = 8, B_JAC2 = 9, B_TAB = 10, B_MSM = 11, B_FB1 = 12, B_FB2 = 13, B_X = 14, B_V1 = 15, B_V2 = 16, B_V3 = 17, B_V4 = 18, B_V5 = 19, B_V6 = 20, B_COUNT = 21 };
 static const size_t HOST_CHUNK = (size_t)1 << 18;  // elements per pipelined chunk in host-pointer mode
 
 struct Lane {
@@ -942,10 +1119,11 @@ static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
 // What one chunk does is the only thing that differs between ecg_mul_batch, ecg_mul_gen_batch, ecg_mul_gen_add_batch,
 // ecg_batch_normalize and ecg_field_op_batch:
 struct BatchOp {
-  enum Kind { MUL, MULGEN, MULGENADD, NORMALIZE, FIELD } kind;
+  enum Kind { MUL, MULGEN, MULGENADD, NORMALIZE, FIELD, SCHNORR, ECDSA } kind;
   ecg_curve curve;
-  int fop = 0;
+  int fop = 0;  // field op, or the ECDSA low-S flag
   const uint8_t *k = nullptr, *a = nullptr, *p = nullptr, *inf = nullptr;  // host or device, per ctx flags
+  const uint8_t* x = nullptr;  // extra 64-byte-stride input (ECDSA public keys)
   size_t pstride = 64;
   uint8_t *out = nullptr, *oinf = nullptr;
   size_t ostride = 64;
@@ -958,7 +1136,53 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
   ST_TRY(stage_in(ctx, L, B_A, op.a, off, cnt, 32, &dp.a));
   ST_TRY(stage_in(ctx, L, B_P, op.p, off, cnt, op.pstride, &dp.p));
   ST_TRY(stage_in(ctx, L, B_INF, op.inf, off, cnt, 1, &dp.inf));
+  const uint8_t* dx = nullptr;
+  ST_TRY(stage_in(ctx, L, B_X, op.x, off, cnt, 64, &dx));
   ST_TRY(stage_out(ctx, L, off, cnt, op.out, op.ostride, op.oinf, dp));
+  if (op.kind == BatchOp::SCHNORR || op.kind == BatchOp::ECDSA) {
+    // front end -> (a, b, P) -> a*G + b*P -> affine -> verdict, all on the device
+    ST_TRY(ensure(ctx, L, B_V1, cnt * 64));
+    ST_TRY(ensure(ctx, L, B_V2, cnt * 32));
+    ST_TRY(ensure(ctx, L, B_V3, cnt * 32));
+    ST_TRY(ensure(ctx, L, B_V4, cnt));
+    ST_TRY(ensure(ctx, L, B_V5, cnt * 64));
+    ST_TRY(ensure(ctx, L, B_V6, cnt));
+    ST_TRY(ensure(ctx, L, B_JAC, cnt * 96));
+    ST_TRY(ensure_tab(ctx, L, op.curve, cnt));
+    uint8_t *vp = (uint8_t*)L.buf[B_V1], *va = (uint8_t*)L.buf[B_V2], *vb = (uint8_t*)L.buf[B_V3], *vok = (uint8_t*)L.buf[B_V4];
+    uint8_t *vxy = (uint8_t*)L.buf[B_V5], *vinf = (uint8_t*)L.buf[B_V6];
+    uint32_t* vj = (uint32_t*)L.buf[B_JAC];
+    const bool k1c = op.curve == ECG_SECP256K1;
+    if (op.kind == BatchOp::SCHNORR) {
+      schnorr_prep_kernel<<<grid_for(cnt, 128), 128, 0, L.s()>>>(dp.k, dp.a, dp.p, cnt, vp, va, vb, vok);
+    } else {
+      ST_TRY(ensure(ctx, L, B_SCR, cnt * 32));
+      size_t want_threads = std::max<size_t>((cnt + 31) / 32, std::min<size_t>(cnt, (size_t)d.sm_count * 128));
+      if (k1c)
+        ecdsa_prep_kernel<CurveK256><<<grid_for(want_threads, 128), 128, 0, L.s()>>>(dp.k, dp.p, dx, cnt, op.fop, (uint32_t*)L.buf[B_SCR], vp, va, vb, vok);
+      else
+        ecdsa_prep_kernel<CurveP256><<<grid_for(want_threads, 128), 128, 0, L.s()>>>(dp.k, dp.p, dx, cnt, op.fop, (uint32_t*)L.buf[B_SCR], vp, va, vb, vok);
+    }
+    LAUNCHED(ctx);
+    DOM_BEGIN(ctx, L);
+    if (k1c)
+      mul_gen_add_kernel<CurveK256, K_BLOCK, K_MINBLK, true><<<grid_for(cnt, K_BLOCK), K_BLOCK, 0, L.s()>>>(
+          va, vb, vp, nullptr, cnt, d.fb_table[op.curve], vj, (uint32_t*)L.buf[B_TAB], L.status, off);
+    else
+      mul_gen_add_kernel<CurveP256, P_BLOCK, P_MINBLK, false><<<grid_for(cnt, P_BLOCK), P_BLOCK, 0, L.s()>>>(
+          va, vb, vp, nullptr, cnt, d.fb_table[op.curve], vj, (uint32_t*)L.buf[B_TAB], L.status, off);
+    LAUNCHED(ctx);
+    DOM_END(ctx, L);
+    ST_TRY(launch_norm(ctx, d, L, op.curve, cnt, vj, vxy, vinf));
+    if (op.kind == BatchOp::SCHNORR)
+      schnorr_check_kernel<<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, vxy, vinf, vok, cnt, dp.out);
+    else if (k1c)
+      ecdsa_check_kernel<CurveK256><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, vxy, vinf, vok, cnt, dp.out);
+    else
+      ecdsa_check_kernel<CurveP256><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, vxy, vinf, vok, cnt, dp.out);
+    LAUNCHED(ctx);
+    return copy_back(ctx, L, off, cnt, op.out, op.ostride, nullptr, dp);
+  }
   uint32_t* jac = nullptr;
   if (op.kind != BatchOp::FIELD) {
     ST_TRY(ensure(ctx, L, B_JAC, cnt * 96));
@@ -997,6 +1221,9 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
         import_jac_kernel<CurveP256><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, cnt, jac, L.status, off);
       LAUNCHED(ctx);
       break;
+    case BatchOp::SCHNORR:
+    case BatchOp::ECDSA:
+      break;  // handled above
     case BatchOp::FIELD:
       if (k1)
         field_op_kernel<CurveK256><<<grid_for(cnt, 256), 256, 0, L.s()>>>(op.fop, cnt, dp.k, dp.a, dp.out, L.status, off);
@@ -1011,7 +1238,7 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
 
 static ecg_status run_batch(ecg_ctx* ctx, const BatchOp& op, size_t n) {
   std::vector<Shard> shards = make_shards(n, ctx->devs.size());
-  bool need_table = op.kind == BatchOp::MULGEN || op.kind == BatchOp::MULGENADD;
+  bool need_table = op.kind == BatchOp::MULGEN || op.kind == BatchOp::MULGENADD || op.kind == BatchOp::SCHNORR || op.kind == BatchOp::ECDSA;
   for (size_t i = 0; i < ctx->devs.size(); i++) {
     if (shards[i].cnt == 0) continue;
     DevState& d = ctx->devs[i];
@@ -1098,6 +1325,45 @@ extern "C" ecg_status ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve curve, size_
   op.inf = P_inf;
   op.out = out_xy;
   op.oinf = out_inf;
+  return run_batch(ctx, op, n);
+}
+
+extern "C" ecg_status ecg_schnorr_verify_batch(ecg_ctx* ctx, size_t n, const uint8_t* pk_x, const uint8_t* msg32, const uint8_t* sig64,
+                                                uint8_t* valid) {
+  if (!ctx) return ECG_EINVAL;
+  if (n == 0) return ECG_OK;
+  if (!pk_x || !msg32 || !sig64 || !valid) {
+    ctx->err = "ecg_schnorr_verify_batch: null pointer";
+    return ECG_EINVAL;
+  }
+  BatchOp op;
+  op.kind = BatchOp::SCHNORR;
+  op.curve = ECG_SECP256K1;
+  op.k = pk_x;
+  op.a = msg32;
+  op.p = sig64;
+  op.out = valid;
+  op.ostride = 1;
+  return run_batch(ctx, op, n);
+}
+
+extern "C" ecg_status ecg_ecdsa_verify_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* z32, const uint8_t* sig64,
+                                              const uint8_t* Q_xy, int low_s_only, uint8_t* valid) {
+  if (!ctx) return ECG_EINVAL;
+  if (n == 0) return ECG_OK;
+  if (!z32 || !sig64 || !Q_xy || !valid || !curve_ok(curve)) {
+    ctx->err = "ecg_ecdsa_verify_batch: null pointer or unknown curve";
+    return ECG_EINVAL;
+  }
+  BatchOp op;
+  op.kind = BatchOp::ECDSA;
+  op.curve = curve;
+  op.fop = low_s_only ? 1 : 0;
+  op.k = z32;
+  op.p = sig64;
+  op.x = Q_xy;
+  op.out = valid;
+  op.ostride = 1;
   return run_batch(ctx, op, n);
 }
 

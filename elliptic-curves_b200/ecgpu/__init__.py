@@ -37,6 +37,7 @@ EXPORTS = [
     "ecg_mul_batch", "ecg_mul_gen_batch", "ecg_lincomb", "ecg_lincomb_partial", "ecg_point_sum",
     "ecg_mul_gen_add_batch", "ecg_batch_normalize", "ecg_field_op_batch", "ecg_microbench",
     "ecg_kernel_launches", "ecg_version", "ecg_timing_enable", "ecg_timing_read",
+    "ecg_schnorr_verify_batch", "ecg_ecdsa_verify_batch",
 ]
 
 
@@ -102,6 +103,10 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.ecg_timing_enable.restype = ctypes.c_int
     lib.ecg_timing_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
     lib.ecg_timing_read.restype = ctypes.c_int
+    lib.ecg_schnorr_verify_batch.argtypes = [vp, sz, u8p, u8p, u8p, u8p]
+    lib.ecg_schnorr_verify_batch.restype = ctypes.c_int
+    lib.ecg_ecdsa_verify_batch.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p, ctypes.c_int, u8p]
+    lib.ecg_ecdsa_verify_batch.restype = ctypes.c_int
     lib.ecg_version.argtypes = []
     lib.ecg_version.restype = ctypes.c_char_p
     if path is None:
@@ -234,6 +239,27 @@ class Engine:
         out_inf = np.empty(n, np.uint8)
         self._check(self.lib.ecg_mul_gen_add_batch(self._ctx, c, n, _ptr(a), _ptr(b), _ptr(P_xy), _ptr(P_inf), _ptr(out_xy), _ptr(out_inf)))
         return out_xy.reshape(n, 64), out_inf
+
+    def schnorr_verify_batch(self, pk_x, msg32, sig64):
+        """BIP340: VerifyingKey::verify_raw over a batch (k256/src/schnorr/verifying.rs:76-99) -> uint8 flags"""
+        n = np.asarray(pk_x).size // 32
+        pk_x = _u8(pk_x, 32 * n, "pk_x")
+        msg32 = _u8(msg32, 32 * n, "msg32")
+        sig64 = _u8(sig64, 64 * n, "sig64")
+        valid = np.zeros(n, np.uint8)
+        self._check(self.lib.ecg_schnorr_verify_batch(self._ctx, n, _ptr(pk_x), _ptr(msg32), _ptr(sig64), _ptr(valid)))
+        return valid
+
+    def ecdsa_verify_batch(self, curve, z32, sig64, Q_xy, low_s_only=False):
+        """ECDSA verify_prehash over a batch -> uint8 flags"""
+        c = CURVE_IDS[curve]
+        n = np.asarray(z32).size // 32
+        z32 = _u8(z32, 32 * n, "z32")
+        sig64 = _u8(sig64, 64 * n, "sig64")
+        Q_xy = _u8(Q_xy, 64 * n, "Q_xy")
+        valid = np.zeros(n, np.uint8)
+        self._check(self.lib.ecg_ecdsa_verify_batch(self._ctx, c, n, _ptr(z32), _ptr(sig64), _ptr(Q_xy), 1 if low_s_only else 0, _ptr(valid)))
+        return valid
 
     def batch_normalize(self, curve, xyz):
         c = CURVE_IDS[curve]

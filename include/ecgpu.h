@@ -107,6 +107,24 @@ ecg_status ecg_point_sum(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t*
 ecg_status ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, const uint8_t* b,
                                  const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
 
+/* ---- first widening step: batched signature verification ------------------
+ * Invalid encodings (r, s, public key out of range / off curve) are NOT API errors: valid[i] = 0, like the
+ * reference's per-signature Err(Error). */
+
+/* BIP340 Schnorr verification, secp256k1: valid[i] = 1 iff sig[i] (r || s, 64 bytes) is a valid signature of the
+ * 32-byte message msg32[i] under the x-only public key pk_x[i].
+ * Replaces VerifyingKey::verify_raw over a batch (k256/src/schnorr/verifying.rs:76-99), including
+ * VerifyingKey::from_bytes (lift_x, :36-52) and the tagged challenge hash (k256/src/schnorr.rs:85,221-227). */
+ecg_status ecg_schnorr_verify_batch(ecg_ctx* ctx, size_t n, const uint8_t* pk_x, const uint8_t* msg32,
+                                    const uint8_t* sig64, uint8_t* valid);
+
+/* ECDSA verification: z32[i] = message digest (reduced mod n inside), sig64[i] = r || s (Signature::try_from
+ * encoding), Q_xy[i] = public key x || y.  low_s_only != 0 additionally rejects s > n/2 (EcdsaCurve::NORMALIZE_S,
+ * k256/src/ecdsa.rs:104-106).  Replaces ecdsa_core::VerifyingKey::verify_prehash for k256::ecdsa::VerifyingKey /
+ * p256::ecdsa::VerifyingKey (k256/src/ecdsa.rs:93-121, p256/src/ecdsa.rs) over a batch. */
+ecg_status ecg_ecdsa_verify_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* z32, const uint8_t* sig64,
+                                  const uint8_t* Q_xy, int low_s_only, uint8_t* valid);
+
 /* Projective (Jacobian X||Y||Z, n*96 bytes) -> affine, one shared inversion per thread-group
  * (Montgomery's trick).  Replaces BatchNormalize::batch_normalize (k256/src/arithmetic/projective.rs:345-391,
  * primeorder/src/projective.rs:435-478).  Coordinates must be < p. */

@@ -78,8 +78,48 @@ def bench_scalars(curve):
     return {"source": f"{curve}/benches/point.rs", "scalars": out}
 
 
+def bip340_vectors():
+    """k256/src/schnorr.rs: BIP340_SIGN_VECTORS (all valid) and BIP340_VERIFY_VECTORS (valid flag)."""
+    txt = open(f"{REF}/k256/src/schnorr.rs").read()
+    out = []
+    sign = txt[txt.index("const BIP340_SIGN_VECTORS"):txt.index("fn bip340_sign_vectors")]
+    for m in re.finditer(r"SignVector\s*\{(.*?)\n        \},", sign, re.S):
+        body = m.group(1)
+        idx = int(re.search(r"index:\s*(\d+)", body).group(1))
+        f = {k: re.sub(r"\s+", "", v) for k, v in re.findall(r'(\w+):\s*hex!\(\s*"([0-9A-Fa-f\s]+)"\s*\)', body)}
+        out.append({"index": idx, "pk": f["public_key"].lower(), "msg": f["message"].lower(), "sig": f["signature"].lower(), "valid": True,
+                    "sk": f["secret_key"].lower(), "aux": f["aux_rand"].lower()})
+    ver = txt[txt.index("const BIP340_VERIFY_VECTORS"):txt.index("fn bip340_verify_vectors")]
+    for m in re.finditer(r"VerifyVector\s*\{(.*?)\n        \},", ver, re.S):
+        body = m.group(1)
+        idx = int(re.search(r"index:\s*(\d+)", body).group(1))
+        f = {k: re.sub(r"\s+", "", v) for k, v in re.findall(r'(\w+):\s*hex!\(\s*"([0-9A-Fa-f\s]+)"\s*\)', body)}
+        valid = re.search(r"valid:\s*(true|false)", body).group(1) == "true"
+        out.append({"index": idx, "pk": f["public_key"].lower(), "msg": f["message"].lower(), "sig": f["signature"].lower(), "valid": valid})
+    return {"source": "k256/src/schnorr.rs (BIP340_SIGN_VECTORS, BIP340_VERIFY_VECTORS)", "vectors": out}
+
+
+def ecdsa_full(curve):
+    txt = open(f"{REF}/{curve}/src/test_vectors/ecdsa.rs").read()
+    out = []
+    for m in re.finditer(r"TestVector\s*\{(.*?)\}", txt, re.S):
+        f = {k: v.lower() for k, v in re.findall(r'(\w+):\s*&hex!\("([0-9a-fA-F]+)"\)', m.group(1))}
+        if {"d", "q_x", "q_y", "k", "m", "r", "s"} <= set(f):
+            out.append(f)
+    return {"source": f"{curve}/src/test_vectors/ecdsa.rs", "vectors": out}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "k256_bip340.json"), "w") as f:
+        v = bip340_vectors()
+        json.dump(v, f, indent=1)
+        print("bip340", len(v["vectors"]))
+    for curve in ("k256", "p256"):
+        with open(os.path.join(OUT, f"{curve}_ecdsa.json"), "w") as f:
+            v = ecdsa_full(curve)
+            json.dump(v, f, indent=1)
+            print("ecdsa", curve, len(v["vectors"]))
     for curve in ("k256", "p256"):
         data = {
             "curve": curve,

@@ -161,3 +161,69 @@ def glv_split(k: int):
     k2 = -c1 * b1 - c2 * b2
     assert (k1 + k2 * K256_LAMBDA - k) % n == 0
     return k1, k2
+
+
+# ---- signature verification (first widening step) ---------------------------------
+# BIP340: k256/src/schnorr/verifying.rs:76-99 (verify_raw), :36-52 (from_bytes / lift_x), k256/src/schnorr.rs:221-227
+# (tagged_hash).  ECDSA: SEC1 4.1.4 as implemented by the `ecdsa` crate the curve crates re-export
+# (k256/src/ecdsa.rs:93-121); low-S rule = EcdsaCurve::NORMALIZE_S (k256/src/ecdsa.rs:104-106).
+
+def tagged_hash(tag: bytes, data: bytes) -> bytes:
+    t = hashlib.sha256(tag).digest()
+    return hashlib.sha256(t + t + data).digest()
+
+
+def lift_x(x: int):
+    p = K256.p
+    if x >= p:
+        return None
+    rhs = (pow(x, 3, p) + 7) % p
+    y = pow(rhs, (p + 1) // 4, p)
+    if y * y % p != rhs:
+        return None
+    return (x, y if y % 2 == 0 else p - y)
+
+
+def bip340_verify(pk32: bytes, msg: bytes, sig64: bytes) -> bool:
+    p, n = K256.p, K256.n
+    P = lift_x(int.from_bytes(pk32, "big"))
+    r = int.from_bytes(sig64[:32], "big")
+    s = int.from_bytes(sig64[32:], "big")
+    if P is None or r >= p or s >= n or s == 0:   # Signature::try_from: s is a NonZeroScalar
+        return False
+    e = int.from_bytes(tagged_hash(b"BIP0340/challenge", sig64[:32] + pk32 + msg), "big") % n
+    R = add(K256, mul(K256, s, G(K256)), mul(K256, (n - e) % n, P))
+    return R is not None and R[1] % 2 == 0 and R[0] == r
+
+
+def bip340_sign(sk: int, msg: bytes, aux: bytes) -> tuple[bytes, bytes]:
+    """BIP340 default signing (test-data generator only). Returns (pk32, sig64)."""
+    n = K256.n
+    P = mul(K256, sk, G(K256))
+    d = sk if P[1] % 2 == 0 else n - sk
+    pk = P[0].to_bytes(32, "big")
+    t = (d ^ int.from_bytes(tagged_hash(b"BIP0340/aux", aux), "big")).to_bytes(32, "big")
+    k0 = int.from_bytes(tagged_hash(b"BIP0340/nonce", t + pk + msg), "big") % n
+    R = mul(K256, k0, G(K256))
+    k = k0 if R[1] % 2 == 0 else n - k0
+    e = int.from_bytes(tagged_hash(b"BIP0340/challenge", R[0].to_bytes(32, "big") + pk + msg), "big") % n
+    return pk, R[0].to_bytes(32, "big") + ((k + e * d) % n).to_bytes(32, "big")
+
+
+def ecdsa_verify(c: Curve, z: int, r: int, s: int, Q, low_s_only: bool = False) -> bool:
+    n = c.n
+    if not (0 < r < n and 0 < s < n) or Q is None or not on_curve(c, Q):
+        return False
+    if low_s_only and s > n // 2:
+        return False
+    w = pow(s, -1, n)
+    R = add(c, mul(c, (z % n) * w % n, G(c)), mul(c, r * w % n, Q))
+    return R is not None and R[0] % n == r
+
+
+def ecdsa_sign(c: Curve, d: int, z: int, k: int):
+    n = c.n
+    R = mul(c, k, G(c))
+    r = R[0] % n
+    s = pow(k, -1, n) * (z + r * d) % n
+    return r, s

@@ -9,6 +9,7 @@
 #include "../../elliptic-curves_b200/csrc/ecg_mul.cuh"
 #include "../../elliptic-curves_b200/csrc/ecg_io.cuh"
 #include "../../elliptic-curves_b200/csrc/ecg_msm.cuh"
+#include "../../elliptic-curves_b200/csrc/ecg_verify.cuh"
 
 using namespace ecg;
 
@@ -173,6 +174,48 @@ int sim_fe_mul_kara(int curve, const uint8_t* a, const uint8_t* b, uint8_t* out)
     FpP256T<9>::normalize(r, r);
   }
   store_be32(out, r.v);
+  return 0;
+}
+// ---- verification front end (ecg_verify.cuh) ----
+int sim_bip340_challenge(const uint8_t* r32, const uint8_t* pk32, const uint8_t* m32, uint8_t* e_be) {
+  alignas(4) uint8_t rb[32], pb[32], mb[32];
+  memcpy(rb, r32, 32);
+  memcpy(pb, pk32, 32);
+  memcpy(mb, m32, 32);
+  uint32_t e[8];
+  bip340_challenge(e, rb, pb, mb);
+  store_be32(e_be, e);
+  return 0;
+}
+int sim_k256_lift_x(const uint8_t* x_be, uint8_t* y_be) {
+  uint32_t x[8];
+  load_be32(x, x_be);
+  Aff P;
+  if (!k256_lift_x<FpK256>(P, x)) return 0;
+  Fe y;
+  FpK256::normalize(y, P.y);
+  store_be32(y_be, y.v);
+  return 1;
+}
+// op 0: a*b mod n, op 1: a^-1 mod n   (plain in, plain out; exercises to_mont / mul / inv / from_mont)
+int sim_fn_op(int curve, int op, const uint8_t* a_be, const uint8_t* b_be, uint8_t* out_be) {
+  uint32_t a[8], b[8], am[8], bm[8], r[8];
+  load_be32(a, a_be);
+  load_be32(b, b_be);
+  if (curve == 0) {
+    typedef FnMont<CurveK256> N;
+    N::to_mont(am, a);
+    N::to_mont(bm, b);
+    if (op == 0) N::mul(r, am, bm); else N::inv(r, am);
+    N::from_mont(r, r);
+  } else {
+    typedef FnMont<CurveP256> N;
+    N::to_mont(am, a);
+    N::to_mont(bm, b);
+    if (op == 0) N::mul(r, am, bm); else N::inv(r, am);
+    N::from_mont(r, r);
+  }
+  store_be32(out_be, r);
   return 0;
 }
 // bucket-method digit recoding (ecg_msm.cuh): m little-endian 36 bytes -> W signed digits

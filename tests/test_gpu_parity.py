@@ -476,3 +476,97 @@ def test_reference_proptest_properties(engine, curve):
         xyz += (P[0] * z * z % c.p).to_bytes(32, "big") + (P[1] * z * z * z % c.p).to_bytes(32, "big") + z.to_bytes(32, "big")
     b_xy, b_inf = engine.batch_normalize(curve, np.frombuffer(bytes(xyz), np.uint8))
     assert np.array_equal(np.asarray(b_xy).reshape(-1), np.asarray(p_xy).reshape(-1)) and not b_inf.any()
+
+
+# ---------------------------------------------------------------- first widening step: signature verification
+def test_bip340_reference_vectors_and_random_batch(engine):
+    import json
+    import os
+
+    from helpers import GOLDEN
+
+    v = json.load(open(os.path.join(GOLDEN, "k256_bip340.json")))["vectors"]
+    pk = np.frombuffer(b"".join(bytes.fromhex(x["pk"]) for x in v), np.uint8)
+    msg = np.frombuffer(b"".join(bytes.fromhex(x["msg"]) for x in v), np.uint8)
+    sig = np.frombuffer(b"".join(bytes.fromhex(x["sig"]) for x in v), np.uint8)
+    valid = engine.schnorr_verify_batch(pk, msg, sig)
+    assert [bool(b) for b in valid] == [x["valid"] for x in v]
+    # random batch: valid signatures, then every kind of corruption
+    rng = random.Random(340)
+    n = 400
+    pks, msgs, sigs, exp = [], [], [], []
+    for i in range(n):
+        sk = rng.randrange(1, pyref.K256.n)
+        m = rng.randbytes(32)
+        p_, s_ = pyref.bip340_sign(sk, m, rng.randbytes(32))
+        kind = i % 8
+        if kind == 1:
+            s_ = bytes([s_[0] ^ 1]) + s_[1:]                       # r flipped
+        elif kind == 2:
+            s_ = s_[:40] + bytes([s_[40] ^ 0x10]) + s_[41:]         # s flipped
+        elif kind == 3:
+            m = bytes([m[0] ^ 0x80]) + m[1:]                        # other message
+        elif kind == 4:
+            p_ = bytes([p_[5] ^ 2]) + p_[1:] if False else p_[:5] + bytes([p_[5] ^ 2]) + p_[6:]  # other / invalid key
+        elif kind == 5:
+            s_ = s_[:32] + pyref.K256.n.to_bytes(32, "big")         # s = n (out of range)
+        elif kind == 6:
+            s_ = pyref.K256.p.to_bytes(32, "big") + s_[32:]         # r = p (out of range)
+        pks.append(p_)
+        msgs.append(m)
+        sigs.append(s_)
+        exp.append(pyref.bip340_verify(p_, m, s_))
+    valid = engine.schnorr_verify_batch(np.frombuffer(b"".join(pks), np.uint8), np.frombuffer(b"".join(msgs), np.uint8),
+                                        np.frombuffer(b"".join(sigs), np.uint8))
+    assert [bool(b) for b in valid] == exp
+    assert sum(exp) >= n // 8 * 2
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_ecdsa_reference_vectors_and_random_batch(engine, curve):
+    import json
+    import os
+
+    from helpers import GOLDEN
+
+    c = pyref.CURVES[curve]
+    vec = json.load(open(os.path.join(GOLDEN, f"{curve}_ecdsa.json")))["vectors"]
+    z = np.frombuffer(b"".join(bytes.fromhex(x["m"]) for x in vec), np.uint8)
+    sig = np.frombuffer(b"".join(bytes.fromhex(x["r"] + x["s"]) for x in vec), np.uint8)
+    q = np.frombuffer(b"".join(bytes.fromhex(x["q_x"] + x["q_y"]) for x in vec), np.uint8)
+    assert engine.ecdsa_verify_batch(curve, z, sig, q).all()
+    bad = sig.copy()
+    bad[31] ^= 1
+    assert not engine.ecdsa_verify_batch(curve, z, bad, q).any()
+    rng = random.Random(186)
+    n = 400
+    zs, sigs, qs, exp, exp_low = [], [], [], [], []
+    for i in range(n):
+        d = rng.randrange(1, c.n)
+        Q = pyref.mul(c, d, pyref.G(c))
+        zi = rng.getrandbits(256)
+        r, s = pyref.ecdsa_sign(c, d, zi % c.n, rng.randrange(1, c.n))
+        kind = i % 8
+        qb = Q[0].to_bytes(32, "big") + Q[1].to_bytes(32, "big")
+        if kind == 1:
+            r ^= 1 << 7
+        elif kind == 2:
+            s = 0
+        elif kind == 3:
+            zi ^= 1
+        elif kind == 4:
+            qb = qb[:63] + bytes([qb[63] ^ 1])                    # off-curve key
+        elif kind == 5:
+            r = c.n                                                # out of range
+        elif kind == 6:
+            s = c.n - s                                            # the other valid s (high/low twin)
+        zs.append(zi.to_bytes(32, "big"))
+        sigs.append((r % 2**256).to_bytes(32, "big") + s.to_bytes(32, "big"))
+        qs.append(qb)
+        Qp = (int.from_bytes(qb[:32], "big"), int.from_bytes(qb[32:], "big"))
+        exp.append(pyref.ecdsa_verify(c, zi, r, s, Qp))
+        exp_low.append(pyref.ecdsa_verify(c, zi, r, s, Qp, low_s_only=True))
+    Z, S, Qa = (np.frombuffer(b"".join(a), np.uint8) for a in (zs, sigs, qs))
+    assert [bool(b) for b in engine.ecdsa_verify_batch(curve, Z, S, Qa)] == exp
+    assert [bool(b) for b in engine.ecdsa_verify_batch(curve, Z, S, Qa, low_s_only=True)] == exp_low
+    assert sum(exp) > sum(exp_low) > 0

@@ -131,3 +131,27 @@ def test_glv_decomposition_matches_reference_definition():
         assert min(r1, n - r1) < 2**128 and min(r2, n - r2) < 2**128
         k1, k2 = pyref.glv_split(k)
         assert (k1 % n, k2 % n) == (r1, r2)
+
+
+def test_oracle_signature_verification_vs_reference_vectors():
+    """BIP340 vectors (k256/src/schnorr.rs) incl. the 10 invalid cases; FIPS 186-4 ECDSA vectors
+    ({k256,p256}/src/test_vectors/ecdsa.rs): signing reproduces (r, s), verification accepts, tampering rejects."""
+    import json
+    import os
+
+    from helpers import GOLDEN
+
+    v = json.load(open(os.path.join(GOLDEN, "k256_bip340.json")))["vectors"]
+    assert len(v) == 15 and sum(x["valid"] for x in v) == 5
+    for x in v:
+        assert pyref.bip340_verify(bytes.fromhex(x["pk"]), bytes.fromhex(x["msg"]), bytes.fromhex(x["sig"])) == x["valid"], x["index"]
+        if "sk" in x:
+            pk, sig = pyref.bip340_sign(int(x["sk"], 16), bytes.fromhex(x["msg"]), bytes.fromhex(x["aux"]))
+            assert pk.hex() == x["pk"] and sig.hex() == x["sig"]
+    for curve in CURVES:
+        c = pyref.CURVES[curve]
+        for x in json.load(open(os.path.join(GOLDEN, f"{curve}_ecdsa.json")))["vectors"]:
+            d, k, z, r, s = (int(x[t], 16) for t in ("d", "k", "m", "r", "s"))
+            Q = (int(x["q_x"], 16), int(x["q_y"], 16))
+            assert pyref.ecdsa_sign(c, d, z, k) == (r, s)
+            assert pyref.ecdsa_verify(c, z, r, s, Q) and not pyref.ecdsa_verify(c, z ^ 1, r, s, Q)

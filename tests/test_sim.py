@@ -158,6 +158,38 @@ def test_msm_digit_recoding(sim):
                 assert 0 <= d[-1] <= (1 << (c + 1)) + 1
 
 
+def test_verify_front_end_pieces(sim):
+    """SHA-256 challenge, lift_x and mod-n Montgomery arithmetic used by the signature-verification kernels"""
+    rng = random.Random(9)
+    for _ in range(50):
+        r, pk, m = rng.randbytes(32), rng.randbytes(32), rng.randbytes(32)
+        out = ctypes.create_string_buffer(32)
+        sim.sim_bip340_challenge(r, pk, m, out)
+        assert out.raw == pyref.tagged_hash(b"BIP0340/challenge", r + pk + m)
+    hits = 0
+    for i in range(60):
+        x = rng.randrange(pyref.K256.p) if i else pyref.K256.gx
+        out = ctypes.create_string_buffer(32)
+        ok = sim.sim_k256_lift_x(x.to_bytes(32, "big"), out)
+        exp = pyref.lift_x(x)
+        assert bool(ok) == (exp is not None)
+        if exp:
+            hits += 1
+            assert int.from_bytes(out.raw, "big") == exp[1]
+    assert hits > 10
+    assert sim.sim_k256_lift_x((pyref.K256.p + 1).to_bytes(32, "big"), ctypes.create_string_buffer(32)) == 0
+    for ci, curve in enumerate(("k256", "p256")):
+        n = pyref.CURVES[curve].n
+        for a, b in [(1, 1), (n - 1, n - 1), (2, (n + 1) // 2), (n - 1, 2)] + [(rng.randrange(1, n), rng.randrange(1, n)) for _ in range(40)]:
+            out = ctypes.create_string_buffer(32)
+            sim.sim_fn_op(ci, 0, a.to_bytes(32, "big"), b.to_bytes(32, "big"), out)
+            assert int.from_bytes(out.raw, "big") == a * b % n
+        for a in [1, 2, n - 1] + [rng.randrange(1, n) for _ in range(5)]:
+            out = ctypes.create_string_buffer(32)
+            sim.sim_fn_op(ci, 1, a.to_bytes(32, "big"), (1).to_bytes(32, "big"), out)
+            assert int.from_bytes(out.raw, "big") == pow(a, -1, n)
+
+
 def test_on_curve_check(sim):
     for curve in ("k256", "p256"):
         c = pyref.CURVES[curve]
