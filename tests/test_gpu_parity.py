@@ -536,8 +536,11 @@ def test_ecdsa_reference_vectors_and_random_batch(engine, curve):
     q = np.frombuffer(b"".join(bytes.fromhex(x["q_x"] + x["q_y"]) for x in vec), np.uint8)
     assert engine.ecdsa_verify_batch(curve, z, sig, q).all()
     bad = sig.copy()
-    bad[31] ^= 1
+    bad.reshape(-1, 64)[:, 31] ^= 1  # corrupt r of every signature
     assert not engine.ecdsa_verify_batch(curve, z, bad, q).any()
+    one = sig.copy()
+    one[31] ^= 1  # corrupt only the first: verdicts are per signature
+    assert list(engine.ecdsa_verify_batch(curve, z, one, q)) == [0] + [1] * (len(vec) - 1)
     rng = random.Random(186)
     n = 400
     zs, sigs, qs, exp, exp_low = [], [], [], [], []
