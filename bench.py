@@ -40,16 +40,20 @@ WORKLOADS = {
     "p256_varbase": ("p256", "mul", 20, 2, "scalar-mults/s"),
     "k256_fixedbase": ("k256", "mulgen", 22, 3, "scalar-mults/s"),
     "k256_lincomb": ("k256", "lincomb", 21, 4, "terms/s"),
+    # first widening step, not a BASELINE.json config: BIP340 verification
+    "k256_schnorr_verify": ("k256", "schnorr", 20, None, "verifications/s"),
 }
-SEEDS = {"k256_varbase": 0xB2000001, "p256_varbase": 0xB2000002, "k256_fixedbase": 0xB2000003, "k256_lincomb": 0xB2000004}
-ALGO_BYTES = {"mul": 160, "mulgen": 96, "lincomb": 96}  # algorithmic bytes per unit
+SEEDS = {"k256_varbase": 0xB2000001, "p256_varbase": 0xB2000002, "k256_fixedbase": 0xB2000003, "k256_lincomb": 0xB2000004,
+         "k256_schnorr_verify": 0xB2000005}
+ALGO_BYTES = {"mul": 160, "mulgen": 96, "lincomb": 96, "schnorr": 129}  # algorithmic bytes per unit
 # IMAD.WIDE (32x32->64 multiply-accumulate) instructions per unit of work in the dominant kernel, counted from
 # the kernels' operation schedule (derivation: DESIGN.md "Integer roofline"):
 #   k256: M = 64 + 8 (product + reduction), S = 36 + 8;  var-base = 1046 M + 748 S + 129 mul_small*8 + GLV ~200
 #   p256: M = 64, S = 36 (Solinas reduction uses no multiplier); var-base = 1885 M + 1316 S + 258*8
 #   k256 fixed-base: 17 mixed additions = 136 M + 51 S
 #   k256 lincomb (bucket kernel, c = 16): 2 halves x 8 windows mixed additions = 128 M + 48 S per term
-IMADW_PER_UNIT = {("k256", "mul"): 109_500, ("p256", "mul"): 170_100, ("k256", "mulgen"): 12_000, ("k256", "lincomb"): 11_300}
+#   k256 schnorr verify (mul_gen_add kernel): var-base + fixed-base accumulation
+IMADW_PER_UNIT = {("k256", "schnorr"): 121_500, ("k256", "mul"): 109_500, ("p256", "mul"): 170_100, ("k256", "mulgen"): 12_000, ("k256", "lincomb"): 11_300}
 
 
 def synth_scalars(curve, seed, start, count):
@@ -84,6 +88,41 @@ def synth_point_scalars(curve, seed, start, count):
             v = 1
         out[32 * j:32 * j + 32] = v.to_bytes(32, "big")
     return np.frombuffer(bytes(out), dtype=np.uint8).copy()
+
+
+def synth_schnorr(eng, seed, start, count):
+    """count valid BIP340 (pk, msg, sig) triples: keys and nonces from the seeded hash, k*G / d*G on the GPU's
+    fixed-base path, challenges with hashlib, s = k + e*d on the host."""
+    import pyref
+
+    c = pyref.K256
+    n, p = c.n, c.p
+    d = synth_point_scalars("k256", seed, start, count)
+    k = synth_scalars("k256", seed ^ 0x5A5A, start, count)
+    Pxy, _ = eng.mul_by_generator("k256", d)
+    Rxy, Rinf = eng.mul_by_generator("k256", k)
+    Pxy, Rxy = np.asarray(Pxy).reshape(count, 64), np.asarray(Rxy).reshape(count, 64)
+    pk = np.ascontiguousarray(Pxy[:, :32]).reshape(-1)
+    msg = synth_scalars("k256", seed ^ 0xA5A5, start, count)  # any 32 bytes
+    sig = np.empty((count, 64), np.uint8)
+    th = hashlib.sha256(b"BIP0340/challenge").digest()
+    pre = hashlib.sha256(th + th)
+    dv, kv, mv = d.reshape(count, 32), k.reshape(count, 32), msg.reshape(count, 32)
+    for i in range(count):
+        di = int.from_bytes(dv[i].tobytes(), "big")
+        ki = int.from_bytes(kv[i].tobytes(), "big")
+        if ki == 0 or Rinf[i]:
+            ki = 1
+        if Pxy[i, 63] & 1:
+            di = n - di
+        if Rxy[i, 63] & 1:
+            ki = n - ki
+        h = pre.copy()
+        h.update(Rxy[i, :32].tobytes() + Pxy[i, :32].tobytes() + mv[i].tobytes())
+        e = int.from_bytes(h.digest(), "big") % n
+        sig[i, :32] = Rxy[i, :32]
+        sig[i, 32:] = np.frombuffer(((ki + e * di) % n).to_bytes(32, "big"), np.uint8)
+    return pk, msg, sig.reshape(-1)
 
 
 class ClockSampler:
@@ -201,21 +240,32 @@ def run_ours(args):
     start = rank * n
 
     # ---- synthetic inputs: scalars hashed on the host, points P_i = t_i*G made with the fixed-base kernel
-    k_host = torch.from_numpy(synth_scalars(curve, seed, start, n)).pin_memory()
     host_eng = ecgpu.Engine([local])
-    if op != "mulgen":
+    if op == "schnorr":
+        pk_np, msg_np, sig_np = synth_schnorr(host_eng, seed, start, n)
+        k_host = torch.from_numpy(pk_np).pin_memory()      # pk  (32 B)
+        a_host = torch.from_numpy(msg_np).pin_memory()     # msg (32 B)
+        p_host = torch.from_numpy(sig_np).pin_memory()     # sig (64 B)
+    else:
+        k_host = torch.from_numpy(synth_scalars(curve, seed, start, n)).pin_memory()
+        a_host = None
+    if op == "schnorr":
+        pass
+    elif op != "mulgen":
         t_host = synth_point_scalars(curve, seed, start, n)
         pxy, pinf = host_eng.mul_by_generator(curve, t_host)
         assert not pinf.any()
         p_host = torch.from_numpy(np.ascontiguousarray(pxy).reshape(-1)).pin_memory()
     else:
         p_host = None
-    out_host = torch.empty(64 * n if op != "lincomb" else 64, dtype=torch.uint8).pin_memory()
+    out_bytes = {"lincomb": 64, "schnorr": n}.get(op, 64 * n)
+    out_host = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
     oinf_host = torch.empty(n if op != "lincomb" else 1, dtype=torch.uint8).pin_memory()
 
     kd = k_host.to(dev)
     pd = p_host.to(dev) if p_host is not None else None
-    oxy = torch.empty(64 * n if op != "lincomb" else 64, dtype=torch.uint8, device=dev)
+    ad = a_host.to(dev) if a_host is not None else None
+    oxy = torch.empty(out_bytes, dtype=torch.uint8, device=dev)
     oinf = torch.empty(n if op != "lincomb" else 1, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     part_d = torch.empty(96, dtype=torch.uint8, device=dev)
@@ -231,6 +281,8 @@ def run_ours(args):
             eng.mul_batch_ptr(curve, n, kd.data_ptr(), pd.data_ptr(), 0, oxy.data_ptr(), oinf.data_ptr())
         elif op == "mulgen":
             eng.mul_gen_batch_ptr(curve, n, kd.data_ptr(), oxy.data_ptr(), oinf.data_ptr())
+        elif op == "schnorr":
+            eng.schnorr_verify_ptr(n, kd.data_ptr(), ad.data_ptr(), pd.data_ptr(), oxy.data_ptr())
         elif world == 1:
             eng.lincomb_ptr(curve, n, kd.data_ptr(), pd.data_ptr(), 0, oxy.data_ptr(), oinf.data_ptr())
         else:
@@ -250,6 +302,8 @@ def run_ours(args):
             host_eng.mul_batch(curve, k_np, p_host.numpy(), None, o_np, oi_np)
         elif op == "mulgen":
             host_eng.mul_by_generator(curve, k_np, o_np, oi_np)
+        elif op == "schnorr":
+            o_np[:] = host_eng.schnorr_verify_batch(k_np, a_host.numpy(), p_host.numpy())
         else:
             xy, inf = host_eng.lincomb(curve, k_np, p_host.numpy(), None)
             o_np[:] = xy
@@ -289,12 +343,14 @@ def run_ours(args):
     barrier_sync(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
     e2e_value = world * n * args.steps / e2e_s
-    h2d = 32 * n + (64 * n if op != "mulgen" else 0)
-    d2h = (65 * n) if op != "lincomb" else 65
+    h2d = 32 * n + (64 * n if op != "mulgen" else 0) + (32 * n if op == "schnorr" else 0)
+    d2h = {"lincomb": 65, "schnorr": n}.get(op, 65 * n)
 
     # ---- device result of the last device step == host-API result (same inputs)?
     if op == "lincomb" and world > 1:
         same = True  # the device path produced the GLOBAL sum (checked against the oracle below on rank 0)
+    elif op == "schnorr":
+        same = bool(np.array_equal(oxy.cpu().numpy(), out_host.numpy())) and bool(out_host.numpy().all())
     else:
         same = bool(np.array_equal(oxy.cpu().numpy(), out_host.numpy())) and bool(np.array_equal(oinf.cpu().numpy(), oinf_host.numpy()))
 
@@ -328,14 +384,23 @@ def run_ours(args):
         ns = min(n, 1 << 18) if op != "mulgen" else min(n, 1 << 19)
         k_s = k_host.numpy()[:32 * ns]
         t0 = time.perf_counter()
-        if op == "mul":
+        if op == "schnorr":
+            # the reference's verify_raw = tagged hash + mul_by_generator_and_mul_add_vartime(s, -e, P) + checks;
+            # the sample times the group-operation part (a*G + b*P, oracle/ecref.c) on the same keys
+            s_s = np.ascontiguousarray(p_host.numpy().reshape(n, 64)[:ns, 32:]).reshape(-1)
+            pxy_s, _ = host_eng.mul_by_generator(curve, synth_point_scalars(curve, seed, start, ns))
+            t0 = time.perf_counter()
+            r_xy, r_inf = ecref.mul_gen_add_batch(curve, s_s, k_s, np.asarray(pxy_s).reshape(-1), None, nthreads=cores)
+        elif op == "mul":
             r_xy, r_inf = ecref.mul_batch(curve, k_s, p_host.numpy()[:64 * ns], None, nthreads=cores, variant=0)
         elif op == "mulgen":
             r_xy, r_inf = ecref.mul_gen_batch(curve, k_s, nthreads=cores)
         else:
             r_xy, r_inf = ecref.lincomb(curve, k_s, p_host.numpy()[:64 * ns], None, nthreads=cores)
         cpu_s = time.perf_counter() - t0
-        if op != "lincomb":
+        if op == "schnorr":
+            bit_exact = bool(out_host.numpy().all())  # every synthetic signature is valid by construction
+        elif op != "lincomb":
             bit_exact = bool(np.array_equal(out_host.numpy()[:64 * ns], r_xy.reshape(-1))) and bool(np.array_equal(oinf_host.numpy()[:ns], r_inf))
         else:
             sub_xy, sub_inf = host_eng.lincomb(curve, k_s, p_host.numpy()[:64 * ns], None)
@@ -349,7 +414,8 @@ def run_ours(args):
             "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"BASELINE.json configs[{cfg_idx}]: {args.workload}, batch 2^{logn} per GPU", "curve": curve,
+            "config": {"workload": (f"BASELINE.json configs[{cfg_idx}]: " if cfg_idx is not None else "widening step (not a BASELINE config): ")
+                                   + f"{args.workload}, batch 2^{logn} per GPU", "curve": curve,
                        "batch_per_gpu": n, "inputs": "k_i, t_i = SHA-256(seed||tag||LE64(i)) mod n; P_i = t_i*G (SURVEY 8(d))",
                        "l2": "256 MiB buffer written between timed iterations (L2 flush); working set 288 MiB > L2",
                        "parallelism": f"batch sharded over {world} rank(s), no data-path collective"},

@@ -293,6 +293,9 @@ class Engine:
     def lincomb_ptr(self, curve, n, k, P_xy, P_inf, out_xy, out_inf):
         self._check(self.lib.ecg_lincomb(self._ctx, CURVE_IDS[curve], n, _ptr(k), _ptr(P_xy), _ptr(P_inf), _ptr(out_xy), _ptr(out_inf)))
 
+    def schnorr_verify_ptr(self, n, pk_x, msg32, sig64, valid):
+        self._check(self.lib.ecg_schnorr_verify_batch(self._ctx, n, _ptr(pk_x), _ptr(msg32), _ptr(sig64), _ptr(valid)))
+
     def timing_enable(self, on: bool = True):
         self._check(self.lib.ecg_timing_enable(self._ctx, 1 if on else 0))
 

@@ -1097,6 +1097,24 @@ static void k_mul_vartime(kpt* out, const kpt* x, const uint8_t* k_be) {
   k_wnaf_multi_exp(out, &T.tab[0][0], &T.dg[0][0], T.len, 2, 130);
 }
 
+/* mul.rs:303-310 mul_by_generator_and_mul_add_vartime: a*G + b*P = lincomb_vartime_glv_wnaf of the two decomposed terms */
+static kpt K_GEN;
+static void k_mul_gen_add(kpt* out, const uint8_t* a_be, const uint8_t* b_be, const kpt* P) {
+  kwterm T[2];
+  k_prepare_wterm(&T[0], &K_GEN, a_be);
+  k_prepare_wterm(&T[1], P, b_be);
+  kpt tabs[4 * WNAF_TAB];
+  int8_t dg[4 * 130];
+  int lens[4];
+  for (int t = 0; t < 2; t++)
+    for (int h = 0; h < 2; h++) {
+      memcpy(&tabs[(2 * t + h) * WNAF_TAB], T[t].tab[h], sizeof(kpt) * WNAF_TAB);
+      memcpy(&dg[(2 * t + h) * 130], T[t].dg[h], 130);
+      lens[2 * t + h] = T[t].len[h];
+    }
+  k_wnaf_multi_exp(out, tabs, dg, lens, 4, 130);
+}
+
 /* ---- p256 drivers (primeorder/src/projective.rs:133-144, :532-557) -------------------------------- */
 typedef struct {
   ppt t[8];
@@ -1138,6 +1156,23 @@ static void p_mul_vartime(ppt* out, const ppt* x, const uint8_t* k_be) {
   p_wnaf_multi_exp(out, tab, dg, &len, 1, 260);
 }
 
+/* primeorder/src/mul_backend.rs:31-40 (default): lincomb_vartime(&[(G, a), (P, b)]) = 2-term wNAF-5 Straus
+ * (primeorder/src/projective.rs:525-529) */
+static ppt P_GEN;
+static void p_mul_gen_add(ppt* out, const uint8_t* a_be, const uint8_t* b_be, const ppt* P) {
+  ppt tabs[2 * WNAF_TAB];
+  int8_t dg[2 * 260];
+  int lens[2];
+  uint8_t le[32];
+  for (int i = 0; i < 32; i++) le[i] = a_be[31 - i];
+  lens[0] = wnaf_form(&dg[0], le, 32, 256, WNAF_W);
+  for (int i = 0; i < 32; i++) le[i] = b_be[31 - i];
+  lens[1] = wnaf_form(&dg[260], le, 32, 256, WNAF_W);
+  p_wnaf_table(&tabs[0], &P_GEN);
+  p_wnaf_table(&tabs[WNAF_TAB], P);
+  p_wnaf_multi_exp(out, tabs, dg, lens, 2, 260);
+}
+
 /* ================================================================================================
  * Exported batch API (ctypes).  curve: 0 = k256, 1 = p256.  Bytes as in include/ecgpu.h.
  * variant: 0 = constant-time `*` path (mul.rs:236-238 / projective.rs:133-137), 1 = mul_vartime.
@@ -1166,6 +1201,7 @@ void ecref_init(void) {
     hex32(b, "4fe342e2fe1a7f9b8ee7eb4a7c0f9e162bce33576b315ececbb6406837bf51f5");
     fp_from_be(&P256_GY, b);
     ppt pg = {P256_GX, P256_GY, P256_ONE};
+    P_GEN = pg;
     p_basetab_init(&pg);
     kpt kg;
     hex32(b, "79be667ef9dcbbac55a06295ce870b07029bfcdb2dce28d959f2815b16f81798"); /* k256/src/arithmetic/affine.rs:61-77 */
@@ -1173,6 +1209,7 @@ void ecref_init(void) {
     hex32(b, "483ada7726a3c4655da4fbfc0e1108a8fd17b448a68554199c47d08ffb10d4b8");
     fe52_from_be(&kg.y, b);
     kg.z = FE52_ONE;
+    K_GEN = kg;
     k_basetab_init(&kg);
     g_init = 1;
   }
@@ -1261,7 +1298,7 @@ static void p_store_point(uint8_t* xy, uint8_t* inf, const ppt* p) {
 typedef struct {
   int curve, variant, op;
   size_t lo, hi;
-  const uint8_t *k, *pxy, *pinf;
+  const uint8_t *k, *pxy, *pinf, *a;
   uint8_t *oxy, *oinf;
   int err; /* 0 ok, 2 scalar range, 3 not on curve (ecg_status values) */
   size_t err_index;
@@ -1270,7 +1307,7 @@ typedef struct {
   ppt pacc;
 } job;
 
-enum { OP_MUL = 0, OP_MULGEN = 1, OP_LINCOMB = 2 };
+enum { OP_MUL = 0, OP_MULGEN = 1, OP_LINCOMB = 2, OP_MULGENADD = 3 };
 #define LINCOMB_CHUNK 256 /* terms per reference-style lincomb call (the reference's single call needs ~2 KiB/term) */
 
 static void* worker(void* arg) {
@@ -1340,7 +1377,14 @@ static void* worker(void* arg) {
           j->err_index = i;
           return NULL;
         }
-        if (j->variant == 0)
+        if (j->op == OP_MULGENADD) {
+          if (!scalar_in_range(j->curve, j->a + 32 * i)) {
+            j->err = 2;
+            j->err_index = i;
+            return NULL;
+          }
+          k_mul_gen_add(&R, j->a + 32 * i, j->k + 32 * i, &P);
+        } else if (j->variant == 0)
           k_mul_ct(&R, &P, j->k + 32 * i);
         else
           k_mul_vartime(&R, &P, j->k + 32 * i);
@@ -1356,7 +1400,14 @@ static void* worker(void* arg) {
           j->err_index = i;
           return NULL;
         }
-        if (j->variant == 0)
+        if (j->op == OP_MULGENADD) {
+          if (!scalar_in_range(j->curve, j->a + 32 * i)) {
+            j->err = 2;
+            j->err_index = i;
+            return NULL;
+          }
+          p_mul_gen_add(&R, j->a + 32 * i, j->k + 32 * i, &P);
+        } else if (j->variant == 0)
           p_mul_ct(&R, &P, j->k + 32 * i);
         else
           p_mul_vartime(&R, &P, j->k + 32 * i);
@@ -1403,6 +1454,22 @@ int ecref_mul_batch(int curve, size_t n, const uint8_t* k, const uint8_t* pxy, c
   t.variant = variant;
   t.op = OP_MUL;
   t.k = k;
+  t.pxy = pxy;
+  t.pinf = pinf;
+  t.oxy = oxy;
+  t.oinf = oinf;
+  return run_jobs(&t, n, nthreads, NULL);
+}
+/* out[i] = a[i]*G + b[i]*P[i]  (mul_by_generator_and_mul_add_vartime) */
+int ecref_mul_gen_add_batch(int curve, size_t n, const uint8_t* a, const uint8_t* b, const uint8_t* pxy, const uint8_t* pinf,
+                            uint8_t* oxy, uint8_t* oinf, int nthreads) {
+  if (n == 0) return 0;
+  job t;
+  memset(&t, 0, sizeof t);
+  t.curve = curve;
+  t.op = OP_MULGENADD;
+  t.a = a;
+  t.k = b;
   t.pxy = pxy;
   t.pinf = pinf;
   t.oxy = oxy;

@@ -49,6 +49,7 @@ def lib():
         vp, sz = ctypes.c_void_p, ctypes.c_size_t
         _lib.ecref_mul_batch.argtypes = [ctypes.c_int, sz, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int]
         _lib.ecref_mul_gen_batch.argtypes = [ctypes.c_int, sz, vp, vp, vp, ctypes.c_int]
+        _lib.ecref_mul_gen_add_batch.argtypes = [ctypes.c_int, sz, vp, vp, vp, vp, vp, vp, ctypes.c_int]
         _lib.ecref_lincomb.argtypes = [ctypes.c_int, sz, vp, vp, vp, vp, vp, ctypes.c_int]
         _lib.ecref_field_op.argtypes = [ctypes.c_int, ctypes.c_int, sz, vp, vp, vp]
         _lib.ecref_radix16.argtypes = [vp, ctypes.c_int, vp]
@@ -87,6 +88,21 @@ def mul_gen_batch(curve, k, nthreads=1):
     rc = lib().ecref_mul_gen_batch(CURVE[curve], n, _p(k), _p(oxy), _p(oinf), nthreads)
     if rc:
         raise ValueError(f"ecref_mul_gen_batch rc={rc}")
+    return oxy.reshape(n, 64), oinf
+
+
+def mul_gen_add_batch(curve, a, b, pxy, pinf=None, nthreads=1):
+    a = np.ascontiguousarray(a, np.uint8).reshape(-1)
+    b = np.ascontiguousarray(b, np.uint8).reshape(-1)
+    n = a.size // 32
+    pxy = np.ascontiguousarray(pxy, np.uint8).reshape(-1)
+    if pinf is not None:
+        pinf = np.ascontiguousarray(pinf, np.uint8).reshape(-1)
+    oxy = np.zeros(64 * n, np.uint8)
+    oinf = np.zeros(n, np.uint8)
+    rc = lib().ecref_mul_gen_add_batch(CURVE[curve], n, _p(a), _p(b), _p(pxy), _p(pinf), _p(oxy), _p(oinf), nthreads)
+    if rc:
+        raise ValueError(f"ecref_mul_gen_add_batch rc={rc}")
     return oxy.reshape(n, 64), oinf
 
 

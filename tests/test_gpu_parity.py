@@ -183,6 +183,17 @@ def test_mul_gen_add(engine, curve):
     G = pyref.G(c)
     for i in range(n):
         assert got[i] == pyref.add(c, pyref.mul(c, a[i], G), pyref.mul(c, b[i], Ps[i])), i
+    # bit-exact against the reference's mul_by_generator_and_mul_add_vartime restatement on a larger batch
+    n2 = 3000
+    a2 = np.frombuffer(rng.randbytes(32 * n2), np.uint8).copy().reshape(n2, 32)
+    b2 = np.frombuffer(rng.randbytes(32 * n2), np.uint8).copy().reshape(n2, 32)
+    a2[:, 0] &= 0x7F
+    b2[:, 0] &= 0x7F
+    bxy, _ = pack_points(base)
+    xy2 = np.tile(bxy.reshape(16, 64), (n2 // 16 + 1, 1))[:n2].reshape(-1).copy()
+    o_xy, o_inf = engine.mul_by_generator_and_mul_add(curve, a2, b2, xy2, None)
+    r_xy, r_inf = ecref.mul_gen_add_batch(curve, a2, b2, xy2, None, nthreads=8)
+    assert np.array_equal(np.asarray(o_xy).reshape(-1), r_xy.reshape(-1)) and np.array_equal(o_inf, r_inf)
 
 
 # ---------------------------------------------------------------- lincomb (rows a7, a8, a12)

@@ -97,6 +97,26 @@ def test_ecref_lincomb_vs_bigint(curve):
         assert pyref.dec_point(oxy.tobytes(), oinf) == pyref.lincomb(c, ks, Ps)
 
 
+@pytest.mark.parametrize("curve", CURVES)
+def test_ecref_mul_gen_add_vs_bigint(curve):
+    c = pyref.CURVES[curve]
+    rng = random.Random(77)
+    n = 40
+    Ps = random_points(c, n, seed=5)
+    a = [rng.randrange(c.n) for _ in range(n)]
+    b = [rng.randrange(c.n) for _ in range(n)]
+    a[0], b[0] = 0, 0
+    a[1], b[1] = 3, 0
+    a[2], b[2] = 0, 9
+    Ps[3] = None
+    Ps[4] = pyref.G(c)
+    b[4] = c.n - a[4]
+    xy, inf = pack_points(Ps)
+    oxy, oinf = ecref.mul_gen_add_batch(curve, pack_scalars(a), pack_scalars(b), xy, inf, nthreads=2)
+    G = pyref.G(c)
+    assert unpack_points(oxy, oinf) == [pyref.add(c, pyref.mul(c, x, G), pyref.mul(c, y, P)) for x, y, P in zip(a, b, Ps)]
+
+
 def test_radix16_properties():
     # primeorder/src/tables/radix16.rs:110-172: digits in [-8, 8], reconstruct the scalar
     rng = random.Random(3)
