@@ -190,6 +190,61 @@ ECG_D void k256_sqrt_candidate(Fe& r, const Fe& a) {
   F::sqr_n(r, t, 2);
 }
 
+// NIST P-256 square root: a^((p+1)/4), (p+1)/4 = 2^254 - 2^222 + 2^190 + 2^94
+// (FieldElement::sqrt, p256/src/arithmetic/field.rs:121-147)
+template <class F>
+ECG_D void p256_sqrt_candidate(Fe& r, const Fe& a) {
+  Fe x2, x4, x8, x16, x32, t;
+  F::sqr(x2, a);
+  F::mul(x2, x2, a);
+  F::sqr_n(x4, x2, 2);
+  F::mul(x4, x4, x2);
+  F::sqr_n(x8, x4, 4);
+  F::mul(x8, x8, x4);
+  F::sqr_n(x16, x8, 8);
+  F::mul(x16, x16, x8);
+  F::sqr_n(x32, x16, 16);
+  F::mul(x32, x32, x16);
+  F::sqr_n(t, x32, 32);
+  F::mul(t, t, a);
+  F::sqr_n(t, t, 96);
+  F::mul(t, t, a);
+  F::sqr_n(r, t, 94);
+}
+
+// SEC1 decompression (AffinePoint::decompress, primeorder/src/affine.rs:179-198; k256/src/arithmetic/affine.rs
+// DecompressPoint): y = sqrt(x^3 + a x + b) with the requested parity, or false (x >= p / no square root).
+template <class C>
+ECG_D bool sec1_decompress(Aff& P, const uint32_t* x_le, uint32_t y_is_odd) {
+  typedef typename C::F F;
+  if (!lt8(x_le, C::P())) return false;
+  Fe xc, x, rhs, t, b, y, chk;
+#pragma unroll
+  for (int i = 0; i < 8; i++) xc.v[i] = x_le[i];
+  F::from_canonical(x, xc);
+  F::sqr(rhs, x);
+  F::mul(rhs, rhs, x);
+  if (C::A_IS_MINUS3) {
+    F::mul_small(t, x, 3);
+    F::sub(rhs, rhs, t);
+  }
+  C::b_internal(b);
+  F::add(rhs, rhs, b);
+  if (C::A_IS_MINUS3)
+    p256_sqrt_candidate<F>(y, rhs);
+  else
+    k256_sqrt_candidate<F>(y, rhs);
+  F::sqr(chk, y);
+  F::sub(chk, chk, rhs);
+  if (!F::is_zero(chk)) return false;
+  Fe yc;
+  F::to_canonical(yc, y);
+  if ((yc.v[0] & 1u) != (y_is_odd & 1u)) F::neg(y, y);
+  P.x = x;
+  P.y = y;
+  return true;
+}
+
 // lift_x: the point with the given x and even y, or false (x >= p or x^3 + 7 not a square).
 template <class F>
 ECG_D bool k256_lift_x(Aff& P, const uint32_t* x_le) {

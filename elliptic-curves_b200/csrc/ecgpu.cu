@@ -423,6 +423,44 @@ __global__ void __launch_bounds__(256)
   valid[idx] = (ok[idx] && !rinf[idx] && same) ? 1 : 0;
 }
 
+// SEC1 compressed points (33 bytes: 02/03 || x; 33 zero bytes = identity) -> affine x || y, identity flag, validity.
+template <class C>
+__global__ void __launch_bounds__(128)
+    decompress_kernel(const uint8_t* __restrict__ sec1, size_t n, uint8_t* __restrict__ out_xy, uint8_t* __restrict__ out_inf,
+                      uint8_t* __restrict__ valid) {
+  typedef typename C::F F;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const uint8_t* rec = sec1 + 33 * idx;
+  uint8_t tag = rec[0];
+  uint32_t x[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {  // unaligned big-endian words
+    const uint8_t* b = rec + 1 + 4 * (7 - i);
+    x[i] = ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
+  }
+  bool zero = (x[0] | x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7]) == 0;
+  Aff P;
+  bool ok = false, inf = false;
+  if (tag == 0 && zero) {
+    ok = inf = true;
+  } else if (tag == 2 || tag == 3) {
+    ok = sec1_decompress<C>(P, x, tag & 1u);
+  }
+  Fe cx, cy;
+  if (ok && !inf) {
+    F::to_canonical(cx, P.x);
+    F::to_canonical(cy, P.y);
+  } else {
+    F::set_zero(cx);
+    F::set_zero(cy);
+  }
+  store_be32(out_xy + 64 * idx, cx.v);
+  store_be32(out_xy + 64 * idx + 32, cy.v);
+  out_inf[idx] = inf ? 1 : 0;
+  valid[idx] = ok ? 1 : 0;
+}
+
 // canonical affine big-endian bytes (n*64) -> table words (internal form); used once, when a table is built
 template <class C>
 __global__ void __launch_bounds__(256)
@@ -1119,13 +1157,14 @@ static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
 // What one chunk does is the only thing that differs between ecg_mul_batch, ecg_mul_gen_batch, ecg_mul_gen_add_batch,
 // ecg_batch_normalize and ecg_field_op_batch:
 struct BatchOp {
-  enum Kind { MUL, MULGEN, MULGENADD, NORMALIZE, FIELD, SCHNORR, ECDSA } kind;
+  enum Kind { MUL, MULGEN, MULGENADD, NORMALIZE, FIELD, SCHNORR, ECDSA, DECOMPRESS } kind;
   ecg_curve curve;
   int fop = 0;  // field op, or the ECDSA low-S flag
   const uint8_t *k = nullptr, *a = nullptr, *p = nullptr, *inf = nullptr;  // host or device, per ctx flags
   const uint8_t* x = nullptr;  // extra 64-byte-stride input (ECDSA public keys)
   size_t pstride = 64;
   uint8_t *out = nullptr, *oinf = nullptr;
+  uint8_t* aux_out = nullptr;  // third output array (decompress: validity flags)
   size_t ostride = 64;
 };
 
@@ -1139,6 +1178,18 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
   const uint8_t* dx = nullptr;
   ST_TRY(stage_in(ctx, L, B_X, op.x, off, cnt, 64, &dx));
   ST_TRY(stage_out(ctx, L, off, cnt, op.out, op.ostride, op.oinf, dp));
+  if (op.kind == BatchOp::DECOMPRESS) {
+    // out = xy (64 B), oinf = identity flags, valid flags go to a third host array staged through B_V4
+    ST_TRY(ensure(ctx, L, B_V4, cnt));
+    uint8_t* vvalid = (ctx->devptr() && op.aux_out) ? op.aux_out + off : (uint8_t*)L.buf[B_V4];
+    if (op.curve == ECG_SECP256K1)
+      decompress_kernel<CurveK256><<<grid_for(cnt, 128), 128, 0, L.s()>>>(dp.p, cnt, dp.out, dp.oinf, vvalid);
+    else
+      decompress_kernel<CurveP256><<<grid_for(cnt, 128), 128, 0, L.s()>>>(dp.p, cnt, dp.out, dp.oinf, vvalid);
+    LAUNCHED(ctx);
+    if (!ctx->devptr() && op.aux_out) CU_TRY(ctx, cudaMemcpyAsync(op.aux_out + off, vvalid, cnt, cudaMemcpyDeviceToHost, L.s()));
+    return copy_back(ctx, L, off, cnt, op.out, op.ostride, op.oinf, dp);
+  }
   if (op.kind == BatchOp::SCHNORR || op.kind == BatchOp::ECDSA) {
     // front end -> (a, b, P) -> a*G + b*P -> affine -> verdict, all on the device
     ST_TRY(ensure(ctx, L, B_V1, cnt * 64));
@@ -1223,6 +1274,7 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
       break;
     case BatchOp::SCHNORR:
     case BatchOp::ECDSA:
+    case BatchOp::DECOMPRESS:
       break;  // handled above
     case BatchOp::FIELD:
       if (k1)
@@ -1325,6 +1377,25 @@ extern "C" ecg_status ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve curve, size_
   op.inf = P_inf;
   op.out = out_xy;
   op.oinf = out_inf;
+  return run_batch(ctx, op, n);
+}
+
+extern "C" ecg_status ecg_decompress_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* sec1_33, uint8_t* out_xy,
+                                            uint8_t* out_inf, uint8_t* valid) {
+  if (!ctx) return ECG_EINVAL;
+  if (n == 0) return ECG_OK;
+  if (!sec1_33 || !out_xy || !out_inf || !valid || !curve_ok(curve)) {
+    ctx->err = "ecg_decompress_batch: null pointer or unknown curve";
+    return ECG_EINVAL;
+  }
+  BatchOp op;
+  op.kind = BatchOp::DECOMPRESS;
+  op.curve = curve;
+  op.p = sec1_33;
+  op.pstride = 33;
+  op.out = out_xy;
+  op.oinf = out_inf;
+  op.aux_out = valid;
   return run_batch(ctx, op, n);
 }
 

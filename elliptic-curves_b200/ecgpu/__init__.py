@@ -37,7 +37,7 @@ EXPORTS = [
     "ecg_mul_batch", "ecg_mul_gen_batch", "ecg_lincomb", "ecg_lincomb_partial", "ecg_point_sum",
     "ecg_mul_gen_add_batch", "ecg_batch_normalize", "ecg_field_op_batch", "ecg_microbench",
     "ecg_kernel_launches", "ecg_version", "ecg_timing_enable", "ecg_timing_read",
-    "ecg_schnorr_verify_batch", "ecg_ecdsa_verify_batch",
+    "ecg_schnorr_verify_batch", "ecg_ecdsa_verify_batch", "ecg_decompress_batch",
 ]
 
 
@@ -107,6 +107,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.ecg_schnorr_verify_batch.restype = ctypes.c_int
     lib.ecg_ecdsa_verify_batch.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p, ctypes.c_int, u8p]
     lib.ecg_ecdsa_verify_batch.restype = ctypes.c_int
+    lib.ecg_decompress_batch.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p, u8p]
+    lib.ecg_decompress_batch.restype = ctypes.c_int
     lib.ecg_version.argtypes = []
     lib.ecg_version.restype = ctypes.c_char_p
     if path is None:
@@ -260,6 +262,17 @@ class Engine:
         valid = np.zeros(n, np.uint8)
         self._check(self.lib.ecg_ecdsa_verify_batch(self._ctx, c, n, _ptr(z32), _ptr(sig64), _ptr(Q_xy), 1 if low_s_only else 0, _ptr(valid)))
         return valid
+
+    def decompress_batch(self, curve, sec1_33):
+        """AffinePoint::decompress over a batch of 33-byte SEC1 compressed records -> (xy, inf, valid)"""
+        c = CURVE_IDS[curve]
+        n = np.asarray(sec1_33).size // 33
+        sec1_33 = _u8(sec1_33, 33 * n, "sec1_33")
+        out_xy = np.empty(64 * n, np.uint8)
+        out_inf = np.empty(n, np.uint8)
+        valid = np.empty(n, np.uint8)
+        self._check(self.lib.ecg_decompress_batch(self._ctx, c, n, _ptr(sec1_33), _ptr(out_xy), _ptr(out_inf), _ptr(valid)))
+        return out_xy.reshape(n, 64), out_inf, valid
 
     def batch_normalize(self, curve, xyz):
         c = CURVE_IDS[curve]

@@ -125,6 +125,14 @@ ecg_status ecg_schnorr_verify_batch(ecg_ctx* ctx, size_t n, const uint8_t* pk_x,
 ecg_status ecg_ecdsa_verify_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* z32, const uint8_t* sig64,
                                   const uint8_t* Q_xy, int low_s_only, uint8_t* valid);
 
+/* SEC1 compressed point decoding (rank 2 of SURVEY 8(f)): records of 33 bytes (02|03 || x; 33 zero bytes = the
+ * identity).  valid[i] = 0 when the tag is unknown, x >= p, or x^3 + ax + b has no square root; out_xy / out_inf as
+ * in ecg_mul_batch.  Replaces AffinePoint::decompress / from_sec1_point over a batch
+ * (primeorder/src/affine.rs:179-198, :212-232; k256/src/arithmetic/affine.rs DecompressPoint; sqrt:
+ * k256/src/arithmetic/field.rs:200-235, p256/src/arithmetic/field.rs:121-147). */
+ecg_status ecg_decompress_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* sec1_33, uint8_t* out_xy,
+                                uint8_t* out_inf, uint8_t* valid);
+
 /* Projective (Jacobian X||Y||Z, n*96 bytes) -> affine, one shared inversion per thread-group
  * (Montgomery's trick).  Replaces BatchNormalize::batch_normalize (k256/src/arithmetic/projective.rs:345-391,
  * primeorder/src/projective.rs:435-478).  Coordinates must be < p. */

@@ -197,6 +197,21 @@ int sim_k256_lift_x(const uint8_t* x_be, uint8_t* y_be) {
   store_be32(y_be, y.v);
   return 1;
 }
+int sim_sec1_decompress(int curve, const uint8_t* x_be, int y_is_odd, uint8_t* y_be) {
+  uint32_t x[8];
+  load_be32(x, x_be);
+  Aff P;
+  Fe y;
+  if (curve == 0) {
+    if (!sec1_decompress<CurveK256>(P, x, (uint32_t)y_is_odd)) return 0;
+    FpK256::to_canonical(y, P.y);
+  } else {
+    if (!sec1_decompress<CurveP256>(P, x, (uint32_t)y_is_odd)) return 0;
+    FpP256::to_canonical(y, P.y);
+  }
+  store_be32(y_be, y.v);
+  return 1;
+}
 // op 0: a*b mod n, op 1: a^-1 mod n   (plain in, plain out; exercises to_mont / mul / inv / from_mont)
 int sim_fn_op(int curve, int op, const uint8_t* a_be, const uint8_t* b_be, uint8_t* out_be) {
   uint32_t a[8], b[8], am[8], bm[8], r[8];

@@ -584,3 +584,38 @@ def test_ecdsa_reference_vectors_and_random_batch(engine, curve):
     assert [bool(b) for b in engine.ecdsa_verify_batch(curve, Z, S, Qa)] == exp
     assert [bool(b) for b in engine.ecdsa_verify_batch(curve, Z, S, Qa, low_s_only=True)] == exp_low
     assert sum(exp) > sum(exp_low) > 0
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_sec1_decompress_batch(engine, curve):
+    """AffinePoint::decompress over a batch; fixtures: the compressed base points the reference's tests use
+    (p256/tests/affine.rs:17-18; k256 generator, k256/src/arithmetic/affine.rs:61-77)."""
+    c = pyref.CURVES[curve]
+    rng = random.Random(21)
+    pts = random_points(c, 50, seed=12) + [pyref.G(c)]
+    recs, exp = [], []
+    for P in pts:
+        recs.append(bytes([2 + (P[1] & 1)]) + P[0].to_bytes(32, "big"))
+        exp.append((P, 0, 1))
+        recs.append(bytes([3 - (P[1] & 1)]) + P[0].to_bytes(32, "big"))       # the other root
+        exp.append(((P[0], c.p - P[1]), 0, 1))
+    recs.append(bytes(33))
+    exp.append((None, 1, 1))                                                     # identity
+    recs.append(bytes([4]) + pts[0][0].to_bytes(32, "big"))
+    exp.append((None, 0, 0))                                                     # unknown tag
+    recs.append(bytes([2]) + c.p.to_bytes(32, "big"))
+    exp.append((None, 0, 0))                                                     # x >= p
+    x = 5
+    while pyref.lift_x(x) is not None if curve == "k256" else pow((x**3 + c.a * x + c.b) % c.p, (c.p - 1) // 2, c.p) == 1:
+        x += 1
+    recs.append(bytes([2]) + x.to_bytes(32, "big"))
+    exp.append((None, 0, 0))                                                     # not a square
+    xy, inf, valid = engine.decompress_batch(curve, np.frombuffer(b"".join(recs), np.uint8))
+    for i, (P, f, v) in enumerate(exp):
+        assert int(valid[i]) == v and int(inf[i]) == f, i
+        if v and not f:
+            assert pyref.dec_point(xy[i].tobytes(), 0) == P, i
+    if curve == "p256":
+        g = bytes.fromhex("036B17D1F2E12C4247F8BCE6E563A440F277037D812DEB33A0F4A13945D898C296")
+        xy, inf, valid = engine.decompress_batch(curve, np.frombuffer(g, np.uint8))
+        assert valid[0] == 1 and pyref.dec_point(xy[0].tobytes(), 0) == pyref.G(c)

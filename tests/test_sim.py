@@ -190,6 +190,29 @@ def test_verify_front_end_pieces(sim):
             assert int.from_bytes(out.raw, "big") == pow(a, -1, n)
 
 
+def test_sec1_decompress(sim):
+    rng = random.Random(33)
+    for ci, curve in enumerate(("k256", "p256")):
+        c = pyref.CURVES[curve]
+        p = c.p
+        hits = 0
+        for i in range(40):
+            x = c.gx if i == 0 else rng.randrange(p)
+            rhs = (pow(x, 3, p) + c.a * x + c.b) % p
+            y = pow(rhs, (p + 1) // 4, p)
+            exists = y * y % p == rhs
+            for odd in (0, 1):
+                out = ctypes.create_string_buffer(32)
+                ok = sim.sim_sec1_decompress(ci, x.to_bytes(32, "big"), odd, out)
+                assert bool(ok) == exists
+                if exists:
+                    hits += 1
+                    yy = int.from_bytes(out.raw, "big")
+                    assert yy % 2 == odd and yy in (y, p - y) and pyref.on_curve(c, (x, yy))
+        assert hits > 10
+        assert sim.sim_sec1_decompress(ci, p.to_bytes(32, "big"), 0, ctypes.create_string_buffer(32)) == 0
+
+
 def test_on_curve_check(sim):
     for curve in ("k256", "p256"):
         c = pyref.CURVES[curve]
