@@ -12,10 +12,8 @@
 #include <stdint.h>
 
 #if defined(__CUDACC__)
-#define ECG_HD __host__ __device__ __forceinline__
 #define ECG_D __device__ __forceinline__
 #else
-#define ECG_HD inline
 #define ECG_D inline
 #endif
 

@@ -4,6 +4,7 @@
 // There is no CPU fallback in this file: every compute entry launches sm_100a kernels or fails.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -715,6 +716,7 @@ __global__ void __launch_bounds__(256) mb_fmul_kernel(uint32_t* out, int iters, 
 // kernels of chunk c (PCIe is the only thing between the caller's buffers and the SMs).
 enum { B_K = 0, B_P = 1, B_INF = 2, B_JAC = 3, B_SCR = 4, B_OUT = 5, B_OINF = 6, B_AUX = 7, B_A = 8, B_JAC2 = 9, B_TAB = 10, B_MSM = 11, B_FB1 = 12, B_FB2 = 13, B_X = 14, B_V1 = 15, B_V2 = 16, B_V3 = 17, B_V4 = 18, B_V5 = 19, B_V6 = 20, B_COUNT = 21 };
 static const size_t HOST_CHUNK = (size_t)1 << 18;  // elements per pipelined chunk in host-pointer mode
+static const size_t DEV_CHUNK = (size_t)1 << 22;   // device-pointer mode: bound the temporaries (tables 512-768 B/element)
 
 struct Lane {
   cudaStream_t stream = nullptr;       // owned
@@ -1302,8 +1304,10 @@ static ecg_status run_batch(ecg_ctx* ctx, const BatchOp& op, size_t n) {
   }
   if (ctx->devptr()) {
     DevState& d = ctx->devs[0];
-    ecg_status st = run_chunk(ctx, d, d.lane[0], op, 0, n);
-    if (st != ECG_OK) return fail(ctx, st);
+    for (size_t lo = 0; lo < n; lo += DEV_CHUNK) {
+      ecg_status st = run_chunk(ctx, d, d.lane[0], op, lo, std::min(DEV_CHUNK, n - lo));
+      if (st != ECG_OK) return fail(ctx, st);
+    }
     return finish(ctx);
   }
   // host mode: interleave chunks across devices and lanes so copies and kernels of different chunks overlap
@@ -1490,7 +1494,16 @@ static ecg_status reduce_points_c(ecg_ctx* ctx, Lane& L, ecg_curve curve, uint32
 
 // ---- bucket-method lincomb (ecg_msm.cuh) ------------------------------------------------------------
 static const size_t MSM_MIN_TERMS = (size_t)1 << 13;   // below this the per-term kernel + tree sum is faster
-static const size_t MSM_MAX_TERMS = (size_t)1 << 24;   // per call (32-bit list offsets); larger shards are cut
+static const size_t MSM_MAX_TERMS_DEFAULT = (size_t)1 << 24;  // per call (32-bit list offsets); larger shards are cut
+// ECG_MSM_MAX_TERMS (environment) lowers the piece size so that tests can exercise the multi-piece path cheaply
+static size_t msm_max_terms() {
+  const char* e = getenv("ECG_MSM_MAX_TERMS");
+  if (e) {
+    size_t v = (size_t)strtoull(e, nullptr, 10);
+    if (v >= MSM_MIN_TERMS && v <= MSM_MAX_TERMS_DEFAULT) return v;
+  }
+  return MSM_MAX_TERMS_DEFAULT;
+}
 
 static MsmGeom msm_geometry(ecg_curve curve, size_t n) {
   MsmGeom g;
@@ -1614,6 +1627,7 @@ static ecg_status lincomb_shard(ecg_ctx* ctx, DevState& d, ecg_curve curve, cons
   ST_TRY(stage_in(ctx, L, B_INF, P_inf, sh.off, sh.cnt, 1, &dp.inf));
   if (sh.cnt >= MSM_MIN_TERMS) {
     // bucket method, in pieces of at most MSM_MAX_TERMS terms whose partial sums are added at the end
+    const size_t MSM_MAX_TERMS = msm_max_terms();
     size_t pieces = (sh.cnt + MSM_MAX_TERMS - 1) / MSM_MAX_TERMS;
     ST_TRY(ensure(ctx, L, B_JAC, pieces * 96 + 96));
     ST_TRY(ensure(ctx, L, B_JAC2, pieces * 96 + 96));

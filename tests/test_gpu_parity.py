@@ -275,6 +275,27 @@ def test_lincomb_bucket_method_vs_oracle(engine, curve):
     assert ei.value.index == 4321
 
 
+def test_lincomb_multi_piece_path(monkeypatch):
+    """shards larger than the per-call bucket-method limit are cut into pieces whose sums are added; the limit is
+    lowered through ECG_MSM_MAX_TERMS so that four pieces fit in a test"""
+    import ecgpu
+
+    monkeypatch.setenv("ECG_MSM_MAX_TERMS", str(1 << 14))
+    c = pyref.K256
+    rng = random.Random(5)
+    n = 3 * (1 << 14) + 5
+    base = random_points(c, 32, seed=44)
+    bxy, _ = pack_points(base)
+    xy = np.tile(bxy.reshape(32, 64), (n // 32 + 1, 1))[:n].reshape(-1).copy()
+    K = np.frombuffer(rng.randbytes(32 * n), dtype=np.uint8).copy().reshape(n, 32)
+    K[:, 0] &= 0x7F
+    eng = ecgpu.Engine([0])
+    out_xy, out_inf = eng.lincomb("k256", K, xy, None)
+    ref_xy, ref_inf = ecref.lincomb("k256", K, xy, None, nthreads=8)
+    assert np.array_equal(out_xy, ref_xy) and out_inf == ref_inf
+    eng.close()
+
+
 @pytest.mark.parametrize("curve", CURVES)
 def test_lincomb_partial_and_point_sum(engine, curve):
     """config-5 shape: per-rank partial sums (Jacobian, 96 B) combined by ecg_point_sum == one big lincomb."""
