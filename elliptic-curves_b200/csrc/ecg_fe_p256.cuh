@@ -169,13 +169,56 @@ struct FpP256T {
     for (int i = 0; i < 8; i++) r.v[i] = acc[i];
   }
 
+  // Alternative reduction (OPT bit 4): the same recombination written per output word on signed 64-bit accumulators;
+  // fewer instructions, but nvcc lowers part of it to IMAD/IMAD.MOV on the FMA pipe (measured in tools/kbench.cu).
+  ECG_D static void reduce16_cols(Fe& r, const uint32_t* c) {
+    int64_t t;
+    uint32_t o[8];
+    t = (int64_t)c[0] + c[8] + c[9] - c[11] - c[12] - c[13] - c[14];
+    o[0] = (uint32_t)t;
+    t >>= 32;
+    t += (int64_t)c[1] + c[9] + c[10] - c[12] - c[13] - c[14] - c[15];
+    o[1] = (uint32_t)t;
+    t >>= 32;
+    t += (int64_t)c[2] + c[10] + c[11] - c[13] - c[14] - c[15];
+    o[2] = (uint32_t)t;
+    t >>= 32;
+    t += (int64_t)c[3] + 2 * ((int64_t)c[11] + c[12]) + c[13] - c[15] - c[8] - c[9];
+    o[3] = (uint32_t)t;
+    t >>= 32;
+    t += (int64_t)c[4] + 2 * ((int64_t)c[12] + c[13]) + c[14] - c[9] - c[10];
+    o[4] = (uint32_t)t;
+    t >>= 32;
+    t += (int64_t)c[5] + 2 * ((int64_t)c[13] + c[14]) + c[15] - c[10] - c[11];
+    o[5] = (uint32_t)t;
+    t >>= 32;
+    t += (int64_t)c[6] + 3 * (int64_t)c[14] + 2 * (int64_t)c[15] + c[13] - c[8] - c[9];
+    o[6] = (uint32_t)t;
+    t >>= 32;
+    t += (int64_t)c[7] + 3 * (int64_t)c[15] + c[8] - c[10] - c[11] - c[12] - c[13];
+    o[7] = (uint32_t)t;
+    t >>= 32;
+    int32_t ov = (int32_t)t;   // |ov| <= 6
+    ov = fold_signed(o, ov);    // now in {-1, 0, 1}
+    ov = fold_signed(o, ov);    // now 0
+    (void)ov;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = o[i];
+  }
+  ECG_D static void reduce(Fe& r, const uint32_t* t) {
+    if (OPT & 16)
+      reduce16_cols(r, t);
+    else
+      reduce16(r, t);
+  }
+
   ECG_D static void mul_body(Fe& r, const Fe& a, const Fe& b) {
     uint32_t t[16];
     if (OPT & 8)  // OPT bit 3: one-level Karatsuba (48 products + ~60 extra adds) instead of the 64-product schoolbook
       mul8x8_kara(t, a.v, b.v);
     else
       mul8x8(t, a.v, b.v);
-    reduce16(r, t);
+    reduce(r, t);
   }
   ECG_D static void sqr_body(Fe& r, const Fe& a) {
     uint32_t t[16];
@@ -183,7 +226,7 @@ struct FpP256T {
       sqr8(t, a.v);
     else
       mul8x8(t, a.v, a.v);
-    reduce16(r, t);
+    reduce(r, t);
   }
   static ECG_NOINLINE_D Fe mul_call(Fe a, Fe b) {
     Fe r;

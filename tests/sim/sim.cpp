@@ -172,6 +172,11 @@ int sim_fe_mul_kara(int curve, const uint8_t* a, const uint8_t* b, uint8_t* out)
   } else {
     FpP256T<9>::mul(r, x, y);
     FpP256T<9>::normalize(r, r);
+    Fe r2;
+    FpP256T<17>::mul(r2, x, y);  // column-sum reduction variant must agree
+    FpP256T<17>::normalize(r2, r2);
+    for (int i = 0; i < 8; i++)
+      if (r2.v[i] != r.v[i]) return 1;
   }
   store_be32(out, r.v);
   return 0;

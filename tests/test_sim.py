@@ -98,7 +98,7 @@ def test_karatsuba_multiplier_variant(sim):
         for i in range(4000):
             a, b = (structured(), structured()) if i % 2 else (rng.getrandbits(256), rng.getrandbits(256))
             out = ctypes.create_string_buffer(32)
-            sim.sim_fe_mul_kara(ci, a.to_bytes(32, "big"), b.to_bytes(32, "big"), out)
+            assert sim.sim_fe_mul_kara(ci, a.to_bytes(32, "big"), b.to_bytes(32, "big"), out) == 0
             assert int.from_bytes(out.raw, "big") == a * b % p
 
 

@@ -272,7 +272,10 @@ int main(int argc, char** argv) {
   runp<FpP256T<3>, 128, 2, false>("p256 call   (128,2) smem", n, jac, gtab);
   runp<FpP256T<3>, 128, 3, true>("p256 call   (128,3) gtab", n, jac, gtab);
   runp<FpP256T<3>, 128, 4, true>("p256 call   (128,4) gtab", n, jac, gtab);
-  runp<FpP256T<11>, 128, 4, true>("p256 kara call (128,4) gtab", n, jac, gtab);
+  run_fmul<FpP256T<19>>("p256 fmul call cols");
+  runp<FpP256T<19>, 128, 4, true>("p256 cols call (128,4) gtab", n, jac, gtab);
+  runp<FpP256T<19>, 128, 3, true>("p256 cols call (128,3) gtab", n, jac, gtab);
+  runp<FpP256T<23>, 128, 4, true>("p256 cols mulcall sqr-inl (128,4)", n, jac, gtab);
   runp<FpP256T<7>, 128, 4, true>("p256 mul call, sqr inl (128,4) gtab", n, jac, gtab);
   runp<FpP256T<7>, 128, 3, true>("p256 mul call, sqr inl (128,3) gtab", n, jac, gtab);
   return 0;
