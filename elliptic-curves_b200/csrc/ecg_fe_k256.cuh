@@ -120,6 +120,14 @@ struct FpK256T {
     else
       mul_body(r, a, b);
   }
+  // multiplication as used inside the doubling formula: OPT bit 5 keeps those three inlined (fewer calls on the
+  // hottest path) while the mixed addition still calls
+  ECG_D static void mul_d(Fe& r, const Fe& a, const Fe& b) {
+    if ((OPT & 2) && !(OPT & 32))
+      r = mul_call(a, b);
+    else
+      mul_body(r, a, b);
+  }
   ECG_D static void sqr(Fe& r, const Fe& a) {
     if ((OPT & 2) && !(OPT & 4))  // OPT bit 2: keep the (smaller) squaring inlined even when mul is a call
       r = sqr_call(a);

@@ -51,20 +51,20 @@ ECG_D void jac_dbl(Jac& r, const Jac& p) {
     F::sqr(zz, p.Z);
     F::sub(u, p.X, zz);
     F::add(v, p.X, zz);
-    F::mul(L, u, v);  // X^2 - Z^4
+    F::mul_d(L, u, v);  // X^2 - Z^4
   } else {
     F::sqr(L, p.X);
   }
   F::mul_small(L, L, 3);
   F::half(L, L);
-  F::mul(T, p.X, A);   // X*Y^2
-  F::mul(r.Z, p.Y, p.Z);
+  F::mul_d(T, p.X, A);   // X*Y^2
+  F::mul_d(r.Z, p.Y, p.Z);
   F::sqr(D, A);        // Y^4
   F::sqr(r.X, L);
   F::add(t, T, T);
   F::sub(r.X, r.X, t);
   F::sub(t, T, r.X);
-  F::mul(r.Y, L, t);
+  F::mul_d(r.Y, L, t);
   F::sub(r.Y, r.Y, D);
 }
 

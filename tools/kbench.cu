@@ -252,7 +252,9 @@ int main(int argc, char** argv) {
   run<FpK256T<3>, 192, 2, false>("v3 call,   sqr8      (192,2) smem", n, jac, gtab);
   run<FpK256T<3>, 96, 4, false>("v3 call,   sqr8      (96,4)  smem", n, jac, gtab);
   run<FpK256T<3>, 64, 7, false>("v3 call,   sqr8      (64,7)  smem", n, jac, gtab);
-  run<FpK256T<15>, 128, 4, true>("v15 kara call, sqr inl (128,4) gtab", n, jac, gtab);
+  run<FpK256T<39>, 128, 4, true>("v39 dbl inline, madd calls (128,4)", n, jac, gtab);
+  run<FpK256T<39>, 128, 3, true>("v39 dbl inline, madd calls (128,3)", n, jac, gtab);
+  run<FpK256T<39>, 128, 5, true>("v39 dbl inline, madd calls (128,5)", n, jac, gtab);
   run<FpK256T<11>, 128, 4, true>("v11 kara call, sqr call(128,4) gtab", n, jac, gtab);
   run<FpK256T<11>, 128, 5, true>("v11 kara call, sqr call(128,5) gtab", n, jac, gtab);
   run<FpK256T<7>, 128, 5, true>("v7 mul call, sqr inl (128,5) gtab", n, jac, gtab);
@@ -260,7 +262,9 @@ int main(int argc, char** argv) {
   run<FpK256T<1>, 128, 5, true>("v1 inline, sqr8      (128,5) gtab", n, jac, gtab);
   run<FpK256T<3>, 128, 5, true>("v3 call,   sqr8      (128,5) gtab", n, jac, gtab);
   run<FpK256T<3>, 256, 2, true>("v3 call,   sqr8      (256,2) gtab", n, jac, gtab);
-  run<FpK256T<15>, 128, 4, true>("v15 kara call, sqr inl (128,4) gtab", n, jac, gtab);
+  run<FpK256T<39>, 128, 4, true>("v39 dbl inline, madd calls (128,4)", n, jac, gtab);
+  run<FpK256T<39>, 128, 3, true>("v39 dbl inline, madd calls (128,3)", n, jac, gtab);
+  run<FpK256T<39>, 128, 5, true>("v39 dbl inline, madd calls (128,5)", n, jac, gtab);
   run<FpK256T<11>, 128, 4, true>("v11 kara call, sqr call(128,4) gtab", n, jac, gtab);
   run<FpK256T<11>, 128, 5, true>("v11 kara call, sqr call(128,5) gtab", n, jac, gtab);
   run<FpK256T<7>, 128, 5, true>("v7 mul call, sqr inl (128,5) gtab", n, jac, gtab);
