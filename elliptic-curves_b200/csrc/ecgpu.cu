@@ -12,700 +12,9 @@
 #include <vector>
 
 #include "../../include/ecgpu.h"
-#include "ecg_curves.cuh"
-#include "ecg_io.cuh"
-#include "ecg_mul.cuh"
+#include "ecg_kernels.cuh"
+#include "ecg_microbench.cuh"
 #include "ecg_msm.cuh"
-#include "ecg_verify.cuh"
-
-using namespace ecg;
-
-// ------------------------------------------------------------------------------------------------
-// error flags written by kernels into status[0]; status[1] = smallest offending index
-#define ERRF_SCALAR 1u
-#define ERRF_POINT 2u
-
-__device__ __forceinline__ void report_error(uint32_t* status, uint32_t flag, size_t idx) {
-  atomicOr(&status[0], flag);
-  atomicMin(&status[1], (uint32_t)(idx > 0xFFFFFFFEull ? 0xFFFFFFFEull : idx));
-}
-
-// SoA word-major intermediate layout: word w of element idx at buf[w*n + idx] (coalesced per word)
-template <int NW>
-__device__ __forceinline__ void soa_store(uint32_t* buf, size_t n, size_t idx, const uint32_t* v, int w0) {
-#pragma unroll
-  for (int w = 0; w < NW; w++) buf[(size_t)(w0 + w) * n + idx] = v[w];
-}
-template <int NW>
-__device__ __forceinline__ void soa_load(uint32_t* v, const uint32_t* buf, size_t n, size_t idx, int w0) {
-#pragma unroll
-  for (int w = 0; w < NW; w++) v[w] = buf[(size_t)(w0 + w) * n + idx];
-}
-
-// Load + validate one (scalar, point) pair.  Returns error flags (0 = fine).  On error / identity the
-// caller still runs the arithmetic on a harmless substitute (k = 1, P = G) and forces Z = 0 afterwards so
-// that warps stay converged.
-template <class C>
-__device__ __forceinline__ uint32_t load_pair(uint32_t* k, Aff& P, bool& inf, const uint8_t* kb,
-                                              const uint8_t* pxy, const uint8_t* pinf, size_t idx) {
-  typedef typename C::F F;
-  uint32_t err = 0;
-  load_be32(k, kb + 32 * idx);
-  if (!lt8(k, C::N())) err |= ERRF_SCALAR;
-  inf = pinf != nullptr && pinf[idx] != 0;
-  Fe x, y;
-  load_be32(x.v, pxy + 64 * idx);
-  load_be32(y.v, pxy + 64 * idx + 32);
-  if (!inf) {
-    bool ok = lt8(x.v, C::P()) && lt8(y.v, C::P());
-    F::from_canonical(P.x, x);
-    F::from_canonical(P.y, y);
-    if (ok) {
-      Fe b;
-      C::b_internal(b);
-      ok = aff_on_curve<F, C::A_IS_MINUS3>(P, b);
-    }
-    if (!ok) err |= ERRF_POINT;
-  }
-  if (inf || err) {
-    C::generator(P);
-#pragma unroll
-    for (int i = 0; i < 8; i++) k[i] = (i == 0);
-  }
-  return err;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Per-thread window tables live in global memory, one slot per block: word w of entry e of thread t at
-// gtab[blockIdx*BLOCK*EW + (e*WPE + w)*BLOCK + t]  (EW = words per thread: 128 affine / 192 Jacobian).
-// A warp's access to one (e, w) of differing e per lane touches 32 distinct 4-byte words spread over at most 8
-// rows; the blocks resident at any time keep ~50 MB of tables live, which stays in the 126 MB L2.  Shared memory
-// was the first home of these tables (512-768 B/thread capped occupancy at 8-12 warps/SM); moving them out lets
-// registers set the occupancy (16-20 warps/SM) and measured +7 % (k256) / +16 % (P-256), tools/kbench.cu.
-#define K_TAB_WORDS 128  /* 8 affine entries  x 16 words */
-#define P_TAB_WORDS 192  /* 8 Jacobian entries x 24 words */
-
-// secp256k1 variable-base: one pair per thread.
-template <int BLOCK, int MINBLK>
-__global__ void __launch_bounds__(BLOCK, MINBLK)
-    k256_varbase_kernel(const uint8_t* __restrict__ kb, const uint8_t* __restrict__ pxy,
-                        const uint8_t* __restrict__ pinf, size_t n, uint32_t* __restrict__ jac,
-                        uint32_t* __restrict__ gtab, uint32_t* __restrict__ status, size_t base) {
-  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-  if (idx >= n) return;
-  uint32_t k[8];
-  Aff P;
-  bool inf;
-  uint32_t err = load_pair<CurveK256>(k, P, inf, kb, pxy, pinf, idx);
-  if (err) report_error(status, err, base + idx);
-  TabRef tab{gtab + (size_t)blockIdx.x * BLOCK * K_TAB_WORDS + threadIdx.x, (uint32_t)BLOCK};
-  Jac r;
-  k256_mul_thread(r, k, P, tab);
-  if (inf || err) FpK256::set_zero(r.Z);
-  soa_store<8>(jac, n, idx, r.X.v, 0);
-  soa_store<8>(jac, n, idx, r.Y.v, 8);
-  soa_store<8>(jac, n, idx, r.Z.v, 16);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Generic prime-order curve (P-256) variable-base: Jacobian window table (768 B / thread).
-template <class C, int BLOCK, int MINBLK>
-__global__ void __launch_bounds__(BLOCK, MINBLK)
-    generic_varbase_kernel(const uint8_t* __restrict__ kb, const uint8_t* __restrict__ pxy,
-                           const uint8_t* __restrict__ pinf, size_t n, uint32_t* __restrict__ jac,
-                           uint32_t* __restrict__ gtab, uint32_t* __restrict__ status, size_t base) {
-  typedef typename C::F F;
-  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-  if (idx >= n) return;
-  uint32_t k[8];
-  Aff P;
-  bool inf;
-  uint32_t err = load_pair<C>(k, P, inf, kb, pxy, pinf, idx);
-  if (err) report_error(status, err, base + idx);
-  TabRefJ tab{gtab + (size_t)blockIdx.x * BLOCK * P_TAB_WORDS + threadIdx.x, (uint32_t)BLOCK};
-  Jac r;
-  generic_mul_thread<F, C::A_IS_MINUS3>(r, k, P, tab);
-  if (inf || err) F::set_zero(r.Z);
-  soa_store<8>(jac, n, idx, r.X.v, 0);
-  soa_store<8>(jac, n, idx, r.Y.v, 8);
-  soa_store<8>(jac, n, idx, r.Z.v, 16);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Fixed-base k*G from a device-resident table of affine odd multiples.
-//   table layout: window i (0..FB_WINDOWS-1), entry j (0..2^(FB_W-1)-1) = (2j+1) * 2^(FB_W*i) * G, 16 words
-//   (x[8], y[8], internal form); one extra entry at the end = 2^256 * G (the recoding's implicit top digit).
-// Replaces BasepointTable (primeorder/src/tables/basepoint.rs:41-125; k256/src/arithmetic/tables.rs:12-22):
-// same idea (precomputed multiples of G, only additions at run time), sized for a 126 MB L2 instead of a
-// 30 KiB L1: 16 sixteen-bit windows -> 17 mixed additions and no doubling per scalar.
-#define FB_W 16
-#define FB_WINDOWS 16
-#define FB_ENTRIES (1u << (FB_W - 1))
-#define FB_TABLE_POINTS ((size_t)FB_WINDOWS * FB_ENTRIES + 1)
-
-__device__ __forceinline__ void fb_load_entry(Aff& e, const uint32_t* __restrict__ table, size_t point) {
-  const uint4* p = reinterpret_cast<const uint4*>(table + point * 16);
-  uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
-  e.x.v[0] = a.x; e.x.v[1] = a.y; e.x.v[2] = a.z; e.x.v[3] = a.w;
-  e.x.v[4] = b.x; e.x.v[5] = b.y; e.x.v[6] = b.z; e.x.v[7] = b.w;
-  e.y.v[0] = c.x; e.y.v[1] = c.y; e.y.v[2] = c.z; e.y.v[3] = c.w;
-  e.y.v[4] = d.x; e.y.v[5] = d.y; e.y.v[6] = d.z; e.y.v[7] = d.w;
-}
-
-// acc += k*G (acc Jacobian on the true curve; pass Z = 0 to start from the identity)
-template <class C, bool FROM_IDENTITY>
-__device__ __forceinline__ void fixedbase_accumulate(Jac& acc, const uint32_t* k, const uint32_t* __restrict__ table) {
-  typedef typename C::F F;
-  FullRecode rc;
-  recode_full(rc, k);
-  Aff e;
-  fb_load_entry(e, table, (size_t)FB_WINDOWS * FB_ENTRIES);  // 2^256 * G
-  if (FROM_IDENTITY) {
-    acc.X = e.x;
-    acc.Y = e.y;
-    F::set_one(acc.Z);
-  } else {
-    jac_madd<F, C::A_IS_MINUS3>(acc, acc, e);
-  }
-#pragma unroll 1
-  for (int i = 0; i < FB_WINDOWS; i++) {
-    uint32_t w = rc.h[0] & 0xFFFFu;
-#pragma unroll
-    for (int j = 0; j < 7; j++) rc.h[j] = funnel_r(rc.h[j], rc.h[j + 1], 16);
-    rc.h[7] >>= 16;
-    uint32_t pos = w >> (FB_W - 1);
-    uint32_t idx = pos ? (w & (FB_ENTRIES - 1)) : (FB_ENTRIES - 1 - w);
-    fb_load_entry(e, table, (size_t)i * FB_ENTRIES + idx);
-    fe_cneg<F>(e.y, pos ^ 1u);
-    jac_madd<F, C::A_IS_MINUS3>(acc, acc, e);
-  }
-  // parity correction: subtract G if k was even
-  fb_load_entry(e, table, 0);
-  F::neg(e.y, e.y);
-  Jac t;
-  jac_madd<F, C::A_IS_MINUS3>(t, acc, e);
-  jac_csel(acc, t, rc.even);
-}
-
-template <class C>
-__global__ void __launch_bounds__(128, 4)
-    fixedbase_kernel(const uint8_t* __restrict__ kb, size_t n, const uint32_t* __restrict__ table,
-                     uint32_t* __restrict__ jac, uint32_t* __restrict__ status, size_t base) {
-  typedef typename C::F F;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  uint32_t k[8];
-  load_be32(k, kb + 32 * idx);
-  bool bad = !lt8(k, C::N());
-  if (bad) {
-    report_error(status, ERRF_SCALAR, base + idx);
-#pragma unroll
-    for (int i = 0; i < 8; i++) k[i] = (i == 0);
-  }
-  Jac acc;
-  fixedbase_accumulate<C, true>(acc, k, table);
-  if (bad) F::set_zero(acc.Z);
-  soa_store<8>(jac, n, idx, acc.X.v, 0);
-  soa_store<8>(jac, n, idx, acc.Y.v, 8);
-  soa_store<8>(jac, n, idx, acc.Z.v, 16);
-}
-
-// a*G + b*P : variable-base thread routine, then the fixed-base accumulation on the same accumulator.
-// Replaces mul_by_generator_and_mul_add_vartime (k256/src/arithmetic/mul.rs:303-310, primeorder/src/mul_backend.rs:31-40).
-template <class C, int BLOCK, int MINBLK, bool IS_K256>
-__global__ void __launch_bounds__(BLOCK, MINBLK)
-    mul_gen_add_kernel(const uint8_t* __restrict__ ab, const uint8_t* __restrict__ kb,
-                       const uint8_t* __restrict__ pxy, const uint8_t* __restrict__ pinf, size_t n,
-                       const uint32_t* __restrict__ table, uint32_t* __restrict__ jac, uint32_t* __restrict__ gtab,
-                       uint32_t* __restrict__ status, size_t base) {
-  typedef typename C::F F;
-  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-  if (idx >= n) return;
-  uint32_t k[8], a[8];
-  Aff P;
-  bool inf;
-  uint32_t err = load_pair<C>(k, P, inf, kb, pxy, pinf, idx);
-  load_be32(a, ab + 32 * idx);
-  if (!lt8(a, C::N())) err |= ERRF_SCALAR;
-  if (err) report_error(status, err, base + idx);
-  Jac r;
-  if (IS_K256) {
-    TabRef tab{gtab + (size_t)blockIdx.x * BLOCK * K_TAB_WORDS + threadIdx.x, (uint32_t)BLOCK};
-    k256_mul_thread(r, k, P, tab);
-  } else {
-    TabRefJ tab{gtab + (size_t)blockIdx.x * BLOCK * P_TAB_WORDS + threadIdx.x, (uint32_t)BLOCK};
-    generic_mul_thread<F, C::A_IS_MINUS3>(r, k, P, tab);
-  }
-  if (inf) F::set_zero(r.Z);  // b * O = O, the sum is a*G
-  if (err) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) a[i] = (i == 0);
-  }
-  fixedbase_accumulate<C, false>(r, a, table);
-  if (err) F::set_zero(r.Z);
-  soa_store<8>(jac, n, idx, r.X.v, 0);
-  soa_store<8>(jac, n, idx, r.Y.v, 8);
-  soa_store<8>(jac, n, idx, r.Z.v, 16);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Signature verification front ends (ecg_verify.cuh).  Both reduce to a*G + b*P through mul_gen_add_kernel; the
-// kernels here prepare (a, b, P) and judge the result.  Invalid encodings never raise an API error: they are
-// marked not-ok, replaced by harmless operands (a = b = 1, P = G) so warps stay converged, and reported as
-// valid[i] = 0 — the reference returns Err(Error) per signature, not a batch failure.
-__device__ __forceinline__ void store_scalar_be(uint8_t* dst, const uint32_t* limbs) { store_be32(dst, limbs); }
-
-// BIP340: pk (x only), 32-byte message, signature r || s.
-__global__ void __launch_bounds__(128)
-    schnorr_prep_kernel(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, const uint8_t* __restrict__ sig, size_t n,
-                        uint8_t* __restrict__ pxy, uint8_t* __restrict__ a_out, uint8_t* __restrict__ b_out, uint8_t* __restrict__ ok_out) {
-  typedef FpK256 F;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  uint32_t x[8], r[8], sv[8], e[8];
-  load_be32(x, pk + 32 * idx);
-  load_be32(r, sig + 64 * idx);
-  load_be32(sv, sig + 64 * idx + 32);
-  Aff P;
-  bool ok = k256_lift_x<F>(P, x);                    // VerifyingKey::from_bytes (schnorr/verifying.rs:36-52)
-  ok = ok && lt8(r, K256_P);                           // Signature::try_from: r is a field element,
-  ok = ok && lt8(sv, K256_N) && !FnMont<CurveK256>::is_zero(sv);  //   s a non-zero scalar (schnorr.rs:150-170)
-  bip340_challenge(e, sig + 64 * idx, pk + 32 * idx, msg + 32 * idx);
-  if (!lt8(e, K256_N)) {  // Reduce<FieldBytes>: one conditional subtraction (2^256 < 2n)
-    uint32_t t[8];
-    sub8(t, e, K256_N);
-#pragma unroll
-    for (int i = 0; i < 8; i++) e[i] = t[i];
-  }
-  // b = -e mod n
-  uint32_t ne[8];
-  if (FnMont<CurveK256>::is_zero(e)) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) ne[i] = 0;
-  } else {
-    sub8(ne, K256_N, e);
-  }
-  if (!ok) {
-    CurveK256::generator(P);
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      sv[i] = (i == 0);
-      ne[i] = (i == 0);
-    }
-  }
-  Fe cx, cy;
-  F::to_canonical(cx, P.x);
-  F::to_canonical(cy, P.y);
-  store_be32(pxy + 64 * idx, cx.v);
-  store_be32(pxy + 64 * idx + 32, cy.v);
-  store_scalar_be(a_out + 32 * idx, sv);
-  store_scalar_be(b_out + 32 * idx, ne);
-  ok_out[idx] = ok ? 1 : 0;
-}
-__global__ void __launch_bounds__(256)
-    schnorr_check_kernel(const uint8_t* __restrict__ sig, const uint8_t* __restrict__ rxy, const uint8_t* __restrict__ rinf,
-                         const uint8_t* __restrict__ ok, size_t n, uint8_t* __restrict__ valid) {
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  const uint32_t* r = reinterpret_cast<const uint32_t*>(sig + 64 * idx);
-  const uint32_t* x = reinterpret_cast<const uint32_t*>(rxy + 64 * idx);
-  bool same = true;
-#pragma unroll
-  for (int i = 0; i < 8; i++) same = same && (r[i] == x[i]);
-  bool y_even = (rxy[64 * idx + 63] & 1u) == 0;
-  valid[idx] = (ok[idx] && !rinf[idx] && y_even && same) ? 1 : 0;  // verifying.rs:94
-}
-
-// ECDSA: z (32-byte hash), signature r || s, public key Q (x || y).  One modular inversion per thread slice
-// (Montgomery's trick over s_i, as in normalize_kernel); scr: 8*n words.
-template <class C>
-__global__ void __launch_bounds__(128)
-    ecdsa_prep_kernel(const uint8_t* __restrict__ zb, const uint8_t* __restrict__ sig, const uint8_t* __restrict__ qxy, size_t n,
-                      int low_s_only, uint32_t* __restrict__ scr, uint8_t* __restrict__ pxy, uint8_t* __restrict__ a_out,
-                      uint8_t* __restrict__ b_out, uint8_t* __restrict__ ok_out) {
-  typedef typename C::F F;
-  typedef FnMont<C> N;
-  size_t T = (size_t)gridDim.x * blockDim.x;
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  uint32_t acc[8], sm[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) acc[i] = C::N_ONE()[i];
-  size_t last = t;
-  // forward: validate, prefix products of the (Montgomery-form) s_i
-  for (size_t idx = t; idx < n; idx += T) {
-    uint32_t r[8], sv[8];
-    load_be32(r, sig + 64 * idx);
-    load_be32(sv, sig + 64 * idx + 32);
-    bool ok = lt8(r, C::N()) && !N::is_zero(r) && lt8(sv, C::N()) && !N::is_zero(sv);
-    if (ok && low_s_only) {  // EcdsaCurve::NORMALIZE_S (k256/src/ecdsa.rs:104-106): reject s > n/2
-      uint32_t twice[8];
-      uint32_t c = add8(twice, sv, sv);
-      ok = !c && lt8(twice, C::N());
-    }
-    Aff Q;
-    Fe qx, qy;
-    load_be32(qx.v, qxy + 64 * idx);
-    load_be32(qy.v, qxy + 64 * idx + 32);
-    bool qok = lt8(qx.v, C::P()) && lt8(qy.v, C::P());
-    F::from_canonical(Q.x, qx);
-    F::from_canonical(Q.y, qy);
-    if (qok) {
-      Fe b;
-      C::b_internal(b);
-      qok = aff_on_curve<F, C::A_IS_MINUS3>(Q, b);
-    }
-    ok = ok && qok;
-    ok_out[idx] = ok ? 1 : 0;
-    if (!ok) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) sv[i] = (i == 0);
-    }
-    N::to_mont(sm, sv);
-    soa_store<8>(scr, n, idx, acc, 0);
-    N::mul(acc, acc, sm);
-    last = idx;
-  }
-  uint32_t inv[8];
-  N::inv(inv, acc);
-  for (size_t idx = last;; idx -= T) {
-    uint32_t r[8], sv[8], z[8], pre[8], w[8], u1[8], u2[8];
-    bool ok = ok_out[idx] != 0;
-    load_be32(r, sig + 64 * idx);
-    load_be32(sv, sig + 64 * idx + 32);
-    load_be32(z, zb + 32 * idx);
-    if (!ok) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) sv[i] = (i == 0);
-    }
-    N::to_mont(sm, sv);
-    soa_load<8>(pre, scr, n, idx, 0);
-    N::mul(w, inv, pre);   // w = s^-1 (Montgomery form)
-    N::mul(inv, inv, sm);
-    N::cond_sub_n(z, N::ge_n(z));  // bits2field + reduce for 256-bit curves
-    // u1 = z*w, u2 = r*w: mont_mul(plain, mont) = plain product
-    N::mul(u1, z, w);
-    N::mul(u2, r, w);
-    if (!ok) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        u1[i] = (i == 0);
-        u2[i] = (i == 0);
-      }
-      Aff G;
-      C::generator(G);
-      Fe gx, gy;
-      F::to_canonical(gx, G.x);
-      F::to_canonical(gy, G.y);
-      store_be32(pxy + 64 * idx, gx.v);
-      store_be32(pxy + 64 * idx + 32, gy.v);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; i++) reinterpret_cast<uint32_t*>(pxy + 64 * idx)[i] = reinterpret_cast<const uint32_t*>(qxy + 64 * idx)[i];
-    }
-    store_scalar_be(a_out + 32 * idx, u1);
-    store_scalar_be(b_out + 32 * idx, u2);
-    if (idx < T) break;
-  }
-}
-template <class C>
-__global__ void __launch_bounds__(256)
-    ecdsa_check_kernel(const uint8_t* __restrict__ sig, const uint8_t* __restrict__ rxy, const uint8_t* __restrict__ rinf,
-                       const uint8_t* __restrict__ ok, size_t n, uint8_t* __restrict__ valid) {
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  uint32_t r[8], x[8];
-  load_be32(r, sig + 64 * idx);
-  load_be32(x, rxy + 64 * idx);
-  FnMont<C>::cond_sub_n(x, FnMont<C>::ge_n(x));  // x(R) mod n  (p < 2n)
-  bool same = true;
-#pragma unroll
-  for (int i = 0; i < 8; i++) same = same && (r[i] == x[i]);
-  valid[idx] = (ok[idx] && !rinf[idx] && same) ? 1 : 0;
-}
-
-// SEC1 compressed points (33 bytes: 02/03 || x; 33 zero bytes = identity) -> affine x || y, identity flag, validity.
-template <class C>
-__global__ void __launch_bounds__(128)
-    decompress_kernel(const uint8_t* __restrict__ sec1, size_t n, uint8_t* __restrict__ out_xy, uint8_t* __restrict__ out_inf,
-                      uint8_t* __restrict__ valid) {
-  typedef typename C::F F;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  const uint8_t* rec = sec1 + 33 * idx;
-  uint8_t tag = rec[0];
-  uint32_t x[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) {  // unaligned big-endian words
-    const uint8_t* b = rec + 1 + 4 * (7 - i);
-    x[i] = ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
-  }
-  bool zero = (x[0] | x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7]) == 0;
-  Aff P;
-  bool ok = false, inf = false;
-  if (tag == 0 && zero) {
-    ok = inf = true;
-  } else if (tag == 2 || tag == 3) {
-    ok = sec1_decompress<C>(P, x, tag & 1u);
-  }
-  Fe cx, cy;
-  if (ok && !inf) {
-    F::to_canonical(cx, P.x);
-    F::to_canonical(cy, P.y);
-  } else {
-    F::set_zero(cx);
-    F::set_zero(cy);
-  }
-  store_be32(out_xy + 64 * idx, cx.v);
-  store_be32(out_xy + 64 * idx + 32, cy.v);
-  out_inf[idx] = inf ? 1 : 0;
-  valid[idx] = ok ? 1 : 0;
-}
-
-// canonical affine big-endian bytes (n*64) -> table words (internal form); used once, when a table is built
-template <class C>
-__global__ void __launch_bounds__(256)
-    affine_to_table_kernel(const uint8_t* __restrict__ xy, size_t n, uint32_t* __restrict__ table) {
-  typedef typename C::F F;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  Fe x, y;
-  load_be32(x.v, xy + 64 * idx);
-  load_be32(y.v, xy + 64 * idx + 32);
-  F::from_canonical(x, x);
-  F::from_canonical(y, y);
-#pragma unroll
-  for (int w = 0; w < 8; w++) {
-    table[idx * 16 + w] = x.v[w];
-    table[idx * 16 + 8 + w] = y.v[w];
-  }
-}
-
-// Sum of Jacobian points: thread t adds elements t, t+T, t+2T, ... of `in` (SoA, n_in) and writes partial t of
-// `out` (SoA, n_out = T).  Applied repeatedly until one point is left (lincomb's final reduction).
-template <class C>
-__global__ void __launch_bounds__(128)
-    jac_sum_kernel(const uint32_t* __restrict__ in, size_t n_in, uint32_t* __restrict__ out, size_t n_out) {
-  typedef typename C::F F;
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_out) return;
-  Jac acc;
-  F::set_zero(acc.X);
-  F::set_one(acc.Y);
-  F::set_zero(acc.Z);
-  for (size_t idx = t; idx < n_in; idx += n_out) {
-    Jac p;
-    soa_load<8>(p.X.v, in, n_in, idx, 0);
-    soa_load<8>(p.Y.v, in, n_in, idx, 8);
-    soa_load<8>(p.Z.v, in, n_in, idx, 16);
-    jac_add<F, C::A_IS_MINUS3>(acc, acc, p);
-  }
-  soa_store<8>(out, n_out, t, acc.X.v, 0);
-  soa_store<8>(out, n_out, t, acc.Y.v, 8);
-  soa_store<8>(out, n_out, t, acc.Z.v, 16);
-}
-
-// SoA internal Jacobian -> AoS canonical big-endian X||Y||Z (96 bytes per point)
-template <class C>
-__global__ void __launch_bounds__(128)
-    export_jac_kernel(const uint32_t* __restrict__ jac, size_t n, uint8_t* __restrict__ xyz) {
-  typedef typename C::F F;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-#pragma unroll 1
-  for (int c = 0; c < 3; c++) {
-    Fe v;
-    soa_load<8>(v.v, jac, n, idx, 8 * c);
-    F::to_canonical(v, v);
-    store_be32(xyz + 96 * idx + 32 * c, v.v);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Jacobian (SoA) -> canonical affine bytes with Montgomery's trick along each thread's strided slice:
-// thread t owns elements t, t+T, t+2T, ... ; one field inversion per thread, 7 field multiplications per
-// element.  Replaces batch_normalize / BatchInvert (k256/src/arithmetic/projective.rs:367-391,
-// k256/src/arithmetic/field.rs:244-291).  scr: 8*n words of scratch (prefix products).
-template <class F>
-__global__ void __launch_bounds__(256)
-    normalize_kernel(const uint32_t* __restrict__ jac, size_t n, uint32_t* __restrict__ scr,
-                     uint8_t* __restrict__ out_xy, uint8_t* __restrict__ out_inf) {
-  size_t T = (size_t)gridDim.x * blockDim.x;
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  Fe acc, one;
-  F::set_one(one);
-  acc = one;
-  size_t last = t;
-  for (size_t idx = t; idx < n; idx += T) {
-    Fe z;
-    soa_load<8>(z.v, jac, n, idx, 16);
-    if (F::is_zero(z)) z = one;
-    soa_store<8>(scr, n, idx, acc.v, 0);
-    F::mul(acc, acc, z);
-    last = idx;
-  }
-  Fe inv;
-  F::inv(inv, acc);
-  for (size_t idx = last;; idx -= T) {
-    Jac p;
-    soa_load<8>(p.Z.v, jac, n, idx, 16);
-    bool inf = F::is_zero(p.Z);
-    if (inf) p.Z = one;
-    Fe pre, zinv;
-    soa_load<8>(pre.v, scr, n, idx, 0);
-    F::mul(zinv, inv, pre);
-    F::mul(inv, inv, p.Z);
-    soa_load<8>(p.X.v, jac, n, idx, 0);
-    soa_load<8>(p.Y.v, jac, n, idx, 8);
-    Fe x, y;
-    jac_to_affine_canonical<F>(x, y, p, zinv);
-    if (inf) {
-      F::set_zero(x);
-      F::set_zero(y);
-    }
-    store_be32(out_xy + 64 * idx, x.v);
-    store_be32(out_xy + 64 * idx + 32, y.v);
-    out_inf[idx] = inf ? 1 : 0;
-    if (idx < T) break;
-  }
-}
-
-// AoS big-endian X||Y||Z (n*96 bytes, canonical) -> SoA internal form; validates coordinates < p.
-template <class C>
-__global__ void __launch_bounds__(256)
-    import_jac_kernel(const uint8_t* __restrict__ xyz, size_t n, uint32_t* __restrict__ jac,
-                      uint32_t* __restrict__ status, size_t base) {
-  typedef typename C::F F;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-#pragma unroll 1
-  for (int c = 0; c < 3; c++) {
-    Fe v, w;
-    load_be32(v.v, xyz + 96 * idx + 32 * c);
-    if (!lt8(v.v, C::P())) report_error(status, ERRF_POINT, base + idx);
-    F::from_canonical(w, v);
-    soa_store<8>(jac, n, idx, w.v, 8 * c);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-template <class C>
-__global__ void __launch_bounds__(256)
-    field_op_kernel(int op, size_t n, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
-                    uint8_t* __restrict__ out, uint32_t* __restrict__ status, size_t base) {
-  typedef typename C::F F;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  Fe x, y, r;
-  load_be32(x.v, a + 32 * idx);
-  if (!lt8(x.v, C::P())) report_error(status, ERRF_POINT, base + idx);
-  F::from_canonical(x, x);
-  bool binary = (op == ECG_FOP_ADD || op == ECG_FOP_SUB || op == ECG_FOP_MUL);
-  if (binary) {
-    load_be32(y.v, b + 32 * idx);
-    if (!lt8(y.v, C::P())) report_error(status, ERRF_POINT, base + idx);
-    F::from_canonical(y, y);
-  } else {
-    y = x;
-  }
-  switch (op) {
-    case ECG_FOP_ADD: F::add(r, x, y); break;
-    case ECG_FOP_SUB: F::sub(r, x, y); break;
-    case ECG_FOP_NEG: F::neg(r, x); break;
-    case ECG_FOP_MUL: F::mul(r, x, y); break;
-    case ECG_FOP_SQR: F::sqr(r, x); break;
-    default: F::inv(r, x); break;
-  }
-  F::to_canonical(r, r);
-  store_be32(out + 32 * idx, r.v);
-}
-
-// ------------------------------------------------------------------------------------------------
-// integer-pipe microbenchmarks (roofline denominators)
-__global__ void __launch_bounds__(256) mb_imad_wide_kernel(uint32_t* out, int iters, uint32_t seed) {
-  uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3 + 1, b0 = seed ^ 0x9E3779B9u, b1 = b0 + blockIdx.x;
-  uint32_t r[16];
-#pragma unroll
-  for (int i = 0; i < 16; i++) r[i] = a0 + i;
-#pragma unroll 1
-  for (int it = 0; it < iters; it++) {
-    // 4 independent chains of 4 IMAD.WIDE.U32.X each = 16 per iteration, x4 unrolled = 64
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      mad_wide_cc(r[0], r[1], a0, b0);
-      madc_wide_cc(r[2], r[3], a1, b0);
-      madc_wide_cc(r[4], r[5], a0, b1);
-      madc_wide_cc(r[6], r[7], a1, b1);
-      mad_wide_cc(r[8], r[9], a1, b0);
-      madc_wide_cc(r[10], r[11], a0, b1);
-      madc_wide_cc(r[12], r[13], a1, b1);
-      madc_wide_cc(r[14], r[15], a0, b0);
-    }
-  }
-  uint32_t s = 0;
-#pragma unroll
-  for (int i = 0; i < 16; i++) s ^= r[i];
-  if (s == 0x12345678u) out[0] = s;
-}
-__global__ void __launch_bounds__(256) mb_imad_kernel(uint32_t* out, int iters, uint32_t seed) {
-  uint32_t a = seed + threadIdx.x, b = seed ^ 0x9E3779B9u;
-  uint32_t r[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) r[i] = a + i;
-#pragma unroll 1
-  for (int it = 0; it < iters; it++) {
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) r[i] = r[i] * a + b;
-    }
-  }
-  uint32_t s = 0;
-#pragma unroll
-  for (int i = 0; i < 8; i++) s ^= r[i];
-  if (s == 0x12345678u) out[0] = s;
-}
-__global__ void __launch_bounds__(256) mb_iadd_kernel(uint32_t* out, int iters, uint32_t seed) {
-  uint32_t a = seed + threadIdx.x;
-  uint32_t r[16];
-#pragma unroll
-  for (int i = 0; i < 16; i++) r[i] = a + i;
-#pragma unroll 1
-  for (int it = 0; it < iters; it++) {
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      r[0] = add_cc(r[0], r[8]);
-#pragma unroll
-      for (int i = 1; i < 8; i++) r[i] = addc_cc(r[i], r[8 + i]);
-      r[8] = add_cc(r[8], r[1]);
-#pragma unroll
-      for (int i = 1; i < 8; i++) r[8 + i] = addc_cc(r[8 + i], r[(i + 1) & 7]);
-    }
-  }
-  uint32_t s = 0;
-#pragma unroll
-  for (int i = 0; i < 16; i++) s ^= r[i];
-  if (s == 0x12345678u) out[0] = s;
-}
-template <class F>
-__global__ void __launch_bounds__(256) mb_fmul_kernel(uint32_t* out, int iters, uint32_t seed) {
-  Fe a, b;
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    a.v[i] = seed * (i + 1) + threadIdx.x;
-    b.v[i] = (seed ^ 0x9E3779B9u) * (i + 3) + blockIdx.x;
-  }
-#pragma unroll 1
-  for (int it = 0; it < iters; it++) {
-    F::mul(a, a, b);
-    F::mul(b, b, a);
-  }
-  uint32_t s = 0;
-#pragma unroll
-  for (int i = 0; i < 8; i++) s ^= a.v[i] ^ b.v[i];
-  if (s == 0x12345678u) out[0] = s;
-}
 
 // ------------------------------------------------------------------------------------------------
 // host side
