@@ -111,7 +111,15 @@ ECG_D void build_table_iso_a0(const TabRef& tab, Fe& Zg, const Aff& P) {
 // secp256k1: r = k*P (Jacobian, true curve).  k: 8 LE limbs, k < n.  P: affine, on curve, not identity.
 // GLV split -> two 128-bit halves -> 32 shared windows of (4 dbl + 2 madd); the lambda-half reuses the
 // same table through (x,y) -> (beta x, y) (ProjectivePoint::endomorphism, projective.rs:241-247).
-template <class F = FpK256>
+// PHASE_SYNC (experiment, tools/kbench.cu): a block-wide barrier between the doubling phase and the addition phase
+// keeps all warps of a block in the same stretch of code, so a fully inlined body only needs one phase's
+// instructions resident in the instruction cache at a time.
+#if defined(__CUDA_ARCH__)
+#define ECG_BLOCK_SYNC() __syncthreads()
+#else
+#define ECG_BLOCK_SYNC() ((void)0)
+#endif
+template <class F = FpK256, bool PHASE_SYNC = false>
 ECG_D void k256_mul_thread(Jac& r, const uint32_t* k, const Aff& P, const TabRef& tab) {
   GlvHalf g1, g2;
   glv_split_k256(g1, g2, k);
@@ -132,8 +140,10 @@ ECG_D void k256_mul_thread(Jac& r, const uint32_t* k, const Aff& P, const TabRef
 
 #pragma unroll 1
   for (int i = 0; i < 32; i++) {
+    if (PHASE_SYNC) ECG_BLOCK_SYNC();
 #pragma unroll 1
     for (int j = 0; j < 4; j++) jac_dbl<F, false>(acc, acc);
+    if (PHASE_SYNC) ECG_BLOCK_SYNC();
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
       uint32_t n = half ? next_window(g2.h) : next_window(g1.h);

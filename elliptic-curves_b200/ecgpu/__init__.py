@@ -197,6 +197,12 @@ class Engine:
         self._check(self.lib.ecg_mul_gen_batch(self._ctx, c, n, _ptr(k), _ptr(out_xy), _ptr(out_inf)))
         return out_xy.reshape(n, 64), out_inf
 
+    def diffie_hellman(self, curve, secret_k, public_xy):
+        """ECDH batch: x-coordinate of k[i] * P[i] (k256/src/ecdh.rs:46-60 `diffie_hellman`: `(public * secret).to_affine().x`).
+        Returns (shared_x n x 32, inf)."""
+        out_xy, out_inf = self.mul_batch(curve, secret_k, public_xy, None)
+        return np.ascontiguousarray(out_xy[:, :32]), out_inf
+
     def lincomb(self, curve, k, P_xy, P_inf=None):
         c = CURVE_IDS[curve]
         n = np.asarray(k).size // 32

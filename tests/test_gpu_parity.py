@@ -640,3 +640,25 @@ def test_sec1_decompress_batch(engine, curve):
         g = bytes.fromhex("036B17D1F2E12C4247F8BCE6E563A440F277037D812DEB33A0F4A13945D898C296")
         xy, inf, valid = engine.decompress_batch(curve, np.frombuffer(g, np.uint8))
         assert valid[0] == 1 and pyref.dec_point(xy[0].tobytes(), 0) == pyref.G(c)
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_ecdh_batch_agrees_both_ways(engine, curve):
+    """rank 3 of SURVEY 8(f): k256/src/ecdh.rs:46-60 — a*(b*G) and b*(a*G) give the same x; checked against OpenSSL."""
+    c = pyref.CURVES[curve]
+    rng = random.Random(66)
+    n = 64
+    a = [rng.randrange(1, c.n) for _ in range(n)]
+    b = [rng.randrange(1, c.n) for _ in range(n)]
+    A, _ = engine.mul_by_generator(curve, pack_scalars(a))
+    B, _ = engine.mul_by_generator(curve, pack_scalars(b))
+    s1, i1 = engine.diffie_hellman(curve, pack_scalars(a), B)
+    s2, i2 = engine.diffie_hellman(curve, pack_scalars(b), A)
+    assert np.array_equal(s1, s2) and not i1.any() and not i2.any()
+    ec = pytest.importorskip("cryptography.hazmat.primitives.asymmetric.ec")
+    oc = ec.SECP256K1() if curve == "k256" else ec.SECP256R1()
+    for i in range(0, n, 9):
+        priv = ec.derive_private_key(a[i], oc)
+        Bx, By = (int.from_bytes(np.asarray(B)[i, :32].tobytes(), "big"), int.from_bytes(np.asarray(B)[i, 32:].tobytes(), "big"))
+        peer = ec.EllipticCurvePublicNumbers(Bx, By, oc).public_key()
+        assert priv.exchange(ec.ECDH(), peer) == s1[i].tobytes()

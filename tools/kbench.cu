@@ -11,6 +11,7 @@
 #include "../elliptic-curves_b200/csrc/ecg_mul.cuh"
 using namespace ecg;
 
+static uint64_t checksum(const std::vector<uint32_t>& v);
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
 __device__ __forceinline__ void make_inputs(uint32_t* k, Aff& P, size_t idx) {
@@ -44,6 +45,51 @@ __global__ void __launch_bounds__(BLOCK, MINBLK) kb_varbase(size_t n, uint32_t* 
     jac[(size_t)(8 + w) * n + idx] = r.Y.v[w];
     jac[(size_t)(16 + w) * n + idx] = r.Z.v[w];
   }
+}
+
+// phase-synchronised variant: every thread of the block stays alive (clamped index) so the barriers are legal
+template <class F, int BLOCK, int MINBLK>
+__global__ void __launch_bounds__(BLOCK, MINBLK) kb_varbase_sync(size_t n, uint32_t* __restrict__ jac, uint32_t* __restrict__ gtab) {
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  size_t cidx = idx < n ? idx : n - 1;
+  uint32_t k[8];
+  Aff P;
+  make_inputs(k, P, cidx);
+  Jac r;
+  size_t slot = ((size_t)blockIdx.x % (148 * 8)) * BLOCK;
+  TabRef tab{gtab + slot * 128 + threadIdx.x, (uint32_t)BLOCK};
+  k256_mul_thread<F, true>(r, k, P, tab);
+  if (idx >= n) return;
+  for (int w = 0; w < 8; w++) {
+    jac[(size_t)w * n + idx] = r.X.v[w];
+    jac[(size_t)(8 + w) * n + idx] = r.Y.v[w];
+    jac[(size_t)(16 + w) * n + idx] = r.Z.v[w];
+  }
+}
+template <class F, int BLOCK, int MINBLK>
+static void run_sync(const char* name, size_t n, uint32_t* jac, uint32_t* gtab) {
+  auto kern = kb_varbase_sync<F, BLOCK, MINBLK>;
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, kern));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, 0));
+  unsigned grid = (unsigned)((n + BLOCK - 1) / BLOCK);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(e0));
+    kern<<<grid, BLOCK>>>(n, jac, gtab);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  std::vector<uint32_t> h(24 * 4096);
+  for (int w = 0; w < 24; w++) CK(cudaMemcpy(&h[w * 4096], jac + (size_t)w * n, 4096 * 4, cudaMemcpyDeviceToHost));
+  printf("%-34s regs %3d  blocks/SM %d  warps/SM %2d  %8.3f ms  %.4g mults/s  chk %016llx\n", name, fa.numRegs, occ, occ * BLOCK / 32, best,
+         n / (best * 1e-3), (unsigned long long)checksum(h));
 }
 
 template <class F, int BLOCK, int MINBLK, bool GLOBAL_TAB>
@@ -222,7 +268,7 @@ int main(int argc, char** argv) {
   size_t n = (size_t)1 << (argc > 1 ? atoi(argv[1]) : 20);
   uint32_t *jac, *gtab;
   CK(cudaMalloc(&jac, n * 96));
-  CK(cudaMalloc(&gtab, (size_t)148 * 8 * 256 * 192 * 4));
+  CK(cudaMalloc(&gtab, (size_t)148 * 8 * 640 * 192 * 4));
   printf("n = %zu\n", n);
   {
     double* dout; CK(cudaMalloc(&dout, 256));
@@ -252,6 +298,10 @@ int main(int argc, char** argv) {
   run<FpK256T<3>, 192, 2, false>("v3 call,   sqr8      (192,2) smem", n, jac, gtab);
   run<FpK256T<3>, 96, 4, false>("v3 call,   sqr8      (96,4)  smem", n, jac, gtab);
   run<FpK256T<3>, 64, 7, false>("v3 call,   sqr8      (64,7)  smem", n, jac, gtab);
+  run_sync<FpK256T<1>, 512, 1>("sync inline sqr8 (512,1)", n, jac, gtab);
+  run_sync<FpK256T<1>, 256, 2>("sync inline sqr8 (256,2)", n, jac, gtab);
+  run_sync<FpK256T<1>, 640, 1>("sync inline sqr8 (640,1)", n, jac, gtab);
+  run_sync<FpK256T<7>, 512, 1>("sync v7 (512,1)", n, jac, gtab);
   run<FpK256T<39>, 128, 4, true>("v39 dbl inline, madd calls (128,4)", n, jac, gtab);
   run<FpK256T<39>, 128, 3, true>("v39 dbl inline, madd calls (128,3)", n, jac, gtab);
   run<FpK256T<39>, 128, 5, true>("v39 dbl inline, madd calls (128,5)", n, jac, gtab);
@@ -262,6 +312,10 @@ int main(int argc, char** argv) {
   run<FpK256T<1>, 128, 5, true>("v1 inline, sqr8      (128,5) gtab", n, jac, gtab);
   run<FpK256T<3>, 128, 5, true>("v3 call,   sqr8      (128,5) gtab", n, jac, gtab);
   run<FpK256T<3>, 256, 2, true>("v3 call,   sqr8      (256,2) gtab", n, jac, gtab);
+  run_sync<FpK256T<1>, 512, 1>("sync inline sqr8 (512,1)", n, jac, gtab);
+  run_sync<FpK256T<1>, 256, 2>("sync inline sqr8 (256,2)", n, jac, gtab);
+  run_sync<FpK256T<1>, 640, 1>("sync inline sqr8 (640,1)", n, jac, gtab);
+  run_sync<FpK256T<7>, 512, 1>("sync v7 (512,1)", n, jac, gtab);
   run<FpK256T<39>, 128, 4, true>("v39 dbl inline, madd calls (128,4)", n, jac, gtab);
   run<FpK256T<39>, 128, 3, true>("v39 dbl inline, madd calls (128,3)", n, jac, gtab);
   run<FpK256T<39>, 128, 5, true>("v39 dbl inline, madd calls (128,5)", n, jac, gtab);
