@@ -224,6 +224,11 @@ static ecg_status stage_in(ecg_ctx* ctx, Lane& L, int slot, const uint8_t* src, 
     return ECG_OK;
   }
   if (ctx->devptr()) {
+    // the kernels read 32/64/96-byte records with 32-bit loads (ecg_io.cuh load_be32)
+    if ((stride % 4 == 0) && (reinterpret_cast<uintptr_t>(src) & 3)) {
+      ctx->err = "device pointer not 4-byte aligned";
+      return ECG_EINVAL;
+    }
     *dst = src + off * stride;
     return ECG_OK;
   }
@@ -235,6 +240,10 @@ static ecg_status stage_in(ecg_ctx* ctx, Lane& L, int slot, const uint8_t* src, 
 static ecg_status stage_out(ecg_ctx* ctx, Lane& L, size_t off, size_t cnt, uint8_t* out, size_t ostride, uint8_t* oinf,
                             DevPtrs& dp) {
   if (ctx->devptr()) {
+    if ((ostride % 4 == 0) && (reinterpret_cast<uintptr_t>(out) & 3)) {
+      ctx->err = "device pointer not 4-byte aligned";
+      return ECG_EINVAL;
+    }
     dp.out = out + off * ostride;
     dp.oinf = oinf ? oinf + off : nullptr;
     if (!dp.oinf) {

@@ -52,7 +52,8 @@ typedef enum {
 } ecg_field_op;
 
 /* ctx flags */
-#define ECG_FLAG_DEVICE_PTRS 1u /* every data pointer is a device pointer on device_ids[0] (n_devices must be 1) */
+#define ECG_FLAG_DEVICE_PTRS 1u /* every data pointer is a device pointer on device_ids[0] (n_devices must be 1);
+                                   32/64/96-byte record arrays must be 4-byte aligned (ECG_EINVAL otherwise) */
 
 /* Create a context on the given CUDA devices (NULL/0 = device 0).  With several devices a host-pointer
  * batch is split into contiguous index ranges, one per device; there is no

@@ -468,6 +468,11 @@ def test_device_pointer_mode():
     eng.mul_batch_ptr("k256", n, kd.data_ptr(), pd.data_ptr(), 0, oxy.data_ptr(), oinf.data_ptr())
     ref_xy, ref_inf = ecref.mul_batch("k256", K, xy, None, nthreads=8)
     assert np.array_equal(oxy.cpu().numpy(), ref_xy.reshape(-1)) and np.array_equal(oinf.cpu().numpy(), ref_inf)
+    # a record array that is not 4-byte aligned is refused (the kernels use 32-bit loads), not read
+    kd1 = torch.empty(n * 32 + 4, dtype=torch.uint8, device=dev)
+    with pytest.raises(ecgpu.EcgError) as ei:
+        eng.mul_batch_ptr("k256", n - 1, kd1.data_ptr() + 1, pd.data_ptr(), 0, oxy.data_ptr(), oinf.data_ptr())
+    assert ei.value.code == 1 and "aligned" in str(ei.value)
     eng.close()
 
 
