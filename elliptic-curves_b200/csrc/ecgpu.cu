@@ -608,6 +608,30 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
   return copy_back(ctx, L, off, cnt, op.out, op.ostride, op.oinf, dp);
 }
 
+// Chunks of one device's range in host-pointer mode.  Two things cost time when a batch is cut into chunks: the first
+// chunk's upload and the last chunk's download are not hidden behind a kernel of the other lane, and every chunk whose
+// size is not a whole number of waves (all threads of the scalar-multiplication kernels run equally long, so a wave
+// ends sharply) wastes part of its last wave.  So chunks are whole waves: 1, 2, then 3 waves, ending with one wave plus
+// whatever is left.  `wave` = SMs x resident blocks x block size of the variable-base kernels.
+static std::vector<Shard> chunk_schedule(size_t cnt, size_t wave) {
+  std::vector<Shard> v;
+  const size_t maxc = std::max(wave, HOST_CHUNK / wave * wave);
+  size_t off = 0, next = wave;
+  while (off < cnt) {
+    size_t left = cnt - off;
+    size_t c = std::min(next, left);
+    size_t rest = left - c;
+    if (rest > 0 && rest < wave)
+      c = left >= 2 * wave ? (left - wave) / wave * wave : left;  // no tiny tail
+    else if (rest == 0 && left > 2 * wave)
+      c = (left - wave) / wave * wave;  // split the final chunk so that the exposed download is small
+    v.push_back({off, c});
+    off += c;
+    next = std::min(next + wave, maxc);
+  }
+  return v;
+}
+
 static ecg_status run_batch(ecg_ctx* ctx, const BatchOp& op, size_t n) {
   std::vector<Shard> shards = make_shards(n, ctx->devs.size());
   bool need_table = op.kind == BatchOp::MULGEN || op.kind == BatchOp::MULGENADD || op.kind == BatchOp::SCHNORR || op.kind == BatchOp::ECDSA;
@@ -629,17 +653,18 @@ static ecg_status run_batch(ecg_ctx* ctx, const BatchOp& op, size_t n) {
     return finish(ctx);
   }
   // host mode: interleave chunks across devices and lanes so copies and kernels of different chunks overlap
+  std::vector<std::vector<Shard>> sched(shards.size());
   size_t maxchunks = 0;
-  for (const Shard& sh : shards) maxchunks = std::max(maxchunks, (sh.cnt + HOST_CHUNK - 1) / HOST_CHUNK);
+  for (size_t i = 0; i < shards.size(); i++) {
+    sched[i] = chunk_schedule(shards[i].cnt, (size_t)ctx->devs[i].sm_count * K_MINBLK * K_BLOCK);
+    maxchunks = std::max(maxchunks, sched[i].size());
+  }
   for (size_t c = 0; c < maxchunks; c++) {
     for (size_t i = 0; i < ctx->devs.size(); i++) {
-      const Shard& sh = shards[i];
-      size_t lo = c * HOST_CHUNK;
-      if (lo >= sh.cnt) continue;
-      size_t cnt = std::min(HOST_CHUNK, sh.cnt - lo);
+      if (c >= sched[i].size()) continue;
       DevState& d = ctx->devs[i];
       CU_TRY(ctx, cudaSetDevice(d.dev));
-      ecg_status st = run_chunk(ctx, d, d.lane[c & 1], op, sh.off + lo, cnt);
+      ecg_status st = run_chunk(ctx, d, d.lane[c & 1], op, shards[i].off + sched[i][c].off, sched[i][c].cnt);
       if (st != ECG_OK) return fail(ctx, st);
     }
   }
