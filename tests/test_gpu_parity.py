@@ -425,6 +425,26 @@ def test_multi_device_ctx_shards_the_batch():
     with pytest.raises(ecgpu.ScalarRangeError) as ei:
         multi.mul_batch("k256", bad, xy, inf)
     assert ei.value.index == n - 3
+    # several pipelined chunks per device (host mode cuts each shard into whole-wave chunks): same bytes as one device
+    big = 200_003 * nd
+    seed = np.frombuffer(np.random.default_rng(5).bytes(32 * big), np.uint8).reshape(big, 32).copy()
+    seed[:, 0] &= 0x7F                      # < n
+    single = ecgpu.Engine([0])
+    pts, pinf = single.mul_by_generator("k256", seed)
+    kk = np.roll(seed, 1, axis=0).copy()
+    m_xy, m_inf = multi.mul_batch("k256", kk, pts, pinf)
+    s_xy, s_inf = single.mul_batch("k256", kk, pts, pinf)
+    assert np.array_equal(m_xy, s_xy) and np.array_equal(m_inf, s_inf)
+    spot = list(range(0, big, big // 7)) + [big - 1]
+    o_xy, o_inf = ecref.mul_batch("k256", kk[spot], np.asarray(pts)[spot], np.asarray(pinf)[spot], nthreads=8)
+    assert np.array_equal(np.asarray(m_xy)[spot].reshape(-1), o_xy.reshape(-1))
+    bad = kk.copy()
+    where = big - 70_000                    # inside the last device's last chunk
+    bad[where] = 0xFF
+    with pytest.raises(ecgpu.ScalarRangeError) as ei:
+        multi.mul_batch("k256", bad, pts, pinf)
+    assert ei.value.index == where
+    single.close()
     multi.close()
 
 
