@@ -27,6 +27,9 @@ namespace ecg {
 template <int OPT>
 struct FpK256T {
   static constexpr uint32_t C0 = 977u;  // C = 2^32 + 977
+  // OPT bits 6/7: the doubling / mixed addition trade one multiplication for a squaring + 4 linear ops
+  static constexpr bool SQR_TRADE_DBL = (OPT & 64) != 0;
+  static constexpr bool SQR_TRADE_MADD = (OPT & 128) != 0;
 
   ECG_D static void set_zero(Fe& r) {
 #pragma unroll

@@ -26,6 +26,9 @@ namespace ecg {
 
 template <int OPT>
 struct FpP256T {
+  // the P-256 squaring is bound by its reduction's adds, not by products: no multiplication-for-squaring trades
+  static constexpr bool SQR_TRADE_DBL = false;
+  static constexpr bool SQR_TRADE_MADD = false;
   ECG_D static void set_zero(Fe& r) {
 #pragma unroll
     for (int i = 0; i < 8; i++) r.v[i] = 0;

@@ -40,7 +40,7 @@ ECG_D void jac_csel(Jac& r, const Jac& t, uint32_t c) {
   }
 }
 
-// Doubling in "halved" form (Z3 = Y*Z, X3 = X3_std/4, Y3 = Y3_std/8): 3M+4S (a=0) / 4M+4S (a=-3),
+// Doubling in "halved" form (Z3 = Y*Z, X3 = X3_std/4, Y3 = Y3_std/8): 3M+4S (a=0; 2M+5S with F::SQR_TRADE_DBL) / 4M+4S (a=-3),
 // 8 cheap linear ops.   L = (3X^2 + a Z^4)/2;  X3 = L^2 - 2XY^2;  Y3 = L(XY^2 - X3) - Y^4.
 template <class F, bool A_IS_MINUS3>
 ECG_D void jac_dbl(Jac& r, const Jac& p) {
@@ -55,11 +55,20 @@ ECG_D void jac_dbl(Jac& r, const Jac& p) {
   } else {
     F::sqr(L, p.X);
   }
+  F::sqr(D, A);  // Y^4
+  if (!A_IS_MINUS3 && F::SQR_TRADE_DBL) {
+    // X*Y^2 = ((X + Y^2)^2 - X^2 - Y^4)/2: a squaring (36 products) plus four linear ops instead of a multiplication (64)
+    F::add(t, p.X, A);
+    F::sqr(T, t);
+    F::sub(T, T, L);
+    F::sub(T, T, D);
+    F::half(T, T);
+  } else {
+    F::mul_d(T, p.X, A);  // X*Y^2
+  }
   F::mul_small(L, L, 3);
   F::half(L, L);
-  F::mul_d(T, p.X, A);   // X*Y^2
   F::mul_d(r.Z, p.Y, p.Z);
-  F::sqr(D, A);        // Y^4
   F::sqr(r.X, L);
   F::add(t, T, T);
   F::sub(r.X, r.X, t);
@@ -100,7 +109,7 @@ inline
   }
 }
 
-// r = p + q, q affine and not the identity.  8M+3S.  If zr != nullptr it receives Z3/Z1 (= H).
+// r = p + q, q affine and not the identity.  8M+3S (7M+4S with F::SQR_TRADE_MADD).  If zr != nullptr it receives Z3/Z1 (= H).
 template <class F, bool A_IS_MINUS3>
 ECG_D void jac_madd(Jac& r, const Jac& p, const Aff& q, Fe* zr = nullptr) {
   Fe zz, u2, s2, H, R, hh, hhh, V, t;
@@ -120,7 +129,15 @@ ECG_D void jac_madd(Jac& r, const Jac& p, const Aff& q, Fe* zr = nullptr) {
   F::sqr(hh, H);
   F::mul(hhh, H, hh);
   F::mul(V, p.X, hh);
-  F::mul(r.Z, p.Z, H);
+  if (F::SQR_TRADE_MADD) {  // Z1*H = ((Z1 + H)^2 - Z1^2 - H^2)/2
+    F::add(t, p.Z, H);
+    F::sqr(t, t);
+    F::sub(t, t, zz);
+    F::sub(t, t, hh);
+    F::half(r.Z, t);
+  } else {
+    F::mul(r.Z, p.Z, H);
+  }
   if (zr) *zr = H;
   F::sqr(t, R);
   F::sub(t, t, hhh);

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <vector>
+#include <cstring>
 #define ECG_K256_OPT 7
 #include "../elliptic-curves_b200/csrc/ecg_curves.cuh"
 #include "../elliptic-curves_b200/csrc/ecg_io.cuh"
@@ -270,6 +271,17 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&jac, n * 96));
   CK(cudaMalloc(&gtab, (size_t)148 * 8 * 640 * 192 * 4));
   printf("n = %zu\n", n);
+  if (argc > 2 && !strcmp(argv[2], "trade")) {  // multiplication-for-squaring trades in the point formulas (OPT bits 6/7)
+    for (int round = 0; round < 2; round++) {
+      run<FpK256T<7>, 128, 4, true>("v7   base                (128,4)", n, jac, gtab);
+      run<FpK256T<71>, 128, 4, true>("v71  dbl 2M+5S           (128,4)", n, jac, gtab);
+      run<FpK256T<135>, 128, 4, true>("v135 madd 7M+4S          (128,4)", n, jac, gtab);
+      run<FpK256T<199>, 128, 4, true>("v199 both                (128,4)", n, jac, gtab);
+    }
+    run<FpK256T<199>, 128, 5, true>("v199 both                (128,5)", n, jac, gtab);
+    run<FpK256T<199>, 128, 3, true>("v199 both                (128,3)", n, jac, gtab);
+    return 0;
+  }
   {
     double* dout; CK(cudaMalloc(&dout, 256));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
