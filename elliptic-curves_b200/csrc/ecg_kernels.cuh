@@ -1,7 +1,19 @@
 // ecg_kernels.cuh — every __global__ kernel of libecgpu.so except the microbenchmarks (ecg_microbench.cuh) and the
 // bucket-method kernels (ecg_msm.cuh).  Host orchestration (contexts, lanes, staging, launches) is in ecgpu.cu.
 #pragma once
+#if defined(__CUDACC__)
 #include <cuda_runtime.h>
+#define ECG_KERNEL(...) __global__ void __launch_bounds__(__VA_ARGS__)
+#define ECG_DEV __device__ __forceinline__
+#else
+// Host build: only tests/sim/sim.cpp, which executes a kernel body once per simulated thread (it supplies threadIdx,
+// blockIdx, blockDim, gridDim, atomicOr/atomicMin, uint4 and __ldg).  Never part of libecgpu.so.
+#ifndef ECG_HOST_SIM
+#error "ecg_kernels.cuh is CUDA code; a host build exists only for the test simulation (tests/sim/sim.cpp)"
+#endif
+#define ECG_KERNEL(...) static void
+#define ECG_DEV inline
+#endif
 
 #include "../../include/ecgpu.h"
 #include "ecg_curves.cuh"
@@ -16,19 +28,19 @@ using namespace ecg;
 #define ERRF_SCALAR 1u
 #define ERRF_POINT 2u
 
-__device__ __forceinline__ void report_error(uint32_t* status, uint32_t flag, size_t idx) {
+ECG_DEV void report_error(uint32_t* status, uint32_t flag, size_t idx) {
   atomicOr(&status[0], flag);
   atomicMin(&status[1], (uint32_t)(idx > 0xFFFFFFFEull ? 0xFFFFFFFEull : idx));
 }
 
 // SoA word-major intermediate layout: word w of element idx at buf[w*n + idx] (coalesced per word)
 template <int NW>
-__device__ __forceinline__ void soa_store(uint32_t* buf, size_t n, size_t idx, const uint32_t* v, int w0) {
+ECG_DEV void soa_store(uint32_t* buf, size_t n, size_t idx, const uint32_t* v, int w0) {
 #pragma unroll
   for (int w = 0; w < NW; w++) buf[(size_t)(w0 + w) * n + idx] = v[w];
 }
 template <int NW>
-__device__ __forceinline__ void soa_load(uint32_t* v, const uint32_t* buf, size_t n, size_t idx, int w0) {
+ECG_DEV void soa_load(uint32_t* v, const uint32_t* buf, size_t n, size_t idx, int w0) {
 #pragma unroll
   for (int w = 0; w < NW; w++) v[w] = buf[(size_t)(w0 + w) * n + idx];
 }
@@ -37,7 +49,7 @@ __device__ __forceinline__ void soa_load(uint32_t* v, const uint32_t* buf, size_
 // caller still runs the arithmetic on a harmless substitute (k = 1, P = G) and forces Z = 0 afterwards so
 // that warps stay converged.
 template <class C>
-__device__ __forceinline__ uint32_t load_pair(uint32_t* k, Aff& P, bool& inf, const uint8_t* kb,
+ECG_DEV uint32_t load_pair(uint32_t* k, Aff& P, bool& inf, const uint8_t* kb,
                                               const uint8_t* pxy, const uint8_t* pinf, size_t idx) {
   typedef typename C::F F;
   uint32_t err = 0;
@@ -78,7 +90,7 @@ __device__ __forceinline__ uint32_t load_pair(uint32_t* k, Aff& P, bool& inf, co
 
 // secp256k1 variable-base: one pair per thread.
 template <int BLOCK, int MINBLK>
-__global__ void __launch_bounds__(BLOCK, MINBLK)
+ECG_KERNEL(BLOCK, MINBLK)
     k256_varbase_kernel(const uint8_t* __restrict__ kb, const uint8_t* __restrict__ pxy,
                         const uint8_t* __restrict__ pinf, size_t n, uint32_t* __restrict__ jac,
                         uint32_t* __restrict__ gtab, uint32_t* __restrict__ status, size_t base) {
@@ -101,7 +113,7 @@ __global__ void __launch_bounds__(BLOCK, MINBLK)
 // ------------------------------------------------------------------------------------------------
 // Generic prime-order curve (P-256) variable-base: Jacobian window table (768 B / thread).
 template <class C, int BLOCK, int MINBLK>
-__global__ void __launch_bounds__(BLOCK, MINBLK)
+ECG_KERNEL(BLOCK, MINBLK)
     generic_varbase_kernel(const uint8_t* __restrict__ kb, const uint8_t* __restrict__ pxy,
                            const uint8_t* __restrict__ pinf, size_t n, uint32_t* __restrict__ jac,
                            uint32_t* __restrict__ gtab, uint32_t* __restrict__ status, size_t base) {
@@ -134,7 +146,7 @@ __global__ void __launch_bounds__(BLOCK, MINBLK)
 #define FB_ENTRIES (1u << (FB_W - 1))
 #define FB_TABLE_POINTS ((size_t)FB_WINDOWS * FB_ENTRIES + 1)
 
-__device__ __forceinline__ void fb_load_entry(Aff& e, const uint32_t* __restrict__ table, size_t point) {
+ECG_DEV void fb_load_entry(Aff& e, const uint32_t* __restrict__ table, size_t point) {
   const uint4* p = reinterpret_cast<const uint4*>(table + point * 16);
   uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
   e.x.v[0] = a.x; e.x.v[1] = a.y; e.x.v[2] = a.z; e.x.v[3] = a.w;
@@ -145,7 +157,7 @@ __device__ __forceinline__ void fb_load_entry(Aff& e, const uint32_t* __restrict
 
 // acc += k*G (acc Jacobian on the true curve; pass Z = 0 to start from the identity)
 template <class C, bool FROM_IDENTITY>
-__device__ __forceinline__ void fixedbase_accumulate(Jac& acc, const uint32_t* k, const uint32_t* __restrict__ table) {
+ECG_DEV void fixedbase_accumulate(Jac& acc, const uint32_t* k, const uint32_t* __restrict__ table) {
   typedef typename C::F F;
   FullRecode rc;
   recode_full(rc, k);
@@ -179,7 +191,7 @@ __device__ __forceinline__ void fixedbase_accumulate(Jac& acc, const uint32_t* k
 }
 
 template <class C>
-__global__ void __launch_bounds__(128, 4)
+ECG_KERNEL(128, 4)
     fixedbase_kernel(const uint8_t* __restrict__ kb, size_t n, const uint32_t* __restrict__ table,
                      uint32_t* __restrict__ jac, uint32_t* __restrict__ status, size_t base) {
   typedef typename C::F F;
@@ -204,7 +216,7 @@ __global__ void __launch_bounds__(128, 4)
 // a*G + b*P : variable-base thread routine, then the fixed-base accumulation on the same accumulator.
 // Replaces mul_by_generator_and_mul_add_vartime (k256/src/arithmetic/mul.rs:303-310, primeorder/src/mul_backend.rs:31-40).
 template <class C, int BLOCK, int MINBLK, bool IS_K256>
-__global__ void __launch_bounds__(BLOCK, MINBLK)
+ECG_KERNEL(BLOCK, MINBLK)
     mul_gen_add_kernel(const uint8_t* __restrict__ ab, const uint8_t* __restrict__ kb,
                        const uint8_t* __restrict__ pxy, const uint8_t* __restrict__ pinf, size_t n,
                        const uint32_t* __restrict__ table, uint32_t* __restrict__ jac, uint32_t* __restrict__ gtab,
@@ -244,10 +256,10 @@ __global__ void __launch_bounds__(BLOCK, MINBLK)
 // kernels here prepare (a, b, P) and judge the result.  Invalid encodings never raise an API error: they are
 // marked not-ok, replaced by harmless operands (a = b = 1, P = G) so warps stay converged, and reported as
 // valid[i] = 0 — the reference returns Err(Error) per signature, not a batch failure.
-__device__ __forceinline__ void store_scalar_be(uint8_t* dst, const uint32_t* limbs) { store_be32(dst, limbs); }
+ECG_DEV void store_scalar_be(uint8_t* dst, const uint32_t* limbs) { store_be32(dst, limbs); }
 
 // BIP340: pk (x only), 32-byte message, signature r || s.
-__global__ void __launch_bounds__(128)
+ECG_KERNEL(128)
     schnorr_prep_kernel(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, const uint8_t* __restrict__ sig, size_t n,
                         uint8_t* __restrict__ pxy, uint8_t* __restrict__ a_out, uint8_t* __restrict__ b_out, uint8_t* __restrict__ ok_out) {
   typedef FpK256 F;
@@ -293,7 +305,7 @@ __global__ void __launch_bounds__(128)
   store_scalar_be(b_out + 32 * idx, ne);
   ok_out[idx] = ok ? 1 : 0;
 }
-__global__ void __launch_bounds__(256)
+ECG_KERNEL(256)
     schnorr_check_kernel(const uint8_t* __restrict__ sig, const uint8_t* __restrict__ rxy, const uint8_t* __restrict__ rinf,
                          const uint8_t* __restrict__ ok, size_t n, uint8_t* __restrict__ valid) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -310,7 +322,7 @@ __global__ void __launch_bounds__(256)
 // ECDSA: z (32-byte hash), signature r || s, public key Q (x || y).  One modular inversion per thread slice
 // (Montgomery's trick over s_i, as in normalize_kernel); scr: 8*n words.
 template <class C>
-__global__ void __launch_bounds__(128)
+ECG_KERNEL(128)
     ecdsa_prep_kernel(const uint8_t* __restrict__ zb, const uint8_t* __restrict__ sig, const uint8_t* __restrict__ qxy, size_t n,
                       int low_s_only, uint32_t* __restrict__ scr, uint8_t* __restrict__ pxy, uint8_t* __restrict__ a_out,
                       uint8_t* __restrict__ b_out, uint8_t* __restrict__ ok_out) {
@@ -400,7 +412,7 @@ __global__ void __launch_bounds__(128)
   }
 }
 template <class C>
-__global__ void __launch_bounds__(256)
+ECG_KERNEL(256)
     ecdsa_check_kernel(const uint8_t* __restrict__ sig, const uint8_t* __restrict__ rxy, const uint8_t* __restrict__ rinf,
                        const uint8_t* __restrict__ ok, size_t n, uint8_t* __restrict__ valid) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -417,7 +429,7 @@ __global__ void __launch_bounds__(256)
 
 // SEC1 compressed points (33 bytes: 02/03 || x; 33 zero bytes = identity) -> affine x || y, identity flag, validity.
 template <class C>
-__global__ void __launch_bounds__(128)
+ECG_KERNEL(128)
     decompress_kernel(const uint8_t* __restrict__ sec1, size_t n, uint8_t* __restrict__ out_xy, uint8_t* __restrict__ out_inf,
                       uint8_t* __restrict__ valid) {
   typedef typename C::F F;
@@ -455,7 +467,7 @@ __global__ void __launch_bounds__(128)
 
 // canonical affine big-endian bytes (n*64) -> table words (internal form); used once, when a table is built
 template <class C>
-__global__ void __launch_bounds__(256)
+ECG_KERNEL(256)
     affine_to_table_kernel(const uint8_t* __restrict__ xy, size_t n, uint32_t* __restrict__ table) {
   typedef typename C::F F;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -475,7 +487,7 @@ __global__ void __launch_bounds__(256)
 // Sum of Jacobian points: thread t adds elements t, t+T, t+2T, ... of `in` (SoA, n_in) and writes partial t of
 // `out` (SoA, n_out = T).  Applied repeatedly until one point is left (lincomb's final reduction).
 template <class C>
-__global__ void __launch_bounds__(128)
+ECG_KERNEL(128)
     jac_sum_kernel(const uint32_t* __restrict__ in, size_t n_in, uint32_t* __restrict__ out, size_t n_out) {
   typedef typename C::F F;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -498,7 +510,7 @@ __global__ void __launch_bounds__(128)
 
 // SoA internal Jacobian -> AoS canonical big-endian X||Y||Z (96 bytes per point)
 template <class C>
-__global__ void __launch_bounds__(128)
+ECG_KERNEL(128)
     export_jac_kernel(const uint32_t* __restrict__ jac, size_t n, uint8_t* __restrict__ xyz) {
   typedef typename C::F F;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -518,7 +530,7 @@ __global__ void __launch_bounds__(128)
 // element.  Replaces batch_normalize / BatchInvert (k256/src/arithmetic/projective.rs:367-391,
 // k256/src/arithmetic/field.rs:244-291).  scr: 8*n words of scratch (prefix products).
 template <class F>
-__global__ void __launch_bounds__(256)
+ECG_KERNEL(256)
     normalize_kernel(const uint32_t* __restrict__ jac, size_t n, uint32_t* __restrict__ scr,
                      uint8_t* __restrict__ out_xy, uint8_t* __restrict__ out_inf) {
   size_t T = (size_t)gridDim.x * blockDim.x;
@@ -564,7 +576,7 @@ __global__ void __launch_bounds__(256)
 
 // AoS big-endian X||Y||Z (n*96 bytes, canonical) -> SoA internal form; validates coordinates < p.
 template <class C>
-__global__ void __launch_bounds__(256)
+ECG_KERNEL(256)
     import_jac_kernel(const uint8_t* __restrict__ xyz, size_t n, uint32_t* __restrict__ jac,
                       uint32_t* __restrict__ status, size_t base) {
   typedef typename C::F F;
@@ -582,7 +594,7 @@ __global__ void __launch_bounds__(256)
 
 // ------------------------------------------------------------------------------------------------
 template <class C>
-__global__ void __launch_bounds__(256)
+ECG_KERNEL(256)
     field_op_kernel(int op, size_t n, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
                     uint8_t* __restrict__ out, uint32_t* __restrict__ status, size_t base) {
   typedef typename C::F F;

@@ -109,8 +109,62 @@ def ecdsa_full(curve):
     return {"source": f"{curve}/src/test_vectors/ecdsa.rs", "vectors": out}
 
 
+def _vlq(d, pos):
+    """git-flavoured variable-length quantity used by the `blobby` 0.4 container"""
+    b = d[pos]
+    pos += 1
+    val = b & 0x7F
+    while b & 0x80:
+        b = d[pos]
+        pos += 1
+        val = ((val + 1) << 7) + (b & 0x7F)
+    return val, pos
+
+
+def blobby(path):
+    """blobby 0.4: VLQ blob count, VLQ size of the de-duplication table, its entries (VLQ length + bytes), then one
+    VLQ per blob: odd = reference (n >> 1) into the table, even = (n >> 1) inline bytes."""
+    d = open(path, "rb").read()
+    total, pos = _vlq(d, 0)
+    nd, pos = _vlq(d, pos)
+    table = []
+    for _ in range(nd):
+        m, pos = _vlq(d, pos)
+        table.append(d[pos:pos + m])
+        pos += m
+    blobs = []
+    while pos < len(d):
+        n, pos = _vlq(d, pos)
+        if n & 1:
+            blobs.append(table[n >> 1])
+        else:
+            blobs.append(d[pos:pos + (n >> 1)])
+            pos += n >> 1
+    assert pos == len(d) and len(blobs) == total and total % 5 == 0
+    return blobs
+
+
+def wycheproof(curve):
+    """ECDSA verification vectors of the reference's Wycheproof tests (k256/src/ecdsa.rs:262-389,
+    p256/src/ecdsa.rs:166-169): records of (wx, wy, msg, sig, pass); `fmt` = der | p1363."""
+    out = []
+    files = [("wycheproof.blb", "der")] + ([("wycheproof-p1316.blb", "p1363")] if curve == "k256" else [])
+    for name, fmt in files:
+        b = blobby(f"{REF}/{curve}/src/test_vectors/data/{name}")
+        for i in range(0, len(b), 5):
+            wx, wy, msg, sig, ok = b[i:i + 5]
+            assert ok in (b"\x00", b"\x01")
+            out.append({"wx": wx.hex(), "wy": wy.hex(), "msg": msg.hex(), "sig": sig.hex(), "pass": ok[0], "fmt": fmt})
+    return {"source": f"{curve}/src/test_vectors/data/wycheproof*.blb", "vectors": out}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    for curve in ("k256", "p256"):
+        with open(os.path.join(OUT, f"{curve}_wycheproof.json"), "w") as f:
+            v = wycheproof(curve)
+            json.dump(v, f, indent=0)
+            print("wycheproof", curve, len(v["vectors"]), sum(x["pass"] for x in v["vectors"]), "valid")
     with open(os.path.join(OUT, "k256_bip340.json"), "w") as f:
         v = bip340_vectors()
         json.dump(v, f, indent=1)

@@ -11,7 +11,43 @@
 #include "../../elliptic-curves_b200/csrc/ecg_msm.cuh"
 #include "../../elliptic-curves_b200/csrc/ecg_verify.cuh"
 
+// ---- execution-model shim for ecg_kernels.cuh: one simulated thread at a time (no kernel there uses shared memory,
+// barriers or warp collectives, so running the threads of a grid one after another is a valid schedule)
+#define ECG_HOST_SIM 1
+struct SimDim {
+  unsigned x = 0, y = 0, z = 0;
+};
+static SimDim threadIdx, blockIdx, blockDim, gridDim;
+static inline uint32_t atomicOr(uint32_t* p, uint32_t v) {
+  uint32_t o = *p;
+  *p |= v;
+  return o;
+}
+static inline uint32_t atomicMin(uint32_t* p, uint32_t v) {
+  uint32_t o = *p;
+  if (v < o) *p = v;
+  return o;
+}
+struct uint4 {
+  uint32_t x, y, z, w;
+};
+static inline uint4 __ldg(const uint4* p) { return *p; }
+#include "../../elliptic-curves_b200/csrc/ecg_kernels.cuh"
+
 using namespace ecg;
+
+template <class Body>
+static void sim_launch(size_t threads, unsigned block, Body body) {
+  unsigned grid = (unsigned)((threads + block - 1) / block);
+  gridDim.x = grid ? grid : 1;
+  blockDim.x = block;
+  for (unsigned b = 0; b < gridDim.x; b++)
+    for (unsigned t = 0; t < block; t++) {
+      blockIdx.x = b;
+      threadIdx.x = t;
+      body();
+    }
+}
 
 extern "C" {
 
@@ -250,4 +286,122 @@ int sim_msm_recode(const uint8_t* m_le36, int c, int nbits, int32_t* out) {
   msm_recode(out, m, g);
   return g.W;
 }
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Kernel-level simulation: the kernel sequences of ecgpu.cu (run_chunk / launch_varbase / launch_norm), executed on
+// the host.  `table` is the fixed-base table in the device layout (simk_affine_to_table of the 16*2^15+1 points).
+static const int SIM_BLOCK = 128;
+
+template <class C>
+static void simk_normalize(std::vector<uint32_t>& jac, size_t n, uint8_t* out_xy, uint8_t* out_inf) {
+  std::vector<uint32_t> scr(8 * n + 8);
+  size_t threads = (n + 31) / 32;  // as launch_norm: slices of up to 32 elements share one inversion
+  sim_launch(threads, 256, [&] { normalize_kernel<typename C::F>(jac.data(), n, scr.data(), out_xy, out_inf); });
+}
+
+extern "C" int simk_affine_to_table(int curve, size_t n, const uint8_t* xy, uint32_t* table) {
+  if (curve == 0)
+    sim_launch(n, 256, [&] { affine_to_table_kernel<CurveK256>(xy, n, table); });
+  else
+    sim_launch(n, 256, [&] { affine_to_table_kernel<CurveP256>(xy, n, table); });
+  return 0;
+}
+
+// ecg_mul_batch: status[0] = error flags, status[1] = first offending index
+extern "C" int simk_mul_batch(int curve, size_t n, const uint8_t* k, const uint8_t* pxy, const uint8_t* pinf, uint8_t* out_xy,
+                   uint8_t* out_inf, uint32_t* status) {
+  std::vector<uint32_t> jac(24 * n + 24);
+  size_t blocks = (n + SIM_BLOCK - 1) / SIM_BLOCK;
+  status[0] = 0;
+  status[1] = 0xFFFFFFFFu;
+  if (curve == 0) {
+    std::vector<uint32_t> gtab(blocks * SIM_BLOCK * K_TAB_WORDS);
+    sim_launch(n, SIM_BLOCK, [&] { k256_varbase_kernel<SIM_BLOCK, 4>(k, pxy, pinf, n, jac.data(), gtab.data(), status, 0); });
+    simk_normalize<CurveK256>(jac, n, out_xy, out_inf);
+  } else {
+    std::vector<uint32_t> gtab(blocks * SIM_BLOCK * P_TAB_WORDS);
+    sim_launch(n, SIM_BLOCK, [&] { generic_varbase_kernel<CurveP256, SIM_BLOCK, 4>(k, pxy, pinf, n, jac.data(), gtab.data(), status, 0); });
+    simk_normalize<CurveP256>(jac, n, out_xy, out_inf);
+  }
+  return 0;
+}
+
+extern "C" int simk_mul_gen_batch(int curve, size_t n, const uint8_t* k, const uint32_t* table, uint8_t* out_xy, uint8_t* out_inf,
+                       uint32_t* status) {
+  std::vector<uint32_t> jac(24 * n + 24);
+  status[0] = 0;
+  status[1] = 0xFFFFFFFFu;
+  if (curve == 0) {
+    sim_launch(n, 128, [&] { fixedbase_kernel<CurveK256>(k, n, table, jac.data(), status, 0); });
+    simk_normalize<CurveK256>(jac, n, out_xy, out_inf);
+  } else {
+    sim_launch(n, 128, [&] { fixedbase_kernel<CurveP256>(k, n, table, jac.data(), status, 0); });
+    simk_normalize<CurveP256>(jac, n, out_xy, out_inf);
+  }
+  return 0;
+}
+
+template <class C, bool IS_K256>
+static void simk_mga(size_t n, const uint8_t* a, const uint8_t* b, const uint8_t* pxy, const uint8_t* pinf,
+                     const uint32_t* table, uint8_t* out_xy, uint8_t* out_inf, uint32_t* status) {
+  std::vector<uint32_t> jac(24 * n + 24);
+  size_t blocks = (n + SIM_BLOCK - 1) / SIM_BLOCK;
+  std::vector<uint32_t> gtab(blocks * SIM_BLOCK * (IS_K256 ? K_TAB_WORDS : P_TAB_WORDS));
+  sim_launch(n, SIM_BLOCK, [&] {
+    mul_gen_add_kernel<C, SIM_BLOCK, 4, IS_K256>(a, b, pxy, pinf, n, table, jac.data(), gtab.data(), status, 0);
+  });
+  simk_normalize<C>(jac, n, out_xy, out_inf);
+}
+
+extern "C" int simk_mul_gen_add_batch(int curve, size_t n, const uint8_t* a, const uint8_t* b, const uint8_t* pxy, const uint8_t* pinf,
+                           const uint32_t* table, uint8_t* out_xy, uint8_t* out_inf, uint32_t* status) {
+  status[0] = 0;
+  status[1] = 0xFFFFFFFFu;
+  if (curve == 0)
+    simk_mga<CurveK256, true>(n, a, b, pxy, pinf, table, out_xy, out_inf, status);
+  else
+    simk_mga<CurveP256, false>(n, a, b, pxy, pinf, table, out_xy, out_inf, status);
+  return 0;
+}
+
+// ecg_ecdsa_verify_batch: prep (range / low-s / on-curve checks, batched s^-1) -> a*G + b*Q -> affine -> verdict
+template <class C, bool IS_K256>
+static void simk_ecdsa(size_t n, const uint8_t* z, const uint8_t* sig, const uint8_t* q, int low_s, const uint32_t* table,
+                       uint8_t* valid) {
+  std::vector<uint32_t> scr(8 * n + 8);
+  std::vector<uint8_t> vp(64 * n), va(32 * n), vb(32 * n), vok(n), vxy(64 * n), vinf(n);
+  uint32_t status[2] = {0, 0xFFFFFFFFu};
+  size_t threads = (n + 31) / 32;
+  sim_launch(threads, 128, [&] { ecdsa_prep_kernel<C>(z, sig, q, n, low_s, scr.data(), vp.data(), va.data(), vb.data(), vok.data()); });
+  simk_mga<C, IS_K256>(n, va.data(), vb.data(), vp.data(), nullptr, table, vxy.data(), vinf.data(), status);
+  sim_launch(n, 256, [&] { ecdsa_check_kernel<C>(sig, vxy.data(), vinf.data(), vok.data(), n, valid); });
+}
+
+extern "C" int simk_ecdsa_verify_batch(int curve, size_t n, const uint8_t* z, const uint8_t* sig, const uint8_t* q, int low_s,
+                            const uint32_t* table, uint8_t* valid) {
+  if (curve == 0)
+    simk_ecdsa<CurveK256, true>(n, z, sig, q, low_s, table, valid);
+  else
+    simk_ecdsa<CurveP256, false>(n, z, sig, q, low_s, table, valid);
+  return 0;
+}
+
+// ecg_schnorr_verify_batch (BIP340)
+extern "C" int simk_schnorr_verify_batch(size_t n, const uint8_t* pk, const uint8_t* msg, const uint8_t* sig, const uint32_t* table,
+                              uint8_t* valid) {
+  std::vector<uint8_t> vp(64 * n), va(32 * n), vb(32 * n), vok(n), vxy(64 * n), vinf(n);
+  uint32_t status[2] = {0, 0xFFFFFFFFu};
+  sim_launch(n, 128, [&] { schnorr_prep_kernel(pk, msg, sig, n, vp.data(), va.data(), vb.data(), vok.data()); });
+  simk_mga<CurveK256, true>(n, va.data(), vb.data(), vp.data(), nullptr, table, vxy.data(), vinf.data(), status);
+  sim_launch(n, 256, [&] { schnorr_check_kernel(sig, vxy.data(), vinf.data(), vok.data(), n, valid); });
+  return 0;
+}
+
+extern "C" int simk_decompress_batch(int curve, size_t n, const uint8_t* sec1, uint8_t* out_xy, uint8_t* out_inf, uint8_t* valid) {
+  if (curve == 0)
+    sim_launch(n, 128, [&] { decompress_kernel<CurveK256>(sec1, n, out_xy, out_inf, valid); });
+  else
+    sim_launch(n, 128, [&] { decompress_kernel<CurveP256>(sec1, n, out_xy, out_inf, valid); });
+  return 0;
 }
