@@ -3,16 +3,13 @@
 #pragma once
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
-#define ECG_KERNEL(...) __global__ void __launch_bounds__(__VA_ARGS__)
-#define ECG_DEV __device__ __forceinline__
 #else
 // Host build: only tests/sim/sim.cpp, which executes a kernel body once per simulated thread (it supplies threadIdx,
-// blockIdx, blockDim, gridDim, atomicOr/atomicMin, uint4 and __ldg).  Never part of libecgpu.so.
+// blockIdx, blockDim, gridDim, the atomics, uint4 and __ldg; ECG_KERNEL / ECG_DEV come from ecg_prim.cuh).  Never
+// part of libecgpu.so.
 #ifndef ECG_HOST_SIM
 #error "ecg_kernels.cuh is CUDA code; a host build exists only for the test simulation (tests/sim/sim.cpp)"
 #endif
-#define ECG_KERNEL(...) static void
-#define ECG_DEV inline
 #endif
 
 #include "../../include/ecgpu.h"

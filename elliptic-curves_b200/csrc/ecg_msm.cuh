@@ -56,12 +56,12 @@ ECG_D void msm_recode(int32_t* out, const uint32_t* m, const MsmGeom& g) {
   out[g.W - 1] = (int32_t)(msm_bits(m, top, width) + carry);
 }
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) || defined(ECG_HOST_SIM)  // kernels: CUDA, or the host simulation of tests/sim
 
 // pts: sub-point j at pts[j*16 .. j*16+15] (x[8], y[8], internal form).  digits: sub-term j, window w at
 // digits[w * nsub + j] (signed, the sub-scalar's own sign already folded in; 0 = nothing to add).
 template <class C, bool GLV>
-__global__ void __launch_bounds__(128)
+ECG_KERNEL(128)
     msm_prep_kernel(const uint8_t* __restrict__ kb, const uint8_t* __restrict__ pxy, const uint8_t* __restrict__ pinf,
                     size_t n, MsmGeom g, uint32_t* __restrict__ pts, int32_t* __restrict__ digits,
                     uint32_t* __restrict__ count, uint32_t* __restrict__ status, size_t base) {
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(128)
 #define MSM_SCAN_BLOCK 256
 #define MSM_SCAN_PER_THREAD 16
 #define MSM_SCAN_CHUNK (MSM_SCAN_BLOCK * MSM_SCAN_PER_THREAD)
-__global__ void __launch_bounds__(MSM_SCAN_BLOCK)
+ECG_KERNEL(MSM_SCAN_BLOCK)
     msm_scan_partial_kernel(const uint32_t* __restrict__ count, size_t m, uint32_t* __restrict__ blocksum, uint32_t* __restrict__ maxcnt) {
   __shared__ uint32_t ssum[MSM_SCAN_BLOCK], smax[MSM_SCAN_BLOCK];
   size_t lo = (size_t)blockIdx.x * MSM_SCAN_CHUNK + (size_t)threadIdx.x * MSM_SCAN_PER_THREAD;
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(MSM_SCAN_BLOCK)
     atomicMax(maxcnt, smax[0]);
   }
 }
-__global__ void __launch_bounds__(1024)
+ECG_KERNEL(1024)
     msm_scan_top_kernel(uint32_t* __restrict__ blocksum, size_t nblocks, uint32_t* __restrict__ offset, size_t m) {
   // nblocks <= a few thousand: serial per-thread chunks + one serial pass over 1024 partials
   __shared__ uint32_t part[1024];
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(1024)
     run += t;
   }
 }
-__global__ void __launch_bounds__(MSM_SCAN_BLOCK)
+ECG_KERNEL(MSM_SCAN_BLOCK)
     msm_scan_final_kernel(const uint32_t* __restrict__ count, size_t m, const uint32_t* __restrict__ blockoff, uint32_t* __restrict__ offset) {
   __shared__ uint32_t ssum[MSM_SCAN_BLOCK];
   size_t lo = (size_t)blockIdx.x * MSM_SCAN_CHUNK + (size_t)threadIdx.x * MSM_SCAN_PER_THREAD;
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(MSM_SCAN_BLOCK)
     }
 }
 
-__global__ void __launch_bounds__(256)
+ECG_KERNEL(256)
     msm_scatter_kernel(const int32_t* __restrict__ digits, size_t nsub, MsmGeom g, const uint32_t* __restrict__ offset,
                        uint32_t* __restrict__ cursor, uint32_t* __restrict__ list) {
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-__device__ __forceinline__ void msm_load_point(Aff& e, const uint32_t* __restrict__ pts, uint32_t j) {
+ECG_DEV void msm_load_point(Aff& e, const uint32_t* __restrict__ pts, uint32_t j) {
   const uint4* p = reinterpret_cast<const uint4*>(pts + (size_t)j * 16);
   uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
   e.x.v[0] = a.x; e.x.v[1] = a.y; e.x.v[2] = a.z; e.x.v[3] = a.w;
@@ -268,7 +268,7 @@ __device__ __forceinline__ void msm_load_point(Aff& e, const uint32_t* __restric
 
 // One thread per bucket: B = sum of its (signed) points.  bkt: SoA Jacobian over nb = W*nbw buckets.
 template <class C>
-__global__ void __launch_bounds__(128, 4)
+ECG_KERNEL(128, 4)
     msm_bucket_kernel(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ list, const uint32_t* __restrict__ offset,
                       size_t nb, uint32_t* __restrict__ bkt) {
   typedef typename C::F F;
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(128, 4)
   }
 }
 
-__device__ __forceinline__ void msm_jload(Jac& p, const uint32_t* __restrict__ a, size_t n, size_t i) {
+ECG_DEV void msm_jload(Jac& p, const uint32_t* __restrict__ a, size_t n, size_t i) {
 #pragma unroll
   for (int w = 0; w < 8; w++) {
     p.X.v[w] = a[(size_t)w * n + i];
@@ -319,7 +319,7 @@ __device__ __forceinline__ void msm_jload(Jac& p, const uint32_t* __restrict__ a
     p.Z.v[w] = a[(size_t)(16 + w) * n + i];
   }
 }
-__device__ __forceinline__ void msm_jstore(uint32_t* __restrict__ a, size_t n, size_t i, const Jac& p) {
+ECG_DEV void msm_jstore(uint32_t* __restrict__ a, size_t n, size_t i, const Jac& p) {
 #pragma unroll
   for (int w = 0; w < 8; w++) {
     a[(size_t)w * n + i] = p.X.v[w];
@@ -340,7 +340,7 @@ __device__ __forceinline__ void msm_jstore(uint32_t* __restrict__ a, size_t n, s
 #define MSM_CH 16
 #define MSM_CH_LOG2 4
 template <class C>
-__global__ void __launch_bounds__(128)
+ECG_KERNEL(128)
     msm_wreduce_kernel(const uint32_t* __restrict__ in, size_t n_in, size_t stride_in, size_t off, size_t len, int W, size_t nch,
                        const uint32_t* __restrict__ Xprev, int level, uint32_t* __restrict__ outS, uint32_t* __restrict__ outX) {
   typedef typename C::F F;
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(128)
 
 // R_w = X_L[w] - k * Btot[w],  k = CH + CH^2 + ... + CH^L;  then out = sum_w 2^(c w) R_w  (Horner, thread 0).
 template <class C>
-__global__ void __launch_bounds__(32)
+ECG_KERNEL(32)
     msm_final_kernel(const uint32_t* __restrict__ XL, const uint32_t* __restrict__ SL, int W, int c, int levels,
                      uint32_t* __restrict__ R, uint32_t* __restrict__ out) {
   typedef typename C::F F;
@@ -410,6 +410,6 @@ __global__ void __launch_bounds__(32)
   }
 }
 
-#endif  // __CUDACC__
+#endif  // __CUDACC__ || ECG_HOST_SIM
 
 }  // namespace ecg

@@ -13,8 +13,14 @@
 
 #if defined(__CUDACC__)
 #define ECG_D __device__ __forceinline__
+// kernels (ecg_kernels.cuh, ecg_msm.cuh): ECG_KERNEL(launch bounds...) name(args) { ... }
+#define ECG_KERNEL(...) __global__ void __launch_bounds__(__VA_ARGS__)
+#define ECG_DEV __device__ __forceinline__
 #else
 #define ECG_D inline
+// host build of a kernel header: only tests/sim/sim.cpp (ECG_HOST_SIM), which runs a kernel body per simulated thread
+#define ECG_KERNEL(...) static void
+#define ECG_DEV inline
 #endif
 
 namespace ecg {

@@ -3,39 +3,59 @@
 // replaced by their C emulation (ecg_prim.cuh, #else branch), so that field / point / scalar-mult logic
 // can be checked against the big-integer oracle in a container that has no GPU.  Never linked into
 // libecgpu.so; never used as a fallback.
-#include <cstring>
-#include <vector>
-#include "../../elliptic-curves_b200/csrc/ecg_curves.cuh"
-#include "../../elliptic-curves_b200/csrc/ecg_mul.cuh"
-#include "../../elliptic-curves_b200/csrc/ecg_io.cuh"
-#include "../../elliptic-curves_b200/csrc/ecg_msm.cuh"
-#include "../../elliptic-curves_b200/csrc/ecg_verify.cuh"
+#include <pthread.h>
 
-// ---- execution-model shim for ecg_kernels.cuh: one simulated thread at a time (no kernel there uses shared memory,
-// barriers or warp collectives, so running the threads of a grid one after another is a valid schedule)
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+// ---- execution-model shim for the kernel headers (ecg_kernels.cuh, ecg_msm.cuh) -------------------------------
+// A kernel is an ordinary function; the launchers below run its body once per simulated thread.  Kernels without
+// barriers run their threads one after another (a valid schedule: they share nothing but global memory they own or
+// update atomically).  Kernels with __shared__ / __syncthreads() run one block at a time on real threads with a
+// pthread barrier.
 #define ECG_HOST_SIM 1
 struct SimDim {
   unsigned x = 0, y = 0, z = 0;
 };
-static SimDim threadIdx, blockIdx, blockDim, gridDim;
-static inline uint32_t atomicOr(uint32_t* p, uint32_t v) {
-  uint32_t o = *p;
-  *p |= v;
+static thread_local SimDim threadIdx, blockIdx, blockDim, gridDim;
+static pthread_barrier_t* sim_block_barrier = nullptr;
+static inline void __syncthreads() {
+  if (sim_block_barrier) pthread_barrier_wait(sim_block_barrier);
+}
+#define __shared__ static /* one block at a time, so a function-level static is the block's shared memory */
+static inline uint32_t atomicOr(uint32_t* p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline uint32_t atomicMin(uint32_t* p, uint32_t v) {
+  uint32_t o = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+  }
   return o;
 }
-static inline uint32_t atomicMin(uint32_t* p, uint32_t v) {
-  uint32_t o = *p;
-  if (v < o) *p = v;
+static inline uint32_t atomicMax(uint32_t* p, uint32_t v) {
+  uint32_t o = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+  }
   return o;
 }
 struct uint4 {
   uint32_t x, y, z, w;
 };
 static inline uint4 __ldg(const uint4* p) { return *p; }
+
+#include "../../elliptic-curves_b200/csrc/ecg_curves.cuh"
+#include "../../elliptic-curves_b200/csrc/ecg_mul.cuh"
+#include "../../elliptic-curves_b200/csrc/ecg_io.cuh"
+#include "../../elliptic-curves_b200/csrc/ecg_msm.cuh"
+#include "../../elliptic-curves_b200/csrc/ecg_verify.cuh"
+
 #include "../../elliptic-curves_b200/csrc/ecg_kernels.cuh"
 
 using namespace ecg;
 
+// grid of ceil(threads / block) blocks, threads executed one after another
 template <class Body>
 static void sim_launch(size_t threads, unsigned block, Body body) {
   unsigned grid = (unsigned)((threads + block - 1) / block);
@@ -47,6 +67,28 @@ static void sim_launch(size_t threads, unsigned block, Body body) {
       threadIdx.x = t;
       body();
     }
+}
+// `grid` blocks of `block` real threads each (kernels that use __shared__ / __syncthreads), one block at a time
+template <class Body>
+static void sim_launch_blocks(unsigned grid, unsigned block, Body body) {
+  for (unsigned b = 0; b < grid; b++) {
+    pthread_barrier_t bar;
+    pthread_barrier_init(&bar, nullptr, block);
+    sim_block_barrier = &bar;
+    std::vector<std::thread> th;
+    th.reserve(block);
+    for (unsigned t = 0; t < block; t++)
+      th.emplace_back([=, &body] {
+        gridDim.x = grid;
+        blockDim.x = block;
+        blockIdx.x = b;
+        threadIdx.x = t;
+        body();
+      });
+    for (auto& x : th) x.join();
+    sim_block_barrier = nullptr;
+    pthread_barrier_destroy(&bar);
+  }
 }
 
 extern "C" {
@@ -403,5 +445,121 @@ extern "C" int simk_decompress_batch(int curve, size_t n, const uint8_t* sec1, u
     sim_launch(n, 128, [&] { decompress_kernel<CurveK256>(sec1, n, out_xy, out_inf, valid); });
   else
     sim_launch(n, 128, [&] { decompress_kernel<CurveP256>(sec1, n, out_xy, out_inf, valid); });
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ecg_lincomb on the host: the kernel sequences of ecgpu.cu's lincomb_shard / msm_run / reduce_points, with
+// std::vector buffers in place of the lane arena.  `msm_min_terms` plays MSM_MIN_TERMS (2^13 in the product) so that a
+// test can send a few hundred terms through the bucket method.  *path: 0 per-term kernel + tree sum, 1 bucket method,
+// 2 bucket method refused the input as too skewed and the per-term path ran instead.
+static MsmGeom simk_msm_geometry(int curve, size_t n) {  // = msm_geometry (ecgpu.cu)
+  MsmGeom g;
+  bool glv = curve == 0;
+  size_t nsub = glv ? 2 * n : n;
+  int lg = 0;
+  while (((size_t)1 << (lg + 1)) <= nsub) lg++;
+  g.c = std::min(16, std::max(8, lg - 5));
+  g.nbits = glv ? 128 : 256;
+  g.W = (g.nbits + g.c - 1) / g.c;
+  g.nbw = ((uint32_t)1 << (g.c + 1)) + 2;
+  return g;
+}
+
+template <class C>
+static std::vector<uint32_t> simk_reduce_points(std::vector<uint32_t> a, size_t n) {  // = reduce_points
+  while (n > 1) {
+    size_t m = (n + 31) / 32;
+    std::vector<uint32_t> b(24 * m);
+    sim_launch(m, 128, [&] { jac_sum_kernel<C>(a.data(), n, b.data(), m); });
+    a.swap(b);
+    n = m;
+  }
+  return a;
+}
+
+template <class C, bool GLV>
+static bool simk_msm_run(const uint8_t* k, const uint8_t* pxy, const uint8_t* pinf, size_t n, const MsmGeom& g,
+                         uint32_t* status, std::vector<uint32_t>& result) {  // = msm_run; false = too skewed
+  const size_t nsub = GLV ? 2 * n : n;
+  const size_t nb = (size_t)g.W * g.nbw;
+  std::vector<size_t> lens, nchs;
+  size_t len = g.nbw - 1;
+  for (;;) {
+    size_t nch = (len + MSM_CH - 1) / MSM_CH;
+    lens.push_back(len);
+    nchs.push_back(nch);
+    if (nch == 1) break;
+    len = nch;
+  }
+  const int levels = (int)lens.size();
+  std::vector<uint32_t> pts(nsub * 16), count(2 * nb + 4, 0), offset(nb + 1), list(nsub * (size_t)g.W + 1), bkt(nb * 24);
+  std::vector<int32_t> digits(nsub * (size_t)g.W);
+  const unsigned sb = (unsigned)((nb + MSM_SCAN_CHUNK - 1) / MSM_SCAN_CHUNK);
+  std::vector<uint32_t> blocksum(sb + 1);
+  uint32_t* cursor = count.data() + nb + 1;
+  uint32_t* maxcnt = count.data() + 2 * nb + 3;
+  sim_launch(n, 128, [&] { msm_prep_kernel<C, GLV>(k, pxy, pinf, n, g, pts.data(), digits.data(), count.data(), status, 0); });
+  sim_launch_blocks(sb, MSM_SCAN_BLOCK, [&] { msm_scan_partial_kernel(count.data(), nb, blocksum.data(), maxcnt); });
+  sim_launch_blocks(1, 1024, [&] { msm_scan_top_kernel(blocksum.data(), sb, offset.data(), nb); });
+  sim_launch_blocks(sb, MSM_SCAN_BLOCK, [&] { msm_scan_final_kernel(count.data(), nb, blocksum.data(), offset.data()); });
+  size_t avg = nsub / ((size_t)1 << (g.c - 1)) + 1;
+  if ((size_t)*maxcnt > 4096 && (size_t)*maxcnt > 32 * avg) return false;
+  sim_launch(nsub, 256, [&] { msm_scatter_kernel(digits.data(), nsub, g, offset.data(), cursor, list.data()); });
+  sim_launch(nb, 128, [&] { msm_bucket_kernel<C>(pts.data(), list.data(), offset.data(), nb, bkt.data()); });
+  std::vector<std::vector<uint32_t>> S(levels), X(levels);
+  for (int l = 0; l < levels; l++) {
+    S[l].assign((size_t)g.W * nchs[l] * 24, 0);
+    X[l].assign((size_t)g.W * nchs[l] * 24, 0);
+    const uint32_t* in = l == 0 ? bkt.data() : S[l - 1].data();
+    size_t n_in = l == 0 ? nb : (size_t)g.W * nchs[l - 1];
+    size_t stride = l == 0 ? g.nbw : nchs[l - 1];
+    size_t off = l == 0 ? 1 : 0;
+    sim_launch((size_t)g.W * nchs[l], 128, [&] {
+      msm_wreduce_kernel<C>(in, n_in, stride, off, lens[l], g.W, nchs[l], l == 0 ? nullptr : X[l - 1].data(), l, S[l].data(), X[l].data());
+    });
+  }
+  std::vector<uint32_t> Rw((size_t)g.W * 24);
+  result.assign(24, 0);
+  sim_launch_blocks(1, 32, [&] { msm_final_kernel<C>(X[levels - 1].data(), S[levels - 1].data(), g.W, g.c, levels - 1, Rw.data(), result.data()); });
+  return true;
+}
+
+template <class C, bool GLV, bool IS_K256>
+static void simk_lincomb_t(int curve, size_t n, const uint8_t* k, const uint8_t* pxy, const uint8_t* pinf, size_t msm_min_terms,
+                           uint8_t* out_xy, uint8_t* out_inf, uint32_t* status, int* path) {
+  std::vector<uint32_t> res;
+  *path = 0;
+  if (n >= msm_min_terms) {
+    MsmGeom g = simk_msm_geometry(curve, n);
+    *path = simk_msm_run<C, GLV>(k, pxy, pinf, n, g, status, res) ? 1 : 2;
+  }
+  if (*path != 1) {  // per-term kernel + tree sum
+    std::vector<uint32_t> jac(24 * n);
+    size_t blocks = (n + SIM_BLOCK - 1) / SIM_BLOCK;
+    std::vector<uint32_t> gtab(blocks * SIM_BLOCK * (IS_K256 ? K_TAB_WORDS : P_TAB_WORDS));
+    if (IS_K256)
+      sim_launch(n, SIM_BLOCK, [&] { k256_varbase_kernel<SIM_BLOCK, 4>(k, pxy, pinf, n, jac.data(), gtab.data(), status, 0); });
+    else
+      sim_launch(n, SIM_BLOCK, [&] { generic_varbase_kernel<CurveP256, SIM_BLOCK, 4>(k, pxy, pinf, n, jac.data(), gtab.data(), status, 0); });
+    res = simk_reduce_points<C>(jac, n);
+  }
+  simk_normalize<C>(res, 1, out_xy, out_inf);
+}
+
+extern "C" int simk_lincomb(int curve, size_t n, const uint8_t* k, const uint8_t* pxy, const uint8_t* pinf, size_t msm_min_terms,
+                            uint8_t* out_xy, uint8_t* out_inf, uint32_t* status, int* path) {
+  status[0] = 0;
+  status[1] = 0xFFFFFFFFu;
+  if (n == 0) {  // empty sum = identity
+    memset(out_xy, 0, 64);
+    *out_inf = 1;
+    *path = 0;
+    return 0;
+  }
+  if (curve == 0)
+    simk_lincomb_t<CurveK256, true, true>(curve, n, k, pxy, pinf, msm_min_terms, out_xy, out_inf, status, path);
+  else
+    simk_lincomb_t<CurveP256, false, false>(curve, n, k, pxy, pinf, msm_min_terms, out_xy, out_inf, status, path);
   return 0;
 }

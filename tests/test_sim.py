@@ -21,7 +21,7 @@ def sim():
     csrc = os.path.join(HERE, "..", "elliptic-curves_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc)]
     if not os.path.exists(SIM_SO) or any(os.path.getmtime(d) > os.path.getmtime(SIM_SO) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-shared", "-fPIC", "-o", SIM_SO, src])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-shared", "-fPIC", "-pthread", "-o", SIM_SO, src])
     return ctypes.CDLL(SIM_SO)
 
 

@@ -199,3 +199,54 @@ def test_decompress_kernel(sim, curve):
             assert (int.from_bytes(oxy[64 * i:64 * i + 32].tobytes(), "big"), int.from_bytes(oxy[64 * i + 32:64 * i + 64].tobytes(), "big")) == w
     assert valid[60] == 1 and oinf[60] == 1 and valid[61] == 0 and valid[62] == 0
     assert sum(w is not None for w in want) > 15
+
+
+@pytest.mark.parametrize("curve", ["k256", "p256"])
+def test_lincomb_kernels_per_term_and_bucket_method(sim, curve):
+    """ecg_lincomb's two kernel chains on the host (tests/sim/sim.cpp simk_lincomb mirrors lincomb_shard / msm_run):
+    per-term kernel + tree sum, and the bucket method (prep, three-kernel scan, scatter, buckets, recursive weighted
+    reduction, final) including its refusal of skewed inputs.  LinearCombination::lincomb, k256 mul.rs:66-175."""
+    c = pyref.CURVES[curve]
+    rng = random.Random(77)
+    base = random_points(c, 24, seed=31) + [None]
+
+    def run(ks, Ps, msm_min):
+        n = len(ks)
+        xy, inf = pack_points(Ps)
+        oxy, oinf, stt = np.zeros(64, np.uint8), np.zeros(1, np.uint8), np.zeros(2, np.uint32)
+        path = ctypes.c_int(-1)
+        sim.simk_lincomb(CID[curve], ctypes.c_size_t(n), _p(pack_scalars(ks)), _p(xy), _p(inf), ctypes.c_size_t(msm_min),
+                         _p(oxy), _p(oinf), _p(stt), ctypes.byref(path))
+        assert stt[0] == 0
+        return pyref.dec_point(oxy.tobytes(), int(oinf[0])), path.value
+
+    def want(ks, Ps):
+        if len(ks) <= 40:
+            return pyref.lincomb(c, ks, Ps)
+        xy, inf = pack_points(Ps)
+        rxy, rinf = ecref.lincomb(curve, pack_scalars(ks), xy, inf, nthreads=4)
+        return pyref.dec_point(np.asarray(rxy).tobytes(), int(rinf))
+
+    for n in (1, 2, 3, 33, 70):                                # per-term path, ragged tree sizes
+        ks = [rng.randrange(c.n) for _ in range(n)]
+        Ps = [base[rng.randrange(len(base))] for _ in range(n)]
+        got, path = run(ks, Ps, 1 << 13)
+        assert path == 0 and got == want(ks, Ps)
+    for n in (300, 777):                                       # bucket method on distinct points
+        ks = [rng.randrange(c.n) for _ in range(n)]
+        ks[5], ks[6] = 0, c.n - 1
+        pts = random_points(c, n - 1, seed=n) + [None]
+        got, path = run(ks, pts, 64)
+        assert path == 1 and got == want(ks, pts)
+    # terms that cancel: k*P + (n-k)*P over the bucket path -> identity
+    P = base[0]
+    ks = [rng.randrange(1, c.n) for _ in range(100)]
+    got, path = run(ks + [c.n - k for k in ks], [P] * 200, 64)
+    assert path == 1 and got is None
+    # the same point 6000 times with the same scalar: every digit lands in one bucket per window -> refused as skewed,
+    # the per-term path answers
+    k0 = rng.randrange(c.n)
+    got, path = run([k0] * 6000, [P] * 6000, 64)
+    assert path == 2 and got == pyref.mul(c, k0 * 6000 % c.n, P)
+    got, path = run([], [], 64)
+    assert got is None
