@@ -51,6 +51,16 @@ class SimBackend:
         return oxy.reshape(n, 64), oinf
 
 
+    def lincomb(self, curve, K, xy, inf):
+        n = K.size // 32
+        oxy, oinf, stt = np.zeros(64, np.uint8), np.zeros(1, np.uint8), np.zeros(2, np.uint32)
+        path = ctypes.c_int(-1)
+        self.lib.simk_lincomb(CID[curve], ctypes.c_size_t(n), _p(K), _p(np.ascontiguousarray(xy)), _p(inf), ctypes.c_size_t(1 << 13),
+                              _p(oxy), _p(oinf), _p(stt), ctypes.byref(path))
+        assert stt[0] == 0
+        return oxy, int(oinf[0])
+
+
 def _check(be, curve, rows, with_lincomb):
     c = pyref.CURVES[curve]
     G = pyref.G(c)
@@ -88,7 +98,7 @@ def test_properties_on_host_executed_kernels(sim, fb_tables, curve):
     @settings(**SETTINGS)
     @given(rows=batch)
     def run(rows):
-        _check(be, curve, rows, with_lincomb=False)
+        _check(be, curve, rows, with_lincomb=True)
 
     run()
 
