@@ -112,13 +112,22 @@ struct FpK256T {
     mul_body(r, a, b);
     return r;
   }
+  // OPT bit 8 (experiment, tools/kbench.cu): operands and result travel through local memory (LDL/STL on the idle LSU
+  // pipe) instead of the register ABI, whose marshalling ptxas emits as IMAD.MOV on the FMA pipe
+  static ECG_NOINLINE_D void mul_call_mem(Fe* r, const Fe* a, const Fe* b) {
+    Fe x = *a, y = *b, z;
+    mul_body(z, x, y);
+    *r = z;
+  }
   static ECG_NOINLINE_D Fe sqr_call(Fe a) {
     Fe r;
     sqr_body(r, a);
     return r;
   }
   ECG_D static void mul(Fe& r, const Fe& a, const Fe& b) {
-    if (OPT & 2)
+    if (OPT & 256)
+      mul_call_mem(&r, &a, &b);
+    else if (OPT & 2)
       r = mul_call(a, b);
     else
       mul_body(r, a, b);
@@ -126,7 +135,9 @@ struct FpK256T {
   // multiplication as used inside the doubling formula: OPT bit 5 keeps those three inlined (fewer calls on the
   // hottest path) while the mixed addition still calls
   ECG_D static void mul_d(Fe& r, const Fe& a, const Fe& b) {
-    if ((OPT & 2) && !(OPT & 32))
+    if (OPT & 256)
+      mul_call_mem(&r, &a, &b);
+    else if ((OPT & 2) && !(OPT & 32))
       r = mul_call(a, b);
     else
       mul_body(r, a, b);

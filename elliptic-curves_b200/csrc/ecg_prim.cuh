@@ -174,7 +174,12 @@ inline uint32_t bswap32(uint32_t x) { return __builtin_bswap32(x); }
 
 // ---- 8-limb helpers shared by both fields ---------------------------------------------------
 
-struct Fe {
+// ECG_FE_ALIGN = 16 lets local-memory copies of a field element move as two 128-bit accesses (only the kbench
+// "operands through memory" experiment, OPT bit 8, sets it; the library keeps natural alignment)
+#ifndef ECG_FE_ALIGN
+#define ECG_FE_ALIGN 4
+#endif
+struct alignas(ECG_FE_ALIGN) Fe {
   uint32_t v[8];  // little-endian 32-bit limbs
 };
 

@@ -1,6 +1,7 @@
 // tools/kbench.cu — development harness: times kernel variants of the secp256k1 variable-base path on one GPU
 // and cross-checks that every variant produces identical Jacobian words.  Not part of the product or of bench.py.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tools/kbench tools/kbench.cu
+//   modes: kbench 20 | kbench 20 trade | kbench 20 mem   (mem: also build with -DECG_FE_ALIGN=16 as tools/kbench_a16)
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -271,6 +272,17 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&jac, n * 96));
   CK(cudaMalloc(&gtab, (size_t)148 * 8 * 640 * 192 * 4));
   printf("n = %zu\n", n);
+  if (argc > 2 && !strcmp(argv[2], "mem")) {  // mul operands through local memory instead of the register ABI (OPT bit 8)
+    // build twice: default, and with -DECG_FE_ALIGN=16 (128-bit LDL/STL)
+    for (int round = 0; round < 2; round++) {
+      run<FpK256T<7>, 128, 4, true>("v7   base                 (128,4)", n, jac, gtab);
+      run<FpK256T<263>, 128, 4, true>("v263 mul via memory       (128,4)", n, jac, gtab);
+      run<FpK256T<263>, 128, 5, true>("v263 mul via memory       (128,5)", n, jac, gtab);
+      run<FpK256T<263>, 128, 6, true>("v263 mul via memory       (128,6)", n, jac, gtab);
+      run<FpK256T<263>, 128, 8, true>("v263 mul via memory       (128,8)", n, jac, gtab);
+    }
+    return 0;
+  }
   if (argc > 2 && !strcmp(argv[2], "trade")) {  // multiplication-for-squaring trades in the point formulas (OPT bits 6/7)
     for (int round = 0; round < 2; round++) {
       run<FpK256T<7>, 128, 4, true>("v7   base                (128,4)", n, jac, gtab);
