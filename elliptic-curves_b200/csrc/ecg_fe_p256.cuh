@@ -241,8 +241,21 @@ struct FpP256T {
     sqr_body(r, a);
     return r;
   }
+  // OPT bit 8 (experiment, tools/kbench.cu mode `mem`): operands and result through local memory, see ecg_fe_k256.cuh
+  static ECG_NOINLINE_D void mul_call_mem(Fe* r, const Fe* a, const Fe* b) {
+    Fe x = *a, y = *b, z;
+    mul_body(z, x, y);
+    *r = z;
+  }
+  static ECG_NOINLINE_D void sqr_call_mem(Fe* r, const Fe* a) {
+    Fe x = *a, z;
+    sqr_body(z, x);
+    *r = z;
+  }
   ECG_D static void mul(Fe& r, const Fe& a, const Fe& b) {
-    if (OPT & 2)
+    if (OPT & 256)
+      mul_call_mem(&r, &a, &b);
+    else if (OPT & 2)
       r = mul_call(a, b);
     else
       mul_body(r, a, b);
@@ -250,13 +263,17 @@ struct FpP256T {
   // multiplication as used inside the doubling formula: OPT bit 5 keeps those three inlined (fewer calls on the
   // hottest path) while the mixed addition still calls
   ECG_D static void mul_d(Fe& r, const Fe& a, const Fe& b) {
-    if ((OPT & 2) && !(OPT & 32))
+    if (OPT & 256)
+      mul_call_mem(&r, &a, &b);
+    else if ((OPT & 2) && !(OPT & 32))
       r = mul_call(a, b);
     else
       mul_body(r, a, b);
   }
   ECG_D static void sqr(Fe& r, const Fe& a) {
-    if ((OPT & 2) && !(OPT & 4))  // OPT bit 2: keep the (smaller) squaring inlined even when mul is a call
+    if ((OPT & 256) && !(OPT & 4))
+      sqr_call_mem(&r, &a);
+    else if ((OPT & 2) && !(OPT & 4))  // OPT bit 2: keep the (smaller) squaring inlined even when mul is a call
       r = sqr_call(a);
     else
       sqr_body(r, a);
