@@ -119,6 +119,11 @@ struct FpK256T {
     mul_body(z, x, y);
     *r = z;
   }
+  static ECG_NOINLINE_D void sqr_call_mem(Fe* r, const Fe* a) {
+    Fe x = *a, z;
+    sqr_body(z, x);
+    *r = z;
+  }
   static ECG_NOINLINE_D Fe sqr_call(Fe a) {
     Fe r;
     sqr_body(r, a);
@@ -143,7 +148,9 @@ struct FpK256T {
       mul_body(r, a, b);
   }
   ECG_D static void sqr(Fe& r, const Fe& a) {
-    if ((OPT & 2) && !(OPT & 4))  // OPT bit 2: keep the (smaller) squaring inlined even when mul is a call
+    if ((OPT & 256) && !(OPT & 4))
+      sqr_call_mem(&r, &a);
+    else if ((OPT & 2) && !(OPT & 4))  // OPT bit 2: keep the (smaller) squaring inlined even when mul is a call
       r = sqr_call(a);
     else
       sqr_body(r, a);

@@ -280,6 +280,8 @@ int main(int argc, char** argv) {
       run<FpK256T<263>, 128, 5, true>("v263 mul via memory       (128,5)", n, jac, gtab);
       run<FpK256T<263>, 128, 6, true>("v263 mul via memory       (128,6)", n, jac, gtab);
       run<FpK256T<263>, 128, 8, true>("v263 mul via memory       (128,8)", n, jac, gtab);
+      run<FpK256T<259>, 128, 5, true>("v259 mul+sqr via memory   (128,5)", n, jac, gtab);
+      run<FpK256T<259>, 128, 8, true>("v259 mul+sqr via memory   (128,8)", n, jac, gtab);
       runp<FpP256T<3>, 128, 4, true>("p256 v3 base              (128,4)", n, jac, gtab);
       runp<FpP256T<259>, 128, 4, true>("p256 v259 mul+sqr via mem (128,4)", n, jac, gtab);
       runp<FpP256T<259>, 128, 5, true>("p256 v259 mul+sqr via mem (128,5)", n, jac, gtab);
