@@ -250,3 +250,31 @@ def test_lincomb_kernels_per_term_and_bucket_method(sim, curve):
     assert path == 2 and got == pyref.mul(c, k0 * 6000 % c.n, P)
     got, path = run([], [], 64)
     assert got is None
+
+
+@pytest.mark.parametrize("curve", ["k256", "p256"])
+def test_varbase_kernel_scalar_sweeps(sim, curve):
+    """Dense sweeps where the recoding and the exceptional additions bite: every scalar in [0, 1500) and (n-1500, n),
+    neighbours of multiples of lambda (k256: one GLV half tiny or zero) and of powers of two, times G and a random
+    point — against the C oracle (bit-exact) and, on a sample, the big-integer model."""
+    c = pyref.CURVES[curve]
+    rng = random.Random(101)
+    ks = list(range(1500)) + [c.n - i for i in range(1, 1500)]
+    for e in range(8, 257, 8):
+        ks += [(1 << e) % c.n, ((1 << e) - 1) % c.n, ((1 << e) + 1) % c.n]
+    if curve == "k256":
+        lam = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
+        for m in range(1, 40):
+            for d in (-2, -1, 0, 1, 2):
+                ks += [(m * lam + d) % c.n, (c.n - m * lam + d) % c.n]
+    P = pyref.mul(c, rng.randrange(1, c.n), pyref.G(c))
+    for pt in (pyref.G(c), P):
+        xy, inf = pack_points([pt] * len(ks))
+        K = pack_scalars(ks)
+        oxy, oinf, st = _mul_batch(sim, curve, K, xy, inf)
+        assert st[0] == 0
+        rxy, rinf = ecref.mul_batch(curve, K, xy, inf, nthreads=os.cpu_count() or 4)
+        assert np.array_equal(oxy.reshape(-1), np.asarray(rxy).reshape(-1)) and np.array_equal(oinf, rinf)
+        got = unpack_points(oxy, oinf)
+        for i in list(range(0, 40)) + list(range(1500, 1540)) + list(range(len(ks) - 30, len(ks))):
+            assert got[i] == pyref.mul(c, ks[i], pt)
