@@ -278,3 +278,27 @@ def test_varbase_kernel_scalar_sweeps(sim, curve):
         got = unpack_points(oxy, oinf)
         for i in list(range(0, 40)) + list(range(1500, 1540)) + list(range(len(ks) - 30, len(ks))):
             assert got[i] == pyref.mul(c, ks[i], pt)
+
+
+@pytest.mark.parametrize("curve", ["k256", "p256"])
+def test_fixedbase_kernel_window_patterns(sim, fb_tables, curve):
+    """The fixed-base recoding uses signed odd 16-bit digits with a carry into the next window and one 2^256 entry:
+    sweep every window through its boundary values (0000, 0001, 7fff, 8000, 8001, ffff) with zero / all-ones / random
+    neighbours, plus small and near-order scalars, against the C oracle."""
+    c = pyref.CURVES[curve]
+    rng = random.Random(202)
+    ks = list(range(300)) + [c.n - i for i in range(1, 300)]
+    pats = (0x0000, 0x0001, 0x7FFF, 0x8000, 0x8001, 0xFFFF, 0xFFFE)
+    for w in range(16):
+        for v in pats:
+            for fill in (0, (1 << 256) - 1, rng.getrandbits(256)):
+                k = (fill & ~(0xFFFF << (16 * w))) | (v << (16 * w))
+                ks.append(k % c.n)
+    n = len(ks)
+    K = pack_scalars(ks)
+    oxy, oinf, st = np.zeros(64 * n, np.uint8), np.zeros(n, np.uint8), np.zeros(2, np.uint32)
+    sim.simk_mul_gen_batch(CID[curve], ctypes.c_size_t(n), _p(K), _p(fb_tables[curve]), _p(oxy), _p(oinf), _p(st))
+    assert st[0] == 0
+    rxy, rinf = ecref.mul_gen_batch(curve, K, nthreads=os.cpu_count() or 4)
+    assert np.array_equal(oxy, np.asarray(rxy).reshape(-1)) and np.array_equal(oinf, rinf)
+    assert [int(x) for x in oinf] == [int(k == 0) for k in ks]   # the identity exactly where k = 0
