@@ -280,6 +280,31 @@ class Engine:
         self._check(self.lib.ecg_decompress_batch(self._ctx, c, n, _ptr(sec1_33), _ptr(out_xy), _ptr(out_inf), _ptr(valid)))
         return out_xy.reshape(n, 64), out_inf, valid
 
+    @staticmethod
+    def sec1_compress(xy, inf=None):
+        """`GroupEncoding::to_bytes` / `to_sec1_point(true)` for a batch of affine outputs (primeorder/src/affine.rs:387-402):
+        33-byte records, tag 02/03 by the parity of y then x; the identity is 33 zero bytes.  Pure byte shuffling on
+        the host — the arithmetic (normalisation) already happened on the device."""
+        xy = np.ascontiguousarray(xy, dtype=np.uint8).reshape(-1, 64)
+        out = np.zeros((xy.shape[0], 33), np.uint8)
+        out[:, 0] = 2 + (xy[:, 63] & 1)
+        out[:, 1:] = xy[:, :32]
+        if inf is not None:
+            out[np.asarray(inf).reshape(-1) != 0] = 0
+        return out
+
+    def derive_public_keys(self, curve, secret_k, compressed=True):
+        """Public-key derivation batch: `PublicKey::from_secret_scalar` = k * G, SEC1-encoded (SURVEY 8(f) rank 3;
+        k256/src/schnorr/signing.rs:151 does the same for BIP340 keys).  Returns (records, inf)."""
+        xy, inf = self.mul_by_generator(curve, secret_k)
+        if compressed:
+            return self.sec1_compress(xy, inf), inf
+        out = np.zeros((xy.shape[0], 65), np.uint8)
+        out[:, 0] = 4
+        out[:, 1:] = xy
+        out[inf != 0] = 0
+        return out, inf
+
     def batch_normalize(self, curve, xyz):
         c = CURVE_IDS[curve]
         xyz = np.ascontiguousarray(xyz, dtype=np.uint8).reshape(-1)

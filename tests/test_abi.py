@@ -61,3 +61,22 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "ecref" not in txt and "pyref" not in txt and "oracle/" not in txt.replace("see oracle/", ""), f
+
+
+def test_sec1_compress_is_pure_byte_layout():
+    """Engine.sec1_compress needs no device: tag by y parity, x, identity = 33 zero bytes; inverse of the decompressor's input"""
+    import numpy as np
+    import ecgpu
+    import pyref
+
+    c = pyref.K256
+    pts = [pyref.mul(c, k, pyref.G(c)) for k in (1, 2, 3, 7)]
+    xy = np.frombuffer(b"".join(P[0].to_bytes(32, "big") + P[1].to_bytes(32, "big") for P in pts) + bytes(64), np.uint8).reshape(5, 64)
+    inf = np.array([0, 0, 0, 0, 1], np.uint8)
+    rec = ecgpu.Engine.sec1_compress(xy, inf)
+    assert rec.shape == (5, 33)
+    for r, P in zip(rec, pts):
+        assert r[0] == 2 + (P[1] & 1) and int.from_bytes(r[1:].tobytes(), "big") == P[0]
+    assert not rec[4].any()
+    # the generator's well-known compressed encoding
+    assert rec[0].tobytes().hex() == "0279be667ef9dcbbac55a06295ce870b07029bfcdb2dce28d959f2815b16f81798"

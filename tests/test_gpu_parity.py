@@ -707,3 +707,24 @@ def test_ecdsa_wycheproof_vectors(engine, curve):
     want = np.array([int(x[4]) for x in cases], np.uint8)
     assert np.array_equal(got, want), f"first difference at {int(np.flatnonzero(got != want)[0])}"
     assert want.sum() > 100 and (want == 0).sum() >= 20
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_public_key_derivation_round_trip(engine, curve):
+    """k*G, SEC1-compressed; decompressing the records gives the points back, and OpenSSL derives
+    the same keys."""
+    c = pyref.CURVES[curve]
+    rng = random.Random(404)
+    ks = [rng.randrange(1, c.n) for _ in range(200)]
+    rec, inf = engine.derive_public_keys(curve, pack_scalars(ks))
+    assert rec.shape == (200, 33) and not inf.any()
+    xy, dinf, valid = engine.decompress_batch(curve, rec)
+    assert valid.all() and not dinf.any()
+    gxy, _ = engine.mul_by_generator(curve, pack_scalars(ks))
+    assert np.array_equal(np.asarray(xy), np.asarray(gxy))
+    ser = pytest.importorskip("cryptography.hazmat.primitives.serialization")
+    ec = pytest.importorskip("cryptography.hazmat.primitives.asymmetric.ec")
+    oc = ec.SECP256K1() if curve == "k256" else ec.SECP256R1()
+    for i in range(0, 200, 23):
+        pub = ec.derive_private_key(ks[i], oc).public_key().public_bytes(ser.Encoding.X962, ser.PublicFormat.CompressedPoint)
+        assert pub == rec[i].tobytes()
