@@ -99,6 +99,62 @@ class Engine {
     return unpack(out, oinf);
   }
 
+  // ---- widening: verification, wire format, key agreement ----
+  using Bytes32 = std::array<uint8_t, 32>;
+  using Sig64 = std::array<uint8_t, 64>;
+  using Sec1Compressed = std::array<uint8_t, 33>;
+
+  // schnorr::VerifyingKey::verify_raw over a batch (k256/src/schnorr/verifying.rs:76-99); secp256k1 only
+  std::vector<bool> schnorr_verify(const std::vector<Bytes32>& pk_x, const std::vector<Bytes32>& msg, const std::vector<Sig64>& sig) {
+    size_t n = check_sizes(pk_x.size(), msg.size());
+    check_sizes(n, sig.size());
+    std::vector<uint8_t> valid(n);
+    check(ecg_schnorr_verify_batch(ctx_, n, reinterpret_cast<const uint8_t*>(pk_x.data()), reinterpret_cast<const uint8_t*>(msg.data()),
+                                   reinterpret_cast<const uint8_t*>(sig.data()), valid.data()));
+    return std::vector<bool>(valid.begin(), valid.end());
+  }
+  // ecdsa::VerifyingKey::verify_prehash over a batch (k256/src/ecdsa.rs:93-121); low_s_only = EcdsaCurve::NORMALIZE_S
+  std::vector<bool> ecdsa_verify_prehash(const std::vector<Bytes32>& z, const std::vector<Sig64>& sig, const std::vector<AffinePoint>& q,
+                                         bool low_s_only) {
+    size_t n = check_sizes(z.size(), sig.size());
+    check_sizes(n, q.size());
+    pack(q);
+    std::vector<uint8_t> valid(n);
+    check(ecg_ecdsa_verify_batch(ctx_, curve_, n, reinterpret_cast<const uint8_t*>(z.data()), reinterpret_cast<const uint8_t*>(sig.data()),
+                                 xy_.data(), low_s_only ? 1 : 0, valid.data()));
+    return std::vector<bool>(valid.begin(), valid.end());
+  }
+  // AffinePoint::decompress over a batch (primeorder/src/affine.rs:179-198); ok[i] = false where x is not on the curve
+  std::vector<AffinePoint> decompress(const std::vector<Sec1Compressed>& rec, std::vector<bool>* ok = nullptr) {
+    size_t n = rec.size();
+    std::vector<uint8_t> out(64 * n), oinf(n), valid(n);
+    check(ecg_decompress_batch(ctx_, curve_, n, reinterpret_cast<const uint8_t*>(rec.data()), out.data(), oinf.data(), valid.data()));
+    if (ok) ok->assign(valid.begin(), valid.end());
+    return unpack(out, oinf);
+  }
+  // to_sec1_point(true) / GroupEncoding::to_bytes (primeorder/src/affine.rs:387-402): byte layout only, no device work
+  static Sec1Compressed compress(const AffinePoint& p) {
+    Sec1Compressed r{};
+    if (p.infinity) return r;  // identity = 33 zero bytes
+    r[0] = 2 + (p.y[31] & 1);
+    std::copy(p.x.begin(), p.x.end(), r.begin() + 1);
+    return r;
+  }
+  // diffie_hellman (k256/src/ecdh.rs:46-60): x-coordinate of secret[i] * public[i]
+  std::vector<Bytes32> diffie_hellman(const std::vector<Scalar>& secret, const std::vector<AffinePoint>& pub) {
+    std::vector<AffinePoint> s = mul(pub, secret);
+    std::vector<Bytes32> r(s.size());
+    for (size_t i = 0; i < s.size(); i++) r[i] = s[i].x;
+    return r;
+  }
+  // PublicKey::from_secret_scalar over a batch, SEC1-compressed
+  std::vector<Sec1Compressed> derive_public_keys(const std::vector<Scalar>& secret) {
+    std::vector<AffinePoint> p = mul_by_generator(secret);
+    std::vector<Sec1Compressed> r(p.size());
+    for (size_t i = 0; i < p.size(); i++) r[i] = compress(p[i]);
+    return r;
+  }
+
   uint64_t kernel_launches() const { return ecg_kernel_launches(ctx_); }
 
  private:
