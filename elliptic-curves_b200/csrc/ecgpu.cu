@@ -428,16 +428,32 @@ static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
     for (uint32_t j = 0; j < FB_ENTRIES; j++) scalar_be_from_shifted(&hk[((size_t)i * FB_ENTRIES + j) * 32], 2ull * j + 1, FB_W * i, n_le);
   scalar_be_from_shifted(&hk[(np - 1) * 32], 1, 256, n_le);  // 2^256 mod n
   for (size_t i = 0; i < np; i++) memcpy(&hp[i * 64], g, 64);
+  // temporaries are released on every exit path; `table` is released unless it is handed to the DevState
+  struct Scratch {
+    void* p[8] = {nullptr};
+    ~Scratch() {
+      for (void* q : p)
+        if (q) cudaFree(q);
+    }
+  } tmp;
   uint8_t *dk = nullptr, *dpnt = nullptr, *dxy = nullptr, *dinf = nullptr;
   uint32_t *jac = nullptr, *scr = nullptr, *table = nullptr, *st = nullptr;
-  CU_TRY(ctx, cudaMalloc((void**)&dk, np * 32));
-  CU_TRY(ctx, cudaMalloc((void**)&dpnt, np * 64));
-  CU_TRY(ctx, cudaMalloc((void**)&dxy, np * 64));
-  CU_TRY(ctx, cudaMalloc((void**)&dinf, np));
-  CU_TRY(ctx, cudaMalloc((void**)&jac, np * 96));
-  CU_TRY(ctx, cudaMalloc((void**)&scr, np * 32));
-  CU_TRY(ctx, cudaMalloc((void**)&table, np * 64));
-  CU_TRY(ctx, cudaMalloc((void**)&st, 8));  // private status: building the table must not disturb a caller's validation state
+  CU_TRY(ctx, cudaMalloc(&tmp.p[0], np * 32));
+  CU_TRY(ctx, cudaMalloc(&tmp.p[1], np * 64));
+  CU_TRY(ctx, cudaMalloc(&tmp.p[2], np * 64));
+  CU_TRY(ctx, cudaMalloc(&tmp.p[3], np));
+  CU_TRY(ctx, cudaMalloc(&tmp.p[4], np * 96));
+  CU_TRY(ctx, cudaMalloc(&tmp.p[5], np * 32));
+  CU_TRY(ctx, cudaMalloc(&tmp.p[6], np * 64));
+  CU_TRY(ctx, cudaMalloc(&tmp.p[7], 8));  // private status: building the table must not disturb a caller's validation state
+  dk = (uint8_t*)tmp.p[0];
+  dpnt = (uint8_t*)tmp.p[1];
+  dxy = (uint8_t*)tmp.p[2];
+  dinf = (uint8_t*)tmp.p[3];
+  jac = (uint32_t*)tmp.p[4];
+  scr = (uint32_t*)tmp.p[5];
+  table = (uint32_t*)tmp.p[6];
+  st = (uint32_t*)tmp.p[7];
   CU_TRY(ctx, cudaMemsetAsync(st, 0, 8, L.s()));
   CU_TRY(ctx, cudaMemcpyAsync(dk, hk.data(), np * 32, cudaMemcpyHostToDevice, L.s()));
   CU_TRY(ctx, cudaMemcpyAsync(dpnt, hp.data(), np * 64, cudaMemcpyHostToDevice, L.s()));
@@ -448,7 +464,10 @@ static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
   ctx->timing = false;
   ecg_status rc = launch_varbase(ctx, L, curve, np, dp, jac, st, 0);
   ctx->timing = saved_timing;
-  if (rc != ECG_OK) return rc;
+  if (rc != ECG_OK) {
+    cudaStreamSynchronize(L.s());  // nothing may still be using the temporaries when they are freed
+    return rc;
+  }
   size_t want_threads = std::max<size_t>((np + 31) / 32, std::min<size_t>(np, (size_t)d.sm_count * 256));
   if (curve == ECG_SECP256K1) {
     normalize_kernel<FpK256><<<grid_for(want_threads, 256), 256, 0, L.s()>>>(jac, np, scr, dxy, dinf);
@@ -461,13 +480,7 @@ static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
   }
   LAUNCHED(ctx);
   CU_TRY(ctx, cudaStreamSynchronize(L.s()));
-  cudaFree(dk);
-  cudaFree(dpnt);
-  cudaFree(dxy);
-  cudaFree(dinf);
-  cudaFree(jac);
-  cudaFree(scr);
-  cudaFree(st);
+  tmp.p[6] = nullptr;  // keep the table
   // lane 1 (and any caller stream) may use the table from now on: it was completed with a full synchronize
   d.fb_table[curve] = table;
   return ECG_OK;
