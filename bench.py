@@ -466,7 +466,9 @@ def run_ours(args):
             "roofline": {"bound": "int32-imad", "achieved": ach_alg, "peak": imadw_peak, "unit": "IMAD/s", "frac": ach_alg / imadw_peak,
                          "traffic": traffic, "kernel_ms": dom_avg_ms, "imad_per_unit": survey_unit,
                          "model": "SURVEY.md 8(d) canonical algorithmic count; peak = measured IMAD.WIDE.U32 issue rate (this run)",
-                         "note": "a frac near 1 means the kernel needs fewer products than the canonical model, see roofline_int for executed instructions"},
+                         "note": ("SURVEY's canonical model counts more multiply-adds per unit than this kernel executes "
+                                  f"({survey_unit:.3g} vs {imadw_unit or 0:.3g}); frac is therefore an algorithmic-throughput ratio and can "
+                                  "approach or exceed 1. roofline_int is the fraction of the multiplier's issue rate actually used.")},
             "roofline_int": roofline_int,
             "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                              "peak_source": peak_src, "algorithmic_bytes_per_unit": ALGO_BYTES[op],
