@@ -311,6 +311,101 @@ ECG_KERNEL(128, 4)
   }
 }
 
+// The sum of one bucket (list entries offset[b] .. offset[b+1]) -> bkt (shared by both bucket kernels).
+template <class C>
+ECG_DEV void msm_bucket_sum(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ list, uint32_t lo, uint32_t hi, size_t b,
+                            size_t nb, uint32_t* __restrict__ bkt) {
+  typedef typename C::F F;
+  Jac acc;
+  F::set_zero(acc.X);
+  F::set_one(acc.Y);
+  F::set_zero(acc.Z);
+  if (lo < hi) {
+    uint32_t ent = list[lo];
+    Aff e, nx;
+    msm_load_point(e, pts, ent >> 1);
+    fe_cneg<F>(e.y, ent & 1u);
+    acc.X = e.x;
+    acc.Y = e.y;
+    F::set_one(acc.Z);
+    uint32_t nent = lo + 1 < hi ? list[lo + 1] : 0;
+    if (lo + 1 < hi) msm_load_point(nx, pts, nent >> 1);
+#pragma unroll 1
+    for (uint32_t i = lo + 1; i < hi; i++) {
+      e = nx;
+      ent = nent;
+      if (i + 1 < hi) {
+        nent = list[i + 1];
+        msm_load_point(nx, pts, nent >> 1);
+      }
+      fe_cneg<F>(e.y, ent & 1u);
+      jac_madd<F, C::A_IS_MINUS3>(acc, acc, e);
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    bkt[(size_t)w * nb + b] = acc.X.v[w];
+    bkt[(size_t)(8 + w) * nb + b] = acc.Y.v[w];
+    bkt[(size_t)(16 + w) * nb + b] = acc.Z.v[w];
+  }
+}
+
+// Variant of msm_bucket_kernel that balances the lanes of a warp (ECG_MSM_BUCKETS_PER_THREAD=K, K > 1; off by
+// default until measured).  Bucket sizes are Poisson-like (mean 32 at 2^21 terms), and a warp waits for its largest
+// bucket: max over 32 lanes ~ mean + 2 sigma = +35 %.  Here a block of 128 threads owns 128*K consecutive buckets,
+// orders them by size with a counting sort in shared memory (256 size classes, largest first) and processes them in K
+// rounds, thread t taking the (r*128 + t)-th largest: the 32 lanes of a warp get neighbours in that order, i.e.
+// buckets of (almost) equal size.  Results land in the same bkt slots, so everything downstream is unchanged.
+#define MSM_BS_BLOCK 128
+template <class C, int K>
+ECG_KERNEL(MSM_BS_BLOCK, 4)
+    msm_bucket_sorted_kernel(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ list, const uint32_t* __restrict__ offset,
+                             size_t nb, uint32_t* __restrict__ bkt) {
+  __shared__ uint32_t hist[256], start[256], part[MSM_BS_BLOCK];
+  __shared__ uint16_t order[MSM_BS_BLOCK * K];
+  const unsigned t = threadIdx.x;
+  const size_t base = (size_t)blockIdx.x * (MSM_BS_BLOCK * K);
+  hist[t] = 0;
+  hist[t + MSM_BS_BLOCK] = 0;
+  __syncthreads();
+  uint32_t cls[K];
+#pragma unroll
+  for (int i = 0; i < K; i++) {
+    size_t b = base + (size_t)i * MSM_BS_BLOCK + t;
+    uint32_t sz = b < nb ? offset[b + 1] - offset[b] : 0u;
+    cls[i] = 255u - (sz < 255u ? sz : 255u);  // class 0 = largest
+    atomicAdd(&hist[cls[i]], 1u);
+  }
+  __syncthreads();
+  // exclusive scan of the 256 class counts: per-thread pairs, one serial pass over 128 partials
+  uint32_t h0 = hist[2 * t], h1 = hist[2 * t + 1];
+  part[t] = h0 + h1;
+  __syncthreads();
+  if (t == 0) {
+    uint32_t run = 0;
+    for (int i = 0; i < MSM_BS_BLOCK; i++) {
+      uint32_t v = part[i];
+      part[i] = run;
+      run += v;
+    }
+  }
+  __syncthreads();
+  start[2 * t] = part[t];
+  start[2 * t + 1] = part[t] + h0;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < K; i++) {
+    uint32_t pos = atomicAdd(&start[cls[i]], 1u);
+    order[pos] = (uint16_t)(i * MSM_BS_BLOCK + t);
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int r = 0; r < K; r++) {
+    size_t b = base + order[r * MSM_BS_BLOCK + t];
+    if (b < nb) msm_bucket_sum<C>(pts, list, offset[b], offset[b + 1], b, nb, bkt);
+  }
+}
+
 ECG_DEV void msm_jload(Jac& p, const uint32_t* __restrict__ a, size_t n, size_t i) {
 #pragma unroll
   for (int w = 0; w < 8; w++) {

@@ -861,6 +861,13 @@ static size_t msm_max_terms() {
   return MSM_MAX_TERMS_DEFAULT;
 }
 
+// ECG_MSM_BUCKETS_PER_THREAD = 4 | 8 selects msm_bucket_sorted_kernel (experiment, default 1 = msm_bucket_kernel)
+static int msm_buckets_per_thread() {
+  const char* e = getenv("ECG_MSM_BUCKETS_PER_THREAD");
+  int v = e ? atoi(e) : 1;
+  return (v == 4 || v == 8) ? v : 1;
+}
+
 static MsmGeom msm_geometry(ecg_curve curve, size_t n) {
   MsmGeom g;
   bool glv = curve == ECG_SECP256K1;
@@ -953,7 +960,16 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
   msm_scatter_kernel<<<grid_for(nsub, 256), 256, 0, L.s()>>>(digits, nsub, g, offset, cursor, list);
   LAUNCHED(ctx);
   DOM_BEGIN(ctx, L);
-  msm_bucket_kernel<C><<<grid_for(nb, 128), 128, 0, L.s()>>>(pts, list, offset, nb, bkt);
+  switch (msm_buckets_per_thread()) {  // > 1: warp-balanced variant (ecg_msm.cuh), off unless the environment asks for it
+    case 8:
+      msm_bucket_sorted_kernel<C, 8><<<grid_for(nb, MSM_BS_BLOCK * 8), MSM_BS_BLOCK, 0, L.s()>>>(pts, list, offset, nb, bkt);
+      break;
+    case 4:
+      msm_bucket_sorted_kernel<C, 4><<<grid_for(nb, MSM_BS_BLOCK * 4), MSM_BS_BLOCK, 0, L.s()>>>(pts, list, offset, nb, bkt);
+      break;
+    default:
+      msm_bucket_kernel<C><<<grid_for(nb, 128), 128, 0, L.s()>>>(pts, list, offset, nb, bkt);
+  }
   LAUNCHED(ctx);
   DOM_END(ctx, L);
   // weighted reduction, level by level (ecg_msm.cuh)

@@ -480,7 +480,7 @@ static std::vector<uint32_t> simk_reduce_points(std::vector<uint32_t> a, size_t 
 
 template <class C, bool GLV>
 static bool simk_msm_run(const uint8_t* k, const uint8_t* pxy, const uint8_t* pinf, size_t n, const MsmGeom& g,
-                         uint32_t* status, std::vector<uint32_t>& result) {  // = msm_run; false = too skewed
+                         uint32_t* status, std::vector<uint32_t>& result, int bucket_k) {  // = msm_run; false = too skewed
   const size_t nsub = GLV ? 2 * n : n;
   const size_t nb = (size_t)g.W * g.nbw;
   std::vector<size_t> lens, nchs;
@@ -506,7 +506,14 @@ static bool simk_msm_run(const uint8_t* k, const uint8_t* pxy, const uint8_t* pi
   size_t avg = nsub / ((size_t)1 << (g.c - 1)) + 1;
   if ((size_t)*maxcnt > 4096 && (size_t)*maxcnt > 32 * avg) return false;
   sim_launch(nsub, 256, [&] { msm_scatter_kernel(digits.data(), nsub, g, offset.data(), cursor, list.data()); });
-  sim_launch(nb, 128, [&] { msm_bucket_kernel<C>(pts.data(), list.data(), offset.data(), nb, bkt.data()); });
+  if (bucket_k == 8)  // ECG_MSM_BUCKETS_PER_THREAD in the product: the warp-balanced variant (shared memory + barriers)
+    sim_launch_blocks((unsigned)((nb + MSM_BS_BLOCK * 8 - 1) / (MSM_BS_BLOCK * 8)), MSM_BS_BLOCK,
+                      [&] { msm_bucket_sorted_kernel<C, 8>(pts.data(), list.data(), offset.data(), nb, bkt.data()); });
+  else if (bucket_k == 4)
+    sim_launch_blocks((unsigned)((nb + MSM_BS_BLOCK * 4 - 1) / (MSM_BS_BLOCK * 4)), MSM_BS_BLOCK,
+                      [&] { msm_bucket_sorted_kernel<C, 4>(pts.data(), list.data(), offset.data(), nb, bkt.data()); });
+  else
+    sim_launch(nb, 128, [&] { msm_bucket_kernel<C>(pts.data(), list.data(), offset.data(), nb, bkt.data()); });
   std::vector<std::vector<uint32_t>> S(levels), X(levels);
   for (int l = 0; l < levels; l++) {
     S[l].assign((size_t)g.W * nchs[l] * 24, 0);
@@ -527,12 +534,12 @@ static bool simk_msm_run(const uint8_t* k, const uint8_t* pxy, const uint8_t* pi
 
 template <class C, bool GLV, bool IS_K256>
 static void simk_lincomb_t(int curve, size_t n, const uint8_t* k, const uint8_t* pxy, const uint8_t* pinf, size_t msm_min_terms,
-                           uint8_t* out_xy, uint8_t* out_inf, uint32_t* status, int* path) {
+                           uint8_t* out_xy, uint8_t* out_inf, uint32_t* status, int* path, int bucket_k) {
   std::vector<uint32_t> res;
   *path = 0;
   if (n >= msm_min_terms) {
     MsmGeom g = simk_msm_geometry(curve, n);
-    *path = simk_msm_run<C, GLV>(k, pxy, pinf, n, g, status, res) ? 1 : 2;
+    *path = simk_msm_run<C, GLV>(k, pxy, pinf, n, g, status, res, bucket_k) ? 1 : 2;
   }
   if (*path != 1) {  // per-term kernel + tree sum
     std::vector<uint32_t> jac(24 * n);
@@ -547,8 +554,8 @@ static void simk_lincomb_t(int curve, size_t n, const uint8_t* k, const uint8_t*
   simk_normalize<C>(res, 1, out_xy, out_inf);
 }
 
-extern "C" int simk_lincomb(int curve, size_t n, const uint8_t* k, const uint8_t* pxy, const uint8_t* pinf, size_t msm_min_terms,
-                            uint8_t* out_xy, uint8_t* out_inf, uint32_t* status, int* path) {
+extern "C" int simk_lincomb_k(int curve, size_t n, const uint8_t* k, const uint8_t* pxy, const uint8_t* pinf, size_t msm_min_terms,
+                              uint8_t* out_xy, uint8_t* out_inf, uint32_t* status, int* path, int bucket_k) {
   status[0] = 0;
   status[1] = 0xFFFFFFFFu;
   if (n == 0) {  // empty sum = identity
@@ -558,8 +565,12 @@ extern "C" int simk_lincomb(int curve, size_t n, const uint8_t* k, const uint8_t
     return 0;
   }
   if (curve == 0)
-    simk_lincomb_t<CurveK256, true, true>(curve, n, k, pxy, pinf, msm_min_terms, out_xy, out_inf, status, path);
+    simk_lincomb_t<CurveK256, true, true>(curve, n, k, pxy, pinf, msm_min_terms, out_xy, out_inf, status, path, bucket_k);
   else
-    simk_lincomb_t<CurveP256, false, false>(curve, n, k, pxy, pinf, msm_min_terms, out_xy, out_inf, status, path);
+    simk_lincomb_t<CurveP256, false, false>(curve, n, k, pxy, pinf, msm_min_terms, out_xy, out_inf, status, path, bucket_k);
   return 0;
+}
+extern "C" int simk_lincomb(int curve, size_t n, const uint8_t* k, const uint8_t* pxy, const uint8_t* pinf, size_t msm_min_terms,
+                            uint8_t* out_xy, uint8_t* out_inf, uint32_t* status, int* path) {
+  return simk_lincomb_k(curve, n, k, pxy, pinf, msm_min_terms, out_xy, out_inf, status, path, 1);
 }

@@ -302,3 +302,27 @@ def test_fixedbase_kernel_window_patterns(sim, fb_tables, curve):
     rxy, rinf = ecref.mul_gen_batch(curve, K, nthreads=os.cpu_count() or 4)
     assert np.array_equal(oxy, np.asarray(rxy).reshape(-1)) and np.array_equal(oinf, rinf)
     assert [int(x) for x in oinf] == [int(k == 0) for k in ks]   # the identity exactly where k = 0
+
+
+@pytest.mark.parametrize("curve", ["k256", "p256"])
+@pytest.mark.parametrize("bucket_k", [4, 8])
+def test_lincomb_warp_balanced_bucket_kernel(sim, curve, bucket_k):
+    """msm_bucket_sorted_kernel (ECG_MSM_BUCKETS_PER_THREAD = 4 | 8 in the product): a block orders its 128*K buckets by
+    size in shared memory; the sums must land in the same slots, so the lincomb result is unchanged."""
+    c = pyref.CURVES[curve]
+    rng = random.Random(500 + bucket_k)
+    for n in (300, 1100):
+        ks = [rng.randrange(c.n) for _ in range(n)]
+        ks[3] = 0
+        # a few popular points make some buckets much larger than others
+        pts = random_points(c, 40, seed=n + bucket_k) + [None]
+        Ps = [pts[min(rng.randrange(60), 40)] for _ in range(n)]
+        xy, inf = pack_points(Ps)
+        K = pack_scalars(ks)
+        oxy, oinf, stt = np.zeros(64, np.uint8), np.zeros(1, np.uint8), np.zeros(2, np.uint32)
+        path = ctypes.c_int(-1)
+        sim.simk_lincomb_k(CID[curve], ctypes.c_size_t(n), _p(K), _p(xy), _p(inf), ctypes.c_size_t(64), _p(oxy), _p(oinf), _p(stt),
+                           ctypes.byref(path), bucket_k)
+        assert stt[0] == 0 and path.value == 1
+        rxy, rinf = ecref.lincomb(curve, K, xy, inf, nthreads=4)
+        assert np.array_equal(oxy, np.asarray(rxy).reshape(-1)) and int(oinf[0]) == int(rinf)
