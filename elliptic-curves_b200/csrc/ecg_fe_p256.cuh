@@ -3,18 +3,21 @@
 // Replaces (same values, different representation) the reference's Montgomery-form field
 //   p256/src/arithmetic/field.rs:59-118 over p256/src/arithmetic/field/field64.rs:7-144 (add, sub,
 //   montgomery_reduce) and primefield/src/monty.rs:319-375.
-// Representation: plain integers (no Montgomery domain — there is no per-multiplication conversion to
-// pay for on a machine where the reduction is shifts and adds anyway), weakly reduced to [0, 2^256).
-// Reduction is the Solinas / FIPS 186-4 D.2.3 word recombination on 32-bit words followed by folding the
-// small signed overflow with 2^256 == K (mod p), K = 2^224 - 2^192 - 2^96 + 1.  No multiplier is used by
-// the reduction: the whole of it runs on the ALU pipe, concurrently with the next product's IMAD.WIDEs.
+// Representation (OPT bit 9, the default): the reference's own Montgomery domain, a*R mod p with R = 2^256, weakly
+// reduced to [0, 2^256).  p == -1 (mod 2^96), so the Montgomery factor of every 32-bit word is the word itself
+// (p' = 1, field64.rs:59-66) and the reduction `redc16` needs no multiplier: three rounds (96 + 96 + 64 bits) of
+// "add M * (p + 1) / 2^k" written as 32-bit carry chains — 59 add/sub instructions on the ALU pipe, against ~110 for
+// the Solinas / FIPS 186-4 D.2.3 word recombination (`reduce16`, kept behind OPT bit 9 = 0 for comparison in
+// tools/kbench.cu), which made the P-256 multiplier ALU-bound in round 1.  Conversions happen only at the boundary
+// (from_canonical = multiplication by R^2, to_canonical = one reduction).  2^256 == K (mod p),
+// K = 2^224 - 2^192 - 2^96 + 1, folds the carry-out of additions in either representation.
 #pragma once
 #include "ecg_prim.cuh"
 
 namespace ecg {
 
 #ifndef ECG_P256_OPT
-#define ECG_P256_OPT 3  // bit 0: dedicated squaring; bit 1: mul/sqr as real device functions (see ecg_fe_k256.cuh)
+#define ECG_P256_OPT 515  // bit 0: dedicated squaring; bit 1: mul/sqr as real device functions (see ecg_fe_k256.cuh); bit 9: Montgomery domain
 #endif
 #ifndef ECG_NOINLINE_D
 #if defined(__CUDA_ARCH__) || defined(__CUDACC__)
@@ -33,9 +36,15 @@ struct FpP256T {
 #pragma unroll
     for (int i = 0; i < 8; i++) r.v[i] = 0;
   }
+  static constexpr bool MONT = (OPT & 512) != 0;
+  // internal-form one: 1, or R mod p = K in the Montgomery domain
   ECG_D static void set_one(Fe& r) {
     set_zero(r);
     r.v[0] = 1;
+    if (MONT) {
+      r.v[3] = r.v[4] = r.v[5] = 0xFFFFFFFFu;
+      r.v[6] = 0xFFFFFFFEu;
+    }
   }
 
   // r += c*K for c in {0,1}; returns the carry out of bit 256.  K = {1,0,0,~0,~0,~0,~0-1,0}
@@ -208,8 +217,76 @@ struct FpP256T {
 #pragma unroll
     for (int i = 0; i < 8; i++) r.v[i] = o[i];
   }
+  // Montgomery reduction (OPT bit 9): r = t / 2^256 mod p (weakly reduced) for a 16-limb t < 2^512.
+  // field64.rs:83-123 does this one 64-bit word at a time with p' = 1; here the words are 32 bits and, because
+  // p == -1 (mod 2^96), three words are retired per round: with M = the low 96 bits of the running value,
+  //   (t + M*p) / 2^96 = t / 2^96 + M * (2^160 - 2^128 + 2^96 + 1)            [p + 1 = 2^256 - 2^224 + 2^192 + 2^96]
+  // and M * (2^64 - 2^32 + 1) < 2^160 is formed by one 3-instruction addition and one 4-instruction subtraction.
+  // Rounds: 96 + 96 + 64 bits.  The sum stays below 2^512 + 2^256 p, so the quotient is below 2^256 + p: one
+  // conditional fold with K brings it under 2^256.
+  ECG_D static void redc16(Fe& r, const uint32_t* t) {
+    uint32_t u[16];
+    uint32_t x2, x3, x4, n1, n2, n3, n4, ov;
+    // round A: M = t[0..2]
+    x2 = add_cc(t[2], t[0]);
+    x3 = addc_cc(t[1], 0u);
+    x4 = addc(t[2], 0u);
+    n1 = sub_cc(t[1], t[0]);
+    n2 = subc_cc(x2, t[1]);
+    n3 = subc_cc(x3, t[2]);
+    n4 = subc(x4, 0u);
+    u[3] = add_cc(t[3], t[0]);
+    u[4] = addc_cc(t[4], t[1]);
+    u[5] = addc_cc(t[5], t[2]);
+    u[6] = addc_cc(t[6], t[0]);
+    u[7] = addc_cc(t[7], n1);
+    u[8] = addc_cc(t[8], n2);
+    u[9] = addc_cc(t[9], n3);
+    u[10] = addc_cc(t[10], n4);
+#pragma unroll
+    for (int i = 11; i < 16; i++) u[i] = addc_cc(t[i], 0u);
+    ov = addc(0u, 0u);
+    // round B: M = u[3..5]
+    x2 = add_cc(u[5], u[3]);
+    x3 = addc_cc(u[4], 0u);
+    x4 = addc(u[5], 0u);
+    n1 = sub_cc(u[4], u[3]);
+    n2 = subc_cc(x2, u[4]);
+    n3 = subc_cc(x3, u[5]);
+    n4 = subc(x4, 0u);
+    uint32_t m0 = u[3], m1 = u[4], m2 = u[5];
+    u[6] = add_cc(u[6], m0);
+    u[7] = addc_cc(u[7], m1);
+    u[8] = addc_cc(u[8], m2);
+    u[9] = addc_cc(u[9], m0);
+    u[10] = addc_cc(u[10], n1);
+    u[11] = addc_cc(u[11], n2);
+    u[12] = addc_cc(u[12], n3);
+    u[13] = addc_cc(u[13], n4);
+    u[14] = addc_cc(u[14], 0u);
+    u[15] = addc_cc(u[15], 0u);
+    ov = addc(ov, 0u);
+    // round C: M = u[6..7] (64 bits): + M * (2^192 - 2^160 + 2^128 + 2^32) at word 8
+    m0 = u[6];
+    m1 = u[7];
+    n1 = sub_cc(m1, m0);
+    n2 = subc_cc(m0, m1);
+    n3 = subc(m1, 0u);
+    r.v[0] = u[8];
+    r.v[1] = add_cc(u[9], m0);
+    r.v[2] = addc_cc(u[10], m1);
+    r.v[3] = addc_cc(u[11], 0u);
+    r.v[4] = addc_cc(u[12], m0);
+    r.v[5] = addc_cc(u[13], n1);
+    r.v[6] = addc_cc(u[14], n2);
+    r.v[7] = addc_cc(u[15], n3);
+    ov = addc(ov, 0u);
+    (void)add_K(r.v, ov);
+  }
   ECG_D static void reduce(Fe& r, const uint32_t* t) {
-    if (OPT & 16)
+    if (MONT)
+      redc16(r, t);
+    else if (OPT & 16)
       reduce16_cols(r, t);
     else
       reduce16(r, t);
@@ -370,8 +447,33 @@ struct FpP256T {
     sqr_n(t, t, 2);
     mul(r, t, a);
   }
-  ECG_D static void from_canonical(Fe& r, const Fe& a) { r = a; }
-  ECG_D static void to_canonical(Fe& r, const Fe& a) { normalize(r, a); }
+  // boundary encoding: the C ABI speaks canonical integers.  Montgomery domain: in = a * R^2 / R, out = a / R
+  // (FieldElement::from_uint_unchecked / to_canonical, p256/src/arithmetic/field.rs:59-64, 94-96).
+  ECG_D static void from_canonical(Fe& r, const Fe& a) {
+    if (MONT) {
+      Fe r2;  // R^2 mod p (p256/src/arithmetic/field.rs:181-186)
+      r2.v[0] = 0x00000003u; r2.v[1] = 0x00000000u; r2.v[2] = 0xFFFFFFFFu; r2.v[3] = 0xFFFFFFFBu;
+      r2.v[4] = 0xFFFFFFFEu; r2.v[5] = 0xFFFFFFFFu; r2.v[6] = 0xFFFFFFFDu; r2.v[7] = 0x00000004u;
+      mul(r, a, r2);
+    } else {
+      r = a;
+    }
+  }
+  ECG_D static void to_canonical(Fe& r, const Fe& a) {
+    if (MONT) {
+      uint32_t t[16];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        t[i] = a.v[i];
+        t[8 + i] = 0;
+      }
+      Fe q;
+      redc16(q, t);
+      normalize(r, q);
+    } else {
+      normalize(r, a);
+    }
+  }
 };
 
 typedef FpP256T<ECG_P256_OPT> FpP256;

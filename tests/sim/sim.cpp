@@ -190,12 +190,18 @@ int sim_p256_fe_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     case 7: F::inv(r, x); break;
     case 8: r = x; break;
     case 9: F::mul_small(r, x, 8); break;
+    // boundary conversions (canonical in, canonical out): identity round trip, product, inverse
+    case 10: F::from_canonical(r, x); F::to_canonical(r, r); store_be32(out, r.v); return 0;
+    case 11: F::from_canonical(x, x); F::from_canonical(y, y); F::mul(r, x, y); F::to_canonical(r, r); store_be32(out, r.v); return 0;
+    case 12: F::from_canonical(x, x); F::inv(r, x); F::to_canonical(r, r); store_be32(out, r.v); return 0;
     default: return -1;
   }
   F::normalize(r, r);
   store_be32(out, r.v);
   return 0;
 }
+// 1 when FpP256's internal form is the Montgomery domain (ops 2, 3, 7 of sim_p256_fe_op then carry a factor R^-1 / R^2)
+int sim_p256_is_mont(void) { return FpP256::MONT ? 1 : 0; }
 }  // extern "C"
 template <class F, bool AM3>
 static int sim_generic_mul(const uint8_t* k_be, const uint8_t* P_xy, uint8_t* out_xy, uint8_t* out_inf) {
@@ -204,6 +210,8 @@ static int sim_generic_mul(const uint8_t* k_be, const uint8_t* P_xy, uint8_t* ou
   Aff P;
   load_be32(P.x.v, P_xy);
   load_be32(P.y.v, P_xy + 32);
+  F::from_canonical(P.x, P.x);
+  F::from_canonical(P.y, P.y);
   std::vector<uint32_t> tabmem(8 * 24);
   TabRefJ tab{tabmem.data(), 1};
   Jac r;
@@ -234,6 +242,8 @@ int sim_p256_on_curve(const uint8_t* P_xy) {
   Aff P;
   load_be32(P.x.v, P_xy);
   load_be32(P.y.v, P_xy + 32);
+  F::from_canonical(P.x, P.x);
+  F::from_canonical(P.y, P.y);
   Fe b;
   CurveP256::b_internal(b);
   return aff_on_curve<F, true>(P, b) ? 1 : 0;

@@ -31,9 +31,18 @@ def _feop(sim, curve, op, a, b=0):
     return int.from_bytes(out.raw, "big")
 
 
+def _mont(sim, curve):
+    """(R^-1, R^2) mod p when the curve's internal form is the Montgomery domain (raw values x stand for x/R), else (1, 1)"""
+    p = pyref.CURVES[curve].p
+    if curve == "p256" and sim.sim_p256_is_mont():
+        return pow(2**256, -1, p), pow(2**256, 2, p)
+    return 1, 1
+
+
 @pytest.mark.parametrize("curve", ["k256", "p256"])
 def test_field_ops_full_256bit_range(sim, curve):
     p = pyref.CURVES[curve].p
+    ri, r2 = _mont(sim, curve)
     rng = random.Random(7)
     edge = [0, 1, 2, p - 1, p, p + 1, 2**256 - 1, 2**256 - 2, 2**256 - p, 2**256 - p - 1, p - 2, (p + 1) // 2,
             2**255, 2**128, 2**224, 2**192, 2**96, 2**224 - 1, 2**256 - 2**224]
@@ -42,15 +51,22 @@ def test_field_ops_full_256bit_range(sim, curve):
         for b in rng.sample(vals, 8) + edge[:8]:
             assert _feop(sim, curve, 0, a, b) == (a + b) % p
             assert _feop(sim, curve, 1, a, b) == (a - b) % p
-            assert _feop(sim, curve, 2, a, b) == a * b % p
-        assert _feop(sim, curve, 3, a) == a * a % p
+            assert _feop(sim, curve, 2, a, b) == a * b * ri % p
+        assert _feop(sim, curve, 3, a) == a * a * ri % p
         assert _feop(sim, curve, 4, a) == (-a) % p
         assert _feop(sim, curve, 5, a) == a * pow(2, -1, p) % p
         assert _feop(sim, curve, 6, a) == 3 * a % p
         assert _feop(sim, curve, 9, a) == 8 * a % p
         assert _feop(sim, curve, 8, a) == a % p
     for a in vals[:30]:
-        assert _feop(sim, curve, 7, a) == (pow(a % p, -1, p) if a % p else 0)
+        assert _feop(sim, curve, 7, a) == (pow(a % p, -1, p) * r2 % p if a % p else 0)
+    if curve == "p256":  # boundary conversions: canonical in, canonical out
+        for a in [v % p for v in vals]:
+            assert _feop(sim, curve, 10, a) == a
+            b = rng.randrange(p)
+            assert _feop(sim, curve, 11, a, b) == a * b % p
+        for a in [v % p for v in vals[:12]]:
+            assert _feop(sim, curve, 12, a) == (pow(a, -1, p) if a else 0)
 
 
 def test_field_mul_extremes(sim):
@@ -59,7 +75,7 @@ def test_field_mul_extremes(sim):
     for a in xs:
         for b in xs:
             assert _feop(sim, "k256", 2, a, b) == a * b % pyref.K256.p
-            assert _feop(sim, "p256", 2, a, b) == a * b % pyref.P256.p
+            assert _feop(sim, "p256", 2, a, b) == a * b * _mont(sim, "p256")[0] % pyref.P256.p
 
 
 def test_field_mul_structured_stress(sim):
@@ -76,10 +92,11 @@ def test_field_mul_structured_stress(sim):
 
     for curve in ("k256", "p256"):
         p = pyref.CURVES[curve].p
+        ri = _mont(sim, curve)[0]
         for _ in range(3000):
             a, b = structured(), structured()
-            assert _feop(sim, curve, 2, a, b) == a * b % p
-            assert _feop(sim, curve, 3, a) == a * a % p
+            assert _feop(sim, curve, 2, a, b) == a * b * ri % p
+            assert _feop(sim, curve, 3, a) == a * a * ri % p
 
 
 def test_karatsuba_multiplier_variant(sim):

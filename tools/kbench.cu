@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(BLOCK, MINBLK) kb_generic(size_t n, uint32_t* 
   uint32_t k[8];
   Aff P;
   make_inputs(k, P, idx);
-  CurveP256::generator(P);
+  CurveP256T<F>::generator(P);
   Jac r;
   if (GLOBAL_TAB) {
     size_t slot = ((size_t)blockIdx.x % (148 * 8)) * BLOCK;
@@ -282,7 +282,16 @@ int main(int argc, char** argv) {
       run<FpK256T<263>, 128, 8, true>("v263 mul via memory       (128,8)", n, jac, gtab);
       run<FpK256T<259>, 128, 5, true>("v259 mul+sqr via memory   (128,5)", n, jac, gtab);
       run<FpK256T<259>, 128, 8, true>("v259 mul+sqr via memory   (128,8)", n, jac, gtab);
-      runp<FpP256T<3>, 128, 4, true>("p256 v3 base              (128,4)", n, jac, gtab);
+      runp<FpP256T<3>, 128, 4, true>("p256 v3 Solinas base      (128,4)", n, jac, gtab);
+      runp<FpP256T<515>, 128, 4, true>("p256 v515 Montgomery call (128,4)", n, jac, gtab);
+      runp<FpP256T<515>, 128, 5, true>("p256 v515 Montgomery call (128,5)", n, jac, gtab);
+      runp<FpP256T<519>, 128, 4, true>("p256 v519 Mont, sqr inl   (128,4)", n, jac, gtab);
+      runp<FpP256T<513>, 128, 4, true>("p256 v513 Mont, all inl   (128,4)", n, jac, gtab);
+      runp<FpP256T<771>, 128, 4, true>("p256 v771 Mont via mem    (128,4)", n, jac, gtab);
+      runp<FpP256T<771>, 128, 5, true>("p256 v771 Mont via mem    (128,5)", n, jac, gtab);
+      run_fmul<FpP256T<3>>("p256 fmul call Solinas");
+      run_fmul<FpP256T<515>>("p256 fmul call Montgomery");
+      run_fmul<FpP256T<513>>("p256 fmul inline Montgomery");
       runp<FpP256T<259>, 128, 4, true>("p256 v259 mul+sqr via mem (128,4)", n, jac, gtab);
       runp<FpP256T<259>, 128, 5, true>("p256 v259 mul+sqr via mem (128,5)", n, jac, gtab);
       runp<FpP256T<259>, 128, 6, true>("p256 v259 mul+sqr via mem (128,6)", n, jac, gtab);
