@@ -326,9 +326,8 @@ def run_ours(args):
 
             eng.lincomb_partial_ptr(curve, n, kd.data_ptr(), pd.data_ptr(), 0, part_d.data_ptr())
             dist.all_gather_into_tensor(parts_d, part_d)
-            if rank == 0:
-                xy, inf = host_eng.point_sum(curve, parts_d.cpu().numpy())
-                lincomb_result[0] = (xy, inf)
+            if rank == 0:  # the `world` partial points are summed where the all_gather left them: no host staging
+                eng.point_sum_ptr(curve, world, parts_d.data_ptr(), oxy.data_ptr(), oinf.data_ptr())
 
     def step_host():
         k_np, o_np, oi_np = k_host.numpy(), out_host.numpy(), oinf_host.numpy()

@@ -24,6 +24,7 @@ using namespace ecg;
 // error flags written by kernels into status[0]; status[1] = smallest offending index
 #define ERRF_SCALAR 1u
 #define ERRF_POINT 2u
+#define ERRF_SKEW 4u /* not an error: the bucket method declined a skewed input (MSM_SKEW_FLAG, ecg_msm.cuh) */
 
 ECG_DEV void report_error(uint32_t* status, uint32_t flag, size_t idx) {
   atomicOr(&status[0], flag);

@@ -266,13 +266,34 @@ ECG_DEV void msm_load_point(Aff& e, const uint32_t* __restrict__ pts, uint32_t j
   e.y.v[4] = d.x; e.y.v[5] = d.y; e.y.v[6] = d.z; e.y.v[7] = d.w;
 }
 
+// Skew guard, decided on the device (no host round trip in the middle of a call): one bucket thread adds its points
+// serially, so an input that piles thousands of terms into one bucket (e.g. many identical terms) would serialise the
+// whole accumulation.  When the largest bucket population (written by msm_scan_partial_kernel) exceeds both limits the
+// bucket kernels do nothing except raise MSM_SKEW_FLAG in status[0]; the host sees the flag when the call finishes and
+// repeats the call on the per-term path, whose cost does not depend on the data.
+#define MSM_SKEW_FLAG 4u
+struct MsmSkew {
+  const uint32_t* maxcnt;
+  uint32_t limit_abs, limit_rel;
+  uint32_t* status;
+};
+ECG_DEV bool msm_skewed(const MsmSkew& sk, bool reporter) {
+  uint32_t m = *sk.maxcnt;
+  if (m > sk.limit_abs && m > sk.limit_rel) {
+    if (reporter) atomicOr(&sk.status[0], MSM_SKEW_FLAG);
+    return true;
+  }
+  return false;
+}
+
 // One thread per bucket: B = sum of its (signed) points.  bkt: SoA Jacobian over nb = W*nbw buckets.
 template <class C>
 ECG_KERNEL(128, 4)
     msm_bucket_kernel(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ list, const uint32_t* __restrict__ offset,
-                      size_t nb, uint32_t* __restrict__ bkt) {
+                      size_t nb, uint32_t* __restrict__ bkt, MsmSkew sk) {
   typedef typename C::F F;
   size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (msm_skewed(sk, b == 0)) return;
   if (b >= nb) return;
   uint32_t lo = offset[b], hi = offset[b + 1];
   Jac acc;
@@ -360,11 +381,12 @@ ECG_DEV void msm_bucket_sum(const uint32_t* __restrict__ pts, const uint32_t* __
 template <class C, int K>
 ECG_KERNEL(MSM_BS_BLOCK, 4)
     msm_bucket_sorted_kernel(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ list, const uint32_t* __restrict__ offset,
-                             size_t nb, uint32_t* __restrict__ bkt) {
+                             size_t nb, uint32_t* __restrict__ bkt, MsmSkew sk) {
   __shared__ uint32_t hist[256], start[256], part[MSM_BS_BLOCK];
   __shared__ uint16_t order[MSM_BS_BLOCK * K];
   const unsigned t = threadIdx.x;
   const size_t base = (size_t)blockIdx.x * (MSM_BS_BLOCK * K);
+  if (msm_skewed(sk, blockIdx.x == 0 && t == 0)) return;  // block-uniform: every thread takes the same exit
   hist[t] = 0;
   hist[t + MSM_BS_BLOCK] = 0;
   __syncthreads();

@@ -34,11 +34,12 @@ struct Lane {
   void* buf[B_COUNT] = {nullptr};
   size_t cap[B_COUNT] = {0};
   uint32_t* status = nullptr;    // 2 words: error flags, smallest offending index
-  uint32_t* h_status = nullptr;  // pinned
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // bracket the dominant kernel of the last call (ecg_timing)
-  bool ev_pending = false;
+  uint32_t* h_status = nullptr;  // pinned: 2 status words, then 96 bytes for one exported point (h_point())
+  std::vector<cudaEvent_t> evs;  // event pairs bracketing the dominant kernel of every chunk of the current call (ecg_timing)
+  size_t ev_used = 0;            // events of `evs` recorded by the current call (2 per chunk)
   bool used = false;  // touched by the current call
   cudaStream_t s() const { return use_user_stream ? user_stream : stream; }
+  uint8_t* h_point() const { return reinterpret_cast<uint8_t*>(h_status + 2); }
 };
 struct DevState {
   int dev = 0;
@@ -56,6 +57,7 @@ struct ecg_ctx {
   bool timing = false;    // ecg_timing_enable
   double dom_ms_sum = 0;  // accumulated device time of the dominant kernel (max over devices per call)
   uint64_t dom_calls = 0;
+  bool skew = false;  // set by finish(): the bucket method declined a skewed input (MSM_SKEW_FLAG), the caller repeats per term
   bool devptr() const { return (flags & ECG_FLAG_DEVICE_PTRS) != 0; }
 };
 
@@ -80,17 +82,20 @@ struct ecg_ctx {
     CU_TRY(ctx, cudaGetLastError()); \
   } while (0)
 // CUDA events around the dominant kernel of a call, on the launching stream (bench.py's roofline numerator)
-#define DOM_BEGIN(ctx, L)                                              \
-  do {                                                                 \
-    if ((ctx)->timing) CU_TRY(ctx, cudaEventRecord((L).ev0, (L).s())); \
-  } while (0)
-#define DOM_END(ctx, L)                                  \
-  do {                                                   \
-    if ((ctx)->timing) {                                 \
-      CU_TRY(ctx, cudaEventRecord((L).ev1, (L).s()));    \
-      (L).ev_pending = true;                             \
-    }                                                    \
-  } while (0)
+// (one pair per chunk: a call cut into several chunks per lane accumulates all of them in finish())
+static ecg_status dom_record(ecg_ctx* ctx, Lane& L) {
+  if (!ctx->timing) return ECG_OK;
+  if (L.ev_used == L.evs.size()) {
+    cudaEvent_t e = nullptr;
+    CU_TRY(ctx, cudaEventCreate(&e));
+    L.evs.push_back(e);
+  }
+  CU_TRY(ctx, cudaEventRecord(L.evs[L.ev_used], L.s()));
+  L.ev_used++;
+  return ECG_OK;
+}
+#define DOM_BEGIN(ctx, L) ST_TRY(dom_record(ctx, L))
+#define DOM_END(ctx, L) ST_TRY(dom_record(ctx, L))
 
 static ecg_status ensure(ecg_ctx* ctx, Lane& L, int which, size_t bytes) {
   if (bytes <= L.cap[which]) return ECG_OK;
@@ -131,8 +136,7 @@ extern "C" ecg_status ecg_ctx_create(const int* device_ids, int n_devices, unsig
     for (int l = 0; ok && l < 2; l++) {
       Lane& L = d.lane[l];
       ok = cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) == cudaSuccess &&
-           cudaMalloc((void**)&L.status, 8) == cudaSuccess && cudaMallocHost((void**)&L.h_status, 8) == cudaSuccess &&
-           cudaEventCreate(&L.ev0) == cudaSuccess && cudaEventCreate(&L.ev1) == cudaSuccess;
+           cudaMalloc((void**)&L.status, 8) == cudaSuccess && cudaMallocHost((void**)&L.h_status, 8 + 96) == cudaSuccess;
     }
     if (!ok) {
       ecg_ctx_destroy(ctx);
@@ -159,8 +163,7 @@ extern "C" void ecg_ctx_destroy(ecg_ctx* ctx) {
         if (L.buf[i]) cudaFree(L.buf[i]);
       if (L.status) cudaFree(L.status);
       if (L.h_status) cudaFreeHost(L.h_status);
-      if (L.ev0) cudaEventDestroy(L.ev0);
-      if (L.ev1) cudaEventDestroy(L.ev1);
+      for (cudaEvent_t e : L.evs) cudaEventDestroy(e);
     }
     for (int i = 0; i < 2; i++)
       if (d.fb_table[i]) cudaFree(d.fb_table[i]);
@@ -288,13 +291,14 @@ static ecg_status finish(ecg_ctx* ctx) {
       CU_TRY(ctx, cudaMemcpyAsync(L.h_status, L.status, 8, cudaMemcpyDeviceToHost, L.s()));
       CU_TRY(ctx, cudaStreamSynchronize(L.s()));
       CU_TRY(ctx, cudaGetLastError());
-      if (L.ev_pending) {
+      for (size_t e = 0; e + 1 < L.ev_used; e += 2) {
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, L.ev0, L.ev1) == cudaSuccess) dev_ms += ms;
-        L.ev_pending = false;
+        if (cudaEventElapsedTime(&ms, L.evs[e], L.evs[e + 1]) == cudaSuccess) dev_ms += ms;
         any_timed = true;
       }
-      if (L.h_status[0] && (size_t)L.h_status[1] < first) {
+      L.ev_used = 0;
+      if (L.h_status[0] & ERRF_SKEW) ctx->skew = true;
+      if ((L.h_status[0] & (ERRF_SCALAR | ERRF_POINT)) && (size_t)L.h_status[1] < first) {
         first = L.h_status[1];
         rc = (L.h_status[0] & ERRF_POINT) ? ECG_ENOT_ON_CURVE : ECG_ESCALAR_RANGE;
       }
@@ -320,7 +324,7 @@ static ecg_status fail(ecg_ctx* ctx, ecg_status rc) {
         cudaSetDevice(d.dev);
         cudaStreamSynchronize(d.lane[l].s());
         d.lane[l].used = false;
-        d.lane[l].ev_pending = false;
+        d.lane[l].ev_used = 0;
       }
   ctx->err = saved;
   return rc;
@@ -421,13 +425,16 @@ static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
   if (d.fb_table[curve]) return ECG_OK;
   Lane& L = d.lane[0];
   const size_t np = FB_TABLE_POINTS;
-  std::vector<uint8_t> hk(np * 32), hp(np * 64);
+  // built in pieces of FB_PIECE points so that the lane's window-table slots (512-768 B per element) and the
+  // temporaries stay small: 2^16 points need 33-50 MB of slots instead of 268-402 MB for one launch over all of them
+  const size_t FB_PIECE = (size_t)1 << 16;
+  std::vector<uint8_t> hk(np * 32), hp(FB_PIECE * 64);
   const uint32_t* n_le = curve == ECG_SECP256K1 ? H_K256_N : H_P256_N;
   const uint8_t* g = curve == ECG_SECP256K1 ? H_K256_G : H_P256_G;
   for (int i = 0; i < FB_WINDOWS; i++)
     for (uint32_t j = 0; j < FB_ENTRIES; j++) scalar_be_from_shifted(&hk[((size_t)i * FB_ENTRIES + j) * 32], 2ull * j + 1, FB_W * i, n_le);
   scalar_be_from_shifted(&hk[(np - 1) * 32], 1, 256, n_le);  // 2^256 mod n
-  for (size_t i = 0; i < np; i++) memcpy(&hp[i * 64], g, 64);
+  for (size_t i = 0; i < FB_PIECE; i++) memcpy(&hp[i * 64], g, 64);
   // temporaries are released on every exit path; `table` is released unless it is handed to the DevState
   struct Scratch {
     void* p[8] = {nullptr};
@@ -436,52 +443,50 @@ static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
         if (q) cudaFree(q);
     }
   } tmp;
-  uint8_t *dk = nullptr, *dpnt = nullptr, *dxy = nullptr, *dinf = nullptr;
-  uint32_t *jac = nullptr, *scr = nullptr, *table = nullptr, *st = nullptr;
   CU_TRY(ctx, cudaMalloc(&tmp.p[0], np * 32));
-  CU_TRY(ctx, cudaMalloc(&tmp.p[1], np * 64));
-  CU_TRY(ctx, cudaMalloc(&tmp.p[2], np * 64));
-  CU_TRY(ctx, cudaMalloc(&tmp.p[3], np));
-  CU_TRY(ctx, cudaMalloc(&tmp.p[4], np * 96));
-  CU_TRY(ctx, cudaMalloc(&tmp.p[5], np * 32));
+  CU_TRY(ctx, cudaMalloc(&tmp.p[1], FB_PIECE * 64));
+  CU_TRY(ctx, cudaMalloc(&tmp.p[2], FB_PIECE * 64));
+  CU_TRY(ctx, cudaMalloc(&tmp.p[3], FB_PIECE));
+  CU_TRY(ctx, cudaMalloc(&tmp.p[4], FB_PIECE * 96));
+  CU_TRY(ctx, cudaMalloc(&tmp.p[5], FB_PIECE * 32));
   CU_TRY(ctx, cudaMalloc(&tmp.p[6], np * 64));
   CU_TRY(ctx, cudaMalloc(&tmp.p[7], 8));  // private status: building the table must not disturb a caller's validation state
-  dk = (uint8_t*)tmp.p[0];
-  dpnt = (uint8_t*)tmp.p[1];
-  dxy = (uint8_t*)tmp.p[2];
-  dinf = (uint8_t*)tmp.p[3];
-  jac = (uint32_t*)tmp.p[4];
-  scr = (uint32_t*)tmp.p[5];
-  table = (uint32_t*)tmp.p[6];
-  st = (uint32_t*)tmp.p[7];
+  uint8_t *dk = (uint8_t*)tmp.p[0], *dpnt = (uint8_t*)tmp.p[1], *dxy = (uint8_t*)tmp.p[2], *dinf = (uint8_t*)tmp.p[3];
+  uint32_t *jac = (uint32_t*)tmp.p[4], *scr = (uint32_t*)tmp.p[5], *table = (uint32_t*)tmp.p[6], *st = (uint32_t*)tmp.p[7];
   CU_TRY(ctx, cudaMemsetAsync(st, 0, 8, L.s()));
   CU_TRY(ctx, cudaMemcpyAsync(dk, hk.data(), np * 32, cudaMemcpyHostToDevice, L.s()));
-  CU_TRY(ctx, cudaMemcpyAsync(dpnt, hp.data(), np * 64, cudaMemcpyHostToDevice, L.s()));
-  DevPtrs dp;
-  dp.k = dk;
-  dp.p = dpnt;
+  CU_TRY(ctx, cudaMemcpyAsync(dpnt, hp.data(), FB_PIECE * 64, cudaMemcpyHostToDevice, L.s()));
   bool saved_timing = ctx->timing;
   ctx->timing = false;
-  ecg_status rc = launch_varbase(ctx, L, curve, np, dp, jac, st, 0);
+  ecg_status rc = ECG_OK;
+  for (size_t lo = 0; lo < np && rc == ECG_OK; lo += FB_PIECE) {
+    size_t cnt = std::min(FB_PIECE, np - lo);
+    DevPtrs dp;
+    dp.k = dk + 32 * lo;
+    dp.p = dpnt;
+    rc = launch_varbase(ctx, L, curve, cnt, dp, jac, st, lo);
+    if (rc != ECG_OK) break;
+    size_t want_threads = std::max<size_t>((cnt + 31) / 32, std::min<size_t>(cnt, (size_t)d.sm_count * 256));
+    if (curve == ECG_SECP256K1) {
+      normalize_kernel<FpK256><<<grid_for(want_threads, 256), 256, 0, L.s()>>>(jac, cnt, scr, dxy, dinf);
+      affine_to_table_kernel<CurveK256><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dxy, cnt, table + lo * 16);
+    } else {
+      normalize_kernel<FpP256><<<grid_for(want_threads, 256), 256, 0, L.s()>>>(jac, cnt, scr, dxy, dinf);
+      affine_to_table_kernel<CurveP256><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dxy, cnt, table + lo * 16);
+    }
+    ctx->launches += 2;
+    if (cudaGetLastError() != cudaSuccess) {
+      ctx->err = "fixed-base table build: kernel launch failed";
+      rc = ECG_ECUDA;
+    }
+  }
   ctx->timing = saved_timing;
-  if (rc != ECG_OK) {
-    cudaStreamSynchronize(L.s());  // nothing may still be using the temporaries when they are freed
-    return rc;
-  }
-  size_t want_threads = std::max<size_t>((np + 31) / 32, std::min<size_t>(np, (size_t)d.sm_count * 256));
-  if (curve == ECG_SECP256K1) {
-    normalize_kernel<FpK256><<<grid_for(want_threads, 256), 256, 0, L.s()>>>(jac, np, scr, dxy, dinf);
-    LAUNCHED(ctx);
-    affine_to_table_kernel<CurveK256><<<grid_for(np, 256), 256, 0, L.s()>>>(dxy, np, table);
-  } else {
-    normalize_kernel<FpP256><<<grid_for(want_threads, 256), 256, 0, L.s()>>>(jac, np, scr, dxy, dinf);
-    LAUNCHED(ctx);
-    affine_to_table_kernel<CurveP256><<<grid_for(np, 256), 256, 0, L.s()>>>(dxy, np, table);
-  }
-  LAUNCHED(ctx);
-  CU_TRY(ctx, cudaStreamSynchronize(L.s()));
+  // nothing may still be using the temporaries when they are freed; lane 1 (and any caller stream) may use the table
+  // from now on: it was completed with a full synchronize
+  cudaError_t se = cudaStreamSynchronize(L.s());
+  if (rc != ECG_OK) return rc;
+  CU_TRY(ctx, se);
   tmp.p[6] = nullptr;  // keep the table
-  // lane 1 (and any caller stream) may use the table from now on: it was completed with a full synchronize
   d.fb_table[curve] = table;
   return ECG_OK;
 }
@@ -645,7 +650,7 @@ static std::vector<Shard> chunk_schedule(size_t cnt, size_t wave) {
   return v;
 }
 
-static ecg_status run_batch(ecg_ctx* ctx, const BatchOp& op, size_t n) {
+static ecg_status run_batch_inner(ecg_ctx* ctx, const BatchOp& op, size_t n) {
   std::vector<Shard> shards = make_shards(n, ctx->devs.size());
   bool need_table = op.kind == BatchOp::MULGEN || op.kind == BatchOp::MULGENADD || op.kind == BatchOp::SCHNORR || op.kind == BatchOp::ECDSA;
   for (size_t i = 0; i < ctx->devs.size(); i++) {
@@ -682,6 +687,12 @@ static ecg_status run_batch(ecg_ctx* ctx, const BatchOp& op, size_t n) {
     }
   }
   return finish(ctx);
+}
+
+// every error exit (including CUDA failures inside finish()) leaves the lanes reset: fail() is idempotent
+static ecg_status run_batch(ecg_ctx* ctx, const BatchOp& op, size_t n) {
+  ecg_status st = run_batch_inner(ctx, op, n);
+  return st == ECG_OK ? st : fail(ctx, st);
 }
 
 extern "C" ecg_status ecg_mul_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
@@ -893,7 +904,8 @@ struct Carver {
   }
 };
 
-// *result == nullptr on return means "input too skewed for the bucket method, use the per-term path".
+// Everything is enqueued without waiting; if the input turns out too skewed for the bucket method the result is
+// garbage and finish() sets ctx->skew (the caller then repeats the call with per_term = true).
 template <class C, bool GLV>
 static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, size_t base, const MsmGeom& g, uint32_t** result) {
   const size_t nsub = GLV ? 2 * n : n;
@@ -946,29 +958,23 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
     msm_scan_final_kernel<<<sb, MSM_SCAN_BLOCK, 0, L.s()>>>(count, nb, blocksum, offset);
     LAUNCHED(ctx);
   }
-  {
-    // one bucket thread adds its points serially: refuse pathologically skewed inputs (e.g. thousands of identical
-    // terms) and let the caller use the per-term kernel, whose cost does not depend on the data
-    CU_TRY(ctx, cudaMemcpyAsync(L.h_status, maxcnt, 4, cudaMemcpyDeviceToHost, L.s()));
-    CU_TRY(ctx, cudaStreamSynchronize(L.s()));
-    size_t avg = nsub / ((size_t)1 << (g.c - 1)) + 1;
-    if ((size_t)L.h_status[0] > 4096 && (size_t)L.h_status[0] > 32 * avg) {
-      *result = nullptr;
-      return ECG_OK;
-    }
-  }
+  // one bucket thread adds its points serially: pathologically skewed inputs (e.g. thousands of identical terms) are
+  // declined by the bucket kernel itself (MsmSkew, ecg_msm.cuh) — no host round trip here; finish() reports the flag
+  // and the caller repeats the call on the per-term path, whose cost does not depend on the data
+  const size_t avg = nsub / ((size_t)1 << (g.c - 1)) + 1;
+  MsmSkew sk{maxcnt, 4096u, (uint32_t)std::min<size_t>(32 * avg, 0xFFFFFFFFu), L.status};
   msm_scatter_kernel<<<grid_for(nsub, 256), 256, 0, L.s()>>>(digits, nsub, g, offset, cursor, list);
   LAUNCHED(ctx);
   DOM_BEGIN(ctx, L);
   switch (msm_buckets_per_thread()) {  // > 1: warp-balanced variant (ecg_msm.cuh), off unless the environment asks for it
     case 8:
-      msm_bucket_sorted_kernel<C, 8><<<grid_for(nb, MSM_BS_BLOCK * 8), MSM_BS_BLOCK, 0, L.s()>>>(pts, list, offset, nb, bkt);
+      msm_bucket_sorted_kernel<C, 8><<<grid_for(nb, MSM_BS_BLOCK * 8), MSM_BS_BLOCK, 0, L.s()>>>(pts, list, offset, nb, bkt, sk);
       break;
     case 4:
-      msm_bucket_sorted_kernel<C, 4><<<grid_for(nb, MSM_BS_BLOCK * 4), MSM_BS_BLOCK, 0, L.s()>>>(pts, list, offset, nb, bkt);
+      msm_bucket_sorted_kernel<C, 4><<<grid_for(nb, MSM_BS_BLOCK * 4), MSM_BS_BLOCK, 0, L.s()>>>(pts, list, offset, nb, bkt, sk);
       break;
     default:
-      msm_bucket_kernel<C><<<grid_for(nb, 128), 128, 0, L.s()>>>(pts, list, offset, nb, bkt);
+      msm_bucket_kernel<C><<<grid_for(nb, 128), 128, 0, L.s()>>>(pts, list, offset, nb, bkt, sk);
   }
   LAUNCHED(ctx);
   DOM_END(ctx, L);
@@ -990,14 +996,14 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
 
 // one shard -> one Jacobian point left in *result (SoA with n = 1, i.e. 24 consecutive words), on lane 0
 static ecg_status lincomb_shard(ecg_ctx* ctx, DevState& d, ecg_curve curve, const Shard& sh, const uint8_t* k,
-                                const uint8_t* P_xy, const uint8_t* P_inf, uint32_t** result) {
+                                const uint8_t* P_xy, const uint8_t* P_inf, bool per_term, uint32_t** result) {
   Lane& L = d.lane[0];
   DevPtrs dp;
   ST_TRY(begin_lane(ctx, L));
   ST_TRY(stage_in(ctx, L, B_K, k, sh.off, sh.cnt, 32, &dp.k));
   ST_TRY(stage_in(ctx, L, B_P, P_xy, sh.off, sh.cnt, 64, &dp.p));
   ST_TRY(stage_in(ctx, L, B_INF, P_inf, sh.off, sh.cnt, 1, &dp.inf));
-  if (sh.cnt >= MSM_MIN_TERMS) {
+  if (sh.cnt >= MSM_MIN_TERMS && !per_term) {
     // bucket method, in pieces of at most MSM_MAX_TERMS terms whose partial sums are added at the end
     const size_t MSM_MAX_TERMS = msm_max_terms();
     size_t pieces = (sh.cnt + MSM_MAX_TERMS - 1) / MSM_MAX_TERMS;
@@ -1016,12 +1022,6 @@ static ecg_status lincomb_shard(ecg_ctx* ctx, DevState& d, ecg_curve curve, cons
         ST_TRY((msm_run<CurveK256, true>(ctx, L, q, cnt, sh.off + lo, g, &r1)));
       else
         ST_TRY((msm_run<CurveP256, false>(ctx, L, q, cnt, sh.off + lo, g, &r1)));
-      if (r1 == nullptr) {  // skewed input: per-term path for this piece
-        ST_TRY(ensure(ctx, L, B_FB1, cnt * 96));
-        ST_TRY(ensure(ctx, L, B_FB2, ((cnt + 31) / 32) * 96 + 256));
-        ST_TRY(launch_varbase(ctx, L, curve, cnt, q, (uint32_t*)L.buf[B_FB1], L.status, sh.off + lo));
-        ST_TRY(reduce_points_c(ctx, L, curve, (uint32_t*)L.buf[B_FB1], (uint32_t*)L.buf[B_FB2], cnt, &r1));
-      }
       if (pieces == 1) {
         *result = r1;
         return ECG_OK;
@@ -1032,10 +1032,33 @@ static ecg_status lincomb_shard(ecg_ctx* ctx, DevState& d, ecg_curve curve, cons
     }
     return reduce_points_c(ctx, L, curve, parts, (uint32_t*)L.buf[B_JAC2], pieces, result);
   }
-  ST_TRY(ensure(ctx, L, B_JAC, sh.cnt * 96));
-  ST_TRY(ensure(ctx, L, B_JAC2, ((sh.cnt + 31) / 32) * 96 + 96));
-  ST_TRY(launch_varbase(ctx, L, curve, sh.cnt, dp, (uint32_t*)L.buf[B_JAC], L.status, sh.off));
-  return reduce_points_c(ctx, L, curve, (uint32_t*)L.buf[B_JAC], (uint32_t*)L.buf[B_JAC2], sh.cnt, result);
+  // per-term path: one scalar multiplication per term in pieces of at most PT_CHUNK terms (bounds the window tables:
+  // 512-768 B per term), each piece tree-summed to one point, the piece sums added at the end
+  const size_t PT_CHUNK = (size_t)1 << 20;
+  const size_t pieces = (sh.cnt + PT_CHUNK - 1) / PT_CHUNK;
+  const size_t c0 = std::min(sh.cnt, PT_CHUNK);
+  ST_TRY(ensure(ctx, L, B_FB1, c0 * 96));
+  ST_TRY(ensure(ctx, L, B_FB2, ((c0 + 31) / 32) * 96 + 256));
+  ST_TRY(ensure(ctx, L, B_JAC, pieces * 96 + 96));
+  ST_TRY(ensure(ctx, L, B_JAC2, ((pieces + 31) / 32) * 96 + 96));
+  uint32_t* parts = (uint32_t*)L.buf[B_JAC];
+  for (size_t pc = 0; pc < pieces; pc++) {
+    size_t lo = pc * PT_CHUNK, cnt = std::min(PT_CHUNK, sh.cnt - lo);
+    DevPtrs q;
+    q.k = dp.k + 32 * lo;
+    q.p = dp.p + 64 * lo;
+    q.inf = dp.inf ? dp.inf + lo : nullptr;
+    uint32_t* r1 = nullptr;
+    ST_TRY(launch_varbase(ctx, L, curve, cnt, q, (uint32_t*)L.buf[B_FB1], L.status, sh.off + lo));
+    ST_TRY(reduce_points_c(ctx, L, curve, (uint32_t*)L.buf[B_FB1], (uint32_t*)L.buf[B_FB2], cnt, &r1));
+    if (pieces == 1) {
+      *result = r1;
+      return ECG_OK;
+    }
+    for (int w = 0; w < 24; w++)
+      CU_TRY(ctx, cudaMemcpyAsync(parts + (size_t)w * pieces + pc, r1 + w, 4, cudaMemcpyDeviceToDevice, L.s()));
+  }
+  return reduce_points_c(ctx, L, curve, parts, (uint32_t*)L.buf[B_JAC2], pieces, result);
 }
 
 static ecg_status export_point(ecg_ctx* ctx, Lane& L, ecg_curve curve, const uint32_t* jac1, uint8_t* dev_xyz) {
@@ -1044,6 +1067,24 @@ static ecg_status export_point(ecg_ctx* ctx, Lane& L, ecg_curve curve, const uin
   else
     export_jac_kernel<CurveP256><<<1, 128, 0, L.s()>>>(jac1, 1, dev_xyz);
   LAUNCHED(ctx);
+  return ECG_OK;
+}
+
+// One attempt at ecg_lincomb_partial (per_term = false: bucket method where it applies).
+static ecg_status lincomb_partial_attempt(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
+                                          const uint8_t* P_inf, uint8_t* out_xyz, bool per_term) {
+  DevState& d = ctx->devs[0];
+  Lane& L = d.lane[0];
+  Shard sh = {0, n};
+  uint32_t* res = nullptr;
+  ST_TRY(lincomb_shard(ctx, d, curve, sh, k, P_xy, P_inf, per_term, &res));
+  uint8_t* dst = out_xyz;
+  if (!ctx->devptr()) {
+    ST_TRY(ensure(ctx, L, B_AUX, 256));
+    dst = (uint8_t*)L.buf[B_AUX];
+  }
+  ST_TRY(export_point(ctx, L, curve, res, dst));
+  if (!ctx->devptr()) CU_TRY(ctx, cudaMemcpyAsync(out_xyz, dst, 96, cudaMemcpyDeviceToHost, L.s()));
   return ECG_OK;
 }
 
@@ -1059,7 +1100,6 @@ extern "C" ecg_status ecg_lincomb_partial(ecg_ctx* ctx, ecg_curve curve, size_t 
     return ECG_EINVAL;
   }
   DevState& d = ctx->devs[0];
-  Lane& L = d.lane[0];
   CU_TRY(ctx, cudaSetDevice(d.dev));
   if (n == 0) {  // empty sum = identity (0 : 1 : 0)
     uint8_t z[96];
@@ -1071,33 +1111,33 @@ extern "C" ecg_status ecg_lincomb_partial(ecg_ctx* ctx, ecg_curve curve, size_t 
       memcpy(out_xyz, z, 96);
     return ECG_OK;
   }
-  Shard sh = {0, n};
-  uint32_t* res = nullptr;
-  ecg_status st = lincomb_shard(ctx, d, curve, sh, k, P_xy, P_inf, &res);
-  if (st != ECG_OK) return fail(ctx, st);
-  uint8_t* dst = out_xyz;
-  if (!ctx->devptr()) {
-    if ((st = ensure(ctx, L, B_AUX, 256)) != ECG_OK) return fail(ctx, st);
-    dst = (uint8_t*)L.buf[B_AUX];
+  ctx->skew = false;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    ecg_status st = lincomb_partial_attempt(ctx, curve, n, k, P_xy, P_inf, out_xyz, attempt == 1);
+    if (st != ECG_OK) return fail(ctx, st);
+    st = finish(ctx);
+    if (st != ECG_OK || !ctx->skew) return st;
+    ctx->skew = false;  // the bucket method declined the input: once more, per term
   }
-  if ((st = export_point(ctx, L, curve, res, dst)) != ECG_OK) return fail(ctx, st);
-  if (!ctx->devptr()) CU_TRY(ctx, cudaMemcpyAsync(out_xyz, dst, 96, cudaMemcpyDeviceToHost, L.s()));
-  return finish(ctx);
+  return ECG_OK;
 }
 
-// m Jacobian points as host bytes -> affine sum (device 0 of the ctx, lane 0)
-static ecg_status point_sum_host(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* xyz, uint8_t* out_xy, uint8_t* out_inf) {
+// m Jacobian points (X||Y||Z bytes, host or device per the ctx flags) -> affine sum (device 0 of the ctx, lane 0).
+// Nothing is waited for: the caller finishes the lane.
+static ecg_status point_sum_enqueue(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* xyz, uint8_t* out_xy, uint8_t* out_inf,
+                                    bool xyz_on_host) {
   DevState& d = ctx->devs[0];
   Lane& L = d.lane[0];
   CU_TRY(ctx, cudaSetDevice(d.dev));
   ST_TRY(begin_lane(ctx, L));
-  ST_TRY(ensure(ctx, L, B_AUX, m * 96 + 256));
   ST_TRY(ensure(ctx, L, B_JAC, m * 96 + 96));
   ST_TRY(ensure(ctx, L, B_JAC2, ((m + 31) / 32) * 96 + 96));
-  ST_TRY(ensure(ctx, L, B_OUT, 64));
-  ST_TRY(ensure(ctx, L, B_OINF, 1));
-  uint8_t* dxyz = (uint8_t*)L.buf[B_AUX];
-  CU_TRY(ctx, cudaMemcpyAsync(dxyz, xyz, m * 96, cudaMemcpyHostToDevice, L.s()));
+  const uint8_t* dxyz = xyz;
+  if (xyz_on_host) {
+    ST_TRY(ensure(ctx, L, B_AUX, m * 96 + 256));
+    CU_TRY(ctx, cudaMemcpyAsync(L.buf[B_AUX], xyz, m * 96, cudaMemcpyHostToDevice, L.s()));
+    dxyz = (const uint8_t*)L.buf[B_AUX];
+  }
   uint32_t* jac = (uint32_t*)L.buf[B_JAC];
   if (curve == ECG_SECP256K1)
     import_jac_kernel<CurveK256><<<grid_for(m, 256), 256, 0, L.s()>>>(dxyz, m, jac, L.status, 0);
@@ -1106,23 +1146,75 @@ static ecg_status point_sum_host(ecg_ctx* ctx, ecg_curve curve, size_t m, const 
   LAUNCHED(ctx);
   uint32_t* res = nullptr;
   ST_TRY(reduce_points_c(ctx, L, curve, jac, (uint32_t*)L.buf[B_JAC2], m, &res));
-  ST_TRY(launch_norm(ctx, d, L, curve, 1, res, (uint8_t*)L.buf[B_OUT], (uint8_t*)L.buf[B_OINF]));
-  CU_TRY(ctx, cudaMemcpyAsync(out_xy, L.buf[B_OUT], 64, cudaMemcpyDeviceToHost, L.s()));
-  CU_TRY(ctx, cudaMemcpyAsync(out_inf, L.buf[B_OINF], 1, cudaMemcpyDeviceToHost, L.s()));
-  return finish(ctx);
+  DevPtrs dp;
+  ST_TRY(stage_out(ctx, L, 0, 1, out_xy, 64, out_inf, dp));
+  ST_TRY(launch_norm(ctx, d, L, curve, 1, res, dp.out, dp.oinf));
+  return copy_back(ctx, L, 0, 1, out_xy, 64, out_inf, dp);
 }
 
 extern "C" ecg_status ecg_point_sum(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* xyz, uint8_t* out_xy,
                                     uint8_t* out_inf) {
   if (!ctx) return ECG_EINVAL;
   if (!out_xy || !out_inf || !curve_ok(curve) || (m > 0 && !xyz)) return ECG_EINVAL;
+  if (ctx->devptr() && ((reinterpret_cast<uintptr_t>(xyz) | reinterpret_cast<uintptr_t>(out_xy)) & 3)) {
+    ctx->err = "device pointer not 4-byte aligned";
+    return ECG_EINVAL;
+  }
   if (m == 0) {
-    memset(out_xy, 0, 64);
-    *out_inf = 1;
+    uint8_t z[65];
+    memset(z, 0, sizeof z);
+    if (ctx->devptr()) {
+      CU_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
+      CU_TRY(ctx, cudaMemcpy(out_xy, z, 64, cudaMemcpyHostToDevice));
+      z[0] = 1;
+      CU_TRY(ctx, cudaMemcpy(out_inf, z, 1, cudaMemcpyHostToDevice));
+    } else {
+      memcpy(out_xy, z, 64);
+      *out_inf = 1;
+    }
     return ECG_OK;
   }
-  ecg_status st = point_sum_host(ctx, curve, m, xyz, out_xy, out_inf);
-  return st == ECG_OK ? st : fail(ctx, st);
+  ecg_status st = point_sum_enqueue(ctx, curve, m, xyz, out_xy, out_inf, !ctx->devptr());
+  if (st != ECG_OK) return fail(ctx, st);
+  return finish(ctx);
+}
+
+// One attempt at ecg_lincomb: every device's shard is ENQUEUED (no waiting between devices), the per-device partial
+// points come back through pinned host memory, device 0 adds them.
+static ecg_status lincomb_attempt(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf,
+                                  uint8_t* out_xy, uint8_t* out_inf, bool per_term, std::vector<uint8_t>& partial) {
+  size_t nd = ctx->devs.size();
+  std::vector<Shard> shards = make_shards(n, nd);
+  if (nd == 1) {
+    DevState& d = ctx->devs[0];
+    Lane& L = d.lane[0];
+    CU_TRY(ctx, cudaSetDevice(d.dev));
+    uint32_t* res = nullptr;
+    ST_TRY(lincomb_shard(ctx, d, curve, shards[0], k, P_xy, P_inf, per_term, &res));
+    DevPtrs dp;
+    ST_TRY(stage_out(ctx, L, 0, 1, out_xy, 64, out_inf, dp));
+    ST_TRY(launch_norm(ctx, d, L, curve, 1, res, dp.out, dp.oinf));
+    return copy_back(ctx, L, 0, 1, out_xy, 64, out_inf, dp);
+  }
+  for (size_t i = 0; i < nd; i++) {
+    DevState& d = ctx->devs[i];
+    Lane& L = d.lane[0];
+    if (shards[i].cnt == 0) continue;
+    CU_TRY(ctx, cudaSetDevice(d.dev));
+    uint32_t* res = nullptr;
+    ST_TRY(lincomb_shard(ctx, d, curve, shards[i], k, P_xy, P_inf, per_term, &res));
+    ST_TRY(ensure(ctx, L, B_AUX, 256));
+    ST_TRY(export_point(ctx, L, curve, res, (uint8_t*)L.buf[B_AUX]));
+    CU_TRY(ctx, cudaMemcpyAsync(L.h_point(), L.buf[B_AUX], 96, cudaMemcpyDeviceToHost, L.s()));
+  }
+  ST_TRY(finish(ctx));
+  if (ctx->skew) return ECG_OK;  // the caller repeats per term
+  for (size_t i = 0; i < nd; i++) {
+    memset(&partial[i * 96], 0, 96);
+    partial[i * 96 + 63] = 1;  // identity (0:1:0) for empty shards
+    if (shards[i].cnt) memcpy(&partial[i * 96], ctx->devs[i].lane[0].h_point(), 96);
+  }
+  return point_sum_enqueue(ctx, curve, nd, partial.data(), out_xy, out_inf, true);
 }
 
 extern "C" ecg_status ecg_lincomb(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
@@ -1145,38 +1237,16 @@ extern "C" ecg_status ecg_lincomb(ecg_ctx* ctx, ecg_curve curve, size_t n, const
     }
     return ECG_OK;
   }
-  size_t nd = ctx->devs.size();
-  std::vector<Shard> shards = make_shards(n, nd);
-  ecg_status st;
-  if (nd == 1) {
-    DevState& d = ctx->devs[0];
-    Lane& L = d.lane[0];
-    CU_TRY(ctx, cudaSetDevice(d.dev));
-    uint32_t* res = nullptr;
-    if ((st = lincomb_shard(ctx, d, curve, shards[0], k, P_xy, P_inf, &res)) != ECG_OK) return fail(ctx, st);
-    DevPtrs dp;
-    if ((st = stage_out(ctx, L, 0, 1, out_xy, 64, out_inf, dp)) != ECG_OK) return fail(ctx, st);
-    if ((st = launch_norm(ctx, d, L, curve, 1, res, dp.out, dp.oinf)) != ECG_OK) return fail(ctx, st);
-    if ((st = copy_back(ctx, L, 0, 1, out_xy, 64, out_inf, dp)) != ECG_OK) return fail(ctx, st);
-    return finish(ctx);
+  std::vector<uint8_t> partial(ctx->devs.size() * 96, 0);
+  ctx->skew = false;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    ecg_status st = lincomb_attempt(ctx, curve, n, k, P_xy, P_inf, out_xy, out_inf, attempt == 1, partial);
+    if (st != ECG_OK) return fail(ctx, st);
+    st = finish(ctx);
+    if (st != ECG_OK || !ctx->skew) return st;
+    ctx->skew = false;  // the bucket method declined the input: once more, per term
   }
-  // several devices: one partial point per device, gathered through the host (96 B each), summed on device 0
-  std::vector<uint8_t> partial(nd * 96, 0);
-  for (size_t i = 0; i < nd; i++) {
-    DevState& d = ctx->devs[i];
-    Lane& L = d.lane[0];
-    partial[i * 96 + 63] = 1;  // identity (0:1:0) for empty shards
-    if (shards[i].cnt == 0) continue;
-    CU_TRY(ctx, cudaSetDevice(d.dev));
-    uint32_t* res = nullptr;
-    if ((st = lincomb_shard(ctx, d, curve, shards[i], k, P_xy, P_inf, &res)) != ECG_OK) return fail(ctx, st);
-    if ((st = ensure(ctx, L, B_AUX, 256)) != ECG_OK) return fail(ctx, st);
-    if ((st = export_point(ctx, L, curve, res, (uint8_t*)L.buf[B_AUX])) != ECG_OK) return fail(ctx, st);
-    CU_TRY(ctx, cudaMemcpyAsync(&partial[i * 96], L.buf[B_AUX], 96, cudaMemcpyDeviceToHost, L.s()));
-  }
-  if ((st = finish(ctx)) != ECG_OK) return st;
-  st = point_sum_host(ctx, curve, nd, partial.data(), out_xy, out_inf);
-  return st == ECG_OK ? st : fail(ctx, st);
+  return ECG_OK;
 }
 
 extern "C" ecg_status ecg_microbench(ecg_ctx* ctx, int which, int iters, double* ops_per_s, double* elapsed_ms) {

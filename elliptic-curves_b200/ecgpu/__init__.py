@@ -337,6 +337,10 @@ class Engine:
     def lincomb_ptr(self, curve, n, k, P_xy, P_inf, out_xy, out_inf):
         self._check(self.lib.ecg_lincomb(self._ctx, CURVE_IDS[curve], n, _ptr(k), _ptr(P_xy), _ptr(P_inf), _ptr(out_xy), _ptr(out_inf)))
 
+    def point_sum_ptr(self, curve, m, xyz, out_xy, out_inf):
+        """sum of m Jacobian points (m*96 bytes in device memory, e.g. an all_gather receive buffer) -> affine, on the device"""
+        self._check(self.lib.ecg_point_sum(self._ctx, CURVE_IDS[curve], m, _ptr(xyz), _ptr(out_xy), _ptr(out_inf)))
+
     def schnorr_verify_ptr(self, n, pk_x, msg32, sig64, valid):
         self._check(self.lib.ecg_schnorr_verify_batch(self._ctx, n, _ptr(pk_x), _ptr(msg32), _ptr(sig64), _ptr(valid)))
 

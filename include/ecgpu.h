@@ -97,8 +97,10 @@ ecg_status ecg_lincomb(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k
 ecg_status ecg_lincomb_partial(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
                                const uint8_t* P_inf, uint8_t out_xyz[96]);
 
-/* out = sum of m Jacobian points given as m*96 bytes (X||Y||Z), normalised to affine.  Always HOST
- * pointers (m is the number of ranks). */
+/* out = sum of m Jacobian points given as m*96 bytes (X||Y||Z), normalised to affine (m is the number of ranks).
+ * Pointers follow the ctx flags like every other entry: with ECG_FLAG_DEVICE_PTRS the points are read straight from
+ * device memory (e.g. the receive buffer of the all_gather that is config 5's one exchange step) and the 64 + 1 result
+ * bytes are written to device memory: import -> sum -> normalise, no host staging. */
 ecg_status ecg_point_sum(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* xyz, uint8_t out_xy[64],
                          uint8_t* out_inf);
 

@@ -514,16 +514,20 @@ static bool simk_msm_run(const uint8_t* k, const uint8_t* pxy, const uint8_t* pi
   sim_launch_blocks(1, 1024, [&] { msm_scan_top_kernel(blocksum.data(), sb, offset.data(), nb); });
   sim_launch_blocks(sb, MSM_SCAN_BLOCK, [&] { msm_scan_final_kernel(count.data(), nb, blocksum.data(), offset.data()); });
   size_t avg = nsub / ((size_t)1 << (g.c - 1)) + 1;
-  if ((size_t)*maxcnt > 4096 && (size_t)*maxcnt > 32 * avg) return false;
+  MsmSkew sk{maxcnt, 4096u, (uint32_t)std::min<size_t>(32 * avg, 0xFFFFFFFFu), status};
   sim_launch(nsub, 256, [&] { msm_scatter_kernel(digits.data(), nsub, g, offset.data(), cursor, list.data()); });
   if (bucket_k == 8)  // ECG_MSM_BUCKETS_PER_THREAD in the product: the warp-balanced variant (shared memory + barriers)
     sim_launch_blocks((unsigned)((nb + MSM_BS_BLOCK * 8 - 1) / (MSM_BS_BLOCK * 8)), MSM_BS_BLOCK,
-                      [&] { msm_bucket_sorted_kernel<C, 8>(pts.data(), list.data(), offset.data(), nb, bkt.data()); });
+                      [&] { msm_bucket_sorted_kernel<C, 8>(pts.data(), list.data(), offset.data(), nb, bkt.data(), sk); });
   else if (bucket_k == 4)
     sim_launch_blocks((unsigned)((nb + MSM_BS_BLOCK * 4 - 1) / (MSM_BS_BLOCK * 4)), MSM_BS_BLOCK,
-                      [&] { msm_bucket_sorted_kernel<C, 4>(pts.data(), list.data(), offset.data(), nb, bkt.data()); });
+                      [&] { msm_bucket_sorted_kernel<C, 4>(pts.data(), list.data(), offset.data(), nb, bkt.data(), sk); });
   else
-    sim_launch(nb, 128, [&] { msm_bucket_kernel<C>(pts.data(), list.data(), offset.data(), nb, bkt.data()); });
+    sim_launch(nb, 128, [&] { msm_bucket_kernel<C>(pts.data(), list.data(), offset.data(), nb, bkt.data(), sk); });
+  if (status[0] & MSM_SKEW_FLAG) {  // as finish() + the caller in ecgpu.cu: the flag is consumed, the per-term path runs
+    status[0] &= ~MSM_SKEW_FLAG;
+    return false;
+  }
   std::vector<std::vector<uint32_t>> S(levels), X(levels);
   for (int l = 0; l < levels; l++) {
     S[l].assign((size_t)g.W * nchs[l] * 24, 0);
