@@ -258,23 +258,83 @@ def max_over_ranks(x, world):
     return float(t.item())
 
 
-def run_ours(args):
+class Bench:
+    """What every measured config shares on this rank: engines, L2-flush buffer, integer peak, host core budget."""
+
+    def __init__(self, args):
+        import torch
+
+        import ecgpu
+
+        self.args = args
+        self.world, self.rank, self.local = dist_setup(args.gpus)
+        self.dev = torch.device("cuda", self.local)
+        self.host_eng = ecgpu.Engine([self.local])                       # host-buffer ABI (e2e)
+        self.eng = ecgpu.Engine([self.local], device_ptrs=True)          # device-resident ABI (value)
+        self.eng.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self.imadw_peak, _ = self.eng.microbench(0, 4000)                # IMAD.WIDE issue rate, this GPU, this run
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            self.hbm_peak, self.hbm_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        else:
+            self.hbm_peak, self.hbm_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+        self.traffic = {}
+        for name in ("r02_traffic.json", "r01_traffic.json"):
+            prof = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(prof):
+                for k, v in json.load(open(prof)).items():
+                    self.traffic.setdefault(k, v)
+        # host cores: the cgroup quota is shared by all ranks of the job; every rank checks its own outputs with its share
+        import ecref
+
+        self.cores, self.cores_why = host_cores()
+        k_probe = synth_scalars("k256", 1, 0, 4096)
+        self.threads_total = best_thread_count(lambda nt: ecref.mul_gen_batch("k256", k_probe, nthreads=max(1, nt // self.world)), self.cores)
+        self.threads = max(1, self.threads_total // self.world)
+
+    def all_true(self, flag):
+        """logical AND of a per-rank boolean"""
+        import torch
+
+        if self.world == 1:
+            return bool(flag)
+        import torch.distributed as dist
+
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def sum_over_ranks(self, x):
+        import torch
+
+        if self.world == 1:
+            return x
+        import torch.distributed as dist
+
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+
+def measure(B, workload, steps, warmup, sample_clocks):
+    """One BASELINE config on this job's ranks: device-resident rate (`value`), end-to-end rate through the host-buffer ABI,
+    bit-exact comparison of EVERY output with the CPU restatement, roofline.  Returns the record on rank 0, None elsewhere."""
     import torch
 
-    import ecgpu
+    import ecref
     import pyref
 
-    curve, op, logn, cfg_idx, unit = WORKLOADS[args.workload]
+    args, world, rank, dev, eng, host_eng = B.args, B.world, B.rank, B.dev, B.eng, B.host_eng
+    curve, op, logn, cfg_idx, unit = WORKLOADS[workload]
     if args.log2_batch:
         logn = args.log2_batch
     n = 1 << logn
-    world, rank, local = dist_setup(args.gpus)
-    dev = torch.device("cuda", local)
-    seed = SEEDS[args.workload]
+    seed = SEEDS[workload]
     start = rank * n
 
     # ---- synthetic inputs: scalars hashed on the host, points P_i = t_i*G made with the fixed-base kernel
-    host_eng = ecgpu.Engine([local])
+    a_host = None
     if op == "schnorr":
         pk_np, msg_np, sig_np = synth_schnorr(host_eng, seed, start, n)
         k_host = torch.from_numpy(pk_np).pin_memory()      # pk  (32 B)
@@ -282,51 +342,45 @@ def run_ours(args):
         p_host = torch.from_numpy(sig_np).pin_memory()     # sig (64 B)
     else:
         k_host = torch.from_numpy(synth_scalars(curve, seed, start, n)).pin_memory()
-        a_host = None
-    if op == "schnorr":
-        pass
-    elif op != "mulgen":
-        t_host = synth_point_scalars(curve, seed, start, n)
-        pxy, pinf = host_eng.mul_by_generator(curve, t_host)
-        assert not pinf.any()
-        p_host = torch.from_numpy(np.ascontiguousarray(pxy).reshape(-1)).pin_memory()
-    else:
-        p_host = None
+        if op != "mulgen":
+            t_host = synth_point_scalars(curve, seed, start, n)
+            pxy, pinf = host_eng.mul_by_generator(curve, t_host)
+            assert not pinf.any()
+            p_host = torch.from_numpy(np.ascontiguousarray(pxy).reshape(-1)).pin_memory()
+        else:
+            p_host = None
     out_bytes = {"lincomb": 64, "schnorr": n}.get(op, 64 * n)
+    n_inf = n if op != "lincomb" else 1
     out_host = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
-    oinf_host = torch.empty(n if op != "lincomb" else 1, dtype=torch.uint8).pin_memory()
-
+    oinf_host = torch.empty(n_inf, dtype=torch.uint8).pin_memory()
     kd = k_host.to(dev)
     pd = p_host.to(dev) if p_host is not None else None
     ad = a_host.to(dev) if a_host is not None else None
-    oxy = torch.empty(out_bytes, dtype=torch.uint8, device=dev)
-    oinf = torch.empty(n if op != "lincomb" else 1, dtype=torch.uint8, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    oxy = torch.zeros(out_bytes, dtype=torch.uint8, device=dev)
+    oinf = torch.zeros(n_inf, dtype=torch.uint8, device=dev)
     part_d = torch.empty(96, dtype=torch.uint8, device=dev)
     parts_d = torch.empty(96 * world, dtype=torch.uint8, device=dev)
-    lincomb_result = [None]
+    exchange = op == "lincomb" and world > 1
+    if exchange:
+        import torch.distributed as dist
 
-    eng = ecgpu.Engine([local], device_ptrs=True)
-    eng.set_stream(torch.cuda.current_stream().cuda_stream)
-
-    def step_dev():
-        flush.zero_()  # L2 flush between timed iterations
+    def step_dev(with_exchange=True):
+        B.flush.zero_()  # L2 flush between timed iterations
         if op == "mul":
             eng.mul_batch_ptr(curve, n, kd.data_ptr(), pd.data_ptr(), 0, oxy.data_ptr(), oinf.data_ptr())
         elif op == "mulgen":
             eng.mul_gen_batch_ptr(curve, n, kd.data_ptr(), oxy.data_ptr(), oinf.data_ptr())
         elif op == "schnorr":
             eng.schnorr_verify_ptr(n, kd.data_ptr(), ad.data_ptr(), pd.data_ptr(), oxy.data_ptr())
-        elif world == 1:
+        elif not (exchange and with_exchange):
             eng.lincomb_ptr(curve, n, kd.data_ptr(), pd.data_ptr(), 0, oxy.data_ptr(), oinf.data_ptr())
         else:
-            # config 5: every rank reduces its 2^21 terms to one Jacobian point, ONE exchange step (all_gather of
-            # 96 bytes per rank over NCCL), rank 0 adds the `world` partial points and normalises
-            import torch.distributed as dist
-
+            # config 5: every rank reduces its 2^21 terms to one Jacobian point; ONE exchange step (all_gather of 96 bytes
+            # per rank over NCCL/NVLink); rank 0 adds the `world` partial points where the all_gather left them and
+            # normalises — nothing of the exchange touches the host
             eng.lincomb_partial_ptr(curve, n, kd.data_ptr(), pd.data_ptr(), 0, part_d.data_ptr())
             dist.all_gather_into_tensor(parts_d, part_d)
-            if rank == 0:  # the `world` partial points are summed where the all_gather left them: no host staging
+            if rank == 0:
                 eng.point_sum_ptr(curve, world, parts_d.data_ptr(), oxy.data_ptr(), oinf.data_ptr())
 
     def step_host():
@@ -337,149 +391,350 @@ def run_ours(args):
             host_eng.mul_by_generator(curve, k_np, o_np, oi_np)
         elif op == "schnorr":
             o_np[:] = host_eng.schnorr_verify_batch(k_np, a_host.numpy(), p_host.numpy())
-        else:
+        elif not exchange:
             xy, inf = host_eng.lincomb(curve, k_np, p_host.numpy(), None)
             o_np[:] = xy
             oi_np[0] = inf
+        else:
+            part = host_eng.lincomb_partial(curve, k_np, p_host.numpy(), None)   # H2D of this rank's terms inside
+            part_d.copy_(torch.from_numpy(part), non_blocking=False)
+            dist.all_gather_into_tensor(parts_d, part_d)
+            if rank == 0:
+                eng.point_sum_ptr(curve, world, parts_d.data_ptr(), oxy.data_ptr(), oinf.data_ptr())
+                o_np[:] = oxy.cpu().numpy()                                   # D2H of the result
+                oi_np[0] = int(oinf.cpu()[0])
+
+    def timed(fn, k):
+        barrier_sync(world)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(k):
+            fn()
+        ev1.record()
+        barrier_sync(world)
+        return max_over_ranks(ev0.elapsed_time(ev1), world)
 
     # ---- device-resident timing (the `value`)
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(B.local) if (rank == 0 and sample_clocks) else None
     if sampler:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step_dev()
     eng.timing_enable(True)
     launches0 = eng.kernel_launches
-    barrier_sync(world)
     m0 = sampler.mark() if sampler else 0
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        step_dev()
-    ev1.record()
-    barrier_sync(world)
+    ms_total = timed(step_dev, steps)
     clocks = sampler.stop(m0, sampler.mark()) if sampler else None
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1), world)
     launches = eng.kernel_launches - launches0
     dom_ms, dom_calls = eng.timing_read()
     eng.timing_enable(False)
-    ms_per_step = ms_total / args.steps
-    value = world * n * args.steps / (ms_total * 1e-3)
+    ms_per_step = ms_total / steps
+    value = world * n * steps / (ms_total * 1e-3)
+    dev_xy, dev_inf = oxy.cpu().numpy().copy(), oinf.cpu().numpy().copy()
+    exch = None
+    if exchange:
+        # the same call without the exchange step (every rank reduces and normalises its own terms): what the NCCL
+        # exchange + the device-side point sum add to a step, measured in the same run
+        for _ in range(2):
+            step_dev(False)
+        ms_local = timed(lambda: step_dev(False), steps) / steps
+        exch = {"ms_per_step_with_exchange": ms_per_step, "ms_per_step_local_only": ms_local,
+                "exchange_efficiency": ms_local / ms_per_step,
+                "what": "all_gather_into_tensor of 96 B per rank (NCCL) + ecg_point_sum on rank 0 straight from the receive buffer"}
 
     # ---- end-to-end through the host-buffer ABI (pinned host memory, H2D + D2H inside the timed region)
     for _ in range(2):
         step_host()
     barrier_sync(world)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_host()
     barrier_sync(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
-    e2e_value = world * n * args.steps / e2e_s
+    e2e_value = world * n * steps / e2e_s
     h2d = 32 * n + (64 * n if op != "mulgen" else 0) + (32 * n if op == "schnorr" else 0)
     d2h = {"lincomb": 65, "schnorr": n}.get(op, 65 * n)
-
-    # ---- device result of the last device step == host-API result (same inputs)?
-    if op == "lincomb" and world > 1:
-        same = True  # the device path produced the GLOBAL sum (checked against the oracle below on rank 0)
+    if exchange:
+        same = True if rank != 0 else bool(np.array_equal(dev_xy, out_host.numpy()) and dev_inf[0] == oinf_host.numpy()[0])
     elif op == "schnorr":
-        same = bool(np.array_equal(oxy.cpu().numpy(), out_host.numpy())) and bool(out_host.numpy().all())
+        same = bool(np.array_equal(dev_xy, out_host.numpy())) and bool(out_host.numpy().all())
     else:
-        same = bool(np.array_equal(oxy.cpu().numpy(), out_host.numpy())) and bool(np.array_equal(oinf.cpu().numpy(), oinf_host.numpy()))
+        same = bool(np.array_equal(dev_xy, out_host.numpy())) and bool(np.array_equal(dev_inf, oinf_host.numpy()))
+    same = B.all_true(same)
 
-    line = None
-    if rank == 0:
-        # ---- integer-pipe peak measured live on this GPU
-        imadw_peak, _ = eng.microbench(0, 4000)
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            hbm_peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
-        else:
-            hbm_peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-        dom_avg_ms = dom_ms / max(dom_calls, 1)
-        achieved_gbs = ALGO_BYTES[op] * n / (dom_avg_ms * 1e-3) / 1e9
-        traffic = None
-        prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(prof):
-            traffic = json.load(open(prof)).get(args.workload)
-        imadw_unit = IMADW_PER_UNIT.get((curve, op))
-        roofline_int = None
-        if imadw_unit:
-            ach = imadw_unit * n / (dom_avg_ms * 1e-3)
-            roofline_int = {"bound": "int32 multiply issue (IMAD.WIDE.U32, half-rate FMA pipe)", "achieved": ach, "peak": imadw_peak,
-                            "unit": "IMAD.WIDE/s (executed)", "frac": ach / imadw_peak, "imad_wide_per_unit": imadw_unit,
-                            "peak_source": "ecg_microbench(0) in this run"}
-        survey_unit = SURVEY_IMAD_PER_UNIT.get((curve, op))
-        ach_alg = survey_unit * n / (dom_avg_ms * 1e-3)
-
-        # ---- CPU baseline: the oracle (C restatement of the reference path) on all host cores, bounded sample
-        import ecref
-
-        cores, cores_why = host_cores()
-        threads = best_thread_count(lambda nt: ecref.mul_gen_batch(curve, k_host.numpy()[:32 * 4096], nthreads=nt), cores)
-        ns = min(n, 1 << 18) if op != "mulgen" else min(n, 1 << 19)
-        k_s = k_host.numpy()[:32 * ns]
+    # ---- parity: EVERY output of this rank against the CPU restatement (oracle/ecref.c, constant-time `*` path), on this
+    #      rank's share of the host cores, outside the timed regions.  Its duration is the CPU baseline of this config.
+    nt = B.threads
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    if op == "schnorr":
+        # the reference's verify_raw = tagged hash + mul_by_generator_and_mul_add_vartime(s, -e, P) + checks; the CPU leg
+        # times the group-operation part on a sample; validity itself is known by construction (every signature is valid)
+        ns = min(n, 1 << 16)
+        s_s = np.ascontiguousarray(p_host.numpy().reshape(n, 64)[:ns, 32:]).reshape(-1)
+        pxy_s, _ = host_eng.mul_by_generator(curve, synth_point_scalars(curve, seed, start, ns))
         t0 = time.perf_counter()
-        if op == "schnorr":
-            # the reference's verify_raw = tagged hash + mul_by_generator_and_mul_add_vartime(s, -e, P) + checks;
-            # the sample times the group-operation part (a*G + b*P, oracle/ecref.c) on the same keys
-            s_s = np.ascontiguousarray(p_host.numpy().reshape(n, 64)[:ns, 32:]).reshape(-1)
-            pxy_s, _ = host_eng.mul_by_generator(curve, synth_point_scalars(curve, seed, start, ns))
-            t0 = time.perf_counter()
-            r_xy, r_inf = ecref.mul_gen_add_batch(curve, s_s, k_s, np.asarray(pxy_s).reshape(-1), None, nthreads=threads)
-        elif op == "mul":
-            r_xy, r_inf = ecref.mul_batch(curve, k_s, p_host.numpy()[:64 * ns], None, nthreads=threads, variant=0)
-        elif op == "mulgen":
-            r_xy, r_inf = ecref.mul_gen_batch(curve, k_s, nthreads=threads)
-        else:
-            r_xy, r_inf = ecref.lincomb(curve, k_s, p_host.numpy()[:64 * ns], None, nthreads=threads)
-        cpu_s = time.perf_counter() - t0
-        if op == "schnorr":
-            bit_exact = bool(out_host.numpy().all())  # every synthetic signature is valid by construction
-        elif op != "lincomb":
-            bit_exact = bool(np.array_equal(out_host.numpy()[:64 * ns], r_xy.reshape(-1))) and bool(np.array_equal(oinf_host.numpy()[:ns], r_inf))
-        else:
-            sub_xy, sub_inf = host_eng.lincomb(curve, k_s, p_host.numpy()[:64 * ns], None)
-            bit_exact = bool(np.array_equal(sub_xy, r_xy)) and sub_inf == r_inf
-        cpu_baseline = {"value": ns / cpu_s, "unit": unit, "cores": cores, "threads": threads, "cores_source": cores_why, "kind": "port",
-                        "sample": f"first 2^{ns.bit_length() - 1} units of the same workload, constant-time `*` path (oracle/ecref.c), {threads} threads on {cores} usable cores",
-                        "bit_exact_vs_gpu": bit_exact}
+        ecref.mul_gen_add_batch(curve, s_s, k_host.numpy()[:32 * ns], np.asarray(pxy_s).reshape(-1), None, nthreads=nt)
+        cpu_units, bit_exact = ns, bool(out_host.numpy().all())
+    elif op == "mul":
+        r_xy, r_inf = ecref.mul_batch(curve, k_host.numpy(), p_host.numpy(), None, nthreads=nt, variant=0)
+        cpu_units, bit_exact = n, bool(np.array_equal(out_host.numpy(), r_xy.reshape(-1)) and np.array_equal(oinf_host.numpy(), r_inf))
+    elif op == "mulgen":
+        r_xy, r_inf = ecref.mul_gen_batch(curve, k_host.numpy(), nthreads=nt)
+        cpu_units, bit_exact = n, bool(np.array_equal(out_host.numpy(), r_xy.reshape(-1)) and np.array_equal(oinf_host.numpy(), r_inf))
+    else:
+        r_xy, r_inf = ecref.lincomb(curve, k_host.numpy(), p_host.numpy(), None, nthreads=nt)   # this rank's terms
+        cpu_units = n
+        if not exchange:
+            bit_exact = bool(np.array_equal(out_host.numpy(), r_xy) and int(oinf_host.numpy()[0]) == r_inf)
+    cpu_s = time.perf_counter() - t0
+    if exchange:
+        # the oracle's per-rank sums travel to rank 0 (65 bytes each), which adds them with the big-integer model and
+        # compares with the GPU job's global result: 100 % of the 2^21 * world terms are covered
+        mine = torch.from_numpy(np.concatenate([r_xy.reshape(-1), np.array([r_inf], np.uint8)])).to(dev)
+        allp = torch.empty(65 * world, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allp, mine)
+        bit_exact = True
+        if rank == 0:
+            c = pyref.CURVES[curve]
+            acc = None
+            for r in range(world):
+                rec = allp[65 * r:65 * r + 65].cpu().numpy()
+                acc = pyref.add(c, acc, pyref.dec_point(rec[:64].tobytes(), int(rec[64])))
+            exp_xy, exp_inf = pyref.enc_point(acc)
+            bit_exact = bool(out_host.numpy().tobytes() == exp_xy and int(oinf_host.numpy()[0]) == exp_inf
+                             and dev_xy.tobytes() == exp_xy and int(dev_inf[0]) == exp_inf)
+    bit_exact = B.all_true(bit_exact)
+    cpu_rate = B.sum_over_ranks(cpu_units / cpu_s)
 
-        line = {
-            "metric": "scalar-mults/sec (var-base, batch) at 1/2/4/8 B200 vs reference Rust CPU" if op == "mul" else f"{unit} ({args.workload})",
-            "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32", "data": "synthetic",
-            "config": {"workload": (f"BASELINE.json configs[{cfg_idx}]: " if cfg_idx is not None else "widening step (not a BASELINE config): ")
-                                   + f"{args.workload}, batch 2^{logn} per GPU", "curve": curve,
-                       "batch_per_gpu": n, "inputs": "k_i, t_i = SHA-256(seed||tag||LE64(i)) mod n; P_i = t_i*G (SURVEY 8(d))",
-                       "l2": "256 MiB buffer written between timed iterations (L2 flush); working set 288 MiB > L2",
-                       "parallelism": f"batch sharded over {world} rank(s), no data-path collective"},
-            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": "host-buffer C ABI call, pinned host memory, copies inside the timed region", "matches_device_path": same},
-            "gpu_launches": launches,
-            "clocks": clocks,
-            # "neither HBM nor tensor cores - the INT32 multiply-add issue rate"; achieved =
-            # algorithmic IMADs per unit (SURVEY's canonical model) x units / dominant-kernel time; peak = IMAD.WIDE
-            # issue rate measured live by ecg_microbench(0) (MEASURED_PEAKS.json has no integer peak)
-            "roofline": {"bound": "int32-imad", "achieved": ach_alg, "peak": imadw_peak, "unit": "IMAD/s", "frac": ach_alg / imadw_peak,
-                         "traffic": traffic, "kernel_ms": dom_avg_ms, "imad_per_unit": survey_unit,
-                         "model": "SURVEY.md 8(d) canonical algorithmic count; peak = measured IMAD.WIDE.U32 issue rate (this run)",
-                         "note": ("SURVEY's canonical model counts more multiply-adds per unit than this kernel executes "
-                                  f"({survey_unit:.3g} vs {imadw_unit or 0:.3g}); frac is therefore an algorithmic-throughput ratio and can "
-                                  "approach or exceed 1. roofline_int is the fraction of the multiplier's issue rate actually used.")},
-            "roofline_int": roofline_int,
-            "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                             "peak_source": peak_src, "algorithmic_bytes_per_unit": ALGO_BYTES[op],
-                             "note": "reported because north_star asks for it; this path is not HBM bound"},
-            "cpu_baseline": cpu_baseline,
-        }
+    if rank != 0:
+        return None
+    dom_avg_ms = dom_ms / max(dom_calls, 1)
+    achieved_gbs = ALGO_BYTES[op] * n / (dom_avg_ms * 1e-3) / 1e9
+    imadw_unit = IMADW_PER_UNIT.get((curve, op))
+    roofline_int = None
+    if imadw_unit:
+        ach = imadw_unit * n / (dom_avg_ms * 1e-3)
+        roofline_int = {"bound": "int32 multiply issue (IMAD.WIDE.U32 on the fmaheavy pipe, 4 cycles per warp instruction)", "achieved": ach,
+                        "peak": B.imadw_peak, "unit": "IMAD.WIDE/s (executed)", "frac": ach / B.imadw_peak, "imad_wide_per_unit": imadw_unit,
+                        "peak_source": "ecg_microbench(0) in this run; independent record: profiles/r02_ncu_mb_imad_wide.json (fmaheavy 95.3 % busy)"}
+    survey_unit = SURVEY_IMAD_PER_UNIT.get((curve, op))
+    ach_alg = survey_unit * n / (dom_avg_ms * 1e-3)
+    covered = "every output" if op != "schnorr" else "every verdict (all signatures valid by construction)"
+    rec = {
+        "metric": "scalar-mults/sec (var-base, batch) at 1/2/4/8 B200 vs reference Rust CPU" if op == "mul" and curve == "k256" else f"{unit} ({workload})",
+        "value": value, "unit": unit, "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": (f"BASELINE.json configs[{cfg_idx}]: " if cfg_idx is not None else "widening step (not a BASELINE config): ")
+                               + f"{workload}, batch 2^{logn} per GPU", "curve": curve,
+                   "batch_per_gpu": n, "inputs": "k_i, t_i = SHA-256(seed||tag||LE64(i)) mod n; P_i = t_i*G (SURVEY 8(d))",
+                   "l2": "256 MiB buffer written between timed iterations (L2 flush); working set > L2",
+                   "parallelism": (f"terms sharded over {world} rank(s); one exchange step: all_gather of 96 B per rank over NCCL, "
+                                   "device-side sum of the partial points on rank 0" if exchange else
+                                   f"batch sharded over {world} rank(s), no data-path collective")},
+        "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": "host-buffer C ABI call, pinned host memory, copies inside the timed region", "matches_device_path": same},
+        "gpu_launches": launches,
+        "bit_exact": bit_exact,
+        "bit_exact_coverage": f"{covered} of every rank vs the CPU restatement (oracle/ecref.c), {world * cpu_units} units",
+        # "neither HBM nor tensor cores - the INT32 multiply-add issue rate"; achieved =
+        # algorithmic IMADs per unit (SURVEY's canonical model) x units / dominant-kernel time; peak = IMAD.WIDE
+        # issue rate measured live by ecg_microbench(0) (MEASURED_PEAKS.json has no integer peak)
+        "roofline": {"bound": "int32-imad", "achieved": ach_alg, "peak": B.imadw_peak, "unit": "IMAD/s", "frac": ach_alg / B.imadw_peak,
+                     "traffic": B.traffic.get(workload), "kernel_ms": dom_avg_ms, "imad_per_unit": survey_unit,
+                     "model": "SURVEY.md 8(d) canonical algorithmic count; peak = measured IMAD.WIDE.U32 issue rate (this run)",
+                     "note": ("SURVEY's canonical model counts more multiply-adds per unit than this kernel executes "
+                              f"({survey_unit:.3g} vs {imadw_unit or 0:.3g}); frac is therefore an algorithmic-throughput ratio and can "
+                              "approach or exceed 1. roofline_int is the fraction of the multiplier's issue rate actually used.")},
+        "roofline_int": roofline_int,
+        "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": B.hbm_peak, "unit": "GB/s", "frac": achieved_gbs / B.hbm_peak,
+                         "peak_source": B.hbm_src, "algorithmic_bytes_per_unit": ALGO_BYTES[op],
+                         "note": "reported because north_star asks for it; this path is not HBM bound"},
+        "cpu_baseline": {"value": cpu_rate, "unit": unit, "cores": B.cores, "threads": B.threads * world, "cores_source": B.cores_why, "kind": "port",
+                         "sample": (f"the whole workload ({world * cpu_units} units), constant-time `*` path (oracle/ecref.c), "
+                                    f"{B.threads} thread(s) per rank x {world} rank(s) on {B.cores} usable cores; the same pass is the parity check"),
+                         "bit_exact_vs_gpu": bit_exact},
+    }
+    if clocks is not None:
+        rec["clocks"] = clocks
+    if exch is not None:
+        rec["exchange"] = exch
+    return rec
+
+
+def config1_plumbing(B):
+    """BASELINE.json configs[0] / BASELINE.md section 3 row 1: single-thread latencies of the reference's benchmarked
+    operations (k256/benches/point.rs:62-104) on the CPU restatement, and the restatement's results on the reference's
+    own vectors.  No GPU in this record."""
+    import ecref
+    import pyref
+    from helpers import golden
+
+    out = {"workload": "BASELINE.json configs[0]: k256 ProjectivePoint::mul, scalar x G on CPU (plumbing)", "kind": "port", "threads": 1}
+    for curve in ("k256", "p256"):
+        c = pyref.CURVES[curve]
+        g = golden(curve)
+        ks = np.frombuffer(b"".join(bytes.fromhex(v["k"]) for v in g["group"]["mul"]), np.uint8)
+        want = b"".join(bytes.fromhex(v["x"]) + bytes.fromhex(v["y"]) for v in g["group"]["mul"])
+        Gxy, _ = pyref.enc_point(pyref.G(c))
+        m = ks.size // 32
+        Pg = np.frombuffer(Gxy * m, np.uint8)
+        ok = ecref.mul_gen_batch(curve, ks, nthreads=1)[0].tobytes() == want
+        ok = ok and ecref.mul_batch(curve, ks, Pg, None, nthreads=1, variant=0)[0].tobytes() == want
+        ok = ok and ecref.mul_batch(curve, ks, Pg, None, nthreads=1, variant=1)[0].tobytes() == want
+        # the bench scalars of k256/benches/point.rs:18-40 (and the P-256 twins), repeated: single-thread rate -> latency
+        bs = [bytes.fromhex(v["k"]) for v in g["bench"]["scalars"]]
+        reps = 1500
+        kk = np.frombuffer(b"".join(bs[i % len(bs)] for i in range(reps)), np.uint8)
+        PP = np.frombuffer(Gxy * reps, np.uint8)
+        lat = {}
+        for name, fn in (("mul (constant-time `*`)", lambda: ecref.mul_batch(curve, kk, PP, None, nthreads=1, variant=0)),
+                         ("mul_vartime", lambda: ecref.mul_batch(curve, kk, PP, None, nthreads=1, variant=1)),
+                         ("mul_by_generator", lambda: ecref.mul_gen_batch(curve, kk, nthreads=1)),
+                         ("lincomb (2 terms)", lambda: [ecref.lincomb(curve, kk[:64], PP[:128], None, nthreads=1) for _ in range(300)])):
+            fn()
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            lat[name] = {"us_per_op": dt / (300 if name.startswith("lincomb") else reps) * 1e6}
+        out[curve] = {"golden_mul_vectors": m, "golden_ok": bool(ok), "single_thread_latency": lat}
+    return out
+
+
+def strong_scaling(B):
+    """One host-resident batch of 2^LOG pairs held by rank 0, split over the job's GPUs two ways:
+       (a) NCCL: rank 0 uploads everything over ITS PCIe link, scatter / gather over NVLink (ecgpu.dist),
+       (b) one multi-device ecg_ctx in rank 0's process: every GPU pulls its slice over its own PCIe link.
+    Both are timed end to end (host buffers in, host buffers out); the results must be identical."""
+    import torch
+    import torch.distributed as dist
+
+    import ecgpu
+    import ecref
+    from ecgpu import dist as ecdist
+
+    world, rank = B.world, B.rank
+    logn = B.args.strong_log2
+    n = 1 << logn
+    rec = None
+    k = pxy = None
+    if rank == 0:
+        rng = np.random.default_rng(0xB2000006)
+        k = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        k[:, 0] &= 0x7F   # < 2^255 < n
+        t = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        t[:, 0] &= 0x7F
+        t[:, 31] |= 1     # non-zero
+        pxy, pinf = B.host_eng.mul_by_generator("k256", t.reshape(-1))
+        k = torch.from_numpy(k.reshape(-1)).pin_memory().numpy()
+        pxy = torch.from_numpy(np.ascontiguousarray(pxy).reshape(-1)).pin_memory().numpy()
+    reps = 3
+    times_a = []
+    out_a = None
+    for it in range(reps + 1):
+        barrier_sync(world)
+        t0 = time.perf_counter()
+        out_a = ecdist.mul_batch_distributed(B.eng, "k256", n, k, pxy, src=0)
+        barrier_sync(world)
+        if it:
+            times_a.append(time.perf_counter() - t0)
+    times_b = []
+    out_b = None
+    if rank == 0:
+        md = ecgpu.Engine(list(range(world)))
+        oxy = torch.empty(64 * n, dtype=torch.uint8).pin_memory().numpy()
+        oinf = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
+        for it in range(reps + 1):
+            t0 = time.perf_counter()
+            md.mul_batch("k256", k, pxy, None, oxy, oinf)
+            if it:
+                times_b.append(time.perf_counter() - t0)
+        out_b = (oxy, oinf)
+        md.close()
+    barrier_sync(world)
+    if rank == 0:
+        same = bool(np.array_equal(out_a[0], out_b[0]) and np.array_equal(out_a[1], out_b[1]))
+        ns = min(n, 1 << 17)
+        r_xy, r_inf = ecref.mul_batch("k256", np.concatenate([k[:32 * ns], k[-32 * ns:]]), np.concatenate([pxy[:64 * ns], pxy[-64 * ns:]]), None,
+                                      nthreads=B.threads_total, variant=0)
+        got = np.concatenate([out_b[0][:64 * ns], out_b[0][-64 * ns:]])
+        ok = bool(np.array_equal(got, r_xy.reshape(-1)))
+        ta, tb = min(times_a), min(times_b)
+        rec = {"workload": f"k256 var-base, ONE batch of 2^{logn} pairs in rank 0's pinned host memory, {world} GPUs (strong scaling)",
+               "nccl_scatter_gather": {"mults_per_s": n / ta, "ms": ta * 1e3,
+                                       "path": "rank 0 H2D (one PCIe link) -> dist.scatter over NVLink -> kernels -> dist.gather -> rank 0 D2H"},
+               "multi_device_ctx": {"mults_per_s": n / tb, "ms": tb * 1e3,
+                                    "path": "one ecg_ctx over all GPUs in rank 0's process: every GPU copies its own slice over its own PCIe link"},
+               "bytes_over_rank0_pcie": {"nccl": 161 * n, "multi_device_ctx": 161 * n // world},
+               "limiter": "rank 0's PCIe link for the NCCL variant (all 161 B/pair cross it); per-GPU PCIe + the host memory system for the multi-device ctx",
+               "results_identical": same, "bit_exact_sample": ok,
+               "bit_exact_coverage": f"first and last 2^{ns.bit_length() - 1} pairs vs oracle/ecref.c; (a) == (b) on all 2^{logn} outputs"}
+    return rec
+
+
+def multi_device_parity(B):
+    """tests/test_gpu_parity.py::test_multi_device_ctx_shards_the_batch needs >= 2 GPUs, which the 1-GPU test box does not
+    have: the same check runs here whenever the bench is launched on several GPUs (rank 0, every visible device)."""
+    import ecgpu
+    import ecref
+
+    n = 5003
+    k = synth_scalars("k256", 0xB2000007, 0, n)
+    t = synth_point_scalars("k256", 0xB2000007, 0, n)
+    pxy, _ = B.host_eng.mul_by_generator("k256", t)
+    pxy = np.ascontiguousarray(pxy).reshape(-1)
+    md = ecgpu.Engine(list(range(B.world)))
+    res = {}
+    for curve in ("k256",):
+        oxy, oinf = md.mul_batch(curve, k, pxy)
+        r_xy, r_inf = ecref.mul_batch(curve, k, pxy, None, nthreads=B.threads_total, variant=0)
+        res["mul_batch"] = bool(np.array_equal(np.asarray(oxy).reshape(-1), r_xy.reshape(-1)) and np.array_equal(oinf, r_inf))
+        gxy, ginf = md.mul_by_generator(curve, k)
+        r_xy, r_inf = ecref.mul_gen_batch(curve, k, nthreads=B.threads_total)
+        res["mul_gen_batch"] = bool(np.array_equal(np.asarray(gxy).reshape(-1), r_xy.reshape(-1)) and np.array_equal(ginf, r_inf))
+        lxy, linf = md.lincomb(curve, np.tile(k, 4), np.tile(pxy, 4))          # 20012 terms: bucket method on every device
+        r_xy, r_inf = ecref.lincomb(curve, np.tile(k, 4), np.tile(pxy, 4), None, nthreads=B.threads_total)
+        res["lincomb"] = bool(np.array_equal(lxy, r_xy) and linf == r_inf)
+        bad = k.copy()
+        bad[32 * 4999:32 * 5000] = 0xFF
+        try:
+            md.mul_batch(curve, bad, pxy)
+            res["error_index"] = False
+        except ecgpu.ScalarRangeError as e:
+            res["error_index"] = e.index == 4999
+    md.close()
+    res["devices"] = B.world
+    res["elements"] = n
+    return res
+
+
+def run_ours(args):
+    B = Bench(args)
+    world, rank = B.world, B.rank
+    line = measure(B, args.workload, args.steps, args.warmup, sample_clocks=True)
+    configs = {}
+    if args.configs == "all" and args.workload == "k256_varbase":
+        sub_steps = max(3, min(args.steps, args.sub_steps))
+        if rank == 0:
+            configs["1_k256_plumbing_cpu"] = config1_plumbing(B)
+        for key, wl in (("3_p256_varbase", "p256_varbase"), ("4_k256_fixedbase", "k256_fixedbase"), ("5_k256_lincomb", "k256_lincomb")):
+            configs[key] = measure(B, wl, sub_steps, 3, sample_clocks=False)
+        if world > 1:
+            configs["strong_scaling"] = strong_scaling(B)
+            barrier_sync(world)
+            if rank == 0:
+                configs["multi_device_parity"] = multi_device_parity(B)
+            barrier_sync(world)
     if world > 1:
         import torch.distributed as dist
 
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
+        if configs:
+            line["configs"] = configs
+            line["configs_green"] = bool(all(c.get("bit_exact", True) for c in configs.values() if isinstance(c, dict)))
         print(json.dumps(line), flush=True)
 
 
@@ -546,6 +801,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="k256_varbase", choices=sorted(WORKLOADS))
     ap.add_argument("--log2-batch", type=int, default=0, help="override the per-GPU batch (development only)")
+    ap.add_argument("--configs", default="all", choices=["all", "none"],
+                    help="all: the headline line also carries a `configs` object with BASELINE.json configs 1, 3, 4, 5 (+ strong scaling at N > 1)")
+    ap.add_argument("--sub-steps", type=int, default=10, help="timed steps of the non-headline configs")
+    ap.add_argument("--strong-log2", type=int, default=23, help="log2 of the strong-scaling batch (N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

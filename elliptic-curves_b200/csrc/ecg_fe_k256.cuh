@@ -30,6 +30,13 @@ struct FpK256T {
   // OPT bits 6/7: the doubling / mixed addition trade one multiplication for a squaring + 4 linear ops
   static constexpr bool SQR_TRADE_DBL = (OPT & 64) != 0;
   static constexpr bool SQR_TRADE_MADD = (OPT & 128) != 0;
+  // OPT bits 11/12 (experiments, tools/kbench.cu): the point doubling / the mixed addition is ONE non-inlined function
+  // (Jacobian point in registers in and out) whose field operations are all inlined — one call per point operation
+  // instead of one per field multiplication, so the call marshalling (IMAD.MOV on the FMA pipe) shrinks accordingly
+  static constexpr bool DBL_CALL = (OPT & 2048) != 0;
+  static constexpr bool MADD_CALL = (OPT & 4096) != 0;
+  static constexpr bool DBL_3M5S = false;
+  typedef FpK256T<(OPT & (1 | 8 | 64 | 128))> Inline;  // the same field with mul / sqr inlined
 
   ECG_D static void set_zero(Fe& r) {
 #pragma unroll

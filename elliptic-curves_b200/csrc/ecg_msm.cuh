@@ -458,13 +458,18 @@ ECG_DEV void msm_jstore(uint32_t* __restrict__ a, size_t n, size_t i, const Jac&
 #define MSM_CH_LOG2 4
 template <class C>
 ECG_KERNEL(128)
-    msm_wreduce_kernel(const uint32_t* __restrict__ in, size_t n_in, size_t stride_in, size_t off, size_t len, int W, size_t nch,
-                       const uint32_t* __restrict__ Xprev, int level, uint32_t* __restrict__ outS, uint32_t* __restrict__ outX) {
+    msm_wreduce_kernel(const uint32_t* __restrict__ in, size_t n_in, size_t stride_in, size_t off, size_t len, size_t len_low, int W,
+                       size_t nch, const uint32_t* __restrict__ Xprev, int level, uint32_t* __restrict__ outS, uint32_t* __restrict__ outX) {
   typedef typename C::F F;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)W * nch) return;
   size_t w = t / nch, ch = t % nch;
-  size_t lo = ch * MSM_CH, hi = lo + MSM_CH < len ? lo + MSM_CH : len;
+  // only the top window (unsigned, absorbs the recoding carry and the slack bit) uses all `len` slots of its row; the
+  // signed windows below it stop at len_low = 2^(c-1) at level 0: three quarters of the rows' slots are never
+  // populated, and the chunks that cover only such slots contribute the identity without being read
+  const size_t len_w = (w + 1 == (size_t)W) ? len : len_low;
+  size_t lo = ch * MSM_CH, hi = lo + MSM_CH < len_w ? lo + MSM_CH : len_w;
+  if (hi < lo) hi = lo;
   Jac S, T, X, p;
   F::set_zero(S.X);
   F::set_one(S.Y);

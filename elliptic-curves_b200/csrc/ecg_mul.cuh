@@ -119,7 +119,7 @@ ECG_D void build_table_iso_a0(const TabRef& tab, Fe& Zg, const Aff& P) {
 #else
 #define ECG_BLOCK_SYNC() ((void)0)
 #endif
-template <class F = FpK256, bool PHASE_SYNC = false>
+template <class F = FpK256, int PHASE_SYNC = 0>  // 0 none, 1 per phase (doublings | additions), 2 before every point operation
 ECG_D void k256_mul_thread(Jac& r, const uint32_t* k, const Aff& P, const TabRef& tab) {
   GlvHalf g1, g2;
   glv_split_k256(g1, g2, k);
@@ -140,12 +140,16 @@ ECG_D void k256_mul_thread(Jac& r, const uint32_t* k, const Aff& P, const TabRef
 
 #pragma unroll 1
   for (int i = 0; i < 32; i++) {
-    if (PHASE_SYNC) ECG_BLOCK_SYNC();
+    if (PHASE_SYNC == 1) ECG_BLOCK_SYNC();
 #pragma unroll 1
-    for (int j = 0; j < 4; j++) jac_dbl<F, false>(acc, acc);
-    if (PHASE_SYNC) ECG_BLOCK_SYNC();
+    for (int j = 0; j < 4; j++) {
+      if (PHASE_SYNC == 2) ECG_BLOCK_SYNC();
+      jac_dbl<F, false>(acc, acc);
+    }
+    if (PHASE_SYNC == 1) ECG_BLOCK_SYNC();
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
+      if (PHASE_SYNC == 2) ECG_BLOCK_SYNC();
       uint32_t n = half ? next_window(g2.h) : next_window(g1.h);
       uint32_t sneg = half ? g2.neg : g1.neg;
       uint32_t pos = n >> 3;                       // digit sign: n>=8 -> positive
@@ -178,7 +182,7 @@ ECG_D void k256_mul_thread(Jac& r, const uint32_t* k, const Aff& P, const TabRef
 // 256-bit scalar: implicit top digit +1, then 64 windows of (4 dbl + 1 add) against a table of the eight
 // odd multiples kept in Jacobian form (the shared-denominator trick of build_table_iso_a0 needs a = 0).
 // Replaces primeorder ProjectivePoint::mul / mul_vartime (primeorder/src/projective.rs:133-144, :532-557).
-template <class F, bool A_IS_MINUS3>
+template <class F, bool A_IS_MINUS3, int PHASE_SYNC = 0>
 ECG_D void generic_mul_thread(Jac& r, const uint32_t* k, const Aff& P, const TabRefJ& tab) {
   FullRecode rc;
   recode_full(rc, k);
@@ -199,7 +203,11 @@ ECG_D void generic_mul_thread(Jac& r, const uint32_t* k, const Aff& P, const Tab
 #pragma unroll 1
   for (int i = 0; i < 64; i++) {
 #pragma unroll 1
-    for (int j = 0; j < 4; j++) jac_dbl<F, A_IS_MINUS3>(acc, acc);
+    for (int j = 0; j < 4; j++) {
+      if (PHASE_SYNC == 2) ECG_BLOCK_SYNC();
+      jac_dbl<F, A_IS_MINUS3>(acc, acc);
+    }
+    if (PHASE_SYNC == 2) ECG_BLOCK_SYNC();
     uint32_t n = next_window8(rc.h);
     uint32_t pos = n >> 3;
     uint32_t idx = pos ? (n & 7u) : (7u - n);

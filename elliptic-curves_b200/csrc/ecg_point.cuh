@@ -43,11 +43,11 @@ ECG_D void jac_csel(Jac& r, const Jac& t, uint32_t c) {
 // Doubling in "halved" form (Z3 = Y*Z, X3 = X3_std/4, Y3 = Y3_std/8): 3M+4S (a=0; 2M+5S with F::SQR_TRADE_DBL) / 4M+4S (a=-3),
 // 8 cheap linear ops.   L = (3X^2 + a Z^4)/2;  X3 = L^2 - 2XY^2;  Y3 = L(XY^2 - X3) - Y^4.
 template <class F, bool A_IS_MINUS3>
-ECG_D void jac_dbl(Jac& r, const Jac& p) {
-  Fe A, L, T, D, t;
+ECG_D void jac_dbl_body(Jac& r, const Jac& p) {
+  Fe A, L, T, D, t, zz;
   F::sqr(A, p.Y);  // Y^2
   if (A_IS_MINUS3) {
-    Fe zz, u, v;
+    Fe u, v;
     F::sqr(zz, p.Z);
     F::sub(u, p.X, zz);
     F::add(v, p.X, zz);
@@ -68,13 +68,41 @@ ECG_D void jac_dbl(Jac& r, const Jac& p) {
   }
   F::mul_small(L, L, 3);
   F::half(L, L);
-  F::mul_d(r.Z, p.Y, p.Z);
+  if (A_IS_MINUS3 && F::DBL_3M5S) {  // Y*Z = ((Y+Z)^2 - Y^2 - Z^2)/2 ; zz was computed for L
+    Fe s2;
+    F::add(s2, p.Y, p.Z);
+    F::sqr(s2, s2);
+    F::sub(s2, s2, A);
+    F::sub(s2, s2, zz);
+    F::half(r.Z, s2);
+  } else {
+    F::mul_d(r.Z, p.Y, p.Z);
+  }
   F::sqr(r.X, L);
   F::add(t, T, T);
   F::sub(r.X, r.X, t);
   F::sub(t, T, r.X);
   F::mul_d(r.Y, L, t);
   F::sub(r.Y, r.Y, D);
+}
+
+#if defined(__CUDA_ARCH__) || defined(__CUDACC__)
+#define ECG_NOINLINE_PT __device__ __noinline__
+#else
+#define ECG_NOINLINE_PT
+#endif
+template <class F, bool A_IS_MINUS3>
+ECG_NOINLINE_PT Jac jac_dbl_call(Jac p) {
+  Jac r;
+  jac_dbl_body<typename F::Inline, A_IS_MINUS3>(r, p);
+  return r;
+}
+template <class F, bool A_IS_MINUS3>
+ECG_D void jac_dbl(Jac& r, const Jac& p) {
+  if (F::DBL_CALL)
+    r = jac_dbl_call<F, A_IS_MINUS3>(p);
+  else
+    jac_dbl_body<F, A_IS_MINUS3>(r, p);
 }
 
 // 2*(x,y) for an affine input (Z = 1): saves the Z products.
@@ -111,7 +139,7 @@ inline
 
 // r = p + q, q affine and not the identity.  8M+3S (7M+4S with F::SQR_TRADE_MADD).  If zr != nullptr it receives Z3/Z1 (= H).
 template <class F, bool A_IS_MINUS3>
-ECG_D void jac_madd(Jac& r, const Jac& p, const Aff& q, Fe* zr = nullptr) {
+ECG_D void jac_madd_body(Jac& r, const Jac& p, const Aff& q, Fe* zr = nullptr) {
   Fe zz, u2, s2, H, R, hh, hhh, V, t;
   F::sqr(zz, p.Z);
   F::mul(u2, q.x, zz);
@@ -147,6 +175,20 @@ ECG_D void jac_madd(Jac& r, const Jac& p, const Aff& q, Fe* zr = nullptr) {
   F::mul(t, t, R);
   F::mul(hhh, hhh, p.Y);
   F::sub(r.Y, t, hhh);
+}
+
+template <class F, bool A_IS_MINUS3>
+ECG_NOINLINE_PT Jac jac_madd_call(Jac p, Aff q) {
+  Jac r;
+  jac_madd_body<typename F::Inline, A_IS_MINUS3>(r, p, q, nullptr);
+  return r;
+}
+template <class F, bool A_IS_MINUS3>
+ECG_D void jac_madd(Jac& r, const Jac& p, const Aff& q, Fe* zr = nullptr) {
+  if (F::MADD_CALL && zr == nullptr)
+    r = jac_madd_call<F, A_IS_MINUS3>(p, q);
+  else
+    jac_madd_body<F, A_IS_MINUS3>(r, p, q, zr);
 }
 
 // r = p + q, both Jacobian.  12M+4S.

@@ -1067,8 +1067,11 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
     size_t n_in = l == 0 ? nb : (size_t)g.W * nchs[l - 1];
     size_t stride = l == 0 ? g.nbw : nchs[l - 1];
     size_t off = l == 0 ? 1 : 0;
-    msm_wreduce_kernel<C><<<grid_for((size_t)g.W * nchs[l], 128), 128, 0, L.s()>>>(in, n_in, stride, off, lens[l], g.W, nchs[l],
-                                                                                 l == 0 ? nullptr : X[l - 1], l, S[l], X[l]);
+    // rows below the top window only populate the first 2^(c-1) slots (level 0), i.e. ceil(that / CH^l) chunk totals at level l
+    size_t len_low = ((size_t)1 << (g.c - 1));
+    for (int q = 0; q < l; q++) len_low = (len_low + MSM_CH - 1) / MSM_CH;
+    msm_wreduce_kernel<C><<<grid_for((size_t)g.W * nchs[l], 128), 128, 0, L.s()>>>(in, n_in, stride, off, lens[l], std::min(len_low, lens[l]), g.W,
+                                                                                 nchs[l], l == 0 ? nullptr : X[l - 1], l, S[l], X[l]);
     LAUNCHED(ctx);
   }
   msm_final_kernel<C><<<1, 32, 0, L.s()>>>(X[levels - 1], S[levels - 1], g.W, g.c, levels - 1, Rw, res);

@@ -233,6 +233,34 @@ extern "C" {
 int sim_p256_mul(const uint8_t* k_be, const uint8_t* P_xy, uint8_t* out_xy, uint8_t* out_inf) {
   return sim_generic_mul<FpP256, true>(k_be, P_xy, out_xy, out_inf);
 }
+// experiment variants measured in tools/kbench.cu: a = -3 doubling as 3M+5S, point-level call structure
+int sim_p256_mul_3m5s(const uint8_t* k_be, const uint8_t* P_xy, uint8_t* out_xy, uint8_t* out_inf) {
+  return sim_generic_mul<FpP256T<515 | 1024 | 2048>, true>(k_be, P_xy, out_xy, out_inf);
+}
+int sim_k256_mul_ptcalls(const uint8_t* k_be, const uint8_t* P_xy, uint8_t* out_xy, uint8_t* out_inf) {
+  typedef FpK256T<6151> F;
+  uint32_t k[8];
+  load_be32(k, k_be);
+  Aff P;
+  load_be32(P.x.v, P_xy);
+  load_be32(P.y.v, P_xy + 32);
+  std::vector<uint32_t> tabmem(8 * 16);
+  TabRef tab{tabmem.data(), 1};
+  Jac r;
+  k256_mul_thread<F>(r, k, P, tab);
+  if (F::is_zero(r.Z)) {
+    memset(out_xy, 0, 64);
+    *out_inf = 1;
+    return 0;
+  }
+  Fe zinv, x, y;
+  F::inv(zinv, r.Z);
+  jac_to_affine_canonical<F>(x, y, r, zinv);
+  store_be32(out_xy, x.v);
+  store_be32(out_xy + 32, y.v);
+  *out_inf = 0;
+  return 0;
+}
 // generic (no-endomorphism) path instantiated for secp256k1 as a cross-check of the shared code
 int sim_k256_mul_generic(const uint8_t* k_be, const uint8_t* P_xy, uint8_t* out_xy, uint8_t* out_inf) {
   return sim_generic_mul<FpK256, false>(k_be, P_xy, out_xy, out_inf);
@@ -536,8 +564,11 @@ static bool simk_msm_run(const uint8_t* k, const uint8_t* pxy, const uint8_t* pi
     size_t n_in = l == 0 ? nb : (size_t)g.W * nchs[l - 1];
     size_t stride = l == 0 ? g.nbw : nchs[l - 1];
     size_t off = l == 0 ? 1 : 0;
+    size_t len_low = ((size_t)1 << (g.c - 1));
+    for (int q = 0; q < l; q++) len_low = (len_low + MSM_CH - 1) / MSM_CH;
+    len_low = std::min(len_low, lens[l]);
     sim_launch((size_t)g.W * nchs[l], 128, [&] {
-      msm_wreduce_kernel<C>(in, n_in, stride, off, lens[l], g.W, nchs[l], l == 0 ? nullptr : X[l - 1].data(), l, S[l].data(), X[l].data());
+      msm_wreduce_kernel<C>(in, n_in, stride, off, lens[l], len_low, g.W, nchs[l], l == 0 ? nullptr : X[l - 1].data(), l, S[l].data(), X[l].data());
     });
   }
   std::vector<uint32_t> Rw((size_t)g.W * 24);

@@ -141,7 +141,8 @@ def _mul(sim, fn, c, k, P):
     return pyref.dec_point(out.raw, inf.raw[0])
 
 
-@pytest.mark.parametrize("curve,fn", [("k256", "sim_k256_mul"), ("p256", "sim_p256_mul"), ("k256", "sim_k256_mul_generic")])
+@pytest.mark.parametrize("curve,fn", [("k256", "sim_k256_mul"), ("p256", "sim_p256_mul"), ("k256", "sim_k256_mul_generic"),
+                                      ("p256", "sim_p256_mul_3m5s"), ("k256", "sim_k256_mul_ptcalls")])
 def test_scalar_mul_thread_routine(sim, curve, fn):
     c = pyref.CURVES[curve]
     G = pyref.G(c)

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(BLOCK, MINBLK) kb_varbase(size_t n, uint32_t* 
 }
 
 // phase-synchronised variant: every thread of the block stays alive (clamped index) so the barriers are legal
-template <class F, int BLOCK, int MINBLK>
+template <class F, int BLOCK, int MINBLK, int LEVEL = 1>
 __global__ void __launch_bounds__(BLOCK, MINBLK) kb_varbase_sync(size_t n, uint32_t* __restrict__ jac, uint32_t* __restrict__ gtab) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   size_t cidx = idx < n ? idx : n - 1;
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(BLOCK, MINBLK) kb_varbase_sync(size_t n, uint3
   Jac r;
   size_t slot = ((size_t)blockIdx.x % (148 * 8)) * BLOCK;
   TabRef tab{gtab + slot * 128 + threadIdx.x, (uint32_t)BLOCK};
-  k256_mul_thread<F, true>(r, k, P, tab);
+  k256_mul_thread<F, LEVEL>(r, k, P, tab);
   if (idx >= n) return;
   for (int w = 0; w < 8; w++) {
     jac[(size_t)w * n + idx] = r.X.v[w];
@@ -68,9 +68,9 @@ __global__ void __launch_bounds__(BLOCK, MINBLK) kb_varbase_sync(size_t n, uint3
     jac[(size_t)(16 + w) * n + idx] = r.Z.v[w];
   }
 }
-template <class F, int BLOCK, int MINBLK>
+template <class F, int BLOCK, int MINBLK, int LEVEL = 1>
 static void run_sync(const char* name, size_t n, uint32_t* jac, uint32_t* gtab) {
-  auto kern = kb_varbase_sync<F, BLOCK, MINBLK>;
+  auto kern = kb_varbase_sync<F, BLOCK, MINBLK, LEVEL>;
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, kern));
   int occ = 0;
@@ -186,6 +186,83 @@ __global__ void __launch_bounds__(256) kb_mix(double* out, int iters, double see
   if (s == 12345.678 && x == 77) out[0] = s;
 }
 
+// P-256 with a barrier before every point operation (all threads stay alive: clamped index)
+template <class F, int BLOCK, int MINBLK, int LEVEL>
+__global__ void __launch_bounds__(BLOCK, MINBLK) kb_generic_sync(size_t n, uint32_t* __restrict__ jac, uint32_t* __restrict__ gtab) {
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  size_t cidx = idx < n ? idx : n - 1;
+  uint32_t k[8];
+  Aff P;
+  make_inputs(k, P, cidx);
+  CurveP256T<F>::generator(P);
+  Jac r;
+  size_t slot = ((size_t)blockIdx.x % (148 * 8)) * BLOCK;
+  TabRefJ tab{gtab + slot * 192 + threadIdx.x, (uint32_t)BLOCK};
+  generic_mul_thread<F, true, LEVEL>(r, k, P, tab);
+  if (idx >= n) return;
+  for (int w = 0; w < 8; w++) {
+    jac[(size_t)w * n + idx] = r.X.v[w];
+    jac[(size_t)(8 + w) * n + idx] = r.Y.v[w];
+    jac[(size_t)(16 + w) * n + idx] = r.Z.v[w];
+  }
+}
+template <class F, int BLOCK, int MINBLK, int LEVEL>
+static void runp_sync(const char* name, size_t n, uint32_t* jac, uint32_t* gtab) {
+  auto kern = kb_generic_sync<F, BLOCK, MINBLK, LEVEL>;
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, kern));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, 0));
+  unsigned grid = (unsigned)((n + BLOCK - 1) / BLOCK);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    CK(cudaEventRecord(e0));
+    kern<<<grid, BLOCK>>>(n, jac, gtab);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  std::vector<uint32_t> h(24 * 4096);
+  for (int w = 0; w < 24; w++) CK(cudaMemcpy(&h[w * 4096], jac + (size_t)w * n, 4096 * 4, cudaMemcpyDeviceToHost));
+  printf("%-34s regs %3d  blocks/SM %d  warps/SM %2d  %8.3f ms  %.4g mults/s  chk %016llx\n", name, fa.numRegs, occ, occ * BLOCK / 32, best,
+         n / (best * 1e-3), (unsigned long long)checksum(h));
+}
+
+// Ceiling of a double-precision multiplier (52-bit limbs, Emmart-style split): the 25 limb products of a 5x5 schoolbook,
+// each as hi = fma_rz(a, b, 2^104), lo = fma_rz(a, b, (2^104 + 2^52) - hi), both halves accumulated into 64-bit integer
+// column sums.  No carry resolution, no reduction, no int<->double conversion: if THIS is not well above the integer
+// multiplier's 1.1e11 field-mul/s there is nothing to build on.
+__global__ void __launch_bounds__(256) kb_dfma_product(unsigned long long* out, int iters, double seed) {
+  double a[5], b[5];
+  for (int i = 0; i < 5; i++) { a[i] = (double)((threadIdx.x * 7919u + i * 104729u) & 0xFFFFFu) + seed; b[i] = (double)((blockIdx.x * 31u + i * 1299709u) & 0xFFFFFu) + 3.0; }
+  const double C1 = 20282409603651670423947251286016.0;       // 2^104
+  const double C2 = 20282409603651674927546878656512.0;       // 2^104 + 2^52
+  long long col[10];
+  for (int i = 0; i < 10; i++) col[i] = 0;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+#pragma unroll
+      for (int j = 0; j < 5; j++) {
+        double hi = __fma_rz(a[i], b[j], C1);
+        double lo = __fma_rz(a[i], b[j], C2 - hi);
+        col[i + j + 1] += __double_as_longlong(hi);
+        col[i + j] += __double_as_longlong(lo);
+      }
+    }
+    // feed something back so that iterations depend on each other without touching the FP64 pipe much
+    a[0] = __longlong_as_double((col[3] & 0xFFFFFFFFFll) | 0x4330000000000000ll) - 4503599627370496.0;
+  }
+  long long s = 0;
+  for (int i = 0; i < 10; i++) s ^= col[i];
+  if (s == 0x1234567) out[0] = (unsigned long long)s;
+}
+
 static uint64_t checksum(const std::vector<uint32_t>& v) {
   uint64_t h = 1469598103934665603ull;
   for (uint32_t x : v) { h ^= x; h *= 1099511628211ull; }
@@ -296,6 +373,47 @@ int main(int argc, char** argv) {
       runp<FpP256T<259>, 128, 5, true>("p256 v259 mul+sqr via mem (128,5)", n, jac, gtab);
       runp<FpP256T<259>, 128, 6, true>("p256 v259 mul+sqr via mem (128,6)", n, jac, gtab);
       runp<FpP256T<263>, 128, 5, true>("p256 v263 mul via mem     (128,5)", n, jac, gtab);
+    }
+    return 0;
+  }
+  if (argc > 2 && !strcmp(argv[2], "r2")) {  // round-2 experiments: point-level calls, barriers per point operation, P-256 doubling, DFMA ceiling
+    {
+      unsigned long long* dout; CK(cudaMalloc(&dout, 256));
+      cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+      float best = 1e30f; int iters = 2000; unsigned blocks = 148 * 8;
+      for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(e0));
+        kb_dfma_product<<<blocks, 256>>>(dout, iters, 1.0 + rep);
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+      }
+      printf("DFMA 5x5 product core (50 DFMA + 25 DADD + 50 IADD64, no carries / reduction): %.4g products/s (%.3f ms)\n",
+             (double)blocks * 256 * iters / (best * 1e-3), best);
+    }
+    for (int round = 0; round < 2; round++) {
+      run<FpK256T<7>, 128, 4, true>("v7    base                (128,4)", n, jac, gtab);
+      run<FpK256T<2055>, 128, 4, true>("v2055 dbl=call(inl inside)(128,4)", n, jac, gtab);
+      run<FpK256T<2055>, 128, 3, true>("v2055 dbl=call(inl inside)(128,3)", n, jac, gtab);
+      run<FpK256T<2055>, 256, 2, true>("v2055 dbl=call(inl inside)(256,2)", n, jac, gtab);
+      run<FpK256T<6151>, 128, 4, true>("v6151 dbl+madd calls      (128,4)", n, jac, gtab);
+      run<FpK256T<6151>, 128, 3, true>("v6151 dbl+madd calls      (128,3)", n, jac, gtab);
+      run<FpK256T<6145>, 128, 4, true>("v6145 dbl+madd calls, rest inline(128,4)", n, jac, gtab);
+      run_sync<FpK256T<1>, 256, 2, 2>("sync2 inline sqr8 (256,2)", n, jac, gtab);
+      run_sync<FpK256T<1>, 512, 1, 2>("sync2 inline sqr8 (512,1)", n, jac, gtab);
+      run_sync<FpK256T<1>, 384, 1, 2>("sync2 inline sqr8 (384,1)", n, jac, gtab);
+      run_sync<FpK256T<1>, 256, 2, 1>("sync1 inline sqr8 (256,2)", n, jac, gtab);
+      run_sync<FpK256T<6145>, 256, 2, 2>("sync2 dbl+madd calls (256,2)", n, jac, gtab);
+      run_sync<FpK256T<6145>, 512, 1, 2>("sync2 dbl+madd calls (512,1)", n, jac, gtab);
+      runp<FpP256T<515>, 128, 4, true>("p256 v515  Montgomery call (128,4)", n, jac, gtab);
+      runp<FpP256T<1539>, 128, 4, true>("p256 v1539 + dbl 3M+5S     (128,4)", n, jac, gtab);
+      runp<FpP256T<1539>, 128, 5, true>("p256 v1539 + dbl 3M+5S     (128,5)", n, jac, gtab);
+      runp<FpP256T<2563>, 128, 4, true>("p256 v2563 dbl=call        (128,4)", n, jac, gtab);
+      runp<FpP256T<3587>, 128, 4, true>("p256 v3587 dbl=call 3M+5S  (128,4)", n, jac, gtab);
+      runp<FpP256T<3587>, 128, 3, true>("p256 v3587 dbl=call 3M+5S  (128,3)", n, jac, gtab);
+      runp_sync<FpP256T<513>, 256, 2, 2>("p256 sync2 inline (256,2)", n, jac, gtab);
+      runp_sync<FpP256T<513>, 512, 1, 2>("p256 sync2 inline (512,1)", n, jac, gtab);
+      runp_sync<FpP256T<1537>, 512, 1, 2>("p256 sync2 inline 3M+5S (512,1)", n, jac, gtab);
     }
     return 0;
   }
