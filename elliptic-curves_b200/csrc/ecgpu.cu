@@ -368,6 +368,36 @@ static ecg_status launch_norm(ecg_ctx* ctx, DevState& d, Lane& L, ecg_curve curv
 static const int K_BLOCK = 128, K_MINBLK = 4;  // secp256k1: <= 128 registers -> 16 warps/SM (mul = call, sqr inlined: OPT 7)
 static const int P_BLOCK = 128, P_MINBLK = 4;  // P-256   : <= 128 registers -> 16 warps/SM
 
+// P-256 variable base = three kernels per piece of at most P_PIECE_WAVES waves (ecg_kernels.cuh: generic_table_kernel ->
+// table_affine_kernel -> generic_main_kernel): the piece's tables (768 + 512 B per pair) then stay in the 126 MB L2
+static const size_t P_PIECE_WAVES = 1;
+static const int PM_BLOCK = 128, PM_MINBLK = 4;  // main-loop kernel launch geometry
+static ecg_status launch_varbase_p256(ecg_ctx* ctx, DevState& d, Lane& L, size_t n, const DevPtrs& dp, uint32_t* jac, uint32_t* status,
+                                      size_t base) {
+  const size_t wave = (size_t)d.sm_count * PM_MINBLK * PM_BLOCK;
+  const size_t piece = std::min(n, P_PIECE_WAVES * wave);
+  ST_TRY(ensure(ctx, L, B_TAB, piece * (192 + 128) * 4 + piece + 256));
+  ST_TRY(ensure(ctx, L, B_SCR, piece * 8 * 32));
+  uint32_t* jtab = (uint32_t*)L.buf[B_TAB];
+  uint32_t* atab = jtab + piece * 192;
+  uint8_t* flag = (uint8_t*)(atab + piece * 128);
+  DOM_BEGIN(ctx, L);
+  for (size_t lo = 0; lo < n; lo += piece) {
+    size_t cnt = std::min(piece, n - lo);
+    const uint8_t* pinf = dp.inf ? dp.inf + lo : nullptr;
+    generic_table_kernel<CurveP256, P_BLOCK, P_MINBLK><<<grid_for(cnt, P_BLOCK), P_BLOCK, 0, L.s()>>>(dp.k + 32 * lo, dp.p + 64 * lo, pinf, cnt, jtab, flag,
+                                                                                                     status, base + lo);
+    LAUNCHED(ctx);
+    size_t want_threads = std::max<size_t>((8 * cnt + 31) / 32, std::min<size_t>(8 * cnt, (size_t)d.sm_count * 1024));
+    table_affine_kernel<FpP256><<<grid_for(want_threads, 256), 256, 0, L.s()>>>(jtab, cnt, (uint32_t*)L.buf[B_SCR], atab);
+    LAUNCHED(ctx);
+    generic_main_kernel<CurveP256, PM_BLOCK, PM_MINBLK><<<grid_for(cnt, PM_BLOCK), PM_BLOCK, 0, L.s()>>>(dp.k + 32 * lo, cnt, atab, flag, jac, n, lo);
+    LAUNCHED(ctx);
+  }
+  DOM_END(ctx, L);
+  return ECG_OK;
+}
+
 // per-block window-table slots for a launch of n elements
 static ecg_status ensure_tab(ecg_ctx* ctx, Lane& L, ecg_curve curve, size_t n) {
   size_t block = curve == ECG_SECP256K1 ? K_BLOCK : P_BLOCK;
@@ -377,8 +407,9 @@ static ecg_status ensure_tab(ecg_ctx* ctx, Lane& L, ecg_curve curve, size_t n) {
 }
 
 // k*P for one chunk -> Jacobian SoA in `jac`; `status` / `base` locate validation errors
-static ecg_status launch_varbase(ecg_ctx* ctx, Lane& L, ecg_curve curve, size_t n, const DevPtrs& dp, uint32_t* jac,
+static ecg_status launch_varbase(ecg_ctx* ctx, DevState& d, Lane& L, ecg_curve curve, size_t n, const DevPtrs& dp, uint32_t* jac,
                                  uint32_t* status, size_t base) {
+  if (curve == ECG_NISTP256) return launch_varbase_p256(ctx, d, L, n, dp, jac, status, base);
   ST_TRY(ensure_tab(ctx, L, curve, n));
   uint32_t* gtab = (uint32_t*)L.buf[B_TAB];
   DOM_BEGIN(ctx, L);
@@ -481,7 +512,7 @@ static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
     DevPtrs dp;
     dp.k = dk + 32 * lo;
     dp.p = dpnt;
-    rc = launch_varbase(ctx, L, curve, cnt, dp, jac, st, lo);
+    rc = launch_varbase(ctx, d, L, curve, cnt, dp, jac, st, lo);
     if (rc != ECG_OK) break;
     size_t want_threads = std::max<size_t>((cnt + 31) / 32, std::min<size_t>(cnt, (size_t)d.sm_count * 256));
     if (curve == ECG_SECP256K1) {
@@ -606,7 +637,7 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
   const bool k1 = op.curve == ECG_SECP256K1;
   switch (op.kind) {
     case BatchOp::MUL:
-      ST_TRY(launch_varbase(ctx, L, op.curve, cnt, dp, jac, L.status, off));
+      ST_TRY(launch_varbase(ctx, d, L, op.curve, cnt, dp, jac, L.status, off));
       break;
     case BatchOp::MULGEN:
       DOM_BEGIN(ctx, L);
@@ -1006,7 +1037,7 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
   const int levels = (int)lens.size();
   // carve the scratch arena (first pass sizes it, second pass hands out pointers)
   uint32_t *pts = nullptr, *count = nullptr, *cursor = nullptr, *offset = nullptr, *list = nullptr, *bkt = nullptr, *res = nullptr;
-  uint32_t* blocksum = nullptr;
+  uint32_t *blocksum = nullptr, *order = nullptr, *ohist = nullptr;
   int32_t* digits = nullptr;
   std::vector<uint32_t*> S(levels), X(levels);
   uint32_t* Rw = nullptr;
@@ -1020,6 +1051,8 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
     offset = cv.take<uint32_t>(nb + 1);
     list = cv.take<uint32_t>(nsub * (size_t)g.W);
     bkt = cv.take<uint32_t>(nb * 24);
+    order = cv.take<uint32_t>(nb);
+    ohist = cv.take<uint32_t>(MSM_ORDER_CLASSES + 1);
     for (int l = 0; l < levels; l++) {
       S[l] = cv.take<uint32_t>((size_t)g.W * nchs[l] * 24);
       X[l] = cv.take<uint32_t>((size_t)g.W * nchs[l] * 24);
@@ -1048,6 +1081,21 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
   MsmSkew sk{maxcnt, 4096u, (uint32_t)std::min<size_t>(32 * avg, 0xFFFFFFFFu), L.status};
   msm_scatter_kernel<<<grid_for(nsub, 256), 256, 0, L.s()>>>(digits, nsub, g, offset, cursor, list);
   LAUNCHED(ctx);
+  // bucket ids by decreasing population (ECG_MSM_ORDER=0 keeps the natural order: measurement knob)
+  static const bool use_order = []() {
+    const char* e = getenv("ECG_MSM_ORDER");
+    return !(e && e[0] == '0');
+  }();
+  if (use_order) {
+    CU_TRY(ctx, cudaMemsetAsync(ohist, 0, (MSM_ORDER_CLASSES + 1) * 4, L.s()));
+    unsigned ob = (unsigned)std::min<size_t>((nb + 255) / 256, 592);
+    msm_order_hist_kernel<<<ob, 256, 0, L.s()>>>(offset, nb, ohist);
+    LAUNCHED(ctx);
+    msm_order_scan_kernel<<<1, MSM_ORDER_CLASSES, 0, L.s()>>>(ohist);
+    LAUNCHED(ctx);
+    msm_order_scatter_kernel<<<ob, 256, 0, L.s()>>>(offset, nb, ohist, order);
+    LAUNCHED(ctx);
+  }
   DOM_BEGIN(ctx, L);
   switch (msm_buckets_per_thread()) {  // > 1: warp-balanced variant (ecg_msm.cuh), off unless the environment asks for it
     case 8:
@@ -1057,7 +1105,7 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
       msm_bucket_sorted_kernel<C, 4><<<grid_for(nb, MSM_BS_BLOCK * 4), MSM_BS_BLOCK, 0, L.s()>>>(pts, list, offset, nb, bkt, sk);
       break;
     default:
-      msm_bucket_kernel<C><<<grid_for(nb, 128), 128, 0, L.s()>>>(pts, list, offset, nb, bkt, sk);
+      msm_bucket_kernel<C><<<grid_for(nb, 128), 128, 0, L.s()>>>(pts, list, offset, nb, bkt, sk, use_order ? order : nullptr);
   }
   LAUNCHED(ctx);
   DOM_END(ctx, L);
@@ -1135,7 +1183,7 @@ static ecg_status lincomb_shard(ecg_ctx* ctx, DevState& d, ecg_curve curve, cons
     q.p = dp.p + 64 * lo;
     q.inf = dp.inf ? dp.inf + lo : nullptr;
     uint32_t* r1 = nullptr;
-    ST_TRY(launch_varbase(ctx, L, curve, cnt, q, (uint32_t*)L.buf[B_FB1], L.status, sh.off + lo));
+    ST_TRY(launch_varbase(ctx, d, L, curve, cnt, q, (uint32_t*)L.buf[B_FB1], L.status, sh.off + lo));
     ST_TRY(reduce_points_c(ctx, L, curve, (uint32_t*)L.buf[B_FB1], (uint32_t*)L.buf[B_FB2], cnt, &r1));
     if (pieces == 1) {
       *result = r1;

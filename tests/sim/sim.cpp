@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -400,8 +402,18 @@ extern "C" int simk_mul_batch(int curve, size_t n, const uint8_t* k, const uint8
     sim_launch(n, SIM_BLOCK, [&] { k256_varbase_kernel<SIM_BLOCK, 4>(k, pxy, pinf, n, jac.data(), gtab.data(), status, 0); });
     simk_normalize<CurveK256>(jac, n, out_xy, out_inf);
   } else {
-    std::vector<uint32_t> gtab(blocks * SIM_BLOCK * P_TAB_WORDS);
-    sim_launch(n, SIM_BLOCK, [&] { generic_varbase_kernel<CurveP256, SIM_BLOCK, 4>(k, pxy, pinf, n, jac.data(), gtab.data(), status, 0); });
+    // as launch_varbase_p256: table kernel -> affine-table kernel -> main kernel, in pieces (here: of 1000 pairs)
+    (void)blocks;
+    const size_t piece = std::min<size_t>(n, 1000);
+    std::vector<uint32_t> jtab(piece * 192), atab(piece * 128), scr(piece * 64 + 8);
+    std::vector<uint8_t> flag(piece);
+    for (size_t lo = 0; lo < n; lo += piece) {
+      size_t cnt = std::min(piece, n - lo);
+      const uint8_t* pi = pinf ? pinf + lo : nullptr;
+      sim_launch(cnt, SIM_BLOCK, [&] { generic_table_kernel<CurveP256, SIM_BLOCK, 4>(k + 32 * lo, pxy + 64 * lo, pi, cnt, jtab.data(), flag.data(), status, lo); });
+      sim_launch((8 * cnt + 31) / 32, 256, [&] { table_affine_kernel<FpP256>(jtab.data(), cnt, scr.data(), atab.data()); });
+      sim_launch(cnt, SIM_BLOCK, [&] { generic_main_kernel<CurveP256, SIM_BLOCK, 4>(k + 32 * lo, cnt, atab.data(), flag.data(), jac.data(), n, lo); });
+    }
     simk_normalize<CurveP256>(jac, n, out_xy, out_inf);
   }
   return 0;
@@ -551,7 +563,22 @@ static bool simk_msm_run(const uint8_t* k, const uint8_t* pxy, const uint8_t* pi
     sim_launch_blocks((unsigned)((nb + MSM_BS_BLOCK * 4 - 1) / (MSM_BS_BLOCK * 4)), MSM_BS_BLOCK,
                       [&] { msm_bucket_sorted_kernel<C, 4>(pts.data(), list.data(), offset.data(), nb, bkt.data(), sk); });
   else
-    sim_launch(nb, 128, [&] { msm_bucket_kernel<C>(pts.data(), list.data(), offset.data(), nb, bkt.data(), sk); });
+  {
+    // as msm_run: bucket ids by decreasing population, then one thread per bucket in that order
+    std::vector<uint32_t> order(nb), ohist(MSM_ORDER_CLASSES + 1, 0);
+    unsigned ob = (unsigned)std::min<size_t>((nb + 255) / 256, 7);
+    sim_launch_blocks(ob, 256, [&] { msm_order_hist_kernel(offset.data(), nb, ohist.data()); });
+    sim_launch_blocks(1, MSM_ORDER_CLASSES, [&] { msm_order_scan_kernel(ohist.data()); });
+    sim_launch_blocks(ob, 256, [&] { msm_order_scatter_kernel(offset.data(), nb, ohist.data(), order.data()); });
+    std::vector<uint32_t> seen(nb, 0);
+    for (uint32_t b : order) seen[b]++;
+    for (size_t b = 0; b < nb; b++)
+      if (seen[b] != 1) {
+        fprintf(stderr, "msm_order_*: bucket order is not a permutation (bucket %zu seen %u times)\n", b, seen[b]);
+        abort();
+      }
+    sim_launch(nb, 128, [&] { msm_bucket_kernel<C>(pts.data(), list.data(), offset.data(), nb, bkt.data(), sk, order.data()); });
+  }
   if (status[0] & MSM_SKEW_FLAG) {  // as finish() + the caller in ecgpu.cu: the flag is consumed, the per-term path runs
     status[0] &= ~MSM_SKEW_FLAG;
     return false;
