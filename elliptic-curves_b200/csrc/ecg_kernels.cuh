@@ -133,103 +133,6 @@ ECG_KERNEL(BLOCK, MINBLK)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Generic prime-order curve, the same multiplication as three kernels with an AFFINE window table (see ecg_mul.cuh):
-//   jtab : Jacobian entries, word w of entry e of pair idx at jtab[(e*24 + w)*n + idx]        (768 B / pair)
-//   atab : affine entries (internal form), word w of entry e at atab[(e*16 + w)*n + idx]       (512 B / pair)
-//   flag : 1 where the pair is an identity / invalid input (the kernels computed on the substitute k = 1, P = G)
-// All three are launched over the same n pairs (one or two waves, so that the tables stay in L2).
-template <class C, int BLOCK, int MINBLK>
-ECG_KERNEL(BLOCK, MINBLK)
-    generic_table_kernel(const uint8_t* __restrict__ kb, const uint8_t* __restrict__ pxy, const uint8_t* __restrict__ pinf, size_t n,
-                         uint32_t* __restrict__ jtab, uint8_t* __restrict__ flag, uint32_t* __restrict__ status, size_t base) {
-  typedef typename C::F F;
-  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-  if (idx >= n) return;
-  uint32_t k[8];
-  Aff P;
-  bool inf;
-  uint32_t err = load_pair<C>(k, P, inf, kb, pxy, pinf, idx);
-  if (err) report_error(status, err, base + idx);
-  flag[idx] = (inf || err) ? 1 : 0;
-  TabRefJ tab{jtab + idx, (uint32_t)n};
-  generic_table_thread<F, C::A_IS_MINUS3>(P, tab);
-}
-
-// Montgomery's trick over the Z coordinates of the 8n table entries: thread t owns entries t, t+T, ... (entry j = (e, idx)
-// with e = j / n); 7 multiplications per entry + one inversion per thread.  scr: 8 * 8n words (prefix products).
-template <class F>
-ECG_KERNEL(256)
-    table_affine_kernel(const uint32_t* __restrict__ jtab, size_t n, uint32_t* __restrict__ scr, uint32_t* __restrict__ atab) {
-  const size_t N = 8 * n;
-  size_t T = (size_t)gridDim.x * blockDim.x;
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= N) return;
-  Fe acc;
-  F::set_one(acc);
-  size_t last = t;
-  for (size_t j = t; j < N; j += T) {
-    size_t e = j / n, idx = j - e * n;
-    Fe z;
-#pragma unroll
-    for (int w = 0; w < 8; w++) z.v[w] = jtab[(e * 24 + 16 + w) * n + idx];
-    if (F::is_zero(z)) F::set_one(z);  // unreachable for points of prime order; never let one entry poison a slice
-    soa_store<8>(scr, N, j, acc.v, 0);
-    F::mul(acc, acc, z);
-    last = j;
-  }
-  Fe inv;
-  F::inv(inv, acc);
-  for (size_t j = last;; j -= T) {
-    size_t e = j / n, idx = j - e * n;
-    Fe X, Y, Z, pre, zinv, z2, z3;
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-      X.v[w] = jtab[(e * 24 + w) * n + idx];
-      Y.v[w] = jtab[(e * 24 + 8 + w) * n + idx];
-      Z.v[w] = jtab[(e * 24 + 16 + w) * n + idx];
-    }
-    if (F::is_zero(Z)) F::set_one(Z);
-    soa_load<8>(pre.v, scr, N, j, 0);
-    F::mul(zinv, inv, pre);
-    F::mul(inv, inv, Z);
-    F::sqr(z2, zinv);
-    F::mul(z3, z2, zinv);
-    F::mul(X, X, z2);
-    F::mul(Y, Y, z3);
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-      atab[(e * 16 + w) * n + idx] = X.v[w];
-      atab[(e * 16 + 8 + w) * n + idx] = Y.v[w];
-    }
-    if (j < T) break;
-  }
-}
-
-// jac: SoA over jn points; this launch writes points j0 .. j0+n-1
-template <class C, int BLOCK, int MINBLK>
-ECG_KERNEL(BLOCK, MINBLK)
-    generic_main_kernel(const uint8_t* __restrict__ kb, size_t n, const uint32_t* __restrict__ atab, const uint8_t* __restrict__ flag,
-                        uint32_t* __restrict__ jac, size_t jn, size_t j0) {
-  typedef typename C::F F;
-  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-  if (idx >= n) return;
-  uint32_t k[8];
-  load_be32(k, kb + 32 * idx);
-  bool sub = flag[idx] != 0;
-  if (sub) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) k[i] = (i == 0);
-  }
-  TabRef tab{const_cast<uint32_t*>(atab) + idx, (uint32_t)n};
-  Jac r;
-  generic_main_thread<F, C::A_IS_MINUS3>(r, k, tab);
-  if (sub) F::set_zero(r.Z);
-  soa_store<8>(jac, jn, j0 + idx, r.X.v, 0);
-  soa_store<8>(jac, jn, j0 + idx, r.Y.v, 8);
-  soa_store<8>(jac, jn, j0 + idx, r.Z.v, 16);
-}
-
-// ------------------------------------------------------------------------------------------------
 // Fixed-base k*G from a device-resident table of affine odd multiples.
 //   table layout: window i (0..FB_WINDOWS-1), entry j (0..2^(FB_W-1)-1) = (2j+1) * 2^(FB_W*i) * G, 16 words
 //   (x[8], y[8], internal form); one extra entry at the end = 2^256 * G (the recoding's implicit top digit).

@@ -226,56 +226,4 @@ ECG_D void generic_mul_thread(Jac& r, const uint32_t* k, const Aff& P, const Tab
   r = acc;
 }
 
-// ---- the same multiplication cut in three for curves without the shared-denominator trick (a != 0) -------------------
-// The window additions of generic_mul_thread are full Jacobian additions (12M+4S) because the table entries keep their
-// own Z.  Making the table affine needs an inversion, which only pays when it is shared: so the work is cut into
-//   generic_table_thread   build the 8 odd multiples (Jacobian) and leave them in global memory      [kernel 1]
-//   table_affine_kernel    Montgomery's trick over the Z coordinates of MANY pairs' entries          [kernel 2, ecg_kernels.cuh]
-//   generic_main_thread    64 windows of (4 dbl + 1 MIXED addition, 8M+3S) against the affine table  [kernel 3]
-// which trades 64 x (4M+1S) per pair for ~7 multiplications per table entry (batched inversion).
-template <class F, bool A_IS_MINUS3>
-ECG_D void generic_table_thread(const Aff& P, const TabRefJ& tab) {
-  Jac d, cur;
-  aff_dbl<F, A_IS_MINUS3>(d, P);
-  cur.X = P.x;
-  cur.Y = P.y;
-  F::set_one(cur.Z);
-  tab.store(0, cur);
-  jac_madd<F, A_IS_MINUS3>(cur, d, P);  // 3P
-  tab.store(1, cur);
-#pragma unroll 1
-  for (int i = 2; i < 8; i++) {
-    jac_add<F, A_IS_MINUS3>(cur, cur, d);
-    tab.store(i, cur);
-  }
-}
-// tab: the affine odd multiples {1,3,...,15} * P (entry 0 is P itself)
-template <class F, bool A_IS_MINUS3>
-ECG_D void generic_main_thread(Jac& r, const uint32_t* k, const TabRef& tab) {
-  FullRecode rc;
-  recode_full(rc, k);
-  Jac acc;
-  Aff e;
-  tab.load(0, acc.X, acc.Y);  // top digit (+1) * P
-  F::set_one(acc.Z);
-#pragma unroll 1
-  for (int i = 0; i < 64; i++) {
-#pragma unroll 1
-    for (int j = 0; j < 4; j++) jac_dbl<F, A_IS_MINUS3>(acc, acc);
-    uint32_t n = next_window8(rc.h);
-    uint32_t pos = n >> 3;
-    uint32_t idx = pos ? (n & 7u) : (7u - n);
-    tab.load((int)idx, e.x, e.y);
-    fe_cneg<F>(e.y, pos ^ 1u);
-    jac_madd<F, A_IS_MINUS3>(acc, acc, e);
-  }
-  // parity correction: the loop computed (k+1)*P when k was even
-  tab.load(0, e.x, e.y);
-  F::neg(e.y, e.y);
-  Jac t;
-  jac_madd<F, A_IS_MINUS3>(t, acc, e);
-  jac_csel(acc, t, rc.even);
-  r = acc;
-}
-
 }  // namespace ecg

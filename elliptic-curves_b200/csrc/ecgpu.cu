@@ -366,37 +366,7 @@ static ecg_status launch_norm(ecg_ctx* ctx, DevState& d, Lane& L, ecg_curve curv
 
 // launch geometry of the variable-base kernels (registers set the occupancy; tables are in global memory)
 static const int K_BLOCK = 128, K_MINBLK = 4;  // secp256k1: <= 128 registers -> 16 warps/SM (mul = call, sqr inlined: OPT 7)
-static const int P_BLOCK = 128, P_MINBLK = 4;  // P-256   : <= 128 registers -> 16 warps/SM
-
-// P-256 variable base = three kernels per piece of at most P_PIECE_WAVES waves (ecg_kernels.cuh: generic_table_kernel ->
-// table_affine_kernel -> generic_main_kernel): the piece's tables (768 + 512 B per pair) then stay in the 126 MB L2
-static const size_t P_PIECE_WAVES = 1;
-static const int PM_BLOCK = 128, PM_MINBLK = 4;  // main-loop kernel launch geometry
-static ecg_status launch_varbase_p256(ecg_ctx* ctx, DevState& d, Lane& L, size_t n, const DevPtrs& dp, uint32_t* jac, uint32_t* status,
-                                      size_t base) {
-  const size_t wave = (size_t)d.sm_count * PM_MINBLK * PM_BLOCK;
-  const size_t piece = std::min(n, P_PIECE_WAVES * wave);
-  ST_TRY(ensure(ctx, L, B_TAB, piece * (192 + 128) * 4 + piece + 256));
-  ST_TRY(ensure(ctx, L, B_SCR, piece * 8 * 32));
-  uint32_t* jtab = (uint32_t*)L.buf[B_TAB];
-  uint32_t* atab = jtab + piece * 192;
-  uint8_t* flag = (uint8_t*)(atab + piece * 128);
-  DOM_BEGIN(ctx, L);
-  for (size_t lo = 0; lo < n; lo += piece) {
-    size_t cnt = std::min(piece, n - lo);
-    const uint8_t* pinf = dp.inf ? dp.inf + lo : nullptr;
-    generic_table_kernel<CurveP256, P_BLOCK, P_MINBLK><<<grid_for(cnt, P_BLOCK), P_BLOCK, 0, L.s()>>>(dp.k + 32 * lo, dp.p + 64 * lo, pinf, cnt, jtab, flag,
-                                                                                                     status, base + lo);
-    LAUNCHED(ctx);
-    size_t want_threads = std::max<size_t>((8 * cnt + 31) / 32, std::min<size_t>(8 * cnt, (size_t)d.sm_count * 1024));
-    table_affine_kernel<FpP256><<<grid_for(want_threads, 256), 256, 0, L.s()>>>(jtab, cnt, (uint32_t*)L.buf[B_SCR], atab);
-    LAUNCHED(ctx);
-    generic_main_kernel<CurveP256, PM_BLOCK, PM_MINBLK><<<grid_for(cnt, PM_BLOCK), PM_BLOCK, 0, L.s()>>>(dp.k + 32 * lo, cnt, atab, flag, jac, n, lo);
-    LAUNCHED(ctx);
-  }
-  DOM_END(ctx, L);
-  return ECG_OK;
-}
+static const int P_BLOCK = 128, P_MINBLK = 5;  // P-256   : <= 96 registers -> 20 warps/SM (Montgomery field: 34.09 vs 34.65 ms at (128,4), tools/kbench.cu)
 
 // per-block window-table slots for a launch of n elements
 static ecg_status ensure_tab(ecg_ctx* ctx, Lane& L, ecg_curve curve, size_t n) {
@@ -409,7 +379,7 @@ static ecg_status ensure_tab(ecg_ctx* ctx, Lane& L, ecg_curve curve, size_t n) {
 // k*P for one chunk -> Jacobian SoA in `jac`; `status` / `base` locate validation errors
 static ecg_status launch_varbase(ecg_ctx* ctx, DevState& d, Lane& L, ecg_curve curve, size_t n, const DevPtrs& dp, uint32_t* jac,
                                  uint32_t* status, size_t base) {
-  if (curve == ECG_NISTP256) return launch_varbase_p256(ctx, d, L, n, dp, jac, status, base);
+  (void)d;
   ST_TRY(ensure_tab(ctx, L, curve, n));
   uint32_t* gtab = (uint32_t*)L.buf[B_TAB];
   DOM_BEGIN(ctx, L);
@@ -736,7 +706,7 @@ static ecg_status run_batch_inner(ecg_ctx* ctx, const BatchOp& op, size_t n) {
   std::vector<std::vector<Shard>> sched(shards.size());
   size_t maxchunks = 0;
   for (size_t i = 0; i < shards.size(); i++) {
-    sched[i] = chunk_schedule(shards[i].cnt, (size_t)ctx->devs[i].sm_count * K_MINBLK * K_BLOCK);
+    sched[i] = chunk_schedule(shards[i].cnt, (size_t)ctx->devs[i].sm_count * (op.curve == ECG_SECP256K1 ? K_MINBLK * K_BLOCK : P_MINBLK * P_BLOCK));
     maxchunks = std::max(maxchunks, sched[i].size());
   }
   for (size_t c = 0; c < maxchunks; c++) {

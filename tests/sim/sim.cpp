@@ -402,18 +402,8 @@ extern "C" int simk_mul_batch(int curve, size_t n, const uint8_t* k, const uint8
     sim_launch(n, SIM_BLOCK, [&] { k256_varbase_kernel<SIM_BLOCK, 4>(k, pxy, pinf, n, jac.data(), gtab.data(), status, 0); });
     simk_normalize<CurveK256>(jac, n, out_xy, out_inf);
   } else {
-    // as launch_varbase_p256: table kernel -> affine-table kernel -> main kernel, in pieces (here: of 1000 pairs)
-    (void)blocks;
-    const size_t piece = std::min<size_t>(n, 1000);
-    std::vector<uint32_t> jtab(piece * 192), atab(piece * 128), scr(piece * 64 + 8);
-    std::vector<uint8_t> flag(piece);
-    for (size_t lo = 0; lo < n; lo += piece) {
-      size_t cnt = std::min(piece, n - lo);
-      const uint8_t* pi = pinf ? pinf + lo : nullptr;
-      sim_launch(cnt, SIM_BLOCK, [&] { generic_table_kernel<CurveP256, SIM_BLOCK, 4>(k + 32 * lo, pxy + 64 * lo, pi, cnt, jtab.data(), flag.data(), status, lo); });
-      sim_launch((8 * cnt + 31) / 32, 256, [&] { table_affine_kernel<FpP256>(jtab.data(), cnt, scr.data(), atab.data()); });
-      sim_launch(cnt, SIM_BLOCK, [&] { generic_main_kernel<CurveP256, SIM_BLOCK, 4>(k + 32 * lo, cnt, atab.data(), flag.data(), jac.data(), n, lo); });
-    }
+    std::vector<uint32_t> gtab(blocks * SIM_BLOCK * P_TAB_WORDS);
+    sim_launch(n, SIM_BLOCK, [&] { generic_varbase_kernel<CurveP256, SIM_BLOCK, 4>(k, pxy, pinf, n, jac.data(), gtab.data(), status, 0); });
     simk_normalize<CurveP256>(jac, n, out_xy, out_inf);
   }
   return 0;
