@@ -26,6 +26,10 @@ namespace ecg {
 
 template <int OPT>
 struct FpK256T {
+  static constexpr int NL = 8;  // 32-bit limbs per field element
+  typedef FeN<8> FeT;
+  typedef JacN<8> JacT;
+  typedef AffN<8> AffT;
   static constexpr uint32_t C0 = 977u;  // C = 2^32 + 977
   // OPT bits 6/7: the doubling / mixed addition trade one multiplication for a squaring + 4 linear ops
   static constexpr bool SQR_TRADE_DBL = (OPT & 64) != 0;

@@ -29,6 +29,10 @@ namespace ecg {
 
 template <int OPT>
 struct FpP256T {
+  static constexpr int NL = 8;  // 32-bit limbs per field element
+  typedef FeN<8> FeT;
+  typedef JacN<8> JacT;
+  typedef AffN<8> AffT;
   // the P-256 squaring is bound by its reduction's adds, not by products: no multiplication-for-squaring trades
   static constexpr bool SQR_TRADE_DBL = false;
   static constexpr bool SQR_TRADE_MADD = false;

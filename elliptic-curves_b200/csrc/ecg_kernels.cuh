@@ -47,18 +47,20 @@ ECG_DEV void soa_load(uint32_t* v, const uint32_t* buf, size_t n, size_t idx, in
 // caller still runs the arithmetic on a harmless substitute (k = 1, P = G) and forces Z = 0 afterwards so
 // that warps stay converged.
 template <class C>
-ECG_DEV uint32_t load_pair(uint32_t* k, Aff& P, bool& inf, const uint8_t* kb,
+ECG_DEV uint32_t load_pair(uint32_t* k, typename C::F::AffT& P, bool& inf, const uint8_t* kb,
                                               const uint8_t* pxy, const uint8_t* pinf, size_t idx) {
   typedef typename C::F F;
+  typedef typename F::FeT Fe;
+  constexpr int NL = F::NL, FB = 4 * F::NL;  // limbs and bytes per field element / scalar
   uint32_t err = 0;
-  load_be32(k, kb + 32 * idx);
-  if (!lt8(k, C::N())) err |= ERRF_SCALAR;
+  load_be<NL>(k, kb + FB * idx);
+  if (!ltN<NL>(k, C::N())) err |= ERRF_SCALAR;
   inf = pinf != nullptr && pinf[idx] != 0;
   Fe x, y;
-  load_be32(x.v, pxy + 64 * idx);
-  load_be32(y.v, pxy + 64 * idx + 32);
+  load_be<NL>(x.v, pxy + 2 * FB * idx);
+  load_be<NL>(y.v, pxy + 2 * FB * idx + FB);
   if (!inf) {
-    bool ok = lt8(x.v, C::P()) && lt8(y.v, C::P());
+    bool ok = ltN<NL>(x.v, C::P()) && ltN<NL>(y.v, C::P());
     F::from_canonical(P.x, x);
     F::from_canonical(P.y, y);
     if (ok) {
@@ -71,7 +73,7 @@ ECG_DEV uint32_t load_pair(uint32_t* k, Aff& P, bool& inf, const uint8_t* kb,
   if (inf || err) {
     C::generator(P);
 #pragma unroll
-    for (int i = 0; i < 8; i++) k[i] = (i == 0);
+    for (int i = 0; i < NL; i++) k[i] = (i == 0);
   }
   return err;
 }
@@ -116,20 +118,21 @@ ECG_KERNEL(BLOCK, MINBLK)
                            const uint8_t* __restrict__ pinf, size_t n, uint32_t* __restrict__ jac,
                            uint32_t* __restrict__ gtab, uint32_t* __restrict__ status, size_t base) {
   typedef typename C::F F;
+  constexpr int NL = F::NL;
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   if (idx >= n) return;
-  uint32_t k[8];
-  Aff P;
+  uint32_t k[NL];
+  typename F::AffT P;
   bool inf;
   uint32_t err = load_pair<C>(k, P, inf, kb, pxy, pinf, idx);
   if (err) report_error(status, err, base + idx);
-  TabRefJ tab{gtab + (size_t)blockIdx.x * BLOCK * P_TAB_WORDS + threadIdx.x, (uint32_t)BLOCK};
-  Jac r;
+  TabRefJN<NL> tab{gtab + (size_t)blockIdx.x * BLOCK * (8 * 3 * NL) + threadIdx.x, (uint32_t)BLOCK};  // 8 Jacobian entries
+  typename F::JacT r;
   generic_mul_thread<F, C::A_IS_MINUS3>(r, k, P, tab);
   if (inf || err) F::set_zero(r.Z);
-  soa_store<8>(jac, n, idx, r.X.v, 0);
-  soa_store<8>(jac, n, idx, r.Y.v, 8);
-  soa_store<8>(jac, n, idx, r.Z.v, 16);
+  soa_store<NL>(jac, n, idx, r.X.v, 0);
+  soa_store<NL>(jac, n, idx, r.Y.v, NL);
+  soa_store<NL>(jac, n, idx, r.Z.v, 2 * NL);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -140,27 +143,39 @@ ECG_KERNEL(BLOCK, MINBLK)
 // same idea (precomputed multiples of G, only additions at run time), sized for a 126 MB L2 instead of a
 // 30 KiB L1: 16 sixteen-bit windows -> 17 mixed additions and no doubling per scalar.
 #define FB_W 16
-#define FB_WINDOWS 16
 #define FB_ENTRIES (1u << (FB_W - 1))
-#define FB_TABLE_POINTS ((size_t)FB_WINDOWS * FB_ENTRIES + 1)
+// 16-bit windows over an NL-limb scalar: 2*NL windows (16 for the 256-bit curves, 24 for P-384) + the implicit top digit
+#define FB_WINDOWS_NL(NL) (2 * (NL))
+#define FB_TABLE_POINTS_NL(NL) ((size_t)FB_WINDOWS_NL(NL) * FB_ENTRIES + 1)
+#define FB_WINDOWS FB_WINDOWS_NL(8)
+#define FB_TABLE_POINTS FB_TABLE_POINTS_NL(8)
 
-ECG_DEV void fb_load_entry(Aff& e, const uint32_t* __restrict__ table, size_t point) {
-  const uint4* p = reinterpret_cast<const uint4*>(table + point * 16);
-  uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
-  e.x.v[0] = a.x; e.x.v[1] = a.y; e.x.v[2] = a.z; e.x.v[3] = a.w;
-  e.x.v[4] = b.x; e.x.v[5] = b.y; e.x.v[6] = b.z; e.x.v[7] = b.w;
-  e.y.v[0] = c.x; e.y.v[1] = c.y; e.y.v[2] = c.z; e.y.v[3] = c.w;
-  e.y.v[4] = d.x; e.y.v[5] = d.y; e.y.v[6] = d.z; e.y.v[7] = d.w;
+// one table entry = x[NL], y[NL] (internal form), read as 128-bit loads
+template <int NL>
+ECG_DEV void fb_load_entry(AffN<NL>& e, const uint32_t* __restrict__ table, size_t point) {
+  const uint4* p = reinterpret_cast<const uint4*>(table + point * (2 * NL));
+  uint32_t w[2 * NL];
+#pragma unroll
+  for (int q = 0; q < NL / 2; q++) {
+    uint4 v = __ldg(p + q);
+    w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+  }
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    e.x.v[i] = w[i];
+    e.y.v[i] = w[NL + i];
+  }
 }
 
 // acc += k*G (acc Jacobian on the true curve; pass Z = 0 to start from the identity)
 template <class C, bool FROM_IDENTITY>
-ECG_DEV void fixedbase_accumulate(Jac& acc, const uint32_t* k, const uint32_t* __restrict__ table) {
+ECG_DEV void fixedbase_accumulate(typename C::F::JacT& acc, const uint32_t* k, const uint32_t* __restrict__ table) {
   typedef typename C::F F;
-  FullRecode rc;
-  recode_full(rc, k);
-  Aff e;
-  fb_load_entry(e, table, (size_t)FB_WINDOWS * FB_ENTRIES);  // 2^256 * G
+  constexpr int NL = F::NL, NW = FB_WINDOWS_NL(F::NL);
+  FullRecodeN<NL> rc;
+  recode_full<NL>(rc, k);
+  typename F::AffT e;
+  fb_load_entry<NL>(e, table, (size_t)NW * FB_ENTRIES);  // 2^(32 NL) * G
   if (FROM_IDENTITY) {
     acc.X = e.x;
     acc.Y = e.y;
@@ -169,21 +184,21 @@ ECG_DEV void fixedbase_accumulate(Jac& acc, const uint32_t* k, const uint32_t* _
     jac_madd<F, C::A_IS_MINUS3>(acc, acc, e);
   }
 #pragma unroll 1
-  for (int i = 0; i < FB_WINDOWS; i++) {
+  for (int i = 0; i < NW; i++) {
     uint32_t w = rc.h[0] & 0xFFFFu;
 #pragma unroll
-    for (int j = 0; j < 7; j++) rc.h[j] = funnel_r(rc.h[j], rc.h[j + 1], 16);
-    rc.h[7] >>= 16;
+    for (int j = 0; j < NL - 1; j++) rc.h[j] = funnel_r(rc.h[j], rc.h[j + 1], 16);
+    rc.h[NL - 1] >>= 16;
     uint32_t pos = w >> (FB_W - 1);
     uint32_t idx = pos ? (w & (FB_ENTRIES - 1)) : (FB_ENTRIES - 1 - w);
-    fb_load_entry(e, table, (size_t)i * FB_ENTRIES + idx);
+    fb_load_entry<NL>(e, table, (size_t)i * FB_ENTRIES + idx);
     fe_cneg<F>(e.y, pos ^ 1u);
     jac_madd<F, C::A_IS_MINUS3>(acc, acc, e);
   }
   // parity correction: subtract G if k was even
-  fb_load_entry(e, table, 0);
+  fb_load_entry<NL>(e, table, 0);
   F::neg(e.y, e.y);
-  Jac t;
+  typename F::JacT t;
   jac_madd<F, C::A_IS_MINUS3>(t, acc, e);
   jac_csel(acc, t, rc.even);
 }
@@ -193,22 +208,23 @@ ECG_KERNEL(128, 4)
     fixedbase_kernel(const uint8_t* __restrict__ kb, size_t n, const uint32_t* __restrict__ table,
                      uint32_t* __restrict__ jac, uint32_t* __restrict__ status, size_t base) {
   typedef typename C::F F;
+  constexpr int NL = F::NL;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
-  uint32_t k[8];
-  load_be32(k, kb + 32 * idx);
-  bool bad = !lt8(k, C::N());
+  uint32_t k[NL];
+  load_be<NL>(k, kb + 4 * NL * idx);
+  bool bad = !ltN<NL>(k, C::N());
   if (bad) {
     report_error(status, ERRF_SCALAR, base + idx);
 #pragma unroll
-    for (int i = 0; i < 8; i++) k[i] = (i == 0);
+    for (int i = 0; i < NL; i++) k[i] = (i == 0);
   }
-  Jac acc;
+  typename F::JacT acc;
   fixedbase_accumulate<C, true>(acc, k, table);
   if (bad) F::set_zero(acc.Z);
-  soa_store<8>(jac, n, idx, acc.X.v, 0);
-  soa_store<8>(jac, n, idx, acc.Y.v, 8);
-  soa_store<8>(jac, n, idx, acc.Z.v, 16);
+  soa_store<NL>(jac, n, idx, acc.X.v, 0);
+  soa_store<NL>(jac, n, idx, acc.Y.v, NL);
+  soa_store<NL>(jac, n, idx, acc.Z.v, 2 * NL);
 }
 
 // a*G + b*P : variable-base thread routine, then the fixed-base accumulation on the same accumulator.
@@ -463,22 +479,23 @@ ECG_KERNEL(128)
   valid[idx] = ok ? 1 : 0;
 }
 
-// canonical affine big-endian bytes (n*64) -> table words (internal form); used once, when a table is built
+// canonical affine big-endian bytes (n * 2FB) -> table words (internal form); used once, when a table is built
 template <class C>
 ECG_KERNEL(256)
     affine_to_table_kernel(const uint8_t* __restrict__ xy, size_t n, uint32_t* __restrict__ table) {
   typedef typename C::F F;
+  constexpr int NL = F::NL, FB = 4 * F::NL;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
-  Fe x, y;
-  load_be32(x.v, xy + 64 * idx);
-  load_be32(y.v, xy + 64 * idx + 32);
+  typename F::FeT x, y;
+  load_be<NL>(x.v, xy + 2 * FB * idx);
+  load_be<NL>(y.v, xy + 2 * FB * idx + FB);
   F::from_canonical(x, x);
   F::from_canonical(y, y);
 #pragma unroll
-  for (int w = 0; w < 8; w++) {
-    table[idx * 16 + w] = x.v[w];
-    table[idx * 16 + 8 + w] = y.v[w];
+  for (int w = 0; w < NL; w++) {
+    table[idx * (2 * NL) + w] = x.v[w];
+    table[idx * (2 * NL) + NL + w] = y.v[w];
   }
 }
 
@@ -488,37 +505,39 @@ template <class C>
 ECG_KERNEL(128)
     jac_sum_kernel(const uint32_t* __restrict__ in, size_t n_in, uint32_t* __restrict__ out, size_t n_out) {
   typedef typename C::F F;
+  constexpr int NL = F::NL;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_out) return;
-  Jac acc;
+  typename F::JacT acc;
   F::set_zero(acc.X);
   F::set_one(acc.Y);
   F::set_zero(acc.Z);
   for (size_t idx = t; idx < n_in; idx += n_out) {
-    Jac p;
-    soa_load<8>(p.X.v, in, n_in, idx, 0);
-    soa_load<8>(p.Y.v, in, n_in, idx, 8);
-    soa_load<8>(p.Z.v, in, n_in, idx, 16);
+    typename F::JacT p;
+    soa_load<NL>(p.X.v, in, n_in, idx, 0);
+    soa_load<NL>(p.Y.v, in, n_in, idx, NL);
+    soa_load<NL>(p.Z.v, in, n_in, idx, 2 * NL);
     jac_add<F, C::A_IS_MINUS3>(acc, acc, p);
   }
-  soa_store<8>(out, n_out, t, acc.X.v, 0);
-  soa_store<8>(out, n_out, t, acc.Y.v, 8);
-  soa_store<8>(out, n_out, t, acc.Z.v, 16);
+  soa_store<NL>(out, n_out, t, acc.X.v, 0);
+  soa_store<NL>(out, n_out, t, acc.Y.v, NL);
+  soa_store<NL>(out, n_out, t, acc.Z.v, 2 * NL);
 }
 
-// SoA internal Jacobian -> AoS canonical big-endian X||Y||Z (96 bytes per point)
+// SoA internal Jacobian -> AoS canonical big-endian X||Y||Z (3 FB bytes per point)
 template <class C>
 ECG_KERNEL(128)
     export_jac_kernel(const uint32_t* __restrict__ jac, size_t n, uint8_t* __restrict__ xyz) {
   typedef typename C::F F;
+  constexpr int NL = F::NL, FB = 4 * F::NL;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
 #pragma unroll 1
   for (int c = 0; c < 3; c++) {
-    Fe v;
-    soa_load<8>(v.v, jac, n, idx, 8 * c);
+    typename F::FeT v;
+    soa_load<NL>(v.v, jac, n, idx, NL * c);
     F::to_canonical(v, v);
-    store_be32(xyz + 96 * idx + 32 * c, v.v);
+    store_be<NL>(xyz + 3 * FB * idx + FB * c, v.v);
   }
 }
 
@@ -526,13 +545,15 @@ ECG_KERNEL(128)
 // Jacobian (SoA) -> canonical affine bytes with Montgomery's trick along each thread's strided slice:
 // thread t owns elements t, t+T, t+2T, ... ; one field inversion per thread, 7 field multiplications per
 // element.  Replaces batch_normalize / BatchInvert (k256/src/arithmetic/projective.rs:367-391,
-// k256/src/arithmetic/field.rs:244-291).  scr: 8*n words of scratch (prefix products).
-// X_ONLY: write only the x coordinate (32-byte records): ECDH's SharedSecret is affine.x alone (k256/src/ecdh.rs:56-60),
+// k256/src/arithmetic/field.rs:244-291).  scr: NL*n words of scratch (prefix products).
+// X_ONLY: write only the x coordinate (FB-byte records): ECDH's SharedSecret is affine.x alone (k256/src/ecdh.rs:56-60),
 // which saves the Z^-3 and y products (2 of the 7 multiplications per element) and half of the output bytes.
 template <class F, bool X_ONLY = false>
 ECG_KERNEL(256)
     normalize_kernel(const uint32_t* __restrict__ jac, size_t n, uint32_t* __restrict__ scr,
                      uint8_t* __restrict__ out_xy, uint8_t* __restrict__ out_inf) {
+  typedef typename F::FeT Fe;
+  constexpr int NL = F::NL, FB = 4 * F::NL;
   size_t T = (size_t)gridDim.x * blockDim.x;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
@@ -542,24 +563,24 @@ ECG_KERNEL(256)
   size_t last = t;
   for (size_t idx = t; idx < n; idx += T) {
     Fe z;
-    soa_load<8>(z.v, jac, n, idx, 16);
+    soa_load<NL>(z.v, jac, n, idx, 2 * NL);
     if (F::is_zero(z)) z = one;
-    soa_store<8>(scr, n, idx, acc.v, 0);
+    soa_store<NL>(scr, n, idx, acc.v, 0);
     F::mul(acc, acc, z);
     last = idx;
   }
   Fe inv;
   F::inv(inv, acc);
   for (size_t idx = last;; idx -= T) {
-    Jac p;
-    soa_load<8>(p.Z.v, jac, n, idx, 16);
+    typename F::JacT p;
+    soa_load<NL>(p.Z.v, jac, n, idx, 2 * NL);
     bool inf = F::is_zero(p.Z);
     if (inf) p.Z = one;
     Fe pre, zinv;
-    soa_load<8>(pre.v, scr, n, idx, 0);
+    soa_load<NL>(pre.v, scr, n, idx, 0);
     F::mul(zinv, inv, pre);
     F::mul(inv, inv, p.Z);
-    soa_load<8>(p.X.v, jac, n, idx, 0);
+    soa_load<NL>(p.X.v, jac, n, idx, 0);
     Fe x, y;
     if (X_ONLY) {
       Fe z2;
@@ -567,23 +588,23 @@ ECG_KERNEL(256)
       F::mul(x, p.X, z2);
       F::to_canonical(x, x);
       if (inf) F::set_zero(x);
-      store_be32(out_xy + 32 * idx, x.v);
+      store_be<NL>(out_xy + FB * idx, x.v);
     } else {
-      soa_load<8>(p.Y.v, jac, n, idx, 8);
+      soa_load<NL>(p.Y.v, jac, n, idx, NL);
       jac_to_affine_canonical<F>(x, y, p, zinv);
       if (inf) {
         F::set_zero(x);
         F::set_zero(y);
       }
-      store_be32(out_xy + 64 * idx, x.v);
-      store_be32(out_xy + 64 * idx + 32, y.v);
+      store_be<NL>(out_xy + 2 * FB * idx, x.v);
+      store_be<NL>(out_xy + 2 * FB * idx + FB, y.v);
     }
     out_inf[idx] = inf ? 1 : 0;
     if (idx < T) break;
   }
 }
 
-// AoS big-endian X||Y||Z (n*96 bytes, canonical) -> SoA internal form; validates coordinates < p.
+// AoS big-endian X||Y||Z (n * 3FB bytes, canonical) -> SoA internal form; validates coordinates < p.
 // HOM: the input is the reference's own homogeneous projective form (x = X/Z, y = Y/Z, identity (0:1:0):
 // k256/src/arithmetic/projective.rs:49-53,64-75; primeorder/src/projective.rs) and is carried over to the Jacobian
 // point (X Z : Y Z^2 : Z), which has the same affine image: one squaring and two multiplications per point here, so
@@ -593,14 +614,16 @@ ECG_KERNEL(256)
     import_jac_kernel(const uint8_t* __restrict__ xyz, size_t n, uint32_t* __restrict__ jac,
                       uint32_t* __restrict__ status, size_t base) {
   typedef typename C::F F;
+  typedef typename F::FeT Fe;
+  constexpr int NL = F::NL, FB = 4 * F::NL;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   Fe co[3];
 #pragma unroll 1
   for (int c = 0; c < 3; c++) {
     Fe v;
-    load_be32(v.v, xyz + 96 * idx + 32 * c);
-    if (!lt8(v.v, C::P())) report_error(status, ERRF_POINT, base + idx);
+    load_be<NL>(v.v, xyz + 3 * FB * idx + FB * c);
+    if (!ltN<NL>(v.v, C::P())) report_error(status, ERRF_POINT, base + idx);
     F::from_canonical(co[c], v);
   }
   if (HOM) {
@@ -610,7 +633,7 @@ ECG_KERNEL(256)
     F::mul(co[1], co[1], zz);
   }
 #pragma unroll 1
-  for (int c = 0; c < 3; c++) soa_store<8>(jac, n, idx, co[c].v, 8 * c);
+  for (int c = 0; c < 3; c++) soa_store<NL>(jac, n, idx, co[c].v, NL * c);
 }
 
 // out[i] = the square root the reference returns, a^((p+1)/4) (FieldElement::sqrt, k256/src/arithmetic/field.rs:200-235,
@@ -645,16 +668,17 @@ ECG_KERNEL(256)
     field_op_kernel(int op, size_t n, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
                     uint8_t* __restrict__ out, uint32_t* __restrict__ status, size_t base) {
   typedef typename C::F F;
+  constexpr int NL = F::NL, FB = 4 * F::NL;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
-  Fe x, y, r;
-  load_be32(x.v, a + 32 * idx);
-  if (!lt8(x.v, C::P())) report_error(status, ERRF_POINT, base + idx);
+  typename F::FeT x, y, r;
+  load_be<NL>(x.v, a + FB * idx);
+  if (!ltN<NL>(x.v, C::P())) report_error(status, ERRF_POINT, base + idx);
   F::from_canonical(x, x);
   bool binary = (op == ECG_FOP_ADD || op == ECG_FOP_SUB || op == ECG_FOP_MUL);
   if (binary) {
-    load_be32(y.v, b + 32 * idx);
-    if (!lt8(y.v, C::P())) report_error(status, ERRF_POINT, base + idx);
+    load_be<NL>(y.v, b + FB * idx);
+    if (!ltN<NL>(y.v, C::P())) report_error(status, ERRF_POINT, base + idx);
     F::from_canonical(y, y);
   } else {
     y = x;
@@ -668,6 +692,6 @@ ECG_KERNEL(256)
     default: F::inv(r, x); break;
   }
   F::to_canonical(r, r);
-  store_be32(out + 32 * idx, r.v);
+  store_be<NL>(out + FB * idx, r.v);
 }
 

@@ -19,45 +19,49 @@ namespace ecg {
 // Window-table accessor: entry e (0..7), word w (0..15: x[0..7], y[0..7]) lives at base[(e*16+w)*stride].
 // In the kernels base = slot + threadIdx.x and stride = blockDim.x: the 32 lanes of a warp touch 32 consecutive
 // words of each row they select (coalesced when lanes agree on the entry, at worst 8 rows when they do not).
-struct TabRef {
+template <int NL>
+struct TabRefN {
   uint32_t* base;
   uint32_t stride;
-  ECG_D void store(int e, const Fe& x, const Fe& y) const {
+  ECG_D void store(int e, const FeN<NL>& x, const FeN<NL>& y) const {
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
-      base[(e * 16 + w) * stride] = x.v[w];
-      base[(e * 16 + 8 + w) * stride] = y.v[w];
+    for (int w = 0; w < NL; w++) {
+      base[(e * 2 * NL + w) * stride] = x.v[w];
+      base[(e * 2 * NL + NL + w) * stride] = y.v[w];
     }
   }
-  ECG_D void load(int e, Fe& x, Fe& y) const {
+  ECG_D void load(int e, FeN<NL>& x, FeN<NL>& y) const {
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
-      x.v[w] = base[(e * 16 + w) * stride];
-      y.v[w] = base[(e * 16 + 8 + w) * stride];
+    for (int w = 0; w < NL; w++) {
+      x.v[w] = base[(e * 2 * NL + w) * stride];
+      y.v[w] = base[(e * 2 * NL + NL + w) * stride];
     }
   }
 };
-// Same, for Jacobian entries (24 words: X, Y, Z).
-struct TabRefJ {
+typedef TabRefN<8> TabRef;
+// Same, for Jacobian entries (3*NL words: X, Y, Z).
+template <int NL>
+struct TabRefJN {
   uint32_t* base;
   uint32_t stride;
-  ECG_D void store(int e, const Jac& p) const {
+  ECG_D void store(int e, const JacN<NL>& p) const {
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
-      base[(e * 24 + w) * stride] = p.X.v[w];
-      base[(e * 24 + 8 + w) * stride] = p.Y.v[w];
-      base[(e * 24 + 16 + w) * stride] = p.Z.v[w];
+    for (int w = 0; w < NL; w++) {
+      base[(e * 3 * NL + w) * stride] = p.X.v[w];
+      base[(e * 3 * NL + NL + w) * stride] = p.Y.v[w];
+      base[(e * 3 * NL + 2 * NL + w) * stride] = p.Z.v[w];
     }
   }
-  ECG_D void load(int e, Jac& p) const {
+  ECG_D void load(int e, JacN<NL>& p) const {
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
-      p.X.v[w] = base[(e * 24 + w) * stride];
-      p.Y.v[w] = base[(e * 24 + 8 + w) * stride];
-      p.Z.v[w] = base[(e * 24 + 16 + w) * stride];
+    for (int w = 0; w < NL; w++) {
+      p.X.v[w] = base[(e * 3 * NL + w) * stride];
+      p.Y.v[w] = base[(e * 3 * NL + NL + w) * stride];
+      p.Z.v[w] = base[(e * 3 * NL + 2 * NL + w) * stride];
     }
   }
 };
+typedef TabRefJN<8> TabRefJ;
 
 ECG_D void k256_beta(Fe& b) {
   // ENDOMORPHISM_BETA, k256/src/arithmetic/projective.rs:32-37
@@ -183,9 +187,11 @@ ECG_D void k256_mul_thread(Jac& r, const uint32_t* k, const Aff& P, const TabRef
 // odd multiples kept in Jacobian form (the shared-denominator trick of build_table_iso_a0 needs a = 0).
 // Replaces primeorder ProjectivePoint::mul / mul_vartime (primeorder/src/projective.rs:133-144, :532-557).
 template <class F, bool A_IS_MINUS3, int PHASE_SYNC = 0>
-ECG_D void generic_mul_thread(Jac& r, const uint32_t* k, const Aff& P, const TabRefJ& tab) {
-  FullRecode rc;
-  recode_full(rc, k);
+ECG_D void generic_mul_thread(typename F::JacT& r, const uint32_t* k, const typename F::AffT& P, const TabRefJN<F::NL>& tab) {
+  typedef typename F::JacT Jac;
+  typedef typename F::AffT Aff;
+  FullRecodeN<F::NL> rc;
+  recode_full<F::NL>(rc, k);
   Jac d, cur, acc;
   aff_dbl<F, A_IS_MINUS3>(d, P);
   cur.X = P.x;
@@ -201,14 +207,14 @@ ECG_D void generic_mul_thread(Jac& r, const uint32_t* k, const Aff& P, const Tab
     tab.store(i, cur);
   }
 #pragma unroll 1
-  for (int i = 0; i < 64; i++) {
+  for (int i = 0; i < F::NL * 8; i++) {  // one 4-bit window per nibble of the scalar
 #pragma unroll 1
     for (int j = 0; j < 4; j++) {
       if (PHASE_SYNC == 2) ECG_BLOCK_SYNC();
       jac_dbl<F, A_IS_MINUS3>(acc, acc);
     }
     if (PHASE_SYNC == 2) ECG_BLOCK_SYNC();
-    uint32_t n = next_window8(rc.h);
+    uint32_t n = next_windowN<F::NL>(rc.h);
     uint32_t pos = n >> 3;
     uint32_t idx = pos ? (n & 7u) : (7u - n);
     Jac e;

@@ -15,25 +15,24 @@
 
 namespace ecg {
 
-struct Jac {
-  Fe X, Y, Z;
-};
-struct Aff {
-  Fe x, y;
-};
+// JacN / AffN live in ecg_prim.cuh; the 8-limb names are kept for the secp256k1-only code.  The templates below take
+// their types from the field policy (F::FeT, F::JacT, F::AffT), so the same formulas serve 8- and 12-limb fields.
+typedef JacN<8> Jac;
+typedef AffN<8> Aff;
 
 // a = c ? -a : a  (branch-free: lanes of a warp disagree on c)
 template <class F>
-ECG_D void fe_cneg(Fe& a, uint32_t c) {
-  Fe n;
+ECG_D void fe_cneg(typename F::FeT& a, uint32_t c) {
+  typename F::FeT n;
   F::neg(n, a);
 #pragma unroll
-  for (int i = 0; i < 8; i++) a.v[i] = c ? n.v[i] : a.v[i];
+  for (int i = 0; i < F::NL; i++) a.v[i] = c ? n.v[i] : a.v[i];
 }
 // r = c ? t : r
-ECG_D void jac_csel(Jac& r, const Jac& t, uint32_t c) {
+template <int NL>
+ECG_D void jac_csel(JacN<NL>& r, const JacN<NL>& t, uint32_t c) {
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
+  for (int i = 0; i < NL; i++) {
     r.X.v[i] = c ? t.X.v[i] : r.X.v[i];
     r.Y.v[i] = c ? t.Y.v[i] : r.Y.v[i];
     r.Z.v[i] = c ? t.Z.v[i] : r.Z.v[i];
@@ -43,7 +42,8 @@ ECG_D void jac_csel(Jac& r, const Jac& t, uint32_t c) {
 // Doubling in "halved" form (Z3 = Y*Z, X3 = X3_std/4, Y3 = Y3_std/8): 3M+4S (a=0; 2M+5S with F::SQR_TRADE_DBL) / 4M+4S (a=-3),
 // 8 cheap linear ops.   L = (3X^2 + a Z^4)/2;  X3 = L^2 - 2XY^2;  Y3 = L(XY^2 - X3) - Y^4.
 template <class F, bool A_IS_MINUS3>
-ECG_D void jac_dbl_body(Jac& r, const Jac& p) {
+ECG_D void jac_dbl_body(typename F::JacT& r, const typename F::JacT& p) {
+  typedef typename F::FeT Fe;
   Fe A, L, T, D, t, zz;
   F::sqr(A, p.Y);  // Y^2
   if (A_IS_MINUS3) {
@@ -92,13 +92,13 @@ ECG_D void jac_dbl_body(Jac& r, const Jac& p) {
 #define ECG_NOINLINE_PT
 #endif
 template <class F, bool A_IS_MINUS3>
-ECG_NOINLINE_PT Jac jac_dbl_call(Jac p) {
-  Jac r;
+ECG_NOINLINE_PT typename F::JacT jac_dbl_call(typename F::JacT p) {
+  typename F::JacT r;
   jac_dbl_body<typename F::Inline, A_IS_MINUS3>(r, p);
   return r;
 }
 template <class F, bool A_IS_MINUS3>
-ECG_D void jac_dbl(Jac& r, const Jac& p) {
+ECG_D void jac_dbl(typename F::JacT& r, const typename F::JacT& p) {
   if (F::DBL_CALL)
     r = jac_dbl_call<F, A_IS_MINUS3>(p);
   else
@@ -107,8 +107,8 @@ ECG_D void jac_dbl(Jac& r, const Jac& p) {
 
 // 2*(x,y) for an affine input (Z = 1): saves the Z products.
 template <class F, bool A_IS_MINUS3>
-ECG_D void aff_dbl(Jac& r, const Aff& p) {
-  Jac j;
+ECG_D void aff_dbl(typename F::JacT& r, const typename F::AffT& p) {
+  typename F::JacT j;
   j.X = p.x;
   j.Y = p.y;
   F::set_one(j.Z);  // internal-form one
@@ -123,7 +123,7 @@ __device__ __noinline__
 inline
 #endif
     void
-    jac_madd_slow(Jac& r, const Jac& p, const Aff& q, bool z1zero, bool rzero) {
+    jac_madd_slow(typename F::JacT& r, const typename F::JacT& p, const typename F::AffT& q, bool z1zero, bool rzero) {
   if (z1zero) {  // O + Q = Q
     r.X = q.x;
     r.Y = q.y;
@@ -139,7 +139,8 @@ inline
 
 // r = p + q, q affine and not the identity.  8M+3S (7M+4S with F::SQR_TRADE_MADD).  If zr != nullptr it receives Z3/Z1 (= H).
 template <class F, bool A_IS_MINUS3>
-ECG_D void jac_madd_body(Jac& r, const Jac& p, const Aff& q, Fe* zr = nullptr) {
+ECG_D void jac_madd_body(typename F::JacT& r, const typename F::JacT& p, const typename F::AffT& q, typename F::FeT* zr = nullptr) {
+  typedef typename F::FeT Fe;
   Fe zz, u2, s2, H, R, hh, hhh, V, t;
   F::sqr(zz, p.Z);
   F::mul(u2, q.x, zz);
@@ -178,13 +179,13 @@ ECG_D void jac_madd_body(Jac& r, const Jac& p, const Aff& q, Fe* zr = nullptr) {
 }
 
 template <class F, bool A_IS_MINUS3>
-ECG_NOINLINE_PT Jac jac_madd_call(Jac p, Aff q) {
-  Jac r;
+ECG_NOINLINE_PT typename F::JacT jac_madd_call(typename F::JacT p, typename F::AffT q) {
+  typename F::JacT r;
   jac_madd_body<typename F::Inline, A_IS_MINUS3>(r, p, q, nullptr);
   return r;
 }
 template <class F, bool A_IS_MINUS3>
-ECG_D void jac_madd(Jac& r, const Jac& p, const Aff& q, Fe* zr = nullptr) {
+ECG_D void jac_madd(typename F::JacT& r, const typename F::JacT& p, const typename F::AffT& q, typename F::FeT* zr = nullptr) {
   if (F::MADD_CALL && zr == nullptr)
     r = jac_madd_call<F, A_IS_MINUS3>(p, q);
   else
@@ -193,7 +194,8 @@ ECG_D void jac_madd(Jac& r, const Jac& p, const Aff& q, Fe* zr = nullptr) {
 
 // r = p + q, both Jacobian.  12M+4S.
 template <class F, bool A_IS_MINUS3>
-ECG_D void jac_add(Jac& r, const Jac& p, const Jac& q) {
+ECG_D void jac_add(typename F::JacT& r, const typename F::JacT& p, const typename F::JacT& q) {
+  typedef typename F::FeT Fe;
   bool z1zero = F::is_zero(p.Z), z2zero = F::is_zero(q.Z);
   if (z1zero) {
     r = q;
@@ -241,7 +243,8 @@ ECG_D void jac_add(Jac& r, const Jac& p, const Jac& q) {
 
 // y^2 == x^3 + a x + b ?   (AffinePoint::from_coordinates on-curve check, k256/src/arithmetic/affine.rs:134-147)
 template <class F, bool A_IS_MINUS3>
-ECG_D bool aff_on_curve(const Aff& p, const Fe& b_internal) {
+ECG_D bool aff_on_curve(const typename F::AffT& p, const typename F::FeT& b_internal) {
+  typedef typename F::FeT Fe;
   Fe l, r, t;
   F::sqr(l, p.y);
   F::sqr(r, p.x);

@@ -179,8 +179,20 @@ inline uint32_t bswap32(uint32_t x) { return __builtin_bswap32(x); }
 #ifndef ECG_FE_ALIGN
 #define ECG_FE_ALIGN 4
 #endif
-struct alignas(ECG_FE_ALIGN) Fe {
-  uint32_t v[8];  // little-endian 32-bit limbs
+// NL 32-bit limbs, little-endian.  8 limbs: secp256k1 / P-256; 12 limbs: P-384.  Everything above the field layer is
+// written against a field policy F (F::NL, F::FeT, F::JacT, F::AffT), so a curve is a policy plus constants.
+template <int NL>
+struct alignas(ECG_FE_ALIGN) FeN {
+  uint32_t v[NL];
+};
+typedef FeN<8> Fe;
+template <int NL>
+struct JacN {  // Jacobian (X:Y:Z) = (X/Z^2, Y/Z^3); Z == 0 (mod p) is the identity
+  FeN<NL> X, Y, Z;
+};
+template <int NL>
+struct AffN {
+  FeN<NL> x, y;
 };
 
 // r = a + b, returns carry-out (0/1)
@@ -196,6 +208,66 @@ ECG_D uint32_t sub8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 #pragma unroll
   for (int i = 1; i < 8; i++) r[i] = subc_cc(a[i], b[i]);
   return 0u - subc(0, 0);
+}
+
+// N-limb versions (N compile-time): r = a + b / a - b with carry / borrow out
+template <int N>
+ECG_D uint32_t addN(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  r[0] = add_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < N; i++) r[i] = addc_cc(a[i], b[i]);
+  return addc(0, 0);
+}
+template <int N>
+ECG_D uint32_t subN(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  r[0] = sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < N; i++) r[i] = subc_cc(a[i], b[i]);
+  return 0u - subc(0, 0);
+}
+
+// N x N -> 2N limb schoolbook product for any even N: the row structure of mul8x8 below with the bounds written in N
+// (products whose low limb lands on an even position accumulate in E, odd positions in O; O[k] holds position k+1).
+// N*N IMAD.WIDE.  Used for the 12-limb field (P-384); the 8-limb fields keep the hand-checked mul8x8.
+template <int N>
+ECG_D void mulNxN(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  constexpr int H = N / 2;
+  uint32_t E[2 * N], O[2 * N];
+#pragma unroll
+  for (int m = 0; m < H; m++) {
+    mul_wide(E[2 * m], E[2 * m + 1], a[2 * m], b[0]);
+    mul_wide(O[2 * m], O[2 * m + 1], a[2 * m + 1], b[0]);
+  }
+#pragma unroll
+  for (int i = 1; i < N; i++) {
+    if (i & 1) {
+      mad_wide_cc(O[i - 1], O[i], a[0], b[i]);
+#pragma unroll
+      for (int m = 1; m < H; m++) madc_wide_cc(O[i - 1 + 2 * m], O[i + 2 * m], a[2 * m], b[i]);
+      O[i + N - 1] = addc(0, 0);
+      mad_wide_cc(E[i + 1], E[i + 2], a[1], b[i]);
+#pragma unroll
+      for (int m = 1; m < H - 1; m++) madc_wide_cc(E[i + 1 + 2 * m], E[i + 2 + 2 * m], a[2 * m + 1], b[i]);
+      if (i == 1)
+        madc_wide_new(E[i + N - 1], E[i + N], a[N - 1], b[i]);
+      else
+        madc_wide_top(E[i + N - 1], E[i + N], a[N - 1], b[i]);
+    } else {
+      mad_wide_cc(E[i], E[i + 1], a[0], b[i]);
+#pragma unroll
+      for (int m = 1; m < H; m++) madc_wide_cc(E[i + 2 * m], E[i + 1 + 2 * m], a[2 * m], b[i]);
+      E[i + N] = addc(0, 0);
+      mad_wide_cc(O[i], O[i + 1], a[1], b[i]);
+#pragma unroll
+      for (int m = 1; m < H - 1; m++) madc_wide_cc(O[i + 2 * m], O[i + 1 + 2 * m], a[2 * m + 1], b[i]);
+      madc_wide_top(O[i + N - 2], O[i + N - 1], a[N - 1], b[i]);
+    }
+  }
+  r[0] = E[0];
+  r[1] = add_cc(E[1], O[0]);
+#pragma unroll
+  for (int k = 2; k < 2 * N - 1; k++) r[k] = addc_cc(E[k], O[k - 1]);
+  r[2 * N - 1] = addc(E[2 * N - 1], O[2 * N - 2]);
 }
 
 // 8x8 -> 16 limb schoolbook product, row-wise, with the "even/odd accumulator" layout: products whose

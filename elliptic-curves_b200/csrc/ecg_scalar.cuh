@@ -35,14 +35,16 @@ ECG_D void mul_limbs(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   }
 }
 
-// a < m ? (8 limbs)
-ECG_D bool lt8(const uint32_t* a, const uint32_t* m) {
+// a < m ? (N limbs)
+template <int N>
+ECG_D bool ltN(const uint32_t* a, const uint32_t* m) {
   uint32_t t = sub_cc(a[0], m[0]);
 #pragma unroll
-  for (int i = 1; i < 8; i++) t = subc_cc(a[i], m[i]);
+  for (int i = 1; i < N; i++) t = subc_cc(a[i], m[i]);
   (void)t;
   return subc(0, 0) != 0;  // borrow => a < m
 }
+ECG_D bool lt8(const uint32_t* a, const uint32_t* m) { return ltN<8>(a, m); }
 
 struct GlvHalf {
   uint32_t h[4];   // (|k_i| made odd) >> 1 : 32 four-bit windows, MSB-first consumption
@@ -133,26 +135,32 @@ ECG_D uint32_t next_window(uint32_t* h) {
 
 // 256-bit scalar, no endomorphism (P-256): k in [0, n) -> odd m = k or k+1 (k+1 <= n-1+1 < 2^256),
 // windows of h = m >> 1 (255 bits -> 64 windows, top window < 8... see kernels), parity flag.
-struct FullRecode {
-  uint32_t h[8];
+// (NL limbs: 8 for the 256-bit curves, 12 for P-384, whose order is also just below 2^384)
+template <int NL>
+struct FullRecodeN {
+  uint32_t h[NL];
   uint32_t even;
 };
-ECG_D void recode_full(FullRecode& o, const uint32_t* k) {
-  uint32_t v[8];
+typedef FullRecodeN<8> FullRecode;
+template <int NL>
+ECG_D void recode_full(FullRecodeN<NL>& o, const uint32_t* k) {
+  uint32_t v[NL];
   o.even = (~k[0]) & 1u;
   v[0] = add_cc(k[0], o.even);
 #pragma unroll
-  for (int i = 1; i < 8; i++) v[i] = addc_cc(k[i], 0);
+  for (int i = 1; i < NL; i++) v[i] = addc_cc(k[i], 0);
 #pragma unroll
-  for (int i = 0; i < 7; i++) o.h[i] = funnel_r(v[i], v[i + 1], 1);
-  o.h[7] = v[7] >> 1;
+  for (int i = 0; i < NL - 1; i++) o.h[i] = funnel_r(v[i], v[i + 1], 1);
+  o.h[NL - 1] = v[NL - 1] >> 1;
 }
-ECG_D uint32_t next_window8(uint32_t* h) {
-  uint32_t n = h[7] >> 28;
+template <int NL>
+ECG_D uint32_t next_windowN(uint32_t* h) {
+  uint32_t n = h[NL - 1] >> 28;
 #pragma unroll
-  for (int i = 7; i > 0; i--) h[i] = (h[i] << 4) | (h[i - 1] >> 28);
+  for (int i = NL - 1; i > 0; i--) h[i] = (h[i] << 4) | (h[i - 1] >> 28);
   h[0] = h[0] << 4;
   return n;
 }
+ECG_D uint32_t next_window8(uint32_t* h) { return next_windowN<8>(h); }
 
 }  // namespace ecg

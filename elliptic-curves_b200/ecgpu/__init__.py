@@ -187,7 +187,16 @@ class Engine:
         raise EcgError(rc, msg, idx)
 
     def set_stream(self, cuda_stream: int):
+        """Run this ctx's work on the caller's CUDA stream (e.g. `torch.cuda.current_stream().cuda_stream`).  PyTorch's
+        default stream has the handle 0, which the C ABI reads as "back to the ctx-owned stream": it is passed as
+        cudaStreamLegacy (1), the explicit name of the same stream, so that the library's kernels are ordered with the
+        producer of their inputs (a collective, a copy) instead of racing on a separate non-blocking stream."""
+        if cuda_stream == 0:
+            cuda_stream = 1  # cudaStreamLegacy
         self._check(self.lib.ecg_ctx_set_stream(self._ctx, ctypes.c_void_p(cuda_stream)))
+
+    def reset_stream(self):
+        self._check(self.lib.ecg_ctx_set_stream(self._ctx, ctypes.c_void_p(0)))
 
     @property
     def kernel_launches(self) -> int:

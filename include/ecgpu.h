@@ -73,7 +73,8 @@ const char* ecg_last_error(const ecg_ctx* ctx);
 size_t ecg_last_error_index(const ecg_ctx* ctx);
 
 /* Run this ctx's work on a caller-provided cudaStream_t (e.g. PyTorch's current stream) instead of the
- * ctx-owned stream; device 0 of the ctx only.  NULL restores the owned stream. */
+ * ctx-owned stream; device 0 of the ctx only.  NULL restores the owned stream (which is non-blocking: it does NOT
+ * synchronise with the legacy default stream) — to run on the legacy default stream itself pass cudaStreamLegacy. */
 ecg_status ecg_ctx_set_stream(ecg_ctx* ctx, void* cuda_stream);
 
 /* out[i] = k[i] * P[i].

@@ -9,6 +9,7 @@ Sources (relative to /root/reference):
   k256/src/test_vectors/group.rs:9   ADD_TEST_VECTORS (k*G, k=1..20)
   k256/src/test_vectors/group.rs:96  MUL_TEST_VECTORS (k, x, y)
   p256/src/test_vectors/group.rs:8,95   same for P-256
+  p384/src/test_vectors/group.rs:8,175  same for P-384 (48-byte values)
   {k256,p256}/src/test_vectors/field.rs:6  DBL_TEST_VECTORS (2^i, 32 B BE)
   {k256,p256}/src/test_vectors/ecdsa.rs    d -> (q_x, q_y) pairs (a k*G fixture each)
   {k256,p256}/benches/point.rs             the criterion bench scalars
@@ -188,6 +189,14 @@ def main():
             json.dump(data, f, indent=1)
         print(path, len(data["group"]["add"]), len(data["group"]["mul"]), len(data["field"]["dbl"]),
               len(data["ecdsa"]["keypairs"]), len(data["bench"]["scalars"]))
+    # P-384: p384/src/test_vectors/group.rs:8,175 (ADD / MUL vectors, 48-byte coordinates),
+    # p384/src/test_vectors/ecdsa.rs (d -> Q pairs); the crate has no field.rs vector file and no benches/point.rs scalars
+    data = {"curve": "p384", "reference_commit": "739304e026fdf06cd1a31606e4db487d3f47c5ae", "group": group_vectors("p384"),
+            "ecdsa": ecdsa_keypairs("p384")}
+    path = os.path.join(OUT, "p384.json")
+    with open(path, "w") as f:
+        json.dump(data, f, indent=1)
+    print(path, len(data["group"]["add"]), len(data["group"]["mul"]), len(data["ecdsa"]["keypairs"]))
 
 
 if __name__ == "__main__":

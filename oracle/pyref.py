@@ -54,7 +54,23 @@ P256 = Curve(
     gx=0x6B17D1F2E12C4247F8BCE6E563A440F277037D812DEB33A0F4A13945D898C296,
     gy=0x4FE342E2FE1A7F9B8EE7EB4A7C0F9E162BCE33576B315ECECBB6406837BF51F5,
 )
-CURVES = {"k256": K256, "p256": P256, 0: K256, 1: P256}
+# next curve through the same templates: p384/src/arithmetic.rs:53-74, p384/src/lib.rs:73,
+# p384/src/arithmetic/field.rs:35
+P384 = Curve(
+    "p384",
+    p=2**384 - 2**128 - 2**96 + 2**32 - 1,
+    n=0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFC7634D81F4372DDF581A0DB248B0A77AECEC196ACCC52973,
+    a=-3,
+    b=0xB3312FA7E23EE7E4988E056BE3F82D19181D9C6EFE8141120314088F5013875AC656398D8A2ED19D2A85C8EDD3EC2AEF,
+    gx=0xAA87CA22BE8B05378EB1C71EF320AD746E1D3B628BA79B9859F741E082542A385502F25DBF55296C3A545E3872760AB7,
+    gy=0x3617DE4A96262C6F5D9E98BF9292DC29F8F41DBD289A147CE9DA3113B5F0B8C00A60B1CE1D7E819D7A431D7C90EA0E5F,
+)
+CURVES = {"k256": K256, "p256": P256, "p384": P384, 0: K256, 1: P256, 2: P384}
+
+
+def fbytes(c: Curve) -> int:
+    """bytes per field element / scalar in the canonical encoding (32, or 48 for P-384)"""
+    return (c.p.bit_length() + 7) // 8
 
 K256_BETA = 0x7AE96A2B657C07106E64479EAC3434E99CF0497512F58995C1396C28719501EE
 K256_LAMBDA = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
@@ -119,22 +135,22 @@ def G(c: Curve):
 
 # ---- canonical encodings used at the C-ABI boundary ----
 
-def enc_scalar(k: int) -> bytes:
-    return k.to_bytes(32, "big")
+def enc_scalar(k: int, nb: int = 32) -> bytes:
+    return k.to_bytes(nb, "big")
 
 
-def enc_point(P) -> tuple[bytes, int]:
-    """(x||y big-endian 64 B, inf flag). Identity = 64 zero bytes + flag 1
-    (AffinePoint::IDENTITY, k256/src/arithmetic/affine.rs:53-57)."""
+def enc_point(P, nb: int = 32) -> tuple[bytes, int]:
+    """(x||y big-endian 2*nb bytes, inf flag). Identity = zero bytes + flag 1
+    (AffinePoint::IDENTITY, k256/src/arithmetic/affine.rs:53-57).  nb = 32, or 48 for P-384."""
     if P is None:
-        return bytes(64), 1
-    return P[0].to_bytes(32, "big") + P[1].to_bytes(32, "big"), 0
+        return bytes(2 * nb), 1
+    return P[0].to_bytes(nb, "big") + P[1].to_bytes(nb, "big"), 0
 
 
-def dec_point(xy: bytes, inf: int):
+def dec_point(xy: bytes, inf: int, nb: int = 32):
     if inf:
         return None
-    return (int.from_bytes(xy[:32], "big"), int.from_bytes(xy[32:64], "big"))
+    return (int.from_bytes(xy[:nb], "big"), int.from_bytes(xy[nb:2 * nb], "big"))
 
 
 # ---- deterministic synthetic inputs (SURVEY.md section 8(d)) ----

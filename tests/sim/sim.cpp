@@ -207,33 +207,69 @@ int sim_p256_is_mont(void) { return FpP256::MONT ? 1 : 0; }
 }  // extern "C"
 template <class F, bool AM3>
 static int sim_generic_mul(const uint8_t* k_be, const uint8_t* P_xy, uint8_t* out_xy, uint8_t* out_inf) {
-  uint32_t k[8];
-  load_be32(k, k_be);
-  Aff P;
-  load_be32(P.x.v, P_xy);
-  load_be32(P.y.v, P_xy + 32);
+  constexpr int NL = F::NL, FB = 4 * F::NL;
+  uint32_t k[NL];
+  load_be<NL>(k, k_be);
+  typename F::AffT P;
+  load_be<NL>(P.x.v, P_xy);
+  load_be<NL>(P.y.v, P_xy + FB);
   F::from_canonical(P.x, P.x);
   F::from_canonical(P.y, P.y);
-  std::vector<uint32_t> tabmem(8 * 24);
-  TabRefJ tab{tabmem.data(), 1};
-  Jac r;
+  std::vector<uint32_t> tabmem(8 * 3 * NL);
+  TabRefJN<NL> tab{tabmem.data(), 1};
+  typename F::JacT r;
   generic_mul_thread<F, AM3>(r, k, P, tab);
   if (F::is_zero(r.Z)) {
-    memset(out_xy, 0, 64);
+    memset(out_xy, 0, 2 * FB);
     *out_inf = 1;
     return 0;
   }
-  Fe zinv, x, y;
+  typename F::FeT zinv, x, y;
   F::inv(zinv, r.Z);
   jac_to_affine_canonical<F>(x, y, r, zinv);
-  store_be32(out_xy, x.v);
-  store_be32(out_xy + 32, y.v);
+  store_be<NL>(out_xy, x.v);
+  store_be<NL>(out_xy + FB, y.v);
   *out_inf = 0;
   return 0;
 }
 extern "C" {
 int sim_p256_mul(const uint8_t* k_be, const uint8_t* P_xy, uint8_t* out_xy, uint8_t* out_inf) {
   return sim_generic_mul<FpP256, true>(k_be, P_xy, out_xy, out_inf);
+}
+// ---- P-384 (12 limbs) ----
+int sim_p384_fe_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  typedef FpP384 F;
+  F::Fe x, y, r;
+  load_be<12>(x.v, a);
+  load_be<12>(y.v, b);
+  switch (op) {
+    case 0: F::add(r, x, y); break;
+    case 1: F::sub(r, x, y); break;
+    case 2: F::mul(r, x, y); break;
+    case 3: F::sqr(r, x); break;
+    case 4: F::neg(r, x); break;
+    case 5: F::half(r, x); break;
+    case 6: F::mul_small(r, x, 3); break;
+    case 7: F::inv(r, x); break;
+    case 8: r = x; break;
+    case 9: F::mul_small(r, x, 8); break;
+    default: return -1;
+  }
+  F::normalize(r, r);
+  store_be<12>(out, r.v);
+  return F::is_zero(r) ? 1 : 0;
+}
+int sim_p384_mul(const uint8_t* k_be, const uint8_t* P_xy, uint8_t* out_xy, uint8_t* out_inf) {
+  return sim_generic_mul<FpP384, true>(k_be, P_xy, out_xy, out_inf);
+}
+int sim_p384_on_curve(const uint8_t* P_xy) {
+  typedef FpP384 F;
+  AffN<12> P;
+  load_be<12>(P.x.v, P_xy);
+  load_be<12>(P.y.v, P_xy + 48);
+  F::Fe b;
+  CurveP384::b_internal(b);
+  return aff_on_curve<F, true>(P, b) ? 1 : 0;
 }
 // experiment variants measured in tools/kbench.cu: a = -3 doubling as 3M+5S, point-level call structure
 int sim_p256_mul_3m5s(const uint8_t* k_be, const uint8_t* P_xy, uint8_t* out_xy, uint8_t* out_inf) {
@@ -377,7 +413,7 @@ static const int SIM_BLOCK = 128;
 
 template <class C>
 static void simk_normalize(std::vector<uint32_t>& jac, size_t n, uint8_t* out_xy, uint8_t* out_inf) {
-  std::vector<uint32_t> scr(8 * n + 8);
+  std::vector<uint32_t> scr(C::F::NL * n + 8);
   size_t threads = (n + 31) / 32;  // as launch_norm: slices of up to 32 elements share one inversion
   sim_launch(threads, 256, [&] { normalize_kernel<typename C::F>(jac.data(), n, scr.data(), out_xy, out_inf); });
 }
@@ -401,10 +437,14 @@ extern "C" int simk_mul_batch(int curve, size_t n, const uint8_t* k, const uint8
     std::vector<uint32_t> gtab(blocks * SIM_BLOCK * K_TAB_WORDS);
     sim_launch(n, SIM_BLOCK, [&] { k256_varbase_kernel<SIM_BLOCK, 4>(k, pxy, pinf, n, jac.data(), gtab.data(), status, 0); });
     simk_normalize<CurveK256>(jac, n, out_xy, out_inf);
-  } else {
+  } else if (curve == 1) {
     std::vector<uint32_t> gtab(blocks * SIM_BLOCK * P_TAB_WORDS);
     sim_launch(n, SIM_BLOCK, [&] { generic_varbase_kernel<CurveP256, SIM_BLOCK, 4>(k, pxy, pinf, n, jac.data(), gtab.data(), status, 0); });
     simk_normalize<CurveP256>(jac, n, out_xy, out_inf);
+  } else {
+    std::vector<uint32_t> jac12(36 * n + 36), gtab(blocks * SIM_BLOCK * (8 * 36));
+    sim_launch(n, SIM_BLOCK, [&] { generic_varbase_kernel<CurveP384, SIM_BLOCK, 4>(k, pxy, pinf, n, jac12.data(), gtab.data(), status, 0); });
+    simk_normalize<CurveP384>(jac12, n, out_xy, out_inf);
   }
   return 0;
 }
