@@ -34,7 +34,7 @@ struct Lane {
   void* buf[B_COUNT] = {nullptr};
   size_t cap[B_COUNT] = {0};
   uint32_t* status = nullptr;    // 2 words: error flags, smallest offending index
-  uint32_t* h_status = nullptr;  // pinned: 2 status words, then 96 bytes for one exported point (h_point())
+  uint32_t* h_status = nullptr;  // pinned: 2 status words, then up to 144 bytes for one exported point (h_point())
   std::vector<cudaEvent_t> evs;  // event pairs bracketing the dominant kernel of every chunk of the current call (ecg_timing)
   size_t ev_used = 0;            // events of `evs` recorded by the current call (2 per chunk)
   bool used = false;  // touched by the current call
@@ -44,7 +44,7 @@ struct Lane {
 struct DevState {
   int dev = 0;
   Lane lane[2];
-  uint32_t* fb_table[2] = {nullptr, nullptr};  // per curve, built lazily (like the reference's LazyLock table)
+  uint32_t* fb_table[3] = {nullptr, nullptr, nullptr};  // per curve, built lazily (like the reference's LazyLock table)
   int sm_count = 148;
 };
 
@@ -136,7 +136,7 @@ extern "C" ecg_status ecg_ctx_create(const int* device_ids, int n_devices, unsig
     for (int l = 0; ok && l < 2; l++) {
       Lane& L = d.lane[l];
       ok = cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) == cudaSuccess &&
-           cudaMalloc((void**)&L.status, 8) == cudaSuccess && cudaMallocHost((void**)&L.h_status, 8 + 96) == cudaSuccess;
+           cudaMalloc((void**)&L.status, 8) == cudaSuccess && cudaMallocHost((void**)&L.h_status, 8 + 144) == cudaSuccess;
     }
     if (!ok) {
       ecg_ctx_destroy(ctx);
@@ -165,7 +165,7 @@ extern "C" void ecg_ctx_destroy(ecg_ctx* ctx) {
       if (L.h_status) cudaFreeHost(L.h_status);
       for (cudaEvent_t e : L.evs) cudaEventDestroy(e);
     }
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < 3; i++)
       if (d.fb_table[i]) cudaFree(d.fb_table[i]);
   }
   delete ctx;
@@ -345,10 +345,28 @@ static ecg_status fail(ecg_ctx* ctx, ecg_status rc) {
 
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
+// bytes per field element / scalar at the ABI (32; 48 for P-384) and 32-bit limbs per field element
+static inline size_t fbytes(ecg_curve c) { return c == ECG_NISTP384 ? 48 : 32; }
+static inline size_t flimbs(ecg_curve c) { return c == ECG_NISTP384 ? 12 : 8; }
+// run a statement with CV bound to the curve's parameter struct (CurveK256 / CurveP256 / CurveP384)
+#define FOR_CURVE(curve, ...)             \
+  do {                                    \
+    if ((curve) == ECG_SECP256K1) {       \
+      typedef CurveK256 CV;               \
+      __VA_ARGS__;                        \
+    } else if ((curve) == ECG_NISTP256) { \
+      typedef CurveP256 CV;               \
+      __VA_ARGS__;                        \
+    } else {                              \
+      typedef CurveP384 CV;               \
+      __VA_ARGS__;                        \
+    }                                     \
+  } while (0)
+
 template <class F>
 static ecg_status launch_normalize(ecg_ctx* ctx, DevState& d, Lane& L, size_t n, const uint32_t* jac, uint8_t* out, uint8_t* oinf,
                                    bool x_only) {
-  ST_TRY(ensure(ctx, L, B_SCR, n * 32));
+  ST_TRY(ensure(ctx, L, B_SCR, n * 4 * F::NL));
   // ~32 elements per thread amortise the per-thread inversion, but never leave SMs idle for small batches
   size_t want_threads = std::max<size_t>((n + 31) / 32, std::min<size_t>(n, (size_t)d.sm_count * 256));
   if (x_only)
@@ -360,18 +378,25 @@ static ecg_status launch_normalize(ecg_ctx* ctx, DevState& d, Lane& L, size_t n,
 }
 static ecg_status launch_norm(ecg_ctx* ctx, DevState& d, Lane& L, ecg_curve curve, size_t n, const uint32_t* jac, uint8_t* out,
                               uint8_t* oinf, bool x_only = false) {
-  return curve == ECG_SECP256K1 ? launch_normalize<FpK256>(ctx, d, L, n, jac, out, oinf, x_only)
-                                : launch_normalize<FpP256>(ctx, d, L, n, jac, out, oinf, x_only);
+  FOR_CURVE(curve, return launch_normalize<CV::F>(ctx, d, L, n, jac, out, oinf, x_only));
+  return ECG_EINVAL;
 }
 
 // launch geometry of the variable-base kernels (registers set the occupancy; tables are in global memory)
 static const int K_BLOCK = 128, K_MINBLK = 4;  // secp256k1: <= 128 registers -> 16 warps/SM (mul = call, sqr inlined: OPT 7)
 static const int P_BLOCK = 128, P_MINBLK = 5;  // P-256   : <= 96 registers -> 20 warps/SM (Montgomery field: 34.09 vs 34.65 ms at (128,4), tools/kbench.cu)
 
+static const int Q_BLOCK = 128, Q_MINBLK = 3;  // P-384   : 12-limb values, <= 168 registers -> 12 warps/SM
+#define Q_TAB_WORDS (8 * 36) /* 8 Jacobian entries x 36 words */
+
+static size_t wave_elems(const DevState& d, ecg_curve curve) {
+  return (size_t)d.sm_count * (curve == ECG_SECP256K1 ? K_MINBLK * K_BLOCK : curve == ECG_NISTP256 ? P_MINBLK * P_BLOCK : Q_MINBLK * Q_BLOCK);
+}
+
 // per-block window-table slots for a launch of n elements
 static ecg_status ensure_tab(ecg_ctx* ctx, Lane& L, ecg_curve curve, size_t n) {
-  size_t block = curve == ECG_SECP256K1 ? K_BLOCK : P_BLOCK;
-  size_t words = curve == ECG_SECP256K1 ? K_TAB_WORDS : P_TAB_WORDS;
+  size_t block = curve == ECG_SECP256K1 ? K_BLOCK : curve == ECG_NISTP256 ? P_BLOCK : Q_BLOCK;
+  size_t words = curve == ECG_SECP256K1 ? K_TAB_WORDS : curve == ECG_NISTP256 ? P_TAB_WORDS : Q_TAB_WORDS;
   size_t blocks = (n + block - 1) / block;
   return ensure(ctx, L, B_TAB, blocks * block * words * 4);
 }
@@ -385,29 +410,34 @@ static ecg_status launch_varbase(ecg_ctx* ctx, DevState& d, Lane& L, ecg_curve c
   DOM_BEGIN(ctx, L);
   if (curve == ECG_SECP256K1)
     k256_varbase_kernel<K_BLOCK, K_MINBLK><<<grid_for(n, K_BLOCK), K_BLOCK, 0, L.s()>>>(dp.k, dp.p, dp.inf, n, jac, gtab, status, base);
-  else
+  else if (curve == ECG_NISTP256)
     generic_varbase_kernel<CurveP256, P_BLOCK, P_MINBLK><<<grid_for(n, P_BLOCK), P_BLOCK, 0, L.s()>>>(dp.k, dp.p, dp.inf, n, jac, gtab, status, base);
+  else
+    generic_varbase_kernel<CurveP384, Q_BLOCK, Q_MINBLK><<<grid_for(n, Q_BLOCK), Q_BLOCK, 0, L.s()>>>(dp.k, dp.p, dp.inf, n, jac, gtab, status, base);
   LAUNCHED(ctx);
   DOM_END(ctx, L);
   return ECG_OK;
 }
 
-static bool curve_ok(ecg_curve c) { return c == ECG_SECP256K1 || c == ECG_NISTP256; }
+// every curve the hot path serves; curve_256() = the two 256-bit curves the widening entries (verification, SEC1
+// decompression, a*G + b*P, field sqrt) are written for
+static bool curve_ok(ecg_curve c) { return c == ECG_SECP256K1 || c == ECG_NISTP256 || c == ECG_NISTP384; }
+static bool curve_256(ecg_curve c) { return c == ECG_SECP256K1 || c == ECG_NISTP256; }
 
 // ---- fixed-base table ------------------------------------------------------------------------------
 // Built on the device with the variable-base kernel itself: entry (i, j) = ((2j+1) << 16 i mod n) * G.
-static void scalar_be_from_shifted(uint8_t* out, uint64_t odd, int shift_bits, const uint32_t* n_le) {
-  // v = odd << shift_bits  (< 2^257), reduced once by n (v < 2n always holds: n > 2^255 for both curves)
-  uint32_t v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+static void scalar_be_from_shifted(uint8_t* out, uint64_t odd, int shift_bits, const uint32_t* n_le, int nl) {
+  // v = odd << shift_bits  (< 2^(32 nl + 1)), reduced once by n (v < 2n always holds: n > 2^(32 nl - 1) for these curves)
+  uint32_t v[14] = {0};
   int w = shift_bits / 32, b = shift_bits % 32;
   uint64_t lo = odd << b;  // odd < 2^17, b < 32
   v[w] = (uint32_t)lo;
-  if (w + 1 < 10) v[w + 1] = (uint32_t)(lo >> 32);
-  uint32_t nn[9];
-  for (int i = 0; i < 8; i++) nn[i] = n_le[i];
-  nn[8] = 0;
+  if (w + 1 < 14) v[w + 1] = (uint32_t)(lo >> 32);
+  uint32_t nn[13];
+  for (int i = 0; i < nl; i++) nn[i] = n_le[i];
+  nn[nl] = 0;
   bool ge = true;
-  for (int i = 8; i >= 0; i--) {
+  for (int i = nl; i >= 0; i--) {
     if (v[i] != nn[i]) {
       ge = v[i] > nn[i];
       break;
@@ -415,17 +445,18 @@ static void scalar_be_from_shifted(uint8_t* out, uint64_t odd, int shift_bits, c
   }
   if (ge) {
     uint64_t borrow = 0;
-    for (int i = 0; i < 9; i++) {
+    for (int i = 0; i <= nl; i++) {
       uint64_t t = (uint64_t)v[i] - nn[i] - borrow;
       v[i] = (uint32_t)t;
       borrow = (t >> 63) & 1;
     }
   }
-  for (int i = 0; i < 8; i++) {
-    out[31 - 4 * i] = (uint8_t)v[i];
-    out[30 - 4 * i] = (uint8_t)(v[i] >> 8);
-    out[29 - 4 * i] = (uint8_t)(v[i] >> 16);
-    out[28 - 4 * i] = (uint8_t)(v[i] >> 24);
+  const int nb = 4 * nl;
+  for (int i = 0; i < nl; i++) {
+    out[nb - 1 - 4 * i] = (uint8_t)v[i];
+    out[nb - 2 - 4 * i] = (uint8_t)(v[i] >> 8);
+    out[nb - 3 - 4 * i] = (uint8_t)(v[i] >> 16);
+    out[nb - 4 - 4 * i] = (uint8_t)(v[i] >> 24);
   }
 }
 static const uint32_t H_K256_N[8] = {0xD0364141u, 0xBFD25E8Cu, 0xAF48A03Bu, 0xBAAEDCE6u, 0xFFFFFFFEu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
@@ -439,20 +470,31 @@ static const uint8_t H_P256_G[64] = {
     0x33, 0xA0, 0xF4, 0xA1, 0x39, 0x45, 0xD8, 0x98, 0xC2, 0x96, 0x4F, 0xE3, 0x42, 0xE2, 0xFE, 0x1A, 0x7F, 0x9B, 0x8E, 0xE7, 0xEB, 0x4A,
     0x7C, 0x0F, 0x9E, 0x16, 0x2B, 0xCE, 0x33, 0x57, 0x6B, 0x31, 0x5E, 0xCE, 0xCB, 0xB6, 0x40, 0x68, 0x37, 0xBF, 0x51, 0xF5};
 
+static const uint32_t H_P384_N[12] = {0xCCC52973u, 0xECEC196Au, 0x48B0A77Au, 0x581A0DB2u, 0xF4372DDFu, 0xC7634D81u,
+                                      0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+static const uint8_t H_P384_G[96] = {
+    0xAA, 0x87, 0xCA, 0x22, 0xBE, 0x8B, 0x05, 0x37, 0x8E, 0xB1, 0xC7, 0x1E, 0xF3, 0x20, 0xAD, 0x74, 0x6E, 0x1D, 0x3B, 0x62, 0x8B, 0xA7, 0x9B, 0x98,
+    0x59, 0xF7, 0x41, 0xE0, 0x82, 0x54, 0x2A, 0x38, 0x55, 0x02, 0xF2, 0x5D, 0xBF, 0x55, 0x29, 0x6C, 0x3A, 0x54, 0x5E, 0x38, 0x72, 0x76, 0x0A, 0xB7,
+    0x36, 0x17, 0xDE, 0x4A, 0x96, 0x26, 0x2C, 0x6F, 0x5D, 0x9E, 0x98, 0xBF, 0x92, 0x92, 0xDC, 0x29, 0xF8, 0xF4, 0x1D, 0xBD, 0x28, 0x9A, 0x14, 0x7C,
+    0xE9, 0xDA, 0x31, 0x13, 0xB5, 0xF0, 0xB8, 0xC0, 0x0A, 0x60, 0xB1, 0xCE, 0x1D, 0x7E, 0x81, 0x9D, 0x7A, 0x43, 0x1D, 0x7C, 0x90, 0xEA, 0x0E, 0x5F};
+
 static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
   if (d.fb_table[curve]) return ECG_OK;
   Lane& L = d.lane[0];
-  const size_t np = FB_TABLE_POINTS;
+  const int nl = (int)flimbs(curve);
+  const size_t fb = fbytes(curve);
+  const int nwin = 2 * nl;  // FB_WINDOWS_NL
+  const size_t np = (size_t)nwin * FB_ENTRIES + 1;
   // built in pieces of FB_PIECE points so that the lane's window-table slots (512-768 B per element) and the
   // temporaries stay small: 2^16 points need 33-50 MB of slots instead of 268-402 MB for one launch over all of them
   const size_t FB_PIECE = (size_t)1 << 16;
-  std::vector<uint8_t> hk(np * 32), hp(FB_PIECE * 64);
-  const uint32_t* n_le = curve == ECG_SECP256K1 ? H_K256_N : H_P256_N;
-  const uint8_t* g = curve == ECG_SECP256K1 ? H_K256_G : H_P256_G;
-  for (int i = 0; i < FB_WINDOWS; i++)
-    for (uint32_t j = 0; j < FB_ENTRIES; j++) scalar_be_from_shifted(&hk[((size_t)i * FB_ENTRIES + j) * 32], 2ull * j + 1, FB_W * i, n_le);
-  scalar_be_from_shifted(&hk[(np - 1) * 32], 1, 256, n_le);  // 2^256 mod n
-  for (size_t i = 0; i < FB_PIECE; i++) memcpy(&hp[i * 64], g, 64);
+  std::vector<uint8_t> hk(np * fb), hp(FB_PIECE * 2 * fb);
+  const uint32_t* n_le = curve == ECG_SECP256K1 ? H_K256_N : curve == ECG_NISTP256 ? H_P256_N : H_P384_N;
+  const uint8_t* g = curve == ECG_SECP256K1 ? H_K256_G : curve == ECG_NISTP256 ? H_P256_G : H_P384_G;
+  for (int i = 0; i < nwin; i++)
+    for (uint32_t j = 0; j < FB_ENTRIES; j++) scalar_be_from_shifted(&hk[((size_t)i * FB_ENTRIES + j) * fb], 2ull * j + 1, FB_W * i, n_le, nl);
+  scalar_be_from_shifted(&hk[(np - 1) * fb], 1, 32 * nl, n_le, nl);  // 2^(32 nl) mod n
+  for (size_t i = 0; i < FB_PIECE; i++) memcpy(&hp[i * 2 * fb], g, 2 * fb);
   // temporaries are released on every exit path; `table` is released unless it is handed to the DevState
   struct Scratch {
     void* p[8] = {nullptr};
@@ -461,37 +503,32 @@ static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
         if (q) cudaFree(q);
     }
   } tmp;
-  CU_TRY(ctx, cudaMalloc(&tmp.p[0], np * 32));
-  CU_TRY(ctx, cudaMalloc(&tmp.p[1], FB_PIECE * 64));
-  CU_TRY(ctx, cudaMalloc(&tmp.p[2], FB_PIECE * 64));
+  CU_TRY(ctx, cudaMalloc(&tmp.p[0], np * fb));
+  CU_TRY(ctx, cudaMalloc(&tmp.p[1], FB_PIECE * 2 * fb));
+  CU_TRY(ctx, cudaMalloc(&tmp.p[2], FB_PIECE * 2 * fb));
   CU_TRY(ctx, cudaMalloc(&tmp.p[3], FB_PIECE));
-  CU_TRY(ctx, cudaMalloc(&tmp.p[4], FB_PIECE * 96));
-  CU_TRY(ctx, cudaMalloc(&tmp.p[5], FB_PIECE * 32));
-  CU_TRY(ctx, cudaMalloc(&tmp.p[6], np * 64));
+  CU_TRY(ctx, cudaMalloc(&tmp.p[4], FB_PIECE * 3 * fb));
+  CU_TRY(ctx, cudaMalloc(&tmp.p[5], FB_PIECE * fb));
+  CU_TRY(ctx, cudaMalloc(&tmp.p[6], np * 2 * fb));
   CU_TRY(ctx, cudaMalloc(&tmp.p[7], 8));  // private status: building the table must not disturb a caller's validation state
   uint8_t *dk = (uint8_t*)tmp.p[0], *dpnt = (uint8_t*)tmp.p[1], *dxy = (uint8_t*)tmp.p[2], *dinf = (uint8_t*)tmp.p[3];
   uint32_t *jac = (uint32_t*)tmp.p[4], *scr = (uint32_t*)tmp.p[5], *table = (uint32_t*)tmp.p[6], *st = (uint32_t*)tmp.p[7];
   CU_TRY(ctx, cudaMemsetAsync(st, 0, 8, L.s()));
-  CU_TRY(ctx, cudaMemcpyAsync(dk, hk.data(), np * 32, cudaMemcpyHostToDevice, L.s()));
-  CU_TRY(ctx, cudaMemcpyAsync(dpnt, hp.data(), FB_PIECE * 64, cudaMemcpyHostToDevice, L.s()));
+  CU_TRY(ctx, cudaMemcpyAsync(dk, hk.data(), np * fb, cudaMemcpyHostToDevice, L.s()));
+  CU_TRY(ctx, cudaMemcpyAsync(dpnt, hp.data(), FB_PIECE * 2 * fb, cudaMemcpyHostToDevice, L.s()));
   bool saved_timing = ctx->timing;
   ctx->timing = false;
   ecg_status rc = ECG_OK;
   for (size_t lo = 0; lo < np && rc == ECG_OK; lo += FB_PIECE) {
     size_t cnt = std::min(FB_PIECE, np - lo);
     DevPtrs dp;
-    dp.k = dk + 32 * lo;
+    dp.k = dk + fb * lo;
     dp.p = dpnt;
     rc = launch_varbase(ctx, d, L, curve, cnt, dp, jac, st, lo);
     if (rc != ECG_OK) break;
     size_t want_threads = std::max<size_t>((cnt + 31) / 32, std::min<size_t>(cnt, (size_t)d.sm_count * 256));
-    if (curve == ECG_SECP256K1) {
-      normalize_kernel<FpK256><<<grid_for(want_threads, 256), 256, 0, L.s()>>>(jac, cnt, scr, dxy, dinf);
-      affine_to_table_kernel<CurveK256><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dxy, cnt, table + lo * 16);
-    } else {
-      normalize_kernel<FpP256><<<grid_for(want_threads, 256), 256, 0, L.s()>>>(jac, cnt, scr, dxy, dinf);
-      affine_to_table_kernel<CurveP256><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dxy, cnt, table + lo * 16);
-    }
+    FOR_CURVE(curve, normalize_kernel<CV::F><<<grid_for(want_threads, 256), 256, 0, L.s()>>>(jac, cnt, scr, dxy, dinf);
+              affine_to_table_kernel<CV><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dxy, cnt, table + lo * 2 * nl));
     ctx->launches += 2;
     if (cudaGetLastError() != cudaSuccess) {
       ctx->err = "fixed-base table build: kernel launch failed";
@@ -519,6 +556,7 @@ struct BatchOp {
   bool x_only = false;  // MUL: write x coordinates only (ostride 32)
   const uint8_t *k = nullptr, *a = nullptr, *p = nullptr, *inf = nullptr;  // host or device, per ctx flags
   const uint8_t* x = nullptr;  // extra 64-byte-stride input (ECDSA public keys)
+  size_t kstride = 32;  // scalars / field elements / messages: fbytes(curve) for the hot-path entries
   size_t pstride = 64;
   uint8_t *out = nullptr, *oinf = nullptr;
   uint8_t* aux_out = nullptr;  // third output array (decompress: validity flags)
@@ -528,8 +566,8 @@ struct BatchOp {
 static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& op, size_t off, size_t cnt) {
   DevPtrs dp;
   ST_TRY(begin_lane(ctx, L));
-  ST_TRY(stage_in(ctx, L, B_K, op.k, off, cnt, 32, &dp.k));
-  ST_TRY(stage_in(ctx, L, B_A, op.a, off, cnt, 32, &dp.a));
+  ST_TRY(stage_in(ctx, L, B_K, op.k, off, cnt, op.kstride, &dp.k));
+  ST_TRY(stage_in(ctx, L, B_A, op.a, off, cnt, op.kstride, &dp.a));
   ST_TRY(stage_in(ctx, L, B_P, op.p, off, cnt, op.pstride, &dp.p));
   ST_TRY(stage_in(ctx, L, B_INF, op.inf, off, cnt, 1, &dp.inf));
   const uint8_t* dx = nullptr;
@@ -601,7 +639,7 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
   }
   uint32_t* jac = nullptr;
   if (op.kind != BatchOp::FIELD) {
-    ST_TRY(ensure(ctx, L, B_JAC, cnt * 96));
+    ST_TRY(ensure(ctx, L, B_JAC, cnt * 3 * fbytes(op.curve)));
     jac = (uint32_t*)L.buf[B_JAC];
   }
   const bool k1 = op.curve == ECG_SECP256K1;
@@ -611,10 +649,7 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
       break;
     case BatchOp::MULGEN:
       DOM_BEGIN(ctx, L);
-      if (k1)
-        fixedbase_kernel<CurveK256><<<grid_for(cnt, 128), 128, 0, L.s()>>>(dp.k, cnt, d.fb_table[op.curve], jac, L.status, off);
-      else
-        fixedbase_kernel<CurveP256><<<grid_for(cnt, 128), 128, 0, L.s()>>>(dp.k, cnt, d.fb_table[op.curve], jac, L.status, off);
+      FOR_CURVE(op.curve, fixedbase_kernel<CV><<<grid_for(cnt, 128), 128, 0, L.s()>>>(dp.k, cnt, d.fb_table[op.curve], jac, L.status, off));
       LAUNCHED(ctx);
       DOM_END(ctx, L);
       break;
@@ -631,14 +666,10 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
       DOM_END(ctx, L);
       break;
     case BatchOp::NORMALIZE:
-      if (k1 && op.fop)
-        import_jac_kernel<CurveK256, true><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, cnt, jac, L.status, off);
-      else if (k1)
-        import_jac_kernel<CurveK256, false><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, cnt, jac, L.status, off);
-      else if (op.fop)
-        import_jac_kernel<CurveP256, true><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, cnt, jac, L.status, off);
+      if (op.fop)
+        FOR_CURVE(op.curve, import_jac_kernel<CV, true><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, cnt, jac, L.status, off));
       else
-        import_jac_kernel<CurveP256, false><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, cnt, jac, L.status, off);
+        FOR_CURVE(op.curve, import_jac_kernel<CV, false><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, cnt, jac, L.status, off));
       LAUNCHED(ctx);
       break;
     case BatchOp::SCHNORR:
@@ -647,10 +678,7 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
     case BatchOp::FSQRT:
       break;  // handled above
     case BatchOp::FIELD:
-      if (k1)
-        field_op_kernel<CurveK256><<<grid_for(cnt, 256), 256, 0, L.s()>>>(op.fop, cnt, dp.k, dp.a, dp.out, L.status, off);
-      else
-        field_op_kernel<CurveP256><<<grid_for(cnt, 256), 256, 0, L.s()>>>(op.fop, cnt, dp.k, dp.a, dp.out, L.status, off);
+      FOR_CURVE(op.curve, field_op_kernel<CV><<<grid_for(cnt, 256), 256, 0, L.s()>>>(op.fop, cnt, dp.k, dp.a, dp.out, L.status, off));
       LAUNCHED(ctx);
       break;
   }
@@ -706,7 +734,7 @@ static ecg_status run_batch_inner(ecg_ctx* ctx, const BatchOp& op, size_t n) {
   std::vector<std::vector<Shard>> sched(shards.size());
   size_t maxchunks = 0;
   for (size_t i = 0; i < shards.size(); i++) {
-    sched[i] = chunk_schedule(shards[i].cnt, (size_t)ctx->devs[i].sm_count * (op.curve == ECG_SECP256K1 ? K_MINBLK * K_BLOCK : P_MINBLK * P_BLOCK));
+    sched[i] = chunk_schedule(shards[i].cnt, wave_elems(ctx->devs[i], op.curve));
     maxchunks = std::max(maxchunks, sched[i].size());
   }
   for (size_t c = 0; c < maxchunks; c++) {
@@ -738,6 +766,8 @@ extern "C" ecg_status ecg_mul_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, con
   BatchOp op;
   op.kind = BatchOp::MUL;
   op.curve = curve;
+  op.kstride = fbytes(curve);
+  op.pstride = op.ostride = 2 * fbytes(curve);
   op.k = k;
   op.p = P_xy;
   op.inf = P_inf;
@@ -757,6 +787,8 @@ extern "C" ecg_status ecg_mul_gen_batch(ecg_ctx* ctx, ecg_curve curve, size_t n,
   BatchOp op;
   op.kind = BatchOp::MULGEN;
   op.curve = curve;
+  op.kstride = fbytes(curve);
+  op.ostride = 2 * fbytes(curve);
   op.k = k;
   op.out = out_xy;
   op.oinf = out_inf;
@@ -767,7 +799,7 @@ extern "C" ecg_status ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve curve, size_
                                             const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf) {
   if (!ctx) return ECG_EINVAL;
   if (n == 0) return ECG_OK;
-  if (!a || !b || !P_xy || !out_xy || !curve_ok(curve)) {
+  if (!a || !b || !P_xy || !out_xy || !curve_256(curve)) {
     ctx->err = "ecg_mul_gen_add_batch: null pointer or unknown curve";
     return ECG_EINVAL;
   }
@@ -787,7 +819,7 @@ extern "C" ecg_status ecg_decompress_batch(ecg_ctx* ctx, ecg_curve curve, size_t
                                             uint8_t* out_inf, uint8_t* valid) {
   if (!ctx) return ECG_EINVAL;
   if (n == 0) return ECG_OK;
-  if (!sec1_33 || !out_xy || !out_inf || !valid || !curve_ok(curve)) {
+  if (!sec1_33 || !out_xy || !out_inf || !valid || !curve_256(curve)) {
     ctx->err = "ecg_decompress_batch: null pointer or unknown curve";
     return ECG_EINVAL;
   }
@@ -825,7 +857,7 @@ extern "C" ecg_status ecg_ecdsa_verify_batch(ecg_ctx* ctx, ecg_curve curve, size
                                               const uint8_t* Q_xy, int low_s_only, uint8_t* valid) {
   if (!ctx) return ECG_EINVAL;
   if (n == 0) return ECG_OK;
-  if (!z32 || !sig64 || !Q_xy || !valid || !curve_ok(curve)) {
+  if (!z32 || !sig64 || !Q_xy || !valid || !curve_256(curve)) {
     ctx->err = "ecg_ecdsa_verify_batch: null pointer or unknown curve";
     return ECG_EINVAL;
   }
@@ -849,8 +881,9 @@ extern "C" ecg_status ecg_batch_normalize(ecg_ctx* ctx, ecg_curve curve, size_t 
   BatchOp op;
   op.kind = BatchOp::NORMALIZE;
   op.curve = curve;
+  op.ostride = 2 * fbytes(curve);
   op.p = xyz;
-  op.pstride = 96;
+  op.pstride = 3 * fbytes(curve);
   op.out = out_xy;
   op.oinf = out_inf;
   return run_batch(ctx, op, n);
@@ -864,9 +897,10 @@ extern "C" ecg_status ecg_batch_normalize_hom(ecg_ctx* ctx, ecg_curve curve, siz
   BatchOp op;
   op.kind = BatchOp::NORMALIZE;
   op.curve = curve;
+  op.ostride = 2 * fbytes(curve);
   op.fop = 1;  // homogeneous (X:Y:Z), x = X/Z
   op.p = xyz;
-  op.pstride = 96;
+  op.pstride = 3 * fbytes(curve);
   op.out = out_xy;
   op.oinf = out_inf;
   return run_batch(ctx, op, n);
@@ -883,12 +917,14 @@ extern "C" ecg_status ecg_mul_batch_x(ecg_ctx* ctx, ecg_curve curve, size_t n, c
   BatchOp op;
   op.kind = BatchOp::MUL;
   op.curve = curve;
+  op.kstride = fbytes(curve);
+  op.pstride = 2 * fbytes(curve);
   op.k = k;
   op.p = P_xy;
   op.inf = P_inf;
   op.out = out_x;
   op.oinf = out_inf;
-  op.ostride = 32;
+  op.ostride = fbytes(curve);
   op.x_only = true;
   return run_batch(ctx, op, n);
 }
@@ -897,7 +933,7 @@ extern "C" ecg_status ecg_field_sqrt_batch(ecg_ctx* ctx, ecg_curve curve, size_t
                                            uint8_t* is_square) {
   if (!ctx) return ECG_EINVAL;
   if (n == 0) return ECG_OK;
-  if (!a || !out || !is_square || !curve_ok(curve)) return ECG_EINVAL;
+  if (!a || !out || !is_square || !curve_256(curve)) return ECG_EINVAL;
   BatchOp op;
   op.kind = BatchOp::FSQRT;
   op.curve = curve;
@@ -917,11 +953,12 @@ extern "C" ecg_status ecg_field_op_batch(ecg_ctx* ctx, ecg_curve curve, int fop,
   BatchOp op;
   op.kind = BatchOp::FIELD;
   op.curve = curve;
+  op.kstride = fbytes(curve);
   op.fop = fop;
   op.k = a;
   op.a = binary ? b : nullptr;
   op.out = out;
-  op.ostride = 32;
+  op.ostride = fbytes(curve);
   return run_batch(ctx, op, n);
 }
 
@@ -940,7 +977,8 @@ static ecg_status reduce_points(ecg_ctx* ctx, Lane& L, uint32_t* a, uint32_t* b,
   return ECG_OK;
 }
 static ecg_status reduce_points_c(ecg_ctx* ctx, Lane& L, ecg_curve curve, uint32_t* a, uint32_t* b, size_t n, uint32_t** result) {
-  return curve == ECG_SECP256K1 ? reduce_points<CurveK256>(ctx, L, a, b, n, result) : reduce_points<CurveP256>(ctx, L, a, b, n, result);
+  FOR_CURVE(curve, return reduce_points<CV>(ctx, L, a, b, n, result));
+  return ECG_EINVAL;
 }
 
 // ---- bucket-method lincomb (ecg_msm.cuh) ------------------------------------------------------------
@@ -1103,11 +1141,13 @@ static ecg_status lincomb_shard(ecg_ctx* ctx, DevState& d, ecg_curve curve, cons
                                 const uint8_t* P_xy, const uint8_t* P_inf, bool per_term, uint32_t** result) {
   Lane& L = d.lane[0];
   DevPtrs dp;
+  const size_t fb = fbytes(curve), pt = 3 * fb;  // bytes per scalar / per Jacobian point
   ST_TRY(begin_lane(ctx, L));
-  ST_TRY(stage_in(ctx, L, B_K, k, sh.off, sh.cnt, 32, &dp.k));
-  ST_TRY(stage_in(ctx, L, B_P, P_xy, sh.off, sh.cnt, 64, &dp.p));
+  ST_TRY(stage_in(ctx, L, B_K, k, sh.off, sh.cnt, fb, &dp.k));
+  ST_TRY(stage_in(ctx, L, B_P, P_xy, sh.off, sh.cnt, 2 * fb, &dp.p));
   ST_TRY(stage_in(ctx, L, B_INF, P_inf, sh.off, sh.cnt, 1, &dp.inf));
-  if (sh.cnt >= MSM_MIN_TERMS && !per_term) {
+  // the bucket method is written for the 256-bit curves (digits of 8-limb scalars); P-384 sums per term
+  if (sh.cnt >= MSM_MIN_TERMS && !per_term && curve_256(curve)) {
     // bucket method, in pieces of at most MSM_MAX_TERMS terms whose partial sums are added at the end
     const size_t MSM_MAX_TERMS = msm_max_terms();
     size_t pieces = (sh.cnt + MSM_MAX_TERMS - 1) / MSM_MAX_TERMS;
@@ -1141,16 +1181,16 @@ static ecg_status lincomb_shard(ecg_ctx* ctx, DevState& d, ecg_curve curve, cons
   const size_t PT_CHUNK = (size_t)1 << 20;
   const size_t pieces = (sh.cnt + PT_CHUNK - 1) / PT_CHUNK;
   const size_t c0 = std::min(sh.cnt, PT_CHUNK);
-  ST_TRY(ensure(ctx, L, B_FB1, c0 * 96));
-  ST_TRY(ensure(ctx, L, B_FB2, ((c0 + 31) / 32) * 96 + 256));
-  ST_TRY(ensure(ctx, L, B_JAC, pieces * 96 + 96));
-  ST_TRY(ensure(ctx, L, B_JAC2, ((pieces + 31) / 32) * 96 + 96));
+  ST_TRY(ensure(ctx, L, B_FB1, c0 * pt));
+  ST_TRY(ensure(ctx, L, B_FB2, ((c0 + 31) / 32) * pt + 256));
+  ST_TRY(ensure(ctx, L, B_JAC, pieces * pt + pt));
+  ST_TRY(ensure(ctx, L, B_JAC2, ((pieces + 31) / 32) * pt + pt));
   uint32_t* parts = (uint32_t*)L.buf[B_JAC];
   for (size_t pc = 0; pc < pieces; pc++) {
     size_t lo = pc * PT_CHUNK, cnt = std::min(PT_CHUNK, sh.cnt - lo);
     DevPtrs q;
-    q.k = dp.k + 32 * lo;
-    q.p = dp.p + 64 * lo;
+    q.k = dp.k + fb * lo;
+    q.p = dp.p + 2 * fb * lo;
     q.inf = dp.inf ? dp.inf + lo : nullptr;
     uint32_t* r1 = nullptr;
     ST_TRY(launch_varbase(ctx, d, L, curve, cnt, q, (uint32_t*)L.buf[B_FB1], L.status, sh.off + lo));
@@ -1159,17 +1199,14 @@ static ecg_status lincomb_shard(ecg_ctx* ctx, DevState& d, ecg_curve curve, cons
       *result = r1;
       return ECG_OK;
     }
-    for (int w = 0; w < 24; w++)
+    for (int w = 0; w < (int)(3 * flimbs(curve)); w++)
       CU_TRY(ctx, cudaMemcpyAsync(parts + (size_t)w * pieces + pc, r1 + w, 4, cudaMemcpyDeviceToDevice, L.s()));
   }
   return reduce_points_c(ctx, L, curve, parts, (uint32_t*)L.buf[B_JAC2], pieces, result);
 }
 
 static ecg_status export_point(ecg_ctx* ctx, Lane& L, ecg_curve curve, const uint32_t* jac1, uint8_t* dev_xyz) {
-  if (curve == ECG_SECP256K1)
-    export_jac_kernel<CurveK256><<<1, 128, 0, L.s()>>>(jac1, 1, dev_xyz);
-  else
-    export_jac_kernel<CurveP256><<<1, 128, 0, L.s()>>>(jac1, 1, dev_xyz);
+  FOR_CURVE(curve, export_jac_kernel<CV><<<1, 128, 0, L.s()>>>(jac1, 1, dev_xyz));
   LAUNCHED(ctx);
   return ECG_OK;
 }
@@ -1188,7 +1225,7 @@ static ecg_status lincomb_partial_attempt(ecg_ctx* ctx, ecg_curve curve, size_t 
     dst = (uint8_t*)L.buf[B_AUX];
   }
   ST_TRY(export_point(ctx, L, curve, res, dst));
-  if (!ctx->devptr()) CU_TRY(ctx, cudaMemcpyAsync(out_xyz, dst, 96, cudaMemcpyDeviceToHost, L.s()));
+  if (!ctx->devptr()) CU_TRY(ctx, cudaMemcpyAsync(out_xyz, dst, 3 * fbytes(curve), cudaMemcpyDeviceToHost, L.s()));
   return ECG_OK;
 }
 
@@ -1206,13 +1243,14 @@ extern "C" ecg_status ecg_lincomb_partial(ecg_ctx* ctx, ecg_curve curve, size_t 
   DevState& d = ctx->devs[0];
   CU_TRY(ctx, cudaSetDevice(d.dev));
   if (n == 0) {  // empty sum = identity (0 : 1 : 0)
-    uint8_t z[96];
+    const size_t fb = fbytes(curve);
+    uint8_t z[144];
     memset(z, 0, sizeof z);
-    z[63] = 1;
+    z[2 * fb - 1] = 1;
     if (ctx->devptr())
-      CU_TRY(ctx, cudaMemcpy(out_xyz, z, 96, cudaMemcpyHostToDevice));
+      CU_TRY(ctx, cudaMemcpy(out_xyz, z, 3 * fb, cudaMemcpyHostToDevice));
     else
-      memcpy(out_xyz, z, 96);
+      memcpy(out_xyz, z, 3 * fb);
     return ECG_OK;
   }
   ctx->skew = false;
@@ -1233,27 +1271,25 @@ static ecg_status point_sum_enqueue(ecg_ctx* ctx, ecg_curve curve, size_t m, con
   DevState& d = ctx->devs[0];
   Lane& L = d.lane[0];
   CU_TRY(ctx, cudaSetDevice(d.dev));
+  const size_t fb = fbytes(curve), pt = 3 * fb;
   ST_TRY(begin_lane(ctx, L));
-  ST_TRY(ensure(ctx, L, B_JAC, m * 96 + 96));
-  ST_TRY(ensure(ctx, L, B_JAC2, ((m + 31) / 32) * 96 + 96));
+  ST_TRY(ensure(ctx, L, B_JAC, m * pt + pt));
+  ST_TRY(ensure(ctx, L, B_JAC2, ((m + 31) / 32) * pt + pt));
   const uint8_t* dxyz = xyz;
   if (xyz_on_host) {
-    ST_TRY(ensure(ctx, L, B_AUX, m * 96 + 256));
-    CU_TRY(ctx, cudaMemcpyAsync(L.buf[B_AUX], xyz, m * 96, cudaMemcpyHostToDevice, L.s()));
+    ST_TRY(ensure(ctx, L, B_AUX, m * pt + 256));
+    CU_TRY(ctx, cudaMemcpyAsync(L.buf[B_AUX], xyz, m * pt, cudaMemcpyHostToDevice, L.s()));
     dxyz = (const uint8_t*)L.buf[B_AUX];
   }
   uint32_t* jac = (uint32_t*)L.buf[B_JAC];
-  if (curve == ECG_SECP256K1)
-    import_jac_kernel<CurveK256><<<grid_for(m, 256), 256, 0, L.s()>>>(dxyz, m, jac, L.status, 0);
-  else
-    import_jac_kernel<CurveP256><<<grid_for(m, 256), 256, 0, L.s()>>>(dxyz, m, jac, L.status, 0);
+  FOR_CURVE(curve, import_jac_kernel<CV><<<grid_for(m, 256), 256, 0, L.s()>>>(dxyz, m, jac, L.status, 0));
   LAUNCHED(ctx);
   uint32_t* res = nullptr;
   ST_TRY(reduce_points_c(ctx, L, curve, jac, (uint32_t*)L.buf[B_JAC2], m, &res));
   DevPtrs dp;
-  ST_TRY(stage_out(ctx, L, 0, 1, out_xy, 64, out_inf, dp));
+  ST_TRY(stage_out(ctx, L, 0, 1, out_xy, 2 * fb, out_inf, dp));
   ST_TRY(launch_norm(ctx, d, L, curve, 1, res, dp.out, dp.oinf));
-  return copy_back(ctx, L, 0, 1, out_xy, 64, out_inf, dp);
+  return copy_back(ctx, L, 0, 1, out_xy, 2 * fb, out_inf, dp);
 }
 
 extern "C" ecg_status ecg_point_sum(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* xyz, uint8_t* out_xy,
@@ -1265,15 +1301,15 @@ extern "C" ecg_status ecg_point_sum(ecg_ctx* ctx, ecg_curve curve, size_t m, con
     return ECG_EINVAL;
   }
   if (m == 0) {
-    uint8_t z[65];
+    uint8_t z[97];
     memset(z, 0, sizeof z);
     if (ctx->devptr()) {
       CU_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
-      CU_TRY(ctx, cudaMemcpy(out_xy, z, 64, cudaMemcpyHostToDevice));
+      CU_TRY(ctx, cudaMemcpy(out_xy, z, 2 * fbytes(curve), cudaMemcpyHostToDevice));
       z[0] = 1;
       CU_TRY(ctx, cudaMemcpy(out_inf, z, 1, cudaMemcpyHostToDevice));
     } else {
-      memcpy(out_xy, z, 64);
+      memcpy(out_xy, z, 2 * fbytes(curve));
       *out_inf = 1;
     }
     return ECG_OK;
@@ -1296,9 +1332,9 @@ static ecg_status lincomb_attempt(ecg_ctx* ctx, ecg_curve curve, size_t n, const
     uint32_t* res = nullptr;
     ST_TRY(lincomb_shard(ctx, d, curve, shards[0], k, P_xy, P_inf, per_term, &res));
     DevPtrs dp;
-    ST_TRY(stage_out(ctx, L, 0, 1, out_xy, 64, out_inf, dp));
+    ST_TRY(stage_out(ctx, L, 0, 1, out_xy, 2 * fbytes(curve), out_inf, dp));
     ST_TRY(launch_norm(ctx, d, L, curve, 1, res, dp.out, dp.oinf));
-    return copy_back(ctx, L, 0, 1, out_xy, 64, out_inf, dp);
+    return copy_back(ctx, L, 0, 1, out_xy, 2 * fbytes(curve), out_inf, dp);
   }
   for (size_t i = 0; i < nd; i++) {
     DevState& d = ctx->devs[i];
@@ -1309,14 +1345,15 @@ static ecg_status lincomb_attempt(ecg_ctx* ctx, ecg_curve curve, size_t n, const
     ST_TRY(lincomb_shard(ctx, d, curve, shards[i], k, P_xy, P_inf, per_term, &res));
     ST_TRY(ensure(ctx, L, B_AUX, 256));
     ST_TRY(export_point(ctx, L, curve, res, (uint8_t*)L.buf[B_AUX]));
-    CU_TRY(ctx, cudaMemcpyAsync(L.h_point(), L.buf[B_AUX], 96, cudaMemcpyDeviceToHost, L.s()));
+    CU_TRY(ctx, cudaMemcpyAsync(L.h_point(), L.buf[B_AUX], 3 * fbytes(curve), cudaMemcpyDeviceToHost, L.s()));
   }
   ST_TRY(finish(ctx));
   if (ctx->skew) return ECG_OK;  // the caller repeats per term
   for (size_t i = 0; i < nd; i++) {
-    memset(&partial[i * 96], 0, 96);
-    partial[i * 96 + 63] = 1;  // identity (0:1:0) for empty shards
-    if (shards[i].cnt) memcpy(&partial[i * 96], ctx->devs[i].lane[0].h_point(), 96);
+    const size_t pt = 3 * fbytes(curve);
+    memset(&partial[i * pt], 0, pt);
+    partial[i * pt + 2 * fbytes(curve) - 1] = 1;  // identity (0:1:0) for empty shards
+    if (shards[i].cnt) memcpy(&partial[i * pt], ctx->devs[i].lane[0].h_point(), pt);
   }
   return point_sum_enqueue(ctx, curve, nd, partial.data(), out_xy, out_inf, true);
 }
@@ -1329,19 +1366,19 @@ extern "C" ecg_status ecg_lincomb(ecg_ctx* ctx, ecg_curve curve, size_t n, const
     return ECG_EINVAL;
   }
   if (n == 0) {
-    uint8_t z[65];
+    uint8_t z[97];
     memset(z, 0, sizeof z);
     if (ctx->devptr()) {
-      CU_TRY(ctx, cudaMemcpy(out_xy, z, 64, cudaMemcpyHostToDevice));
+      CU_TRY(ctx, cudaMemcpy(out_xy, z, 2 * fbytes(curve), cudaMemcpyHostToDevice));
       z[0] = 1;
       CU_TRY(ctx, cudaMemcpy(out_inf, z, 1, cudaMemcpyHostToDevice));
     } else {
-      memcpy(out_xy, z, 64);
+      memcpy(out_xy, z, 2 * fbytes(curve));
       *out_inf = 1;
     }
     return ECG_OK;
   }
-  std::vector<uint8_t> partial(ctx->devs.size() * 96, 0);
+  std::vector<uint8_t> partial(ctx->devs.size() * 144, 0);
   ctx->skew = false;
   for (int attempt = 0; attempt < 2; attempt++) {
     ecg_status st = lincomb_attempt(ctx, curve, n, k, P_xy, P_inf, out_xy, out_inf, attempt == 1, partial);

@@ -26,7 +26,10 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libecgpu.so")
 
 SECP256K1 = 0
 NISTP256 = 1
-CURVE_IDS = {"k256": SECP256K1, "secp256k1": SECP256K1, "p256": NISTP256, "nistp256": NISTP256, 0: 0, 1: 1}
+NISTP384 = 2
+CURVE_IDS = {"k256": SECP256K1, "secp256k1": SECP256K1, "p256": NISTP256, "nistp256": NISTP256, "p384": NISTP384, "nistp384": NISTP384,
+             0: 0, 1: 1, 2: 2}
+FBYTES = {SECP256K1: 32, NISTP256: 32, NISTP384: 48}  # bytes per scalar / coordinate at the ABI
 
 ECG_OK, ECG_EINVAL, ECG_ESCALAR_RANGE, ECG_ENOT_ON_CURVE, ECG_ECUDA, ECG_ENCCL, ECG_ENOMEM = range(7)
 FLAG_DEVICE_PTRS = 1
@@ -205,37 +208,40 @@ class Engine:
     # ---- host-pointer API (numpy) ----
     def mul_batch(self, curve, k, P_xy, P_inf=None, out_xy=None, out_inf=None):
         c = CURVE_IDS[curve]
-        n = np.asarray(k).size // 32
-        k = _u8(k, 32 * n, "k")
-        P_xy = _u8(P_xy, 64 * n, "P_xy")
+        fb = FBYTES[c]
+        n = np.asarray(k).size // fb
+        k = _u8(k, fb * n, "k")
+        P_xy = _u8(P_xy, 2 * fb * n, "P_xy")
         if P_inf is not None:
             P_inf = _u8(P_inf, n, "P_inf")
-        out_xy = _out(out_xy, 64 * n, "out_xy")
+        out_xy = _out(out_xy, 2 * fb * n, "out_xy")
         out_inf = _out(out_inf, n, "out_inf")
         self._check(self.lib.ecg_mul_batch(self._ctx, c, n, _ptr(k), _ptr(P_xy), _ptr(P_inf), _ptr(out_xy), _ptr(out_inf)))
-        return out_xy.reshape(n, 64), out_inf
+        return out_xy.reshape(n, 2 * fb), out_inf
 
     def mul_by_generator(self, curve, k, out_xy=None, out_inf=None):
         c = CURVE_IDS[curve]
-        n = np.asarray(k).size // 32
-        k = _u8(k, 32 * n, "k")
-        out_xy = _out(out_xy, 64 * n, "out_xy")
+        fb = FBYTES[c]
+        n = np.asarray(k).size // fb
+        k = _u8(k, fb * n, "k")
+        out_xy = _out(out_xy, 2 * fb * n, "out_xy")
         out_inf = _out(out_inf, n, "out_inf")
         self._check(self.lib.ecg_mul_gen_batch(self._ctx, c, n, _ptr(k), _ptr(out_xy), _ptr(out_inf)))
-        return out_xy.reshape(n, 64), out_inf
+        return out_xy.reshape(n, 2 * fb), out_inf
 
     def mul_batch_x(self, curve, k, P_xy, P_inf=None):
         """x coordinate of k[i] * P[i] only (ecg_mul_batch_x) -> (x n x 32, inf)"""
         c = CURVE_IDS[curve]
-        n = np.asarray(k).size // 32
-        k = _u8(k, 32 * n, "k")
-        P_xy = _u8(P_xy, 64 * n, "P_xy")
+        fb = FBYTES[c]
+        n = np.asarray(k).size // fb
+        k = _u8(k, fb * n, "k")
+        P_xy = _u8(P_xy, 2 * fb * n, "P_xy")
         if P_inf is not None:
             P_inf = _u8(P_inf, n, "P_inf")
-        out_x = np.empty(32 * n, np.uint8)
+        out_x = np.empty(fb * n, np.uint8)
         out_inf = np.empty(n, np.uint8)
         self._check(self.lib.ecg_mul_batch_x(self._ctx, c, n, _ptr(k), _ptr(P_xy), _ptr(P_inf), _ptr(out_x), _ptr(out_inf)))
-        return out_x.reshape(n, 32), out_inf
+        return out_x.reshape(n, fb), out_inf
 
     def diffie_hellman_vartime(self, curve, secret_k, public_xy):
         """ECDH batch: x-coordinate of k[i] * P[i] (k256/src/ecdh.rs:46-60 `diffie_hellman`: `(public * secret).to_affine().x`).
@@ -245,8 +251,9 @@ class Engine:
         only where timing of the device is not observable by an adversary, with an Engine(zeroize=True) so the staged
         scalars and tables are cleared after the call.  As in the reference, the inputs are a NonZeroScalar and a
         PublicKey: a zero scalar or an identity result is refused (ValueError) instead of yielding an all-zero secret."""
-        n = np.asarray(secret_k).size // 32
-        kk = _u8(secret_k, 32 * n, "secret_k").reshape(n, 32)
+        fb = FBYTES[CURVE_IDS[curve]]
+        n = np.asarray(secret_k).size // fb
+        kk = _u8(secret_k, fb * n, "secret_k").reshape(n, fb)
         if n and not kk.any(axis=1).all():
             raise ValueError("diffie_hellman_vartime: zero secret scalar (the reference takes a NonZeroScalar)")
         out_x, out_inf = self.mul_batch_x(curve, kk, public_xy, None)
@@ -256,32 +263,34 @@ class Engine:
 
     def lincomb(self, curve, k, P_xy, P_inf=None):
         c = CURVE_IDS[curve]
-        n = np.asarray(k).size // 32
-        k = _u8(k, 32 * n, "k")
-        P_xy = _u8(P_xy, 64 * n, "P_xy")
+        fb = FBYTES[c]
+        n = np.asarray(k).size // fb
+        k = _u8(k, fb * n, "k")
+        P_xy = _u8(P_xy, 2 * fb * n, "P_xy")
         if P_inf is not None:
             P_inf = _u8(P_inf, n, "P_inf")
-        out_xy = np.zeros(64, np.uint8)
+        out_xy = np.zeros(2 * fb, np.uint8)
         out_inf = np.zeros(1, np.uint8)
         self._check(self.lib.ecg_lincomb(self._ctx, c, n, _ptr(k), _ptr(P_xy), _ptr(P_inf), _ptr(out_xy), _ptr(out_inf)))
         return out_xy, int(out_inf[0])
 
     def lincomb_partial(self, curve, k, P_xy, P_inf=None):
         c = CURVE_IDS[curve]
-        n = np.asarray(k).size // 32
-        k = _u8(k, 32 * n, "k")
-        P_xy = _u8(P_xy, 64 * n, "P_xy")
+        fb = FBYTES[c]
+        n = np.asarray(k).size // fb
+        k = _u8(k, fb * n, "k")
+        P_xy = _u8(P_xy, 2 * fb * n, "P_xy")
         if P_inf is not None:
             P_inf = _u8(P_inf, n, "P_inf")
-        out = np.zeros(96, np.uint8)
+        out = np.zeros(3 * fb, np.uint8)
         self._check(self.lib.ecg_lincomb_partial(self._ctx, c, n, _ptr(k), _ptr(P_xy), _ptr(P_inf), _ptr(out)))
         return out
 
     def point_sum(self, curve, xyz):
         c = CURVE_IDS[curve]
         xyz = np.ascontiguousarray(xyz, dtype=np.uint8).reshape(-1)
-        m = xyz.size // 96
-        out_xy = np.zeros(64, np.uint8)
+        m = xyz.size // (3 * FBYTES[c])
+        out_xy = np.zeros(2 * FBYTES[c], np.uint8)
         out_inf = np.zeros(1, np.uint8)
         self._check(self.lib.ecg_point_sum(self._ctx, c, m, _ptr(xyz), _ptr(out_xy), _ptr(out_inf)))
         return out_xy, int(out_inf[0])
@@ -364,21 +373,23 @@ class Engine:
     def batch_normalize(self, curve, xyz):
         c = CURVE_IDS[curve]
         xyz = np.ascontiguousarray(xyz, dtype=np.uint8).reshape(-1)
-        n = xyz.size // 96
-        out_xy = np.empty(64 * n, np.uint8)
+        fb = FBYTES[c]
+        n = xyz.size // (3 * fb)
+        out_xy = np.empty(2 * fb * n, np.uint8)
         out_inf = np.empty(n, np.uint8)
         self._check(self.lib.ecg_batch_normalize(self._ctx, c, n, _ptr(xyz), _ptr(out_xy), _ptr(out_inf)))
-        return out_xy.reshape(n, 64), out_inf
+        return out_xy.reshape(n, 2 * fb), out_inf
 
     def batch_normalize_hom(self, curve, xyz):
         """BatchNormalize for the reference's own homogeneous (X:Y:Z), x = X/Z (ecg_batch_normalize_hom)"""
         c = CURVE_IDS[curve]
         xyz = np.ascontiguousarray(xyz, dtype=np.uint8).reshape(-1)
-        n = xyz.size // 96
-        out_xy = np.empty(64 * n, np.uint8)
+        fb = FBYTES[c]
+        n = xyz.size // (3 * fb)
+        out_xy = np.empty(2 * fb * n, np.uint8)
         out_inf = np.empty(n, np.uint8)
         self._check(self.lib.ecg_batch_normalize_hom(self._ctx, c, n, _ptr(xyz), _ptr(out_xy), _ptr(out_inf)))
-        return out_xy.reshape(n, 64), out_inf
+        return out_xy.reshape(n, 2 * fb), out_inf
 
     def field_sqrt(self, curve, a):
         """FieldElement::sqrt over a batch -> (roots n x 32, is_square)"""
@@ -392,13 +403,14 @@ class Engine:
 
     def field_op(self, curve, op, a, b=None):
         c = CURVE_IDS[curve]
-        n = np.asarray(a).size // 32
-        a = _u8(a, 32 * n, "a")
+        fb = FBYTES[c]
+        n = np.asarray(a).size // fb
+        a = _u8(a, fb * n, "a")
         if b is not None:
-            b = _u8(b, 32 * n, "b")
-        out = np.empty(32 * n, np.uint8)
+            b = _u8(b, fb * n, "b")
+        out = np.empty(fb * n, np.uint8)
         self._check(self.lib.ecg_field_op_batch(self._ctx, c, FOP[op] if isinstance(op, str) else op, n, _ptr(a), _ptr(b), _ptr(out)))
-        return out.reshape(n, 32)
+        return out.reshape(n, fb)
 
     # ---- raw-pointer API (device_ptrs=True): all arguments are integer CUDA device addresses ----
     def mul_batch_ptr(self, curve, n, k, P_xy, P_inf, out_xy, out_inf):

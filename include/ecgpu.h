@@ -40,7 +40,11 @@ typedef enum {
   ECG_ENOMEM = 6
 } ecg_status;
 
-typedef enum { ECG_SECP256K1 = 0, ECG_NISTP256 = 1 } ecg_curve;
+/* ECG_NISTP384: the next curve through the same kernels templates (p384/src/arithmetic.rs:43-75).
+ * Its scalars and coordinates are 48 bytes: read "32 / 64 / 96" as "48 / 96 / 144" in every size below.  Served by the
+ * hot-path entries (mul_batch[_x], mul_gen_batch, lincomb[_partial], point_sum, batch_normalize[_hom], field_op_batch);
+ * the widening entries (verification, SEC1 decompression, a*G + b*P, field sqrt) are 256-bit only: ECG_EINVAL. */
+typedef enum { ECG_SECP256K1 = 0, ECG_NISTP256 = 1, ECG_NISTP384 = 2 } ecg_curve;
 
 typedef enum {
   ECG_FOP_ADD = 0,

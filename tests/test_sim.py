@@ -241,3 +241,65 @@ def test_on_curve_check(sim):
         bad = bytearray(xy)
         bad[40] ^= 4
         assert f(bytes(bad)) == 0
+
+
+# ---- P-384: the same templates with a 12-limb field policy ----
+def _feop384(sim, op, a, b=0):
+    out = ctypes.create_string_buffer(48)
+    sim.sim_p384_fe_op(op, a.to_bytes(48, "big"), b.to_bytes(48, "big"), out)
+    return int.from_bytes(out.raw, "big")
+
+
+def test_p384_field_ops_full_384bit_range(sim):
+    p = pyref.P384.p
+    rng = random.Random(384)
+    edge = [0, 1, 2, p - 1, p, p + 1, 2**384 - 1, 2**384 - 2, 2**384 - p, 2**384 - p - 1, p - 2, (p + 1) // 2, 2**383, 2**128, 2**96,
+            2**32, 2**128 + 2**96 - 2**32 + 1, 2**352, (2**384 - 1) ^ (0xFFFFFFFF << 128)]
+
+    def structured():
+        v = 0
+        for i in range(12):
+            c = rng.random()
+            w = 0 if c < 0.3 else 0xFFFFFFFF if c < 0.6 else 1 if c < 0.65 else 0xFFFFFFFE if c < 0.7 else rng.getrandbits(32)
+            v |= w << (32 * i)
+        return v
+
+    vals = edge + [rng.randrange(2**384) for _ in range(120)] + [structured() for _ in range(400)]
+    for a in vals:
+        for b in rng.sample(vals, 6) + edge[:6]:
+            assert _feop384(sim, 0, a, b) == (a + b) % p
+            assert _feop384(sim, 1, a, b) == (a - b) % p
+            assert _feop384(sim, 2, a, b) == a * b % p
+        assert _feop384(sim, 3, a) == a * a % p
+        assert _feop384(sim, 4, a) == (-a) % p
+        assert _feop384(sim, 5, a) == a * pow(2, -1, p) % p
+        assert _feop384(sim, 6, a) == 3 * a % p
+        assert _feop384(sim, 9, a) == 8 * a % p
+        assert _feop384(sim, 8, a) == a % p
+    for a in vals[:25]:
+        assert _feop384(sim, 7, a) == (pow(a % p, -1, p) if a % p else 0)
+
+
+def test_p384_mul_golden_and_edges(sim):
+    """p384/src/test_vectors/group.rs:8,175 (k*G for k = 1..20, 32 multiplication vectors) + edge scalars, identity results"""
+    c = pyref.P384
+    g = golden("p384")
+    G = pyref.G(c)
+
+    def mul(k, P):
+        xy, _ = pyref.enc_point(P, 48)
+        out = ctypes.create_string_buffer(96)
+        inf = ctypes.create_string_buffer(1)
+        sim.sim_p384_mul(k.to_bytes(48, "big"), xy, out, inf)
+        return pyref.dec_point(out.raw, inf.raw[0], 48)
+
+    for v in g["group"]["add"]:
+        assert mul(v["k"], G) == (int(v["x"], 16), int(v["y"], 16))
+    for v in g["group"]["mul"]:
+        assert mul(int(v["k"], 16), G) == (int(v["x"], 16), int(v["y"], 16))
+    rng = random.Random(5)
+    P = pyref.mul(c, rng.randrange(1, c.n), G)
+    assert sim.sim_p384_on_curve(pyref.enc_point(P, 48)[0]) == 1
+    assert sim.sim_p384_on_curve(pyref.enc_point((P[0], (P[1] + 1) % c.p), 48)[0]) == 0
+    for k in [0, 1, 2, 3, 15, 16, 17, 2**128, 2**383, c.n - 1, c.n - 2, (c.n - 1) // 2] + [rng.randrange(c.n) for _ in range(12)]:
+        assert mul(k, P) == pyref.mul(c, k, P), hex(k)

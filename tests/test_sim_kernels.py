@@ -326,3 +326,31 @@ def test_lincomb_warp_balanced_bucket_kernel(sim, curve, bucket_k):
         assert stt[0] == 0 and path.value == 1
         rxy, rinf = ecref.lincomb(curve, K, xy, inf, nthreads=4)
         assert np.array_equal(oxy, np.asarray(rxy).reshape(-1)) and int(oinf[0]) == int(rinf)
+
+
+def test_p384_varbase_kernel_chain(sim):
+    """P-384 through the same kernels (generic_varbase_kernel<CurveP384> -> normalize_kernel<FpP384>), 48-byte records:
+    the reference's MUL_TEST_VECTORS (p384/src/test_vectors/group.rs:175), edge scalars, identity inputs, validation."""
+    c = pyref.P384
+    g = golden("p384")
+    rng = random.Random(384)
+    ks = [int(v["k"], 16) for v in g["group"]["mul"]] + [0, 1, c.n - 1, 2**383, rng.randrange(c.n)]
+    Ps = [pyref.G(c)] * len(g["group"]["mul"]) + [pyref.mul(c, 7, pyref.G(c))] * 3 + [None, pyref.mul(c, rng.randrange(1, c.n), pyref.G(c))]
+    n = len(ks)
+    K = np.frombuffer(b"".join(k.to_bytes(48, "big") for k in ks), np.uint8).copy()
+    xy = np.frombuffer(b"".join(pyref.enc_point(P, 48)[0] for P in Ps), np.uint8).copy()
+    inf = np.array([1 if P is None else 0 for P in Ps], np.uint8)
+    oxy, oinf, st = np.zeros(96 * n, np.uint8), np.zeros(n, np.uint8), np.zeros(2, np.uint32)
+    sim.simk_mul_batch(2, ctypes.c_size_t(n), _p(K), _p(xy), _p(inf), _p(oxy), _p(oinf), _p(st))
+    assert st[0] == 0
+    got = [pyref.dec_point(oxy[96 * i:96 * i + 96].tobytes(), int(oinf[i]), 48) for i in range(n)]
+    assert got == [pyref.mul(c, k, P) if P is not None else None for k, P in zip(ks, Ps)]
+    for i, v in enumerate(g["group"]["mul"]):
+        assert got[i] == (int(v["x"], 16), int(v["y"], 16))
+    # validation: scalar = n at index 3, off-curve point at index 1 -> flags, smallest index
+    Kb = K.copy()
+    Kb[48 * 3:48 * 4] = np.frombuffer(c.n.to_bytes(48, "big"), np.uint8)
+    xyb = xy.copy()
+    xyb[96 * 1 + 95] ^= 1
+    sim.simk_mul_batch(2, ctypes.c_size_t(n), _p(Kb), _p(xyb), _p(inf), _p(oxy), _p(oinf), _p(st))
+    assert st[0] == 3 and st[1] == 1
