@@ -89,21 +89,30 @@ ECG_DEV uint32_t load_pair(uint32_t* k, typename C::F::AffT& P, bool& inf, const
 #define P_TAB_WORDS 192  /* 8 Jacobian entries x 24 words */
 
 // secp256k1 variable-base: one pair per thread.
+// Field operations fully inlined (FpK256T<1>: no call marshalling) with a block-wide barrier between the doubling phase
+// and the addition phase of every window (k256_mul_thread<.., 1>): all warps of a block then run the same stretch of
+// code, so only one phase's instructions have to be resident in the 32 KB instruction cache at a time — the fully
+// inlined body without the barriers thrashes it (20.1 ms), the call-based body pays ~21 IMAD.MOV per call on the FMA
+// pipe (17.8 ms); this form measures 17.3 ms at (256,2) (profiles/r02_kbench_structure_variants.txt).
+// Every thread of a block must reach the barriers: out-of-range threads redo the block's last valid pair and store nothing.
+typedef FpK256T<1> FpK256Inline;
 template <int BLOCK, int MINBLK>
 ECG_KERNEL(BLOCK, MINBLK)
     k256_varbase_kernel(const uint8_t* __restrict__ kb, const uint8_t* __restrict__ pxy,
                         const uint8_t* __restrict__ pinf, size_t n, uint32_t* __restrict__ jac,
                         uint32_t* __restrict__ gtab, uint32_t* __restrict__ status, size_t base) {
   size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-  if (idx >= n) return;
+  const bool live = idx < n;
+  const size_t cidx = live ? idx : n - 1;
   uint32_t k[8];
   Aff P;
   bool inf;
-  uint32_t err = load_pair<CurveK256>(k, P, inf, kb, pxy, pinf, idx);
-  if (err) report_error(status, err, base + idx);
+  uint32_t err = load_pair<CurveK256>(k, P, inf, kb, pxy, pinf, cidx);
+  if (err && live) report_error(status, err, base + idx);
   TabRef tab{gtab + (size_t)blockIdx.x * BLOCK * K_TAB_WORDS + threadIdx.x, (uint32_t)BLOCK};
   Jac r;
-  k256_mul_thread(r, k, P, tab);
+  k256_mul_thread<FpK256Inline, 1>(r, k, P, tab);
+  if (!live) return;
   if (inf || err) FpK256::set_zero(r.Z);
   soa_store<8>(jac, n, idx, r.X.v, 0);
   soa_store<8>(jac, n, idx, r.Y.v, 8);

@@ -383,7 +383,8 @@ static ecg_status launch_norm(ecg_ctx* ctx, DevState& d, Lane& L, ecg_curve curv
 }
 
 // launch geometry of the variable-base kernels (registers set the occupancy; tables are in global memory)
-static const int K_BLOCK = 128, K_MINBLK = 4;  // secp256k1: <= 128 registers -> 16 warps/SM (mul = call, sqr inlined: OPT 7)
+static const int K_BLOCK = 256, K_MINBLK = 2;  // secp256k1: <= 128 registers -> 16 warps/SM; phase-synchronised inlined body (ecg_kernels.cuh)
+static const int KG_BLOCK = 128, KG_MINBLK = 4;  // secp256k1 a*G + b*P kernel: call-based body (mul = call, sqr inlined: OPT 7)
 static const int P_BLOCK = 128, P_MINBLK = 5;  // P-256   : <= 96 registers -> 20 warps/SM (Montgomery field: 34.09 vs 34.65 ms at (128,4), tools/kbench.cu)
 
 static const int Q_BLOCK = 128, Q_MINBLK = 3;  // P-384   : 12-limb values, <= 168 registers -> 12 warps/SM
@@ -620,7 +621,7 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
     LAUNCHED(ctx);
     DOM_BEGIN(ctx, L);
     if (k1c)
-      mul_gen_add_kernel<CurveK256, K_BLOCK, K_MINBLK, true><<<grid_for(cnt, K_BLOCK), K_BLOCK, 0, L.s()>>>(
+      mul_gen_add_kernel<CurveK256, KG_BLOCK, KG_MINBLK, true><<<grid_for(cnt, KG_BLOCK), KG_BLOCK, 0, L.s()>>>(
           va, vb, vp, nullptr, cnt, d.fb_table[op.curve], vj, (uint32_t*)L.buf[B_TAB], L.status, off);
     else
       mul_gen_add_kernel<CurveP256, P_BLOCK, P_MINBLK, false><<<grid_for(cnt, P_BLOCK), P_BLOCK, 0, L.s()>>>(
@@ -657,7 +658,7 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
       ST_TRY(ensure_tab(ctx, L, op.curve, cnt));
       DOM_BEGIN(ctx, L);
       if (k1)
-        mul_gen_add_kernel<CurveK256, K_BLOCK, K_MINBLK, true><<<grid_for(cnt, K_BLOCK), K_BLOCK, 0, L.s()>>>(
+        mul_gen_add_kernel<CurveK256, KG_BLOCK, KG_MINBLK, true><<<grid_for(cnt, KG_BLOCK), KG_BLOCK, 0, L.s()>>>(
             dp.a, dp.k, dp.p, dp.inf, cnt, d.fb_table[op.curve], jac, (uint32_t*)L.buf[B_TAB], L.status, off);
       else
         mul_gen_add_kernel<CurveP256, P_BLOCK, P_MINBLK, false><<<grid_for(cnt, P_BLOCK), P_BLOCK, 0, L.s()>>>(
