@@ -26,22 +26,22 @@ struct MsmGeom {
   uint32_t nbw;   // bucket slots per window: digits 0 .. 2^(c+1)+1 (slot 0 unused)
 };
 
-// bits [pos, pos+width) of an up-to-288-bit little-endian limb array (9 limbs), width <= 17
-ECG_D uint32_t msm_bits(const uint32_t* m, int pos, int width) {
+// bits [pos, pos+width) of a little-endian limb array of nm limbs (9 for the 256-bit curves, 13 for P-384), width <= 17
+ECG_D uint32_t msm_bits(const uint32_t* m, int pos, int width, int nm = 9) {
   int w = pos >> 5, b = pos & 31;
-  uint64_t lo = m[w];
-  uint64_t hi = (w + 1 < 9) ? m[w + 1] : 0;
+  uint64_t lo = w < nm ? m[w] : 0;
+  uint64_t hi = (w + 1 < nm) ? m[w + 1] : 0;
   uint64_t v = (lo | (hi << 32)) >> b;
   return (uint32_t)(v & ((1u << width) - 1u));
 }
 
 // Signed c-bit digits of a magnitude m (9 limbs, < 2^nbits (+1 bit of slack)): windows 0..W-2 in
 // [-2^(c-1)+1, 2^(c-1)], the top window unsigned (absorbs the carry and any slack bit).  out[w] = digit.
-ECG_D void msm_recode(int32_t* out, const uint32_t* m, const MsmGeom& g) {
+ECG_D void msm_recode(int32_t* out, const uint32_t* m, const MsmGeom& g, int nm = 9) {
   uint32_t carry = 0;
   const uint32_t half = 1u << (g.c - 1);
   for (int w = 0; w < g.W - 1; w++) {
-    uint32_t v = msm_bits(m, g.c * w, g.c) + carry;
+    uint32_t v = msm_bits(m, g.c * w, g.c, nm) + carry;
     if (v > half) {
       out[w] = (int32_t)v - (int32_t)(1u << g.c);
       carry = 1;
@@ -53,7 +53,7 @@ ECG_D void msm_recode(int32_t* out, const uint32_t* m, const MsmGeom& g) {
   int top = g.c * (g.W - 1);
   int width = g.nbits + 1 - top;  // one slack bit
   if (width > 17) width = 17;
-  out[g.W - 1] = (int32_t)(msm_bits(m, top, width) + carry);
+  out[g.W - 1] = (int32_t)(msm_bits(m, top, width, nm) + carry);
 }
 
 #if defined(__CUDACC__) || defined(ECG_HOST_SIM)  // kernels: CUDA, or the host simulation of tests/sim
@@ -66,24 +66,26 @@ ECG_KERNEL(128)
                     size_t n, MsmGeom g, uint32_t* __restrict__ pts, int32_t* __restrict__ digits,
                     uint32_t* __restrict__ count, uint32_t* __restrict__ status, size_t base) {
   typedef typename C::F F;
+  typedef typename F::FeT Fe;
+  constexpr int NL = F::NL, FB = 4 * F::NL;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const size_t nsub = GLV ? 2 * n : n;
-  uint32_t k[8], m[9];
-  Aff P;
+  uint32_t k[NL], m[NL + 1];
+  typename F::AffT P;
   bool skip = false;
   {
     uint32_t err = 0;
-    load_be32(k, kb + 32 * idx);
-    if (!lt8(k, C::N())) err |= 1u;
+    load_be<NL>(k, kb + FB * idx);
+    if (!ltN<NL>(k, C::N())) err |= 1u;
     bool inf = pinf != nullptr && pinf[idx] != 0;
     Fe x, y;
-    load_be32(x.v, pxy + 64 * idx);
-    load_be32(y.v, pxy + 64 * idx + 32);
+    load_be<NL>(x.v, pxy + 2 * FB * idx);
+    load_be<NL>(y.v, pxy + 2 * FB * idx + FB);
     F::from_canonical(P.x, x);
     F::from_canonical(P.y, y);
     if (!inf) {
-      bool ok = lt8(x.v, C::P()) && lt8(y.v, C::P());
+      bool ok = ltN<NL>(x.v, C::P()) && ltN<NL>(y.v, C::P());
       if (ok) {
         Fe b;
         C::b_internal(b);
@@ -98,7 +100,7 @@ ECG_KERNEL(128)
     }
     skip = inf || err != 0;
   }
-  int32_t dg[33];
+  int32_t dg[4 * NL + 1];  // c >= 8 -> at most 4 NL windows
   const int nh = GLV ? 2 : 1;
   GlvHalf h1, h2;
   if (GLV) {
@@ -109,7 +111,7 @@ ECG_KERNEL(128)
     size_t j = GLV ? 2 * idx + half : idx;
     uint32_t neg = 0;
 #pragma unroll
-    for (int i = 0; i < 9; i++) m[i] = 0;
+    for (int i = 0; i < NL + 1; i++) m[i] = 0;
     if (GLV) {
       const GlvHalf& h = half ? h2 : h1;
       // m = 2h + 1 - even
@@ -127,21 +129,23 @@ ECG_KERNEL(128)
       neg = h.neg;
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; i++) m[i] = k[i];
+      for (int i = 0; i < NL; i++) m[i] = k[i];
     }
     // sub-point: P or (beta x, y)
     Fe px = P.x;
-    if (GLV && half) {
-      Fe beta;
-      k256_beta(beta);
-      F::mul(px, px, beta);
+    if constexpr (GLV) {  // secp256k1 only
+      if (half) {
+        Fe beta;
+        k256_beta(beta);
+        F::mul(px, px, beta);
+      }
     }
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
-      pts[j * 16 + w] = px.v[w];
-      pts[j * 16 + 8 + w] = P.y.v[w];
+    for (int w = 0; w < NL; w++) {
+      pts[j * (2 * NL) + w] = px.v[w];
+      pts[j * (2 * NL) + NL + w] = P.y.v[w];
     }
-    msm_recode(dg, m, g);
+    msm_recode(dg, m, g, NL + 1);
     for (int w = 0; w < g.W; w++) {
       int32_t d = skip ? 0 : dg[w];
       if (neg) d = -d;
@@ -257,13 +261,20 @@ ECG_KERNEL(256)
   }
 }
 
-ECG_DEV void msm_load_point(Aff& e, const uint32_t* __restrict__ pts, uint32_t j) {
-  const uint4* p = reinterpret_cast<const uint4*>(pts + (size_t)j * 16);
-  uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
-  e.x.v[0] = a.x; e.x.v[1] = a.y; e.x.v[2] = a.z; e.x.v[3] = a.w;
-  e.x.v[4] = b.x; e.x.v[5] = b.y; e.x.v[6] = b.z; e.x.v[7] = b.w;
-  e.y.v[0] = c.x; e.y.v[1] = c.y; e.y.v[2] = c.z; e.y.v[3] = c.w;
-  e.y.v[4] = d.x; e.y.v[5] = d.y; e.y.v[6] = d.z; e.y.v[7] = d.w;
+template <int NL>
+ECG_DEV void msm_load_point(AffN<NL>& e, const uint32_t* __restrict__ pts, uint32_t j) {
+  const uint4* p = reinterpret_cast<const uint4*>(pts + (size_t)j * (2 * NL));
+  uint32_t w[2 * NL];
+#pragma unroll
+  for (int q = 0; q < NL / 2; q++) {
+    uint4 v = __ldg(p + q);
+    w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+  }
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    e.x.v[i] = w[i];
+    e.y.v[i] = w[NL + i];
+  }
 }
 
 // Bucket ids ordered by decreasing population: counting sort over MSM_ORDER_CLASSES size classes (sizes beyond the
@@ -348,6 +359,9 @@ ECG_KERNEL(128, 4)
     msm_bucket_kernel(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ list, const uint32_t* __restrict__ offset,
                       size_t nb, uint32_t* __restrict__ bkt, MsmSkew sk, const uint32_t* __restrict__ order) {
   typedef typename C::F F;
+  typedef typename F::JacT Jac;
+  typedef typename F::AffT Aff;
+  constexpr int NL = F::NL;
   size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (msm_skewed(sk, b == 0)) return;
   if (b >= nb) return;
@@ -363,7 +377,7 @@ ECG_KERNEL(128, 4)
   if (lo < hi) {
     uint32_t ent = list[lo];
     Aff e, nx;
-    msm_load_point(e, pts, ent >> 1);
+    msm_load_point<NL>(e, pts, ent >> 1);
     fe_cneg<F>(e.y, ent & 1u);
     acc.X = e.x;
     acc.Y = e.y;
@@ -371,24 +385,24 @@ ECG_KERNEL(128, 4)
     // software pipeline: the gather of point i+1 (a random 64-byte read, usually an L2 miss) is issued before the
     // mixed addition of point i
     uint32_t nent = lo + 1 < hi ? list[lo + 1] : 0;
-    if (lo + 1 < hi) msm_load_point(nx, pts, nent >> 1);
+    if (lo + 1 < hi) msm_load_point<NL>(nx, pts, nent >> 1);
 #pragma unroll 1
     for (uint32_t i = lo + 1; i < hi; i++) {
       e = nx;
       ent = nent;
       if (i + 1 < hi) {
         nent = list[i + 1];
-        msm_load_point(nx, pts, nent >> 1);
+        msm_load_point<NL>(nx, pts, nent >> 1);
       }
       fe_cneg<F>(e.y, ent & 1u);
       jac_madd<F, C::A_IS_MINUS3>(acc, acc, e);
     }
   }
 #pragma unroll
-  for (int w = 0; w < 8; w++) {
+  for (int w = 0; w < NL; w++) {
     bkt[(size_t)w * nb + b] = acc.X.v[w];
-    bkt[(size_t)(8 + w) * nb + b] = acc.Y.v[w];
-    bkt[(size_t)(16 + w) * nb + b] = acc.Z.v[w];
+    bkt[(size_t)(NL + w) * nb + b] = acc.Y.v[w];
+    bkt[(size_t)(2 * NL + w) * nb + b] = acc.Z.v[w];
   }
 }
 
@@ -397,6 +411,9 @@ template <class C>
 ECG_DEV void msm_bucket_sum(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ list, uint32_t lo, uint32_t hi, size_t b,
                             size_t nb, uint32_t* __restrict__ bkt) {
   typedef typename C::F F;
+  typedef typename F::JacT Jac;
+  typedef typename F::AffT Aff;
+  constexpr int NL = F::NL;
   Jac acc;
   F::set_zero(acc.X);
   F::set_one(acc.Y);
@@ -404,30 +421,30 @@ ECG_DEV void msm_bucket_sum(const uint32_t* __restrict__ pts, const uint32_t* __
   if (lo < hi) {
     uint32_t ent = list[lo];
     Aff e, nx;
-    msm_load_point(e, pts, ent >> 1);
+    msm_load_point<NL>(e, pts, ent >> 1);
     fe_cneg<F>(e.y, ent & 1u);
     acc.X = e.x;
     acc.Y = e.y;
     F::set_one(acc.Z);
     uint32_t nent = lo + 1 < hi ? list[lo + 1] : 0;
-    if (lo + 1 < hi) msm_load_point(nx, pts, nent >> 1);
+    if (lo + 1 < hi) msm_load_point<NL>(nx, pts, nent >> 1);
 #pragma unroll 1
     for (uint32_t i = lo + 1; i < hi; i++) {
       e = nx;
       ent = nent;
       if (i + 1 < hi) {
         nent = list[i + 1];
-        msm_load_point(nx, pts, nent >> 1);
+        msm_load_point<NL>(nx, pts, nent >> 1);
       }
       fe_cneg<F>(e.y, ent & 1u);
       jac_madd<F, C::A_IS_MINUS3>(acc, acc, e);
     }
   }
 #pragma unroll
-  for (int w = 0; w < 8; w++) {
+  for (int w = 0; w < NL; w++) {
     bkt[(size_t)w * nb + b] = acc.X.v[w];
-    bkt[(size_t)(8 + w) * nb + b] = acc.Y.v[w];
-    bkt[(size_t)(16 + w) * nb + b] = acc.Z.v[w];
+    bkt[(size_t)(NL + w) * nb + b] = acc.Y.v[w];
+    bkt[(size_t)(2 * NL + w) * nb + b] = acc.Z.v[w];
   }
 }
 
@@ -488,20 +505,22 @@ ECG_KERNEL(MSM_BS_BLOCK, 4)
   }
 }
 
-ECG_DEV void msm_jload(Jac& p, const uint32_t* __restrict__ a, size_t n, size_t i) {
+template <int NL>
+ECG_DEV void msm_jload(JacN<NL>& p, const uint32_t* __restrict__ a, size_t n, size_t i) {
 #pragma unroll
-  for (int w = 0; w < 8; w++) {
+  for (int w = 0; w < NL; w++) {
     p.X.v[w] = a[(size_t)w * n + i];
-    p.Y.v[w] = a[(size_t)(8 + w) * n + i];
-    p.Z.v[w] = a[(size_t)(16 + w) * n + i];
+    p.Y.v[w] = a[(size_t)(NL + w) * n + i];
+    p.Z.v[w] = a[(size_t)(2 * NL + w) * n + i];
   }
 }
-ECG_DEV void msm_jstore(uint32_t* __restrict__ a, size_t n, size_t i, const Jac& p) {
+template <int NL>
+ECG_DEV void msm_jstore(uint32_t* __restrict__ a, size_t n, size_t i, const JacN<NL>& p) {
 #pragma unroll
-  for (int w = 0; w < 8; w++) {
+  for (int w = 0; w < NL; w++) {
     a[(size_t)w * n + i] = p.X.v[w];
-    a[(size_t)(8 + w) * n + i] = p.Y.v[w];
-    a[(size_t)(16 + w) * n + i] = p.Z.v[w];
+    a[(size_t)(NL + w) * n + i] = p.Y.v[w];
+    a[(size_t)(2 * NL + w) * n + i] = p.Z.v[w];
   }
 }
 
@@ -521,6 +540,9 @@ ECG_KERNEL(128)
     msm_wreduce_kernel(const uint32_t* __restrict__ in, size_t n_in, size_t stride_in, size_t off, size_t len, size_t len_low, int W,
                        size_t nch, const uint32_t* __restrict__ Xprev, int level, uint32_t* __restrict__ outS, uint32_t* __restrict__ outX) {
   typedef typename C::F F;
+  typedef typename F::JacT Jac;
+  typedef typename F::AffT Aff;
+  constexpr int NL = F::NL;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)W * nch) return;
   size_t w = t / nch, ch = t % nch;
@@ -553,11 +575,15 @@ ECG_KERNEL(128)
 }
 
 // R_w = X_L[w] - k * Btot[w],  k = CH + CH^2 + ... + CH^L;  then out = sum_w 2^(c w) R_w  (Horner, thread 0).
+#define MSM_FINAL_THREADS 64 /* one thread per window: W <= 48 (384-bit scalars at c = 8) */
 template <class C>
-ECG_KERNEL(32)
+ECG_KERNEL(MSM_FINAL_THREADS)
     msm_final_kernel(const uint32_t* __restrict__ XL, const uint32_t* __restrict__ SL, int W, int c, int levels,
                      uint32_t* __restrict__ R, uint32_t* __restrict__ out) {
   typedef typename C::F F;
+  typedef typename F::JacT Jac;
+  typedef typename F::AffT Aff;
+  constexpr int NL = F::NL;
   int w = threadIdx.x;
   if (w < W) {
     Jac x, s, ks, t;

@@ -1009,7 +1009,7 @@ static MsmGeom msm_geometry(ecg_curve curve, size_t n) {
   int lg = 0;
   while (((size_t)1 << (lg + 1)) <= nsub) lg++;
   g.c = std::min(16, std::max(8, lg - 5));
-  g.nbits = glv ? 128 : 256;
+  g.nbits = glv ? 128 : (int)(32 * flimbs(curve));
   g.W = (g.nbits + g.c - 1) / g.c;
   g.nbw = ((uint32_t)1 << (g.c + 1)) + 2;
   return g;
@@ -1033,6 +1033,7 @@ template <class C, bool GLV>
 static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, size_t base, const MsmGeom& g, uint32_t** result) {
   const size_t nsub = GLV ? 2 * n : n;
   const size_t nb = (size_t)g.W * g.nbw;
+  constexpr size_t NLc = C::F::NL;
   // recursion geometry of the weighted reduction
   std::vector<size_t> lens, nchs;
   size_t len = g.nbw - 1;
@@ -1052,22 +1053,22 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
   uint32_t* Rw = nullptr;
   for (int pass = 0; pass < 2; pass++) {
     Carver cv{pass ? (uint8_t*)L.buf[B_MSM] : nullptr};
-    pts = cv.take<uint32_t>(nsub * 16);
+    pts = cv.take<uint32_t>(nsub * 2 * NLc);
     digits = cv.take<int32_t>(nsub * (size_t)g.W);
     count = cv.take<uint32_t>(2 * nb + 4);  // count | cursor | maxcnt, cleared together
     cursor = count ? count + nb + 1 : nullptr;
     blocksum = cv.take<uint32_t>((nb + MSM_SCAN_CHUNK - 1) / MSM_SCAN_CHUNK + 1);
     offset = cv.take<uint32_t>(nb + 1);
     list = cv.take<uint32_t>(nsub * (size_t)g.W);
-    bkt = cv.take<uint32_t>(nb * 24);
+    bkt = cv.take<uint32_t>(nb * 3 * NLc);
     order = cv.take<uint32_t>(nb);
     ohist = cv.take<uint32_t>(MSM_ORDER_CLASSES + 1);
     for (int l = 0; l < levels; l++) {
-      S[l] = cv.take<uint32_t>((size_t)g.W * nchs[l] * 24);
-      X[l] = cv.take<uint32_t>((size_t)g.W * nchs[l] * 24);
+      S[l] = cv.take<uint32_t>((size_t)g.W * nchs[l] * 3 * NLc);
+      X[l] = cv.take<uint32_t>((size_t)g.W * nchs[l] * 3 * NLc);
     }
-    Rw = cv.take<uint32_t>((size_t)g.W * 24);
-    res = cv.take<uint32_t>(24);
+    Rw = cv.take<uint32_t>((size_t)g.W * 3 * NLc);
+    res = cv.take<uint32_t>(3 * NLc);
     if (pass == 0) ST_TRY(ensure(ctx, L, B_MSM, cv.off + 256));
   }
   uint32_t* maxcnt = count + 2 * nb + 3;
@@ -1131,7 +1132,7 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
                                                                                  nchs[l], l == 0 ? nullptr : X[l - 1], l, S[l], X[l]);
     LAUNCHED(ctx);
   }
-  msm_final_kernel<C><<<1, 32, 0, L.s()>>>(X[levels - 1], S[levels - 1], g.W, g.c, levels - 1, Rw, res);
+  msm_final_kernel<C><<<1, MSM_FINAL_THREADS, 0, L.s()>>>(X[levels - 1], S[levels - 1], g.W, g.c, levels - 1, Rw, res);
   LAUNCHED(ctx);
   *result = res;
   return ECG_OK;
@@ -1147,32 +1148,33 @@ static ecg_status lincomb_shard(ecg_ctx* ctx, DevState& d, ecg_curve curve, cons
   ST_TRY(stage_in(ctx, L, B_K, k, sh.off, sh.cnt, fb, &dp.k));
   ST_TRY(stage_in(ctx, L, B_P, P_xy, sh.off, sh.cnt, 2 * fb, &dp.p));
   ST_TRY(stage_in(ctx, L, B_INF, P_inf, sh.off, sh.cnt, 1, &dp.inf));
-  // the bucket method is written for the 256-bit curves (digits of 8-limb scalars); P-384 sums per term
-  if (sh.cnt >= MSM_MIN_TERMS && !per_term && curve_256(curve)) {
+  if (sh.cnt >= MSM_MIN_TERMS && !per_term) {
     // bucket method, in pieces of at most MSM_MAX_TERMS terms whose partial sums are added at the end
     const size_t MSM_MAX_TERMS = msm_max_terms();
     size_t pieces = (sh.cnt + MSM_MAX_TERMS - 1) / MSM_MAX_TERMS;
-    ST_TRY(ensure(ctx, L, B_JAC, pieces * 96 + 96));
-    ST_TRY(ensure(ctx, L, B_JAC2, pieces * 96 + 96));
+    ST_TRY(ensure(ctx, L, B_JAC, pieces * pt + pt));
+    ST_TRY(ensure(ctx, L, B_JAC2, pieces * pt + pt));
     uint32_t* parts = (uint32_t*)L.buf[B_JAC];
     for (size_t pc = 0; pc < pieces; pc++) {
       size_t lo = pc * MSM_MAX_TERMS, cnt = std::min(MSM_MAX_TERMS, sh.cnt - lo);
       DevPtrs q;
-      q.k = dp.k + 32 * lo;
-      q.p = dp.p + 64 * lo;
+      q.k = dp.k + fb * lo;
+      q.p = dp.p + 2 * fb * lo;
       q.inf = dp.inf ? dp.inf + lo : nullptr;
       MsmGeom g = msm_geometry(curve, cnt);
       uint32_t* r1 = nullptr;
       if (curve == ECG_SECP256K1)
         ST_TRY((msm_run<CurveK256, true>(ctx, L, q, cnt, sh.off + lo, g, &r1)));
-      else
+      else if (curve == ECG_NISTP256)
         ST_TRY((msm_run<CurveP256, false>(ctx, L, q, cnt, sh.off + lo, g, &r1)));
+      else
+        ST_TRY((msm_run<CurveP384, false>(ctx, L, q, cnt, sh.off + lo, g, &r1)));
       if (pieces == 1) {
         *result = r1;
         return ECG_OK;
       }
       // gather piece results into an SoA array of `pieces` points (24 strided 4-byte copies)
-      for (int w = 0; w < 24; w++)
+      for (int w = 0; w < (int)(3 * flimbs(curve)); w++)
         CU_TRY(ctx, cudaMemcpyAsync(parts + (size_t)w * pieces + pc, r1 + w, 4, cudaMemcpyDeviceToDevice, L.s()));
     }
     return reduce_points_c(ctx, L, curve, parts, (uint32_t*)L.buf[B_JAC2], pieces, result);

@@ -540,7 +540,7 @@ static MsmGeom simk_msm_geometry(int curve, size_t n) {  // = msm_geometry (ecgp
   int lg = 0;
   while (((size_t)1 << (lg + 1)) <= nsub) lg++;
   g.c = std::min(16, std::max(8, lg - 5));
-  g.nbits = glv ? 128 : 256;
+  g.nbits = glv ? 128 : (curve == 2 ? 384 : 256);
   g.W = (g.nbits + g.c - 1) / g.c;
   g.nbw = ((uint32_t)1 << (g.c + 1)) + 2;
   return g;
@@ -550,7 +550,7 @@ template <class C>
 static std::vector<uint32_t> simk_reduce_points(std::vector<uint32_t> a, size_t n) {  // = reduce_points
   while (n > 1) {
     size_t m = (n + 31) / 32;
-    std::vector<uint32_t> b(24 * m);
+    std::vector<uint32_t> b(3 * C::F::NL * m);
     sim_launch(m, 128, [&] { jac_sum_kernel<C>(a.data(), n, b.data(), m); });
     a.swap(b);
     n = m;
@@ -573,7 +573,8 @@ static bool simk_msm_run(const uint8_t* k, const uint8_t* pxy, const uint8_t* pi
     len = nch;
   }
   const int levels = (int)lens.size();
-  std::vector<uint32_t> pts(nsub * 16), count(2 * nb + 4, 0), offset(nb + 1), list(nsub * (size_t)g.W + 1), bkt(nb * 24);
+  constexpr size_t NLc = C::F::NL;
+  std::vector<uint32_t> pts(nsub * 2 * NLc), count(2 * nb + 4, 0), offset(nb + 1), list(nsub * (size_t)g.W + 1), bkt(nb * 3 * NLc);
   std::vector<int32_t> digits(nsub * (size_t)g.W);
   const unsigned sb = (unsigned)((nb + MSM_SCAN_CHUNK - 1) / MSM_SCAN_CHUNK);
   std::vector<uint32_t> blocksum(sb + 1);
@@ -615,8 +616,8 @@ static bool simk_msm_run(const uint8_t* k, const uint8_t* pxy, const uint8_t* pi
   }
   std::vector<std::vector<uint32_t>> S(levels), X(levels);
   for (int l = 0; l < levels; l++) {
-    S[l].assign((size_t)g.W * nchs[l] * 24, 0);
-    X[l].assign((size_t)g.W * nchs[l] * 24, 0);
+    S[l].assign((size_t)g.W * nchs[l] * 3 * NLc, 0);
+    X[l].assign((size_t)g.W * nchs[l] * 3 * NLc, 0);
     const uint32_t* in = l == 0 ? bkt.data() : S[l - 1].data();
     size_t n_in = l == 0 ? nb : (size_t)g.W * nchs[l - 1];
     size_t stride = l == 0 ? g.nbw : nchs[l - 1];
@@ -628,9 +629,9 @@ static bool simk_msm_run(const uint8_t* k, const uint8_t* pxy, const uint8_t* pi
       msm_wreduce_kernel<C>(in, n_in, stride, off, lens[l], len_low, g.W, nchs[l], l == 0 ? nullptr : X[l - 1].data(), l, S[l].data(), X[l].data());
     });
   }
-  std::vector<uint32_t> Rw((size_t)g.W * 24);
-  result.assign(24, 0);
-  sim_launch_blocks(1, 32, [&] { msm_final_kernel<C>(X[levels - 1].data(), S[levels - 1].data(), g.W, g.c, levels - 1, Rw.data(), result.data()); });
+  std::vector<uint32_t> Rw((size_t)g.W * 3 * NLc);
+  result.assign(3 * NLc, 0);
+  sim_launch_blocks(1, MSM_FINAL_THREADS, [&] { msm_final_kernel<C>(X[levels - 1].data(), S[levels - 1].data(), g.W, g.c, levels - 1, Rw.data(), result.data()); });
   return true;
 }
 
@@ -644,13 +645,14 @@ static void simk_lincomb_t(int curve, size_t n, const uint8_t* k, const uint8_t*
     *path = simk_msm_run<C, GLV>(k, pxy, pinf, n, g, status, res, bucket_k) ? 1 : 2;
   }
   if (*path != 1) {  // per-term kernel + tree sum
-    std::vector<uint32_t> jac(24 * n);
+    constexpr size_t NLc = C::F::NL;
+    std::vector<uint32_t> jac(3 * NLc * n);
     size_t blocks = (n + SIM_BLOCK - 1) / SIM_BLOCK;
-    std::vector<uint32_t> gtab(blocks * SIM_BLOCK * (IS_K256 ? K_TAB_WORDS : P_TAB_WORDS));
-    if (IS_K256)
+    std::vector<uint32_t> gtab(blocks * SIM_BLOCK * (IS_K256 ? K_TAB_WORDS : 8 * 3 * NLc));
+    if constexpr (IS_K256)
       sim_launch(n, SIM_BLOCK, [&] { k256_varbase_kernel<SIM_BLOCK, 4>(k, pxy, pinf, n, jac.data(), gtab.data(), status, 0); });
     else
-      sim_launch(n, SIM_BLOCK, [&] { generic_varbase_kernel<CurveP256, SIM_BLOCK, 4>(k, pxy, pinf, n, jac.data(), gtab.data(), status, 0); });
+      sim_launch(n, SIM_BLOCK, [&] { generic_varbase_kernel<C, SIM_BLOCK, 4>(k, pxy, pinf, n, jac.data(), gtab.data(), status, 0); });
     res = simk_reduce_points<C>(jac, n);
   }
   simk_normalize<C>(res, 1, out_xy, out_inf);
@@ -661,15 +663,17 @@ extern "C" int simk_lincomb_k(int curve, size_t n, const uint8_t* k, const uint8
   status[0] = 0;
   status[1] = 0xFFFFFFFFu;
   if (n == 0) {  // empty sum = identity
-    memset(out_xy, 0, 64);
+    memset(out_xy, 0, curve == 2 ? 96 : 64);
     *out_inf = 1;
     *path = 0;
     return 0;
   }
   if (curve == 0)
     simk_lincomb_t<CurveK256, true, true>(curve, n, k, pxy, pinf, msm_min_terms, out_xy, out_inf, status, path, bucket_k);
-  else
+  else if (curve == 1)
     simk_lincomb_t<CurveP256, false, false>(curve, n, k, pxy, pinf, msm_min_terms, out_xy, out_inf, status, path, bucket_k);
+  else
+    simk_lincomb_t<CurveP384, false, false>(curve, n, k, pxy, pinf, msm_min_terms, out_xy, out_inf, status, path, bucket_k);
   return 0;
 }
 extern "C" int simk_lincomb(int curve, size_t n, const uint8_t* k, const uint8_t* pxy, const uint8_t* pinf, size_t msm_min_terms,

@@ -171,3 +171,23 @@ def test_large_batch_symmetry_and_sample(engine):
     assert not any(ysum)                                                 # y + y' = p
     for i in range(0, n, 1021):
         assert pyref.dec_point(xy[i].tobytes(), 0, NB) == pyref.mul(C, ks[i], Ps[i])
+
+
+def test_lincomb_bucket_method_p384(engine):
+    """>= 2^13 terms take the bucket method (12-limb digits, 384-bit scalars); 16 distinct points repeated, so that the
+    expected sum is 16 big-integer multiplications: sum_i k_i P_(i mod 16) = sum_j (sum_{i = j mod 16} k_i) P_j"""
+    n = 9001
+    rng = random.Random(99)
+    ks = [rng.randrange(C.n) for _ in range(n)]
+    Ps = rand_points(n, 21)
+    pxy, pinf = pts_bytes(Ps)
+    xy, inf = engine.lincomb("p384", ks_bytes(ks), pxy, pinf)
+    acc = None
+    for j in range(16):
+        acc = pyref.add(C, acc, pyref.mul(C, sum(ks[j::16]) % C.n, Ps[j]))
+    assert pyref.dec_point(np.asarray(xy).tobytes(), inf, NB) == acc
+    # thousands of identical terms: the bucket method declines (device-side skew flag), the per-term path answers
+    ks2 = [ks[0]] * n
+    pxy2, pinf2 = pts_bytes([Ps[0]] * n)
+    xy, inf = engine.lincomb("p384", ks_bytes(ks2), pxy2, pinf2)
+    assert pyref.dec_point(np.asarray(xy).tobytes(), inf, NB) == pyref.mul(C, ks[0] * n % C.n, Ps[0])

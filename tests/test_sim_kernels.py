@@ -354,3 +354,28 @@ def test_p384_varbase_kernel_chain(sim):
     xyb[96 * 1 + 95] ^= 1
     sim.simk_mul_batch(2, ctypes.c_size_t(n), _p(Kb), _p(xyb), _p(inf), _p(oxy), _p(oinf), _p(st))
     assert st[0] == 3 and st[1] == 1
+
+
+def test_p384_lincomb_bucket_method_chain(sim):
+    """the bucket-method chain (prep -> scan -> scatter -> order -> buckets -> window reduction -> Horner) with 12-limb
+    scalars and points: 384-bit digits, 48 windows at c = 8"""
+    c = pyref.P384
+    rng = random.Random(12)
+    n = 300
+    base = [pyref.mul(c, rng.randrange(1, c.n), pyref.G(c)) for _ in range(6)]
+    ks = [rng.randrange(c.n) for _ in range(n)]
+    ks[:4] = [0, 1, c.n - 1, 2**383]
+    Ps = [base[i % 6] for i in range(n)]
+    Ps[7] = None
+    K = np.frombuffer(b"".join(k.to_bytes(48, "big") for k in ks), np.uint8).copy()
+    xy = np.frombuffer(b"".join(pyref.enc_point(P, 48)[0] for P in Ps), np.uint8).copy()
+    inf = np.array([1 if P is None else 0 for P in Ps], np.uint8)
+    want = None
+    for k, P in zip(ks, Ps):
+        if P is not None:
+            want = pyref.add(c, want, pyref.mul(c, k, P))
+    for min_terms, path_want in ((64, 1), (10**6, 0)):  # bucket method / per-term path
+        oxy, oinf, st, path = np.zeros(96, np.uint8), np.zeros(1, np.uint8), np.zeros(2, np.uint32), ctypes.c_int(-1)
+        sim.simk_lincomb(2, ctypes.c_size_t(n), _p(K), _p(xy), _p(inf), ctypes.c_size_t(min_terms), _p(oxy), _p(oinf), _p(st), ctypes.byref(path))
+        assert st[0] == 0 and path.value == path_want
+        assert pyref.dec_point(oxy.tobytes(), int(oinf[0]), 48) == want
