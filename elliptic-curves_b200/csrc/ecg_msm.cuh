@@ -362,6 +362,7 @@ ECG_KERNEL(128, 4)
   typedef typename F::JacT Jac;
   typedef typename F::AffT Aff;
   constexpr int NL = F::NL;
+  (void)NL;
   size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (msm_skewed(sk, b == 0)) return;
   if (b >= nb) return;
@@ -414,6 +415,7 @@ ECG_DEV void msm_bucket_sum(const uint32_t* __restrict__ pts, const uint32_t* __
   typedef typename F::JacT Jac;
   typedef typename F::AffT Aff;
   constexpr int NL = F::NL;
+  (void)NL;
   Jac acc;
   F::set_zero(acc.X);
   F::set_one(acc.Y);
@@ -543,6 +545,7 @@ ECG_KERNEL(128)
   typedef typename F::JacT Jac;
   typedef typename F::AffT Aff;
   constexpr int NL = F::NL;
+  (void)NL;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)W * nch) return;
   size_t w = t / nch, ch = t % nch;
@@ -584,6 +587,7 @@ ECG_KERNEL(MSM_FINAL_THREADS)
   typedef typename F::JacT Jac;
   typedef typename F::AffT Aff;
   constexpr int NL = F::NL;
+  (void)NL;
   int w = threadIdx.x;
   if (w < W) {
     Jac x, s, ks, t;

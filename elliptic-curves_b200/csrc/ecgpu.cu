@@ -348,6 +348,29 @@ static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n
 // bytes per field element / scalar at the ABI (32; 48 for P-384) and 32-bit limbs per field element
 static inline size_t fbytes(ecg_curve c) { return c == ECG_NISTP384 ? 48 : 32; }
 static inline size_t flimbs(ecg_curve c) { return c == ECG_NISTP384 ? 12 : 8; }
+// ECG_INLINE_LOOPS=0 (environment) keeps the call-based field operations in the one-point-operation-per-iteration
+// kernels (fixed-base, bucket accumulation): measurement knob, default = inlined
+static bool inline_loops() {
+  static const bool v = []() {
+    const char* e = getenv("ECG_INLINE_LOOPS");
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
+// same as FOR_CURVE below with CV bound to the all-inlined variant of the curve (ecg_curves.cuh)
+#define FOR_CURVE_INL(curve, ...)         \
+  do {                                    \
+    if ((curve) == ECG_SECP256K1) {       \
+      typedef CurveK256I CV;              \
+      __VA_ARGS__;                        \
+    } else if ((curve) == ECG_NISTP256) { \
+      typedef CurveP256I CV;              \
+      __VA_ARGS__;                        \
+    } else {                              \
+      typedef CurveP384I CV;              \
+      __VA_ARGS__;                        \
+    }                                     \
+  } while (0)
 // run a statement with CV bound to the curve's parameter struct (CurveK256 / CurveP256 / CurveP384)
 #define FOR_CURVE(curve, ...)             \
   do {                                    \
@@ -650,7 +673,10 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
       break;
     case BatchOp::MULGEN:
       DOM_BEGIN(ctx, L);
-      FOR_CURVE(op.curve, fixedbase_kernel<CV><<<grid_for(cnt, 128), 128, 0, L.s()>>>(dp.k, cnt, d.fb_table[op.curve], jac, L.status, off));
+      if (inline_loops())
+        FOR_CURVE_INL(op.curve, fixedbase_kernel<CV><<<grid_for(cnt, 128), 128, 0, L.s()>>>(dp.k, cnt, d.fb_table[op.curve], jac, L.status, off));
+      else
+        FOR_CURVE(op.curve, fixedbase_kernel<CV><<<grid_for(cnt, 128), 128, 0, L.s()>>>(dp.k, cnt, d.fb_table[op.curve], jac, L.status, off));
       LAUNCHED(ctx);
       DOM_END(ctx, L);
       break;
@@ -1029,7 +1055,7 @@ struct Carver {
 
 // Everything is enqueued without waiting; if the input turns out too skewed for the bucket method the result is
 // garbage and finish() sets ctx->skew (the caller then repeats the call with per_term = true).
-template <class C, bool GLV>
+template <class C, class CI, bool GLV>
 static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, size_t base, const MsmGeom& g, uint32_t** result) {
   const size_t nsub = GLV ? 2 * n : n;
   const size_t nb = (size_t)g.W * g.nbw;
@@ -1115,7 +1141,10 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
       msm_bucket_sorted_kernel<C, 4><<<grid_for(nb, MSM_BS_BLOCK * 4), MSM_BS_BLOCK, 0, L.s()>>>(pts, list, offset, nb, bkt, sk);
       break;
     default:
-      msm_bucket_kernel<C><<<grid_for(nb, 128), 128, 0, L.s()>>>(pts, list, offset, nb, bkt, sk, use_order ? order : nullptr);
+      if (inline_loops())
+        msm_bucket_kernel<CI><<<grid_for(nb, 128), 128, 0, L.s()>>>(pts, list, offset, nb, bkt, sk, use_order ? order : nullptr);
+      else
+        msm_bucket_kernel<C><<<grid_for(nb, 128), 128, 0, L.s()>>>(pts, list, offset, nb, bkt, sk, use_order ? order : nullptr);
   }
   LAUNCHED(ctx);
   DOM_END(ctx, L);
@@ -1164,11 +1193,11 @@ static ecg_status lincomb_shard(ecg_ctx* ctx, DevState& d, ecg_curve curve, cons
       MsmGeom g = msm_geometry(curve, cnt);
       uint32_t* r1 = nullptr;
       if (curve == ECG_SECP256K1)
-        ST_TRY((msm_run<CurveK256, true>(ctx, L, q, cnt, sh.off + lo, g, &r1)));
+        ST_TRY((msm_run<CurveK256, CurveK256I, true>(ctx, L, q, cnt, sh.off + lo, g, &r1)));
       else if (curve == ECG_NISTP256)
-        ST_TRY((msm_run<CurveP256, false>(ctx, L, q, cnt, sh.off + lo, g, &r1)));
+        ST_TRY((msm_run<CurveP256, CurveP256I, false>(ctx, L, q, cnt, sh.off + lo, g, &r1)));
       else
-        ST_TRY((msm_run<CurveP384, false>(ctx, L, q, cnt, sh.off + lo, g, &r1)));
+        ST_TRY((msm_run<CurveP384, CurveP384I, false>(ctx, L, q, cnt, sh.off + lo, g, &r1)));
       if (pieces == 1) {
         *result = r1;
         return ECG_OK;

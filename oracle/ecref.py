@@ -59,6 +59,31 @@ def lib():
     return _lib
 
 
+LIB384 = os.path.join(_HERE, "libecref384.so")
+_lib384 = None
+
+
+def lib384():
+    """oracle/ecref_p384.c — the P-384 restatement (48-byte records)"""
+    global _lib384
+    if _lib384 is None:
+        tagf = LIB384 + ".host"
+        tag = _host_tag()
+        src = os.path.join(_HERE, "ecref_p384.c")
+        if (not os.path.exists(LIB384) or os.path.getmtime(LIB384) < os.path.getmtime(src) or not os.path.exists(tagf)
+                or open(tagf).read().strip() != tag):
+            subprocess.check_call(["make", "-C", _HERE, "-B", "libecref384.so"], stdout=subprocess.DEVNULL)
+            with open(tagf, "w") as f:
+                f.write(tag)
+        _lib384 = ctypes.CDLL(LIB384)
+        _lib384.ecref384_init()
+        vp, sz = ctypes.c_void_p, ctypes.c_size_t
+        _lib384.ecref384_mul_batch.argtypes = [sz, vp, vp, vp, vp, vp, ctypes.c_int]
+        _lib384.ecref384_mul_gen_batch.argtypes = [sz, vp, vp, vp, ctypes.c_int]
+        _lib384.ecref384_lincomb.argtypes = [sz, vp, vp, vp, vp, vp, ctypes.c_int]
+    return _lib384
+
+
 def _p(a):
     return ctypes.c_void_p(a.ctypes.data) if a is not None else ctypes.c_void_p(0)
 
@@ -68,10 +93,18 @@ CURVE = {"k256": 0, "p256": 1, 0: 0, 1: 1}
 
 def mul_batch(curve, k, pxy, pinf=None, nthreads=1, variant=0):
     k = np.ascontiguousarray(k, np.uint8).reshape(-1)
-    n = k.size // 32
     pxy = np.ascontiguousarray(pxy, np.uint8).reshape(-1)
     if pinf is not None:
         pinf = np.ascontiguousarray(pinf, np.uint8).reshape(-1)
+    if curve in ("p384", 2):
+        n = k.size // 48
+        oxy = np.zeros(96 * n, np.uint8)
+        oinf = np.zeros(n, np.uint8)
+        rc = lib384().ecref384_mul_batch(n, _p(k), _p(pxy), _p(pinf), _p(oxy), _p(oinf), nthreads)
+        if rc:
+            raise ValueError(f"ecref384_mul_batch rc={rc}")
+        return oxy.reshape(n, 96), oinf
+    n = k.size // 32
     oxy = np.zeros(64 * n, np.uint8)
     oinf = np.zeros(n, np.uint8)
     rc = lib().ecref_mul_batch(CURVE[curve], n, _p(k), _p(pxy), _p(pinf), _p(oxy), _p(oinf), nthreads, variant)
@@ -82,6 +115,14 @@ def mul_batch(curve, k, pxy, pinf=None, nthreads=1, variant=0):
 
 def mul_gen_batch(curve, k, nthreads=1):
     k = np.ascontiguousarray(k, np.uint8).reshape(-1)
+    if curve in ("p384", 2):
+        n = k.size // 48
+        oxy = np.zeros(96 * n, np.uint8)
+        oinf = np.zeros(n, np.uint8)
+        rc = lib384().ecref384_mul_gen_batch(n, _p(k), _p(oxy), _p(oinf), nthreads)
+        if rc:
+            raise ValueError(f"ecref384_mul_gen_batch rc={rc}")
+        return oxy.reshape(n, 96), oinf
     n = k.size // 32
     oxy = np.zeros(64 * n, np.uint8)
     oinf = np.zeros(n, np.uint8)
@@ -108,10 +149,18 @@ def mul_gen_add_batch(curve, a, b, pxy, pinf=None, nthreads=1):
 
 def lincomb(curve, k, pxy, pinf=None, nthreads=1):
     k = np.ascontiguousarray(k, np.uint8).reshape(-1)
-    n = k.size // 32
     pxy = np.ascontiguousarray(pxy, np.uint8).reshape(-1)
     if pinf is not None:
         pinf = np.ascontiguousarray(pinf, np.uint8).reshape(-1)
+    if curve in ("p384", 2):
+        n = k.size // 48
+        oxy = np.zeros(96, np.uint8)
+        oinf = np.zeros(1, np.uint8)
+        rc = lib384().ecref384_lincomb(n, _p(k), _p(pxy), _p(pinf), _p(oxy), _p(oinf), nthreads)
+        if rc:
+            raise ValueError(f"ecref384_lincomb rc={rc}")
+        return oxy, int(oinf[0])
+    n = k.size // 32
     oxy = np.zeros(64, np.uint8)
     oinf = np.zeros(1, np.uint8)
     rc = lib().ecref_lincomb(CURVE[curve], n, _p(k), _p(pxy), _p(pinf), _p(oxy), _p(oinf), nthreads)

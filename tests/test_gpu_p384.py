@@ -191,3 +191,23 @@ def test_lincomb_bucket_method_p384(engine):
     pxy2, pinf2 = pts_bytes([Ps[0]] * n)
     xy, inf = engine.lincomb("p384", ks_bytes(ks2), pxy2, pinf2)
     assert pyref.dec_point(np.asarray(xy).tobytes(), inf, NB) == pyref.mul(C, ks[0] * n % C.n, Ps[0])
+
+
+def test_var_base_4096_pairs_vs_c_restatement(engine):
+    """a batch large enough for several blocks per SM, every output against oracle/ecref_p384.c"""
+    import ecref
+
+    n = 4096
+    rng = np.random.default_rng(4096)
+    K = rng.integers(0, 256, size=(n, NB), dtype=np.uint8)
+    K[:, 0] &= 0x7F
+    pxy, pinf = pts_bytes(rand_points(n, 33))
+    xy, inf = engine.mul_batch("p384", K.reshape(-1), pxy, pinf)
+    r_xy, r_inf = ecref.mul_batch("p384", K.reshape(-1), pxy, pinf, nthreads=8)
+    assert np.array_equal(np.asarray(xy).reshape(-1), r_xy.reshape(-1)) and np.array_equal(inf, r_inf)
+    gxy, ginf = engine.mul_by_generator("p384", K.reshape(-1))
+    r_xy, r_inf = ecref.mul_gen_batch("p384", K.reshape(-1), nthreads=8)
+    assert np.array_equal(np.asarray(gxy).reshape(-1), r_xy.reshape(-1)) and np.array_equal(ginf, r_inf)
+    lxy, linf = engine.lincomb("p384", K.reshape(-1), pxy, pinf)
+    e_xy, e_inf = ecref.lincomb("p384", K.reshape(-1), pxy, pinf, nthreads=8)
+    assert np.array_equal(np.asarray(lxy), e_xy) and linf == e_inf

@@ -175,3 +175,48 @@ def test_oracle_signature_verification_vs_reference_vectors():
             Q = (int(x["q_x"], 16), int(x["q_y"], 16))
             assert pyref.ecdsa_sign(c, d, z, k) == (r, s)
             assert pyref.ecdsa_verify(c, z, r, s, Q) and not pyref.ecdsa_verify(c, z ^ 1, r, s, Q)
+
+
+def test_p384_restatement_pinned_to_reference_vectors_and_model():
+    """oracle/ecref_p384.c (the reference's generic primeorder path over a 384-bit Montgomery field) against the reference's
+    own P-384 vectors (p384/src/test_vectors/group.rs:8,175) and the big-integer model: k*G, k*P, lincomb, identities,
+    rejected inputs."""
+    import random
+
+    import numpy as np
+
+    c = pyref.P384
+    g = golden("p384")
+    G = pyref.G(c)
+    ks = list(range(1, 21)) + [int(v["k"], 16) for v in g["group"]["mul"]]
+    want = [(int(v["x"], 16), int(v["y"], 16)) for v in g["group"]["add"]] + [(int(v["x"], 16), int(v["y"], 16)) for v in g["group"]["mul"]]
+    K = np.frombuffer(b"".join(k.to_bytes(48, "big") for k in ks), np.uint8)
+    xy, inf = ecref.mul_gen_batch("p384", K, nthreads=4)
+    assert [pyref.dec_point(xy[i].tobytes(), int(inf[i]), 48) for i in range(len(ks))] == want
+    Gb = np.frombuffer(pyref.enc_point(G, 48)[0] * len(ks), np.uint8)
+    xy, inf = ecref.mul_batch("p384", K, Gb, None, nthreads=4)
+    assert [pyref.dec_point(xy[i].tobytes(), int(inf[i]), 48) for i in range(len(ks))] == want
+    rng = random.Random(384)
+    n = 60
+    ks = [0, 1, c.n - 1, 2**383] + [rng.randrange(c.n) for _ in range(n - 4)]
+    Ps = [pyref.mul(c, rng.randrange(1, c.n), G) for _ in range(n)]
+    Ps[9] = None
+    K = np.frombuffer(b"".join(k.to_bytes(48, "big") for k in ks), np.uint8)
+    P = np.frombuffer(b"".join(pyref.enc_point(p, 48)[0] for p in Ps), np.uint8)
+    I = np.array([1 if p is None else 0 for p in Ps], np.uint8)
+    xy, inf = ecref.mul_batch("p384", K, P, I, nthreads=3)
+    assert [pyref.dec_point(xy[i].tobytes(), int(inf[i]), 48) for i in range(n)] == [pyref.mul(c, k, p) if p is not None else None for k, p in zip(ks, Ps)]
+    lxy, linf = ecref.lincomb("p384", K, P, I, nthreads=3)
+    acc = None
+    for k, p in zip(ks, Ps):
+        if p is not None:
+            acc = pyref.add(c, acc, pyref.mul(c, k, p))
+    assert pyref.dec_point(lxy.tobytes(), linf, 48) == acc
+    bad = K.copy()
+    bad[48 * 5:48 * 6] = np.frombuffer(c.n.to_bytes(48, "big"), np.uint8)
+    with pytest.raises(ValueError):
+        ecref.mul_batch("p384", bad, P, I)
+    off = P.copy()
+    off[96 * 3 + 95] ^= 1
+    with pytest.raises(ValueError):
+        ecref.mul_batch("p384", K, off, I)
