@@ -6,7 +6,8 @@
 // Representation here: plain integers weakly reduced to [0, 2^384) — p == -1 only modulo 2^32, so a multiplier-free
 // Montgomery reduction would need twelve dependent one-word rounds (~400 carry-chain instructions); the Solinas / FIPS
 // 186-4 D.2.4 word recombination needs ~150 and no domain conversion.  2^384 == K (mod p), K = 2^128 + 2^96 - 2^32 + 1.
-// Product: the generic even/odd-accumulator schoolbook mulNxN<12> (144 IMAD.WIDE); squaring reuses it.
+// Product: the generic even/odd-accumulator schoolbook mulNxN<12> (144 IMAD.WIDE); squaring: sqrN<12> (66 cross products
+// column by column + 12 diagonal squares = 78 multiplier slots).
 #pragma once
 #include "ecg_prim.cuh"
 
@@ -171,7 +172,22 @@ struct FpP384T {
       mul_body(r, a, b);
   }
   ECG_D static void mul_d(Fe& r, const Fe& a, const Fe& b) { mul(r, a, b); }
-  ECG_D static void sqr(Fe& r, const Fe& a) { mul(r, a, a); }
+  ECG_D static void sqr_body(Fe& r, const Fe& a) {
+    uint32_t t[24];
+    sqrN<12>(t, a.v);
+    reduce24(r, t);
+  }
+  static ECG_NOINLINE_D Fe sqr_call(Fe a) {
+    Fe r;
+    sqr_body(r, a);
+    return r;
+  }
+  ECG_D static void sqr(Fe& r, const Fe& a) {
+    if (OPT & 2)
+      r = sqr_call(a);
+    else
+      sqr_body(r, a);
+  }
 
   ECG_D static void add(Fe& r, const Fe& a, const Fe& b) {
     uint32_t c = addN<12>(r.v, a.v, b.v);

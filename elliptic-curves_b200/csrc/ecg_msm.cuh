@@ -532,11 +532,19 @@ ECG_DEV void msm_jstore(uint32_t* __restrict__ a, size_t n, size_t i, const JacN
 //     S  = sum A_j                      (chunk total   -> input of level l+1)
 //     T  = sum (j - ch*CH + 1) A_j      (chunk-local weighted sum)
 // and carries the plain sum of everything the lower levels produced:
-//     X_l[ch] = sum_{ch' in chunk} X_{l-1}[ch']  +  CH^l * T          (X_{-1} = nothing)
-// At the last level (one chunk per row)  X_L = R_w + Btot * (CH + CH^2 + ... + CH^L),  Btot = S_L, which
+//     X_l[ch] = sum_{ch' in chunk} X_{l-1}[ch']  +  (CH_0 ... CH_{l-1}) * T          (X_{-1} = nothing)
+// At the last level (one chunk per row)  X_L = R_w + Btot * (CH_0 + CH_0 CH_1 + ... + CH_0 ... CH_{L-1}),  Btot = S_L, which
 // msm_final_kernel undoes before the Horner combination of the windows.
-#define MSM_CH 16
-#define MSM_CH_LOG2 4
+// Chunk sizes: 16 at level 0 (one thread per chunk still gives tens of thousands of threads: throughput-bound), 4 at
+// the levels above, which hold only a few thousand elements and are bound by the LENGTH of each thread's dependent
+// chain (3 additions per element): 16+4+4+... keeps that chain at 12 additions per level instead of 48.
+#define MSM_CH0 16
+#define MSM_CH0_LOG2 4
+#define MSM_CHU 4
+#define MSM_CHU_LOG2 2
+ECG_D int msm_ch(int level) { return level == 0 ? MSM_CH0 : MSM_CHU; }
+// log2 of the product of the chunk sizes of the levels below `level` (the weight of one level-`level` element)
+ECG_D int msm_scale_log2(int level) { return level == 0 ? 0 : MSM_CH0_LOG2 + MSM_CHU_LOG2 * (level - 1); }
 template <class C>
 ECG_KERNEL(128)
     msm_wreduce_kernel(const uint32_t* __restrict__ in, size_t n_in, size_t stride_in, size_t off, size_t len, size_t len_low, int W,
@@ -553,7 +561,8 @@ ECG_KERNEL(128)
   // signed windows below it stop at len_low = 2^(c-1) at level 0: three quarters of the rows' slots are never
   // populated, and the chunks that cover only such slots contribute the identity without being read
   const size_t len_w = (w + 1 == (size_t)W) ? len : len_low;
-  size_t lo = ch * MSM_CH, hi = lo + MSM_CH < len_w ? lo + MSM_CH : len_w;
+  const size_t CHL = (size_t)msm_ch(level);
+  size_t lo = ch * CHL, hi = lo + CHL < len_w ? lo + CHL : len_w;
   if (hi < lo) hi = lo;
   Jac S, T, X, p;
   F::set_zero(S.X);
@@ -570,14 +579,15 @@ ECG_KERNEL(128)
       jac_add<F, C::A_IS_MINUS3>(X, X, p);
     }
   }
-  for (int i = 0; i < MSM_CH_LOG2 * level; i++) jac_dbl<F, C::A_IS_MINUS3>(T, T);
+  for (int i = 0; i < msm_scale_log2(level); i++) jac_dbl<F, C::A_IS_MINUS3>(T, T);
   jac_add<F, C::A_IS_MINUS3>(X, X, T);
   size_t n_out = (size_t)W * nch;
   msm_jstore(outS, n_out, t, S);
   msm_jstore(outX, n_out, t, X);
 }
 
-// R_w = X_L[w] - k * Btot[w],  k = CH + CH^2 + ... + CH^L;  then out = sum_w 2^(c w) R_w  (Horner, thread 0).
+// R_w = X_L[w] - k * Btot[w],  k = CH0 (1 + CHU (1 + CHU (...))) with L factors (one per level above 0);
+// then out = sum_w 2^(c w) R_w  (Horner, thread 0).
 #define MSM_FINAL_THREADS 64 /* one thread per window: W <= 48 (384-bit scalars at c = 8) */
 template <class C>
 ECG_KERNEL(MSM_FINAL_THREADS)
@@ -593,13 +603,13 @@ ECG_KERNEL(MSM_FINAL_THREADS)
     Jac x, s, ks, t;
     msm_jload(x, XL, W, w);
     msm_jload(s, SL, W, w);
-    // ks = k * s by Horner over the base-CH digits 1,1,...,1,0  (k = CH * (1 + CH * (1 + ...)))
+    // ks = k * s by Horner: innermost factor first (levels above 0 use CHU), CH0 last
     ks = s;
     for (int l = 1; l < levels; l++) {
-      for (int i = 0; i < MSM_CH_LOG2; i++) jac_dbl<F, C::A_IS_MINUS3>(ks, ks);
+      for (int i = 0; i < MSM_CHU_LOG2; i++) jac_dbl<F, C::A_IS_MINUS3>(ks, ks);
       jac_add<F, C::A_IS_MINUS3>(ks, ks, s);
     }
-    for (int i = 0; i < MSM_CH_LOG2; i++) jac_dbl<F, C::A_IS_MINUS3>(ks, ks);
+    for (int i = 0; i < MSM_CH0_LOG2; i++) jac_dbl<F, C::A_IS_MINUS3>(ks, ks);
     if (levels == 0) {
       F::set_zero(ks.X);
       F::set_one(ks.Y);

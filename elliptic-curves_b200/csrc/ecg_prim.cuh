@@ -91,6 +91,12 @@ ECG_D void madc_wide_new(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
                : "=r"(lo), "=r"(hi)
                : "r"(a), "r"(b));
 }
+// (c0, c1, c2) += a*b   (three-word running accumulator of a product-scanning column)
+ECG_D void mad_acc3(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t a, uint32_t b) {
+  asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+               : "+r"(c0), "+r"(c1), "+r"(c2)
+               : "r"(a), "r"(b));
+}
 ECG_D uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
 ECG_D uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_l(lo, hi, s); }
 ECG_D uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
@@ -159,6 +165,14 @@ inline void mad_wide_top(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
   uint64_t s0 = (uint64_t)lo + (uint32_t)p;
   lo = (uint32_t)s0;
   hi = (uint32_t)(p >> 32) + (uint32_t)(s0 >> 32);
+}
+inline void mad_acc3(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t a, uint32_t b) {
+  uint64_t p = (uint64_t)a * b;
+  uint64_t s0 = (uint64_t)c0 + (uint32_t)p;
+  uint64_t s1 = (uint64_t)c1 + (uint32_t)(p >> 32) + (s0 >> 32);
+  c0 = (uint32_t)s0;
+  c1 = (uint32_t)s1;
+  c2 += (uint32_t)(s1 >> 32);
 }
 inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
   s &= 31;
@@ -268,6 +282,40 @@ ECG_D void mulNxN(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 #pragma unroll
   for (int k = 2; k < 2 * N - 1; k++) r[k] = addc_cc(E[k], O[k - 1]);
   r[2 * N - 1] = addc(E[2 * N - 1], O[2 * N - 2]);
+}
+
+// N-limb square -> 2N limbs for any N: the N(N-1)/2 cross products a_i*a_j (i < j) once, accumulated column by column
+// in a three-word running sum (each product = one mad.lo / madc.hi pair: the same multiplier time as one IMAD.WIDE),
+// doubled by a 1-bit funnel shift, and the N diagonal squares added with one IMAD.WIDE.X chain: N(N+1)/2 multiplier
+// slots instead of N*N (12 limbs: 78 instead of 144).  The 8-limb fields keep the hand-scheduled sqr8 below.
+template <int N>
+ECG_D void sqrN(uint32_t* r, const uint32_t* a) {
+  uint32_t S[2 * N];
+  uint32_t c0 = 0, c1 = 0, c2 = 0;
+  S[0] = 0;
+#pragma unroll
+  for (int k = 1; k <= 2 * N - 3; k++) {
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const int j = k - i;
+      if (i < j && j < N) mad_acc3(c0, c1, c2, a[i], a[j]);
+    }
+    S[k] = c0;
+    c0 = c1;
+    c1 = c2;
+    c2 = 0;
+  }
+  S[2 * N - 2] = c0;
+  S[2 * N - 1] = c1;
+  uint32_t T[2 * N];
+#pragma unroll
+  for (int k = 2 * N - 1; k >= 1; k--) T[k] = funnel_l(S[k - 1], S[k], 1);
+  T[0] = 0;
+  mad_wide_cc(T[0], T[1], a[0], a[0]);
+#pragma unroll
+  for (int i = 1; i < N; i++) madc_wide_cc(T[2 * i], T[2 * i + 1], a[i], a[i]);
+#pragma unroll
+  for (int k = 0; k < 2 * N; k++) r[k] = T[k];
 }
 
 // 8x8 -> 16 limb schoolbook product, row-wise, with the "even/odd accumulator" layout: products whose

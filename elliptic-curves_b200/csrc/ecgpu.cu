@@ -1064,7 +1064,8 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
   std::vector<size_t> lens, nchs;
   size_t len = g.nbw - 1;
   for (;;) {
-    size_t nch = (len + MSM_CH - 1) / MSM_CH;
+    const size_t chl = lens.empty() ? MSM_CH0 : MSM_CHU;  // chunk size of this level (ecg_msm.cuh)
+    size_t nch = (len + chl - 1) / chl;
     lens.push_back(len);
     nchs.push_back(nch);
     if (nch == 1) break;
@@ -1156,7 +1157,7 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
     size_t off = l == 0 ? 1 : 0;
     // rows below the top window only populate the first 2^(c-1) slots (level 0), i.e. ceil(that / CH^l) chunk totals at level l
     size_t len_low = ((size_t)1 << (g.c - 1));
-    for (int q = 0; q < l; q++) len_low = (len_low + MSM_CH - 1) / MSM_CH;
+    for (int q = 0; q < l; q++) len_low = (len_low + (q == 0 ? MSM_CH0 : MSM_CHU) - 1) / (q == 0 ? MSM_CH0 : MSM_CHU);
     msm_wreduce_kernel<C><<<grid_for((size_t)g.W * nchs[l], 128), 128, 0, L.s()>>>(in, n_in, stride, off, lens[l], std::min(len_low, lens[l]), g.W,
                                                                                  nchs[l], l == 0 ? nullptr : X[l - 1], l, S[l], X[l]);
     LAUNCHED(ctx);

@@ -566,7 +566,8 @@ static bool simk_msm_run(const uint8_t* k, const uint8_t* pxy, const uint8_t* pi
   std::vector<size_t> lens, nchs;
   size_t len = g.nbw - 1;
   for (;;) {
-    size_t nch = (len + MSM_CH - 1) / MSM_CH;
+    const size_t chl = lens.empty() ? MSM_CH0 : MSM_CHU;  // chunk size of this level (ecg_msm.cuh)
+    size_t nch = (len + chl - 1) / chl;
     lens.push_back(len);
     nchs.push_back(nch);
     if (nch == 1) break;
@@ -623,7 +624,7 @@ static bool simk_msm_run(const uint8_t* k, const uint8_t* pxy, const uint8_t* pi
     size_t stride = l == 0 ? g.nbw : nchs[l - 1];
     size_t off = l == 0 ? 1 : 0;
     size_t len_low = ((size_t)1 << (g.c - 1));
-    for (int q = 0; q < l; q++) len_low = (len_low + MSM_CH - 1) / MSM_CH;
+    for (int q = 0; q < l; q++) len_low = (len_low + (q == 0 ? MSM_CH0 : MSM_CHU) - 1) / (q == 0 ? MSM_CH0 : MSM_CHU);
     len_low = std::min(len_low, lens[l]);
     sim_launch((size_t)g.W * nchs[l], 128, [&] {
       msm_wreduce_kernel<C>(in, n_in, stride, off, lens[l], len_low, g.W, nchs[l], l == 0 ? nullptr : X[l - 1].data(), l, S[l].data(), X[l].data());
