@@ -27,6 +27,7 @@ namespace ecg {
 template <int OPT>
 struct FpP384T {
   static constexpr int NL = 12;
+  static constexpr bool LE = false;  // canonical records are big-endian
   typedef FeN<12> FeT;
   typedef JacN<12> JacT;
   typedef AffN<12> AffT;

@@ -20,9 +20,64 @@ ECG_D void store_be(uint8_t* p, const uint32_t* limbs) {
 #pragma unroll
   for (int i = 0; i < NL; i++) w[i] = bswap32(limbs[NL - 1 - i]);
 }
+// little-endian records (bign-curve256v1: primefield ByteOrder::LittleEndian, bignp256/src/arithmetic/field.rs:65)
+template <int NL>
+ECG_D void load_le(uint32_t* limbs, const uint8_t* p) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+  for (int i = 0; i < NL; i++) limbs[i] = w[i];
+}
+template <int NL>
+ECG_D void store_le(uint8_t* p, const uint32_t* limbs) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(p);
+#pragma unroll
+  for (int i = 0; i < NL; i++) w[i] = limbs[i];
+}
+// one canonical record (field element or scalar) of the curve whose field policy is F, in the byte order the
+// reference uses for that curve
+template <class F>
+ECG_D void load_fe(uint32_t* limbs, const uint8_t* p) {
+  if (F::LE)
+    load_le<F::NL>(limbs, p);
+  else
+    load_be<F::NL>(limbs, p);
+}
+template <class F>
+ECG_D void store_fe(uint8_t* p, const uint32_t* limbs) {
+  if (F::LE)
+    store_le<F::NL>(p, limbs);
+  else
+    store_be<F::NL>(p, limbs);
+}
 ECG_D void load_be32(uint32_t* limbs, const uint8_t* p) { load_be<8>(limbs, p); }
 ECG_D void store_be32(uint8_t* p, const uint32_t* limbs) { store_be<8>(p, limbs); }
 
+// one table entry = x[NL], y[NL] (internal form), read as 128-bit loads (64-bit loads when 2 NL words are not a
+// multiple of four: the 7-limb field of P-224)
+template <int NL>
+ECG_DEV void load_aff_entry(AffN<NL>& e, const uint32_t* __restrict__ table, size_t point) {
+  uint32_t w[2 * NL];
+  if ((2 * NL) % 4 == 0) {
+    const uint4* p = reinterpret_cast<const uint4*>(table + point * (2 * NL));
+#pragma unroll
+    for (int q = 0; q < NL / 2; q++) {
+      uint4 v = __ldg(p + q);
+      w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+    }
+  } else {
+    const uint2* p = reinterpret_cast<const uint2*>(table + point * (2 * NL));
+#pragma unroll
+    for (int q = 0; q < NL; q++) {
+      uint2 v = __ldg(p + q);
+      w[2 * q] = v.x; w[2 * q + 1] = v.y;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    e.x.v[i] = w[i];
+    e.y.v[i] = w[NL + i];
+  }
+}
 // (X:Y:Z) with zinv = 1/Z  ->  canonical affine integers
 template <class F>
 ECG_D void jac_to_affine_canonical(typename F::FeT& x, typename F::FeT& y, const typename F::JacT& p, const typename F::FeT& zinv) {

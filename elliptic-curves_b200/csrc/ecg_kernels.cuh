@@ -53,12 +53,12 @@ ECG_DEV uint32_t load_pair(uint32_t* k, typename C::F::AffT& P, bool& inf, const
   typedef typename F::FeT Fe;
   constexpr int NL = F::NL, FB = 4 * F::NL;  // limbs and bytes per field element / scalar
   uint32_t err = 0;
-  load_be<NL>(k, kb + FB * idx);
+  load_fe<F>(k, kb + FB * idx);
   if (!ltN<NL>(k, C::N())) err |= ERRF_SCALAR;
   inf = pinf != nullptr && pinf[idx] != 0;
   Fe x, y;
-  load_be<NL>(x.v, pxy + 2 * FB * idx);
-  load_be<NL>(y.v, pxy + 2 * FB * idx + FB);
+  load_fe<F>(x.v, pxy + 2 * FB * idx);
+  load_fe<F>(y.v, pxy + 2 * FB * idx + FB);
   if (!inf) {
     bool ok = ltN<NL>(x.v, C::P()) && ltN<NL>(y.v, C::P());
     F::from_canonical(P.x, x);
@@ -159,21 +159,9 @@ ECG_KERNEL(BLOCK, MINBLK)
 #define FB_WINDOWS FB_WINDOWS_NL(8)
 #define FB_TABLE_POINTS FB_TABLE_POINTS_NL(8)
 
-// one table entry = x[NL], y[NL] (internal form), read as 128-bit loads
 template <int NL>
 ECG_DEV void fb_load_entry(AffN<NL>& e, const uint32_t* __restrict__ table, size_t point) {
-  const uint4* p = reinterpret_cast<const uint4*>(table + point * (2 * NL));
-  uint32_t w[2 * NL];
-#pragma unroll
-  for (int q = 0; q < NL / 2; q++) {
-    uint4 v = __ldg(p + q);
-    w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
-  }
-#pragma unroll
-  for (int i = 0; i < NL; i++) {
-    e.x.v[i] = w[i];
-    e.y.v[i] = w[NL + i];
-  }
+  load_aff_entry<NL>(e, table, point);
 }
 
 // acc += k*G (acc Jacobian on the true curve; pass Z = 0 to start from the identity)
@@ -221,7 +209,7 @@ ECG_KERNEL(128, 4)
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   uint32_t k[NL];
-  load_be<NL>(k, kb + 4 * NL * idx);
+  load_fe<F>(k, kb + 4 * NL * idx);
   bool bad = !ltN<NL>(k, C::N());
   if (bad) {
     report_error(status, ERRF_SCALAR, base + idx);
@@ -281,6 +269,7 @@ ECG_KERNEL(BLOCK, MINBLK)
 // valid[i] = 0 — the reference returns Err(Error) per signature, not a batch failure.
 ECG_DEV void store_scalar_be(uint8_t* dst, const uint32_t* limbs) { store_be32(dst, limbs); }
 
+#if !defined(ECG_TU) || ECG_TU == 0  // not templates: defined by the translation unit of the 256-bit curves only
 // BIP340: pk (x only), 32-byte message, signature r || s.
 ECG_KERNEL(128)
     schnorr_prep_kernel(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, const uint8_t* __restrict__ sig, size_t n,
@@ -341,6 +330,8 @@ ECG_KERNEL(256)
   bool y_even = (rxy[64 * idx + 63] & 1u) == 0;
   valid[idx] = (ok[idx] && !rinf[idx] && y_even && same) ? 1 : 0;  // verifying.rs:94
 }
+
+#endif
 
 // ECDSA: z (32-byte hash), signature r || s, public key Q (x || y).  One modular inversion per thread slice
 // (Montgomery's trick over s_i, as in normalize_kernel); scr: 8*n words.
@@ -497,8 +488,8 @@ ECG_KERNEL(256)
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   typename F::FeT x, y;
-  load_be<NL>(x.v, xy + 2 * FB * idx);
-  load_be<NL>(y.v, xy + 2 * FB * idx + FB);
+  load_fe<F>(x.v, xy + 2 * FB * idx);
+  load_fe<F>(y.v, xy + 2 * FB * idx + FB);
   F::from_canonical(x, x);
   F::from_canonical(y, y);
 #pragma unroll
@@ -546,7 +537,7 @@ ECG_KERNEL(128)
     typename F::FeT v;
     soa_load<NL>(v.v, jac, n, idx, NL * c);
     F::to_canonical(v, v);
-    store_be<NL>(xyz + 3 * FB * idx + FB * c, v.v);
+    store_fe<F>(xyz + 3 * FB * idx + FB * c, v.v);
   }
 }
 
@@ -597,7 +588,7 @@ ECG_KERNEL(256)
       F::mul(x, p.X, z2);
       F::to_canonical(x, x);
       if (inf) F::set_zero(x);
-      store_be<NL>(out_xy + FB * idx, x.v);
+      store_fe<F>(out_xy + FB * idx, x.v);
     } else {
       soa_load<NL>(p.Y.v, jac, n, idx, NL);
       jac_to_affine_canonical<F>(x, y, p, zinv);
@@ -605,8 +596,8 @@ ECG_KERNEL(256)
         F::set_zero(x);
         F::set_zero(y);
       }
-      store_be<NL>(out_xy + 2 * FB * idx, x.v);
-      store_be<NL>(out_xy + 2 * FB * idx + FB, y.v);
+      store_fe<F>(out_xy + 2 * FB * idx, x.v);
+      store_fe<F>(out_xy + 2 * FB * idx + FB, y.v);
     }
     out_inf[idx] = inf ? 1 : 0;
     if (idx < T) break;
@@ -631,7 +622,7 @@ ECG_KERNEL(256)
 #pragma unroll 1
   for (int c = 0; c < 3; c++) {
     Fe v;
-    load_be<NL>(v.v, xyz + 3 * FB * idx + FB * c);
+    load_fe<F>(v.v, xyz + 3 * FB * idx + FB * c);
     if (!ltN<NL>(v.v, C::P())) report_error(status, ERRF_POINT, base + idx);
     F::from_canonical(co[c], v);
   }
@@ -681,12 +672,12 @@ ECG_KERNEL(256)
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   typename F::FeT x, y, r;
-  load_be<NL>(x.v, a + FB * idx);
+  load_fe<F>(x.v, a + FB * idx);
   if (!ltN<NL>(x.v, C::P())) report_error(status, ERRF_POINT, base + idx);
   F::from_canonical(x, x);
   bool binary = (op == ECG_FOP_ADD || op == ECG_FOP_SUB || op == ECG_FOP_MUL);
   if (binary) {
-    load_be<NL>(y.v, b + FB * idx);
+    load_fe<F>(y.v, b + FB * idx);
     if (!ltN<NL>(y.v, C::P())) report_error(status, ERRF_POINT, base + idx);
     F::from_canonical(y, y);
   } else {
@@ -701,6 +692,6 @@ ECG_KERNEL(256)
     default: F::inv(r, x); break;
   }
   F::to_canonical(r, r);
-  store_be<NL>(out + FB * idx, r.v);
+  store_fe<F>(out + FB * idx, r.v);
 }
 

@@ -15,6 +15,7 @@
 // reference's whatever order the atomics produce.
 #pragma once
 #include "ecg_curves.cuh"
+#include "ecg_io.cuh"
 #include "ecg_mul.cuh"
 
 namespace ecg {
@@ -76,12 +77,12 @@ ECG_KERNEL(128)
   bool skip = false;
   {
     uint32_t err = 0;
-    load_be<NL>(k, kb + FB * idx);
+    load_fe<F>(k, kb + FB * idx);
     if (!ltN<NL>(k, C::N())) err |= 1u;
     bool inf = pinf != nullptr && pinf[idx] != 0;
     Fe x, y;
-    load_be<NL>(x.v, pxy + 2 * FB * idx);
-    load_be<NL>(y.v, pxy + 2 * FB * idx + FB);
+    load_fe<F>(x.v, pxy + 2 * FB * idx);
+    load_fe<F>(y.v, pxy + 2 * FB * idx + FB);
     F::from_canonical(P.x, x);
     F::from_canonical(P.y, y);
     if (!inf) {
@@ -166,6 +167,7 @@ ECG_KERNEL(128)
 #define MSM_SCAN_BLOCK 256
 #define MSM_SCAN_PER_THREAD 16
 #define MSM_SCAN_CHUNK (MSM_SCAN_BLOCK * MSM_SCAN_PER_THREAD)
+template <int ECG_ONCE = 0>  // a template only so that several translation units may define it
 ECG_KERNEL(MSM_SCAN_BLOCK)
     msm_scan_partial_kernel(const uint32_t* __restrict__ count, size_t m, uint32_t* __restrict__ blocksum, uint32_t* __restrict__ maxcnt) {
   __shared__ uint32_t ssum[MSM_SCAN_BLOCK], smax[MSM_SCAN_BLOCK];
@@ -192,6 +194,7 @@ ECG_KERNEL(MSM_SCAN_BLOCK)
     atomicMax(maxcnt, smax[0]);
   }
 }
+template <int ECG_ONCE = 0>  // a template only so that several translation units may define it
 ECG_KERNEL(1024)
     msm_scan_top_kernel(uint32_t* __restrict__ blocksum, size_t nblocks, uint32_t* __restrict__ offset, size_t m) {
   // nblocks <= a few thousand: serial per-thread chunks + one serial pass over 1024 partials
@@ -219,6 +222,7 @@ ECG_KERNEL(1024)
     run += t;
   }
 }
+template <int ECG_ONCE = 0>  // a template only so that several translation units may define it
 ECG_KERNEL(MSM_SCAN_BLOCK)
     msm_scan_final_kernel(const uint32_t* __restrict__ count, size_t m, const uint32_t* __restrict__ blockoff, uint32_t* __restrict__ offset) {
   __shared__ uint32_t ssum[MSM_SCAN_BLOCK];
@@ -246,6 +250,7 @@ ECG_KERNEL(MSM_SCAN_BLOCK)
     }
 }
 
+template <int ECG_ONCE = 0>  // a template only so that several translation units may define it
 ECG_KERNEL(256)
     msm_scatter_kernel(const int32_t* __restrict__ digits, size_t nsub, MsmGeom g, const uint32_t* __restrict__ offset,
                        uint32_t* __restrict__ cursor, uint32_t* __restrict__ list) {
@@ -263,24 +268,14 @@ ECG_KERNEL(256)
 
 template <int NL>
 ECG_DEV void msm_load_point(AffN<NL>& e, const uint32_t* __restrict__ pts, uint32_t j) {
-  const uint4* p = reinterpret_cast<const uint4*>(pts + (size_t)j * (2 * NL));
-  uint32_t w[2 * NL];
-#pragma unroll
-  for (int q = 0; q < NL / 2; q++) {
-    uint4 v = __ldg(p + q);
-    w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
-  }
-#pragma unroll
-  for (int i = 0; i < NL; i++) {
-    e.x.v[i] = w[i];
-    e.y.v[i] = w[NL + i];
-  }
+  load_aff_entry<NL>(e, pts, (size_t)j);  // ecg_io.cuh: 128-bit (or, for odd NL, 64-bit) read-only loads
 }
 
 // Bucket ids ordered by decreasing population: counting sort over MSM_ORDER_CLASSES size classes (sizes beyond the
 // last class share it).  hist: MSM_ORDER_CLASSES + 1 counters, cleared by the host; class 0 = largest.
 #define MSM_ORDER_CLASSES 1024
 ECG_DEV uint32_t msm_size_class(uint32_t sz) { return (MSM_ORDER_CLASSES - 1) - (sz < MSM_ORDER_CLASSES - 1 ? sz : MSM_ORDER_CLASSES - 1); }
+template <int ECG_ONCE = 0>  // a template only so that several translation units may define it
 ECG_KERNEL(256)
     msm_order_hist_kernel(const uint32_t* __restrict__ offset, size_t nb, uint32_t* __restrict__ hist) {
   __shared__ uint32_t sh[MSM_ORDER_CLASSES];
@@ -294,6 +289,7 @@ ECG_KERNEL(256)
 }
 // exclusive scan of the class counts (one block of MSM_ORDER_CLASSES threads), in place: hist[c] becomes the first
 // position of class c
+template <int ECG_ONCE = 0>  // a template only so that several translation units may define it
 ECG_KERNEL(MSM_ORDER_CLASSES)
     msm_order_scan_kernel(uint32_t* __restrict__ hist) {
   __shared__ uint32_t sh[MSM_ORDER_CLASSES];
@@ -311,6 +307,7 @@ ECG_KERNEL(MSM_ORDER_CLASSES)
 }
 // every block takes a contiguous run of buckets, counts its classes in shared memory, reserves one range per class with
 // a single global atomic, and writes its bucket ids there
+template <int ECG_ONCE = 0>  // a template only so that several translation units may define it
 ECG_KERNEL(256)
     msm_order_scatter_kernel(const uint32_t* __restrict__ offset, size_t nb, uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
   __shared__ uint32_t cnt[MSM_ORDER_CLASSES], basep[MSM_ORDER_CLASSES];

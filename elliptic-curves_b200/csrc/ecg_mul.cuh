@@ -186,7 +186,7 @@ ECG_D void k256_mul_thread(Jac& r, const uint32_t* k, const Aff& P, const TabRef
 // 256-bit scalar: implicit top digit +1, then 64 windows of (4 dbl + 1 add) against a table of the eight
 // odd multiples kept in Jacobian form (the shared-denominator trick of build_table_iso_a0 needs a = 0).
 // Replaces primeorder ProjectivePoint::mul / mul_vartime (primeorder/src/projective.rs:133-144, :532-557).
-template <class F, bool A_IS_MINUS3, int PHASE_SYNC = 0>
+template <class F, int A_IS_MINUS3, int PHASE_SYNC = 0>
 ECG_D void generic_mul_thread(typename F::JacT& r, const uint32_t* k, const typename F::AffT& P, const TabRefJN<F::NL>& tab) {
   typedef typename F::JacT Jac;
   typedef typename F::AffT Aff;

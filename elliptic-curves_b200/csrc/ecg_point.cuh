@@ -39,14 +39,17 @@ ECG_D void jac_csel(JacN<NL>& r, const JacN<NL>& t, uint32_t c) {
   }
 }
 
-// Doubling in "halved" form (Z3 = Y*Z, X3 = X3_std/4, Y3 = Y3_std/8): 3M+4S (a=0; 2M+5S with F::SQR_TRADE_DBL) / 4M+4S (a=-3),
+// The curve coefficient a is a template mode (named A_IS_MINUS3 for its first two values): 0: a = 0, 1: a = -3
+// (EquationAIsMinusThree, primeorder/src/point_arithmetic.rs:212-319), 2: any a, read from F::curve_a
+// (EquationAIsGeneric, primeorder/src/point_arithmetic.rs:54-208: brainpoolP256r1 / P384r1, bign-curve256v1).
+// Doubling in "halved" form (Z3 = Y*Z, X3 = X3_std/4, Y3 = Y3_std/8): 3M+4S (a=0; 2M+5S with F::SQR_TRADE_DBL) / 4M+4S (a=-3) / 4M+6S (general a),
 // 8 cheap linear ops.   L = (3X^2 + a Z^4)/2;  X3 = L^2 - 2XY^2;  Y3 = L(XY^2 - X3) - Y^4.
-template <class F, bool A_IS_MINUS3>
+template <class F, int A_IS_MINUS3>
 ECG_D void jac_dbl_body(typename F::JacT& r, const typename F::JacT& p) {
   typedef typename F::FeT Fe;
   Fe A, L, T, D, t, zz;
   F::sqr(A, p.Y);  // Y^2
-  if (A_IS_MINUS3) {
+  if (A_IS_MINUS3 == 1) {
     Fe u, v;
     F::sqr(zz, p.Z);
     F::sub(u, p.X, zz);
@@ -56,7 +59,7 @@ ECG_D void jac_dbl_body(typename F::JacT& r, const typename F::JacT& p) {
     F::sqr(L, p.X);
   }
   F::sqr(D, A);  // Y^4
-  if (!A_IS_MINUS3 && F::SQR_TRADE_DBL) {
+  if (A_IS_MINUS3 == 0 && F::SQR_TRADE_DBL) {
     // X*Y^2 = ((X + Y^2)^2 - X^2 - Y^4)/2: a squaring (36 products) plus four linear ops instead of a multiplication (64)
     F::add(t, p.X, A);
     F::sqr(T, t);
@@ -67,8 +70,16 @@ ECG_D void jac_dbl_body(typename F::JacT& r, const typename F::JacT& p) {
     F::mul_d(T, p.X, A);  // X*Y^2
   }
   F::mul_small(L, L, 3);
+  if constexpr (A_IS_MINUS3 == 2) {  // general a (the field policy of such a curve carries it): L = (3 X^2 + a Z^4) / 2
+    Fe z4, ca;
+    F::sqr(zz, p.Z);
+    F::sqr(z4, zz);
+    F::curve_a(ca);
+    F::mul_d(z4, z4, ca);
+    F::add(L, L, z4);
+  }
   F::half(L, L);
-  if (A_IS_MINUS3 && F::DBL_3M5S) {  // Y*Z = ((Y+Z)^2 - Y^2 - Z^2)/2 ; zz was computed for L
+  if (A_IS_MINUS3 == 1 && F::DBL_3M5S) {  // Y*Z = ((Y+Z)^2 - Y^2 - Z^2)/2 ; zz was computed for L
     Fe s2;
     F::add(s2, p.Y, p.Z);
     F::sqr(s2, s2);
@@ -91,13 +102,13 @@ ECG_D void jac_dbl_body(typename F::JacT& r, const typename F::JacT& p) {
 #else
 #define ECG_NOINLINE_PT
 #endif
-template <class F, bool A_IS_MINUS3>
+template <class F, int A_IS_MINUS3>
 ECG_NOINLINE_PT typename F::JacT jac_dbl_call(typename F::JacT p) {
   typename F::JacT r;
   jac_dbl_body<typename F::Inline, A_IS_MINUS3>(r, p);
   return r;
 }
-template <class F, bool A_IS_MINUS3>
+template <class F, int A_IS_MINUS3>
 ECG_D void jac_dbl(typename F::JacT& r, const typename F::JacT& p) {
   if (F::DBL_CALL)
     r = jac_dbl_call<F, A_IS_MINUS3>(p);
@@ -106,7 +117,7 @@ ECG_D void jac_dbl(typename F::JacT& r, const typename F::JacT& p) {
 }
 
 // 2*(x,y) for an affine input (Z = 1): saves the Z products.
-template <class F, bool A_IS_MINUS3>
+template <class F, int A_IS_MINUS3>
 ECG_D void aff_dbl(typename F::JacT& r, const typename F::AffT& p) {
   typename F::JacT j;
   j.X = p.x;
@@ -116,7 +127,7 @@ ECG_D void aff_dbl(typename F::JacT& r, const typename F::AffT& p) {
 }
 
 // Slow path of mixed addition: identity accumulator, or H == 0.
-template <class F, bool A_IS_MINUS3>
+template <class F, int A_IS_MINUS3>
 #if defined(__CUDA_ARCH__)
 __device__ __noinline__
 #else
@@ -138,7 +149,7 @@ inline
 }
 
 // r = p + q, q affine and not the identity.  8M+3S (7M+4S with F::SQR_TRADE_MADD).  If zr != nullptr it receives Z3/Z1 (= H).
-template <class F, bool A_IS_MINUS3>
+template <class F, int A_IS_MINUS3>
 ECG_D void jac_madd_body(typename F::JacT& r, const typename F::JacT& p, const typename F::AffT& q, typename F::FeT* zr = nullptr) {
   typedef typename F::FeT Fe;
   Fe zz, u2, s2, H, R, hh, hhh, V, t;
@@ -178,13 +189,13 @@ ECG_D void jac_madd_body(typename F::JacT& r, const typename F::JacT& p, const t
   F::sub(r.Y, t, hhh);
 }
 
-template <class F, bool A_IS_MINUS3>
+template <class F, int A_IS_MINUS3>
 ECG_NOINLINE_PT typename F::JacT jac_madd_call(typename F::JacT p, typename F::AffT q) {
   typename F::JacT r;
   jac_madd_body<typename F::Inline, A_IS_MINUS3>(r, p, q, nullptr);
   return r;
 }
-template <class F, bool A_IS_MINUS3>
+template <class F, int A_IS_MINUS3>
 ECG_D void jac_madd(typename F::JacT& r, const typename F::JacT& p, const typename F::AffT& q, typename F::FeT* zr = nullptr) {
   if (F::MADD_CALL && zr == nullptr)
     r = jac_madd_call<F, A_IS_MINUS3>(p, q);
@@ -193,7 +204,7 @@ ECG_D void jac_madd(typename F::JacT& r, const typename F::JacT& p, const typena
 }
 
 // r = p + q, both Jacobian.  12M+4S.
-template <class F, bool A_IS_MINUS3>
+template <class F, int A_IS_MINUS3>
 ECG_D void jac_add(typename F::JacT& r, const typename F::JacT& p, const typename F::JacT& q) {
   typedef typename F::FeT Fe;
   bool z1zero = F::is_zero(p.Z), z2zero = F::is_zero(q.Z);
@@ -242,16 +253,21 @@ ECG_D void jac_add(typename F::JacT& r, const typename F::JacT& p, const typenam
 }
 
 // y^2 == x^3 + a x + b ?   (AffinePoint::from_coordinates on-curve check, k256/src/arithmetic/affine.rs:134-147)
-template <class F, bool A_IS_MINUS3>
+template <class F, int A_IS_MINUS3>
 ECG_D bool aff_on_curve(const typename F::AffT& p, const typename F::FeT& b_internal) {
   typedef typename F::FeT Fe;
   Fe l, r, t;
   F::sqr(l, p.y);
   F::sqr(r, p.x);
   F::mul(r, r, p.x);
-  if (A_IS_MINUS3) {
+  if (A_IS_MINUS3 == 1) {
     F::mul_small(t, p.x, 3);
     F::sub(r, r, t);
+  } else if constexpr (A_IS_MINUS3 == 2) {
+    Fe ca;
+    F::curve_a(ca);
+    F::mul(t, p.x, ca);
+    F::add(r, r, t);
   }
   F::add(r, r, b_internal);
   F::sub(l, l, r);

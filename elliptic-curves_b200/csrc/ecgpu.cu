@@ -11,10 +11,33 @@
 #include <string>
 #include <vector>
 
+// This file is compiled once per curve group (-DECG_TU=0..3) so that the groups build in parallel and the kernels of
+// the headline curves keep their own translation unit:
+//   ECG_TU 0: secp256k1, P-256, P-384 + every extern "C" entry (entries for other curves forward to their group)
+//   ECG_TU 1: sm2, brainpoolP256r1/t1, bign-curve256v1 (8 limbs)   ECG_TU 2: brainpoolP384r1/t1 (12 limbs)
+//   ECG_TU 3: P-224 (7 limbs), P-192 (6 limbs)
+// The groups 1-3 run the generic kernels over the generic Montgomery field policy (ecg_fe_mont.cuh).
+#ifndef ECG_TU
+#define ECG_TU 0
+#endif
+
 #include "../../include/ecgpu.h"
 #include "ecg_kernels.cuh"
+#if ECG_TU == 0
 #include "ecg_microbench.cuh"
+#endif
 #include "ecg_msm.cuh"
+
+#define ECG_CURVE_COUNT 11
+static inline int curve_group(int c) { return c <= 2 ? 0 : c <= 6 ? 1 : c <= 8 ? 2 : 3; }
+// an entry point: extern "C" in group 0, an internal (hidden) function ecg_tuN_<name> in the other groups
+#define ECG_CAT2(a, b) a##b
+#define ECG_CAT(a, b) ECG_CAT2(a, b)
+#if ECG_TU == 0
+#define ECG_API(name) extern "C" ecg_status name
+#else
+#define ECG_API(name) __attribute__((visibility("hidden"))) ecg_status ECG_CAT(ECG_CAT(ECG_CAT(ecg_tu, ECG_TU), _), name)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -44,7 +67,7 @@ struct Lane {
 struct DevState {
   int dev = 0;
   Lane lane[2];
-  uint32_t* fb_table[3] = {nullptr, nullptr, nullptr};  // per curve, built lazily (like the reference's LazyLock table)
+  uint32_t* fb_table[ECG_CURVE_COUNT] = {nullptr};  // per curve, built lazily (like the reference's LazyLock table)
   int sm_count = 148;
 };
 
@@ -111,6 +134,7 @@ static ecg_status ensure(ecg_ctx* ctx, Lane& L, int which, size_t bytes) {
   return ECG_OK;
 }
 
+#if ECG_TU == 0
 extern "C" const char* ecg_version(void) { return "ecgpu 0.3 (sm_100a)"; }
 
 extern "C" ecg_status ecg_ctx_create(const int* device_ids, int n_devices, unsigned flags, ecg_ctx** out) {
@@ -165,7 +189,7 @@ extern "C" void ecg_ctx_destroy(ecg_ctx* ctx) {
       if (L.h_status) cudaFreeHost(L.h_status);
       for (cudaEvent_t e : L.evs) cudaEventDestroy(e);
     }
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < ECG_CURVE_COUNT; i++)
       if (d.fb_table[i]) cudaFree(d.fb_table[i]);
   }
   delete ctx;
@@ -196,6 +220,8 @@ extern "C" ecg_status ecg_ctx_set_stream(ecg_ctx* ctx, void* cuda_stream) {
   L.use_user_stream = cuda_stream != nullptr;
   return ECG_OK;
 }
+
+#endif  // ECG_TU == 0
 
 // Shard [0,n) into contiguous per-device ranges.
 struct Shard {
@@ -346,8 +372,15 @@ static ecg_status fail(ecg_ctx* ctx, ecg_status rc) {
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
 // bytes per field element / scalar at the ABI (32; 48 for P-384) and 32-bit limbs per field element
-static inline size_t fbytes(ecg_curve c) { return c == ECG_NISTP384 ? 48 : 32; }
-static inline size_t flimbs(ecg_curve c) { return c == ECG_NISTP384 ? 12 : 8; }
+static inline size_t flimbs(ecg_curve c) {
+  switch ((int)c) {
+    case ECG_NISTP384: case ECG_BP384R1: case ECG_BP384T1: return 12;
+    case ECG_NISTP224: return 7;
+    case ECG_NISTP192: return 6;
+    default: return 8;
+  }
+}
+static inline size_t fbytes(ecg_curve c) { return 4 * flimbs(c); }
 // ECG_INLINE_LOOPS=0 (environment) keeps the call-based field operations in the one-point-operation-per-iteration
 // kernels (fixed-base, bucket accumulation): measurement knob, default = inlined
 static bool inline_loops() {
@@ -357,7 +390,9 @@ static bool inline_loops() {
   }();
   return v;
 }
-// same as FOR_CURVE below with CV bound to the all-inlined variant of the curve (ecg_curves.cuh)
+// FOR_CURVE(curve, statement): run the statement with CV bound to the curve's parameter struct; FOR_CURVE_INL: to the
+// all-inlined variant of the curve (ecg_curves.cuh) where one exists.  Each translation unit knows its own group.
+#if ECG_TU == 0
 #define FOR_CURVE_INL(curve, ...)         \
   do {                                    \
     if ((curve) == ECG_SECP256K1) {       \
@@ -371,7 +406,6 @@ static bool inline_loops() {
       __VA_ARGS__;                        \
     }                                     \
   } while (0)
-// run a statement with CV bound to the curve's parameter struct (CurveK256 / CurveP256 / CurveP384)
 #define FOR_CURVE(curve, ...)             \
   do {                                    \
     if ((curve) == ECG_SECP256K1) {       \
@@ -385,6 +419,49 @@ static bool inline_loops() {
       __VA_ARGS__;                        \
     }                                     \
   } while (0)
+#elif ECG_TU == 1
+#define FOR_CURVE(curve, ...)             \
+  do {                                    \
+    if ((curve) == ECG_SM2) {             \
+      typedef CurveSm2 CV;                \
+      __VA_ARGS__;                        \
+    } else if ((curve) == ECG_BP256R1) {  \
+      typedef CurveBp256r1 CV;            \
+      __VA_ARGS__;                        \
+    } else if ((curve) == ECG_BP256T1) {  \
+      typedef CurveBp256t1 CV;            \
+      __VA_ARGS__;                        \
+    } else {                              \
+      typedef CurveBignP256 CV;           \
+      __VA_ARGS__;                        \
+    }                                     \
+  } while (0)
+#define FOR_CURVE_INL FOR_CURVE
+#elif ECG_TU == 2
+#define FOR_CURVE(curve, ...)             \
+  do {                                    \
+    if ((curve) == ECG_BP384R1) {         \
+      typedef CurveBp384r1 CV;            \
+      __VA_ARGS__;                        \
+    } else {                              \
+      typedef CurveBp384t1 CV;            \
+      __VA_ARGS__;                        \
+    }                                     \
+  } while (0)
+#define FOR_CURVE_INL FOR_CURVE
+#else
+#define FOR_CURVE(curve, ...)             \
+  do {                                    \
+    if ((curve) == ECG_NISTP224) {        \
+      typedef CurveP224 CV;               \
+      __VA_ARGS__;                        \
+    } else {                              \
+      typedef CurveP192 CV;               \
+      __VA_ARGS__;                        \
+    }                                     \
+  } while (0)
+#define FOR_CURVE_INL FOR_CURVE
+#endif
 
 template <class F>
 static ecg_status launch_normalize(ecg_ctx* ctx, DevState& d, Lane& L, size_t n, const uint32_t* jac, uint8_t* out, uint8_t* oinf,
@@ -413,14 +490,24 @@ static const int P_BLOCK = 128, P_MINBLK = 5;  // P-256   : <= 96 registers -> 2
 static const int Q_BLOCK = 128, Q_MINBLK = 3;  // P-384   : 12-limb values, <= 168 registers -> 12 warps/SM
 #define Q_TAB_WORDS (8 * 36) /* 8 Jacobian entries x 36 words */
 
-static size_t wave_elems(const DevState& d, ecg_curve curve) {
-  return (size_t)d.sm_count * (curve == ECG_SECP256K1 ? K_MINBLK * K_BLOCK : curve == ECG_NISTP256 ? P_MINBLK * P_BLOCK : Q_MINBLK * Q_BLOCK);
+// the curves on the generic Montgomery field (groups 1-3): call-based field operations, 8 Jacobian table entries
+static const int X_BLOCK = 128;
+template <int NL>
+struct XGeom {
+  static constexpr int MINBLK = NL > 8 ? 3 : 4;
+};
+static size_t vb_block(ecg_curve c) { return c == ECG_SECP256K1 ? K_BLOCK : c == ECG_NISTP256 ? P_BLOCK : c == ECG_NISTP384 ? Q_BLOCK : X_BLOCK; }
+static size_t vb_minblk(ecg_curve c) {
+  return c == ECG_SECP256K1 ? K_MINBLK : c == ECG_NISTP256 ? P_MINBLK : c == ECG_NISTP384 ? Q_MINBLK : (flimbs(c) > 8 ? 3 : 4);
 }
+static size_t vb_tab_words(ecg_curve c) { return c == ECG_SECP256K1 ? K_TAB_WORDS : 8 * 3 * flimbs(c); }
+
+static size_t wave_elems(const DevState& d, ecg_curve curve) { return (size_t)d.sm_count * vb_minblk(curve) * vb_block(curve); }
 
 // per-block window-table slots for a launch of n elements
 static ecg_status ensure_tab(ecg_ctx* ctx, Lane& L, ecg_curve curve, size_t n) {
-  size_t block = curve == ECG_SECP256K1 ? K_BLOCK : curve == ECG_NISTP256 ? P_BLOCK : Q_BLOCK;
-  size_t words = curve == ECG_SECP256K1 ? K_TAB_WORDS : curve == ECG_NISTP256 ? P_TAB_WORDS : Q_TAB_WORDS;
+  size_t block = vb_block(curve);
+  size_t words = vb_tab_words(curve);
   size_t blocks = (n + block - 1) / block;
   return ensure(ctx, L, B_TAB, blocks * block * words * 4);
 }
@@ -432,12 +519,17 @@ static ecg_status launch_varbase(ecg_ctx* ctx, DevState& d, Lane& L, ecg_curve c
   ST_TRY(ensure_tab(ctx, L, curve, n));
   uint32_t* gtab = (uint32_t*)L.buf[B_TAB];
   DOM_BEGIN(ctx, L);
+#if ECG_TU == 0
   if (curve == ECG_SECP256K1)
     k256_varbase_kernel<K_BLOCK, K_MINBLK><<<grid_for(n, K_BLOCK), K_BLOCK, 0, L.s()>>>(dp.k, dp.p, dp.inf, n, jac, gtab, status, base);
   else if (curve == ECG_NISTP256)
     generic_varbase_kernel<CurveP256, P_BLOCK, P_MINBLK><<<grid_for(n, P_BLOCK), P_BLOCK, 0, L.s()>>>(dp.k, dp.p, dp.inf, n, jac, gtab, status, base);
   else
     generic_varbase_kernel<CurveP384, Q_BLOCK, Q_MINBLK><<<grid_for(n, Q_BLOCK), Q_BLOCK, 0, L.s()>>>(dp.k, dp.p, dp.inf, n, jac, gtab, status, base);
+#else
+  FOR_CURVE(curve, (generic_varbase_kernel<CV, X_BLOCK, XGeom<CV::F::NL>::MINBLK><<<grid_for(n, X_BLOCK), X_BLOCK, 0, L.s()>>>(dp.k, dp.p, dp.inf, n, jac, gtab,
+                                                                                                                        status, base)));
+#endif
   LAUNCHED(ctx);
   DOM_END(ctx, L);
   return ECG_OK;
@@ -445,29 +537,29 @@ static ecg_status launch_varbase(ecg_ctx* ctx, DevState& d, Lane& L, ecg_curve c
 
 // every curve the hot path serves; curve_256() = the two 256-bit curves the widening entries (verification, SEC1
 // decompression, a*G + b*P, field sqrt) are written for
-static bool curve_ok(ecg_curve c) { return c == ECG_SECP256K1 || c == ECG_NISTP256 || c == ECG_NISTP384; }
+static bool curve_ok(ecg_curve c) { return (int)c >= 0 && (int)c < ECG_CURVE_COUNT && curve_group((int)c) == ECG_TU; }
 static bool curve_256(ecg_curve c) { return c == ECG_SECP256K1 || c == ECG_NISTP256; }
 
 // ---- fixed-base table ------------------------------------------------------------------------------
 // Built on the device with the variable-base kernel itself: entry (i, j) = ((2j+1) << 16 i mod n) * G.
-static void scalar_be_from_shifted(uint8_t* out, uint64_t odd, int shift_bits, const uint32_t* n_le, int nl) {
-  // v = odd << shift_bits  (< 2^(32 nl + 1)), reduced once by n (v < 2n always holds: n > 2^(32 nl - 1) for these curves)
-  uint32_t v[14] = {0};
+// record (curve byte order) of (odd << shift_bits) mod n; the value is below 2^(32 nl + 1) and n above 2^(32 nl - 1)
+static void scalar_rec_from_shifted(uint8_t* out, uint64_t odd, int shift_bits, const uint32_t* n_le, int nl, bool le) {
+  uint32_t v[15] = {0};
   int w = shift_bits / 32, b = shift_bits % 32;
   uint64_t lo = odd << b;  // odd < 2^17, b < 32
   v[w] = (uint32_t)lo;
-  if (w + 1 < 14) v[w + 1] = (uint32_t)(lo >> 32);
-  uint32_t nn[13];
+  v[w + 1] = (uint32_t)(lo >> 32);
+  uint32_t nn[14] = {0};
   for (int i = 0; i < nl; i++) nn[i] = n_le[i];
-  nn[nl] = 0;
-  bool ge = true;
-  for (int i = nl; i >= 0; i--) {
-    if (v[i] != nn[i]) {
-      ge = v[i] > nn[i];
-      break;
+  for (;;) {
+    bool ge = true;
+    for (int i = nl; i >= 0; i--) {
+      if (v[i] != nn[i]) {
+        ge = v[i] > nn[i];
+        break;
+      }
     }
-  }
-  if (ge) {
+    if (!ge) break;
     uint64_t borrow = 0;
     for (int i = 0; i <= nl; i++) {
       uint64_t t = (uint64_t)v[i] - nn[i] - borrow;
@@ -476,12 +568,14 @@ static void scalar_be_from_shifted(uint8_t* out, uint64_t odd, int shift_bits, c
     }
   }
   const int nb = 4 * nl;
-  for (int i = 0; i < nl; i++) {
-    out[nb - 1 - 4 * i] = (uint8_t)v[i];
-    out[nb - 2 - 4 * i] = (uint8_t)(v[i] >> 8);
-    out[nb - 3 - 4 * i] = (uint8_t)(v[i] >> 16);
-    out[nb - 4 - 4 * i] = (uint8_t)(v[i] >> 24);
-  }
+  for (int i = 0; i < nl; i++)
+    for (int j = 0; j < 4; j++) {
+      uint8_t byte = (uint8_t)(v[i] >> (8 * j));
+      if (le)
+        out[4 * i + j] = byte;
+      else
+        out[nb - 1 - 4 * i - j] = byte;
+    }
 }
 static const uint32_t H_K256_N[8] = {0xD0364141u, 0xBFD25E8Cu, 0xAF48A03Bu, 0xBAAEDCE6u, 0xFFFFFFFEu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
 static const uint32_t H_P256_N[8] = {0xFC632551u, 0xF3B9CAC2u, 0xA7179E84u, 0xBCE6FAADu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x00000000u, 0xFFFFFFFFu};
@@ -515,9 +609,16 @@ static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
   std::vector<uint8_t> hk(np * fb), hp(FB_PIECE * 2 * fb);
   const uint32_t* n_le = curve == ECG_SECP256K1 ? H_K256_N : curve == ECG_NISTP256 ? H_P256_N : H_P384_N;
   const uint8_t* g = curve == ECG_SECP256K1 ? H_K256_G : curve == ECG_NISTP256 ? H_P256_G : H_P384_G;
+  bool le = false;
+  for (int e = 0; e < ECG_EXT_CURVE_COUNT; e++)
+    if (ECG_EXT_CURVES[e].id == (int)curve) {
+      n_le = ECG_EXT_CURVES[e].n;
+      g = ECG_EXT_CURVES[e].g;
+      le = ECG_EXT_CURVES[e].le != 0;
+    }
   for (int i = 0; i < nwin; i++)
-    for (uint32_t j = 0; j < FB_ENTRIES; j++) scalar_be_from_shifted(&hk[((size_t)i * FB_ENTRIES + j) * fb], 2ull * j + 1, FB_W * i, n_le, nl);
-  scalar_be_from_shifted(&hk[(np - 1) * fb], 1, 32 * nl, n_le, nl);  // 2^(32 nl) mod n
+    for (uint32_t j = 0; j < FB_ENTRIES; j++) scalar_rec_from_shifted(&hk[((size_t)i * FB_ENTRIES + j) * fb], 2ull * j + 1, FB_W * i, n_le, nl, le);
+  scalar_rec_from_shifted(&hk[(np - 1) * fb], 1, 32 * nl, n_le, nl, le);  // 2^(32 nl) mod n
   for (size_t i = 0; i < FB_PIECE; i++) memcpy(&hp[i * 2 * fb], g, 2 * fb);
   // temporaries are released on every exit path; `table` is released unless it is handed to the DevState
   struct Scratch {
@@ -597,6 +698,7 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
   const uint8_t* dx = nullptr;
   ST_TRY(stage_in(ctx, L, B_X, op.x, off, cnt, 64, &dx));
   ST_TRY(stage_out(ctx, L, off, cnt, op.out, op.ostride, op.oinf, dp));
+#if ECG_TU == 0
   if (op.kind == BatchOp::DECOMPRESS) {
     // out = xy (64 B), oinf = identity flags, valid flags go to a third host array staged through B_V4
     ST_TRY(ensure(ctx, L, B_V4, cnt));
@@ -661,12 +763,14 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
     LAUNCHED(ctx);
     return copy_back(ctx, L, off, cnt, op.out, op.ostride, nullptr, dp);
   }
+#else
+  (void)dx;
+#endif
   uint32_t* jac = nullptr;
   if (op.kind != BatchOp::FIELD) {
     ST_TRY(ensure(ctx, L, B_JAC, cnt * 3 * fbytes(op.curve)));
     jac = (uint32_t*)L.buf[B_JAC];
   }
-  const bool k1 = op.curve == ECG_SECP256K1;
   switch (op.kind) {
     case BatchOp::MUL:
       ST_TRY(launch_varbase(ctx, d, L, op.curve, cnt, dp, jac, L.status, off));
@@ -681,9 +785,10 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
       DOM_END(ctx, L);
       break;
     case BatchOp::MULGENADD:
+#if ECG_TU == 0
       ST_TRY(ensure_tab(ctx, L, op.curve, cnt));
       DOM_BEGIN(ctx, L);
-      if (k1)
+      if (op.curve == ECG_SECP256K1)
         mul_gen_add_kernel<CurveK256, KG_BLOCK, KG_MINBLK, true><<<grid_for(cnt, KG_BLOCK), KG_BLOCK, 0, L.s()>>>(
             dp.a, dp.k, dp.p, dp.inf, cnt, d.fb_table[op.curve], jac, (uint32_t*)L.buf[B_TAB], L.status, off);
       else
@@ -691,6 +796,7 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
             dp.a, dp.k, dp.p, dp.inf, cnt, d.fb_table[op.curve], jac, (uint32_t*)L.buf[B_TAB], L.status, off);
       LAUNCHED(ctx);
       DOM_END(ctx, L);
+#endif
       break;
     case BatchOp::NORMALIZE:
       if (op.fop)
@@ -782,9 +888,55 @@ static ecg_status run_batch(ecg_ctx* ctx, const BatchOp& op, size_t n) {
   return st == ECG_OK ? st : fail(ctx, st);
 }
 
-extern "C" ecg_status ecg_mul_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
+// ---- entry points -------------------------------------------------------------------------------------
+// group 0 owns the extern "C" symbols and hands calls for the other groups' curves to their translation units
+#if ECG_TU == 0
+__attribute__((visibility("hidden"))) ecg_status ecg_tu1_ecg_mul_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu1_ecg_mul_gen_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu1_ecg_batch_normalize(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu1_ecg_batch_normalize_hom(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu1_ecg_mul_batch_x(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_x, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu1_ecg_field_op_batch(ecg_ctx* ctx, ecg_curve curve, int fop, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu1_ecg_lincomb_partial(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xyz);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu1_ecg_point_sum(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* xyz, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu1_ecg_lincomb(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu2_ecg_mul_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu2_ecg_mul_gen_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu2_ecg_batch_normalize(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu2_ecg_batch_normalize_hom(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu2_ecg_mul_batch_x(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_x, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu2_ecg_field_op_batch(ecg_ctx* ctx, ecg_curve curve, int fop, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu2_ecg_lincomb_partial(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xyz);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu2_ecg_point_sum(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* xyz, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu2_ecg_lincomb(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_mul_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_mul_gen_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_batch_normalize(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_batch_normalize_hom(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_mul_batch_x(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_x, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_field_op_batch(ecg_ctx* ctx, ecg_curve curve, int fop, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_lincomb_partial(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xyz);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_point_sum(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* xyz, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_lincomb(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
+#define ECG_FORWARD(name, ...)                                     \
+  do {                                                             \
+    if ((int)curve >= 0 && (int)curve < ECG_CURVE_COUNT) {         \
+      switch (curve_group((int)curve)) {                           \
+        case 1: return ecg_tu1_##name(__VA_ARGS__);                \
+        case 2: return ecg_tu2_##name(__VA_ARGS__);                \
+        case 3: return ecg_tu3_##name(__VA_ARGS__);                \
+        default: break;                                            \
+      }                                                            \
+    }                                                              \
+  } while (0)
+#else
+#define ECG_FORWARD(name, ...) ((void)0)
+#endif
+
+ECG_API(ecg_mul_batch)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
                                     const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf) {
   if (!ctx) return ECG_EINVAL;
+  ECG_FORWARD(ecg_mul_batch, ctx, curve, n, k, P_xy, P_inf, out_xy, out_inf);
   if (n == 0) return ECG_OK;
   if (!k || !P_xy || !out_xy || !curve_ok(curve)) {
     ctx->err = "ecg_mul_batch: null pointer or unknown curve";
@@ -803,9 +955,10 @@ extern "C" ecg_status ecg_mul_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, con
   return run_batch(ctx, op, n);
 }
 
-extern "C" ecg_status ecg_mul_gen_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, uint8_t* out_xy,
+ECG_API(ecg_mul_gen_batch)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, uint8_t* out_xy,
                                         uint8_t* out_inf) {
   if (!ctx) return ECG_EINVAL;
+  ECG_FORWARD(ecg_mul_gen_batch, ctx, curve, n, k, out_xy, out_inf);
   if (n == 0) return ECG_OK;
   if (!k || !out_xy || !curve_ok(curve)) {
     ctx->err = "ecg_mul_gen_batch: null pointer or unknown curve";
@@ -822,6 +975,7 @@ extern "C" ecg_status ecg_mul_gen_batch(ecg_ctx* ctx, ecg_curve curve, size_t n,
   return run_batch(ctx, op, n);
 }
 
+#if ECG_TU == 0
 extern "C" ecg_status ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, const uint8_t* b,
                                             const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf) {
   if (!ctx) return ECG_EINVAL;
@@ -900,9 +1054,12 @@ extern "C" ecg_status ecg_ecdsa_verify_batch(ecg_ctx* ctx, ecg_curve curve, size
   return run_batch(ctx, op, n);
 }
 
-extern "C" ecg_status ecg_batch_normalize(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz, uint8_t* out_xy,
+#endif  // ECG_TU == 0
+
+ECG_API(ecg_batch_normalize)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz, uint8_t* out_xy,
                                           uint8_t* out_inf) {
   if (!ctx) return ECG_EINVAL;
+  ECG_FORWARD(ecg_batch_normalize, ctx, curve, n, xyz, out_xy, out_inf);
   if (n == 0) return ECG_OK;
   if (!xyz || !out_xy || !curve_ok(curve)) return ECG_EINVAL;
   BatchOp op;
@@ -916,9 +1073,10 @@ extern "C" ecg_status ecg_batch_normalize(ecg_ctx* ctx, ecg_curve curve, size_t 
   return run_batch(ctx, op, n);
 }
 
-extern "C" ecg_status ecg_batch_normalize_hom(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz, uint8_t* out_xy,
+ECG_API(ecg_batch_normalize_hom)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz, uint8_t* out_xy,
                                               uint8_t* out_inf) {
   if (!ctx) return ECG_EINVAL;
+  ECG_FORWARD(ecg_batch_normalize_hom, ctx, curve, n, xyz, out_xy, out_inf);
   if (n == 0) return ECG_OK;
   if (!xyz || !out_xy || !curve_ok(curve)) return ECG_EINVAL;
   BatchOp op;
@@ -933,9 +1091,10 @@ extern "C" ecg_status ecg_batch_normalize_hom(ecg_ctx* ctx, ecg_curve curve, siz
   return run_batch(ctx, op, n);
 }
 
-extern "C" ecg_status ecg_mul_batch_x(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
+ECG_API(ecg_mul_batch_x)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
                                       const uint8_t* P_inf, uint8_t* out_x, uint8_t* out_inf) {
   if (!ctx) return ECG_EINVAL;
+  ECG_FORWARD(ecg_mul_batch_x, ctx, curve, n, k, P_xy, P_inf, out_x, out_inf);
   if (n == 0) return ECG_OK;
   if (!k || !P_xy || !out_x || !curve_ok(curve)) {
     ctx->err = "ecg_mul_batch_x: null pointer or unknown curve";
@@ -956,6 +1115,7 @@ extern "C" ecg_status ecg_mul_batch_x(ecg_ctx* ctx, ecg_curve curve, size_t n, c
   return run_batch(ctx, op, n);
 }
 
+#if ECG_TU == 0
 extern "C" ecg_status ecg_field_sqrt_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, uint8_t* out,
                                            uint8_t* is_square) {
   if (!ctx) return ECG_EINVAL;
@@ -971,9 +1131,12 @@ extern "C" ecg_status ecg_field_sqrt_batch(ecg_ctx* ctx, ecg_curve curve, size_t
   return run_batch(ctx, op, n);
 }
 
-extern "C" ecg_status ecg_field_op_batch(ecg_ctx* ctx, ecg_curve curve, int fop, size_t n, const uint8_t* a, const uint8_t* b,
+#endif  // ECG_TU == 0
+
+ECG_API(ecg_field_op_batch)(ecg_ctx* ctx, ecg_curve curve, int fop, size_t n, const uint8_t* a, const uint8_t* b,
                                          uint8_t* out) {
   if (!ctx) return ECG_EINVAL;
+  ECG_FORWARD(ecg_field_op_batch, ctx, curve, fop, n, a, b, out);
   if (n == 0) return ECG_OK;
   bool binary = (fop == ECG_FOP_ADD || fop == ECG_FOP_SUB || fop == ECG_FOP_MUL);
   if (!a || !out || (binary && !b) || fop < 0 || fop > ECG_FOP_INV || !curve_ok(curve)) return ECG_EINVAL;
@@ -1104,11 +1267,11 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
   LAUNCHED(ctx);
   {
     unsigned sb = (unsigned)((nb + MSM_SCAN_CHUNK - 1) / MSM_SCAN_CHUNK);
-    msm_scan_partial_kernel<<<sb, MSM_SCAN_BLOCK, 0, L.s()>>>(count, nb, blocksum, maxcnt);
+    msm_scan_partial_kernel<0><<<sb, MSM_SCAN_BLOCK, 0, L.s()>>>(count, nb, blocksum, maxcnt);
     LAUNCHED(ctx);
-    msm_scan_top_kernel<<<1, 1024, 0, L.s()>>>(blocksum, sb, offset, nb);
+    msm_scan_top_kernel<0><<<1, 1024, 0, L.s()>>>(blocksum, sb, offset, nb);
     LAUNCHED(ctx);
-    msm_scan_final_kernel<<<sb, MSM_SCAN_BLOCK, 0, L.s()>>>(count, nb, blocksum, offset);
+    msm_scan_final_kernel<0><<<sb, MSM_SCAN_BLOCK, 0, L.s()>>>(count, nb, blocksum, offset);
     LAUNCHED(ctx);
   }
   // one bucket thread adds its points serially: pathologically skewed inputs (e.g. thousands of identical terms) are
@@ -1116,7 +1279,7 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
   // and the caller repeats the call on the per-term path, whose cost does not depend on the data
   const size_t avg = nsub / ((size_t)1 << (g.c - 1)) + 1;
   MsmSkew sk{maxcnt, 4096u, (uint32_t)std::min<size_t>(32 * avg, 0xFFFFFFFFu), L.status};
-  msm_scatter_kernel<<<grid_for(nsub, 256), 256, 0, L.s()>>>(digits, nsub, g, offset, cursor, list);
+  msm_scatter_kernel<0><<<grid_for(nsub, 256), 256, 0, L.s()>>>(digits, nsub, g, offset, cursor, list);
   LAUNCHED(ctx);
   // bucket ids by decreasing population (ECG_MSM_ORDER=0 keeps the natural order: measurement knob)
   static const bool use_order = []() {
@@ -1126,21 +1289,23 @@ static ecg_status msm_run(ecg_ctx* ctx, Lane& L, const DevPtrs& dp, size_t n, si
   if (use_order) {
     CU_TRY(ctx, cudaMemsetAsync(ohist, 0, (MSM_ORDER_CLASSES + 1) * 4, L.s()));
     unsigned ob = (unsigned)std::min<size_t>((nb + 255) / 256, 592);
-    msm_order_hist_kernel<<<ob, 256, 0, L.s()>>>(offset, nb, ohist);
+    msm_order_hist_kernel<0><<<ob, 256, 0, L.s()>>>(offset, nb, ohist);
     LAUNCHED(ctx);
-    msm_order_scan_kernel<<<1, MSM_ORDER_CLASSES, 0, L.s()>>>(ohist);
+    msm_order_scan_kernel<0><<<1, MSM_ORDER_CLASSES, 0, L.s()>>>(ohist);
     LAUNCHED(ctx);
-    msm_order_scatter_kernel<<<ob, 256, 0, L.s()>>>(offset, nb, ohist, order);
+    msm_order_scatter_kernel<0><<<ob, 256, 0, L.s()>>>(offset, nb, ohist, order);
     LAUNCHED(ctx);
   }
   DOM_BEGIN(ctx, L);
   switch (msm_buckets_per_thread()) {  // > 1: warp-balanced variant (ecg_msm.cuh), off unless the environment asks for it
+#if ECG_TU == 0
     case 8:
       msm_bucket_sorted_kernel<C, 8><<<grid_for(nb, MSM_BS_BLOCK * 8), MSM_BS_BLOCK, 0, L.s()>>>(pts, list, offset, nb, bkt, sk);
       break;
     case 4:
       msm_bucket_sorted_kernel<C, 4><<<grid_for(nb, MSM_BS_BLOCK * 4), MSM_BS_BLOCK, 0, L.s()>>>(pts, list, offset, nb, bkt, sk);
       break;
+#endif
     default:
       if (inline_loops())
         msm_bucket_kernel<CI><<<grid_for(nb, 128), 128, 0, L.s()>>>(pts, list, offset, nb, bkt, sk, use_order ? order : nullptr);
@@ -1193,12 +1358,16 @@ static ecg_status lincomb_shard(ecg_ctx* ctx, DevState& d, ecg_curve curve, cons
       q.inf = dp.inf ? dp.inf + lo : nullptr;
       MsmGeom g = msm_geometry(curve, cnt);
       uint32_t* r1 = nullptr;
+#if ECG_TU == 0
       if (curve == ECG_SECP256K1)
         ST_TRY((msm_run<CurveK256, CurveK256I, true>(ctx, L, q, cnt, sh.off + lo, g, &r1)));
       else if (curve == ECG_NISTP256)
         ST_TRY((msm_run<CurveP256, CurveP256I, false>(ctx, L, q, cnt, sh.off + lo, g, &r1)));
       else
         ST_TRY((msm_run<CurveP384, CurveP384I, false>(ctx, L, q, cnt, sh.off + lo, g, &r1)));
+#else
+      FOR_CURVE(curve, ST_TRY((msm_run<CV, CV, false>(ctx, L, q, cnt, sh.off + lo, g, &r1))));
+#endif
       if (pieces == 1) {
         *result = r1;
         return ECG_OK;
@@ -1262,9 +1431,10 @@ static ecg_status lincomb_partial_attempt(ecg_ctx* ctx, ecg_curve curve, size_t 
   return ECG_OK;
 }
 
-extern "C" ecg_status ecg_lincomb_partial(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
+ECG_API(ecg_lincomb_partial)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
                                           const uint8_t* P_inf, uint8_t* out_xyz) {
   if (!ctx) return ECG_EINVAL;
+  ECG_FORWARD(ecg_lincomb_partial, ctx, curve, n, k, P_xy, P_inf, out_xyz);
   if (!out_xyz || !curve_ok(curve) || (n > 0 && (!k || !P_xy))) {
     ctx->err = "ecg_lincomb_partial: null pointer or unknown curve";
     return ECG_EINVAL;
@@ -1325,9 +1495,10 @@ static ecg_status point_sum_enqueue(ecg_ctx* ctx, ecg_curve curve, size_t m, con
   return copy_back(ctx, L, 0, 1, out_xy, 2 * fb, out_inf, dp);
 }
 
-extern "C" ecg_status ecg_point_sum(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* xyz, uint8_t* out_xy,
+ECG_API(ecg_point_sum)(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* xyz, uint8_t* out_xy,
                                     uint8_t* out_inf) {
   if (!ctx) return ECG_EINVAL;
+  ECG_FORWARD(ecg_point_sum, ctx, curve, m, xyz, out_xy, out_inf);
   if (!out_xy || !out_inf || !curve_ok(curve) || (m > 0 && !xyz)) return ECG_EINVAL;
   if (ctx->devptr() && ((reinterpret_cast<uintptr_t>(xyz) | reinterpret_cast<uintptr_t>(out_xy)) & 3)) {
     ctx->err = "device pointer not 4-byte aligned";
@@ -1391,9 +1562,10 @@ static ecg_status lincomb_attempt(ecg_ctx* ctx, ecg_curve curve, size_t n, const
   return point_sum_enqueue(ctx, curve, nd, partial.data(), out_xy, out_inf, true);
 }
 
-extern "C" ecg_status ecg_lincomb(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
+ECG_API(ecg_lincomb)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
                                   const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf) {
   if (!ctx) return ECG_EINVAL;
+  ECG_FORWARD(ecg_lincomb, ctx, curve, n, k, P_xy, P_inf, out_xy, out_inf);
   if (!out_xy || !out_inf || !curve_ok(curve) || (n > 0 && (!k || !P_xy))) {
     ctx->err = "ecg_lincomb: null pointer or unknown curve";
     return ECG_EINVAL;
@@ -1423,6 +1595,7 @@ extern "C" ecg_status ecg_lincomb(ecg_ctx* ctx, ecg_curve curve, size_t n, const
   return ECG_OK;
 }
 
+#if ECG_TU == 0
 extern "C" ecg_status ecg_microbench(ecg_ctx* ctx, int which, int iters, double* ops_per_s, double* elapsed_ms) {
   if (!ctx || !ops_per_s || iters <= 0) return ECG_EINVAL;
   DevState& d = ctx->devs[0];
@@ -1463,3 +1636,4 @@ extern "C" ecg_status ecg_microbench(ecg_ctx* ctx, int which, int iters, double*
   if (elapsed_ms) *elapsed_ms = best;
   return ECG_OK;
 }
+#endif  // ECG_TU == 0

@@ -40,11 +40,31 @@ typedef enum {
   ECG_ENOMEM = 6
 } ecg_status;
 
-/* ECG_NISTP384: the next curve through the same kernels templates (p384/src/arithmetic.rs:43-75).
- * Its scalars and coordinates are 48 bytes: read "32 / 64 / 96" as "48 / 96 / 144" in every size below.  Served by the
- * hot-path entries (mul_batch[_x], mul_gen_batch, lincomb[_partial], point_sum, batch_normalize[_hom], field_op_batch);
- * the widening entries (verification, SEC1 decompression, a*G + b*P, field sqrt) are 256-bit only: ECG_EINVAL. */
-typedef enum { ECG_SECP256K1 = 0, ECG_NISTP256 = 1, ECG_NISTP384 = 2 } ecg_curve;
+/* Curves.  The hot path is secp256k1 and P-256; the other ids are the widening row "more curves
+ * through the same templates" (SURVEY 8(f) rank 4): every prime-order Weierstrass curve the reference implements except
+ * P-521 (p384/src/arithmetic.rs:43-75, sm2/src/arithmetic.rs:44-67, bp256/src/{r1,t1}/arithmetic.rs:34-53,
+ * bp384/src/{r1,t1}/arithmetic.rs:34-53, bignp256/src/arithmetic.rs:38-57, p224/src/arithmetic.rs:40-56,
+ * p192/src/arithmetic.rs:38-54), a = -3 and general-a alike (primeorder/src/point_arithmetic.rs:54-208, :212-319).
+ * Record sizes follow the curve: a scalar / field element is FB = 32 bytes for the 256-bit curves, 48 for P-384 and
+ * brainpoolP384, 28 for P-224, 24 for P-192 — read "32 / 64 / 96" in every size below as "FB / 2 FB / 3 FB".
+ * Byte order is the one the reference uses for the curve: big-endian everywhere except bign-curve256v1, whose field
+ * elements and scalars are little-endian (bignp256/src/arithmetic/field.rs:65, bignp256/src/lib.rs:102).
+ * Curves other than secp256k1 / P-256 are served by the hot-path entries (mul_batch[_x], mul_gen_batch,
+ * lincomb[_partial], point_sum, batch_normalize[_hom], field_op_batch); the 256-bit-only widening entries
+ * (verification, SEC1 decompression, a*G + b*P, field sqrt, hash-to-curve) answer ECG_EINVAL for them. */
+typedef enum {
+  ECG_SECP256K1 = 0,
+  ECG_NISTP256 = 1,
+  ECG_NISTP384 = 2,
+  ECG_SM2 = 3,
+  ECG_BP256R1 = 4,   /* brainpoolP256r1: general a */
+  ECG_BP256T1 = 5,   /* brainpoolP256t1: a = -3 */
+  ECG_BIGNP256 = 6,  /* bign-curve256v1 (STB 34.101.45): little-endian records */
+  ECG_BP384R1 = 7,   /* brainpoolP384r1: general a */
+  ECG_BP384T1 = 8,   /* brainpoolP384t1: a = -3 */
+  ECG_NISTP224 = 9,
+  ECG_NISTP192 = 10
+} ecg_curve;
 
 typedef enum {
   ECG_FOP_ADD = 0,

@@ -84,6 +84,35 @@ def lib384():
     return _lib384
 
 
+LIBP = os.path.join(_HERE, "libecrefp.so")
+_libp = None
+# curves served by oracle/ecref_prime.c: id -> bytes per record (ids as in include/ecgpu.h)
+EXT = {"sm2": 3, "bp256r1": 4, "bp256t1": 5, "bignp256": 6, "bp384r1": 7, "bp384t1": 8, "p224": 9, "p192": 10}
+EXT.update({v: v for v in list(EXT.values())})
+EXT_NB = {3: 32, 4: 32, 5: 32, 6: 32, 7: 48, 8: 48, 9: 28, 10: 24}
+
+
+def libp():
+    """oracle/ecref_prime.c — the generic primeorder / Montgomery-field restatement (sm2, brainpool, bign, P-224, P-192)"""
+    global _libp
+    if _libp is None:
+        tagf = LIBP + ".host"
+        tag = _host_tag()
+        srcs = [os.path.join(_HERE, "ecref_prime.c"), os.path.join(_HERE, "ecref_prime_impl.inc")]
+        if (not os.path.exists(LIBP) or os.path.getmtime(LIBP) < max(os.path.getmtime(f) for f in srcs) or not os.path.exists(tagf)
+                or open(tagf).read().strip() != tag):
+            subprocess.check_call(["make", "-C", _HERE, "-B", "libecrefp.so"], stdout=subprocess.DEVNULL)
+            with open(tagf, "w") as f:
+                f.write(tag)
+        _libp = ctypes.CDLL(LIBP)
+        _libp.ecrefp_init()
+        vp, sz = ctypes.c_void_p, ctypes.c_size_t
+        _libp.ecrefp_mul_batch.argtypes = [ctypes.c_int, sz, vp, vp, vp, vp, vp, ctypes.c_int]
+        _libp.ecrefp_mul_gen_batch.argtypes = [ctypes.c_int, sz, vp, vp, vp, ctypes.c_int]
+        _libp.ecrefp_lincomb.argtypes = [ctypes.c_int, sz, vp, vp, vp, vp, vp, ctypes.c_int]
+    return _libp
+
+
 def _p(a):
     return ctypes.c_void_p(a.ctypes.data) if a is not None else ctypes.c_void_p(0)
 
@@ -96,6 +125,16 @@ def mul_batch(curve, k, pxy, pinf=None, nthreads=1, variant=0):
     pxy = np.ascontiguousarray(pxy, np.uint8).reshape(-1)
     if pinf is not None:
         pinf = np.ascontiguousarray(pinf, np.uint8).reshape(-1)
+    if curve in EXT:
+        cid = EXT[curve]
+        nb = EXT_NB[cid]
+        n = k.size // nb
+        oxy = np.zeros(2 * nb * n, np.uint8)
+        oinf = np.zeros(n, np.uint8)
+        rc = libp().ecrefp_mul_batch(cid, n, _p(k), _p(pxy), _p(pinf), _p(oxy), _p(oinf), nthreads)
+        if rc:
+            raise ValueError(f"ecrefp_mul_batch rc={rc}")
+        return oxy.reshape(n, 2 * nb), oinf
     if curve in ("p384", 2):
         n = k.size // 48
         oxy = np.zeros(96 * n, np.uint8)
@@ -115,6 +154,16 @@ def mul_batch(curve, k, pxy, pinf=None, nthreads=1, variant=0):
 
 def mul_gen_batch(curve, k, nthreads=1):
     k = np.ascontiguousarray(k, np.uint8).reshape(-1)
+    if curve in EXT:
+        cid = EXT[curve]
+        nb = EXT_NB[cid]
+        n = k.size // nb
+        oxy = np.zeros(2 * nb * n, np.uint8)
+        oinf = np.zeros(n, np.uint8)
+        rc = libp().ecrefp_mul_gen_batch(cid, n, _p(k), _p(oxy), _p(oinf), nthreads)
+        if rc:
+            raise ValueError(f"ecrefp_mul_gen_batch rc={rc}")
+        return oxy.reshape(n, 2 * nb), oinf
     if curve in ("p384", 2):
         n = k.size // 48
         oxy = np.zeros(96 * n, np.uint8)
@@ -152,6 +201,16 @@ def lincomb(curve, k, pxy, pinf=None, nthreads=1):
     pxy = np.ascontiguousarray(pxy, np.uint8).reshape(-1)
     if pinf is not None:
         pinf = np.ascontiguousarray(pinf, np.uint8).reshape(-1)
+    if curve in EXT:
+        cid = EXT[curve]
+        nb = EXT_NB[cid]
+        n = k.size // nb
+        oxy = np.zeros(2 * nb, np.uint8)
+        oinf = np.zeros(1, np.uint8)
+        rc = libp().ecrefp_lincomb(cid, n, _p(k), _p(pxy), _p(pinf), _p(oxy), _p(oinf), nthreads)
+        if rc:
+            raise ValueError(f"ecrefp_lincomb rc={rc}")
+        return oxy, int(oinf[0])
     if curve in ("p384", 2):
         n = k.size // 48
         oxy = np.zeros(96, np.uint8)

@@ -42,7 +42,7 @@ def group_vectors(curve):
     txt = open(f"{REF}/{curve}/src/test_vectors/group.rs").read()
     c = split_consts(txt)
     add = hexes(c["ADD_TEST_VECTORS"])
-    mul = hexes(c["MUL_TEST_VECTORS"])
+    mul = hexes(c["MUL_TEST_VECTORS"]) if "MUL_TEST_VECTORS" in c else []
     assert len(add) % 2 == 0 and len(mul) % 3 == 0
     return {
         "source": f"{curve}/src/test_vectors/group.rs",
@@ -197,6 +197,16 @@ def main():
     with open(path, "w") as f:
         json.dump(data, f, indent=1)
     print(path, len(data["group"]["add"]), len(data["group"]["mul"]), len(data["ecdsa"]["keypairs"]))
+    # the other prime-order curves with vector files: p224 / p192 (ADD + MUL, big-endian), bignp256 (ADD only, the hex
+    # strings are the curve's little-endian records: bignp256/src/test_vectors/group.rs:8); sm2 and the brainpool crates
+    # hold no group vectors (their parity is pinned to the big-integer model and OpenSSL)
+    for curve in ("p224", "p192", "bignp256"):
+        data = {"curve": curve, "reference_commit": "739304e026fdf06cd1a31606e4db487d3f47c5ae", "group": group_vectors(curve),
+                "little_endian": curve == "bignp256"}
+        path = os.path.join(OUT, f"{curve}.json")
+        with open(path, "w") as f:
+            json.dump(data, f, indent=1)
+        print(path, len(data["group"]["add"]), len(data["group"]["mul"]))
 
 
 if __name__ == "__main__":

@@ -34,6 +34,7 @@ class Curve:
     b: int
     gx: int
     gy: int
+    le: bool = False  # canonical records little-endian (bign-curve256v1 only)
 
 
 K256 = Curve(
@@ -65,7 +66,103 @@ P384 = Curve(
     gx=0xAA87CA22BE8B05378EB1C71EF320AD746E1D3B628BA79B9859F741E082542A385502F25DBF55296C3A545E3872760AB7,
     gy=0x3617DE4A96262C6F5D9E98BF9292DC29F8F41DBD289A147CE9DA3113B5F0B8C00A60B1CE1D7E819D7A431D7C90EA0E5F,
 )
+
+# ---- the remaining prime-order curves of the reference, ids as in include/ecgpu.h ------------
+# sm2/src/arithmetic.rs:44-67, sm2/src/arithmetic/field.rs:34, sm2/src/lib.rs:86
+SM2 = Curve(
+    "sm2",
+    p=0xFFFFFFFEFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFF00000000FFFFFFFFFFFFFFFF,
+    n=0xFFFFFFFEFFFFFFFFFFFFFFFFFFFFFFFF7203DF6B21C6052B53BBF40939D54123,
+    a=-3,
+    b=0x28E9FA9E9D9F5E344D5A9E4BCF6509A7F39789F515AB8F92DDBCBD414D940E93,
+    gx=0x32C4AE2C1F1981195F9904466A39C9948FE30BBFF2660BE1715A4589334C74C7,
+    gy=0xBC3736A2F4F6779C59BDCEE36B692153D0A9877CC62A474002DF32E52139F0A0,
+)
+_BP256_P = 0xA9FB57DBA1EEA9BC3E660A909D838D726E3BF623D52620282013481D1F6E5377
+_BP256_N = 0xA9FB57DBA1EEA9BC3E660A909D838D718C397AA3B561A6F7901E0E82974856A7
+# bp256/src/r1/arithmetic.rs:34-53 (general a), bp256/src/arithmetic/field.rs:53, bp256/src/lib.rs:70
+BP256R1 = Curve(
+    "bp256r1", p=_BP256_P, n=_BP256_N,
+    a=0x7D5A0975FC2C3057EEF67530417AFFE7FB8055C126DC5C6CE94A4B44F330B5D9,
+    b=0x26DC5C6CE94A4B44F330B5D9BBD77CBF958416295CF7E1CE6BCCDC18FF8C07B6,
+    gx=0x8BD2AEB9CB7E57CB2C4B482FFC81B7AFB9DE27E1E3BD23C23A4453BD9ACE3262,
+    gy=0x547EF835C3DAC4FD97F8461A14611DC9C27745132DED8E545C1D54C72F046997,
+)
+# bp256/src/t1/arithmetic.rs:34-51
+BP256T1 = Curve(
+    "bp256t1", p=_BP256_P, n=_BP256_N, a=-3,
+    b=0x662C61C430D84EA4FE66A7733D0B76B7BF93EBC4AF2F49256AE58101FEE92B04,
+    gx=0xA3E8EB3CC1CFE7B7732213B23A656149AFA142C47AAFBC2B79A191562E1305F4,
+    gy=0x2D996C823439C56D7F7B22E14644417E69BCB6DE39D027001DABE8F35B25C9BE,
+)
+# bignp256/src/arithmetic.rs:38-57 (constants written little-endian there), bignp256/src/arithmetic/field.rs:59-65,
+# bignp256/src/lib.rs:74,102: the one curve whose canonical records are little-endian
+BIGNP256 = Curve(
+    "bignp256",
+    p=2**256 - 189,
+    n=0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFD95C8ED60DFB4DFC7E5ABF99263D6607,
+    a=2**256 - 189 - 3,
+    b=0x77CE6C1515F3A8EDD2C13AABE4D8FBBE4CF55069978B9253B22E7D6BD69C03F1,
+    gx=0,
+    gy=0x6BF7FC3CFB16D69F5CE4C9A351D6835D78913966C408F6521E29CF1804516A93,
+    le=True,
+)
+_BP384_P = 0x8CB91E82A3386D280F5D6F7E50E641DF152F7109ED5456B412B1DA197FB71123ACD3A729901D1A71874700133107EC53
+_BP384_N = 0x8CB91E82A3386D280F5D6F7E50E641DF152F7109ED5456B31F166E6CAC0425A7CF3AB6AF6B7FC3103B883202E9046565
+# bp384/src/r1/arithmetic.rs:34-53 (general a), bp384/src/arithmetic/field.rs:53, bp384/src/lib.rs:73
+BP384R1 = Curve(
+    "bp384r1", p=_BP384_P, n=_BP384_N,
+    a=0x7BC382C63D8C150C3C72080ACE05AFA0C2BEA28E4FB22787139165EFBA91F90F8AA5814A503AD4EB04A8C7DD22CE2826,
+    b=0x04A8C7DD22CE28268B39B55416F0447C2FB77DE107DCD2A62E880EA53EEB62D57CB4390295DBC9943AB78696FA504C11,
+    gx=0x1D1C64F068CF45FFA2A63A81B7C13F6B8847A3E77EF14FE3DB7FCAFE0CBD10E8E826E03436D646AAEF87B2E247D4AF1E,
+    gy=0x8ABE1D7520F9C2A45CB1EB8E95CFD55262B70B29FEEC5864E19C054FF99129280E4646217791811142820341263C5315,
+)
+# bp384/src/t1/arithmetic.rs:34-51
+BP384T1 = Curve(
+    "bp384t1", p=_BP384_P, n=_BP384_N, a=-3,
+    b=0x7F519EADA7BDA81BD826DBA647910F8C4B9346ED8CCDC64E4B1ABD11756DCE1D2074AA263B88805CED70355A33B471EE,
+    gx=0x18DE98B02DB9A306F2AFCD7235F72A819B80AB12EBD653172476FECD462AABFFC4FF191B946A5F54D8D0AA2F418808CC,
+    gy=0x25AB056962D30651A114AFD2755AD336747F93475B7A1FCA3B88F2B6A208CCFE469408584DC2B2912675BF5B9E582928,
+)
+# p224/src/arithmetic.rs:40-56, p224/src/arithmetic/field.rs:54-60, p224/src/lib.rs:50-55
+P224 = Curve(
+    "p224",
+    p=2**224 - 2**96 + 1,
+    n=0xFFFFFFFFFFFFFFFFFFFFFFFFFFFF16A2E0B8F03E13DD29455C5C2A3D,
+    a=-3,
+    b=0xB4050A850C04B3ABF54132565044B0B7D7BFD8BA270B39432355FFB4,
+    gx=0xB70E0CBD6BB4BF7F321390B94A03C1D356C21122343280D6115C1D21,
+    gy=0xBD376388B5F723FB4C22DFE6CD4375A05A07476444D5819985007E34,
+)
+# p192/src/arithmetic.rs:38-54, p192/src/arithmetic/field.rs:54, p192/src/lib.rs:41
+P192 = Curve(
+    "p192",
+    p=2**192 - 2**64 - 1,
+    n=0xFFFFFFFFFFFFFFFFFFFFFFFF99DEF836146BC9B1B4D22831,
+    a=-3,
+    b=0x64210519E59C80E70FA7E9AB72243049FEB8DEECC146B9B1,
+    gx=0x188DA80EB03090F67CBF20EB43A18800F4FF0AFD82FF1012,
+    gy=0x07192B95FFC8DA78631011ED6B24CDD573F977A11E794811,
+)
+EXT_CURVES = {3: SM2, 4: BP256R1, 5: BP256T1, 6: BIGNP256, 7: BP384R1, 8: BP384T1, 9: P224, 10: P192}
+CURVE_IDS = {"k256": 0, "p256": 1, "p384": 2}
+CURVE_IDS.update({c.name: i for i, c in EXT_CURVES.items()})
 CURVES = {"k256": K256, "p256": P256, "p384": P384, 0: K256, 1: P256, 2: P384}
+CURVES.update(EXT_CURVES)
+CURVES.update({c.name: c for c in EXT_CURVES.values()})
+
+
+def byteorder(c: Curve) -> str:
+    return "little" if c.le else "big"
+
+
+def enc_fe(c: Curve, v: int) -> bytes:
+    """one canonical record (field element or scalar) in the curve's byte order"""
+    return v.to_bytes(fbytes(c), byteorder(c))
+
+
+def dec_fe(c: Curve, b: bytes) -> int:
+    return int.from_bytes(b, byteorder(c))
 
 
 def fbytes(c: Curve) -> int:

@@ -46,6 +46,10 @@ struct uint4 {
   uint32_t x, y, z, w;
 };
 static inline uint4 __ldg(const uint4* p) { return *p; }
+struct uint2 {
+  uint32_t x, y;
+};
+static inline uint2 __ldg(const uint2* p) { return *p; }
 
 #include "../../elliptic-curves_b200/csrc/ecg_curves.cuh"
 #include "../../elliptic-curves_b200/csrc/ecg_mul.cuh"
@@ -205,7 +209,7 @@ int sim_p256_fe_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
 // 1 when FpP256's internal form is the Montgomery domain (ops 2, 3, 7 of sim_p256_fe_op then carry a factor R^-1 / R^2)
 int sim_p256_is_mont(void) { return FpP256::MONT ? 1 : 0; }
 }  // extern "C"
-template <class F, bool AM3>
+template <class F, int AM3>
 static int sim_generic_mul(const uint8_t* k_be, const uint8_t* P_xy, uint8_t* out_xy, uint8_t* out_inf) {
   constexpr int NL = F::NL, FB = 4 * F::NL;
   uint32_t k[NL];
@@ -270,6 +274,104 @@ int sim_p384_on_curve(const uint8_t* P_xy) {
   F::Fe b;
   CurveP384::b_internal(b);
   return aff_on_curve<F, true>(P, b) ? 1 : 0;
+}
+// ---- curves on the generic Montgomery field policy (ecg_fe_mont.cuh / ecg_curves_ext.cuh) ----
+// curve ids as in include/ecgpu.h: 3 sm2, 4 brainpoolP256r1, 5 brainpoolP256t1, 6 bign-curve256v1, 7 brainpoolP384r1,
+// 8 brainpoolP384t1, 9 P-224, 10 P-192
+}  // extern "C"
+#define SIM_FOR_EXT(curve, ...)                         \
+  switch (curve) {                                      \
+    case 3: { typedef CurveSm2 CV; __VA_ARGS__; } break;      \
+    case 4: { typedef CurveBp256r1 CV; __VA_ARGS__; } break;  \
+    case 5: { typedef CurveBp256t1 CV; __VA_ARGS__; } break;  \
+    case 6: { typedef CurveBignP256 CV; __VA_ARGS__; } break; \
+    case 7: { typedef CurveBp384r1 CV; __VA_ARGS__; } break;  \
+    case 8: { typedef CurveBp384t1 CV; __VA_ARGS__; } break;  \
+    case 9: { typedef CurveP224 CV; __VA_ARGS__; } break;     \
+    case 10: { typedef CurveP192 CV; __VA_ARGS__; } break;    \
+    default: break;                                     \
+  }
+// field operation on canonical records (byte order of the curve); Montgomery conversions at the boundary like the kernels
+template <class C>
+static int sim_ext_fe_op_t(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  typedef typename C::F F;
+  typename F::FeT x, y, r;
+  load_fe<F>(x.v, a);
+  load_fe<F>(y.v, b);
+  F::from_canonical(x, x);
+  F::from_canonical(y, y);
+  switch (op) {
+    case 0: F::add(r, x, y); break;
+    case 1: F::sub(r, x, y); break;
+    case 2: F::mul(r, x, y); break;
+    case 3: F::sqr(r, x); break;
+    case 4: F::neg(r, x); break;
+    case 5: F::half(r, x); break;
+    case 6: F::mul_small(r, x, 3); break;
+    case 7: F::inv(r, x); break;
+    case 8: r = x; break;
+    case 9: F::mul_small(r, x, 8); break;
+    default: return -1;
+  }
+  F::to_canonical(r, r);
+  store_fe<F>(out, r.v);
+  return 0;
+}
+template <class C>
+static int sim_ext_mul_t(const uint8_t* kb, const uint8_t* P_xy, uint8_t* out_xy, uint8_t* out_inf) {
+  typedef typename C::F F;
+  constexpr int NL = F::NL, FB = 4 * F::NL;
+  uint32_t k[NL];
+  load_fe<F>(k, kb);
+  typename F::AffT P;
+  load_fe<F>(P.x.v, P_xy);
+  load_fe<F>(P.y.v, P_xy + FB);
+  F::from_canonical(P.x, P.x);
+  F::from_canonical(P.y, P.y);
+  typename F::FeT bb;
+  C::b_internal(bb);
+  if (!aff_on_curve<F, C::A_IS_MINUS3>(P, bb)) return 3;
+  std::vector<uint32_t> tabmem(8 * 3 * NL);
+  TabRefJN<NL> tab{tabmem.data(), 1};
+  typename F::JacT r;
+  generic_mul_thread<F, C::A_IS_MINUS3>(r, k, P, tab);
+  if (F::is_zero(r.Z)) {
+    memset(out_xy, 0, 2 * FB);
+    *out_inf = 1;
+    return 0;
+  }
+  typename F::FeT zinv, x, y;
+  F::inv(zinv, r.Z);
+  jac_to_affine_canonical<F>(x, y, r, zinv);
+  store_fe<F>(out_xy, x.v);
+  store_fe<F>(out_xy + FB, y.v);
+  *out_inf = 0;
+  return 0;
+}
+template <class C>
+static int sim_ext_gen_t(uint8_t* out_xy) {  // the generator as the device constants hold it, back in canonical bytes
+  typedef typename C::F F;
+  typename F::AffT g;
+  C::generator(g);
+  typename F::FeT x, y;
+  F::to_canonical(x, g.x);
+  F::to_canonical(y, g.y);
+  store_fe<F>(out_xy, x.v);
+  store_fe<F>(out_xy + 4 * F::NL, y.v);
+  return 0;
+}
+extern "C" {
+int sim_ext_fe_op(int curve, int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  SIM_FOR_EXT(curve, return sim_ext_fe_op_t<CV>(op, a, b, out));
+  return -1;
+}
+int sim_ext_mul(int curve, const uint8_t* k, const uint8_t* P_xy, uint8_t* out_xy, uint8_t* out_inf) {
+  SIM_FOR_EXT(curve, return sim_ext_mul_t<CV>(k, P_xy, out_xy, out_inf));
+  return -1;
+}
+int sim_ext_generator(int curve, uint8_t* out_xy) {
+  SIM_FOR_EXT(curve, return sim_ext_gen_t<CV>(out_xy));
+  return -1;
 }
 // experiment variants measured in tools/kbench.cu: a = -3 doubling as 3M+5S, point-level call structure
 int sim_p256_mul_3m5s(const uint8_t* k_be, const uint8_t* P_xy, uint8_t* out_xy, uint8_t* out_inf) {
@@ -421,8 +523,12 @@ static void simk_normalize(std::vector<uint32_t>& jac, size_t n, uint8_t* out_xy
 extern "C" int simk_affine_to_table(int curve, size_t n, const uint8_t* xy, uint32_t* table) {
   if (curve == 0)
     sim_launch(n, 256, [&] { affine_to_table_kernel<CurveK256>(xy, n, table); });
-  else
+  else if (curve == 1)
     sim_launch(n, 256, [&] { affine_to_table_kernel<CurveP256>(xy, n, table); });
+  else if (curve == 2)
+    sim_launch(n, 256, [&] { affine_to_table_kernel<CurveP384>(xy, n, table); });
+  else
+    SIM_FOR_EXT(curve, sim_launch(n, 256, [&] { affine_to_table_kernel<CV>(xy, n, table); }));
   return 0;
 }
 
@@ -441,25 +547,40 @@ extern "C" int simk_mul_batch(int curve, size_t n, const uint8_t* k, const uint8
     std::vector<uint32_t> gtab(blocks * SIM_BLOCK * P_TAB_WORDS);
     sim_launch(n, SIM_BLOCK, [&] { generic_varbase_kernel<CurveP256, SIM_BLOCK, 4>(k, pxy, pinf, n, jac.data(), gtab.data(), status, 0); });
     simk_normalize<CurveP256>(jac, n, out_xy, out_inf);
-  } else {
+  } else if (curve == 2) {
     std::vector<uint32_t> jac12(36 * n + 36), gtab(blocks * SIM_BLOCK * (8 * 36));
     sim_launch(n, SIM_BLOCK, [&] { generic_varbase_kernel<CurveP384, SIM_BLOCK, 4>(k, pxy, pinf, n, jac12.data(), gtab.data(), status, 0); });
     simk_normalize<CurveP384>(jac12, n, out_xy, out_inf);
+  } else {
+    SIM_FOR_EXT(curve, {
+      constexpr size_t NLc = CV::F::NL;
+      std::vector<uint32_t> jx(3 * NLc * n + 36), gtab(blocks * SIM_BLOCK * (8 * 3 * NLc));
+      sim_launch(n, SIM_BLOCK, [&] { generic_varbase_kernel<CV, SIM_BLOCK, 4>(k, pxy, pinf, n, jx.data(), gtab.data(), status, 0); });
+      simk_normalize<CV>(jx, n, out_xy, out_inf);
+    });
   }
   return 0;
 }
 
 extern "C" int simk_mul_gen_batch(int curve, size_t n, const uint8_t* k, const uint32_t* table, uint8_t* out_xy, uint8_t* out_inf,
                        uint32_t* status) {
-  std::vector<uint32_t> jac(24 * n + 24);
+  std::vector<uint32_t> jac(36 * n + 36);
   status[0] = 0;
   status[1] = 0xFFFFFFFFu;
   if (curve == 0) {
     sim_launch(n, 128, [&] { fixedbase_kernel<CurveK256>(k, n, table, jac.data(), status, 0); });
     simk_normalize<CurveK256>(jac, n, out_xy, out_inf);
-  } else {
+  } else if (curve == 1) {
     sim_launch(n, 128, [&] { fixedbase_kernel<CurveP256>(k, n, table, jac.data(), status, 0); });
     simk_normalize<CurveP256>(jac, n, out_xy, out_inf);
+  } else if (curve == 2) {
+    sim_launch(n, 128, [&] { fixedbase_kernel<CurveP384>(k, n, table, jac.data(), status, 0); });
+    simk_normalize<CurveP384>(jac, n, out_xy, out_inf);
+  } else {
+    SIM_FOR_EXT(curve, {
+      sim_launch(n, 128, [&] { fixedbase_kernel<CV>(k, n, table, jac.data(), status, 0); });
+      simk_normalize<CV>(jac, n, out_xy, out_inf);
+    });
   }
   return 0;
 }
@@ -540,7 +661,8 @@ static MsmGeom simk_msm_geometry(int curve, size_t n) {  // = msm_geometry (ecgp
   int lg = 0;
   while (((size_t)1 << (lg + 1)) <= nsub) lg++;
   g.c = std::min(16, std::max(8, lg - 5));
-  g.nbits = glv ? 128 : (curve == 2 ? 384 : 256);
+  static const int ext_bits[] = {256, 256, 256, 256, 384, 384, 224, 192};  // ids 3..10
+  g.nbits = glv ? 128 : (curve == 2 ? 384 : curve >= 3 ? ext_bits[curve - 3] : 256);
   g.W = (g.nbits + g.c - 1) / g.c;
   g.nbw = ((uint32_t)1 << (g.c + 1)) + 2;
   return g;
@@ -664,7 +786,7 @@ extern "C" int simk_lincomb_k(int curve, size_t n, const uint8_t* k, const uint8
   status[0] = 0;
   status[1] = 0xFFFFFFFFu;
   if (n == 0) {  // empty sum = identity
-    memset(out_xy, 0, curve == 2 ? 96 : 64);
+    memset(out_xy, 0, (curve == 2 || curve == 7 || curve == 8) ? 96 : curve == 9 ? 56 : curve == 10 ? 48 : 64);
     *out_inf = 1;
     *path = 0;
     return 0;
@@ -673,8 +795,10 @@ extern "C" int simk_lincomb_k(int curve, size_t n, const uint8_t* k, const uint8
     simk_lincomb_t<CurveK256, true, true>(curve, n, k, pxy, pinf, msm_min_terms, out_xy, out_inf, status, path, bucket_k);
   else if (curve == 1)
     simk_lincomb_t<CurveP256, false, false>(curve, n, k, pxy, pinf, msm_min_terms, out_xy, out_inf, status, path, bucket_k);
-  else
+  else if (curve == 2)
     simk_lincomb_t<CurveP384, false, false>(curve, n, k, pxy, pinf, msm_min_terms, out_xy, out_inf, status, path, bucket_k);
+  else
+    SIM_FOR_EXT(curve, (simk_lincomb_t<CV, false, false>(curve, n, k, pxy, pinf, msm_min_terms, out_xy, out_inf, status, path, bucket_k)));
   return 0;
 }
 extern "C" int simk_lincomb(int curve, size_t n, const uint8_t* k, const uint8_t* pxy, const uint8_t* pinf, size_t msm_min_terms,

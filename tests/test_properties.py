@@ -55,7 +55,8 @@ class SimBackend:
         n = K.size // 32
         oxy, oinf, stt = np.zeros(64, np.uint8), np.zeros(1, np.uint8), np.zeros(2, np.uint32)
         path = ctypes.c_int(-1)
-        self.lib.simk_lincomb(CID[curve], ctypes.c_size_t(n), _p(K), _p(np.ascontiguousarray(xy)), _p(inf), ctypes.c_size_t(1 << 13),
+        xyc = np.ascontiguousarray(xy)
+        self.lib.simk_lincomb(CID[curve], ctypes.c_size_t(n), _p(K), _p(xyc), _p(inf), ctypes.c_size_t(1 << 13),
                               _p(oxy), _p(oinf), _p(stt), ctypes.byref(path))
         assert stt[0] == 0
         return oxy, int(oinf[0])

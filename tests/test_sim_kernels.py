@@ -91,7 +91,8 @@ def test_fixedbase_and_mul_gen_add_kernels(sim, fb_tables, curve):
     ks = [int(v["k"], 16) for v in g["group"]["mul"]] + edge_scalars(c)
     n = len(ks)
     oxy, oinf, st = np.zeros(64 * n, np.uint8), np.zeros(n, np.uint8), np.zeros(2, np.uint32)
-    sim.simk_mul_gen_batch(CID[curve], ctypes.c_size_t(n), _p(pack_scalars(ks)), _p(table), _p(oxy), _p(oinf), _p(st))
+    K = pack_scalars(ks)  # kept alive across the call (_p() only takes the address)
+    sim.simk_mul_gen_batch(CID[curve], ctypes.c_size_t(n), _p(K), _p(table), _p(oxy), _p(oinf), _p(st))
     assert st[0] == 0
     got = unpack_points(oxy.reshape(n, 64), oinf)
     for v, P in zip(g["group"]["mul"], got):
@@ -152,9 +153,9 @@ def test_ecdsa_kernels_against_wycheproof_and_fips_vectors(sim, fb_tables, curve
         z, r, s, q, exp = next(x for x in cases if x[4])
         one = np.full(1, 7, np.uint8)
         hi = np.frombuffer(r.to_bytes(32, "big") + (c.n - s).to_bytes(32, "big"), np.uint8)
-        sim.simk_ecdsa_verify_batch(0, ctypes.c_size_t(1), _p(np.frombuffer(z, np.uint8)), _p(hi),
-                                    _p(np.frombuffer(q[0].to_bytes(32, "big") + q[1].to_bytes(32, "big"), np.uint8)), 1,
-                                    _p(fb_tables[curve]), _p(one))
+        zb = np.frombuffer(z, np.uint8)
+        qb = np.frombuffer(q[0].to_bytes(32, "big") + q[1].to_bytes(32, "big"), np.uint8)
+        sim.simk_ecdsa_verify_batch(0, ctypes.c_size_t(1), _p(zb), _p(hi), _p(qb), 1, _p(fb_tables[curve]), _p(one))
         assert one[0] == 0
 
 
@@ -215,7 +216,8 @@ def test_lincomb_kernels_per_term_and_bucket_method(sim, curve):
         xy, inf = pack_points(Ps)
         oxy, oinf, stt = np.zeros(64, np.uint8), np.zeros(1, np.uint8), np.zeros(2, np.uint32)
         path = ctypes.c_int(-1)
-        sim.simk_lincomb(CID[curve], ctypes.c_size_t(n), _p(pack_scalars(ks)), _p(xy), _p(inf), ctypes.c_size_t(msm_min),
+        K = pack_scalars(ks)
+        sim.simk_lincomb(CID[curve], ctypes.c_size_t(n), _p(K), _p(xy), _p(inf), ctypes.c_size_t(msm_min),
                          _p(oxy), _p(oinf), _p(stt), ctypes.byref(path))
         assert stt[0] == 0
         return pyref.dec_point(oxy.tobytes(), int(oinf[0])), path.value
