@@ -809,6 +809,101 @@ def measure_p384(B, steps):
                              "bit_exact_vs_gpu": ok}}
 
 
+def measure_more_curves(B, steps):
+    """Widening record (not a BASELINE config): the other prime-order curves of the reference through
+    the same kernels over the generic Montgomery field policy — variable-base multiplication, 2^16 pairs per GPU and
+    curve.  Parity: every output of every rank against oracle/ecref_prime.c (the reference's generic primeorder path:
+    RCB formulas for a = -3 / general a, radix-16 constant-time lincomb; its duration is the CPU baseline)."""
+    import torch
+
+    import ecref
+    import pyref
+
+    eng, host_eng, dev, world, rank = B.eng, B.host_eng, B.dev, B.world, B.rank
+    n = 1 << 16
+    out = {}
+    all_ok = True
+    for cid, c in sorted(pyref.EXT_CURVES.items()):
+        nb = pyref.fbytes(c)
+        nl = nb // 4
+        rng = np.random.default_rng(0xB2000100 + 16 * cid + rank)
+        msb = nb - 1 if c.le else 0
+        top = c.n >> (8 * (nb - 1))
+
+        def scalars():
+            K = rng.integers(0, 256, size=(n, nb), dtype=np.uint8)
+            K[:, msb] = K[:, msb] % top
+            return K
+
+        K, T = scalars(), scalars()
+        T[:, nb - 1 - msb] |= 1                                     # t != 0
+        pxy, pinf = host_eng.mul_by_generator(c.name, T.reshape(-1))  # uniformly random points t*G (fixed-base table of the curve)
+        assert not pinf.any()
+        k_host = torch.from_numpy(K.reshape(-1)).pin_memory()
+        p_host = torch.from_numpy(np.ascontiguousarray(pxy).reshape(-1)).pin_memory()
+        o_host = torch.empty(2 * nb * n, dtype=torch.uint8).pin_memory()
+        oi_host = torch.empty(n, dtype=torch.uint8).pin_memory()
+        kd, pd = k_host.to(dev), p_host.to(dev)
+        oxy = torch.empty(2 * nb * n, dtype=torch.uint8, device=dev)
+        oinf = torch.empty(n, dtype=torch.uint8, device=dev)
+
+        def step_dev():
+            B.flush.zero_()
+            eng.mul_batch_ptr(c.name, n, kd.data_ptr(), pd.data_ptr(), 0, oxy.data_ptr(), oinf.data_ptr())
+
+        for _ in range(3):
+            step_dev()
+        barrier_sync(world)
+        eng.timing_enable(True)
+        for _ in range(steps):
+            step_dev()
+        torch.cuda.synchronize()
+        dom_ms, dom_calls = eng.timing_read()
+        eng.timing_enable(False)
+        dom = max_over_ranks(dom_ms / max(dom_calls, 1), world)
+        host_eng.mul_batch(c.name, k_host.numpy(), p_host.numpy(), None, o_host.numpy(), oi_host.numpy())
+        barrier_sync(world)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            host_eng.mul_batch(c.name, k_host.numpy(), p_host.numpy(), None, o_host.numpy(), oi_host.numpy())
+        barrier_sync(world)
+        e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+        dev_same = bool(np.array_equal(oxy.cpu().numpy(), o_host.numpy()))
+        barrier_sync(world)
+        t0 = time.perf_counter()
+        r_xy, r_inf = ecref.mul_batch(c.name, k_host.numpy(), p_host.numpy(), None, nthreads=B.threads)
+        cpu_s = time.perf_counter() - t0
+        full = bool(np.array_equal(o_host.numpy(), r_xy.reshape(-1)) and np.array_equal(oi_host.numpy(), r_inf))
+        cpu_rate = B.sum_over_ranks(n / cpu_s)
+        ok = B.all_true(dev_same and full)
+        all_ok = all_ok and ok
+        # multiplier slots executed per pair: M = 2 NL^2 + NL (integrated Montgomery product), S = NL(NL+1)/2 + NL^2 + NL;
+        # 32 NL doublings (4M+4S; general a: 5M+6S) + 8 NL + 1 Jacobian additions (12M+4S) + table (1 dbl + 1 madd + 6 add)
+        M, S = 2 * nl * nl + nl, nl * (nl + 1) // 2 + nl * nl + nl
+        general_a = (c.a % c.p) != c.p - 3
+        dbl = (5 * M + 6 * S) if general_a else (4 * M + 4 * S)
+        slots = 32 * nl * dbl + (8 * nl + 1) * (12 * M + 4 * S) + dbl + (8 * M + 3 * S) + 6 * (12 * M + 4 * S)
+        out[c.name] = {"value": world * n / (dom * 1e-3), "unit": "scalar-mults/s", "kernel_ms": dom, "record_bytes": nb,
+                       "little_endian_records": bool(c.le), "equation_a": "general" if general_a else "-3",
+                       "e2e": {"value": world * n * steps / e2e_s, "unit": "scalar-mults/s", "h2d_bytes_per_step": 3 * nb * n,
+                               "d2h_bytes_per_step": (2 * nb + 1) * n, "matches_device_path": dev_same},
+                       "roofline_int": {"achieved": slots * n / (dom * 1e-3), "peak": B.imadw_peak, "frac": slots * n / (dom * 1e-3) / B.imadw_peak,
+                                        "unit": "IMAD.WIDE/s (executed)", "imad_wide_per_unit": slots},
+                       "cpu_baseline": {"value": cpu_rate, "unit": "scalar-mults/s", "cores": B.cores, "threads": B.threads * world, "kind": "port",
+                                        "sample": f"the whole workload ({world * n} units), constant-time `*` path (oracle/ecref_prime.c)"},
+                       "bit_exact": ok}
+    if rank != 0:
+        return None
+    return {"metric": "scalar-mults/s (variable base, per curve)", "unit": "scalar-mults/s", "n_gpus": world, "steps": steps,
+            "config": {"workload": "widening step (SURVEY 8(f) rank 4, not a BASELINE config): sm2, brainpoolP256r1/t1, bign-curve256v1, "
+                                   "brainpoolP384r1/t1, P-224, P-192 variable base, batch 2^16 per GPU and curve, kernel time by CUDA events "
+                                   "(ecg_timing), L2 flushed between steps", "batch_per_gpu": n},
+            "curves": out, "bit_exact": all_ok,
+            "bit_exact_coverage": f"every output of every rank and curve vs oracle/ecref_prime.c ({world * n} units per curve); the oracle is "
+                                  "pinned to the reference's p224 / p192 / bignp256 vectors, to the big-integer model and (brainpool, P-224, "
+                                  "P-192) to OpenSSL by tests/test_curves_ext.py"}
+
+
 def run_ours(args):
     B = Bench(args)
     world, rank = B.world, B.rank
@@ -821,6 +916,7 @@ def run_ours(args):
         for key, wl in (("3_p256_varbase", "p256_varbase"), ("4_k256_fixedbase", "k256_fixedbase"), ("5_k256_lincomb", "k256_lincomb")):
             configs[key] = measure(B, wl, sub_steps, 3, sample_clocks=False)
         configs["6_p384_varbase"] = measure_p384(B, max(3, sub_steps // 2))
+        configs["7_more_curves"] = measure_more_curves(B, 3)
         if world > 1:
             configs["strong_scaling"] = strong_scaling(B)
             barrier_sync(world)

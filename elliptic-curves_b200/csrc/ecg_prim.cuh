@@ -97,6 +97,13 @@ ECG_D void mad_acc3(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t a, uint32
                : "+r"(c0), "+r"(c1), "+r"(c2)
                : "r"(a), "r"(b));
 }
+// the same with early-clobber accumulators: a multiplicand may be a value the compiler keeps in the register of c0
+// (the Montgomery factor m = c0 * n0inv when n0inv == 1: sm2, P-192), and c0 is written before a is read again
+ECG_D void mad_acc3x(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t a, uint32_t b) {
+  asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+               : "+&r"(c0), "+&r"(c1), "+&r"(c2)
+               : "r"(a), "r"(b));
+}
 ECG_D uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
 ECG_D uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_l(lo, hi, s); }
 ECG_D uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
@@ -174,6 +181,7 @@ inline void mad_acc3(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t a, uint3
   c1 = (uint32_t)s1;
   c2 += (uint32_t)(s1 >> 32);
 }
+inline void mad_acc3x(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t a, uint32_t b) { mad_acc3(c0, c1, c2, a, b); }
 inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
   s &= 31;
   return s ? (lo >> s) | (hi << (32 - s)) : lo;

@@ -24,6 +24,7 @@
 #include "../../include/ecgpu.h"
 #include "ecg_kernels.cuh"
 #if ECG_TU == 0
+#include "ecg_h2c.cuh"
 #include "ecg_microbench.cuh"
 #endif
 #include "ecg_msm.cuh"
@@ -1594,6 +1595,152 @@ ECG_API(ecg_lincomb)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, 
   }
   return ECG_OK;
 }
+
+#if ECG_TU == 0
+// ---- hash to curve / hash to scalar (ecg_h2c.cuh) ---------------------------------------------------------------
+// host-side SHA-256, only for a DST longer than 255 bytes (RFC 9380 section 5.3.3: DST = H("H2C-OVERSIZE-DST-" || DST))
+static void host_sha256(const uint8_t* data, size_t len, uint8_t out[32]) {
+  static const uint32_t K[64] = {
+      0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u, 0xd807aa98u, 0x12835b01u,
+      0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u, 0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu,
+      0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau, 0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u,
+      0x06ca6351u, 0x14292967u, 0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u,
+      0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u, 0x19a4c116u, 0x1e376c08u,
+      0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u, 0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u,
+      0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
+  uint32_t st[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+  std::vector<uint8_t> buf(data, data + len);
+  buf.push_back(0x80);
+  while (buf.size() % 64 != 56) buf.push_back(0);
+  for (int i = 7; i >= 0; i--) buf.push_back((uint8_t)(((uint64_t)len * 8) >> (8 * i)));
+  auto rotr = [](uint32_t x, int n) { return (x >> n) | (x << (32 - n)); };
+  for (size_t off = 0; off < buf.size(); off += 64) {
+    uint32_t w[64];
+    for (int i = 0; i < 16; i++)
+      w[i] = ((uint32_t)buf[off + 4 * i] << 24) | ((uint32_t)buf[off + 4 * i + 1] << 16) | ((uint32_t)buf[off + 4 * i + 2] << 8) | buf[off + 4 * i + 3];
+    for (int i = 16; i < 64; i++)
+      w[i] = w[i - 16] + (rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3)) + w[i - 7] + (rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10));
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+    for (int i = 0; i < 64; i++) {
+      uint32_t t1 = h + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + ((e & f) ^ (~e & g)) + K[i] + w[i];
+      uint32_t t2 = (rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+      h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+  }
+  for (int i = 0; i < 8; i++)
+    for (int j = 0; j < 4; j++) out[4 * i + j] = (uint8_t)(st[i] >> (24 - 8 * j));
+}
+
+// mode 0: hash_to_curve (RO), 1: encode_to_curve (NU), 2: hash_to_scalar
+static ecg_status h2c_run(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* msgs, const uint64_t* offsets, const uint8_t* dst,
+                          size_t dst_len, int mode, uint8_t* out, uint8_t* out_inf) {
+  DevState& d = ctx->devs[0];
+  Lane& L = d.lane[0];
+  CU_TRY(ctx, cudaSetDevice(d.dev));
+  // DST_prime = DST || I2OSP(len(DST), 1), an oversize DST replaced by its hash (expand_msg.rs:76-95)
+  uint8_t dst_prime[256];
+  uint32_t dpl;
+  if (dst_len > 255) {
+    std::vector<uint8_t> salted;
+    const char* salt = "H2C-OVERSIZE-DST-";
+    salted.insert(salted.end(), salt, salt + 17);
+    salted.insert(salted.end(), dst, dst + dst_len);
+    host_sha256(salted.data(), salted.size(), dst_prime);
+    dst_prime[32] = 32;
+    dpl = 33;
+  } else {
+    memcpy(dst_prime, dst, dst_len);
+    dst_prime[dst_len] = (uint8_t)dst_len;
+    dpl = (uint32_t)dst_len + 1;
+  }
+  ST_TRY(begin_lane(ctx, L));
+  ST_TRY(ensure(ctx, L, B_A, 256));
+  CU_TRY(ctx, cudaMemcpyAsync(L.buf[B_A], dst_prime, dpl, cudaMemcpyHostToDevice, L.s()));  // pageable, <= 256 bytes: staged by the driver
+  const uint8_t* dmsgs = msgs;
+  const uint64_t* doffs = offsets;
+  uint64_t base = 0;
+  if (!ctx->devptr()) {
+    base = offsets[0];
+    const uint64_t total = offsets[n] - base;
+    for (size_t i = 0; i < n; i++)
+      if (offsets[i + 1] < offsets[i]) {
+        ctx->err = "hash_to_curve: message offsets must be non-decreasing";
+        return ECG_EINVAL;
+      }
+    ST_TRY(ensure(ctx, L, B_P, (size_t)total + 16));
+    ST_TRY(ensure(ctx, L, B_K, (n + 1) * 8));
+    if (total) CU_TRY(ctx, cudaMemcpyAsync(L.buf[B_P], msgs + base, (size_t)total, cudaMemcpyHostToDevice, L.s()));
+    CU_TRY(ctx, cudaMemcpyAsync(L.buf[B_K], offsets, (n + 1) * 8, cudaMemcpyHostToDevice, L.s()));
+    dmsgs = (const uint8_t*)L.buf[B_P];
+    doffs = (const uint64_t*)L.buf[B_K];
+  } else if (reinterpret_cast<uintptr_t>(offsets) & 7) {
+    ctx->err = "device pointer (offsets) not 8-byte aligned";
+    return ECG_EINVAL;
+  }
+  const uint8_t* dprime = (const uint8_t*)L.buf[B_A];
+  const bool k1 = curve == ECG_SECP256K1;
+  DevPtrs dp;
+  if (mode == 2) {
+    ST_TRY(stage_out(ctx, L, 0, n, out, 32, nullptr, dp));
+    DOM_BEGIN(ctx, L);
+    if (k1)
+      h2s_kernel<CurveK256><<<grid_for(n, 128), 128, 0, L.s()>>>(dmsgs, doffs, base, n, dprime, dpl, dp.out);
+    else
+      h2s_kernel<CurveP256><<<grid_for(n, 128), 128, 0, L.s()>>>(dmsgs, doffs, base, n, dprime, dpl, dp.out);
+    LAUNCHED(ctx);
+    DOM_END(ctx, L);
+    return copy_back(ctx, L, 0, n, out, 32, nullptr, dp);
+  }
+  ST_TRY(stage_out(ctx, L, 0, n, out, 64, out_inf, dp));
+  ST_TRY(ensure(ctx, L, B_JAC, n * 96));
+  uint32_t* jac = (uint32_t*)L.buf[B_JAC];
+  DOM_BEGIN(ctx, L);
+  if (k1 && mode == 0)
+    h2c_kernel<CurveK256, false><<<grid_for(n, 128), 128, 0, L.s()>>>(dmsgs, doffs, base, n, dprime, dpl, jac);
+  else if (k1)
+    h2c_kernel<CurveK256, true><<<grid_for(n, 128), 128, 0, L.s()>>>(dmsgs, doffs, base, n, dprime, dpl, jac);
+  else if (mode == 0)
+    h2c_kernel<CurveP256, false><<<grid_for(n, 128), 128, 0, L.s()>>>(dmsgs, doffs, base, n, dprime, dpl, jac);
+  else
+    h2c_kernel<CurveP256, true><<<grid_for(n, 128), 128, 0, L.s()>>>(dmsgs, doffs, base, n, dprime, dpl, jac);
+  LAUNCHED(ctx);
+  DOM_END(ctx, L);
+  ST_TRY(launch_norm(ctx, d, L, curve, n, jac, dp.out, dp.oinf));
+  return copy_back(ctx, L, 0, n, out, 64, out_inf, dp);
+}
+
+static ecg_status h2c_entry(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* msgs, const uint64_t* offsets, const uint8_t* dst,
+                            size_t dst_len, int mode, uint8_t* out, uint8_t* out_inf) {
+  if (!ctx) return ECG_EINVAL;
+  if (!curve_256(curve) || !dst || dst_len == 0 || dst_len > 65535) {  // ExpandMsgXmdError::EmptyDst
+    ctx->err = "hash_to_curve: secp256k1 / P-256 only, and a non-empty domain separation tag is required";
+    return ECG_EINVAL;
+  }
+  if (n == 0) return ECG_OK;
+  if (!offsets || !out || (mode != 2 && !out_inf) || n > ((size_t)1 << 31)) {
+    ctx->err = "hash_to_curve: null pointer";
+    return ECG_EINVAL;
+  }
+  if (!msgs && (ctx->devptr() || offsets[n] != offsets[0])) {
+    ctx->err = "hash_to_curve: null message buffer";
+    return ECG_EINVAL;
+  }
+  ecg_status st = h2c_run(ctx, curve, n, msgs, offsets, dst, dst_len, mode, out, out_inf);
+  if (st != ECG_OK) return fail(ctx, st);
+  st = finish(ctx);
+  return st == ECG_OK ? st : fail(ctx, st);
+}
+
+extern "C" ecg_status ecg_hash_to_curve_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* msgs, const uint64_t* offsets,
+                                              const uint8_t* dst, size_t dst_len, int nonuniform, uint8_t* out_xy, uint8_t* out_inf) {
+  return h2c_entry(ctx, curve, n, msgs, offsets, dst, dst_len, nonuniform ? 1 : 0, out_xy, out_inf);
+}
+extern "C" ecg_status ecg_hash_to_scalar_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* msgs, const uint64_t* offsets,
+                                               const uint8_t* dst, size_t dst_len, uint8_t* out) {
+  return h2c_entry(ctx, curve, n, msgs, offsets, dst, dst_len, 2, out, nullptr);
+}
+#endif  // ECG_TU == 0
 
 #if ECG_TU == 0
 extern "C" ecg_status ecg_microbench(ecg_ctx* ctx, int which, int iters, double* ops_per_s, double* elapsed_ms) {

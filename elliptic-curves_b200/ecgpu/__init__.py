@@ -51,6 +51,7 @@ EXPORTS = [
     "ecg_kernel_launches", "ecg_version", "ecg_timing_enable", "ecg_timing_read",
     "ecg_schnorr_verify_batch", "ecg_ecdsa_verify_batch", "ecg_decompress_batch",
     "ecg_batch_normalize_hom", "ecg_mul_batch_x", "ecg_field_sqrt_batch",
+    "ecg_hash_to_curve_batch", "ecg_hash_to_scalar_batch",
 ]
 
 
@@ -128,6 +129,10 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.ecg_mul_batch_x.restype = ctypes.c_int
     lib.ecg_field_sqrt_batch.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p]
     lib.ecg_field_sqrt_batch.restype = ctypes.c_int
+    lib.ecg_hash_to_curve_batch.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p, sz, ctypes.c_int, u8p, u8p]
+    lib.ecg_hash_to_curve_batch.restype = ctypes.c_int
+    lib.ecg_hash_to_scalar_batch.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p, sz, u8p]
+    lib.ecg_hash_to_scalar_batch.restype = ctypes.c_int
     lib.ecg_version.argtypes = []
     lib.ecg_version.restype = ctypes.c_char_p
     if path is None:
@@ -315,6 +320,41 @@ class Engine:
         out_inf = np.empty(n, np.uint8)
         self._check(self.lib.ecg_mul_gen_add_batch(self._ctx, c, n, _ptr(a), _ptr(b), _ptr(P_xy), _ptr(P_inf), _ptr(out_xy), _ptr(out_inf)))
         return out_xy.reshape(n, 64), out_inf
+
+    @staticmethod
+    def _pack_messages(msgs):
+        """list of bytes -> (concatenated uint8 array, n + 1 uint64 offsets)"""
+        offs = np.zeros(len(msgs) + 1, np.uint64)
+        if len(msgs):
+            offs[1:] = np.cumsum([len(m) for m in msgs], dtype=np.uint64)
+        data = np.frombuffer(b"".join(bytes(m) for m in msgs), np.uint8).copy() if offs[-1] else np.zeros(1, np.uint8)
+        return data, offs
+
+    def hash_to_curve(self, curve, msgs, dst: bytes, nonuniform: bool = False):
+        """GroupDigest::hash_from_bytes / encode_from_bytes over a batch of messages (hash2curve/src/group_digest.rs:88-118)
+        -> (xy n x 64, inf)"""
+        c = CURVE_IDS[curve]
+        n = len(msgs)
+        data, offs = self._pack_messages(msgs)
+        d = np.frombuffer(bytes(dst), np.uint8).copy() if len(dst) else np.zeros(1, np.uint8)
+        out_xy = np.empty(64 * n, np.uint8)
+        out_inf = np.empty(n, np.uint8)
+        self._check(self.lib.ecg_hash_to_curve_batch(self._ctx, c, n, _ptr(data), _ptr(offs), _ptr(d), len(dst), 1 if nonuniform else 0,
+                                                     _ptr(out_xy), _ptr(out_inf)))
+        return out_xy.reshape(n, 64), out_inf
+
+    def encode_to_curve(self, curve, msgs, dst: bytes):
+        return self.hash_to_curve(curve, msgs, dst, nonuniform=True)
+
+    def hash_to_scalar(self, curve, msgs, dst: bytes):
+        """hash2curve::hash_to_scalar over a batch (group_digest.rs:131-143) -> n x 32 big-endian scalars"""
+        c = CURVE_IDS[curve]
+        n = len(msgs)
+        data, offs = self._pack_messages(msgs)
+        d = np.frombuffer(bytes(dst), np.uint8).copy() if len(dst) else np.zeros(1, np.uint8)
+        out = np.empty(32 * n, np.uint8)
+        self._check(self.lib.ecg_hash_to_scalar_batch(self._ctx, c, n, _ptr(data), _ptr(offs), _ptr(d), len(dst), _ptr(out)))
+        return out.reshape(n, 32)
 
     def schnorr_verify_batch(self, pk_x, msg32, sig64):
         """BIP340: VerifyingKey::verify_raw over a batch (k256/src/schnorr/verifying.rs:76-99) -> uint8 flags"""

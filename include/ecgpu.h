@@ -191,6 +191,24 @@ ecg_status ecg_mul_batch_x(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_
 ecg_status ecg_field_sqrt_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, uint8_t* out,
                                 uint8_t* is_square);
 
+/* ---- hash to curve ("hash-to-curve front end"), RFC 9380 with expand_message_xmd over
+ * SHA-256: the suites secp256k1_XMD:SHA-256_SSWU_{RO,NU}_ (k256/src/arithmetic/hash2curve.rs:14-20) and
+ * P256_XMD:SHA-256_SSWU_{RO,NU}_ (p256/src/arithmetic/hash2curve.rs:13-19); other curves: ECG_EINVAL.
+ * Message i is msgs[offsets[i] .. offsets[i+1]) (offsets: n + 1 non-decreasing uint64 values; with ECG_FLAG_DEVICE_PTRS
+ * msgs, offsets and the outputs are device pointers, offsets 8-byte aligned).  dst / dst_len: the domain separation tag,
+ * always a host pointer; empty -> ECG_EINVAL (ExpandMsgXmdError::EmptyDst, hash2curve/src/hash2field/expand_msg.rs:101-106),
+ * longer than 255 bytes -> replaced by SHA-256("H2C-OVERSIZE-DST-" || dst) as in the reference (expand_msg.rs:107-121).
+ * nonuniform = 0: out[i] = hash_to_curve(msg_i) (GroupDigest::hash_from_bytes, hash2curve/src/group_digest.rs:88-97:
+ * two field elements, two maps, one addition); nonuniform != 0: encode_to_curve (encode_from_bytes, :110-118). */
+ecg_status ecg_hash_to_curve_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* msgs, const uint64_t* offsets,
+                                   const uint8_t* dst, size_t dst_len, int nonuniform, uint8_t* out_xy, uint8_t* out_inf);
+
+/* out[i] = hash_to_scalar(msg_i) as 32 big-endian bytes: hash_to_field with the group order as modulus and L = 48
+ * (hash2curve/src/group_digest.rs:131-143 with Reduce<Array<u8, U48>> for Scalar, k256/src/arithmetic/hash2curve.rs:151-166,
+ * p256/src/arithmetic/hash2curve.rs:77-94) — the VOPRF DeriveKeyPair / HashToScalar primitive. */
+ecg_status ecg_hash_to_scalar_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* msgs, const uint64_t* offsets,
+                                    const uint8_t* dst, size_t dst_len, uint8_t* out);
+
 /* out[i] = a[i] op b[i] in F_p.
  * Replaces FieldElement add/sub/neg/mul/square/invert: k256/src/arithmetic/field.rs:116-196 over
  * field_5x52.rs:203-414; p256/src/arithmetic/field.rs:67-118 over field64.rs:7-144. */

@@ -159,6 +159,28 @@ def wycheproof(curve):
     return {"source": f"{curve}/src/test_vectors/data/wycheproof*.blb", "vectors": out}
 
 
+def h2c_vectors():
+    """RFC 9380 vectors the reference tests hold (k256/src/arithmetic/hash2curve.rs:289-370, p256/src/arithmetic/
+    hash2curve.rs:133-256) and the VOPRF hash_to_scalar vectors (p256/src/arithmetic/hash2curve.rs:257-310)."""
+    out = {"source": "k256/src/arithmetic/hash2curve.rs, p256/src/arithmetic/hash2curve.rs (#[cfg(test)] vectors)", "suites": {}}
+    for curve in ("k256", "p256"):
+        txt = open(f"{REF}/{curve}/src/arithmetic/hash2curve.rs").read()
+        dst = re.search(r'const DST: &\[u8\] = b"(QUUX[^"]+)"', txt).group(1)
+        vecs = []
+        for m in re.finditer(r'TestVector \{\s*msg: b"([^"]*)",(.*?)\},', txt, re.S):
+            fields = dict(re.findall(r'(\w+): hex!\("([0-9a-f]+)"\)', m.group(2)))
+            if "p_x" in fields:
+                vecs.append({"msg": m.group(1), **fields})
+        out["suites"][curve] = {"dst": dst, "vectors": vecs}
+    txt = open(f"{REF}/p256/src/arithmetic/hash2curve.rs").read()
+    sc = []
+    for m in re.finditer(r'dst: b"([^"]+)",\s*key_info: b"([^"]+)",\s*seed: &hex!\("([0-9a-f]+)"\),\s*sk_sm: &hex!\("([0-9a-f]+)"\)', txt):
+        dst = m.group(1).encode().decode("unicode_escape").encode("latin1").hex()
+        sc.append({"dst_hex": dst, "key_info": m.group(2), "seed": m.group(3), "sk_sm": m.group(4)})
+    out["p256_hash_to_scalar_voprf"] = sc
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     for curve in ("k256", "p256"):
@@ -200,6 +222,10 @@ def main():
     # the other prime-order curves with vector files: p224 / p192 (ADD + MUL, big-endian), bignp256 (ADD only, the hex
     # strings are the curve's little-endian records: bignp256/src/test_vectors/group.rs:8); sm2 and the brainpool crates
     # hold no group vectors (their parity is pinned to the big-integer model and OpenSSL)
+    with open(os.path.join(OUT, "h2c.json"), "w") as f:
+        v = h2c_vectors()
+        json.dump(v, f, indent=1)
+        print("h2c", {k: len(x["vectors"]) for k, x in v["suites"].items()}, len(v["p256_hash_to_scalar_voprf"]))
     for curve in ("p224", "p192", "bignp256"):
         data = {"curve": curve, "reference_commit": "739304e026fdf06cd1a31606e4db487d3f47c5ae", "group": group_vectors(curve),
                 "little_endian": curve == "bignp256"}

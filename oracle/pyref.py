@@ -340,3 +340,104 @@ def ecdsa_sign(c: Curve, d: int, z: int, k: int):
     r = R[0] % n
     s = pow(k, -1, n) * (z + r * d) % n
     return r, s
+
+
+# ---- hash to curve (RFC 9380), the suites the reference implements with SHA-256 -------------------------------------
+# hash2curve/src/group_digest.rs:88-143 (hash_from_bytes / encode_from_bytes / hash_to_scalar),
+# hash2curve/src/hash2field.rs + hash2field/expand_msg/xmd.rs (hash_to_field over expand_message_xmd),
+# primeorder/src/osswu.rs:60-146 (simplified SWU for q = 3 mod 4), k256/src/arithmetic/hash2curve.rs:52-148
+# (secp256k1: SSWU on the 3-isogenous curve E' + isogeny map, :169-258), p256/src/arithmetic/hash2curve.rs:44-75.
+H2C_SUITES = {
+    "k256": {"ro": b"secp256k1_XMD:SHA-256_SSWU_RO_", "nu": b"secp256k1_XMD:SHA-256_SSWU_NU_", "Z": -11,
+             "A": 0x3F8731ABDD661ADCA08A5558F0F5D272E953D363CB6F0E5D405447C01A444533, "B": 1771},
+    "p256": {"ro": b"P256_XMD:SHA-256_SSWU_RO_", "nu": b"P256_XMD:SHA-256_SSWU_NU_", "Z": -10, "A": -3, "B": P256.b},
+}
+# 3-isogeny E' -> secp256k1 (RFC 9380 appendix E.1; k256/src/arithmetic/hash2curve.rs:170-239), coefficients of x^0..x^3
+K256_ISO = {
+    "xnum": [0x8E38E38E38E38E38E38E38E38E38E38E38E38E38E38E38E38E38E38DAAAAA8C7, 0x07D3D4C80BC321D5B9F315CEA7FD44C5D595D2FC0BF63B92DFFF1044F17C6581,
+             0x534C328D23F234E6E2A413DECA25CAECE4506144037C40314ECBD0B53D9DD262, 0x8E38E38E38E38E38E38E38E38E38E38E38E38E38E38E38E38E38E38DAAAAA88C],
+    "xden": [0xD35771193D94918A9CA34CCBB7B640DD86CD409542F8487D9FE6B745781EB49B, 0xEDADC6F64383DC1DF7C4B2D51B54225406D36B641F5E41BBC52A56612A8C6D14, 1],
+    "ynum": [0x4BDA12F684BDA12F684BDA12F684BDA12F684BDA12F684BDA12F684B8E38E23C, 0xC75E0C32D5CB7C0FA9D0A54B12A0A6D5647AB046D686DA6FDFFC90FC201D71A3,
+             0x29A6194691F91A73715209EF6512E576722830A201BE2018A765E85A9ECEE931, 0x2F684BDA12F684BDA12F684BDA12F684BDA12F684BDA12F684BDA12F38E38D84],
+    "yden": [0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEFFFFF93B, 0x7A06534BB8BDB49FD5E9E6632722C2989467C1BFC8E8D978DFB425D2685C2573,
+             0x6484AA716545CA2CF3A70C3FA8FE337E0A3D21162F0D6299A7BF8192BFD2A76F, 1],
+}
+
+
+def expand_message_xmd(msg: bytes, dst: bytes, len_in_bytes: int) -> bytes:
+    """RFC 9380 section 5.3.1 with SHA-256 (hash2curve/src/hash2field/expand_msg/xmd.rs:43-99); oversize DSTs are hashed
+    first (expand_msg.rs:15,76-95)."""
+    if len(dst) > 255:
+        dst = hashlib.sha256(b"H2C-OVERSIZE-DST-" + dst).digest()
+    ell = (len_in_bytes + 31) // 32
+    assert 0 < len_in_bytes <= 65535 and ell <= 255
+    dst_prime = dst + bytes([len(dst)])
+    b0 = hashlib.sha256(bytes(64) + msg + len_in_bytes.to_bytes(2, "big") + b"\x00" + dst_prime).digest()
+    b = [hashlib.sha256(b0 + b"\x01" + dst_prime).digest()]
+    for i in range(2, ell + 1):
+        b.append(hashlib.sha256(bytes(x ^ y for x, y in zip(b0, b[-1])) + bytes([i]) + dst_prime).digest())
+    return b"".join(b)[:len_in_bytes]
+
+
+def hash_to_field(msg: bytes, dst: bytes, count: int, modulus: int, L: int = 48):
+    u = expand_message_xmd(msg, dst, count * L)
+    return [int.from_bytes(u[L * i:L * (i + 1)], "big") % modulus for i in range(count)]
+
+
+def _sqrt_3mod4(v: int, p: int):
+    r = pow(v, (p + 1) // 4, p)
+    return r if r * r % p == v % p else None
+
+
+def sswu(u: int, p: int, A: int, B: int, Z: int):
+    """simplified SWU, RFC 9380 section 6.6.2 (the definition; the reference's straight-line version gives the same point)"""
+    A, B, Z = A % p, B % p, Z % p
+    tv1 = (Z * Z % p * pow(u, 4, p) + Z * u * u) % p
+    if tv1 == 0:
+        x1 = B * pow(Z * A, -1, p) % p
+    else:
+        x1 = (-B) * pow(A, -1, p) % p * (1 + pow(tv1, -1, p)) % p
+    gx1 = (pow(x1, 3, p) + A * x1 + B) % p
+    x2 = Z * u * u % p * x1 % p
+    gx2 = (pow(x2, 3, p) + A * x2 + B) % p
+    y1 = _sqrt_3mod4(gx1, p)
+    if y1 is not None:
+        x, y = x1, y1
+    else:
+        x, y = x2, _sqrt_3mod4(gx2, p)
+    if (u & 1) != (y & 1):
+        y = p - y
+    return x, y
+
+
+def k256_iso_map(x: int, y: int):
+    p = K256.p
+    ev = lambda co: sum(c * pow(x, i, p) for i, c in enumerate(co)) % p  # noqa: E731
+    xd, yd = ev(K256_ISO["xden"]), ev(K256_ISO["yden"])
+    if xd == 0 or yd == 0:
+        return None
+    return ev(K256_ISO["xnum"]) * pow(xd, -1, p) % p, y * ev(K256_ISO["ynum"]) % p * pow(yd, -1, p) % p
+
+
+def map_to_curve(curve: str, u: int):
+    c = CURVES[curve]
+    s = H2C_SUITES[curve]
+    x, y = sswu(u, c.p, s["A"], s["B"], s["Z"])
+    return k256_iso_map(x, y) if curve == "k256" else (x, y)
+
+
+def hash_to_curve(curve: str, msg: bytes, dst: bytes):
+    """hash_from_bytes: two field elements, two maps, one addition (both curves have cofactor 1)"""
+    c = CURVES[curve]
+    u0, u1 = hash_to_field(msg, dst, 2, c.p)
+    return add(c, map_to_curve(curve, u0), map_to_curve(curve, u1))
+
+
+def encode_to_curve(curve: str, msg: bytes, dst: bytes):
+    c = CURVES[curve]
+    (u,) = hash_to_field(msg, dst, 1, c.p)
+    return map_to_curve(curve, u)
+
+
+def hash_to_scalar(curve: str, msg: bytes, dst: bytes) -> int:
+    return hash_to_field(msg, dst, 1, CURVES[curve].n)[0]

@@ -58,6 +58,7 @@ static inline uint2 __ldg(const uint2* p) { return *p; }
 #include "../../elliptic-curves_b200/csrc/ecg_verify.cuh"
 
 #include "../../elliptic-curves_b200/csrc/ecg_kernels.cuh"
+#include "../../elliptic-curves_b200/csrc/ecg_h2c.cuh"
 
 using namespace ecg;
 
@@ -804,4 +805,32 @@ extern "C" int simk_lincomb_k(int curve, size_t n, const uint8_t* k, const uint8
 extern "C" int simk_lincomb(int curve, size_t n, const uint8_t* k, const uint8_t* pxy, const uint8_t* pinf, size_t msm_min_terms,
                             uint8_t* out_xy, uint8_t* out_inf, uint32_t* status, int* path) {
   return simk_lincomb_k(curve, n, k, pxy, pinf, msm_min_terms, out_xy, out_inf, status, path, 1);
+}
+
+// ecg_hash_to_curve_batch / ecg_hash_to_scalar_batch: h2c_kernel (expand_message_xmd, SSWU, isogeny, addition) +
+// normalize_kernel, h2s_kernel.  dst_prime = DST || len(DST) as the host side of ecgpu.cu prepares it.
+extern "C" int simk_hash_to_curve(int curve, size_t n, const uint8_t* msgs, const uint64_t* offsets, const uint8_t* dst_prime,
+                                  uint32_t dpl, int nu, uint8_t* out_xy, uint8_t* out_inf) {
+  std::vector<uint32_t> jac(24 * n + 24);
+  if (curve == 0 && !nu)
+    sim_launch(n, 128, [&] { h2c_kernel<CurveK256, false>(msgs, offsets, 0, n, dst_prime, dpl, jac.data()); });
+  else if (curve == 0)
+    sim_launch(n, 128, [&] { h2c_kernel<CurveK256, true>(msgs, offsets, 0, n, dst_prime, dpl, jac.data()); });
+  else if (!nu)
+    sim_launch(n, 128, [&] { h2c_kernel<CurveP256, false>(msgs, offsets, 0, n, dst_prime, dpl, jac.data()); });
+  else
+    sim_launch(n, 128, [&] { h2c_kernel<CurveP256, true>(msgs, offsets, 0, n, dst_prime, dpl, jac.data()); });
+  if (curve == 0)
+    simk_normalize<CurveK256>(jac, n, out_xy, out_inf);
+  else
+    simk_normalize<CurveP256>(jac, n, out_xy, out_inf);
+  return 0;
+}
+extern "C" int simk_hash_to_scalar(int curve, size_t n, const uint8_t* msgs, const uint64_t* offsets, const uint8_t* dst_prime,
+                                   uint32_t dpl, uint8_t* out) {
+  if (curve == 0)
+    sim_launch(n, 128, [&] { h2s_kernel<CurveK256>(msgs, offsets, 0, n, dst_prime, dpl, out); });
+  else
+    sim_launch(n, 128, [&] { h2s_kernel<CurveP256>(msgs, offsets, 0, n, dst_prime, dpl, out); });
+  return 0;
 }
