@@ -9,6 +9,11 @@
 //   Engine::lincomb(points, scalars)                  <->  LinearCombination::lincomb          (mul.rs:66-109)
 //   Engine::mul_by_generator_and_mul_add_vartime(...) <->  MulByGeneratorVartime::...          (mul.rs:303-310)
 //   Engine::batch_normalize(jacobian)                 <->  BatchNormalize::batch_normalize     (projective.rs:345-365)
+//   Engine::hash_to_curve / encode_to_curve / hash_to_scalar <-> GroupDigest::hash_from_bytes / encode_from_bytes,
+//                                                         hash2curve::hash_to_scalar (hash2curve/src/group_digest.rs:88-143)
+// The typed surface below is for the 256-bit curves with big-endian records (secp256k1, P-256, sm2, brainpoolP256r1/t1);
+// the other curves of include/ecgpu.h (48 / 28 / 24-byte records, bign's little-endian records) are reached through the
+// C ABI directly or the Python mirror, which sizes its buffers per curve.
 // Fallible decoding mirrors CtOption/Result: out-of-range scalars / off-curve points throw DecodeError carrying the
 // index of the first offender; arithmetic itself is total.
 #pragma once
@@ -191,6 +196,37 @@ class Engine {
     std::vector<AffinePoint> p = mul_by_generator(secret);
     std::vector<Sec1Compressed> r(p.size());
     for (size_t i = 0; i < p.size(); i++) r[i] = compress(p[i]);
+    return r;
+  }
+
+  // GroupDigest::hash_from_bytes (nonuniform = false) / encode_from_bytes (true) over a batch of messages, RFC 9380 with
+  // expand_message_xmd<SHA-256> (hash2curve/src/group_digest.rs:88-118; suites of k256 / p256 arithmetic/hash2curve.rs)
+  std::vector<AffinePoint> hash_to_curve(const std::vector<std::string>& msgs, const std::string& dst, bool nonuniform = false) {
+    size_t n = msgs.size();
+    std::vector<uint64_t> offs(n + 1, 0);
+    std::string all;
+    for (size_t i = 0; i < n; i++) {
+      all += msgs[i];
+      offs[i + 1] = all.size();
+    }
+    std::vector<uint8_t> out(64 * n), oinf(n);
+    check(ecg_hash_to_curve_batch(ctx_, curve_, n, reinterpret_cast<const uint8_t*>(all.data()), offs.data(),
+                                  reinterpret_cast<const uint8_t*>(dst.data()), dst.size(), nonuniform ? 1 : 0, out.data(), oinf.data()));
+    return unpack(out, oinf);
+  }
+  std::vector<AffinePoint> encode_to_curve(const std::vector<std::string>& msgs, const std::string& dst) { return hash_to_curve(msgs, dst, true); }
+  // hash2curve::hash_to_scalar over a batch (group_digest.rs:131-143, L = 48)
+  std::vector<Scalar> hash_to_scalar(const std::vector<std::string>& msgs, const std::string& dst) {
+    size_t n = msgs.size();
+    std::vector<uint64_t> offs(n + 1, 0);
+    std::string all;
+    for (size_t i = 0; i < n; i++) {
+      all += msgs[i];
+      offs[i + 1] = all.size();
+    }
+    std::vector<Scalar> r(n);
+    check(ecg_hash_to_scalar_batch(ctx_, curve_, n, reinterpret_cast<const uint8_t*>(all.data()), offs.data(),
+                                   reinterpret_cast<const uint8_t*>(dst.data()), dst.size(), reinterpret_cast<uint8_t*>(r.data())));
     return r;
   }
 

@@ -62,6 +62,13 @@ unsafe extern "C" {
     pub fn ecg_batch_normalize_hom(ctx: *mut ecg_ctx, curve: i32, n: usize, xyz: *const u8, out_xy: *mut u8, out_inf: *mut u8) -> i32;
     /// `FieldElement::{add, sub, neg, mul, square, invert}` (field.rs:116-196)
     pub fn ecg_field_op_batch(ctx: *mut ecg_ctx, curve: i32, op: i32, n: usize, a: *const u8, b: *const u8, out: *mut u8) -> i32;
+    /// `GroupDigest::hash_from_bytes` / `encode_from_bytes` over a batch (hash2curve/src/group_digest.rs:88-118):
+    /// message i = msgs[offsets[i]..offsets[i+1]], n + 1 offsets; secp256k1 / P-256 XMD:SHA-256 SSWU suites
+    pub fn ecg_hash_to_curve_batch(ctx: *mut ecg_ctx, curve: i32, n: usize, msgs: *const u8, offsets: *const u64, dst: *const u8,
+                                   dst_len: usize, nonuniform: i32, out_xy: *mut u8, out_inf: *mut u8) -> i32;
+    /// `hash2curve::hash_to_scalar` over a batch (group_digest.rs:131-143)
+    pub fn ecg_hash_to_scalar_batch(ctx: *mut ecg_ctx, curve: i32, n: usize, msgs: *const u8, offsets: *const u64, dst: *const u8,
+                                    dst_len: usize, out: *mut u8) -> i32;
     /// `FieldElement::sqrt` (field.rs:200-235)
     pub fn ecg_field_sqrt_batch(ctx: *mut ecg_ctx, curve: i32, n: usize, a: *const u8, out: *mut u8, is_square: *mut u8) -> i32;
     /// `schnorr::VerifyingKey::verify_raw` over a batch (schnorr/verifying.rs:76-99)
@@ -219,6 +226,43 @@ impl GpuEngine {
         // SAFETY: as above.
         let rc = unsafe { ecg_field_sqrt_batch(self.ctx, self.curve, n, a.as_ptr().cast(), out.as_mut_ptr().cast(), ok.as_mut_ptr()) };
         self.check(rc).map(|_| out.into_iter().zip(ok).map(|(r, o)| if o != 0 { Some(r) } else { None }).collect())
+    }
+
+    /// `GroupDigest::hash_from_bytes` (`nonuniform = false`) / `encode_from_bytes` (`true`) for a batch of messages.
+    pub fn hash_to_curve_batch(&mut self, msgs: &[&[u8]], dst: &[u8], nonuniform: bool) -> Result<(Vec<[u8; 64]>, Vec<u8>), GpuError> {
+        let n = msgs.len();
+        let mut offsets = Vec::with_capacity(n + 1);
+        let mut data = Vec::new();
+        offsets.push(0u64);
+        for m in msgs {
+            data.extend_from_slice(m);
+            offsets.push(data.len() as u64);
+        }
+        let (mut out_xy, mut out_inf) = (vec![[0u8; 64]; n], vec![0u8; n]);
+        // SAFETY: `data` holds offsets[n] bytes, `offsets` n + 1 values, the outputs n records; all outlive the call.
+        let rc = unsafe {
+            ecg_hash_to_curve_batch(self.ctx, self.curve, n, data.as_ptr(), offsets.as_ptr(), dst.as_ptr(), dst.len(), nonuniform as i32,
+                                    out_xy.as_mut_ptr().cast(), out_inf.as_mut_ptr())
+        };
+        self.check(rc).map(|_| (out_xy, out_inf))
+    }
+
+    /// `hash2curve::hash_to_scalar` for a batch of messages: big-endian scalars below the group order.
+    pub fn hash_to_scalar_batch(&mut self, msgs: &[&[u8]], dst: &[u8]) -> Result<Vec<Bytes32>, GpuError> {
+        let n = msgs.len();
+        let mut offsets = Vec::with_capacity(n + 1);
+        let mut data = Vec::new();
+        offsets.push(0u64);
+        for m in msgs {
+            data.extend_from_slice(m);
+            offsets.push(data.len() as u64);
+        }
+        let mut out = vec![[0u8; 32]; n];
+        // SAFETY: as above.
+        let rc = unsafe {
+            ecg_hash_to_scalar_batch(self.ctx, self.curve, n, data.as_ptr(), offsets.as_ptr(), dst.as_ptr(), dst.len(), out.as_mut_ptr().cast())
+        };
+        self.check(rc).map(|_| out)
     }
 
     /// BIP340 batch verification: one bool per (key, message, signature).  secp256k1 only.

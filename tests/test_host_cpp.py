@@ -107,6 +107,13 @@ static int run(ecg_curve curve, const char** v) {
   threw = false;
   try { eng.mul({G, bad}, {one[0], one[0]}); } catch (const DecodeError& e) { threw = e.code == ECG_ENOT_ON_CURVE && e.index == 1; }
   REQUIRE(threw);
+  // hash to curve: the reference's RFC 9380 vector for msg "abc" (v[17] DST, v[18..19] P), encode_to_curve lands on the curve too
+  auto hp = eng.hash_to_curve({std::string("abc"), std::string("")}, v[17]);
+  REQUIRE(same(hp[0], pt(v[18], v[19])) && !hp[1].infinity);
+  auto ep = eng.encode_to_curve({std::string("abc")}, v[17]);
+  REQUIRE(!ep[0].infinity && same(eng.mul({ep[0]}, one)[0], ep[0]));   // mul validates: the point is on the curve
+  auto hs = eng.hash_to_scalar({std::string("abc")}, v[17]);
+  REQUIRE(hs[0] == h32(v[20]));
   REQUIRE(eng.kernel_launches() > 20);
   return 0;
 }
@@ -152,7 +159,11 @@ def _curve_values(c):
     root = pow(sq_in, (p + 1) // 4, p)
     non = next(x for x in range(2, 50) if pow(x, (p - 1) // 2, p) != 1)
     vals = [G[0], G[1], G5[0], G5[1], *jac, *hom, c.n, a, b, ab[0], sq_in, root, non]
-    return ", ".join('"%s"' % _h(v) for v in vals)
+    h2c = json.load(open(os.path.join(ROOT, "tests", "golden", "h2c.json")))["suites"][c.name]
+    vec = next(v for v in h2c["vectors"] if v["msg"] == "abc")
+    hs = pyref.hash_to_scalar(c.name, b"abc", h2c["dst"].encode())
+    tail = ['"%s"' % h2c["dst"], '"%s"' % vec["p_x"], '"%s"' % vec["p_y"], '"%s"' % _h(hs)]
+    return ", ".join(['"%s"' % _h(v) for v in vals] + tail)
 
 
 def _full_source():
