@@ -825,7 +825,7 @@ def measure_more_curves(B, steps):
     all_ok = True
     for cid, c in sorted(pyref.EXT_CURVES.items()):
         nb = pyref.fbytes(c)
-        nl = nb // 4
+        nl = (nb + 3) // 4
         rng = np.random.default_rng(0xB2000100 + 16 * cid + rank)
         msb = nb - 1 if c.le else 0
         top = c.n >> (8 * (nb - 1))
@@ -896,7 +896,7 @@ def measure_more_curves(B, steps):
         return None
     return {"metric": "scalar-mults/s (variable base, per curve)", "unit": "scalar-mults/s", "n_gpus": world, "steps": steps,
             "config": {"workload": "widening step (SURVEY 8(f) rank 4, not a BASELINE config): sm2, brainpoolP256r1/t1, bign-curve256v1, "
-                                   "brainpoolP384r1/t1, P-224, P-192 variable base, batch 2^16 per GPU and curve, kernel time by CUDA events "
+                                   "brainpoolP384r1/t1, P-224, P-192, P-521 variable base, batch 2^16 per GPU and curve, kernel time by CUDA events "
                                    "(ecg_timing), L2 flushed between steps", "batch_per_gpu": n},
             "curves": out, "bit_exact": all_ok,
             "bit_exact_coverage": f"every output of every rank and curve vs oracle/ecref_prime.c ({world * n} units per curve); the oracle is "

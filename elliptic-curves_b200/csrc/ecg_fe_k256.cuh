@@ -28,6 +28,7 @@ template <int OPT>
 struct FpK256T {
   static constexpr int NL = 8;  // 32-bit limbs per field element
   static constexpr bool LE = false;  // canonical records are big-endian
+  static constexpr int FB = 32;       // bytes per canonical record
   typedef FeN<8> FeT;
   typedef JacN<8> JacT;
   typedef AffN<8> AffT;

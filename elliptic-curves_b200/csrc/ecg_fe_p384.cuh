@@ -28,6 +28,7 @@ template <int OPT>
 struct FpP384T {
   static constexpr int NL = 12;
   static constexpr bool LE = false;  // canonical records are big-endian
+  static constexpr int FB = 48;       // bytes per canonical record
   typedef FeN<12> FeT;
   typedef JacN<12> JacT;
   typedef AffN<12> AffT;

@@ -35,16 +35,45 @@ ECG_D void store_le(uint8_t* p, const uint32_t* limbs) {
 }
 // one canonical record (field element or scalar) of the curve whose field policy is F, in the byte order the
 // reference uses for that curve
+// records whose length is not 4 NL (P-521: 66 big-endian bytes in 17 limbs) are not word-aligned: byte accesses
+template <int NL, int FB>
+ECG_D void load_be_bytes(uint32_t* limbs, const uint8_t* p) {
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int pos = FB - 1 - (4 * i + j);  // byte of weight 256^(4 i + j)
+      if (pos >= 0) v |= (uint32_t)p[pos] << (8 * j);
+    }
+    limbs[i] = v;
+  }
+}
+template <int NL, int FB>
+ECG_D void store_be_bytes(uint8_t* p, const uint32_t* limbs) {
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int pos = FB - 1 - (4 * i + j);
+      if (pos >= 0) p[pos] = (uint8_t)(limbs[i] >> (8 * j));
+    }
+  }
+}
 template <class F>
 ECG_D void load_fe(uint32_t* limbs, const uint8_t* p) {
-  if (F::LE)
+  if (F::FB != 4 * F::NL)
+    load_be_bytes<F::NL, F::FB>(limbs, p);
+  else if (F::LE)
     load_le<F::NL>(limbs, p);
   else
     load_be<F::NL>(limbs, p);
 }
 template <class F>
 ECG_D void store_fe(uint8_t* p, const uint32_t* limbs) {
-  if (F::LE)
+  if (F::FB != 4 * F::NL)
+    store_be_bytes<F::NL, F::FB>(p, limbs);
+  else if (F::LE)
     store_le<F::NL>(p, limbs);
   else
     store_be<F::NL>(p, limbs);

@@ -51,7 +51,7 @@ ECG_DEV uint32_t load_pair(uint32_t* k, typename C::F::AffT& P, bool& inf, const
                                               const uint8_t* pxy, const uint8_t* pinf, size_t idx) {
   typedef typename C::F F;
   typedef typename F::FeT Fe;
-  constexpr int NL = F::NL, FB = 4 * F::NL;  // limbs and bytes per field element / scalar
+  constexpr int NL = F::NL, FB = F::FB;  // limbs and bytes per field element / scalar
   uint32_t err = 0;
   load_fe<F>(k, kb + FB * idx);
   if (!ltN<NL>(k, C::N())) err |= ERRF_SCALAR;
@@ -209,7 +209,7 @@ ECG_KERNEL(128, 4)
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   uint32_t k[NL];
-  load_fe<F>(k, kb + 4 * NL * idx);
+  load_fe<F>(k, kb + F::FB * idx);
   bool bad = !ltN<NL>(k, C::N());
   if (bad) {
     report_error(status, ERRF_SCALAR, base + idx);
@@ -484,7 +484,7 @@ template <class C>
 ECG_KERNEL(256)
     affine_to_table_kernel(const uint8_t* __restrict__ xy, size_t n, uint32_t* __restrict__ table) {
   typedef typename C::F F;
-  constexpr int NL = F::NL, FB = 4 * F::NL;
+  constexpr int NL = F::NL, FB = F::FB;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   typename F::FeT x, y;
@@ -529,7 +529,7 @@ template <class C>
 ECG_KERNEL(128)
     export_jac_kernel(const uint32_t* __restrict__ jac, size_t n, uint8_t* __restrict__ xyz) {
   typedef typename C::F F;
-  constexpr int NL = F::NL, FB = 4 * F::NL;
+  constexpr int NL = F::NL, FB = F::FB;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
 #pragma unroll 1
@@ -553,7 +553,7 @@ ECG_KERNEL(256)
     normalize_kernel(const uint32_t* __restrict__ jac, size_t n, uint32_t* __restrict__ scr,
                      uint8_t* __restrict__ out_xy, uint8_t* __restrict__ out_inf) {
   typedef typename F::FeT Fe;
-  constexpr int NL = F::NL, FB = 4 * F::NL;
+  constexpr int NL = F::NL, FB = F::FB;
   size_t T = (size_t)gridDim.x * blockDim.x;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
@@ -615,7 +615,7 @@ ECG_KERNEL(256)
                       uint32_t* __restrict__ status, size_t base) {
   typedef typename C::F F;
   typedef typename F::FeT Fe;
-  constexpr int NL = F::NL, FB = 4 * F::NL;
+  constexpr int NL = F::NL, FB = F::FB;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   Fe co[3];
@@ -668,7 +668,7 @@ ECG_KERNEL(256)
     field_op_kernel(int op, size_t n, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
                     uint8_t* __restrict__ out, uint32_t* __restrict__ status, size_t base) {
   typedef typename C::F F;
-  constexpr int NL = F::NL, FB = 4 * F::NL;
+  constexpr int NL = F::NL, FB = F::FB;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   typename F::FeT x, y, r;

@@ -68,7 +68,7 @@ ECG_KERNEL(128)
                     uint32_t* __restrict__ count, uint32_t* __restrict__ status, size_t base) {
   typedef typename C::F F;
   typedef typename F::FeT Fe;
-  constexpr int NL = F::NL, FB = 4 * F::NL;
+  constexpr int NL = F::NL, FB = F::FB;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const size_t nsub = GLV ? 2 * n : n;

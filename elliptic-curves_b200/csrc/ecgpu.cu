@@ -15,7 +15,7 @@
 // the headline curves keep their own translation unit:
 //   ECG_TU 0: secp256k1, P-256, P-384 + every extern "C" entry (entries for other curves forward to their group)
 //   ECG_TU 1: sm2, brainpoolP256r1/t1, bign-curve256v1 (8 limbs)   ECG_TU 2: brainpoolP384r1/t1 (12 limbs)
-//   ECG_TU 3: P-224 (7 limbs), P-192 (6 limbs)
+//   ECG_TU 3: P-224 (7 limbs), P-192 (6 limbs)                    ECG_TU 4: P-521 (17 limbs, 66-byte records)
 // The groups 1-3 run the generic kernels over the generic Montgomery field policy (ecg_fe_mont.cuh).
 #ifndef ECG_TU
 #define ECG_TU 0
@@ -29,8 +29,8 @@
 #endif
 #include "ecg_msm.cuh"
 
-#define ECG_CURVE_COUNT 11
-static inline int curve_group(int c) { return c <= 2 ? 0 : c <= 6 ? 1 : c <= 8 ? 2 : 3; }
+#define ECG_CURVE_COUNT 12
+static inline int curve_group(int c) { return c <= 2 ? 0 : c <= 6 ? 1 : c <= 8 ? 2 : c <= 10 ? 3 : 4; }
 // an entry point: extern "C" in group 0, an internal (hidden) function ecg_tuN_<name> in the other groups
 #define ECG_CAT2(a, b) a##b
 #define ECG_CAT(a, b) ECG_CAT2(a, b)
@@ -58,7 +58,7 @@ struct Lane {
   void* buf[B_COUNT] = {nullptr};
   size_t cap[B_COUNT] = {0};
   uint32_t* status = nullptr;    // 2 words: error flags, smallest offending index
-  uint32_t* h_status = nullptr;  // pinned: 2 status words, then up to 144 bytes for one exported point (h_point())
+  uint32_t* h_status = nullptr;  // pinned: 2 status words, then up to 256 bytes for one exported point (h_point())
   std::vector<cudaEvent_t> evs;  // event pairs bracketing the dominant kernel of every chunk of the current call (ecg_timing)
   size_t ev_used = 0;            // events of `evs` recorded by the current call (2 per chunk)
   bool used = false;  // touched by the current call
@@ -161,7 +161,7 @@ extern "C" ecg_status ecg_ctx_create(const int* device_ids, int n_devices, unsig
     for (int l = 0; ok && l < 2; l++) {
       Lane& L = d.lane[l];
       ok = cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) == cudaSuccess &&
-           cudaMalloc((void**)&L.status, 8) == cudaSuccess && cudaMallocHost((void**)&L.h_status, 8 + 144) == cudaSuccess;
+           cudaMalloc((void**)&L.status, 8) == cudaSuccess && cudaMallocHost((void**)&L.h_status, 8 + 256) == cudaSuccess;
     }
     if (!ok) {
       ecg_ctx_destroy(ctx);
@@ -378,10 +378,21 @@ static inline size_t flimbs(ecg_curve c) {
     case ECG_NISTP384: case ECG_BP384R1: case ECG_BP384T1: return 12;
     case ECG_NISTP224: return 7;
     case ECG_NISTP192: return 6;
+    case ECG_NISTP521: return 17;
     default: return 8;
   }
 }
-static inline size_t fbytes(ecg_curve c) { return 4 * flimbs(c); }
+// bytes per canonical record at the ABI: 4 per limb, except P-521 (66 bytes in 17 limbs); bytes of one Jacobian point in
+// the internal SoA form (three NL-word coordinates)
+static inline size_t fbytes(ecg_curve c) { return c == ECG_NISTP521 ? 66 : 4 * flimbs(c); }
+static inline size_t jbytes(ecg_curve c) { return 12 * flimbs(c); }
+static inline bool curve_le(ecg_curve c) { return c == ECG_BIGNP256; }
+// (0 : 1 : 0) as three canonical records in the curve's byte order
+static void identity_xyz(uint8_t* z, ecg_curve c) {
+  const size_t fb = fbytes(c);
+  memset(z, 0, 3 * fb);
+  z[curve_le(c) ? fb : 2 * fb - 1] = 1;
+}
 // ECG_INLINE_LOOPS=0 (environment) keeps the call-based field operations in the one-point-operation-per-iteration
 // kernels (fixed-base, bucket accumulation): measurement knob, default = inlined
 static bool inline_loops() {
@@ -450,7 +461,7 @@ static bool inline_loops() {
     }                                     \
   } while (0)
 #define FOR_CURVE_INL FOR_CURVE
-#else
+#elif ECG_TU == 3
 #define FOR_CURVE(curve, ...)             \
   do {                                    \
     if ((curve) == ECG_NISTP224) {        \
@@ -460,6 +471,13 @@ static bool inline_loops() {
       typedef CurveP192 CV;               \
       __VA_ARGS__;                        \
     }                                     \
+  } while (0)
+#define FOR_CURVE_INL FOR_CURVE
+#else
+#define FOR_CURVE(curve, ...) \
+  do {                        \
+    typedef CurveP521 CV;     \
+    __VA_ARGS__;              \
   } while (0)
 #define FOR_CURVE_INL FOR_CURVE
 #endif
@@ -495,11 +513,11 @@ static const int Q_BLOCK = 128, Q_MINBLK = 3;  // P-384   : 12-limb values, <= 1
 static const int X_BLOCK = 128;
 template <int NL>
 struct XGeom {
-  static constexpr int MINBLK = NL > 8 ? 3 : 4;
+  static constexpr int MINBLK = NL > 12 ? 2 : NL > 8 ? 3 : 4;
 };
 static size_t vb_block(ecg_curve c) { return c == ECG_SECP256K1 ? K_BLOCK : c == ECG_NISTP256 ? P_BLOCK : c == ECG_NISTP384 ? Q_BLOCK : X_BLOCK; }
 static size_t vb_minblk(ecg_curve c) {
-  return c == ECG_SECP256K1 ? K_MINBLK : c == ECG_NISTP256 ? P_MINBLK : c == ECG_NISTP384 ? Q_MINBLK : (flimbs(c) > 8 ? 3 : 4);
+  return c == ECG_SECP256K1 ? K_MINBLK : c == ECG_NISTP256 ? P_MINBLK : c == ECG_NISTP384 ? Q_MINBLK : (flimbs(c) > 12 ? 2 : flimbs(c) > 8 ? 3 : 4);
 }
 static size_t vb_tab_words(ecg_curve c) { return c == ECG_SECP256K1 ? K_TAB_WORDS : 8 * 3 * flimbs(c); }
 
@@ -543,40 +561,43 @@ static bool curve_256(ecg_curve c) { return c == ECG_SECP256K1 || c == ECG_NISTP
 
 // ---- fixed-base table ------------------------------------------------------------------------------
 // Built on the device with the variable-base kernel itself: entry (i, j) = ((2j+1) << 16 i mod n) * G.
-// record (curve byte order) of (odd << shift_bits) mod n; the value is below 2^(32 nl + 1) and n above 2^(32 nl - 1)
-static void scalar_rec_from_shifted(uint8_t* out, uint64_t odd, int shift_bits, const uint32_t* n_le, int nl, bool le) {
-  uint32_t v[15] = {0};
-  int w = shift_bits / 32, b = shift_bits % 32;
-  uint64_t lo = odd << b;  // odd < 2^17, b < 32
-  v[w] = (uint32_t)lo;
-  v[w + 1] = (uint32_t)(lo >> 32);
-  uint32_t nn[14] = {0};
-  for (int i = 0; i < nl; i++) nn[i] = n_le[i];
-  for (;;) {
+// Scalars of the fixed-base table entries, (2j + 1) 2^(16 i) mod n, as records in the curve's byte order.  Built by modular
+// additions (B_i = 2^(16 i) mod n by doubling; entry j + 1 = entry j + 2 B_i), so that any group order below 2^(32 nl)
+// works, however far below (P-521: n < 2^521 in 544-bit limbs).
+struct HostMod {
+  int nl;
+  uint32_t n[19];
+  void add(uint32_t* r, const uint32_t* a, const uint32_t* b) const {  // r = a + b mod n, inputs < n
+    uint32_t t[19];
+    uint64_t c = 0;
+    for (int i = 0; i <= nl; i++) {
+      c += (uint64_t)(i < nl ? a[i] : 0) + (i < nl ? b[i] : 0);
+      t[i] = (uint32_t)c;
+      c >>= 32;
+    }
     bool ge = true;
-    for (int i = nl; i >= 0; i--) {
-      if (v[i] != nn[i]) {
-        ge = v[i] > nn[i];
+    for (int i = nl; i >= 0; i--)
+      if (t[i] != n[i]) {
+        ge = t[i] > n[i];
         break;
       }
+    if (ge) {
+      uint64_t bw = 0;
+      for (int i = 0; i <= nl; i++) {
+        uint64_t d = (uint64_t)t[i] - n[i] - bw;
+        t[i] = (uint32_t)d;
+        bw = (d >> 63) & 1;
+      }
     }
-    if (!ge) break;
-    uint64_t borrow = 0;
-    for (int i = 0; i <= nl; i++) {
-      uint64_t t = (uint64_t)v[i] - nn[i] - borrow;
-      v[i] = (uint32_t)t;
-      borrow = (t >> 63) & 1;
-    }
+    for (int i = 0; i < nl; i++) r[i] = t[i];
   }
-  const int nb = 4 * nl;
-  for (int i = 0; i < nl; i++)
-    for (int j = 0; j < 4; j++) {
-      uint8_t byte = (uint8_t)(v[i] >> (8 * j));
-      if (le)
-        out[4 * i + j] = byte;
-      else
-        out[nb - 1 - 4 * i - j] = byte;
-    }
+};
+static void scalar_record(uint8_t* out, const uint32_t* v, int nl, size_t fb, bool le) {
+  for (size_t byte = 0; byte < fb; byte++) {
+    uint8_t b = (uint8_t)(v[byte >> 2] >> (8 * (byte & 3)));  // byte of weight 256^byte
+    out[le ? byte : fb - 1 - byte] = b;
+  }
+  (void)nl;
 }
 static const uint32_t H_K256_N[8] = {0xD0364141u, 0xBFD25E8Cu, 0xAF48A03Bu, 0xBAAEDCE6u, 0xFFFFFFFEu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
 static const uint32_t H_P256_N[8] = {0xFC632551u, 0xF3B9CAC2u, 0xA7179E84u, 0xBCE6FAADu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x00000000u, 0xFFFFFFFFu};
@@ -617,9 +638,26 @@ static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
       g = ECG_EXT_CURVES[e].g;
       le = ECG_EXT_CURVES[e].le != 0;
     }
-  for (int i = 0; i < nwin; i++)
-    for (uint32_t j = 0; j < FB_ENTRIES; j++) scalar_rec_from_shifted(&hk[((size_t)i * FB_ENTRIES + j) * fb], 2ull * j + 1, FB_W * i, n_le, nl, le);
-  scalar_rec_from_shifted(&hk[(np - 1) * fb], 1, 32 * nl, n_le, nl, le);  // 2^(32 nl) mod n
+  {
+    HostMod M;
+    M.nl = nl;
+    memset(M.n, 0, sizeof M.n);
+    for (int i = 0; i < nl; i++) M.n[i] = n_le[i];
+    uint32_t Bi[19] = {1}, B2[19], cur[19];  // B_i = 2^(16 i) mod n
+    for (int i = 0; i <= nwin; i++) {
+      if (i == nwin) {  // the implicit top digit: 2^(16 nwin) = 2^(32 nl) mod n
+        scalar_record(&hk[(np - 1) * fb], Bi, nl, fb, le);
+        break;
+      }
+      M.add(B2, Bi, Bi);
+      memcpy(cur, Bi, sizeof cur);
+      for (uint32_t j = 0; j < FB_ENTRIES; j++) {
+        scalar_record(&hk[((size_t)i * FB_ENTRIES + j) * fb], cur, nl, fb, le);
+        M.add(cur, cur, B2);
+      }
+      for (int d = 0; d < FB_W; d++) M.add(Bi, Bi, Bi);
+    }
+  }
   for (size_t i = 0; i < FB_PIECE; i++) memcpy(&hp[i * 2 * fb], g, 2 * fb);
   // temporaries are released on every exit path; `table` is released unless it is handed to the DevState
   struct Scratch {
@@ -633,9 +671,9 @@ static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
   CU_TRY(ctx, cudaMalloc(&tmp.p[1], FB_PIECE * 2 * fb));
   CU_TRY(ctx, cudaMalloc(&tmp.p[2], FB_PIECE * 2 * fb));
   CU_TRY(ctx, cudaMalloc(&tmp.p[3], FB_PIECE));
-  CU_TRY(ctx, cudaMalloc(&tmp.p[4], FB_PIECE * 3 * fb));
-  CU_TRY(ctx, cudaMalloc(&tmp.p[5], FB_PIECE * fb));
-  CU_TRY(ctx, cudaMalloc(&tmp.p[6], np * 2 * fb));
+  CU_TRY(ctx, cudaMalloc(&tmp.p[4], FB_PIECE * 12 * (size_t)nl));  // Jacobian SoA, NL words per coordinate
+  CU_TRY(ctx, cudaMalloc(&tmp.p[5], FB_PIECE * 4 * (size_t)nl));   // inversion scratch
+  CU_TRY(ctx, cudaMalloc(&tmp.p[6], np * 8 * (size_t)nl));         // the table: x, y in internal form
   CU_TRY(ctx, cudaMalloc(&tmp.p[7], 8));  // private status: building the table must not disturb a caller's validation state
   uint8_t *dk = (uint8_t*)tmp.p[0], *dpnt = (uint8_t*)tmp.p[1], *dxy = (uint8_t*)tmp.p[2], *dinf = (uint8_t*)tmp.p[3];
   uint32_t *jac = (uint32_t*)tmp.p[4], *scr = (uint32_t*)tmp.p[5], *table = (uint32_t*)tmp.p[6], *st = (uint32_t*)tmp.p[7];
@@ -769,7 +807,7 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
 #endif
   uint32_t* jac = nullptr;
   if (op.kind != BatchOp::FIELD) {
-    ST_TRY(ensure(ctx, L, B_JAC, cnt * 3 * fbytes(op.curve)));
+    ST_TRY(ensure(ctx, L, B_JAC, cnt * jbytes(op.curve)));
     jac = (uint32_t*)L.buf[B_JAC];
   }
   switch (op.kind) {
@@ -919,6 +957,15 @@ __attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_field_op_batch(ecg_
 __attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_lincomb_partial(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xyz);
 __attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_point_sum(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* xyz, uint8_t* out_xy, uint8_t* out_inf);
 __attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_lincomb(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_mul_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_mul_gen_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_batch_normalize(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_batch_normalize_hom(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_mul_batch_x(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_x, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_field_op_batch(ecg_ctx* ctx, ecg_curve curve, int fop, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_lincomb_partial(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xyz);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_point_sum(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* xyz, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_lincomb(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
 #define ECG_FORWARD(name, ...)                                     \
   do {                                                             \
     if ((int)curve >= 0 && (int)curve < ECG_CURVE_COUNT) {         \
@@ -926,6 +973,7 @@ __attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_lincomb(ecg_ctx* ct
         case 1: return ecg_tu1_##name(__VA_ARGS__);                \
         case 2: return ecg_tu2_##name(__VA_ARGS__);                \
         case 3: return ecg_tu3_##name(__VA_ARGS__);                \
+        case 4: return ecg_tu4_##name(__VA_ARGS__);                \
         default: break;                                            \
       }                                                            \
     }                                                              \
@@ -1200,6 +1248,7 @@ static MsmGeom msm_geometry(ecg_curve curve, size_t n) {
   while (((size_t)1 << (lg + 1)) <= nsub) lg++;
   g.c = std::min(16, std::max(8, lg - 5));
   g.nbits = glv ? 128 : (int)(32 * flimbs(curve));
+  while ((g.nbits + g.c - 1) / g.c > MSM_FINAL_THREADS) g.c++;  // msm_final_kernel: one thread per window (P-521: 544 bits -> c >= 9)
   g.W = (g.nbits + g.c - 1) / g.c;
   g.nbw = ((uint32_t)1 << (g.c + 1)) + 2;
   return g;
@@ -1339,7 +1388,7 @@ static ecg_status lincomb_shard(ecg_ctx* ctx, DevState& d, ecg_curve curve, cons
                                 const uint8_t* P_xy, const uint8_t* P_inf, bool per_term, uint32_t** result) {
   Lane& L = d.lane[0];
   DevPtrs dp;
-  const size_t fb = fbytes(curve), pt = 3 * fb;  // bytes per scalar / per Jacobian point
+  const size_t fb = fbytes(curve), pt = jbytes(curve);  // bytes per scalar record / per Jacobian point in the internal SoA form
   ST_TRY(begin_lane(ctx, L));
   ST_TRY(stage_in(ctx, L, B_K, k, sh.off, sh.cnt, fb, &dp.k));
   ST_TRY(stage_in(ctx, L, B_P, P_xy, sh.off, sh.cnt, 2 * fb, &dp.p));
@@ -1448,9 +1497,8 @@ ECG_API(ecg_lincomb_partial)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint
   CU_TRY(ctx, cudaSetDevice(d.dev));
   if (n == 0) {  // empty sum = identity (0 : 1 : 0)
     const size_t fb = fbytes(curve);
-    uint8_t z[144];
-    memset(z, 0, sizeof z);
-    z[2 * fb - 1] = 1;
+    uint8_t z[208];
+    identity_xyz(z, curve);
     if (ctx->devptr())
       CU_TRY(ctx, cudaMemcpy(out_xyz, z, 3 * fb, cudaMemcpyHostToDevice));
     else
@@ -1475,14 +1523,14 @@ static ecg_status point_sum_enqueue(ecg_ctx* ctx, ecg_curve curve, size_t m, con
   DevState& d = ctx->devs[0];
   Lane& L = d.lane[0];
   CU_TRY(ctx, cudaSetDevice(d.dev));
-  const size_t fb = fbytes(curve), pt = 3 * fb;
+  const size_t fb = fbytes(curve), pt = jbytes(curve), rec = 3 * fb;  // internal SoA point / X||Y||Z record at the ABI
   ST_TRY(begin_lane(ctx, L));
   ST_TRY(ensure(ctx, L, B_JAC, m * pt + pt));
   ST_TRY(ensure(ctx, L, B_JAC2, ((m + 31) / 32) * pt + pt));
   const uint8_t* dxyz = xyz;
   if (xyz_on_host) {
-    ST_TRY(ensure(ctx, L, B_AUX, m * pt + 256));
-    CU_TRY(ctx, cudaMemcpyAsync(L.buf[B_AUX], xyz, m * pt, cudaMemcpyHostToDevice, L.s()));
+    ST_TRY(ensure(ctx, L, B_AUX, m * rec + 256));
+    CU_TRY(ctx, cudaMemcpyAsync(L.buf[B_AUX], xyz, m * rec, cudaMemcpyHostToDevice, L.s()));
     dxyz = (const uint8_t*)L.buf[B_AUX];
   }
   uint32_t* jac = (uint32_t*)L.buf[B_JAC];
@@ -1506,7 +1554,7 @@ ECG_API(ecg_point_sum)(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* x
     return ECG_EINVAL;
   }
   if (m == 0) {
-    uint8_t z[97];
+    uint8_t z[137];
     memset(z, 0, sizeof z);
     if (ctx->devptr()) {
       CU_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
@@ -1556,8 +1604,7 @@ static ecg_status lincomb_attempt(ecg_ctx* ctx, ecg_curve curve, size_t n, const
   if (ctx->skew) return ECG_OK;  // the caller repeats per term
   for (size_t i = 0; i < nd; i++) {
     const size_t pt = 3 * fbytes(curve);
-    memset(&partial[i * pt], 0, pt);
-    partial[i * pt + 2 * fbytes(curve) - 1] = 1;  // identity (0:1:0) for empty shards
+    identity_xyz(&partial[i * pt], curve);  // identity (0:1:0) for empty shards
     if (shards[i].cnt) memcpy(&partial[i * pt], ctx->devs[i].lane[0].h_point(), pt);
   }
   return point_sum_enqueue(ctx, curve, nd, partial.data(), out_xy, out_inf, true);
@@ -1572,7 +1619,7 @@ ECG_API(ecg_lincomb)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, 
     return ECG_EINVAL;
   }
   if (n == 0) {
-    uint8_t z[97];
+    uint8_t z[137];
     memset(z, 0, sizeof z);
     if (ctx->devptr()) {
       CU_TRY(ctx, cudaMemcpy(out_xy, z, 2 * fbytes(curve), cudaMemcpyHostToDevice));
@@ -1584,7 +1631,7 @@ ECG_API(ecg_lincomb)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, 
     }
     return ECG_OK;
   }
-  std::vector<uint8_t> partial(ctx->devs.size() * 144, 0);
+  std::vector<uint8_t> partial(ctx->devs.size() * 208, 0);
   ctx->skew = false;
   for (int attempt = 0; attempt < 2; attempt++) {
     ecg_status st = lincomb_attempt(ctx, curve, n, k, P_xy, P_inf, out_xy, out_inf, attempt == 1, partial);

@@ -27,15 +27,15 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libecgpu.so")
 SECP256K1 = 0
 NISTP256 = 1
 NISTP384 = 2
-SM2, BP256R1, BP256T1, BIGNP256, BP384R1, BP384T1, NISTP224, NISTP192 = 3, 4, 5, 6, 7, 8, 9, 10
+SM2, BP256R1, BP256T1, BIGNP256, BP384R1, BP384T1, NISTP224, NISTP192, NISTP521 = 3, 4, 5, 6, 7, 8, 9, 10, 11
 CURVE_IDS = {"k256": SECP256K1, "secp256k1": SECP256K1, "p256": NISTP256, "nistp256": NISTP256, "p384": NISTP384, "nistp384": NISTP384,
              "sm2": SM2, "bp256r1": BP256R1, "brainpoolp256r1": BP256R1, "bp256t1": BP256T1, "brainpoolp256t1": BP256T1,
              "bignp256": BIGNP256, "bp384r1": BP384R1, "brainpoolp384r1": BP384R1, "bp384t1": BP384T1, "brainpoolp384t1": BP384T1,
-             "p224": NISTP224, "nistp224": NISTP224, "p192": NISTP192, "nistp192": NISTP192}
-CURVE_IDS.update({i: i for i in range(11)})
+             "p224": NISTP224, "nistp224": NISTP224, "p192": NISTP192, "nistp192": NISTP192, "p521": NISTP521, "nistp521": NISTP521}
+CURVE_IDS.update({i: i for i in range(12)})
 # bytes per scalar / coordinate at the ABI (include/ecgpu.h)
 FBYTES = {SECP256K1: 32, NISTP256: 32, NISTP384: 48, SM2: 32, BP256R1: 32, BP256T1: 32, BIGNP256: 32, BP384R1: 48, BP384T1: 48,
-          NISTP224: 28, NISTP192: 24}
+          NISTP224: 28, NISTP192: 24, NISTP521: 66}
 # bign-curve256v1 records are little-endian (the reference's byte order for that curve); every other curve is big-endian
 LITTLE_ENDIAN = {BIGNP256}
 

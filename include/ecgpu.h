@@ -41,12 +41,12 @@ typedef enum {
 } ecg_status;
 
 /* Curves.  The hot path is secp256k1 and P-256; the other ids are the widening row "more curves
- * through the same templates" (SURVEY 8(f) rank 4): every prime-order Weierstrass curve the reference implements except
- * P-521 (p384/src/arithmetic.rs:43-75, sm2/src/arithmetic.rs:44-67, bp256/src/{r1,t1}/arithmetic.rs:34-53,
+ * through the same templates" (SURVEY 8(f) rank 4): every prime-order Weierstrass curve the reference implements
+ * (p384/src/arithmetic.rs:43-75, sm2/src/arithmetic.rs:44-67, bp256/src/{r1,t1}/arithmetic.rs:34-53,
  * bp384/src/{r1,t1}/arithmetic.rs:34-53, bignp256/src/arithmetic.rs:38-57, p224/src/arithmetic.rs:40-56,
- * p192/src/arithmetic.rs:38-54), a = -3 and general-a alike (primeorder/src/point_arithmetic.rs:54-208, :212-319).
+ * p192/src/arithmetic.rs:38-54, p521/src/arithmetic.rs:45-90), a = -3 and general-a alike (primeorder/src/point_arithmetic.rs:54-208, :212-319).
  * Record sizes follow the curve: a scalar / field element is FB = 32 bytes for the 256-bit curves, 48 for P-384 and
- * brainpoolP384, 28 for P-224, 24 for P-192 — read "32 / 64 / 96" in every size below as "FB / 2 FB / 3 FB".
+ * brainpoolP384, 28 for P-224, 24 for P-192, 66 for P-521 — read "32 / 64 / 96" in every size below as "FB / 2 FB / 3 FB".
  * Byte order is the one the reference uses for the curve: big-endian everywhere except bign-curve256v1, whose field
  * elements and scalars are little-endian (bignp256/src/arithmetic/field.rs:65, bignp256/src/lib.rs:102).
  * Curves other than secp256k1 / P-256 are served by the hot-path entries (mul_batch[_x], mul_gen_batch,
@@ -63,7 +63,8 @@ typedef enum {
   ECG_BP384R1 = 7,   /* brainpoolP384r1: general a */
   ECG_BP384T1 = 8,   /* brainpoolP384t1: a = -3 */
   ECG_NISTP224 = 9,
-  ECG_NISTP192 = 10
+  ECG_NISTP192 = 10,
+  ECG_NISTP521 = 11  /* 66-byte records (FieldBytesSize = U66, p521/src/lib.rs:63-64) */
 } ecg_curve;
 
 typedef enum {

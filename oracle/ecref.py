@@ -87,9 +87,9 @@ def lib384():
 LIBP = os.path.join(_HERE, "libecrefp.so")
 _libp = None
 # curves served by oracle/ecref_prime.c: id -> bytes per record (ids as in include/ecgpu.h)
-EXT = {"sm2": 3, "bp256r1": 4, "bp256t1": 5, "bignp256": 6, "bp384r1": 7, "bp384t1": 8, "p224": 9, "p192": 10}
+EXT = {"sm2": 3, "bp256r1": 4, "bp256t1": 5, "bignp256": 6, "bp384r1": 7, "bp384t1": 8, "p224": 9, "p192": 10, "p521": 11}
 EXT.update({v: v for v in list(EXT.values())})
-EXT_NB = {3: 32, 4: 32, 5: 32, 6: 32, 7: 48, 8: 48, 9: 28, 10: 24}
+EXT_NB = {3: 32, 4: 32, 5: 32, 6: 32, 7: 48, 8: 48, 9: 28, 10: 24, 11: 66}
 
 
 def libp():

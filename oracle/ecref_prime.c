@@ -1,6 +1,6 @@
 /* ecref_prime.c — CPU restatement of the reference's generic prime-order path for the curves it binds to primeorder
  * over a Montgomery field synthesised from the modulus: sm2, brainpoolP256r1/t1, brainpoolP384r1/t1, bign-curve256v1,
- * P-224, P-192.
+ * P-224, P-192, P-521.
  *
  * TEST INFRASTRUCTURE ONLY: the checker / CPU baseline for those curves.  Only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline leg may load it; the product path never does.
@@ -46,11 +46,15 @@ enum { OP_MUL = 0, OP_MULGEN = 1, OP_LINCOMB = 2 };
 #define NL 6
 #include "ecref_prime_impl.inc"
 #undef NL
+#define NL 9
+#include "ecref_prime_impl.inc"
+#undef NL
 
 /* curve ids as in include/ecgpu.h */
 static curve_4 C_SM2, C_BP256R1, C_BP256T1, C_BIGN, C_P224;
 static curve_6 C_BP384R1, C_BP384T1;
 static curve_3 C_P192;
+static curve_9 C_P521;
 static int g_init = 0;
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 
@@ -98,6 +102,15 @@ void ecrefp_init(void) {
     curve_init_3(&C_P192, 10, 24, 0, 0, "fffffffffffffffffffffffffffffffeffffffffffffffff", "ffffffffffffffffffffffff99def836146bc9b1b4d22831",
                  "fffffffffffffffffffffffffffffffefffffffffffffffc", "64210519e59c80e70fa7e9ab72243049feb8deecc146b9b1",
                  "188da80eb03090f67cbf20eb43a18800f4ff0afd82ff1012", "07192b95ffc8da78631011ed6b24cdd573f977a11e794811");
+    /* P-521: p521/src/arithmetic.rs:45-90 (the reference's field there is fiat-crypto's unsaturated Solinas form, not under
+     * /root/reference; same residues), 66-byte records, U576 on 64-bit targets (p521/src/lib.rs:47) */
+    curve_init_9(&C_P521, 11, 66, 0, 0,
+                 "1ffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffff",
+                 "1fffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffa51868783bf2f966b7fcc0148f709a5d03bb5c9b8899c47aebb6fb71e91386409",
+                 "1fffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffc",
+                 "51953eb9618e1c9a1f929a21a0b68540eea2da725b99b315f3b8b489918ef109e156193951ec7e937b1652c0bd3bb1bf073573df883d2c34f1ef451fd46b503f00",
+                 "c6858e06b70404e9cd9e3ecb662395b4429c648139053fb521f828af606b4d3dbaa14b5e77efe75928fe1dc127a2ffa8de3348b3c1856a429bf97e7e31c2e5bd66",
+                 "11839296a789a3bc0045c8a5fb42c7d1bd998f54449579b446817afbd17273e662c97ee72995ef42640c550b9013fad0761353c7086a272c24088be94769fd16650");
     g_init = 1;
   }
   pthread_mutex_unlock(&g_lock);
@@ -115,6 +128,7 @@ static int dispatch(int curve, int op, size_t n, const uint8_t* k, const uint8_t
     case 8: return run_6(&C_BP384T1, op, n, k, pxy, pinf, oxy, oinf, nthreads);
     case 9: return run_4(&C_P224, op, n, k, pxy, pinf, oxy, oinf, nthreads);
     case 10: return run_3(&C_P192, op, n, k, pxy, pinf, oxy, oinf, nthreads);
+    case 11: return run_9(&C_P521, op, n, k, pxy, pinf, oxy, oinf, nthreads);
     default: return 1;
   }
 }

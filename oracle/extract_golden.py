@@ -226,7 +226,7 @@ def main():
         v = h2c_vectors()
         json.dump(v, f, indent=1)
         print("h2c", {k: len(x["vectors"]) for k, x in v["suites"].items()}, len(v["p256_hash_to_scalar_voprf"]))
-    for curve in ("p224", "p192", "bignp256"):
+    for curve in ("p224", "p192", "bignp256", "p521"):
         data = {"curve": curve, "reference_commit": "739304e026fdf06cd1a31606e4db487d3f47c5ae", "group": group_vectors(curve),
                 "little_endian": curve == "bignp256"}
         path = os.path.join(OUT, f"{curve}.json")

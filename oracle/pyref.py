@@ -144,7 +144,17 @@ P192 = Curve(
     gx=0x188DA80EB03090F67CBF20EB43A18800F4FF0AFD82FF1012,
     gy=0x07192B95FFC8DA78631011ED6B24CDD573F977A11E794811,
 )
-EXT_CURVES = {3: SM2, 4: BP256R1, 5: BP256T1, 6: BIGNP256, 7: BP384R1, 8: BP384T1, 9: P224, 10: P192}
+# p521/src/arithmetic.rs:45-90, p521/src/arithmetic/field.rs:68-80, p521/src/lib.rs:51-74 (66-byte records)
+P521 = Curve(
+    "p521",
+    p=2**521 - 1,
+    n=0x01FFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFA51868783BF2F966B7FCC0148F709A5D03BB5C9B8899C47AEBB6FB71E91386409,
+    a=-3,
+    b=0x0051953EB9618E1C9A1F929A21A0B68540EEA2DA725B99B315F3B8B489918EF109E156193951EC7E937B1652C0BD3BB1BF073573DF883D2C34F1EF451FD46B503F00,
+    gx=0x00C6858E06B70404E9CD9E3ECB662395B4429C648139053FB521F828AF606B4D3DBAA14B5E77EFE75928FE1DC127A2FFA8DE3348B3C1856A429BF97E7E31C2E5BD66,
+    gy=0x011839296A789A3BC0045C8A5FB42C7D1BD998F54449579B446817AFBD17273E662C97EE72995EF42640C550B9013FAD0761353C7086A272C24088BE94769FD16650,
+)
+EXT_CURVES = {3: SM2, 4: BP256R1, 5: BP256T1, 6: BIGNP256, 7: BP384R1, 8: BP384T1, 9: P224, 10: P192, 11: P521}
 CURVE_IDS = {"k256": 0, "p256": 1, "p384": 2}
 CURVE_IDS.update({c.name: i for i, c in EXT_CURVES.items()})
 CURVES = {"k256": K256, "p256": P256, "p384": P384, 0: K256, 1: P256, 2: P384}

@@ -278,7 +278,7 @@ int sim_p384_on_curve(const uint8_t* P_xy) {
 }
 // ---- curves on the generic Montgomery field policy (ecg_fe_mont.cuh / ecg_curves_ext.cuh) ----
 // curve ids as in include/ecgpu.h: 3 sm2, 4 brainpoolP256r1, 5 brainpoolP256t1, 6 bign-curve256v1, 7 brainpoolP384r1,
-// 8 brainpoolP384t1, 9 P-224, 10 P-192
+// 8 brainpoolP384t1, 9 P-224, 10 P-192, 11 P-521
 }  // extern "C"
 #define SIM_FOR_EXT(curve, ...)                         \
   switch (curve) {                                      \
@@ -290,6 +290,7 @@ int sim_p384_on_curve(const uint8_t* P_xy) {
     case 8: { typedef CurveBp384t1 CV; __VA_ARGS__; } break;  \
     case 9: { typedef CurveP224 CV; __VA_ARGS__; } break;     \
     case 10: { typedef CurveP192 CV; __VA_ARGS__; } break;    \
+    case 11: { typedef CurveP521 CV; __VA_ARGS__; } break;    \
     default: break;                                     \
   }
 // field operation on canonical records (byte order of the curve); Montgomery conversions at the boundary like the kernels
@@ -321,7 +322,7 @@ static int sim_ext_fe_op_t(int op, const uint8_t* a, const uint8_t* b, uint8_t* 
 template <class C>
 static int sim_ext_mul_t(const uint8_t* kb, const uint8_t* P_xy, uint8_t* out_xy, uint8_t* out_inf) {
   typedef typename C::F F;
-  constexpr int NL = F::NL, FB = 4 * F::NL;
+  constexpr int NL = F::NL, FB = F::FB;
   uint32_t k[NL];
   load_fe<F>(k, kb);
   typename F::AffT P;
@@ -358,7 +359,7 @@ static int sim_ext_gen_t(uint8_t* out_xy) {  // the generator as the device cons
   F::to_canonical(x, g.x);
   F::to_canonical(y, g.y);
   store_fe<F>(out_xy, x.v);
-  store_fe<F>(out_xy + 4 * F::NL, y.v);
+  store_fe<F>(out_xy + F::FB, y.v);
   return 0;
 }
 extern "C" {
@@ -662,8 +663,9 @@ static MsmGeom simk_msm_geometry(int curve, size_t n) {  // = msm_geometry (ecgp
   int lg = 0;
   while (((size_t)1 << (lg + 1)) <= nsub) lg++;
   g.c = std::min(16, std::max(8, lg - 5));
-  static const int ext_bits[] = {256, 256, 256, 256, 384, 384, 224, 192};  // ids 3..10
+  static const int ext_bits[] = {256, 256, 256, 256, 384, 384, 224, 192, 544};  // ids 3..11 (32 bits per limb)
   g.nbits = glv ? 128 : (curve == 2 ? 384 : curve >= 3 ? ext_bits[curve - 3] : 256);
+  while ((g.nbits + g.c - 1) / g.c > MSM_FINAL_THREADS) g.c++;
   g.W = (g.nbits + g.c - 1) / g.c;
   g.nbw = ((uint32_t)1 << (g.c + 1)) + 2;
   return g;
@@ -787,7 +789,7 @@ extern "C" int simk_lincomb_k(int curve, size_t n, const uint8_t* k, const uint8
   status[0] = 0;
   status[1] = 0xFFFFFFFFu;
   if (n == 0) {  // empty sum = identity
-    memset(out_xy, 0, (curve == 2 || curve == 7 || curve == 8) ? 96 : curve == 9 ? 56 : curve == 10 ? 48 : 64);
+    memset(out_xy, 0, (curve == 2 || curve == 7 || curve == 8) ? 96 : curve == 9 ? 56 : curve == 10 ? 48 : curve == 11 ? 132 : 64);
     *out_inf = 1;
     *path = 0;
     return 0;

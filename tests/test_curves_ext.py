@@ -1,8 +1,8 @@
 """CPU-only parity for the curves on the generic Montgomery field policy: sm2,
-brainpoolP256r1/t1, brainpoolP384r1/t1, bign-curve256v1, P-224, P-192.
+brainpoolP256r1/t1, brainpoolP384r1/t1, bign-curve256v1, P-224, P-192, P-521.
 
  * oracle pinning: the big-integer model (oracle/pyref.py) and the C restatement of the reference's generic primeorder
-   path (oracle/ecref_prime.c) against the reference's own vectors where it holds any (p224 / p192 / bignp256
+   path (oracle/ecref_prime.c) against the reference's own vectors where it holds any (p224 / p192 / p521 / bignp256
    src/test_vectors/group.rs -> tests/golden/*.json), against OpenSSL where it knows the curve, and against each other;
  * the device code itself, executed on the host (tests/sim): field policy (ecg_fe_mont.cuh), the general-a formulas,
    the variable-base / fixed-base / bucket-method kernel chains with the records in each curve's byte order."""
@@ -54,7 +54,7 @@ def golden_points(name):
 # ---------------------------------------------------------------------------------------------------------------------
 # oracle pinning
 
-@pytest.mark.parametrize("name", ["p224", "p192", "bignp256"])
+@pytest.mark.parametrize("name", ["p224", "p192", "bignp256", "p521"])
 def test_oracles_reproduce_the_reference_vectors(name):
     c = pyref.CURVES[name]
     vec = golden_points(name)
@@ -94,7 +94,7 @@ def test_curve_constants_and_c_restatement_vs_model(cid):
         ecref.mul_batch(c.name, recs(c, [5]), *pts(c, [tuple(bad)]))
 
 
-@pytest.mark.parametrize("name,ossl", [("bp256r1", "BrainpoolP256R1"), ("bp384r1", "BrainpoolP384R1"), ("p224", "SECP224R1"), ("p192", "SECP192R1")])
+@pytest.mark.parametrize("name,ossl", [("bp256r1", "BrainpoolP256R1"), ("bp384r1", "BrainpoolP384R1"), ("p224", "SECP224R1"), ("p192", "SECP192R1"), ("p521", "SECP521R1")])
 def test_model_agrees_with_openssl(name, ossl):
     ec = pytest.importorskip("cryptography.hazmat.primitives.asymmetric.ec")
     c = pyref.CURVES[name]
@@ -175,7 +175,7 @@ def test_varbase_kernel_chain(sim, cid):
     Ps = [base[i % 6] for i in range(len(ks))]
     Ps[7] = None
     want = [pyref.mul(c, k, P) if P is not None else None for k, P in zip(ks, Ps)]
-    if c.name in ("p224", "p192", "bignp256"):
+    if c.name in ("p224", "p192", "bignp256", "p521"):
         for k, P in golden_points(c.name):
             ks.append(k)
             Ps.append(G)
@@ -244,7 +244,7 @@ def test_fixedbase_kernel_chain(sim, fb_tables, cid):
         assert got[i] == pyref.mul(c, ks[i], pyref.G(c))
 
 
-@pytest.mark.parametrize("cid", [4, 5, 6, 8, 10])
+@pytest.mark.parametrize("cid", [4, 5, 6, 8, 10, 11])
 def test_lincomb_kernel_chain_per_term_and_bucket_method(sim, cid):
     c = EXT[cid]
     nb = pyref.fbytes(c)

@@ -1,7 +1,7 @@
 """GPU parity, through the C ABI, for the curves on the generic Montgomery field policy:
-sm2, brainpoolP256r1 / t1, brainpoolP384r1 / t1, bign-curve256v1 (little-endian records), P-224, P-192 — against the
+sm2, brainpoolP256r1 / t1, brainpoolP384r1 / t1, bign-curve256v1 (little-endian records), P-224, P-192, P-521 (66-byte records) — against the
 C restatement of the reference's generic primeorder path (oracle/ecref_prime.c), the big-integer model, and the
-reference's own vectors where the crate holds any (tests/golden/{p224,p192,bignp256}.json)."""
+reference's own vectors where the crate holds any (tests/golden/{p224,p192,p521,bignp256}.json)."""
 import random
 
 import numpy as np
@@ -34,7 +34,7 @@ def rand_scalars(c, n, seed):
     return K
 
 
-@pytest.mark.parametrize("name", ["p224", "p192", "bignp256"])
+@pytest.mark.parametrize("name", ["p224", "p192", "bignp256", "p521"])
 def test_reference_vectors(engine, name):
     c = pyref.CURVES[name]
     vec = golden_points(name)
@@ -175,7 +175,7 @@ def test_rejects_bad_inputs_and_unsupported_entries(engine, cid):
     assert lib.ecg_ecdsa_verify_batch(engine._ctx, cid, 1, vp(z), vp(z), vp(z), 0, vp(z)) == ecgpu.ECG_EINVAL
     assert lib.ecg_decompress_batch(engine._ctx, cid, 1, vp(z), vp(z), vp(z), vp(z)) == ecgpu.ECG_EINVAL
     assert lib.ecg_field_sqrt_batch(engine._ctx, cid, 1, vp(z), vp(z), vp(z)) == ecgpu.ECG_EINVAL
-    assert lib.ecg_mul_batch(engine._ctx, 11, 1, vp(z), vp(z), None, vp(z), vp(z)) == ecgpu.ECG_EINVAL   # unknown curve id
+    assert lib.ecg_mul_batch(engine._ctx, 12, 1, vp(z), vp(z), None, vp(z), vp(z)) == ecgpu.ECG_EINVAL   # unknown curve id
 
 
 @pytest.mark.parametrize("cid", IDS)

@@ -77,6 +77,16 @@ CURVES = [
          gx=0x188DA80EB03090F67CBF20EB43A18800F4FF0AFD82FF1012,
          gy=0x07192B95FFC8DA78631011ED6B24CDD573F977A11E794811, le=False,
          src="p192/src/arithmetic.rs:38-54, p192/src/arithmetic/field.rs:54, p192/src/lib.rs:41"),
+    dict(id=11, name="P521", enum="ECG_NISTP521", nl=17, fb=66,
+         p=2**521 - 1,
+         n=0x01FFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFA51868783BF2F966B7FCC0148F709A5D03BB5C9B8899C47AEBB6FB71E91386409,
+         a=-3,
+         b=0x0051953EB9618E1C9A1F929A21A0B68540EEA2DA725B99B315F3B8B489918EF109E156193951EC7E937B1652C0BD3BB1BF073573DF883D2C34F1EF451FD46B503F00,
+         gx=0x00C6858E06B70404E9CD9E3ECB662395B4429C648139053FB521F828AF606B4D3DBAA14B5E77EFE75928FE1DC127A2FFA8DE3348B3C1856A429BF97E7E31C2E5BD66,
+         gy=0x011839296A789A3BC0045C8A5FB42C7D1BD998F54449579B446817AFBD17273E662C97EE72995EF42640C550B9013FAD0761353C7086A272C24088BE94769FD16650,
+         le=False,
+         src="p521/src/arithmetic.rs:45-90, p521/src/arithmetic/field.rs:68-80 (the reference's field is fiat-crypto's "
+             "unsaturated Solinas form; the values are the same residues), p521/src/lib.rs:51-74; 66-byte records in 17 limbs"),
 ]
 
 
@@ -115,7 +125,8 @@ def main():
         out.append("// ---- %s: %s ----\n" % (c["name"], c["src"]))
         if field not in fields_done:
             fields_done.add(field)
-            out.append("struct Mp%s {\n  static constexpr int NL = %d;\n  static constexpr bool LE = %s;\n" % (field, nl, "true" if c["le"] else "false"))
+            out.append("struct Mp%s {\n  static constexpr int NL = %d;\n  static constexpr int FB = %d;  // bytes per canonical record\n  static constexpr bool LE = %s;\n"
+                       % (field, nl, c.get("fb", 4 * nl), "true" if c["le"] else "false"))
             out.append("  static constexpr uint32_t N0INV = 0x%08Xu;  // -p^-1 mod 2^32\n" % ((-pow(p, -1, 1 << 32)) % (1 << 32)))
             out.append(accessor("P", p, nl))
             out.append(accessor("ONE", R % p, nl))
@@ -134,17 +145,18 @@ def main():
         out.append("  ECG_D static void b_internal(FeN<%d>& b) {\n    const uint32_t t[%d] = %s;\n#pragma unroll\n    for (int i = 0; i < %d; i++) b.v[i] = t[i];\n  }\n" % (nl, nl, carr(c["b"] * R % p, nl), nl))
         out.append("  ECG_D static void generator(AffN<%d>& g) {\n    const uint32_t x[%d] = %s;\n    const uint32_t y[%d] = %s;\n#pragma unroll\n    for (int i = 0; i < %d; i++) {\n      g.x.v[i] = x[i];\n      g.y.v[i] = y[i];\n    }\n  }\n};\n\n"
                    % (nl, nl, carr(c["gx"] * R % p, nl), nl, carr(c["gy"] * R % p, nl), nl))
-        fb = 4 * nl
+        fb = c.get("fb", 4 * nl)
         order = "little" if c["le"] else "big"
         gbytes = c["gx"].to_bytes(fb, order) + c["gy"].to_bytes(fb, order)
         host.append((c, gbytes))
     out.append("}  // namespace ecg\n\n")
     # host-side table: order limbs, generator bytes (ABI byte order), sizes
     out.append("// host-side descriptors (ecgpu.cu: sizes at the ABI, fixed-base table construction)\n")
-    out.append("struct EcgExtCurveHost {\n  int id, nl, le;\n  uint32_t n[12];\n  uint8_t g[96];\n};\n")
+    out.append("struct EcgExtCurveHost {\n  int id, nl, fb, le;  // limbs, bytes per record, little-endian records\n  uint32_t n[18];\n  uint8_t g[136];\n};\n")
     out.append("static const EcgExtCurveHost ECG_EXT_CURVES[] = {\n")
     for c, g in host:
-        out.append("    {%d, %d, %d, %s, {%s}},  // %s\n" % (c["id"], c["nl"], 1 if c["le"] else 0, carr(c["n"], c["nl"]), ", ".join("0x%02X" % b for b in g), c["enum"]))
+        out.append("    {%d, %d, %d, %d, %s, {%s}},  // %s\n" % (c["id"], c["nl"], c.get("fb", 4 * c["nl"]), 1 if c["le"] else 0, carr(c["n"], c["nl"]),
+                                                              ", ".join("0x%02X" % b for b in g), c["enum"]))
     out.append("};\nstatic const int ECG_EXT_CURVE_COUNT = %d;\n" % len(host))
     open(OUT, "w").write("".join(out))
     print("wrote", OUT)
