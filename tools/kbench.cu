@@ -1,7 +1,7 @@
 // tools/kbench.cu — development harness: times kernel variants of the secp256k1 variable-base path on one GPU
 // and cross-checks that every variant produces identical Jacobian words.  Not part of the product or of bench.py.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tools/kbench tools/kbench.cu
-//   modes: kbench 20 | kbench 20 trade | kbench 20 mem   (mem: also build with -DECG_FE_ALIGN=16 as tools/kbench_a16)
+//   modes: kbench 20 | kbench 20 trade | kbench 20 shape | kbench 20 mem   (mem: also build with -DECG_FE_ALIGN=16 as tools/kbench_a16)
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -343,12 +343,146 @@ static void run_fmul(const char* name) {
   }
 }
 
+
+// ---- "shape" mode: one measured line for each kernel-shape clause of north_star that the product does not follow ----
+// (a) 4 x u64 limbs with mul.lo.u64 / mul.hi.u64 (+ 64-bit carry chains): the 256 x 256 -> 512-bit product only, no reduction
+__device__ __forceinline__ void mac3_u64(unsigned long long& c0, unsigned long long& c1, unsigned long long& c2, unsigned long long a,
+                                         unsigned long long b) {
+  asm volatile("{\n\t.reg .u64 lo, hi;\n\tmul.lo.u64 lo, %3, %4;\n\tmul.hi.u64 hi, %3, %4;\n\tadd.cc.u64 %0, %0, lo;\n\taddc.cc.u64 %1, %1, hi;\n\taddc.u64 %2, %2, 0;\n\t}"
+               : "+&l"(c0), "+&l"(c1), "+&l"(c2)
+               : "l"(a), "l"(b));
+}
+__global__ void __launch_bounds__(256) kb_prod_u64(unsigned long long* out, int iters, unsigned long long seed) {
+  unsigned long long a[4], b[4], r[8];
+  for (int i = 0; i < 4; i++) { a[i] = seed * (2 * i + 1) + threadIdx.x; b[i] = (seed ^ 0x9E3779B97F4A7C15ull) * (2 * i + 3) + blockIdx.x; }
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    unsigned long long c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int j = k - i;
+        if (j >= 0 && j < 4) mac3_u64(c0, c1, c2, a[i], b[j]);
+      }
+      r[k] = c0; c0 = c1; c1 = c2; c2 = 0;
+    }
+    r[7] = c0;
+    for (int i = 0; i < 4; i++) { a[i] = r[i] ^ r[i + 4]; b[i] += r[7 - i]; }  // keep the chain alive, no modular meaning
+  }
+  unsigned long long x = 0;
+  for (int i = 0; i < 4; i++) x ^= a[i] ^ b[i];
+  if (x == 0x1234567812345678ull) out[0] = x;
+}
+// the same product on 8 x u32 limbs (the product's mul8x8), also without reduction, for the like-for-like comparison
+__global__ void __launch_bounds__(256) kb_prod_u32(uint32_t* out, int iters, uint32_t seed) {
+  uint32_t a[8], b[8], r[16];
+  for (int i = 0; i < 8; i++) { a[i] = seed * (i + 1) + threadIdx.x; b[i] = (seed ^ 0x9E3779B9u) * (i + 3) + blockIdx.x; }
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    mul8x8(r, a, b);
+    for (int i = 0; i < 8; i++) { a[i] = r[i] ^ r[i + 8]; b[i] += r[15 - i]; }
+  }
+  uint32_t x = 0;
+  for (int i = 0; i < 8; i++) x ^= a[i] ^ b[i];
+  if (x == 0x12345678u) out[0] = x;
+}
+// (b) warp-cooperative layout, 8 lanes per field element (4 elements per warp), lane l holds limb l of a and of b.
+// Product core only: lane l accumulates column l (products a_i b_(l-i), i <= l) and column l + 8 (a_i b_(l+8-i), i > l):
+// 8 products per lane = the same 64 products per element, operands fetched with two shuffles per product; NO carry
+// resolution across lanes, no reduction (both would add further shuffle rounds).
+__global__ void __launch_bounds__(256) kb_prod_warp8(uint32_t* out, int iters, uint32_t seed) {
+  const unsigned lane = threadIdx.x & 31u, l = lane & 7u, base = lane & ~7u;
+  uint32_t a = seed * (l + 1) + threadIdx.x, b = (seed ^ 0x9E3779B9u) * (l + 3) + blockIdx.x;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    uint32_t s0 = 0, s1 = 0, s2 = 0, t0 = 0, t1 = 0, t2 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      uint32_t ai = __shfl_sync(0xFFFFFFFFu, a, base + i);
+      uint32_t bj = __shfl_sync(0xFFFFFFFFu, b, base + ((l - i) & 7u));  // b_(l-i) for i <= l, b_(l+8-i) for i > l
+      if ((unsigned)i <= l)
+        mad_acc3(s0, s1, s2, ai, bj);
+      else
+        mad_acc3(t0, t1, t2, ai, bj);
+    }
+    a = s0 ^ t1 ^ s2;
+    b += s1 ^ t0 ^ t2;
+  }
+  if ((a ^ b) == 0x12345678u) out[0] = a;
+}
+// (c) record loads: 96 bytes per pair (32 k + 64 P) as 24 x 32-bit loads (the product's load_be) vs 6 x 128-bit loads
+template <bool VEC>
+__global__ void __launch_bounds__(256) kb_record_loads(const uint8_t* __restrict__ kb, const uint8_t* __restrict__ pxy, size_t n, uint32_t* out) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  uint32_t w[24];
+  if (VEC) {
+    const uint4* k4 = reinterpret_cast<const uint4*>(kb + 32 * idx);
+    const uint4* p4 = reinterpret_cast<const uint4*>(pxy + 64 * idx);
+#pragma unroll
+    for (int q = 0; q < 2; q++) { uint4 v = __ldg(k4 + q); w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w; }
+#pragma unroll
+    for (int q = 0; q < 4; q++) { uint4 v = __ldg(p4 + q); w[8 + 4 * q] = v.x; w[9 + 4 * q] = v.y; w[10 + 4 * q] = v.z; w[11 + 4 * q] = v.w; }
+  } else {
+    const uint32_t* k1 = reinterpret_cast<const uint32_t*>(kb + 32 * idx);
+    const uint32_t* p1 = reinterpret_cast<const uint32_t*>(pxy + 64 * idx);
+#pragma unroll
+    for (int q = 0; q < 8; q++) w[q] = __ldg(k1 + q);
+#pragma unroll
+    for (int q = 0; q < 16; q++) w[8 + q] = __ldg(p1 + q);
+  }
+  uint32_t x = 0;
+#pragma unroll
+  for (int q = 0; q < 24; q++) x ^= bswap32(w[q]) + q;
+  if (x == 0x12345678u) out[0] = x;
+}
+template <class K, class... A>
+static float time_best(int reps, K launch, A... args) {
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < reps; rep++) {
+    CK(cudaEventRecord(e0));
+    launch(args...);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  return best;
+}
+static void run_shape(size_t n) {
+  void* out; CK(cudaMalloc(&out, 256));
+  const int iters = 4000; const unsigned blocks = 148 * 8;
+  const double units = (double)blocks * 256 * iters;
+  float t32 = time_best(4, [&] { kb_prod_u32<<<blocks, 256>>>((uint32_t*)out, iters, 777u); });
+  float t64 = time_best(4, [&] { kb_prod_u64<<<blocks, 256>>>((unsigned long long*)out, iters, 777ull); });
+  float tw = time_best(4, [&] { kb_prod_warp8<<<blocks, 256>>>((uint32_t*)out, iters, 777u); });
+  printf("256x256 product, 8 x u32 limbs, one thread per element (mul8x8, no reduction): %.4g products/s (%.3f ms)\n", units / (t32 * 1e-3), t32);
+  printf("256x256 product, 4 x u64 limbs, mul.lo/hi.u64 + 64-bit carry chains (no reduction): %.4g products/s (%.3f ms)  = %.2fx the u32 time\n",
+         units / (t64 * 1e-3), t64, t64 / t32);
+  printf("256x256 product, warp-cooperative 8 lanes per element (product core only: no carry resolution, no reduction): %.4g products/s (%.3f ms)  = %.2fx the u32 time\n",
+         units / 8 / (tw * 1e-3), tw, (tw * 8) / t32);
+  uint8_t *kb, *pxy;
+  CK(cudaMalloc(&kb, n * 32)); CK(cudaMalloc(&pxy, n * 64));
+  CK(cudaMemset(kb, 0x5A, n * 32)); CK(cudaMemset(pxy, 0xA5, n * 64));
+  unsigned g = (unsigned)((n + 255) / 256);
+  float l32 = time_best(6, [&] { kb_record_loads<false><<<g, 256>>>(kb, pxy, n, (uint32_t*)out); });
+  float l128 = time_best(6, [&] { kb_record_loads<true><<<g, 256>>>(kb, pxy, n, (uint32_t*)out); });
+  printf("record loads, %zu pairs x 96 B: 24 x LDG.32 per pair %.1f us (%.0f GB/s), 6 x LDG.128 per pair %.1f us (%.0f GB/s); the var-base kernel over the same pairs takes ~17300 us\n",
+         n, l32 * 1e3, n * 96.0 / (l32 * 1e-3) / 1e9, l128 * 1e3, n * 96.0 / (l128 * 1e-3) / 1e9);
+  cudaFree(kb); cudaFree(pxy); cudaFree(out);
+}
+
 int main(int argc, char** argv) {
   size_t n = (size_t)1 << (argc > 1 ? atoi(argv[1]) : 20);
   uint32_t *jac, *gtab;
   CK(cudaMalloc(&jac, n * 96));
   CK(cudaMalloc(&gtab, (size_t)148 * 8 * 640 * 192 * 4));
   printf("n = %zu\n", n);
+  if (argc > 2 && !strcmp(argv[2], "shape")) {  // north_star's kernel-shape clauses the product deviates from, one measured line each
+    run_shape(n);
+    return 0;
+  }
   if (argc > 2 && !strcmp(argv[2], "mem")) {  // mul operands through local memory instead of the register ABI (OPT bit 8)
     // build twice: default, and with -DECG_FE_ALIGN=16 (128-bit LDL/STL)
     for (int round = 0; round < 2; round++) {
