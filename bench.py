@@ -904,6 +904,74 @@ def measure_more_curves(B, steps):
                                   "P-192) to OpenSSL by tests/test_curves_ext.py"}
 
 
+def measure_consttime_cost(B, steps):
+    """What ECG_FLAG_CONSTTIME costs: the variable-base kernels with masked window-table selects and
+    branch-free sign folding, k*G through the variable-base routine instead of the fixed-base table; same inputs through a
+    default ctx and a constant-time ctx, device-resident, outputs compared byte for byte."""
+    import torch
+
+    import ecgpu
+    import pyref
+
+    dev, world, rank, host_eng = B.dev, B.world, B.rank, B.host_eng
+    ct = ecgpu.Engine([B.local], device_ptrs=True, consttime=True)
+    ct.set_stream(torch.cuda.current_stream().cuda_stream)
+    out = {}
+    all_ok = True
+    for name, n in (("k256", 1 << 20), ("p256", 1 << 19)):
+        c = pyref.CURVES[name]
+        rng = np.random.default_rng(0xB2000200 + rank)
+        K = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        K[:, 0] &= 0x7F
+        T = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        T[:, 0] &= 0x7F
+        T[:, 31] |= 1
+        pxy, pinf = host_eng.mul_by_generator(name, T.reshape(-1))
+        kd = torch.from_numpy(K.reshape(-1)).to(dev)
+        pd = torch.from_numpy(np.ascontiguousarray(pxy).reshape(-1)).to(dev)
+        res = {}
+        for label, eng in (("vartime", B.eng), ("consttime", ct)):
+            oxy = torch.empty(64 * n, dtype=torch.uint8, device=dev)
+            oinf = torch.empty(n, dtype=torch.uint8, device=dev)
+            gxy = torch.empty(64 * n, dtype=torch.uint8, device=dev)
+            ginf = torch.empty(n, dtype=torch.uint8, device=dev)
+            times = {}
+            for what, call in (("var_base", lambda: eng.mul_batch_ptr(name, n, kd.data_ptr(), pd.data_ptr(), 0, oxy.data_ptr(), oinf.data_ptr())),
+                               ("mul_by_generator", lambda: eng.mul_gen_batch_ptr(name, n, kd.data_ptr(), gxy.data_ptr(), ginf.data_ptr()))):
+                for _ in range(2):
+                    call()
+                torch.cuda.synchronize()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                for _ in range(steps):
+                    B.flush.zero_()
+                    call()
+                ev1.record()
+                torch.cuda.synchronize()
+                times[what] = max_over_ranks(ev0.elapsed_time(ev1), world) / steps
+            res[label] = (times, oxy, oinf, gxy, ginf)
+        same = bool(torch.equal(res["vartime"][1], res["consttime"][1]) and torch.equal(res["vartime"][2], res["consttime"][2])
+                    and torch.equal(res["vartime"][3], res["consttime"][3]) and torch.equal(res["vartime"][4], res["consttime"][4]))
+        ok = B.all_true(same)
+        all_ok = all_ok and ok
+        v, t = res["vartime"][0], res["consttime"][0]
+        out[name] = {"batch_per_gpu": n,
+                     "var_base_ms": {"vartime": v["var_base"], "consttime": t["var_base"], "ratio": t["var_base"] / v["var_base"]},
+                     "mul_by_generator_ms": {"vartime_fixed_base_table": v["mul_by_generator"], "consttime_variable_base_routine": t["mul_by_generator"],
+                                             "ratio": t["mul_by_generator"] / v["mul_by_generator"]},
+                     "consttime_rate": {"var_base": world * n / (t["var_base"] * 1e-3), "mul_by_generator": world * n / (t["mul_by_generator"] * 1e-3),
+                                        "unit": "scalar-mults/s"},
+                     "bit_exact": ok}
+    ct.close()
+    if rank != 0:
+        return None
+    return {"metric": "ms per step (includes the 256 MiB L2 flush write, both arms alike)", "n_gpus": world, "steps": steps,
+            "config": {"workload": "cost of ECG_FLAG_CONSTTIME: masked table selects + branch-free sign folding (var-base), variable-base "
+                                   "routine instead of the 16-bit fixed-base table (k*G); device-resident operands"},
+            "curves": out, "bit_exact": all_ok,
+            "bit_exact_coverage": "every output of the constant-time ctx equals the default ctx's (which the other configs compare with the CPU restatement)"}
+
+
 def run_ours(args):
     B = Bench(args)
     world, rank = B.world, B.rank
@@ -917,6 +985,7 @@ def run_ours(args):
             configs[key] = measure(B, wl, sub_steps, 3, sample_clocks=False)
         configs["6_p384_varbase"] = measure_p384(B, max(3, sub_steps // 2))
         configs["7_more_curves"] = measure_more_curves(B, 3)
+        configs["8_consttime_cost"] = measure_consttime_cost(B, 5)
         if world > 1:
             configs["strong_scaling"] = strong_scaling(B)
             barrier_sync(world)

@@ -120,8 +120,47 @@ ECG_KERNEL(BLOCK, MINBLK)
 }
 
 // ------------------------------------------------------------------------------------------------
+// ECG_FLAG_CONSTTIME kernels: load_pair, or — with pxy == nullptr — the scalar alone with P = G (mul_by_generator through
+// the variable-base routine, like the reference's mul_backend::VariableOnly: no table indexed by 16 secret bits)
+template <class C>
+ECG_DEV uint32_t load_pair_or_generator(uint32_t* k, typename C::F::AffT& P, bool& inf, const uint8_t* kb, const uint8_t* pxy,
+                                        const uint8_t* pinf, size_t idx) {
+  typedef typename C::F F;
+  if (pxy != nullptr) return load_pair<C>(k, P, inf, kb, pxy, pinf, idx);
+  inf = false;
+  load_fe<F>(k, kb + F::FB * idx);
+  C::generator(P);
+  if (ltN<F::NL>(k, C::N())) return 0;
+#pragma unroll
+  for (int i = 0; i < F::NL; i++) k[i] = (i == 0);
+  return ERRF_SCALAR;
+}
+
+// secp256k1 variable-base with scalar-independent addresses and sign handling (call-based field operations)
+template <int BLOCK, int MINBLK>
+ECG_KERNEL(BLOCK, MINBLK)
+    k256_varbase_ct_kernel(const uint8_t* __restrict__ kb, const uint8_t* __restrict__ pxy, const uint8_t* __restrict__ pinf, size_t n,
+                           uint32_t* __restrict__ jac, uint32_t* __restrict__ gtab, uint32_t* __restrict__ status, size_t base) {
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n) return;
+  uint32_t k[8];
+  Aff P;
+  bool inf;
+  uint32_t err = load_pair_or_generator<CurveK256>(k, P, inf, kb, pxy, pinf, idx);
+  if (err) report_error(status, err, base + idx);
+  TabRef tab{gtab + (size_t)blockIdx.x * BLOCK * K_TAB_WORDS + threadIdx.x, (uint32_t)BLOCK};
+  Jac r;
+  k256_mul_thread<FpK256, 0, true>(r, k, P, tab);
+  if (inf || err) FpK256::set_zero(r.Z);
+  soa_store<8>(jac, n, idx, r.X.v, 0);
+  soa_store<8>(jac, n, idx, r.Y.v, 8);
+  soa_store<8>(jac, n, idx, r.Z.v, 16);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Generic prime-order curve (P-256) variable-base: Jacobian window table (768 B / thread).
-template <class C, int BLOCK, int MINBLK>
+// CT: the ECG_FLAG_CONSTTIME variant (masked table scan; pxy == nullptr selects the generator)
+template <class C, int BLOCK, int MINBLK, bool CT = false>
 ECG_KERNEL(BLOCK, MINBLK)
     generic_varbase_kernel(const uint8_t* __restrict__ kb, const uint8_t* __restrict__ pxy,
                            const uint8_t* __restrict__ pinf, size_t n, uint32_t* __restrict__ jac,
@@ -133,11 +172,11 @@ ECG_KERNEL(BLOCK, MINBLK)
   uint32_t k[NL];
   typename F::AffT P;
   bool inf;
-  uint32_t err = load_pair<C>(k, P, inf, kb, pxy, pinf, idx);
+  uint32_t err = CT ? load_pair_or_generator<C>(k, P, inf, kb, pxy, pinf, idx) : load_pair<C>(k, P, inf, kb, pxy, pinf, idx);
   if (err) report_error(status, err, base + idx);
   TabRefJN<NL> tab{gtab + (size_t)blockIdx.x * BLOCK * (8 * 3 * NL) + threadIdx.x, (uint32_t)BLOCK};  // 8 Jacobian entries
   typename F::JacT r;
-  generic_mul_thread<F, C::A_IS_MINUS3>(r, k, P, tab);
+  generic_mul_thread<F, C::A_IS_MINUS3, 0, CT>(r, k, P, tab);
   if (inf || err) F::set_zero(r.Z);
   soa_store<NL>(jac, n, idx, r.X.v, 0);
   soa_store<NL>(jac, n, idx, r.Y.v, NL);

@@ -37,6 +37,21 @@ struct TabRefN {
       y.v[w] = base[(e * 2 * NL + NL + w) * stride];
     }
   }
+  // entry `idx` without a secret-dependent address: every entry is read, the wanted one kept by mask
+  // (LookupTable::select, primeorder/src/tables/lookup.rs:43-65)
+  ECG_D void load_ct(uint32_t idx, FeN<NL>& x, FeN<NL>& y) const {
+#pragma unroll
+    for (int w = 0; w < NL; w++) x.v[w] = y.v[w] = 0;
+#pragma unroll 1
+    for (uint32_t e = 0; e < 8; e++) {
+      const uint32_t m = 0u - (uint32_t)(e == idx);
+#pragma unroll
+      for (int w = 0; w < NL; w++) {
+        x.v[w] |= base[(e * 2 * NL + w) * stride] & m;
+        y.v[w] |= base[(e * 2 * NL + NL + w) * stride] & m;
+      }
+    }
+  }
 };
 typedef TabRefN<8> TabRef;
 // Same, for Jacobian entries (3*NL words: X, Y, Z).
@@ -58,6 +73,20 @@ struct TabRefJN {
       p.X.v[w] = base[(e * 3 * NL + w) * stride];
       p.Y.v[w] = base[(e * 3 * NL + NL + w) * stride];
       p.Z.v[w] = base[(e * 3 * NL + 2 * NL + w) * stride];
+    }
+  }
+  ECG_D void load_ct(uint32_t idx, JacN<NL>& p) const {  // masked scan over all eight entries (see TabRefN::load_ct)
+#pragma unroll
+    for (int w = 0; w < NL; w++) p.X.v[w] = p.Y.v[w] = p.Z.v[w] = 0;
+#pragma unroll 1
+    for (uint32_t e = 0; e < 8; e++) {
+      const uint32_t m = 0u - (uint32_t)(e == idx);
+#pragma unroll
+      for (int w = 0; w < NL; w++) {
+        p.X.v[w] |= base[(e * 3 * NL + w) * stride] & m;
+        p.Y.v[w] |= base[(e * 3 * NL + NL + w) * stride] & m;
+        p.Z.v[w] |= base[(e * 3 * NL + 2 * NL + w) * stride] & m;
+      }
     }
   }
 };
@@ -123,10 +152,13 @@ ECG_D void build_table_iso_a0(const TabRef& tab, Fe& Zg, const Aff& P) {
 #else
 #define ECG_BLOCK_SYNC() ((void)0)
 #endif
-template <class F = FpK256, int PHASE_SYNC = 0>  // 0 none, 1 per phase (doublings | additions), 2 before every point operation
+// CT (ECG_FLAG_CONSTTIME): window-table entries are fetched by a masked scan over all eight entries and the sign folding
+// of the GLV halves is branch-free, so neither addresses nor branches depend on the scalar (what is left: the
+// exceptional-case branches of the Jacobian formulas, reachable only for k = 0 and a negligible set of scalars).
+template <class F = FpK256, int PHASE_SYNC = 0, bool CT = false>  // PHASE_SYNC: 0 none, 1 per phase (doublings | additions), 2 before every point operation
 ECG_D void k256_mul_thread(Jac& r, const uint32_t* k, const Aff& P, const TabRef& tab) {
   GlvHalf g1, g2;
-  glv_split_k256(g1, g2, k);
+  glv_split_k256<CT>(g1, g2, k);
   Fe Zg, beta;
   build_table_iso_a0<F>(tab, Zg, P);
   k256_beta(beta);
@@ -158,7 +190,10 @@ ECG_D void k256_mul_thread(Jac& r, const uint32_t* k, const Aff& P, const TabRef
       uint32_t sneg = half ? g2.neg : g1.neg;
       uint32_t pos = n >> 3;                       // digit sign: n>=8 -> positive
       uint32_t idx = pos ? (n & 7u) : (7u - n);
-      tab.load((int)idx, e.x, e.y);
+      if (CT)
+        tab.load_ct(idx, e.x, e.y);
+      else
+        tab.load((int)idx, e.x, e.y);
       if (half) F::mul(e.x, e.x, beta);
       fe_cneg<F>(e.y, (pos ^ sneg) ^ 1u);              // negative digit XOR negative half-scalar
       jac_madd<F, false>(acc, acc, e);
@@ -186,7 +221,7 @@ ECG_D void k256_mul_thread(Jac& r, const uint32_t* k, const Aff& P, const TabRef
 // 256-bit scalar: implicit top digit +1, then 64 windows of (4 dbl + 1 add) against a table of the eight
 // odd multiples kept in Jacobian form (the shared-denominator trick of build_table_iso_a0 needs a = 0).
 // Replaces primeorder ProjectivePoint::mul / mul_vartime (primeorder/src/projective.rs:133-144, :532-557).
-template <class F, int A_IS_MINUS3, int PHASE_SYNC = 0>
+template <class F, int A_IS_MINUS3, int PHASE_SYNC = 0, bool CT = false>
 ECG_D void generic_mul_thread(typename F::JacT& r, const uint32_t* k, const typename F::AffT& P, const TabRefJN<F::NL>& tab) {
   typedef typename F::JacT Jac;
   typedef typename F::AffT Aff;
@@ -218,7 +253,10 @@ ECG_D void generic_mul_thread(typename F::JacT& r, const uint32_t* k, const type
     uint32_t pos = n >> 3;
     uint32_t idx = pos ? (n & 7u) : (7u - n);
     Jac e;
-    tab.load((int)idx, e);
+    if (CT)
+      tab.load_ct(idx, e);
+    else
+      tab.load((int)idx, e);
     fe_cneg<F>(e.Y, pos ^ 1u);
     jac_add<F, A_IS_MINUS3>(acc, acc, e);
   }

@@ -53,9 +53,17 @@ struct GlvHalf {
 };
 
 // two's-complement 160-bit -> (magnitude, sign); returns false if |v| >= 2^129 (cannot happen for k < n)
+// CT: the negation is computed for every input and selected by mask (ECG_FLAG_CONSTTIME kernels)
+template <bool CT = false>
 ECG_D bool glv_finish(GlvHalf& o, uint32_t* v /*5 limbs*/) {
   uint32_t s = v[4] >> 31;
-  if (s) {
+  if (CT) {  // v = (v ^ m) + s with m = -s: two's-complement negation when s = 1, identity when s = 0
+    const uint32_t m = 0u - s;
+    v[0] = add_cc(v[0] ^ m, s);
+#pragma unroll
+    for (int i = 1; i < 4; i++) v[i] = addc_cc(v[i] ^ m, 0);
+    v[4] = addc(v[4] ^ m, 0);
+  } else if (s) {
     v[0] = sub_cc(0, v[0]);
 #pragma unroll
     for (int i = 1; i < 4; i++) v[i] = subc_cc(0, v[i]);
@@ -75,6 +83,7 @@ ECG_D bool glv_finish(GlvHalf& o, uint32_t* v /*5 limbs*/) {
 }
 
 // secp256k1 GLV split of k (8 LE limbs, k < n).
+template <bool CT = false>
 ECG_D bool glv_split_k256(GlvHalf& h1, GlvHalf& h2, const uint32_t* k) {
   const uint32_t G1[8] = {0x45DBB031u, 0xE893209Au, 0x71E8CA7Fu, 0x3DAA8A14u, 0x9284EB15u, 0xE86C90E4u, 0xA7D46BCDu, 0x3086D221u};
   const uint32_t G2[8] = {0x8AC47F71u, 0x1571B4AEu, 0x9DF506C6u, 0x221208ACu, 0x0ABFE4C4u, 0x6F547FA9u, 0x010E8828u, 0xE4437ED6u};
@@ -106,7 +115,7 @@ ECG_D bool glv_split_k256(GlvHalf& h1, GlvHalf& h2, const uint32_t* k) {
 #pragma unroll
   for (int i = 1; i < 4; i++) v[i] = subc_cc(p[i], q[i]);
   v[4] = subc(p[4], q[4]);
-  bool ok2 = glv_finish(h2, v);
+  bool ok2 = glv_finish<CT>(h2, v);
   // k1 = k - c1*a1 - c2*a2   (mod 2^160)
   mul_limbs<4, 4>(p, c1, A1);
   mul_limbs<5, 4>(q, A2, c2);
@@ -118,7 +127,7 @@ ECG_D bool glv_split_k256(GlvHalf& h1, GlvHalf& h2, const uint32_t* k) {
 #pragma unroll
   for (int i = 1; i < 4; i++) v[i] = subc_cc(v[i], q[i]);
   v[4] = subc(v[4], q[4]);
-  bool ok1 = glv_finish(h1, v);
+  bool ok1 = glv_finish<CT>(h1, v);
   return ok1 & ok2;
 }
 

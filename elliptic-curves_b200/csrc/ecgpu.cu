@@ -516,6 +516,8 @@ struct XGeom {
   static constexpr int MINBLK = NL > 12 ? 2 : NL > 8 ? 3 : 4;
 };
 static size_t vb_block(ecg_curve c) { return c == ECG_SECP256K1 ? K_BLOCK : c == ECG_NISTP256 ? P_BLOCK : c == ECG_NISTP384 ? Q_BLOCK : X_BLOCK; }
+// (the constant-time secp256k1 kernel runs 128-thread blocks: a table slot sized for 256-thread blocks covers it, since the
+//  slot of block b starts at b * BLOCK * words and 128-thread blocks need half as much per block)
 static size_t vb_minblk(ecg_curve c) {
   return c == ECG_SECP256K1 ? K_MINBLK : c == ECG_NISTP256 ? P_MINBLK : c == ECG_NISTP384 ? Q_MINBLK : (flimbs(c) > 12 ? 2 : flimbs(c) > 8 ? 3 : 4);
 }
@@ -538,6 +540,22 @@ static ecg_status launch_varbase(ecg_ctx* ctx, DevState& d, Lane& L, ecg_curve c
   ST_TRY(ensure_tab(ctx, L, curve, n));
   uint32_t* gtab = (uint32_t*)L.buf[B_TAB];
   DOM_BEGIN(ctx, L);
+  if (ctx->flags & ECG_FLAG_CONSTTIME) {  // masked table selects, branch-free sign folding; dp.p == nullptr: P = G
+#if ECG_TU == 0
+    if (curve == ECG_SECP256K1)
+      k256_varbase_ct_kernel<KG_BLOCK, KG_MINBLK><<<grid_for(n, KG_BLOCK), KG_BLOCK, 0, L.s()>>>(dp.k, dp.p, dp.inf, n, jac, gtab, status, base);
+    else if (curve == ECG_NISTP256)
+      generic_varbase_kernel<CurveP256, P_BLOCK, P_MINBLK, true><<<grid_for(n, P_BLOCK), P_BLOCK, 0, L.s()>>>(dp.k, dp.p, dp.inf, n, jac, gtab, status, base);
+    else
+      generic_varbase_kernel<CurveP384, Q_BLOCK, Q_MINBLK, true><<<grid_for(n, Q_BLOCK), Q_BLOCK, 0, L.s()>>>(dp.k, dp.p, dp.inf, n, jac, gtab, status, base);
+#else
+    FOR_CURVE(curve, (generic_varbase_kernel<CV, X_BLOCK, XGeom<CV::F::NL>::MINBLK, true><<<grid_for(n, X_BLOCK), X_BLOCK, 0, L.s()>>>(dp.k, dp.p, dp.inf, n, jac,
+                                                                                                                                gtab, status, base)));
+#endif
+    LAUNCHED(ctx);
+    DOM_END(ctx, L);
+    return ECG_OK;
+  }
 #if ECG_TU == 0
   if (curve == ECG_SECP256K1)
     k256_varbase_kernel<K_BLOCK, K_MINBLK><<<grid_for(n, K_BLOCK), K_BLOCK, 0, L.s()>>>(dp.k, dp.p, dp.inf, n, jac, gtab, status, base);
@@ -815,6 +833,13 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
       ST_TRY(launch_varbase(ctx, d, L, op.curve, cnt, dp, jac, L.status, off));
       break;
     case BatchOp::MULGEN:
+      if (ctx->flags & ECG_FLAG_CONSTTIME) {  // no table indexed by 16 secret bits: the variable-base routine with P = G
+        DevPtrs g = dp;
+        g.p = nullptr;
+        g.inf = nullptr;
+        ST_TRY(launch_varbase(ctx, d, L, op.curve, cnt, g, jac, L.status, off));
+        break;
+      }
       DOM_BEGIN(ctx, L);
       if (inline_loops())
         FOR_CURVE_INL(op.curve, fixedbase_kernel<CV><<<grid_for(cnt, 128), 128, 0, L.s()>>>(dp.k, cnt, d.fb_table[op.curve], jac, L.status, off));
@@ -884,7 +909,8 @@ static std::vector<Shard> chunk_schedule(size_t cnt, size_t wave) {
 
 static ecg_status run_batch_inner(ecg_ctx* ctx, const BatchOp& op, size_t n) {
   std::vector<Shard> shards = make_shards(n, ctx->devs.size());
-  bool need_table = op.kind == BatchOp::MULGEN || op.kind == BatchOp::MULGENADD || op.kind == BatchOp::SCHNORR || op.kind == BatchOp::ECDSA;
+  bool need_table = (op.kind == BatchOp::MULGEN && !(ctx->flags & ECG_FLAG_CONSTTIME)) || op.kind == BatchOp::MULGENADD ||
+                    op.kind == BatchOp::SCHNORR || op.kind == BatchOp::ECDSA;
   for (size_t i = 0; i < ctx->devs.size(); i++) {
     if (shards[i].cnt == 0) continue;
     DevState& d = ctx->devs[i];
@@ -1393,6 +1419,7 @@ static ecg_status lincomb_shard(ecg_ctx* ctx, DevState& d, ecg_curve curve, cons
   ST_TRY(stage_in(ctx, L, B_K, k, sh.off, sh.cnt, fb, &dp.k));
   ST_TRY(stage_in(ctx, L, B_P, P_xy, sh.off, sh.cnt, 2 * fb, &dp.p));
   ST_TRY(stage_in(ctx, L, B_INF, P_inf, sh.off, sh.cnt, 1, &dp.inf));
+  if (ctx->flags & ECG_FLAG_CONSTTIME) per_term = true;  // the bucket method's memory access pattern IS the scalars
   if (sh.cnt >= MSM_MIN_TERMS && !per_term) {
     // bucket method, in pieces of at most MSM_MAX_TERMS terms whose partial sums are added at the end
     const size_t MSM_MAX_TERMS = msm_max_terms();

@@ -42,6 +42,7 @@ LITTLE_ENDIAN = {BIGNP256}
 ECG_OK, ECG_EINVAL, ECG_ESCALAR_RANGE, ECG_ENOT_ON_CURVE, ECG_ECUDA, ECG_ENCCL, ECG_ENOMEM = range(7)
 FLAG_DEVICE_PTRS = 1
 FLAG_ZEROIZE = 2
+FLAG_CONSTTIME = 4  # scalar-independent table selects / sign folding, k*G through the variable-base routine, per-term lincomb
 FOP = {"add": 0, "sub": 1, "neg": 2, "mul": 3, "sqr": 4, "inv": 5}
 
 EXPORTS = [
@@ -167,13 +168,13 @@ def _ptr(a) -> ctypes.c_void_p:
 class Engine:
     """One ecg_ctx.  `devices=[0]` host-pointer mode by default; `device_ptrs=True` takes raw CUDA pointers."""
 
-    def __init__(self, devices: Optional[Sequence[int]] = None, device_ptrs: bool = False, zeroize: bool = False):
+    def __init__(self, devices: Optional[Sequence[int]] = None, device_ptrs: bool = False, zeroize: bool = False, consttime: bool = False):
         self.lib = load_library()
         devs = list(devices) if devices else [0]
         arr = (ctypes.c_int * len(devs))(*devs)
         self._ctx = ctypes.c_void_p(0)
         self.device_ptrs = device_ptrs
-        flags = (FLAG_DEVICE_PTRS if device_ptrs else 0) | (FLAG_ZEROIZE if zeroize else 0)
+        flags = (FLAG_DEVICE_PTRS if device_ptrs else 0) | (FLAG_ZEROIZE if zeroize else 0) | (FLAG_CONSTTIME if consttime else 0)
         rc = self.lib.ecg_ctx_create(arr, len(devs), flags, ctypes.byref(self._ctx))
         if rc != ECG_OK:
             raise EcgError(rc, "ecg_ctx_create failed (is a CUDA device visible? there is no CPU fallback)")

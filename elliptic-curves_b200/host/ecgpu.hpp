@@ -58,8 +58,10 @@ class Engine {
  public:
   // zeroize: clear the device-side copies of scalars, window tables and intermediates after every call
   // (ECG_FLAG_ZEROIZE; the reference zeroizes secrets on drop)
-  explicit Engine(ecg_curve curve, const std::vector<int>& devices = {0}, bool zeroize = false) : curve_(curve) {
-    ecg_status st = ecg_ctx_create(devices.data(), (int)devices.size(), zeroize ? ECG_FLAG_ZEROIZE : 0u, &ctx_);
+  // consttime: ECG_FLAG_CONSTTIME — scalar-independent table selects and sign folding, k*G through the variable-base
+  // routine, per-term lincomb (the analogue of the reference's constant-time Mul; costs measured in bench.py configs.8)
+  explicit Engine(ecg_curve curve, const std::vector<int>& devices = {0}, bool zeroize = false, bool consttime = false) : curve_(curve) {
+    ecg_status st = ecg_ctx_create(devices.data(), (int)devices.size(), (zeroize ? ECG_FLAG_ZEROIZE : 0u) | (consttime ? ECG_FLAG_CONSTTIME : 0u), &ctx_);
     if (st != ECG_OK) throw Error(st, "ecg_ctx_create failed (no CUDA device? there is no CPU fallback)");
   }
   ~Engine() { ecg_ctx_destroy(ctx_); }

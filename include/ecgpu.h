@@ -86,6 +86,17 @@ typedef enum {
                                    that pass secret scalars (the reference zeroizes secrets on drop); costs one
                                    memset per buffer and call */
 
+#define ECG_FLAG_CONSTTIME 4u   /* scalar-independent execution for the entries that take secret scalars — ecg_mul_batch[_x],
+                                   ecg_mul_gen_batch, ecg_lincomb[_partial] — the analogue of the reference's constant-time
+                                   `Mul` / `lincomb` (k256/src/arithmetic/mul.rs:112-163, LookupTable::select
+                                   primeorder/src/tables/lookup.rs:43-65): window-table entries are fetched by a masked scan
+                                   over all entries, the GLV sign folding is branch-free, k*G runs through the variable-base
+                                   routine (no table indexed by 16 scalar bits, like mul_backend::VariableOnly), lincomb
+                                   always takes the per-term path (the bucket method's access pattern is the scalars).
+                                   Left data-dependent: the exceptional-case branches of the Jacobian formulas, reachable
+                                   only for k = 0 (not a NonZeroScalar) and a negligible set of scalars; kernel timing also
+                                   depends on inputs being rejected.  The default (flag clear) is the vartime analogue. */
+
 /* Create a context on the given CUDA devices (NULL/0 = device 0).  With several devices a host-pointer
  * batch is split into contiguous index ranges, one per device; there is no
  * inter-device traffic.  Replaces nothing in the reference (it has no runtime state except the lazily

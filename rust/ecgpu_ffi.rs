@@ -24,6 +24,7 @@ pub const ECG_SECP256K1: i32 = 0;
 pub const ECG_NISTP256: i32 = 1;
 pub const ECG_FLAG_DEVICE_PTRS: u32 = 1;
 pub const ECG_FLAG_ZEROIZE: u32 = 2;
+pub const ECG_FLAG_CONSTTIME: u32 = 4;
 pub const ECG_FOP_ADD: i32 = 0;
 pub const ECG_FOP_SUB: i32 = 1;
 pub const ECG_FOP_NEG: i32 = 2;
@@ -108,9 +109,11 @@ pub struct GpuEngine {
 
 impl GpuEngine {
     /// `zeroize`: clear the device-side copies of inputs and intermediates after every call (ECG_FLAG_ZEROIZE).
-    pub fn new(curve: i32, devices: &[i32], zeroize: bool) -> Result<Self, GpuError> {
+    /// `consttime`: `ECG_FLAG_CONSTTIME` — masked table selects, branch-free sign folding, `k*G` through the variable-base
+    /// routine, per-term `lincomb`: the ctx to use where the scalars are secret (the default is the `*_vartime` analogue).
+    pub fn new(curve: i32, devices: &[i32], zeroize: bool, consttime: bool) -> Result<Self, GpuError> {
         let mut ctx = core::ptr::null_mut();
-        let flags = if zeroize { ECG_FLAG_ZEROIZE } else { 0 };
+        let flags = (if zeroize { ECG_FLAG_ZEROIZE } else { 0 }) | (if consttime { ECG_FLAG_CONSTTIME } else { 0 });
         // SAFETY: out-pointer is valid; the library copies `devices` before returning.
         match unsafe { ecg_ctx_create(devices.as_ptr(), devices.len() as i32, flags, &mut ctx) } {
             ECG_OK => Ok(Self { ctx, curve }),

@@ -836,3 +836,32 @@ extern "C" int simk_hash_to_scalar(int curve, size_t n, const uint8_t* msgs, con
     sim_launch(n, 128, [&] { h2s_kernel<CurveP256>(msgs, offsets, 0, n, dst_prime, dpl, out); });
   return 0;
 }
+
+// ECG_FLAG_CONSTTIME kernels: masked table selects, branch-free GLV sign folding; pxy == nullptr: P = G
+extern "C" int simk_mul_batch_ct(int curve, size_t n, const uint8_t* k, const uint8_t* pxy, const uint8_t* pinf, uint8_t* out_xy,
+                                 uint8_t* out_inf, uint32_t* status) {
+  size_t blocks = (n + SIM_BLOCK - 1) / SIM_BLOCK;
+  status[0] = 0;
+  status[1] = 0xFFFFFFFFu;
+  if (curve == 0) {
+    std::vector<uint32_t> jac(24 * n + 24), gtab(blocks * SIM_BLOCK * K_TAB_WORDS);
+    sim_launch(n, SIM_BLOCK, [&] { k256_varbase_ct_kernel<SIM_BLOCK, 4>(k, pxy, pinf, n, jac.data(), gtab.data(), status, 0); });
+    simk_normalize<CurveK256>(jac, n, out_xy, out_inf);
+  } else if (curve == 1) {
+    std::vector<uint32_t> jac(24 * n + 24), gtab(blocks * SIM_BLOCK * P_TAB_WORDS);
+    sim_launch(n, SIM_BLOCK, [&] { generic_varbase_kernel<CurveP256, SIM_BLOCK, 4, true>(k, pxy, pinf, n, jac.data(), gtab.data(), status, 0); });
+    simk_normalize<CurveP256>(jac, n, out_xy, out_inf);
+  } else if (curve == 2) {
+    std::vector<uint32_t> jac(36 * n + 36), gtab(blocks * SIM_BLOCK * (8 * 36));
+    sim_launch(n, SIM_BLOCK, [&] { generic_varbase_kernel<CurveP384, SIM_BLOCK, 4, true>(k, pxy, pinf, n, jac.data(), gtab.data(), status, 0); });
+    simk_normalize<CurveP384>(jac, n, out_xy, out_inf);
+  } else {
+    SIM_FOR_EXT(curve, {
+      constexpr size_t NLc = CV::F::NL;
+      std::vector<uint32_t> jx(3 * NLc * n + 36), gtab(blocks * SIM_BLOCK * (8 * 3 * NLc));
+      sim_launch(n, SIM_BLOCK, [&] { generic_varbase_kernel<CV, SIM_BLOCK, 4, true>(k, pxy, pinf, n, jx.data(), gtab.data(), status, 0); });
+      simk_normalize<CV>(jx, n, out_xy, out_inf);
+    });
+  }
+  return 0;
+}

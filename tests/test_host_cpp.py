@@ -123,6 +123,12 @@ int main() {
     const char* P[] = {@P256@};
     if (run(ECG_SECP256K1, K)) return 1;
     if (run(ECG_NISTP256, P)) return 1;
+    {  // the constant-time ctx computes the same points (masked selects, k*G through the variable-base routine)
+      Engine ct(ECG_SECP256K1, {0}, true, /*consttime=*/true);
+      std::vector<Scalar> five(1); five[0][31] = 5;
+      AffinePoint G = pt(K[0], K[1]), G5 = pt(K[2], K[3]);
+      REQUIRE(same(ct.mul_by_generator(five)[0], G5) && same(ct.mul({G}, five)[0], G5) && same(ct.lincomb({G, G5}, {five[0], Scalar{}}), G5));
+    }
     // signatures
     Engine k1(ECG_SECP256K1), p1(ECG_NISTP256);
     auto sv = k1.schnorr_verify({h32("@BPK@"), h32("@BPK@")}, {h32("@BMSG@"), h32("@BMSG2@")}, {h64("@BSIG@"), h64("@BSIG@")});
