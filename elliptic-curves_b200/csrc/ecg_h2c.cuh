@@ -1,24 +1,28 @@
-// ecg_h2c.cuh — hash to curve (RFC 9380) for the two suites the reference implements with SHA-256:
+// ecg_h2c.cuh — hash to curve (RFC 9380) for the four Weierstrass suites the reference implements:
 //   secp256k1_XMD:SHA-256_SSWU_{RO,NU}_  (k256/src/arithmetic/hash2curve.rs:14-20,52-148: simplified SWU on the 3-isogenous
 //                                          curve E', then the isogeny map :169-258)
 //   P256_XMD:SHA-256_SSWU_{RO,NU}_       (p256/src/arithmetic/hash2curve.rs:13-75 over primeorder/src/osswu.rs:60-146)
+//   P384_XMD:SHA-384_SSWU_{RO,NU}_       (p384/src/arithmetic/hash2curve.rs:13-75, L = 72)
+//   P521_XMD:SHA-512_SSWU_{RO,NU}_       (p521/src/arithmetic/hash2curve.rs:13-76, L = 98)
 // and the drivers hash2curve/src/group_digest.rs:88-143 (hash_from_bytes = two field elements, two maps, one addition;
 // encode_from_bytes = one map; hash_to_scalar), hash2curve/src/hash2field.rs + hash2field/expand_msg/xmd.rs:43-99
 // (hash_to_field over expand_message_xmd).  SURVEY.md section 8(f) rank 4 ("hash-to-curve front end").
 //
-// One thread per message: streaming SHA-256 over the message bytes (b_0), the chained blocks b_1..b_ell, the 48-byte
-// reductions d0 * 2^192 + d1, the straight-line SSWU with ONE exponentiation per map (sqrt_ratio for q = 3 mod 4) and
+// One thread per message: streaming SHA-2 over the message bytes (b_0), the chained blocks b_1..b_ell, the L-byte
+// reductions (24-byte chunks folded with 2^192, which is d0 * 2^192 + d1 for L = 48), the straight-line SSWU with ONE exponentiation per map (sqrt_ratio for q = 3 mod 4) and
 // no inversion: the map leaves x as a fraction, which becomes the Z of a Jacobian point (secp256k1: the isogeny is
 // evaluated on the homogenised polynomials), the two points are added with the library's Jacobian addition and the
 // batch is normalised by normalize_kernel (one inversion per ~32 points).
 #pragma once
 #include "ecg_curves.cuh"
 #include "ecg_verify.cuh"
+#include "ecg_h2c_consts.cuh"
 
 namespace ecg {
 
 // ---- streaming SHA-256 (byte-granular updates; compression from ecg_verify.cuh) --------------------------------
 struct Sha256Stream {
+  static constexpr int B = 32, S = 64;  // digest / block bytes
   uint32_t st[8];
   uint32_t blk[16];
   uint32_t fill;   // bytes in blk
@@ -53,30 +57,139 @@ struct Sha256Stream {
     put(w >> 8);
     put(w);
   }
-  ECG_D void finish(uint32_t* digest /* 8 big-endian words */) {
+  ECG_D void zero_block() {  // Z_pad: one block of zero bytes
+    flush_block();
+    total += 64;
+  }
+  ECG_D void finish(uint8_t* digest /* B bytes */) {
     uint64_t bits = total * 8;
     put(0x80u);
-    total--;  // padding is not message
     if (fill > 56) flush_block();
     blk[14] = (uint32_t)(bits >> 32);
     blk[15] = (uint32_t)bits;
     sha256_compress(st, blk);
 #pragma unroll
-    for (int i = 0; i < 8; i++) digest[i] = st[i];
+    for (int i = 0; i < 32; i++) digest[i] = (uint8_t)(st[i >> 2] >> (24 - 8 * (i & 3)));
   }
 };
 
-// uniform[0 .. 32*ELL) = expand_message_xmd(msg, DST, len_in_bytes) as big-endian words (RFC 9380 section 5.3.1,
+// ---- SHA-512 / SHA-384 ------------------------------------------------------------------------------------------
+ECG_D uint64_t sha_rotr64(uint64_t x, int n) { return (x >> n) | (x << (64 - n)); }
+ECG_D void sha512_compress(uint64_t* st, const uint64_t* block) {
+  const uint64_t K[80] = {
+      0x428a2f98d728ae22ull, 0x7137449123ef65cdull, 0xb5c0fbcfec4d3b2full, 0xe9b5dba58189dbbcull, 0x3956c25bf348b538ull, 0x59f111f1b605d019ull,
+      0x923f82a4af194f9bull, 0xab1c5ed5da6d8118ull, 0xd807aa98a3030242ull, 0x12835b0145706fbeull, 0x243185be4ee4b28cull, 0x550c7dc3d5ffb4e2ull,
+      0x72be5d74f27b896full, 0x80deb1fe3b1696b1ull, 0x9bdc06a725c71235ull, 0xc19bf174cf692694ull, 0xe49b69c19ef14ad2ull, 0xefbe4786384f25e3ull,
+      0x0fc19dc68b8cd5b5ull, 0x240ca1cc77ac9c65ull, 0x2de92c6f592b0275ull, 0x4a7484aa6ea6e483ull, 0x5cb0a9dcbd41fbd4ull, 0x76f988da831153b5ull,
+      0x983e5152ee66dfabull, 0xa831c66d2db43210ull, 0xb00327c898fb213full, 0xbf597fc7beef0ee4ull, 0xc6e00bf33da88fc2ull, 0xd5a79147930aa725ull,
+      0x06ca6351e003826full, 0x142929670a0e6e70ull, 0x27b70a8546d22ffcull, 0x2e1b21385c26c926ull, 0x4d2c6dfc5ac42aedull, 0x53380d139d95b3dfull,
+      0x650a73548baf63deull, 0x766a0abb3c77b2a8ull, 0x81c2c92e47edaee6ull, 0x92722c851482353bull, 0xa2bfe8a14cf10364ull, 0xa81a664bbc423001ull,
+      0xc24b8b70d0f89791ull, 0xc76c51a30654be30ull, 0xd192e819d6ef5218ull, 0xd69906245565a910ull, 0xf40e35855771202aull, 0x106aa07032bbd1b8ull,
+      0x19a4c116b8d2d0c8ull, 0x1e376c085141ab53ull, 0x2748774cdf8eeb99ull, 0x34b0bcb5e19b48a8ull, 0x391c0cb3c5c95a63ull, 0x4ed8aa4ae3418acbull,
+      0x5b9cca4f7763e373ull, 0x682e6ff3d6b2b8a3ull, 0x748f82ee5defb2fcull, 0x78a5636f43172f60ull, 0x84c87814a1f0ab72ull, 0x8cc702081a6439ecull,
+      0x90befffa23631e28ull, 0xa4506cebde82bde9ull, 0xbef9a3f7b2c67915ull, 0xc67178f2e372532bull, 0xca273eceea26619cull, 0xd186b8c721c0c207ull,
+      0xeada7dd6cde0eb1eull, 0xf57d4f7fee6ed178ull, 0x06f067aa72176fbaull, 0x0a637dc5a2c898a6ull, 0x113f9804bef90daeull, 0x1b710b35131c471bull,
+      0x28db77f523047d84ull, 0x32caab7b40c72493ull, 0x3c9ebe0a15c9bebcull, 0x431d67c49c100d4cull, 0x4cc5d4becb3e42b6ull, 0x597f299cfc657e2aull,
+      0x5fcb6fab3ad6faecull, 0x6c44198c4a475817ull};
+  uint64_t w[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) w[i] = block[i];
+  uint64_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll 1
+  for (int i = 0; i < 80; i++) {
+    uint64_t wi;
+    if (i < 16) {
+      wi = w[i & 15];
+    } else {
+      uint64_t w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
+      uint64_t s0 = sha_rotr64(w15, 1) ^ sha_rotr64(w15, 8) ^ (w15 >> 7);
+      uint64_t s1 = sha_rotr64(w2, 19) ^ sha_rotr64(w2, 61) ^ (w2 >> 6);
+      wi = w[i & 15] + s0 + w[(i - 7) & 15] + s1;
+      w[i & 15] = wi;
+    }
+    uint64_t S1 = sha_rotr64(e, 14) ^ sha_rotr64(e, 18) ^ sha_rotr64(e, 41);
+    uint64_t ch = (e & f) ^ (~e & g);
+    uint64_t t1 = h + S1 + ch + K[i] + wi;
+    uint64_t S0 = sha_rotr64(a, 28) ^ sha_rotr64(a, 34) ^ sha_rotr64(a, 39);
+    uint64_t mj = (a & b) ^ (a & c) ^ (b & c);
+    uint64_t t2 = S0 + mj;
+    h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+  }
+  st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+template <bool IS384>
+struct Sha512Stream {
+  static constexpr int B = IS384 ? 48 : 64, S = 128;
+  uint64_t st[8];
+  uint64_t blk[16];
+  uint32_t fill;
+  uint64_t total;
+  ECG_D void init() {
+    const uint64_t iv512[8] = {0x6a09e667f3bcc908ull, 0xbb67ae8584caa73bull, 0x3c6ef372fe94f82bull, 0xa54ff53a5f1d36f1ull,
+                               0x510e527fade682d1ull, 0x9b05688c2b3e6c1full, 0x1f83d9abfb41bd6bull, 0x5be0cd19137e2179ull};
+    const uint64_t iv384[8] = {0xcbbb9d5dc1059ed8ull, 0x629a292a367cd507ull, 0x9159015a3070dd17ull, 0x152fecd8f70e5939ull,
+                               0x67332667ffc00b31ull, 0x8eb44a8768581511ull, 0xdb0c2e0d64f98fa7ull, 0x47b5481dbefa4fa4ull};
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = IS384 ? iv384[i] : iv512[i];
+#pragma unroll
+    for (int i = 0; i < 16; i++) blk[i] = 0;
+    fill = 0;
+    total = 0;
+  }
+  ECG_D void flush_block() {
+    sha512_compress(st, blk);
+#pragma unroll
+    for (int i = 0; i < 16; i++) blk[i] = 0;
+    fill = 0;
+  }
+  ECG_D void put(uint32_t byte) {
+    blk[fill >> 3] |= (uint64_t)(byte & 0xFFu) << (56 - 8 * (fill & 7));
+    fill++;
+    total++;
+    if (fill == 128) flush_block();
+  }
+  ECG_D void update(const uint8_t* p, size_t len) {
+    for (size_t i = 0; i < len; i++) put(p[i]);
+  }
+  ECG_D void zero_block() {
+    flush_block();
+    total += 128;
+  }
+  ECG_D void finish(uint8_t* digest /* B bytes */) {
+    uint64_t bits = total * 8;
+    put(0x80u);
+    if (fill > 112) flush_block();
+    blk[15] = bits;  // the 128-bit length: the high word stays zero
+    sha512_compress(st, blk);
+#pragma unroll
+    for (int i = 0; i < B; i++) digest[i] = (uint8_t)(st[i >> 3] >> (56 - 8 * (i & 7)));
+  }
+};
+template <int HASH>
+struct H2cHash;
+template <>
+struct H2cHash<256> {
+  typedef Sha256Stream T;
+};
+template <>
+struct H2cHash<384> {
+  typedef Sha512Stream<true> T;
+};
+template <>
+struct H2cHash<512> {
+  typedef Sha512Stream<false> T;
+};
+
+// uniform[0 .. B*ELL) = expand_message_xmd(msg, DST, len_in_bytes) (RFC 9380 section 5.3.1,
 // hash2curve/src/hash2field/expand_msg/xmd.rs:43-99).  dst_prime = DST || I2OSP(len(DST), 1) (an oversize DST is
-// replaced by its hash on the host: expand_msg.rs:76-95).
-template <int ELL>
-ECG_D void expand_message_xmd_sha256(uint32_t* uniform, const uint8_t* msg, size_t msg_len, const uint8_t* dst_prime, uint32_t dst_prime_len,
-                                     uint32_t len_in_bytes) {
-  Sha256Stream h;
-  uint32_t b0[8], bi[8];
+// replaced by its hash on the host: expand_msg.rs:76-95).  HS: the streaming hash (digest B bytes, block S bytes).
+template <class HS, int ELL>
+ECG_D void expand_message_xmd(uint8_t* uniform, const uint8_t* msg, size_t msg_len, const uint8_t* dst_prime, uint32_t dst_prime_len,
+                              uint32_t len_in_bytes) {
+  HS h;
+  uint8_t b0[HS::B], bi[HS::B];
   h.init();
-  h.flush_block();  // Z_pad: one block of zero bytes
-  h.total = 64;
+  h.zero_block();
   h.update(msg, msg_len);
   h.put(len_in_bytes >> 8);
   h.put(len_in_bytes);
@@ -86,122 +199,31 @@ ECG_D void expand_message_xmd_sha256(uint32_t* uniform, const uint8_t* msg, size
 #pragma unroll 1
   for (int i = 1; i <= ELL; i++) {
     h.init();
-#pragma unroll
-    for (int w = 0; w < 8; w++) h.put_word_be(i == 1 ? b0[w] : (b0[w] ^ bi[w]));
+#pragma unroll 1
+    for (int j = 0; j < HS::B; j++) h.put(i == 1 ? b0[j] : (uint32_t)(b0[j] ^ bi[j]));
     h.put((uint32_t)i);
     h.update(dst_prime, dst_prime_len);
     h.finish(bi);
-#pragma unroll
-    for (int w = 0; w < 8; w++) uniform[8 * (i - 1) + w] = bi[w];
+#pragma unroll 1
+    for (int j = 0; j < HS::B; j++) uniform[HS::B * (i - 1) + j] = bi[j];
   }
 }
 
-// ---- per-suite constants (canonical integers; converted to the field's internal form where they are used) --------
-// C2 = sqrt(-Z) as sqrt_ratio_3mod4 of primeorder/src/osswu.rs:60-88 uses it (P-256: sqrt(10), the reference's value;
-// secp256k1: sqrt(11) — the reference's own k256 map is the older straight-line variant whose constant is sqrt(-Z^3),
-// k256/src/arithmetic/hash2curve.rs:64-69; both produce the same point, the sign of y being fixed by sgn0 at the end).
-template <class C>
-struct H2cSuite;
-template <>
-struct H2cSuite<CurveK256> {
-  static constexpr bool ISOGENY = true;
-  ECG_D static void A(Fe& r) {
-    const uint32_t t[8] = {0x1A444533u, 0x405447C0u, 0xCB6F0E5Du, 0xE953D363u, 0xF0F5D272u, 0xA08A5558u, 0xDD661ADCu, 0x3F8731ABu};
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = t[i];
-  }
-  ECG_D static void B(Fe& r) {
-    const uint32_t t[8] = {0x000006EBu, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u};
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = t[i];
-  }
-  ECG_D static void Z(Fe& r) {
-    const uint32_t t[8] = {0xFFFFFC24u, 0xFFFFFFFEu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = t[i];
-  }
-  ECG_D static void C2(Fe& r) {
-    const uint32_t t[8] = {0x303C4A59u, 0x286729C8u, 0xA74789DDu, 0xEC184F00u, 0x8F842AFEu, 0x7AD13FB3u, 0x724013E5u, 0x31FDF302u};
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = t[i];
-  }
-  ECG_D static void F_2_192(Fe& r) {
-    const uint32_t t[8] = {0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000001u, 0x00000000u};
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = t[i];
-  }
-  ECG_D static uint32_t C1(int i) {  // (p - 3) / 4, the exponent of sqrt_ratio_3mod4
-    const uint32_t t[8] = {0xBFFFFF0Bu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x3FFFFFFFu};
-    return t[i];
-  }
-  ECG_D static void XNUM(Fe& r, int k) {  // coefficient of x^k
-    const uint32_t t[4][8] = {{0xAAAAA8C7u, 0x8E38E38Du, 0xE38E38E3u, 0x38E38E38u, 0x8E38E38Eu, 0xE38E38E3u, 0x38E38E38u, 0x8E38E38Eu}, {0xF17C6581u, 0xDFFF1044u, 0x0BF63B92u, 0xD595D2FCu, 0xA7FD44C5u, 0xB9F315CEu, 0x0BC321D5u, 0x07D3D4C8u}, {0x3D9DD262u, 0x4ECBD0B5u, 0x037C4031u, 0xE4506144u, 0xCA25CAECu, 0xE2A413DEu, 0x23F234E6u, 0x534C328Du}, {0xAAAAA88Cu, 0x8E38E38Du, 0xE38E38E3u, 0x38E38E38u, 0x8E38E38Eu, 0xE38E38E3u, 0x38E38E38u, 0x8E38E38Eu}};
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = t[k][i];
-  }
-  ECG_D static void XDEN(Fe& r, int k) {  // coefficient of x^k
-    const uint32_t t[3][8] = {{0x781EB49Bu, 0x9FE6B745u, 0x42F8487Du, 0x86CD4095u, 0xB7B640DDu, 0x9CA34CCBu, 0x3D94918Au, 0xD3577119u}, {0x2A8C6D14u, 0xC52A5661u, 0x1F5E41BBu, 0x06D36B64u, 0x1B542254u, 0xF7C4B2D5u, 0x4383DC1Du, 0xEDADC6F6u}, {0x00000001u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u}};
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = t[k][i];
-  }
-  ECG_D static void YNUM(Fe& r, int k) {  // coefficient of x^k
-    const uint32_t t[4][8] = {{0x8E38E23Cu, 0xA12F684Bu, 0x12F684BDu, 0x2F684BDAu, 0xF684BDA1u, 0x684BDA12u, 0x84BDA12Fu, 0x4BDA12F6u}, {0x201D71A3u, 0xDFFC90FCu, 0xD686DA6Fu, 0x647AB046u, 0x12A0A6D5u, 0xA9D0A54Bu, 0xD5CB7C0Fu, 0xC75E0C32u}, {0x9ECEE931u, 0xA765E85Au, 0x01BE2018u, 0x722830A2u, 0x6512E576u, 0x715209EFu, 0x91F91A73u, 0x29A61946u}, {0x38E38D84u, 0x84BDA12Fu, 0x4BDA12F6u, 0xBDA12F68u, 0xDA12F684u, 0xA12F684Bu, 0x12F684BDu, 0x2F684BDAu}};
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = t[k][i];
-  }
-  ECG_D static void YDEN(Fe& r, int k) {  // coefficient of x^k
-    const uint32_t t[4][8] = {{0xFFFFF93Bu, 0xFFFFFFFEu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, {0x685C2573u, 0xDFB425D2u, 0xC8E8D978u, 0x9467C1BFu, 0x2722C298u, 0xD5E9E663u, 0xB8BDB49Fu, 0x7A06534Bu}, {0xBFD2A76Fu, 0xA7BF8192u, 0x2F0D6299u, 0x0A3D2116u, 0xA8FE337Eu, 0xF3A70C3Fu, 0x6545CA2Cu, 0x6484AA71u}, {0x00000001u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u}};
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = t[k][i];
-  }
-};
-template <>
-struct H2cSuite<CurveP256> {
-  static constexpr bool ISOGENY = false;
-  ECG_D static void A(Fe& r) {
-    const uint32_t t[8] = {0xFFFFFFFCu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000001u, 0xFFFFFFFFu};
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = t[i];
-  }
-  ECG_D static void B(Fe& r) {
-    const uint32_t t[8] = {0x27D2604Bu, 0x3BCE3C3Eu, 0xCC53B0F6u, 0x651D06B0u, 0x769886BCu, 0xB3EBBD55u, 0xAA3A93E7u, 0x5AC635D8u};
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = t[i];
-  }
-  ECG_D static void Z(Fe& r) {
-    const uint32_t t[8] = {0xFFFFFFF5u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000001u, 0xFFFFFFFFu};
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = t[i];
-  }
-  ECG_D static void C2(Fe& r) {
-    const uint32_t t[8] = {0xE433C47Fu, 0x2CCD3427u, 0x4C55D5B6u, 0x7B8D1FF8u, 0x5180AAB2u, 0xC978FC67u, 0xE1D89B99u, 0xDA538E3Bu};
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = t[i];
-  }
-  ECG_D static void F_2_192(Fe& r) {
-    const uint32_t t[8] = {0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000001u, 0x00000000u};
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = t[i];
-  }
-  ECG_D static uint32_t C1(int i) {  // (p - 3) / 4, the exponent of sqrt_ratio_3mod4
-    const uint32_t t[8] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0x3FFFFFFFu, 0x00000000u, 0x00000000u, 0x40000000u, 0xC0000000u, 0x3FFFFFFFu};
-    return t[i];
-  }
-};
 
-// r = a^((p-3)/4), fixed 4-bit windows over the public exponent (252 squarings + 63 + 14 multiplications)
+
+// r = a^((p-3)/4), fixed 4-bit windows over the public exponent (32 NL - 4 squarings + 8 NL + 14 multiplications)
 template <class C>
-ECG_D void h2c_pow_c1(Fe& r, const Fe& a) {
+ECG_D void h2c_pow_c1(typename C::F::FeT& r, const typename C::F::FeT& a) {
   typedef typename C::F F;
-  Fe tab[16];
+  typename F::FeT tab[16];
   F::set_one(tab[0]);
   tab[1] = a;
 #pragma unroll 1
   for (int i = 2; i < 16; i++) F::mul(tab[i], tab[i - 1], a);
-  Fe acc;
+  typename F::FeT acc;
   F::set_one(acc);
 #pragma unroll 1
-  for (int w = 63; w >= 0; w--) {
+  for (int w = 8 * F::NL - 1; w >= 0; w--) {
     F::sqr_n(acc, acc, 4);
     uint32_t d = (H2cSuite<C>::C1(w >> 3) >> (4 * (w & 7))) & 15u;
     F::mul(acc, acc, tab[d]);
@@ -212,9 +234,9 @@ ECG_D void h2c_pow_c1(Fe& r, const Fe& a) {
 // sqrt_ratio for q = 3 (mod 4): primeorder/src/osswu.rs:60-88 (RFC 9380 F.2.1.2).  Returns is_square(u / v); y = sqrt(u / v) if
 // it is one, sqrt(Z u / v) otherwise.
 template <class C>
-ECG_D bool h2c_sqrt_ratio(Fe& y, const Fe& u, const Fe& v, const Fe& c2) {
+ECG_D bool h2c_sqrt_ratio(typename C::F::FeT& y, const typename C::F::FeT& u, const typename C::F::FeT& v, const typename C::F::FeT& c2) {
   typedef typename C::F F;
-  Fe tv1, tv2, tv3, y1, y2;
+  typename F::FeT tv1, tv2, tv3, y1, y2;
   F::sqr(tv1, v);
   F::mul(tv2, u, v);
   F::mul(tv1, tv1, tv2);
@@ -226,14 +248,14 @@ ECG_D bool h2c_sqrt_ratio(Fe& y, const Fe& u, const Fe& v, const Fe& c2) {
   F::sub(tv3, tv3, u);
   bool is_qr = F::is_zero(tv3);
 #pragma unroll
-  for (int i = 0; i < 8; i++) y.v[i] = is_qr ? y1.v[i] : y2.v[i];
+  for (int i = 0; i < F::NL; i++) y.v[i] = is_qr ? y1.v[i] : y2.v[i];
   return is_qr;
 }
 
 // parity of the canonical representative (Sgn0: k256/src/arithmetic/hash2curve.rs:46-50, p256/.../hash2curve.rs:38-42)
 template <class C>
-ECG_D uint32_t h2c_sgn0(const Fe& a) {
-  Fe t;
+ECG_D uint32_t h2c_sgn0(const typename C::F::FeT& a) {
+  typename C::F::FeT t;
   C::F::to_canonical(t, a);
   return t.v[0] & 1u;
 }
@@ -241,9 +263,11 @@ ECG_D uint32_t h2c_sgn0(const Fe& a) {
 // simplified SWU, straight line (primeorder/src/osswu.rs:92-146, RFC 9380 F.2): the point (xn / xd, y) on the curve
 // y^2 = x^3 + A x + B of the suite (secp256k1: the isogenous curve E').  u in internal form.
 template <class C>
-ECG_D void h2c_sswu(Fe& xn, Fe& xd, Fe& y, const Fe& u) {
+ECG_D void h2c_sswu(typename C::F::FeT& xn, typename C::F::FeT& xd, typename C::F::FeT& y, const typename C::F::FeT& u) {
   typedef typename C::F F;
+  typedef typename F::FeT Fe;
   typedef H2cSuite<C> S;
+  constexpr int NL = F::NL;
   Fe A, B, Z, c2, one, tv1, tv2, tv3, tv4, tv5, tv6, x, y1, t;
   S::A(t);
   F::from_canonical(A, t);
@@ -263,7 +287,7 @@ ECG_D void h2c_sswu(Fe& xn, Fe& xd, Fe& y, const Fe& u) {
   F::neg(t, tv2);          // 7: tv4 = CMOV(Z, -tv2, tv2 != 0)
   bool z2 = F::is_zero(tv2);
 #pragma unroll
-  for (int i = 0; i < 8; i++) tv4.v[i] = z2 ? Z.v[i] : t.v[i];
+  for (int i = 0; i < NL; i++) tv4.v[i] = z2 ? Z.v[i] : t.v[i];
   F::mul(tv4, A, tv4);     // 8
   F::sqr(tv2, tv3);        // 9
   F::sqr(tv6, tv4);        // 10
@@ -278,7 +302,7 @@ ECG_D void h2c_sswu(Fe& xn, Fe& xd, Fe& y, const Fe& u) {
   F::mul(y, tv1, u);       // 19
   F::mul(y, y, y1);        // 20
 #pragma unroll
-  for (int i = 0; i < 8; i++) {  // 21, 22
+  for (int i = 0; i < NL; i++) {  // 21, 22
     x.v[i] = is_sq ? tv3.v[i] : x.v[i];
     y.v[i] = is_sq ? y1.v[i] : y.v[i];
   }
@@ -289,14 +313,15 @@ ECG_D void h2c_sswu(Fe& xn, Fe& xd, Fe& y, const Fe& u) {
 }
 
 // map_to_curve as a Jacobian point of the target curve (no inversion).
-//   P-256: (xn / xd, y) is the point: (X : Y : Z) = (xn xd : y xd^3 : xd).
+//   P-256 / P-384 / P-521: (xn / xd, y) is the point: (X : Y : Z) = (xn xd : y xd^3 : xd).
 //   secp256k1: the 3-isogeny E' -> E (k256/src/arithmetic/hash2curve.rs:169-258, RFC 9380 E.1) on x' = N / D:
 //     x = XN / (D XD),  y = y' YN / YD  with the homogenised polynomials XN = sum k_i N^i D^(3-i), XD = N^2 + ..., so
 //     (X : Y : Z) = (XN D XD YD^2 : y' YN D^3 XD^3 YD^2 : D XD YD); a vanishing denominator gives Z = 0, the identity
 //     (RFC 9380 section 6.6.3: exceptional cases of the isogeny map to the identity).
 template <class C>
-ECG_D void h2c_map_to_curve(Jac& r, const Fe& u) {
+ECG_D void h2c_map_to_curve(typename C::F::JacT& r, const typename C::F::FeT& u) {
   typedef typename C::F F;
+  typedef typename F::FeT Fe;
   typedef H2cSuite<C> S;
   Fe N, D, y;
   h2c_sswu<C>(N, D, y, u);
@@ -362,23 +387,32 @@ ECG_D void h2c_map_to_curve(Jac& r, const Fe& u) {
   }
 }
 
-// 48 uniform bytes (12 big-endian words) -> field element d0 * 2^192 + d1 in internal form
-// (Reduce<Array<u8, U48>> for FieldElement: k256/src/arithmetic/hash2curve.rs:22-44, p256/.../hash2curve.rs:21-36)
-template <class C>
-ECG_D void h2c_field_from_okm(Fe& r, const uint32_t* w /* 12 words, most significant first */) {
-  typedef typename C::F F;
-  Fe d0, d1, f;
+// L uniform bytes (big-endian integer) -> its residue in the field policy FF (internal form): 24-byte chunks, most
+// significant first, folded with 2^192 — for L = 48 this is the reference's d0 * 2^192 + d1
+// (Reduce<Array<u8, U48>> for FieldElement, k256/src/arithmetic/hash2curve.rs:22-44; U72: p384/.../hash2curve.rs:21-38; U98: p521)
+template <class FF, int L>
+ECG_D void h2c_from_okm(typename FF::FeT& r, const uint8_t* okm, const typename FF::FeT& f_2_192 /* internal form */) {
+  typedef typename FF::FeT Fe;
+  constexpr int NL = FF::NL;
+  constexpr int FIRST = (L % 24) ? (L % 24) : 24;
+  int pos = 0;
+  FF::set_zero(r);
+#pragma unroll 1
+  for (int c = 0; pos < L; c++) {
+    const int len = c == 0 ? FIRST : 24;
+    Fe d;
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    d0.v[i] = i < 6 ? w[5 - i] : 0u;
-    d1.v[i] = i < 6 ? w[11 - i] : 0u;
+    for (int i = 0; i < NL; i++) d.v[i] = 0;
+#pragma unroll 1
+    for (int j = 0; j < len; j++) {  // byte of weight 256^(len - 1 - j)
+      const int wgt = len - 1 - j;
+      d.v[wgt >> 2] |= (uint32_t)okm[pos + j] << (8 * (wgt & 3));
+    }
+    FF::from_canonical(d, d);
+    if (c > 0) FF::mul(r, r, f_2_192);
+    FF::add(r, r, d);
+    pos += len;
   }
-  F::from_canonical(d0, d0);
-  F::from_canonical(d1, d1);
-  H2cSuite<C>::F_2_192(f);
-  F::from_canonical(f, f);
-  F::mul(d0, d0, f);
-  F::add(r, d0, d1);
 }
 
 }  // namespace ecg
@@ -390,52 +424,54 @@ ECG_KERNEL(128)
     h2c_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ offsets, uint64_t msgs_base, size_t n,
                const uint8_t* __restrict__ dst_prime, uint32_t dst_prime_len, uint32_t* __restrict__ jac) {
   typedef typename C::F F;
+  typedef ecg::H2cSuite<C> S;
+  typedef typename ecg::H2cHash<S::HASH>::T HS;
+  constexpr int NL = F::NL, L = S::L, COUNT = NU ? 1 : 2, ELL = (COUNT * L + HS::B - 1) / HS::B;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const uint8_t* m = msgs + (offsets[idx] - msgs_base);
   const size_t mlen = (size_t)(offsets[idx + 1] - offsets[idx]);
-  constexpr int ELL = NU ? 2 : 3;
-  uint32_t uniform[8 * ELL];
-  ecg::expand_message_xmd_sha256<ELL>(uniform, m, mlen, dst_prime, dst_prime_len, NU ? 48u : 96u);
-  ecg::Fe u0;
-  ecg::h2c_field_from_okm<C>(u0, uniform);
-  ecg::Jac q0;
+  uint8_t uniform[ELL * HS::B];
+  ecg::expand_message_xmd<HS, ELL>(uniform, m, mlen, dst_prime, dst_prime_len, (uint32_t)(COUNT * L));
+  typename F::FeT f192, u0;
+  S::F_2_192(f192);
+  F::from_canonical(f192, f192);
+  ecg::h2c_from_okm<F, L>(u0, uniform, f192);
+  typename F::JacT q0;
   ecg::h2c_map_to_curve<C>(q0, u0);
   if (!NU) {
-    ecg::Fe u1;
-    ecg::Jac q1;
-    ecg::h2c_field_from_okm<C>(u1, uniform + 12);
+    typename F::FeT u1;
+    typename F::JacT q1;
+    ecg::h2c_from_okm<F, L>(u1, uniform + L, f192);
     ecg::h2c_map_to_curve<C>(q1, u1);
-    ecg::jac_add<F, C::A_IS_MINUS3>(q0, q0, q1);  // both curves have cofactor 1: clear_cofactor is the identity map
+    ecg::jac_add<F, C::A_IS_MINUS3>(q0, q0, q1);  // all four curves have cofactor 1: clear_cofactor is the identity map
   }
-  soa_store<8>(jac, n, idx, q0.X.v, 0);
-  soa_store<8>(jac, n, idx, q0.Y.v, 8);
-  soa_store<8>(jac, n, idx, q0.Z.v, 16);
+  soa_store<NL>(jac, n, idx, q0.X.v, 0);
+  soa_store<NL>(jac, n, idx, q0.Y.v, NL);
+  soa_store<NL>(jac, n, idx, q0.Z.v, 2 * NL);
 }
 
-// hash_to_scalar (hash2curve/src/group_digest.rs:131-143 with L = 48: Reduce<Array<u8, U48>> for Scalar,
-// k256/src/arithmetic/hash2curve.rs:151-166): out[i] = (d0 * 2^192 + d1) mod n as 32 big-endian bytes
-template <class C>
+// hash_to_scalar (hash2curve/src/group_digest.rs:131-143: hash_to_field with the group order as modulus, L as for the field;
+// Reduce<Array<u8, U48 / U72 / U98>> for Scalar, k256/src/arithmetic/hash2curve.rs:151-166, p384 / p521 likewise):
+// out[i] = OS2IP(uniform) mod n as one canonical FB-byte record.  FN: the scalar field as a Montgomery policy over n.
+template <class C, class FN>
 ECG_KERNEL(128)
     h2s_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ offsets, uint64_t msgs_base, size_t n,
                const uint8_t* __restrict__ dst_prime, uint32_t dst_prime_len, uint8_t* __restrict__ out) {
-  typedef ecg::FnMont<C> N;
+  typedef ecg::H2cSuite<C> S;
+  typedef typename ecg::H2cHash<S::HASH>::T HS;
+  constexpr int L = S::L, ELL = (L + HS::B - 1) / HS::B;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const uint8_t* m = msgs + (offsets[idx] - msgs_base);
   const size_t mlen = (size_t)(offsets[idx + 1] - offsets[idx]);
-  uint32_t w[16];
-  ecg::expand_message_xmd_sha256<2>(w, m, mlen, dst_prime, dst_prime_len, 48u);
-  uint32_t d0[8], d1[8], f[8], t[8];
+  uint8_t uniform[ELL * HS::B];
+  ecg::expand_message_xmd<HS, ELL>(uniform, m, mlen, dst_prime, dst_prime_len, (uint32_t)L);
+  typename FN::FeT f192, r;
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    d0[i] = i < 6 ? w[5 - i] : 0u;
-    d1[i] = i < 6 ? w[11 - i] : 0u;
-    f[i] = i == 6 ? 1u : 0u;  // 2^192
-  }
-  N::to_mont(t, d0);
-  N::mul(t, t, f);  // Montgomery form times plain value = plain product d0 * 2^192 mod n
-  uint32_t c = ecg::add8(t, t, d1);
-  N::cond_sub_n(t, c != 0 || N::ge_n(t));
-  ecg::store_be32(out + 32 * idx, t);
+  for (int i = 0; i < FN::NL; i++) f192.v[i] = i == 6 ? 1u : 0u;  // 2^192 < n for every curve here
+  FN::from_canonical(f192, f192);
+  ecg::h2c_from_okm<FN, L>(r, uniform, f192);
+  FN::to_canonical(r, r);
+  ecg::store_fe<FN>(out + FN::FB * idx, r.v);
 }

@@ -23,8 +23,10 @@
 
 #include "../../include/ecgpu.h"
 #include "ecg_kernels.cuh"
-#if ECG_TU == 0
+#if ECG_TU == 0 || ECG_TU == 4  // hash to curve: secp256k1, P-256, P-384 (group 0) and P-521 (group 4)
 #include "ecg_h2c.cuh"
+#endif
+#if ECG_TU == 0
 #include "ecg_microbench.cuh"
 #endif
 #include "ecg_msm.cuh"
@@ -1670,7 +1672,7 @@ ECG_API(ecg_lincomb)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, 
   return ECG_OK;
 }
 
-#if ECG_TU == 0
+#if ECG_TU == 0 || ECG_TU == 4
 // ---- hash to curve / hash to scalar (ecg_h2c.cuh) ---------------------------------------------------------------
 // host-side SHA-256, only for a DST longer than 255 bytes (RFC 9380 section 5.3.3: DST = H("H2C-OVERSIZE-DST-" || DST))
 static void host_sha256(const uint8_t* data, size_t len, uint8_t out[32]) {
@@ -1706,6 +1708,55 @@ static void host_sha256(const uint8_t* data, size_t len, uint8_t out[32]) {
     for (int j = 0; j < 4; j++) out[4 * i + j] = (uint8_t)(st[i] >> (24 - 8 * j));
 }
 
+// host-side SHA-384 / SHA-512 for the same purpose in the P-384 / P-521 suites
+static void host_sha512(const uint8_t* data, size_t len, bool is384, uint8_t* out /* 48 or 64 bytes */) {
+  static const uint64_t K[80] = {
+      0x428a2f98d728ae22ull, 0x7137449123ef65cdull, 0xb5c0fbcfec4d3b2full, 0xe9b5dba58189dbbcull, 0x3956c25bf348b538ull, 0x59f111f1b605d019ull,
+      0x923f82a4af194f9bull, 0xab1c5ed5da6d8118ull, 0xd807aa98a3030242ull, 0x12835b0145706fbeull, 0x243185be4ee4b28cull, 0x550c7dc3d5ffb4e2ull,
+      0x72be5d74f27b896full, 0x80deb1fe3b1696b1ull, 0x9bdc06a725c71235ull, 0xc19bf174cf692694ull, 0xe49b69c19ef14ad2ull, 0xefbe4786384f25e3ull,
+      0x0fc19dc68b8cd5b5ull, 0x240ca1cc77ac9c65ull, 0x2de92c6f592b0275ull, 0x4a7484aa6ea6e483ull, 0x5cb0a9dcbd41fbd4ull, 0x76f988da831153b5ull,
+      0x983e5152ee66dfabull, 0xa831c66d2db43210ull, 0xb00327c898fb213full, 0xbf597fc7beef0ee4ull, 0xc6e00bf33da88fc2ull, 0xd5a79147930aa725ull,
+      0x06ca6351e003826full, 0x142929670a0e6e70ull, 0x27b70a8546d22ffcull, 0x2e1b21385c26c926ull, 0x4d2c6dfc5ac42aedull, 0x53380d139d95b3dfull,
+      0x650a73548baf63deull, 0x766a0abb3c77b2a8ull, 0x81c2c92e47edaee6ull, 0x92722c851482353bull, 0xa2bfe8a14cf10364ull, 0xa81a664bbc423001ull,
+      0xc24b8b70d0f89791ull, 0xc76c51a30654be30ull, 0xd192e819d6ef5218ull, 0xd69906245565a910ull, 0xf40e35855771202aull, 0x106aa07032bbd1b8ull,
+      0x19a4c116b8d2d0c8ull, 0x1e376c085141ab53ull, 0x2748774cdf8eeb99ull, 0x34b0bcb5e19b48a8ull, 0x391c0cb3c5c95a63ull, 0x4ed8aa4ae3418acbull,
+      0x5b9cca4f7763e373ull, 0x682e6ff3d6b2b8a3ull, 0x748f82ee5defb2fcull, 0x78a5636f43172f60ull, 0x84c87814a1f0ab72ull, 0x8cc702081a6439ecull,
+      0x90befffa23631e28ull, 0xa4506cebde82bde9ull, 0xbef9a3f7b2c67915ull, 0xc67178f2e372532bull, 0xca273eceea26619cull, 0xd186b8c721c0c207ull,
+      0xeada7dd6cde0eb1eull, 0xf57d4f7fee6ed178ull, 0x06f067aa72176fbaull, 0x0a637dc5a2c898a6ull, 0x113f9804bef90daeull, 0x1b710b35131c471bull,
+      0x28db77f523047d84ull, 0x32caab7b40c72493ull, 0x3c9ebe0a15c9bebcull, 0x431d67c49c100d4cull, 0x4cc5d4becb3e42b6ull, 0x597f299cfc657e2aull,
+      0x5fcb6fab3ad6faecull, 0x6c44198c4a475817ull};
+  uint64_t st[8];
+  const uint64_t iv512[8] = {0x6a09e667f3bcc908ull, 0xbb67ae8584caa73bull, 0x3c6ef372fe94f82bull, 0xa54ff53a5f1d36f1ull,
+                             0x510e527fade682d1ull, 0x9b05688c2b3e6c1full, 0x1f83d9abfb41bd6bull, 0x5be0cd19137e2179ull};
+  const uint64_t iv384[8] = {0xcbbb9d5dc1059ed8ull, 0x629a292a367cd507ull, 0x9159015a3070dd17ull, 0x152fecd8f70e5939ull,
+                             0x67332667ffc00b31ull, 0x8eb44a8768581511ull, 0xdb0c2e0d64f98fa7ull, 0x47b5481dbefa4fa4ull};
+  for (int i = 0; i < 8; i++) st[i] = is384 ? iv384[i] : iv512[i];
+  std::vector<uint8_t> buf(data, data + len);
+  buf.push_back(0x80);
+  while (buf.size() % 128 != 112) buf.push_back(0);
+  for (int i = 0; i < 8; i++) buf.push_back(0);  // high half of the 128-bit length
+  for (int i = 7; i >= 0; i--) buf.push_back((uint8_t)(((uint64_t)len * 8) >> (8 * i)));
+  auto rotr = [](uint64_t x, int n) { return (x >> n) | (x << (64 - n)); };
+  for (size_t off = 0; off < buf.size(); off += 128) {
+    uint64_t w[80];
+    for (int i = 0; i < 16; i++) {
+      w[i] = 0;
+      for (int j = 0; j < 8; j++) w[i] = (w[i] << 8) | buf[off + 8 * i + j];
+    }
+    for (int i = 16; i < 80; i++)
+      w[i] = w[i - 16] + (rotr(w[i - 15], 1) ^ rotr(w[i - 15], 8) ^ (w[i - 15] >> 7)) + w[i - 7] + (rotr(w[i - 2], 19) ^ rotr(w[i - 2], 61) ^ (w[i - 2] >> 6));
+    uint64_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+    for (int i = 0; i < 80; i++) {
+      uint64_t t1 = h + (rotr(e, 14) ^ rotr(e, 18) ^ rotr(e, 41)) + ((e & f) ^ (~e & g)) + K[i] + w[i];
+      uint64_t t2 = (rotr(a, 28) ^ rotr(a, 34) ^ rotr(a, 39)) + ((a & b) ^ (a & c) ^ (b & c));
+      h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+  }
+  const int nb = is384 ? 48 : 64;
+  for (int i = 0; i < nb; i++) out[i] = (uint8_t)(st[i >> 3] >> (56 - 8 * (i & 7)));
+}
+
 // mode 0: hash_to_curve (RO), 1: encode_to_curve (NU), 2: hash_to_scalar
 static ecg_status h2c_run(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* msgs, const uint64_t* offsets, const uint8_t* dst,
                           size_t dst_len, int mode, uint8_t* out, uint8_t* out_inf) {
@@ -1720,9 +1771,16 @@ static ecg_status h2c_run(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t
     const char* salt = "H2C-OVERSIZE-DST-";
     salted.insert(salted.end(), salt, salt + 17);
     salted.insert(salted.end(), dst, dst + dst_len);
-    host_sha256(salted.data(), salted.size(), dst_prime);
-    dst_prime[32] = 32;
-    dpl = 33;
+    // hashed with the suite's own hash (Domain::xmd<X>, expand_msg.rs:107-121)
+    if (curve_256(curve)) {
+      host_sha256(salted.data(), salted.size(), dst_prime);
+      dpl = 32;
+    } else {
+      host_sha512(salted.data(), salted.size(), curve == ECG_NISTP384, dst_prime);
+      dpl = curve == ECG_NISTP384 ? 48 : 64;
+    }
+    dst_prime[dpl] = (uint8_t)dpl;
+    dpl += 1;
   } else {
     memcpy(dst_prime, dst, dst_len);
     dst_prime[dst_len] = (uint8_t)dst_len;
@@ -1753,42 +1811,62 @@ static ecg_status h2c_run(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t
     return ECG_EINVAL;
   }
   const uint8_t* dprime = (const uint8_t*)L.buf[B_A];
-  const bool k1 = curve == ECG_SECP256K1;
+  const size_t fb = fbytes(curve);
   DevPtrs dp;
+// the suites: group 0 serves secp256k1 / P-256 (SHA-256) and P-384 (SHA-384), group 4 P-521 (SHA-512)
+#if ECG_TU == 0
+#define H2C_FOR_SUITE(...)                \
+  do {                                    \
+    if (curve == ECG_SECP256K1) {         \
+      typedef CurveK256 CV;               \
+      typedef FpMontT<MnK256> FN;         \
+      __VA_ARGS__;                        \
+    } else if (curve == ECG_NISTP256) {   \
+      typedef CurveP256 CV;               \
+      typedef FpMontT<MnP256> FN;         \
+      __VA_ARGS__;                        \
+    } else {                              \
+      typedef CurveP384 CV;               \
+      typedef FpMontT<MnP384> FN;         \
+      __VA_ARGS__;                        \
+    }                                     \
+  } while (0)
+#else
+#define H2C_FOR_SUITE(...)        \
+  do {                            \
+    typedef CurveP521 CV;         \
+    typedef FpMontT<MnP521> FN;   \
+    __VA_ARGS__;                  \
+  } while (0)
+#endif
   if (mode == 2) {
-    ST_TRY(stage_out(ctx, L, 0, n, out, 32, nullptr, dp));
+    ST_TRY(stage_out(ctx, L, 0, n, out, fb, nullptr, dp));
     DOM_BEGIN(ctx, L);
-    if (k1)
-      h2s_kernel<CurveK256><<<grid_for(n, 128), 128, 0, L.s()>>>(dmsgs, doffs, base, n, dprime, dpl, dp.out);
-    else
-      h2s_kernel<CurveP256><<<grid_for(n, 128), 128, 0, L.s()>>>(dmsgs, doffs, base, n, dprime, dpl, dp.out);
+    H2C_FOR_SUITE((h2s_kernel<CV, FN><<<grid_for(n, 128), 128, 0, L.s()>>>(dmsgs, doffs, base, n, dprime, dpl, dp.out)));
     LAUNCHED(ctx);
     DOM_END(ctx, L);
-    return copy_back(ctx, L, 0, n, out, 32, nullptr, dp);
+    return copy_back(ctx, L, 0, n, out, fb, nullptr, dp);
   }
-  ST_TRY(stage_out(ctx, L, 0, n, out, 64, out_inf, dp));
-  ST_TRY(ensure(ctx, L, B_JAC, n * 96));
+  ST_TRY(stage_out(ctx, L, 0, n, out, 2 * fb, out_inf, dp));
+  ST_TRY(ensure(ctx, L, B_JAC, n * jbytes(curve)));
   uint32_t* jac = (uint32_t*)L.buf[B_JAC];
   DOM_BEGIN(ctx, L);
-  if (k1 && mode == 0)
-    h2c_kernel<CurveK256, false><<<grid_for(n, 128), 128, 0, L.s()>>>(dmsgs, doffs, base, n, dprime, dpl, jac);
-  else if (k1)
-    h2c_kernel<CurveK256, true><<<grid_for(n, 128), 128, 0, L.s()>>>(dmsgs, doffs, base, n, dprime, dpl, jac);
-  else if (mode == 0)
-    h2c_kernel<CurveP256, false><<<grid_for(n, 128), 128, 0, L.s()>>>(dmsgs, doffs, base, n, dprime, dpl, jac);
+  if (mode == 0)
+    H2C_FOR_SUITE((h2c_kernel<CV, false><<<grid_for(n, 128), 128, 0, L.s()>>>(dmsgs, doffs, base, n, dprime, dpl, jac)));
   else
-    h2c_kernel<CurveP256, true><<<grid_for(n, 128), 128, 0, L.s()>>>(dmsgs, doffs, base, n, dprime, dpl, jac);
+    H2C_FOR_SUITE((h2c_kernel<CV, true><<<grid_for(n, 128), 128, 0, L.s()>>>(dmsgs, doffs, base, n, dprime, dpl, jac)));
   LAUNCHED(ctx);
   DOM_END(ctx, L);
   ST_TRY(launch_norm(ctx, d, L, curve, n, jac, dp.out, dp.oinf));
-  return copy_back(ctx, L, 0, n, out, 64, out_inf, dp);
+  return copy_back(ctx, L, 0, n, out, 2 * fb, out_inf, dp);
 }
 
 static ecg_status h2c_entry(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* msgs, const uint64_t* offsets, const uint8_t* dst,
                             size_t dst_len, int mode, uint8_t* out, uint8_t* out_inf) {
   if (!ctx) return ECG_EINVAL;
-  if (!curve_256(curve) || !dst || dst_len == 0 || dst_len > 65535) {  // ExpandMsgXmdError::EmptyDst
-    ctx->err = "hash_to_curve: secp256k1 / P-256 only, and a non-empty domain separation tag is required";
+  const bool suite_here = ECG_TU == 0 ? (curve == ECG_SECP256K1 || curve == ECG_NISTP256 || curve == ECG_NISTP384) : curve == ECG_NISTP521;
+  if (!suite_here || !dst || dst_len == 0 || dst_len > 65535) {  // ExpandMsgXmdError::EmptyDst
+    ctx->err = "hash_to_curve: secp256k1 / P-256 / P-384 / P-521 only, and a non-empty domain separation tag is required";
     return ECG_EINVAL;
   }
   if (n == 0) return ECG_OK;
@@ -1806,15 +1884,28 @@ static ecg_status h2c_entry(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8
   return st == ECG_OK ? st : fail(ctx, st);
 }
 
-extern "C" ecg_status ecg_hash_to_curve_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* msgs, const uint64_t* offsets,
-                                              const uint8_t* dst, size_t dst_len, int nonuniform, uint8_t* out_xy, uint8_t* out_inf) {
+#if ECG_TU == 0
+__attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_hash_to_curve_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* msgs,
+                                                                              const uint64_t* offsets, const uint8_t* dst, size_t dst_len,
+                                                                              int nonuniform, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_hash_to_scalar_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* msgs,
+                                                                               const uint64_t* offsets, const uint8_t* dst, size_t dst_len, uint8_t* out);
+#endif
+ECG_API(ecg_hash_to_curve_batch)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* msgs, const uint64_t* offsets,
+                                 const uint8_t* dst, size_t dst_len, int nonuniform, uint8_t* out_xy, uint8_t* out_inf) {
+#if ECG_TU == 0
+  if (ctx && curve == ECG_NISTP521) return ecg_tu4_ecg_hash_to_curve_batch(ctx, curve, n, msgs, offsets, dst, dst_len, nonuniform, out_xy, out_inf);
+#endif
   return h2c_entry(ctx, curve, n, msgs, offsets, dst, dst_len, nonuniform ? 1 : 0, out_xy, out_inf);
 }
-extern "C" ecg_status ecg_hash_to_scalar_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* msgs, const uint64_t* offsets,
-                                               const uint8_t* dst, size_t dst_len, uint8_t* out) {
+ECG_API(ecg_hash_to_scalar_batch)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* msgs, const uint64_t* offsets,
+                                  const uint8_t* dst, size_t dst_len, uint8_t* out) {
+#if ECG_TU == 0
+  if (ctx && curve == ECG_NISTP521) return ecg_tu4_ecg_hash_to_scalar_batch(ctx, curve, n, msgs, offsets, dst, dst_len, out);
+#endif
   return h2c_entry(ctx, curve, n, msgs, offsets, dst, dst_len, 2, out, nullptr);
 }
-#endif  // ECG_TU == 0
+#endif  // ECG_TU == 0 || ECG_TU == 4
 
 #if ECG_TU == 0
 extern "C" ecg_status ecg_microbench(ecg_ctx* ctx, int which, int iters, double* ops_per_s, double* elapsed_ms) {

@@ -338,11 +338,12 @@ class Engine:
         n = len(msgs)
         data, offs = self._pack_messages(msgs)
         d = np.frombuffer(bytes(dst), np.uint8).copy() if len(dst) else np.zeros(1, np.uint8)
-        out_xy = np.empty(64 * n, np.uint8)
+        fb = FBYTES[c]
+        out_xy = np.empty(2 * fb * n, np.uint8)
         out_inf = np.empty(n, np.uint8)
         self._check(self.lib.ecg_hash_to_curve_batch(self._ctx, c, n, _ptr(data), _ptr(offs), _ptr(d), len(dst), 1 if nonuniform else 0,
                                                      _ptr(out_xy), _ptr(out_inf)))
-        return out_xy.reshape(n, 64), out_inf
+        return out_xy.reshape(n, 2 * fb), out_inf
 
     def encode_to_curve(self, curve, msgs, dst: bytes):
         return self.hash_to_curve(curve, msgs, dst, nonuniform=True)
@@ -353,9 +354,10 @@ class Engine:
         n = len(msgs)
         data, offs = self._pack_messages(msgs)
         d = np.frombuffer(bytes(dst), np.uint8).copy() if len(dst) else np.zeros(1, np.uint8)
-        out = np.empty(32 * n, np.uint8)
+        fb = FBYTES[c]
+        out = np.empty(fb * n, np.uint8)
         self._check(self.lib.ecg_hash_to_scalar_batch(self._ctx, c, n, _ptr(data), _ptr(offs), _ptr(d), len(dst), _ptr(out)))
-        return out.reshape(n, 32)
+        return out.reshape(n, fb)
 
     def schnorr_verify_batch(self, pk_x, msg32, sig64):
         """BIP340: VerifyingKey::verify_raw over a batch (k256/src/schnorr/verifying.rs:76-99) -> uint8 flags"""

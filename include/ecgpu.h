@@ -203,19 +203,21 @@ ecg_status ecg_mul_batch_x(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_
 ecg_status ecg_field_sqrt_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, uint8_t* out,
                                 uint8_t* is_square);
 
-/* ---- hash to curve ("hash-to-curve front end"), RFC 9380 with expand_message_xmd over
- * SHA-256: the suites secp256k1_XMD:SHA-256_SSWU_{RO,NU}_ (k256/src/arithmetic/hash2curve.rs:14-20) and
- * P256_XMD:SHA-256_SSWU_{RO,NU}_ (p256/src/arithmetic/hash2curve.rs:13-19); other curves: ECG_EINVAL.
+/* ---- hash to curve ("hash-to-curve front end"), RFC 9380 with expand_message_xmd: the
+ * four Weierstrass suites the reference implements — secp256k1_XMD:SHA-256_SSWU_{RO,NU}_ (k256/src/arithmetic/
+ * hash2curve.rs:14-20), P256_XMD:SHA-256_SSWU_{RO,NU}_ (p256/.../hash2curve.rs:13-19), P384_XMD:SHA-384_SSWU_{RO,NU}_
+ * (p384/.../hash2curve.rs:13-19), P521_XMD:SHA-512_SSWU_{RO,NU}_ (p521/.../hash2curve.rs:13-19); other curves: ECG_EINVAL.
+ * Outputs are the curve's records (2 FB bytes per point, FB per scalar).
  * Message i is msgs[offsets[i] .. offsets[i+1]) (offsets: n + 1 non-decreasing uint64 values; with ECG_FLAG_DEVICE_PTRS
  * msgs, offsets and the outputs are device pointers, offsets 8-byte aligned).  dst / dst_len: the domain separation tag,
  * always a host pointer; empty -> ECG_EINVAL (ExpandMsgXmdError::EmptyDst, hash2curve/src/hash2field/expand_msg.rs:101-106),
- * longer than 255 bytes -> replaced by SHA-256("H2C-OVERSIZE-DST-" || dst) as in the reference (expand_msg.rs:107-121).
+ * longer than 255 bytes -> replaced by H("H2C-OVERSIZE-DST-" || dst), H the suite's hash, as in the reference (expand_msg.rs:107-121).
  * nonuniform = 0: out[i] = hash_to_curve(msg_i) (GroupDigest::hash_from_bytes, hash2curve/src/group_digest.rs:88-97:
  * two field elements, two maps, one addition); nonuniform != 0: encode_to_curve (encode_from_bytes, :110-118). */
 ecg_status ecg_hash_to_curve_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* msgs, const uint64_t* offsets,
                                    const uint8_t* dst, size_t dst_len, int nonuniform, uint8_t* out_xy, uint8_t* out_inf);
 
-/* out[i] = hash_to_scalar(msg_i) as 32 big-endian bytes: hash_to_field with the group order as modulus and L = 48
+/* out[i] = hash_to_scalar(msg_i) as one FB-byte big-endian record: hash_to_field with the group order as modulus and the suite's L (48 / 72 / 98)
  * (hash2curve/src/group_digest.rs:131-143 with Reduce<Array<u8, U48>> for Scalar, k256/src/arithmetic/hash2curve.rs:151-166,
  * p256/src/arithmetic/hash2curve.rs:77-94) — the VOPRF DeriveKeyPair / HashToScalar primitive. */
 ecg_status ecg_hash_to_scalar_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* msgs, const uint64_t* offsets,

@@ -163,12 +163,12 @@ def h2c_vectors():
     """RFC 9380 vectors the reference tests hold (k256/src/arithmetic/hash2curve.rs:289-370, p256/src/arithmetic/
     hash2curve.rs:133-256) and the VOPRF hash_to_scalar vectors (p256/src/arithmetic/hash2curve.rs:257-310)."""
     out = {"source": "k256/src/arithmetic/hash2curve.rs, p256/src/arithmetic/hash2curve.rs (#[cfg(test)] vectors)", "suites": {}}
-    for curve in ("k256", "p256"):
+    for curve in ("k256", "p256", "p384", "p521"):
         txt = open(f"{REF}/{curve}/src/arithmetic/hash2curve.rs").read()
         dst = re.search(r'const DST: &\[u8\] = b"(QUUX[^"]+)"', txt).group(1)
         vecs = []
         for m in re.finditer(r'TestVector \{\s*msg: b"([^"]*)",(.*?)\},', txt, re.S):
-            fields = dict(re.findall(r'(\w+): hex!\("([0-9a-f]+)"\)', m.group(2)))
+            fields = dict(re.findall(r'(\w+): hex!\(\s*"([0-9a-f]+)"\s*\)', m.group(2)))
             if "p_x" in fields:
                 vecs.append({"msg": m.group(1), **fields})
         out["suites"][curve] = {"dst": dst, "vectors": vecs}

@@ -361,6 +361,9 @@ H2C_SUITES = {
     "k256": {"ro": b"secp256k1_XMD:SHA-256_SSWU_RO_", "nu": b"secp256k1_XMD:SHA-256_SSWU_NU_", "Z": -11,
              "A": 0x3F8731ABDD661ADCA08A5558F0F5D272E953D363CB6F0E5D405447C01A444533, "B": 1771},
     "p256": {"ro": b"P256_XMD:SHA-256_SSWU_RO_", "nu": b"P256_XMD:SHA-256_SSWU_NU_", "Z": -10, "A": -3, "B": P256.b},
+    # p384/src/arithmetic/hash2curve.rs:13-75 (SHA-384, L = 72, Z = -12), p521/src/arithmetic/hash2curve.rs:13-76 (SHA-512, L = 98, Z = -4)
+    "p384": {"ro": b"P384_XMD:SHA-384_SSWU_RO_", "nu": b"P384_XMD:SHA-384_SSWU_NU_", "Z": -12, "A": -3, "B": P384.b, "hash": "sha384", "L": 72},
+    "p521": {"ro": b"P521_XMD:SHA-512_SSWU_RO_", "nu": b"P521_XMD:SHA-512_SSWU_NU_", "Z": -4, "A": -3, "hash": "sha512", "L": 98},
 }
 # 3-isogeny E' -> secp256k1 (RFC 9380 appendix E.1; k256/src/arithmetic/hash2curve.rs:170-239), coefficients of x^0..x^3
 K256_ISO = {
@@ -374,23 +377,25 @@ K256_ISO = {
 }
 
 
-def expand_message_xmd(msg: bytes, dst: bytes, len_in_bytes: int) -> bytes:
-    """RFC 9380 section 5.3.1 with SHA-256 (hash2curve/src/hash2field/expand_msg/xmd.rs:43-99); oversize DSTs are hashed
-    first (expand_msg.rs:15,76-95)."""
+def expand_message_xmd(msg: bytes, dst: bytes, len_in_bytes: int, hash_name: str = "sha256") -> bytes:
+    """RFC 9380 section 5.3.1 (hash2curve/src/hash2field/expand_msg/xmd.rs:43-99) with SHA-256 / SHA-384 / SHA-512;
+    oversize DSTs are hashed first (expand_msg.rs:15,76-95)."""
+    H = lambda d: hashlib.new(hash_name, d).digest()  # noqa: E731
+    b_in, s_in = hashlib.new(hash_name).digest_size, hashlib.new(hash_name).block_size
     if len(dst) > 255:
-        dst = hashlib.sha256(b"H2C-OVERSIZE-DST-" + dst).digest()
-    ell = (len_in_bytes + 31) // 32
+        dst = H(b"H2C-OVERSIZE-DST-" + dst)
+    ell = (len_in_bytes + b_in - 1) // b_in
     assert 0 < len_in_bytes <= 65535 and ell <= 255
     dst_prime = dst + bytes([len(dst)])
-    b0 = hashlib.sha256(bytes(64) + msg + len_in_bytes.to_bytes(2, "big") + b"\x00" + dst_prime).digest()
-    b = [hashlib.sha256(b0 + b"\x01" + dst_prime).digest()]
+    b0 = H(bytes(s_in) + msg + len_in_bytes.to_bytes(2, "big") + b"\x00" + dst_prime)
+    b = [H(b0 + b"\x01" + dst_prime)]
     for i in range(2, ell + 1):
-        b.append(hashlib.sha256(bytes(x ^ y for x, y in zip(b0, b[-1])) + bytes([i]) + dst_prime).digest())
+        b.append(H(bytes(x ^ y for x, y in zip(b0, b[-1])) + bytes([i]) + dst_prime))
     return b"".join(b)[:len_in_bytes]
 
 
-def hash_to_field(msg: bytes, dst: bytes, count: int, modulus: int, L: int = 48):
-    u = expand_message_xmd(msg, dst, count * L)
+def hash_to_field(msg: bytes, dst: bytes, count: int, modulus: int, L: int = 48, hash_name: str = "sha256"):
+    u = expand_message_xmd(msg, dst, count * L, hash_name)
     return [int.from_bytes(u[L * i:L * (i + 1)], "big") % modulus for i in range(count)]
 
 
@@ -432,22 +437,27 @@ def k256_iso_map(x: int, y: int):
 def map_to_curve(curve: str, u: int):
     c = CURVES[curve]
     s = H2C_SUITES[curve]
-    x, y = sswu(u, c.p, s["A"], s["B"], s["Z"])
+    x, y = sswu(u, c.p, s["A"], s.get("B", c.b), s["Z"])
     return k256_iso_map(x, y) if curve == "k256" else (x, y)
 
 
+def _h2c_field(curve: str, msg: bytes, dst: bytes, count: int, modulus: int):
+    s = H2C_SUITES[curve]
+    return hash_to_field(msg, dst, count, modulus, s.get("L", 48), s.get("hash", "sha256"))
+
+
 def hash_to_curve(curve: str, msg: bytes, dst: bytes):
-    """hash_from_bytes: two field elements, two maps, one addition (both curves have cofactor 1)"""
+    """hash_from_bytes: two field elements, two maps, one addition (all four curves have cofactor 1)"""
     c = CURVES[curve]
-    u0, u1 = hash_to_field(msg, dst, 2, c.p)
+    u0, u1 = _h2c_field(curve, msg, dst, 2, c.p)
     return add(c, map_to_curve(curve, u0), map_to_curve(curve, u1))
 
 
 def encode_to_curve(curve: str, msg: bytes, dst: bytes):
     c = CURVES[curve]
-    (u,) = hash_to_field(msg, dst, 1, c.p)
+    (u,) = _h2c_field(curve, msg, dst, 1, c.p)
     return map_to_curve(curve, u)
 
 
 def hash_to_scalar(curve: str, msg: bytes, dst: bytes) -> int:
-    return hash_to_field(msg, dst, 1, CURVES[curve].n)[0]
+    return _h2c_field(curve, msg, dst, 1, CURVES[curve].n)[0]

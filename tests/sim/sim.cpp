@@ -811,29 +811,31 @@ extern "C" int simk_lincomb(int curve, size_t n, const uint8_t* k, const uint8_t
 
 // ecg_hash_to_curve_batch / ecg_hash_to_scalar_batch: h2c_kernel (expand_message_xmd, SSWU, isogeny, addition) +
 // normalize_kernel, h2s_kernel.  dst_prime = DST || len(DST) as the host side of ecgpu.cu prepares it.
+// curve: 0 secp256k1, 1 P-256, 2 P-384, 11 P-521
+#define SIM_H2C_SUITE(curve, ...)                                                                  \
+  switch (curve) {                                                                                 \
+    case 0: { typedef CurveK256 CV; typedef FpMontT<MnK256> FN; __VA_ARGS__; } break;              \
+    case 1: { typedef CurveP256 CV; typedef FpMontT<MnP256> FN; __VA_ARGS__; } break;              \
+    case 2: { typedef CurveP384 CV; typedef FpMontT<MnP384> FN; __VA_ARGS__; } break;              \
+    case 11: { typedef CurveP521 CV; typedef FpMontT<MnP521> FN; __VA_ARGS__; } break;             \
+    default: return -1;                                                                            \
+  }
 extern "C" int simk_hash_to_curve(int curve, size_t n, const uint8_t* msgs, const uint64_t* offsets, const uint8_t* dst_prime,
                                   uint32_t dpl, int nu, uint8_t* out_xy, uint8_t* out_inf) {
-  std::vector<uint32_t> jac(24 * n + 24);
-  if (curve == 0 && !nu)
-    sim_launch(n, 128, [&] { h2c_kernel<CurveK256, false>(msgs, offsets, 0, n, dst_prime, dpl, jac.data()); });
-  else if (curve == 0)
-    sim_launch(n, 128, [&] { h2c_kernel<CurveK256, true>(msgs, offsets, 0, n, dst_prime, dpl, jac.data()); });
-  else if (!nu)
-    sim_launch(n, 128, [&] { h2c_kernel<CurveP256, false>(msgs, offsets, 0, n, dst_prime, dpl, jac.data()); });
-  else
-    sim_launch(n, 128, [&] { h2c_kernel<CurveP256, true>(msgs, offsets, 0, n, dst_prime, dpl, jac.data()); });
-  if (curve == 0)
-    simk_normalize<CurveK256>(jac, n, out_xy, out_inf);
-  else
-    simk_normalize<CurveP256>(jac, n, out_xy, out_inf);
+  SIM_H2C_SUITE(curve, {
+    (void)sizeof(FN);
+    std::vector<uint32_t> jac(3 * CV::F::NL * n + 64);
+    if (!nu)
+      sim_launch(n, 128, [&] { h2c_kernel<CV, false>(msgs, offsets, 0, n, dst_prime, dpl, jac.data()); });
+    else
+      sim_launch(n, 128, [&] { h2c_kernel<CV, true>(msgs, offsets, 0, n, dst_prime, dpl, jac.data()); });
+    simk_normalize<CV>(jac, n, out_xy, out_inf);
+  });
   return 0;
 }
 extern "C" int simk_hash_to_scalar(int curve, size_t n, const uint8_t* msgs, const uint64_t* offsets, const uint8_t* dst_prime,
                                    uint32_t dpl, uint8_t* out) {
-  if (curve == 0)
-    sim_launch(n, 128, [&] { h2s_kernel<CurveK256>(msgs, offsets, 0, n, dst_prime, dpl, out); });
-  else
-    sim_launch(n, 128, [&] { h2s_kernel<CurveP256>(msgs, offsets, 0, n, dst_prime, dpl, out); });
+  SIM_H2C_SUITE(curve, { sim_launch(n, 128, [&] { h2s_kernel<CV, FN>(msgs, offsets, 0, n, dst_prime, dpl, out); }); });
   return 0;
 }
 
