@@ -480,6 +480,158 @@ ECG_KERNEL(256)
   valid[idx] = (ok[idx] && !rinf[idx] && same) ? 1 : 0;
 }
 
+// ---- the same two entries for every other curve with ECDSA in the reference (p192, p224, p384, p521, brainpoolP256r1/t1,
+// brainpoolP384r1/t1: */src/ecdsa.rs) — generic twins over the field policy's limb count, arithmetic mod n through
+// ScalarField<C>::T (the Montgomery policy of ecg_fe_mont.cuh instantiated over the group order) ----------------------
+
+// a*G + b*P (MulBackend::mul_by_generator_and_mul_add_vartime, primeorder/src/mul_backend.rs:31-40): the variable-base
+// thread routine, then the fixed-base accumulation on the same accumulator
+template <class C, int BLOCK, int MINBLK>
+ECG_KERNEL(BLOCK, MINBLK)
+    mul_gen_add_generic_kernel(const uint8_t* __restrict__ ab, const uint8_t* __restrict__ kb, const uint8_t* __restrict__ pxy,
+                               const uint8_t* __restrict__ pinf, size_t n, const uint32_t* __restrict__ table, uint32_t* __restrict__ jac,
+                               uint32_t* __restrict__ gtab, uint32_t* __restrict__ status, size_t base) {
+  typedef typename C::F F;
+  constexpr int NL = F::NL;
+  size_t idx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= n) return;
+  uint32_t k[NL], a[NL];
+  typename F::AffT P;
+  bool inf;
+  uint32_t err = load_pair<C>(k, P, inf, kb, pxy, pinf, idx);
+  load_fe<F>(a, ab + F::FB * idx);
+  if (!ltN<NL>(a, C::N())) err |= ERRF_SCALAR;
+  if (err) report_error(status, err, base + idx);
+  TabRefJN<NL> tab{gtab + (size_t)blockIdx.x * BLOCK * (8 * 3 * NL) + threadIdx.x, (uint32_t)BLOCK};
+  typename F::JacT r;
+  generic_mul_thread<F, C::A_IS_MINUS3>(r, k, P, tab);
+  if (inf) F::set_zero(r.Z);  // b * O = O, the sum is a*G
+  if (err) {
+#pragma unroll
+    for (int i = 0; i < NL; i++) a[i] = (i == 0);
+  }
+  fixedbase_accumulate<C, false>(r, a, table);
+  if (err) F::set_zero(r.Z);
+  soa_store<NL>(jac, n, idx, r.X.v, 0);
+  soa_store<NL>(jac, n, idx, r.Y.v, NL);
+  soa_store<NL>(jac, n, idx, r.Z.v, 2 * NL);
+}
+
+// ECDSA front end: z (FB-byte prehash, already through bits2field), signature r || s (2 FB), public key x || y (2 FB).
+// One inversion mod n per thread slice (Montgomery's trick over the s_i); scr: NL * n words.
+template <class C>
+ECG_KERNEL(128)
+    ecdsa_prep_generic_kernel(const uint8_t* __restrict__ zb, const uint8_t* __restrict__ sig, const uint8_t* __restrict__ qxy, size_t n,
+                              int low_s_only, uint32_t* __restrict__ scr, uint8_t* __restrict__ pxy, uint8_t* __restrict__ a_out,
+                              uint8_t* __restrict__ b_out, uint8_t* __restrict__ ok_out) {
+  typedef typename C::F F;
+  typedef typename ScalarField<C>::T FN;
+  typedef typename FN::FeT Sc;
+  constexpr int NL = F::NL, FB = F::FB;
+  size_t T = (size_t)gridDim.x * blockDim.x;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  Sc acc, sm;
+  FN::set_one(acc);
+  size_t last = t;
+  // forward: validate, prefix products of the (Montgomery-form) s_i
+  for (size_t idx = t; idx < n; idx += T) {
+    Sc r, sv;
+    load_fe<F>(r.v, sig + 2 * FB * idx);
+    load_fe<F>(sv.v, sig + 2 * FB * idx + FB);
+    bool ok = ltN<NL>(r.v, C::N()) && !FN::is_zero(r) && ltN<NL>(sv.v, C::N()) && !FN::is_zero(sv);
+    if (ok && low_s_only) {  // EcdsaCurve::NORMALIZE_S: reject s > n/2 (false for all these curves in the reference)
+      uint32_t twice[NL];
+      uint32_t c = addN<NL>(twice, sv.v, sv.v);
+      ok = !c && ltN<NL>(twice, C::N());
+    }
+    typename F::AffT Q;
+    typename F::FeT qx, qy;
+    load_fe<F>(qx.v, qxy + 2 * FB * idx);
+    load_fe<F>(qy.v, qxy + 2 * FB * idx + FB);
+    bool qok = ltN<NL>(qx.v, C::P()) && ltN<NL>(qy.v, C::P());
+    F::from_canonical(Q.x, qx);
+    F::from_canonical(Q.y, qy);
+    if (qok) {
+      typename F::FeT b;
+      C::b_internal(b);
+      qok = aff_on_curve<F, C::A_IS_MINUS3>(Q, b);
+    }
+    ok = ok && qok;
+    ok_out[idx] = ok ? 1 : 0;
+    if (!ok) {
+#pragma unroll
+      for (int i = 0; i < NL; i++) sv.v[i] = (i == 0);
+    }
+    FN::from_canonical(sm, sv);
+    soa_store<NL>(scr, n, idx, acc.v, 0);
+    FN::mul(acc, acc, sm);
+    last = idx;
+  }
+  Sc inv;
+  FN::inv(inv, acc);
+  for (size_t idx = last;; idx -= T) {
+    Sc r, sv, z, pre, w, u1, u2;
+    bool ok = ok_out[idx] != 0;
+    load_fe<F>(r.v, sig + 2 * FB * idx);
+    load_fe<F>(sv.v, sig + 2 * FB * idx + FB);
+    load_fe<F>(z.v, zb + FB * idx);
+    if (!ok) {
+#pragma unroll
+      for (int i = 0; i < NL; i++) {
+        sv.v[i] = (i == 0);
+        r.v[i] = (i == 0);
+      }
+    }
+    FN::from_canonical(sm, sv);
+    soa_load<NL>(pre.v, scr, n, idx, 0);
+    FN::mul(w, inv, pre);   // w = s^-1 (Montgomery form)
+    FN::mul(inv, inv, sm);
+    FN::from_canonical(z, z);  // z * R mod n for ANY z below 2^(32 NL): the reduction of the prehash (Reduce<FieldBytes> for Scalar)
+    FN::from_canonical(r, r);
+    FN::mul(u1, z, w);
+    FN::mul(u2, r, w);
+    FN::to_canonical(u1, u1);
+    FN::to_canonical(u2, u2);
+    if (!ok) {
+#pragma unroll
+      for (int i = 0; i < NL; i++) {
+        u1.v[i] = (i == 0);
+        u2.v[i] = (i == 0);
+      }
+      typename F::AffT G;
+      C::generator(G);
+      typename F::FeT gx, gy;
+      F::to_canonical(gx, G.x);
+      F::to_canonical(gy, G.y);
+      store_fe<F>(pxy + 2 * FB * idx, gx.v);
+      store_fe<F>(pxy + 2 * FB * idx + FB, gy.v);
+    } else {
+      for (int i = 0; i < 2 * FB; i++) pxy[2 * FB * idx + i] = qxy[2 * FB * idx + i];
+    }
+    store_fe<F>(a_out + FB * idx, u1.v);
+    store_fe<F>(b_out + FB * idx, u2.v);
+    if (idx < T) break;
+  }
+}
+template <class C>
+ECG_KERNEL(256)
+    ecdsa_check_generic_kernel(const uint8_t* __restrict__ sig, const uint8_t* __restrict__ rxy, const uint8_t* __restrict__ rinf,
+                               const uint8_t* __restrict__ ok, size_t n, uint8_t* __restrict__ valid) {
+  typedef typename C::F F;
+  constexpr int NL = F::NL, FB = F::FB;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  uint32_t r[NL], x[NL], t[NL];
+  load_fe<F>(r, sig + 2 * FB * idx);
+  load_fe<F>(x, rxy + 2 * FB * idx);
+  uint32_t bw = subN<NL>(t, x, C::N());  // x(R) mod n: x < p < 2n (Hasse), one conditional subtraction
+  bool same = true;
+#pragma unroll
+  for (int i = 0; i < NL; i++) same = same && (r[i] == (bw ? x[i] : t[i]));
+  valid[idx] = (ok[idx] && !rinf[idx] && same) ? 1 : 0;
+}
+
 // SEC1 compressed points (33 bytes: 02/03 || x; 33 zero bytes = identity) -> affine x || y, identity flag, validity.
 template <class C>
 ECG_KERNEL(128)

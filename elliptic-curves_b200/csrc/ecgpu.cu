@@ -739,13 +739,29 @@ struct BatchOp {
   int fop = 0;  // field op, the ECDSA low-S flag, or NORMALIZE's "homogeneous input" flag
   bool x_only = false;  // MUL: write x coordinates only (ostride 32)
   const uint8_t *k = nullptr, *a = nullptr, *p = nullptr, *inf = nullptr;  // host or device, per ctx flags
-  const uint8_t* x = nullptr;  // extra 64-byte-stride input (ECDSA public keys)
+  const uint8_t* x = nullptr;  // extra 2 FB-byte-stride input (ECDSA public keys)
+  size_t xstride = 64;
   size_t kstride = 32;  // scalars / field elements / messages: fbytes(curve) for the hot-path entries
   size_t pstride = 64;
   uint8_t *out = nullptr, *oinf = nullptr;
   uint8_t* aux_out = nullptr;  // third output array (decompress: validity flags)
   size_t ostride = 64;
 };
+
+// the generic twins of the a*G + b*P / ECDSA kernels serve every curve except secp256k1 and P-256: in group 0 that is P-384
+#if ECG_TU == 0
+#define ECDSA_FOR_CURVE(...)  \
+  do {                        \
+    typedef CurveP384 CV;     \
+    __VA_ARGS__;              \
+  } while (0)
+static const int GB = Q_BLOCK;
+#define ECDSA_MINBLK Q_MINBLK
+#else
+#define ECDSA_FOR_CURVE(...) FOR_CURVE(op.curve, __VA_ARGS__)
+static const int GB = X_BLOCK;
+#define ECDSA_MINBLK XGeom<CV::F::NL>::MINBLK
+#endif
 
 static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& op, size_t off, size_t cnt) {
   DevPtrs dp;
@@ -755,8 +771,38 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
   ST_TRY(stage_in(ctx, L, B_P, op.p, off, cnt, op.pstride, &dp.p));
   ST_TRY(stage_in(ctx, L, B_INF, op.inf, off, cnt, 1, &dp.inf));
   const uint8_t* dx = nullptr;
-  ST_TRY(stage_in(ctx, L, B_X, op.x, off, cnt, 64, &dx));
+  ST_TRY(stage_in(ctx, L, B_X, op.x, off, cnt, op.xstride, &dx));
   ST_TRY(stage_out(ctx, L, off, cnt, op.out, op.ostride, op.oinf, dp));
+  if (op.kind == BatchOp::ECDSA && !curve_256(op.curve)) {
+    // ECDSA for the other curves: generic front end -> (u1, u2, Q) -> u1*G + u2*Q -> affine -> verdict (the 256-bit path
+    // below, record sizes by the curve)
+    const size_t fb = fbytes(op.curve), nl = flimbs(op.curve);
+    ST_TRY(ensure(ctx, L, B_V1, cnt * 2 * fb));
+    ST_TRY(ensure(ctx, L, B_V2, cnt * fb));
+    ST_TRY(ensure(ctx, L, B_V3, cnt * fb));
+    ST_TRY(ensure(ctx, L, B_V4, cnt));
+    ST_TRY(ensure(ctx, L, B_V5, cnt * 2 * fb));
+    ST_TRY(ensure(ctx, L, B_V6, cnt));
+    ST_TRY(ensure(ctx, L, B_JAC, cnt * jbytes(op.curve)));
+    ST_TRY(ensure(ctx, L, B_SCR, cnt * 4 * nl));
+    ST_TRY(ensure_tab(ctx, L, op.curve, cnt));
+    uint8_t *vp = (uint8_t*)L.buf[B_V1], *va = (uint8_t*)L.buf[B_V2], *vb = (uint8_t*)L.buf[B_V3], *vok = (uint8_t*)L.buf[B_V4];
+    uint8_t *vxy = (uint8_t*)L.buf[B_V5], *vinf = (uint8_t*)L.buf[B_V6];
+    uint32_t* vj = (uint32_t*)L.buf[B_JAC];
+    size_t want_threads = std::max<size_t>((cnt + 31) / 32, std::min<size_t>(cnt, (size_t)d.sm_count * 128));
+    ECDSA_FOR_CURVE((ecdsa_prep_generic_kernel<CV><<<grid_for(want_threads, 128), 128, 0, L.s()>>>(dp.k, dp.p, dx, cnt, op.fop, (uint32_t*)L.buf[B_SCR], vp, va,
+                                                                                              vb, vok)));
+    LAUNCHED(ctx);
+    DOM_BEGIN(ctx, L);
+    ECDSA_FOR_CURVE((mul_gen_add_generic_kernel<CV, GB, ECDSA_MINBLK><<<grid_for(cnt, GB), GB, 0, L.s()>>>(va, vb, vp, nullptr, cnt, d.fb_table[op.curve], vj,
+                                                                                                     (uint32_t*)L.buf[B_TAB], L.status, off)));
+    LAUNCHED(ctx);
+    DOM_END(ctx, L);
+    ST_TRY(launch_norm(ctx, d, L, op.curve, cnt, vj, vxy, vinf));
+    ECDSA_FOR_CURVE((ecdsa_check_generic_kernel<CV><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, vxy, vinf, vok, cnt, dp.out)));
+    LAUNCHED(ctx);
+    return copy_back(ctx, L, off, cnt, op.out, op.ostride, nullptr, dp);
+  }
 #if ECG_TU == 0
   if (op.kind == BatchOp::DECOMPRESS) {
     // out = xy (64 B), oinf = identity flags, valid flags go to a third host array staged through B_V4
@@ -851,6 +897,15 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
       DOM_END(ctx, L);
       break;
     case BatchOp::MULGENADD:
+      if (!curve_256(op.curve)) {  // generic twin (record sizes by the curve)
+        ST_TRY(ensure_tab(ctx, L, op.curve, cnt));
+        DOM_BEGIN(ctx, L);
+        ECDSA_FOR_CURVE((mul_gen_add_generic_kernel<CV, GB, ECDSA_MINBLK><<<grid_for(cnt, GB), GB, 0, L.s()>>>(dp.a, dp.k, dp.p, dp.inf, cnt, d.fb_table[op.curve], jac,
+                                                                                                         (uint32_t*)L.buf[B_TAB], L.status, off)));
+        LAUNCHED(ctx);
+        DOM_END(ctx, L);
+        break;
+      }
 #if ECG_TU == 0
       ST_TRY(ensure_tab(ctx, L, op.curve, cnt));
       DOM_BEGIN(ctx, L);
@@ -994,6 +1049,14 @@ __attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_field_op_batch(ecg_
 __attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_lincomb_partial(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xyz);
 __attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_point_sum(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* xyz, uint8_t* out_xy, uint8_t* out_inf);
 __attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_lincomb(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu1_ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, const uint8_t* b, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu1_ecg_ecdsa_verify_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* z32, const uint8_t* sig64, const uint8_t* Q_xy, int low_s_only, uint8_t* valid);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu2_ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, const uint8_t* b, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu2_ecg_ecdsa_verify_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* z32, const uint8_t* sig64, const uint8_t* Q_xy, int low_s_only, uint8_t* valid);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, const uint8_t* b, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_ecdsa_verify_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* z32, const uint8_t* sig64, const uint8_t* Q_xy, int low_s_only, uint8_t* valid);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, const uint8_t* b, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_ecdsa_verify_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* z32, const uint8_t* sig64, const uint8_t* Q_xy, int low_s_only, uint8_t* valid);
 #define ECG_FORWARD(name, ...)                                     \
   do {                                                             \
     if ((int)curve >= 0 && (int)curve < ECG_CURVE_COUNT) {         \
@@ -1052,18 +1115,20 @@ ECG_API(ecg_mul_gen_batch)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_
   return run_batch(ctx, op, n);
 }
 
-#if ECG_TU == 0
-extern "C" ecg_status ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, const uint8_t* b,
-                                            const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf) {
+ECG_API(ecg_mul_gen_add_batch)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, const uint8_t* b,
+                               const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf) {
   if (!ctx) return ECG_EINVAL;
+  ECG_FORWARD(ecg_mul_gen_add_batch, ctx, curve, n, a, b, P_xy, P_inf, out_xy, out_inf);
   if (n == 0) return ECG_OK;
-  if (!a || !b || !P_xy || !out_xy || !curve_256(curve)) {
+  if (!a || !b || !P_xy || !out_xy || !curve_ok(curve)) {
     ctx->err = "ecg_mul_gen_add_batch: null pointer or unknown curve";
     return ECG_EINVAL;
   }
   BatchOp op;
   op.kind = BatchOp::MULGENADD;
   op.curve = curve;
+  op.kstride = fbytes(curve);
+  op.pstride = op.ostride = 2 * fbytes(curve);
   op.a = a;
   op.k = b;
   op.p = P_xy;
@@ -1073,6 +1138,7 @@ extern "C" ecg_status ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve curve, size_
   return run_batch(ctx, op, n);
 }
 
+#if ECG_TU == 0
 extern "C" ecg_status ecg_decompress_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* sec1_33, uint8_t* out_xy,
                                             uint8_t* out_inf, uint8_t* valid) {
   if (!ctx) return ECG_EINVAL;
@@ -1111,18 +1177,23 @@ extern "C" ecg_status ecg_schnorr_verify_batch(ecg_ctx* ctx, size_t n, const uin
   return run_batch(ctx, op, n);
 }
 
-extern "C" ecg_status ecg_ecdsa_verify_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* z32, const uint8_t* sig64,
-                                              const uint8_t* Q_xy, int low_s_only, uint8_t* valid) {
+#endif  // ECG_TU == 0
+ECG_API(ecg_ecdsa_verify_batch)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* z32, const uint8_t* sig64,
+                                const uint8_t* Q_xy, int low_s_only, uint8_t* valid) {
   if (!ctx) return ECG_EINVAL;
+  ECG_FORWARD(ecg_ecdsa_verify_batch, ctx, curve, n, z32, sig64, Q_xy, low_s_only, valid);
   if (n == 0) return ECG_OK;
-  if (!z32 || !sig64 || !Q_xy || !valid || !curve_256(curve)) {
-    ctx->err = "ecg_ecdsa_verify_batch: null pointer or unknown curve";
+  // ECDSA is defined by the reference for every curve here except sm2 (SM2DSA) and bign-curve256v1 (its own scheme)
+  if (!z32 || !sig64 || !Q_xy || !valid || !curve_ok(curve) || curve == ECG_SM2 || curve == ECG_BIGNP256) {
+    ctx->err = "ecg_ecdsa_verify_batch: null pointer or a curve without ECDSA";
     return ECG_EINVAL;
   }
   BatchOp op;
   op.kind = BatchOp::ECDSA;
   op.curve = curve;
   op.fop = low_s_only ? 1 : 0;
+  op.kstride = fbytes(curve);
+  op.pstride = op.xstride = 2 * fbytes(curve);
   op.k = z32;
   op.p = sig64;
   op.x = Q_xy;
@@ -1130,6 +1201,8 @@ extern "C" ecg_status ecg_ecdsa_verify_batch(ecg_ctx* ctx, ecg_curve curve, size
   op.ostride = 1;
   return run_batch(ctx, op, n);
 }
+#if ECG_TU == 0
+
 
 #endif  // ECG_TU == 0
 

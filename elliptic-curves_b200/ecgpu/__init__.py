@@ -311,16 +311,17 @@ class Engine:
 
     def mul_by_generator_and_mul_add(self, curve, a, b, P_xy, P_inf=None):
         c = CURVE_IDS[curve]
-        n = np.asarray(a).size // 32
-        a = _u8(a, 32 * n, "a")
-        b = _u8(b, 32 * n, "b")
-        P_xy = _u8(P_xy, 64 * n, "P_xy")
+        fb = FBYTES[c]
+        n = np.asarray(a).size // fb
+        a = _u8(a, fb * n, "a")
+        b = _u8(b, fb * n, "b")
+        P_xy = _u8(P_xy, 2 * fb * n, "P_xy")
         if P_inf is not None:
             P_inf = _u8(P_inf, n, "P_inf")
-        out_xy = np.empty(64 * n, np.uint8)
+        out_xy = np.empty(2 * fb * n, np.uint8)
         out_inf = np.empty(n, np.uint8)
         self._check(self.lib.ecg_mul_gen_add_batch(self._ctx, c, n, _ptr(a), _ptr(b), _ptr(P_xy), _ptr(P_inf), _ptr(out_xy), _ptr(out_inf)))
-        return out_xy.reshape(n, 64), out_inf
+        return out_xy.reshape(n, 2 * fb), out_inf
 
     @staticmethod
     def _pack_messages(msgs):
@@ -370,12 +371,14 @@ class Engine:
         return valid
 
     def ecdsa_verify_batch(self, curve, z32, sig64, Q_xy, low_s_only=False):
-        """ECDSA verify_prehash over a batch -> uint8 flags"""
+        """ECDSA verify_prehash over a batch -> uint8 flags.  Records are FB bytes (the curve's FieldBytes): z = the prehash
+        after bits2field, signature r || s, public key x || y."""
         c = CURVE_IDS[curve]
-        n = np.asarray(z32).size // 32
-        z32 = _u8(z32, 32 * n, "z32")
-        sig64 = _u8(sig64, 64 * n, "sig64")
-        Q_xy = _u8(Q_xy, 64 * n, "Q_xy")
+        fb = FBYTES[c]
+        n = np.asarray(z32).size // fb
+        z32 = _u8(z32, fb * n, "z")
+        sig64 = _u8(sig64, 2 * fb * n, "sig")
+        Q_xy = _u8(Q_xy, 2 * fb * n, "Q_xy")
         valid = np.zeros(n, np.uint8)
         self._check(self.lib.ecg_ecdsa_verify_batch(self._ctx, c, n, _ptr(z32), _ptr(sig64), _ptr(Q_xy), 1 if low_s_only else 0, _ptr(valid)))
         return valid

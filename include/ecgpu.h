@@ -49,9 +49,11 @@ typedef enum {
  * brainpoolP384, 28 for P-224, 24 for P-192, 66 for P-521 — read "32 / 64 / 96" in every size below as "FB / 2 FB / 3 FB".
  * Byte order is the one the reference uses for the curve: big-endian everywhere except bign-curve256v1, whose field
  * elements and scalars are little-endian (bignp256/src/arithmetic/field.rs:65, bignp256/src/lib.rs:102).
- * Curves other than secp256k1 / P-256 are served by the hot-path entries (mul_batch[_x], mul_gen_batch,
- * lincomb[_partial], point_sum, batch_normalize[_hom], field_op_batch); the 256-bit-only widening entries
- * (verification, SEC1 decompression, a*G + b*P, field sqrt, hash-to-curve) answer ECG_EINVAL for them. */
+ * Every curve is served by the hot-path entries (mul_batch[_x], mul_gen_batch, lincomb[_partial], point_sum,
+ * batch_normalize[_hom], field_op_batch) and by mul_gen_add_batch; ecdsa_verify_batch serves every curve the reference
+ * defines ECDSA for (all but sm2 and bign-curve256v1, whose signature schemes differ); hash to curve the four curves with
+ * an RFC 9380 suite in the reference; BIP340, SEC1 decompression and the field square root are written for the two
+ * hot-path curves and answer ECG_EINVAL for the others. */
 typedef enum {
   ECG_SECP256K1 = 0,
   ECG_NISTP256 = 1,
@@ -164,10 +166,12 @@ ecg_status ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const 
 ecg_status ecg_schnorr_verify_batch(ecg_ctx* ctx, size_t n, const uint8_t* pk_x, const uint8_t* msg32,
                                     const uint8_t* sig64, uint8_t* valid);
 
-/* ECDSA verification: z32[i] = message digest (reduced mod n inside), sig64[i] = r || s (Signature::try_from
- * encoding), Q_xy[i] = public key x || y.  low_s_only != 0 additionally rejects s > n/2 (EcdsaCurve::NORMALIZE_S,
- * k256/src/ecdsa.rs:104-106).  Replaces ecdsa_core::VerifyingKey::verify_prehash for k256::ecdsa::VerifyingKey /
- * p256::ecdsa::VerifyingKey (k256/src/ecdsa.rs:93-121, p256/src/ecdsa.rs) over a batch. */
+/* ECDSA verification: z32[i] = the prehash after bits2field, one FB-byte big-endian record (reduced mod n inside),
+ * sig64[i] = r || s (2 FB bytes, Signature::try_from encoding), Q_xy[i] = public key x || y (2 FB).  low_s_only != 0
+ * additionally rejects s > n/2 (EcdsaCurve::NORMALIZE_S: true for k256 only, k256/src/ecdsa.rs:104-106).  Replaces
+ * ecdsa_core::VerifyingKey::verify_prehash over a batch for every curve the reference gives an EcdsaCurve impl:
+ * k256/src/ecdsa.rs:93-121, p256/src/ecdsa.rs, p192 / p224 / p384 / p521 src/ecdsa.rs, bp256/src/{r1,t1}/ecdsa.rs,
+ * bp384/src/{r1,t1}/ecdsa.rs (ECG_SM2, ECG_BIGNP256: ECG_EINVAL — SM2DSA and the bign scheme are not ECDSA). */
 ecg_status ecg_ecdsa_verify_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* z32, const uint8_t* sig64,
                                   const uint8_t* Q_xy, int low_s_only, uint8_t* valid);
 

@@ -104,7 +104,7 @@ def ecdsa_full(curve):
     txt = open(f"{REF}/{curve}/src/test_vectors/ecdsa.rs").read()
     out = []
     for m in re.finditer(r"TestVector\s*\{(.*?)\}", txt, re.S):
-        f = {k: v.lower() for k, v in re.findall(r'(\w+):\s*&hex!\("([0-9a-fA-F]+)"\)', m.group(1))}
+        f = {k: v.lower() for k, v in re.findall(r'(\w+):\s*&hex!\(\s*"([0-9a-fA-F]+)"\s*\)', m.group(1))}
         if {"d", "q_x", "q_y", "k", "m", "r", "s"} <= set(f):
             out.append(f)
     return {"source": f"{curve}/src/test_vectors/ecdsa.rs", "vectors": out}
@@ -183,7 +183,7 @@ def h2c_vectors():
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    for curve in ("k256", "p256"):
+    for curve in ("k256", "p256", "p224", "p384", "p521"):
         with open(os.path.join(OUT, f"{curve}_wycheproof.json"), "w") as f:
             v = wycheproof(curve)
             json.dump(v, f, indent=0)
@@ -192,7 +192,7 @@ def main():
         v = bip340_vectors()
         json.dump(v, f, indent=1)
         print("bip340", len(v["vectors"]))
-    for curve in ("k256", "p256"):
+    for curve in ("k256", "p256", "p192", "p224", "p384", "p521"):
         with open(os.path.join(OUT, f"{curve}_ecdsa.json"), "w") as f:
             v = ecdsa_full(curve)
             json.dump(v, f, indent=1)

@@ -53,10 +53,11 @@ def edge_scalars(c):
 
 # ---- Wycheproof ECDSA vectors (tests/golden/*_wycheproof.json, from the reference's blobby files) ----
 
-def parse_der_signature(sig: bytes, n: int):
+def parse_der_signature(sig: bytes, n: int, nb: int = 32):
     """Strict DER, as `ecdsa::der::Signature::from_der` + `Signature::from_scalars` accept it (the reference's
     Wycheproof harness, k256/src/ecdsa.rs:305-317): SEQUENCE { INTEGER r, INTEGER s }, minimal definite lengths,
-    minimal non-negative INTEGERs of at most 32 significant bytes, nothing trailing, 0 < r, s < n.  -> (r, s) | None"""
+    minimal non-negative INTEGERs of at most nb (the curve's field size) significant bytes, nothing trailing, 0 < r, s < n.
+    -> (r, s) | None"""
     def length(buf, pos):
         if pos >= len(buf):
             return None
@@ -83,7 +84,7 @@ def parse_der_signature(sig: bytes, n: int):
             return None
         if ln > 1 and body[0] == 0 and not body[1] & 0x80:
             return None  # superfluous leading zero
-        if len(body.lstrip(b"\x00")) > 32:
+        if len(body.lstrip(b"\x00")) > nb:
             return None
         return int.from_bytes(body, "big"), pos + ln
 
@@ -123,20 +124,25 @@ def wycheproof_cases(curve: str):
     (each must be an expected failure)."""
     import hashlib
     c = pyref.CURVES[curve]
+    nb = pyref.fbytes(c)
+    # the curve's DigestPrimitive (p224/src/ecdsa.rs, p384/src/ecdsa.rs, p521/src/ecdsa.rs), then bits2field: the leftmost
+    # field-size bytes of a longer digest, a shorter one right-aligned (the `ecdsa` crate's hazmat::bits2field)
+    digest = {"k256": "sha256", "p256": "sha256", "p224": "sha224", "p384": "sha384", "p521": "sha512"}[curve]
     vec = json.load(open(os.path.join(GOLDEN, f"{curve}_wycheproof.json")))["vectors"]
     cases, rejected = [], []
     for v in vec:
         wx, wy = bytes.fromhex(v["wx"]), bytes.fromhex(v["wy"])
-        assert not any(wx[:-32]) and not any(wy[:-32])          # element_from_padded_slice
+        assert not any(wx[:-nb]) and not any(wy[:-nb])          # element_from_padded_slice
         q = (int.from_bytes(wx, "big"), int.from_bytes(wy, "big"))
         sig = bytes.fromhex(v["sig"])
-        rs = parse_der_signature(sig, c.n) if v["fmt"] == "der" else parse_p1363_signature(sig, c.n)
+        rs = parse_der_signature(sig, c.n, nb) if v["fmt"] == "der" else parse_p1363_signature(sig, c.n)
         if rs is None:
             rejected.append(v)
             continue
         r, s = rs
         if curve == "k256" and s > c.n // 2:
             s = c.n - s                                          # Signature::normalize_s
-        z = hashlib.sha256(bytes.fromhex(v["msg"])).digest()
+        h = hashlib.new(digest, bytes.fromhex(v["msg"])).digest()
+        z = h[:nb] if len(h) >= nb else bytes(nb - len(h)) + h
         cases.append((z, r, s, q, bool(v["pass"])))
     return cases, rejected

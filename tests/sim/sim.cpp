@@ -867,3 +867,46 @@ extern "C" int simk_mul_batch_ct(int curve, size_t n, const uint8_t* k, const ui
   }
   return 0;
 }
+
+// ecg_ecdsa_verify_batch / ecg_mul_gen_add_batch for the curves beyond secp256k1 / P-256: the generic twins
+// (ecdsa_prep_generic_kernel -> mul_gen_add_generic_kernel -> normalize -> ecdsa_check_generic_kernel), curve ids 2..11
+#define SIM_FOR_GENERIC(curve, ...)                        \
+  if ((curve) == 2) {                                      \
+    typedef CurveP384 CV;                                  \
+    __VA_ARGS__;                                           \
+  } else {                                                 \
+    SIM_FOR_EXT(curve, __VA_ARGS__);                       \
+  }
+template <class C>
+static void simk_mga_generic(size_t n, const uint8_t* a, const uint8_t* b, const uint8_t* pxy, const uint8_t* pinf, const uint32_t* table,
+                             uint8_t* out_xy, uint8_t* out_inf, uint32_t* status) {
+  constexpr size_t NLc = C::F::NL;
+  std::vector<uint32_t> jac(3 * NLc * n + 64);
+  size_t blocks = (n + SIM_BLOCK - 1) / SIM_BLOCK;
+  std::vector<uint32_t> gtab(blocks * SIM_BLOCK * (8 * 3 * NLc));
+  sim_launch(n, SIM_BLOCK, [&] { mul_gen_add_generic_kernel<C, SIM_BLOCK, 4>(a, b, pxy, pinf, n, table, jac.data(), gtab.data(), status, 0); });
+  simk_normalize<C>(jac, n, out_xy, out_inf);
+}
+extern "C" int simk_mul_gen_add_generic(int curve, size_t n, const uint8_t* a, const uint8_t* b, const uint8_t* pxy, const uint8_t* pinf,
+                                        const uint32_t* table, uint8_t* out_xy, uint8_t* out_inf, uint32_t* status) {
+  status[0] = 0;
+  status[1] = 0xFFFFFFFFu;
+  SIM_FOR_GENERIC(curve, simk_mga_generic<CV>(n, a, b, pxy, pinf, table, out_xy, out_inf, status));
+  return 0;
+}
+template <class C>
+static void simk_ecdsa_generic(size_t n, const uint8_t* z, const uint8_t* sig, const uint8_t* q, int low_s, const uint32_t* table, uint8_t* valid) {
+  constexpr size_t NLc = C::F::NL, FB = C::F::FB;
+  std::vector<uint32_t> scr(NLc * n + 8);
+  std::vector<uint8_t> vp(2 * FB * n), va(FB * n), vb(FB * n), vok(n), vxy(2 * FB * n), vinf(n);
+  uint32_t status[2] = {0, 0xFFFFFFFFu};
+  size_t threads = (n + 31) / 32;
+  sim_launch(threads, 128, [&] { ecdsa_prep_generic_kernel<C>(z, sig, q, n, low_s, scr.data(), vp.data(), va.data(), vb.data(), vok.data()); });
+  simk_mga_generic<C>(n, va.data(), vb.data(), vp.data(), nullptr, table, vxy.data(), vinf.data(), status);
+  sim_launch(n, 256, [&] { ecdsa_check_generic_kernel<C>(sig, vxy.data(), vinf.data(), vok.data(), n, valid); });
+}
+extern "C" int simk_ecdsa_verify_generic(int curve, size_t n, const uint8_t* z, const uint8_t* sig, const uint8_t* q, int low_s,
+                                         const uint32_t* table, uint8_t* valid) {
+  SIM_FOR_GENERIC(curve, simk_ecdsa_generic<CV>(n, z, sig, q, low_s, table, valid));
+  return 0;
+}

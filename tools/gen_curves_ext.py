@@ -149,7 +149,27 @@ def main():
         order = "little" if c["le"] else "big"
         gbytes = c["gx"].to_bytes(fb, order) + c["gy"].to_bytes(fb, order)
         host.append((c, gbytes))
-    out.append("}  // namespace ecg\n\n")
+    # scalar fields: the same Montgomery policy over the group order n (ECDSA verification: s^-1, u1, u2; hash_to_scalar)
+    out.append("// ---- scalar fields: FpMontT over the group order (arithmetic mod n for ECDSA verification and hash_to_scalar) ----\n")
+    out.append("template <class C>\nstruct ScalarField;\n")
+    hot = [("K256", "CurveK256", 8, 32, 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141),
+           ("P256", "CurveP256", 8, 32, 0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551),
+           ("P384", "CurveP384", 12, 48, 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFC7634D81F4372DDF581A0DB248B0A77AECEC196ACCC52973)]
+    allc = hot + [(c["name"], "Curve" + c["name"], c["nl"], c.get("fb", 4 * c["nl"]), c["n"]) for c in CURVES]
+    done = set()
+    for name, cv, nl, fb, n in allc:
+        le = any(c["name"] == name and c["le"] for c in CURVES)
+        key = (n, nl, le)
+        R = 1 << (32 * nl)
+        assert n % 2 == 1 and n < R
+        out.append("struct Mn%s {\n  static constexpr int NL = %d;\n  static constexpr int FB = %d;\n  static constexpr bool LE = %s;\n" % (name, nl, fb, "true" if le else "false"))
+        out.append("  static constexpr uint32_t N0INV = 0x%08Xu;  // -n^-1 mod 2^32\n" % ((-pow(n, -1, 1 << 32)) % (1 << 32)))
+        out.append(accessor("P", n, nl))
+        out.append(accessor("ONE", R % n, nl))
+        out.append(accessor("R2", R * R % n, nl))
+        out.append(accessor("PM2", n - 2, nl))
+        out.append("};\ntemplate <>\nstruct ScalarField<%s> {\n  typedef FpMontT<Mn%s> T;\n};\n" % (cv, name))
+    out.append("\n}  // namespace ecg\n\n")
     # host-side table: order limbs, generator bytes (ABI byte order), sizes
     out.append("// host-side descriptors (ecgpu.cu: sizes at the ABI, fixed-base table construction)\n")
     out.append("struct EcgExtCurveHost {\n  int id, nl, fb, le;  // limbs, bytes per record, little-endian records\n  uint32_t n[18];\n  uint8_t g[136];\n};\n")
