@@ -972,6 +972,83 @@ def measure_consttime_cost(B, steps):
             "bit_exact_coverage": "every output of the constant-time ctx equals the default ctx's (which the other configs compare with the CPU restatement)"}
 
 
+def measure_hash_to_curve(B, steps):
+    """Widening record: RFC 9380 hash_to_curve (RO) over 2^18 messages of 32 bytes per GPU for the two
+    SHA-256 suites — SHA-256 expansion, two SSWU maps (one exponentiation each), the isogeny (secp256k1), one addition, batched
+    normalisation, all on the device.  Parity: a 256-element sample against the big-integer model (pinned to the reference's
+    vectors, tests/test_h2c.py), and every output fed back through ecg_mul_batch with k = 1, whose decoder rejects anything that
+    is not a point of the curve."""
+    import torch
+
+    import pyref
+
+    eng, host_eng, dev, world, rank = B.eng, B.host_eng, B.dev, B.world, B.rank
+    n, mlen = 1 << 18, 32
+    dst = b"QUUX-V01-CS02-with-bench"
+    out = {}
+    all_ok = True
+    for name in ("k256", "p256"):
+        rng = np.random.default_rng(0xB2000300 + rank)
+        M = rng.integers(0, 256, size=(n, mlen), dtype=np.uint8)
+        offs = (np.arange(n + 1, dtype=np.uint64) * mlen)
+        m_host = torch.from_numpy(M.reshape(-1)).pin_memory()
+        o_host = torch.from_numpy(offs.view(np.int64)).pin_memory()
+        md, od = m_host.to(dev), o_host.to(dev)
+        oxy = torch.empty(64 * n, dtype=torch.uint8, device=dev)
+        oinf = torch.empty(n, dtype=torch.uint8, device=dev)
+        d = np.frombuffer(dst, np.uint8).copy()
+        cid = pyref.CURVE_IDS[name]
+
+        def step_dev():
+            B.flush.zero_()
+            eng._check(eng.lib.ecg_hash_to_curve_batch(eng._ctx, cid, n, md.data_ptr(), od.data_ptr(), d.ctypes.data, len(dst), 0,
+                                                       oxy.data_ptr(), oinf.data_ptr()))
+
+        for _ in range(3):
+            step_dev()
+        barrier_sync(world)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            step_dev()
+        ev1.record()
+        barrier_sync(world)
+        ms = max_over_ranks(ev0.elapsed_time(ev1), world) / steps
+        msgs = [M[i].tobytes() for i in range(n)]
+        host_eng.hash_to_curve(name, msgs[:1024], dst)
+        barrier_sync(world)
+        t0 = time.perf_counter()
+        h_xy = h_inf = None
+        for _ in range(steps):
+            h_xy, h_inf = host_eng.hash_to_curve(name, msgs, dst)      # packs the messages, H2D, kernels, D2H
+        barrier_sync(world)
+        e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+        dev_same = bool(np.array_equal(oxy.cpu().numpy(), np.asarray(h_xy).reshape(-1)) and not h_inf.any())
+        sample_ok = all(pyref.dec_point(h_xy[i].tobytes(), 0) == pyref.hash_to_curve(name, msgs[i], dst) for i in range(0, n, n // 256))
+        ones = np.zeros((n, 32), np.uint8)
+        ones[:, 31] = 1
+        try:   # every output is a point of the curve: the decoder of ecg_mul_batch accepts all of them, and 1 * P = P
+            r_xy, r_inf = host_eng.mul_batch(name, ones.reshape(-1), np.asarray(h_xy).reshape(-1), None)
+            on_curve = bool(np.array_equal(r_xy, h_xy) and not r_inf.any())
+        except Exception:  # noqa: BLE001
+            on_curve = False
+        ok = B.all_true(dev_same and sample_ok and on_curve)
+        all_ok = all_ok and ok
+        out[name] = {"value": world * n / (ms * 1e-3), "unit": "messages/s", "ms_per_step": ms, "messages_per_gpu": n, "message_bytes": mlen,
+                     "e2e": {"value": world * n * steps / e2e_s, "unit": "messages/s", "h2d_bytes_per_step": n * (mlen + 8) + 8,
+                             "d2h_bytes_per_step": 65 * n, "matches_device_path": dev_same,
+                             "note": "includes packing 2^18 Python byte strings into one buffer on the host"},
+                     "bit_exact": ok}
+    if rank != 0:
+        return None
+    return {"metric": "messages/s (hash_to_curve, RO)", "unit": "messages/s", "n_gpus": world, "steps": steps,
+            "config": {"workload": "widening step (SURVEY 8(f) rank 4): RFC 9380 hash_to_curve, secp256k1_XMD:SHA-256_SSWU_RO_ and "
+                                   "P256_XMD:SHA-256_SSWU_RO_, 2^18 messages of 32 bytes per GPU, L2 flushed between steps"},
+            "curves": out, "bit_exact": all_ok,
+            "bit_exact_coverage": "256-element sample per curve and rank vs the big-integer model (pinned to the reference's RFC 9380 vectors); "
+                                  "every output accepted by ecg_mul_batch's on-curve decoder and reproduced by 1 * P; host path == device path"}
+
+
 def run_ours(args):
     B = Bench(args)
     world, rank = B.world, B.rank
@@ -986,6 +1063,7 @@ def run_ours(args):
         configs["6_p384_varbase"] = measure_p384(B, max(3, sub_steps // 2))
         configs["7_more_curves"] = measure_more_curves(B, 3)
         configs["8_consttime_cost"] = measure_consttime_cost(B, 5)
+        configs["9_hash_to_curve"] = measure_hash_to_curve(B, 5)
         if world > 1:
             configs["strong_scaling"] = strong_scaling(B)
             barrier_sync(world)
