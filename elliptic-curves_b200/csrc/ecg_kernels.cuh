@@ -670,6 +670,107 @@ ECG_KERNEL(128)
   valid[idx] = ok ? 1 : 0;
 }
 
+// ---- SEC1 decompression and the field square root for the other curves with p = 3 (mod 4) (everything except P-224) -----
+// r = a^((p+1)/4) by fixed 4-bit windows over the public exponent; E supplies PP14(i), the limbs of (p + 1) / 4
+template <class F, class E>
+ECG_DEV void sqrt_candidate_generic(typename F::FeT& r, const typename F::FeT& a) {
+  typename F::FeT tab[16], acc;
+  F::set_one(tab[0]);
+  tab[1] = a;
+#pragma unroll 1
+  for (int i = 2; i < 16; i++) F::mul(tab[i], tab[i - 1], a);
+  F::set_one(acc);
+#pragma unroll 1
+  for (int w = 8 * F::NL - 1; w >= 0; w--) {
+    F::sqr_n(acc, acc, 4);
+    uint32_t limb = 0;
+#pragma unroll
+    for (int i = 0; i < F::NL; i++) limb = (w >> 3) == i ? E::PP14(i) : limb;
+    F::mul(acc, acc, tab[(limb >> (4 * (w & 7))) & 15u]);
+  }
+  r = acc;
+}
+// records: tag (02 / 03; 00 with an all-zero x = the identity) || x, 1 + FB bytes, big-endian (SEC1 2.3.4)
+template <class C, class E>
+ECG_KERNEL(128)
+    decompress_generic_kernel(const uint8_t* __restrict__ sec1, size_t n, uint8_t* __restrict__ out_xy, uint8_t* __restrict__ out_inf,
+                              uint8_t* __restrict__ valid) {
+  typedef typename C::F F;
+  typedef typename F::FeT Fe;
+  constexpr int NL = F::NL, FB = F::FB;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const uint8_t* rec = sec1 + (size_t)(FB + 1) * idx;
+  const uint8_t tag = rec[0];
+  Fe xc;
+  load_be_bytes<NL, FB>(xc.v, rec + 1);  // the x bytes are not word-aligned
+  uint32_t any = 0;
+#pragma unroll
+  for (int i = 0; i < NL; i++) any |= xc.v[i];
+  bool ok = false, inf = false;
+  Fe x, y;
+  if (tag == 0 && any == 0) {
+    ok = inf = true;
+  } else if ((tag == 2 || tag == 3) && ltN<NL>(xc.v, C::P())) {
+    Fe rhs, t, b, chk;
+    F::from_canonical(x, xc);
+    F::sqr(rhs, x);
+    F::mul(rhs, rhs, x);
+    if (C::A_IS_MINUS3 == 1) {
+      F::mul_small(t, x, 3);
+      F::sub(rhs, rhs, t);
+    } else if constexpr (C::A_IS_MINUS3 == 2) {
+      Fe ca;
+      F::curve_a(ca);
+      F::mul(t, x, ca);
+      F::add(rhs, rhs, t);
+    }
+    C::b_internal(b);
+    F::add(rhs, rhs, b);
+    sqrt_candidate_generic<F, E>(y, rhs);
+    F::sqr(chk, y);
+    F::sub(chk, chk, rhs);
+    ok = F::is_zero(chk);
+    Fe yc;
+    F::to_canonical(yc, y);
+    if ((yc.v[0] & 1u) != (uint32_t)(tag & 1u)) F::neg(y, y);
+  }
+  Fe cx, cy;
+  if (ok && !inf) {
+    F::to_canonical(cx, x);
+    F::to_canonical(cy, y);
+  } else {
+    F::set_zero(cx);
+    F::set_zero(cy);
+  }
+  store_fe<F>(out_xy + 2 * FB * idx, cx.v);
+  store_fe<F>(out_xy + 2 * FB * idx + FB, cy.v);
+  out_inf[idx] = inf ? 1 : 0;
+  valid[idx] = ok ? 1 : 0;
+}
+template <class C, class E>
+ECG_KERNEL(128)
+    field_sqrt_generic_kernel(size_t n, const uint8_t* __restrict__ a, uint8_t* __restrict__ out, uint8_t* __restrict__ is_square,
+                              uint32_t* __restrict__ status, size_t base) {
+  typedef typename C::F F;
+  typedef typename F::FeT Fe;
+  constexpr int NL = F::NL, FB = F::FB;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  Fe x, r, chk;
+  load_fe<F>(x.v, a + FB * idx);
+  if (!ltN<NL>(x.v, C::P())) report_error(status, ERRF_POINT, base + idx);
+  F::from_canonical(x, x);
+  sqrt_candidate_generic<F, E>(r, x);
+  F::sqr(chk, r);
+  F::sub(chk, chk, x);
+  bool ok = F::is_zero(chk);
+  F::to_canonical(r, r);
+  if (!ok) F::set_zero(r);
+  store_fe<F>(out + FB * idx, r.v);
+  is_square[idx] = ok ? 1 : 0;
+}
+
 // canonical affine big-endian bytes (n * 2FB) -> table words (internal form); used once, when a table is built
 template <class C>
 ECG_KERNEL(256)

@@ -773,6 +773,20 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
   const uint8_t* dx = nullptr;
   ST_TRY(stage_in(ctx, L, B_X, op.x, off, cnt, op.xstride, &dx));
   ST_TRY(stage_out(ctx, L, off, cnt, op.out, op.ostride, op.oinf, dp));
+  if ((op.kind == BatchOp::DECOMPRESS || op.kind == BatchOp::FSQRT) && !curve_256(op.curve)) {
+    // generic twins: y = rhs^((p+1)/4) for every curve with p = 3 (mod 4)
+    if (op.kind == BatchOp::DECOMPRESS) {
+      ST_TRY(ensure(ctx, L, B_V4, cnt));
+      uint8_t* vvalid = (ctx->devptr() && op.aux_out) ? op.aux_out + off : (uint8_t*)L.buf[B_V4];
+      ECDSA_FOR_CURVE((decompress_generic_kernel<CV, SqrtExp<CV>::T><<<grid_for(cnt, 128), 128, 0, L.s()>>>(dp.p, cnt, dp.out, dp.oinf, vvalid)));
+      LAUNCHED(ctx);
+      if (!ctx->devptr() && op.aux_out) CU_TRY(ctx, cudaMemcpyAsync(op.aux_out + off, vvalid, cnt, cudaMemcpyDeviceToHost, L.s()));
+    } else {
+      ECDSA_FOR_CURVE((field_sqrt_generic_kernel<CV, SqrtExp<CV>::T><<<grid_for(cnt, 128), 128, 0, L.s()>>>(cnt, dp.k, dp.out, dp.oinf, L.status, off)));
+      LAUNCHED(ctx);
+    }
+    return copy_back(ctx, L, off, cnt, op.out, op.ostride, op.oinf, dp);
+  }
   if (op.kind == BatchOp::ECDSA && !curve_256(op.curve)) {
     // ECDSA for the other curves: generic front end -> (u1, u2, Q) -> u1*G + u2*Q -> affine -> verdict (the 256-bit path
     // below, record sizes by the curve)
@@ -1057,6 +1071,14 @@ __attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_mul_gen_add_batch(e
 __attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_ecdsa_verify_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* z32, const uint8_t* sig64, const uint8_t* Q_xy, int low_s_only, uint8_t* valid);
 __attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, const uint8_t* b, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
 __attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_ecdsa_verify_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* z32, const uint8_t* sig64, const uint8_t* Q_xy, int low_s_only, uint8_t* valid);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu1_ecg_decompress_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* sec1_33, uint8_t* out_xy, uint8_t* out_inf, uint8_t* valid);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu1_ecg_field_sqrt_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, uint8_t* out, uint8_t* is_square);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu2_ecg_decompress_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* sec1_33, uint8_t* out_xy, uint8_t* out_inf, uint8_t* valid);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu2_ecg_field_sqrt_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, uint8_t* out, uint8_t* is_square);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_decompress_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* sec1_33, uint8_t* out_xy, uint8_t* out_inf, uint8_t* valid);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu3_ecg_field_sqrt_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, uint8_t* out, uint8_t* is_square);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_decompress_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* sec1_33, uint8_t* out_xy, uint8_t* out_inf, uint8_t* valid);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_field_sqrt_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, uint8_t* out, uint8_t* is_square);
 #define ECG_FORWARD(name, ...)                                     \
   do {                                                             \
     if ((int)curve >= 0 && (int)curve < ECG_CURVE_COUNT) {         \
@@ -1138,25 +1160,28 @@ ECG_API(ecg_mul_gen_add_batch)(ecg_ctx* ctx, ecg_curve curve, size_t n, const ui
   return run_batch(ctx, op, n);
 }
 
-#if ECG_TU == 0
-extern "C" ecg_status ecg_decompress_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* sec1_33, uint8_t* out_xy,
-                                            uint8_t* out_inf, uint8_t* valid) {
+ECG_API(ecg_decompress_batch)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* sec1_33, uint8_t* out_xy,
+                              uint8_t* out_inf, uint8_t* valid) {
   if (!ctx) return ECG_EINVAL;
+  ECG_FORWARD(ecg_decompress_batch, ctx, curve, n, sec1_33, out_xy, out_inf, valid);
   if (n == 0) return ECG_OK;
-  if (!sec1_33 || !out_xy || !out_inf || !valid || !curve_256(curve)) {
-    ctx->err = "ecg_decompress_batch: null pointer or unknown curve";
+  // p = 1 (mod 4) for P-224 (no single-exponentiation square root); bign-curve256v1 has no SEC1 form (little-endian records)
+  if (!sec1_33 || !out_xy || !out_inf || !valid || !curve_ok(curve) || curve == ECG_NISTP224 || curve == ECG_BIGNP256) {
+    ctx->err = "ecg_decompress_batch: null pointer or a curve without SEC1 decompression here";
     return ECG_EINVAL;
   }
   BatchOp op;
   op.kind = BatchOp::DECOMPRESS;
   op.curve = curve;
   op.p = sec1_33;
-  op.pstride = 33;
+  op.pstride = fbytes(curve) + 1;
+  op.ostride = 2 * fbytes(curve);
   op.out = out_xy;
   op.oinf = out_inf;
   op.aux_out = valid;
   return run_batch(ctx, op, n);
 }
+#if ECG_TU == 0
 
 extern "C" ecg_status ecg_schnorr_verify_batch(ecg_ctx* ctx, size_t n, const uint8_t* pk_x, const uint8_t* msg32, const uint8_t* sig64,
                                                 uint8_t* valid) {
@@ -1265,23 +1290,22 @@ ECG_API(ecg_mul_batch_x)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t*
   return run_batch(ctx, op, n);
 }
 
-#if ECG_TU == 0
-extern "C" ecg_status ecg_field_sqrt_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, uint8_t* out,
-                                           uint8_t* is_square) {
+ECG_API(ecg_field_sqrt_batch)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, uint8_t* out,
+                              uint8_t* is_square) {
   if (!ctx) return ECG_EINVAL;
+  ECG_FORWARD(ecg_field_sqrt_batch, ctx, curve, n, a, out, is_square);
   if (n == 0) return ECG_OK;
-  if (!a || !out || !is_square || !curve_256(curve)) return ECG_EINVAL;
+  if (!a || !out || !is_square || !curve_ok(curve) || curve == ECG_NISTP224) return ECG_EINVAL;  // P-224: p = 1 (mod 4)
   BatchOp op;
   op.kind = BatchOp::FSQRT;
   op.curve = curve;
   op.k = a;
+  op.kstride = fbytes(curve);
   op.out = out;
   op.oinf = is_square;
-  op.ostride = 32;
+  op.ostride = fbytes(curve);
   return run_batch(ctx, op, n);
 }
-
-#endif  // ECG_TU == 0
 
 ECG_API(ecg_field_op_batch)(ecg_ctx* ctx, ecg_curve curve, int fop, size_t n, const uint8_t* a, const uint8_t* b,
                                          uint8_t* out) {

@@ -384,15 +384,16 @@ class Engine:
         return valid
 
     def decompress_batch(self, curve, sec1_33):
-        """AffinePoint::decompress over a batch of 33-byte SEC1 compressed records -> (xy, inf, valid)"""
+        """AffinePoint::decompress over a batch of (1 + FB)-byte SEC1 compressed records -> (xy, inf, valid)"""
         c = CURVE_IDS[curve]
-        n = np.asarray(sec1_33).size // 33
-        sec1_33 = _u8(sec1_33, 33 * n, "sec1_33")
-        out_xy = np.empty(64 * n, np.uint8)
+        fb = FBYTES[c]
+        n = np.asarray(sec1_33).size // (fb + 1)
+        sec1_33 = _u8(sec1_33, (fb + 1) * n, "sec1")
+        out_xy = np.empty(2 * fb * n, np.uint8)
         out_inf = np.empty(n, np.uint8)
         valid = np.empty(n, np.uint8)
         self._check(self.lib.ecg_decompress_batch(self._ctx, c, n, _ptr(sec1_33), _ptr(out_xy), _ptr(out_inf), _ptr(valid)))
-        return out_xy.reshape(n, 64), out_inf, valid
+        return out_xy.reshape(n, 2 * fb), out_inf, valid
 
     @staticmethod
     def sec1_compress(xy, inf=None):
@@ -446,14 +447,15 @@ class Engine:
         return out_xy.reshape(n, 2 * fb), out_inf
 
     def field_sqrt(self, curve, a):
-        """FieldElement::sqrt over a batch -> (roots n x 32, is_square)"""
+        """FieldElement::sqrt over a batch -> (roots n x FB, is_square)"""
         c = CURVE_IDS[curve]
-        n = np.asarray(a).size // 32
-        a = _u8(a, 32 * n, "a")
-        out = np.empty(32 * n, np.uint8)
+        fb = FBYTES[c]
+        n = np.asarray(a).size // fb
+        a = _u8(a, fb * n, "a")
+        out = np.empty(fb * n, np.uint8)
         ok = np.empty(n, np.uint8)
         self._check(self.lib.ecg_field_sqrt_batch(self._ctx, c, n, _ptr(a), _ptr(out), _ptr(ok)))
-        return out.reshape(n, 32), ok
+        return out.reshape(n, fb), ok
 
     def field_op(self, curve, op, a, b=None):
         c = CURVE_IDS[curve]

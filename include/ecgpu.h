@@ -52,8 +52,9 @@ typedef enum {
  * Every curve is served by the hot-path entries (mul_batch[_x], mul_gen_batch, lincomb[_partial], point_sum,
  * batch_normalize[_hom], field_op_batch) and by mul_gen_add_batch; ecdsa_verify_batch serves every curve the reference
  * defines ECDSA for (all but sm2 and bign-curve256v1, whose signature schemes differ); hash to curve the four curves with
- * an RFC 9380 suite in the reference; BIP340, SEC1 decompression and the field square root are written for the two
- * hot-path curves and answer ECG_EINVAL for the others. */
+ * an RFC 9380 suite in the reference; SEC1 decompression and the field square root every curve with p = 3 (mod 4), i.e. one
+ * exponentiation by (p + 1) / 4 (all but P-224; decompression also refuses bign-curve256v1, whose SEC1 form is not
+ * pinned by a reference vector); BIP340 is secp256k1's alone.  What a curve does not serve answers ECG_EINVAL. */
 typedef enum {
   ECG_SECP256K1 = 0,
   ECG_NISTP256 = 1,
@@ -175,11 +176,13 @@ ecg_status ecg_schnorr_verify_batch(ecg_ctx* ctx, size_t n, const uint8_t* pk_x,
 ecg_status ecg_ecdsa_verify_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* z32, const uint8_t* sig64,
                                   const uint8_t* Q_xy, int low_s_only, uint8_t* valid);
 
-/* SEC1 compressed point decoding (rank 2 of SURVEY 8(f)): records of 33 bytes (02|03 || x; 33 zero bytes = the
- * identity).  valid[i] = 0 when the tag is unknown, x >= p, or x^3 + ax + b has no square root; out_xy / out_inf as
+/* SEC1 compressed point decoding (rank 2 of SURVEY 8(f)): records of 1 + FB bytes (02|03 || x; all zero bytes = the
+ * identity; 33 bytes for the 256-bit curves, 49 for the 384-bit ones, 25 for P-192, 67 for P-521).  valid[i] = 0 when the tag is unknown, x >= p, or x^3 + ax + b has no square root; out_xy / out_inf as
  * in ecg_mul_batch.  Replaces AffinePoint::decompress / from_sec1_point over a batch
  * (primeorder/src/affine.rs:179-198, :212-232; k256/src/arithmetic/affine.rs DecompressPoint; sqrt:
- * k256/src/arithmetic/field.rs:200-235, p256/src/arithmetic/field.rs:121-147). */
+ * k256/src/arithmetic/field.rs:200-235, p256/src/arithmetic/field.rs:121-147, p384/src/arithmetic/field.rs sqrt,
+ * p521/src/arithmetic/field.rs:386; the primefield-generated fields of sm2 / brainpool / p192 through the same
+ * (p + 1) / 4 exponent).  ECG_NISTP224 (p = 1 mod 4: Tonelli-Shanks) and ECG_BIGNP256: ECG_EINVAL. */
 ecg_status ecg_decompress_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* sec1_33, uint8_t* out_xy,
                                 uint8_t* out_inf, uint8_t* valid);
 
@@ -201,9 +204,10 @@ ecg_status ecg_batch_normalize_hom(ecg_ctx* ctx, ecg_curve curve, size_t n, cons
 ecg_status ecg_mul_batch_x(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy,
                            const uint8_t* P_inf, uint8_t* out_x, uint8_t* out_inf);
 
-/* out[i] = sqrt(a[i]) as the reference returns it, a^((p+1)/4), with is_square[i] = 1; 32 zero bytes and
+/* out[i] = sqrt(a[i]) as the reference returns it, a^((p+1)/4), with is_square[i] = 1; FB zero bytes and
  * is_square[i] = 0 when a[i] is not a square (CtOption::none).  Replaces FieldElement::sqrt
- * (k256/src/arithmetic/field.rs:200-235, p256/src/arithmetic/field.rs:121-147). */
+ * (k256/src/arithmetic/field.rs:200-235, p256/src/arithmetic/field.rs:121-147; every curve with p = 3 (mod 4);
+ * ECG_NISTP224: ECG_EINVAL). */
 ecg_status ecg_field_sqrt_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, uint8_t* out,
                                 uint8_t* is_square);
 

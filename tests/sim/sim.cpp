@@ -910,3 +910,15 @@ extern "C" int simk_ecdsa_verify_generic(int curve, size_t n, const uint8_t* z, 
   SIM_FOR_GENERIC(curve, simk_ecdsa_generic<CV>(n, z, sig, q, low_s, table, valid));
   return 0;
 }
+
+// ecg_decompress_batch / ecg_field_sqrt_batch for the curves beyond secp256k1 / P-256 (p = 3 mod 4)
+extern "C" int simk_decompress_generic(int curve, size_t n, const uint8_t* sec1, uint8_t* out_xy, uint8_t* out_inf, uint8_t* valid) {
+  SIM_FOR_GENERIC(curve, sim_launch(n, 128, [&] { decompress_generic_kernel<CV, SqrtExp<CV>::T>(sec1, n, out_xy, out_inf, valid); }));
+  return 0;
+}
+extern "C" int simk_field_sqrt_generic(int curve, size_t n, const uint8_t* a, uint8_t* out, uint8_t* is_square, uint32_t* status) {
+  status[0] = 0;
+  status[1] = 0xFFFFFFFFu;
+  SIM_FOR_GENERIC(curve, sim_launch(n, 128, [&] { field_sqrt_generic_kernel<CV, SqrtExp<CV>::T>(n, a, out, is_square, status, 0); }));
+  return 0;
+}

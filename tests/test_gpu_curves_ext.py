@@ -167,13 +167,10 @@ def test_rejects_bad_inputs_and_unsupported_entries(engine, cid):
     with pytest.raises(ecgpu.NotOnCurveError) as ei:
         engine.mul_batch(c.name, recs(c, ks), off, pinf)
     assert ei.value.index == 9
-    # SEC1 decompression and the field square root are written for the 256-bit hot-path curves: loud ECG_EINVAL, not a wrong answer
-    # (a*G + b*P and ECDSA verification serve every curve: tests/test_ecdsa_ext.py)
+    # (SEC1 decompression and the field square root: tests/test_sec1_ext.py; a*G + b*P and ECDSA: tests/test_ecdsa_ext.py)
     lib = engine.lib
     z = np.zeros(256, np.uint8)
     vp = lambda a: a.ctypes.data  # noqa: E731
-    assert lib.ecg_decompress_batch(engine._ctx, cid, 1, vp(z), vp(z), vp(z), vp(z)) == ecgpu.ECG_EINVAL
-    assert lib.ecg_field_sqrt_batch(engine._ctx, cid, 1, vp(z), vp(z), vp(z)) == ecgpu.ECG_EINVAL
     assert lib.ecg_mul_batch(engine._ctx, 12, 1, vp(z), vp(z), None, vp(z), vp(z)) == ecgpu.ECG_EINVAL   # unknown curve id
 
 

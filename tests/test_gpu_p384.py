@@ -142,13 +142,7 @@ def test_rejects_bad_inputs_and_unsupported_entries(engine):
     with pytest.raises(ecgpu.NotOnCurveError) as ei:
         engine.mul_batch("p384", ks_bytes(ks), off, pinf)
     assert ei.value.index == 9
-    # SEC1 decompression and the field square root are written for the 256-bit curves: loud ECG_EINVAL, not a wrong answer
-    # (a*G + b*P and ECDSA verification serve P-384 too: tests/test_ecdsa_ext.py)
-    lib = engine.lib
-    z = np.zeros(256, np.uint8)
-    vp = lambda a: a.ctypes.data  # noqa: E731
-    assert lib.ecg_decompress_batch(engine._ctx, 2, 1, vp(z), vp(z), vp(z), vp(z)) == ecgpu.ECG_EINVAL
-    assert lib.ecg_field_sqrt_batch(engine._ctx, 2, 1, vp(z), vp(z), vp(z)) == ecgpu.ECG_EINVAL
+    # (SEC1 decompression, the field square root, a*G + b*P and ECDSA serve P-384 too: tests/test_sec1_ext.py, test_ecdsa_ext.py)
 
 
 def test_large_batch_symmetry_and_sample(engine):

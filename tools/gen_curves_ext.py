@@ -132,6 +132,12 @@ def main():
             out.append(accessor("ONE", R % p, nl))
             out.append(accessor("R2", R * R % p, nl))
             out.append(accessor("PM2", p - 2, nl))
+            if p % 4 == 3:
+                out.append("  static constexpr bool HAS_SQRT_EXP = true;   // p = 3 (mod 4): sqrt(a) = a^((p+1)/4) when a is a square\n")
+                out.append(accessor("PP14", (p + 1) // 4, nl))
+            else:
+                out.append("  static constexpr bool HAS_SQRT_EXP = false;  // p = 1 (mod 4): no single-exponentiation square root\n")
+                out.append(accessor("PP14", 0, nl))
             out.append("};\n")
             out.append("ECG_XCONSTANT uint32_t %s_P[%d] = %s;\n" % (field.upper(), nl, carr(p, nl)))
         if generic_a:
@@ -150,6 +156,11 @@ def main():
         gbytes = c["gx"].to_bytes(fb, order) + c["gy"].to_bytes(fb, order)
         host.append((c, gbytes))
     # scalar fields: the same Montgomery policy over the group order n (ECDSA verification: s^-1, u1, u2; hash_to_scalar)
+    p384 = 2**384 - 2**128 - 2**96 + 2**32 - 1
+    out.append("// (p + 1) / 4 of the hand-written P-384 field policy (square roots: SEC1 decompression)\nstruct SqrtExpP384 {\n  static constexpr bool HAS_SQRT_EXP = true;\n")
+    out.append(accessor("PP14", (p384 + 1) // 4, 12))
+    out.append("};\n")
+    out.append("template <class C>\nstruct SqrtExp {\n  typedef typename C::F::Params T;\n};\ntemplate <>\nstruct SqrtExp<CurveP384> {\n  typedef SqrtExpP384 T;\n};\n")
     out.append("// ---- scalar fields: FpMontT over the group order (arithmetic mod n for ECDSA verification and hash_to_scalar) ----\n")
     out.append("template <class C>\nstruct ScalarField;\n")
     hot = [("K256", "CurveK256", 8, 32, 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141),
