@@ -804,8 +804,16 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
     uint8_t *vxy = (uint8_t*)L.buf[B_V5], *vinf = (uint8_t*)L.buf[B_V6];
     uint32_t* vj = (uint32_t*)L.buf[B_JAC];
     size_t want_threads = std::max<size_t>((cnt + 31) / 32, std::min<size_t>(cnt, (size_t)d.sm_count * 128));
-    ECDSA_FOR_CURVE((ecdsa_prep_generic_kernel<CV><<<grid_for(want_threads, 128), 128, 0, L.s()>>>(dp.k, dp.p, dx, cnt, op.fop, (uint32_t*)L.buf[B_SCR], vp, va,
-                                                                                              vb, vok)));
+#if ECG_TU == 1
+    const bool sm2dsa = (op.fop & 2) != 0;  // ecg_sm2dsa_verify_batch: another front end and verdict around the same a*G + b*P
+    if (sm2dsa)
+      sm2dsa_prep_kernel<CurveSm2><<<grid_for(cnt, 128), 128, 0, L.s()>>>(dp.p, dx, cnt, vp, va, vb, vok);
+    else
+#else
+    const bool sm2dsa = false;
+#endif
+      ECDSA_FOR_CURVE((ecdsa_prep_generic_kernel<CV><<<grid_for(want_threads, 128), 128, 0, L.s()>>>(dp.k, dp.p, dx, cnt, op.fop, (uint32_t*)L.buf[B_SCR], vp,
+                                                                                                va, vb, vok)));
     LAUNCHED(ctx);
     DOM_BEGIN(ctx, L);
     ECDSA_FOR_CURVE((mul_gen_add_generic_kernel<CV, GB, ECDSA_MINBLK><<<grid_for(cnt, GB), GB, 0, L.s()>>>(va, vb, vp, nullptr, cnt, d.fb_table[op.curve], vj,
@@ -813,7 +821,13 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
     LAUNCHED(ctx);
     DOM_END(ctx, L);
     ST_TRY(launch_norm(ctx, d, L, op.curve, cnt, vj, vxy, vinf));
-    ECDSA_FOR_CURVE((ecdsa_check_generic_kernel<CV><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, vxy, vinf, vok, cnt, dp.out)));
+#if ECG_TU == 1
+    if (sm2dsa)
+      sm2dsa_check_kernel<CurveSm2><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.k, dp.p, vxy, vinf, vok, cnt, dp.out);
+    else
+#endif
+      ECDSA_FOR_CURVE((ecdsa_check_generic_kernel<CV><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, vxy, vinf, vok, cnt, dp.out)));
+    (void)sm2dsa;
     LAUNCHED(ctx);
     return copy_back(ctx, L, off, cnt, op.out, op.ostride, nullptr, dp);
   }
@@ -1063,6 +1077,7 @@ __attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_field_op_batch(ecg_
 __attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_lincomb_partial(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xyz);
 __attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_point_sum(ecg_ctx* ctx, ecg_curve curve, size_t m, const uint8_t* xyz, uint8_t* out_xy, uint8_t* out_inf);
 __attribute__((visibility("hidden"))) ecg_status ecg_tu4_ecg_lincomb(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* k, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
+__attribute__((visibility("hidden"))) ecg_status ecg_tu1_ecg_sm2dsa_verify_batch(ecg_ctx* ctx, size_t n, const uint8_t* e32, const uint8_t* sig64, const uint8_t* Q_xy, uint8_t* valid);
 __attribute__((visibility("hidden"))) ecg_status ecg_tu1_ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, const uint8_t* b, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
 __attribute__((visibility("hidden"))) ecg_status ecg_tu1_ecg_ecdsa_verify_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* z32, const uint8_t* sig64, const uint8_t* Q_xy, int low_s_only, uint8_t* valid);
 __attribute__((visibility("hidden"))) ecg_status ecg_tu2_ecg_mul_gen_add_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* a, const uint8_t* b, const uint8_t* P_xy, const uint8_t* P_inf, uint8_t* out_xy, uint8_t* out_inf);
@@ -1226,10 +1241,33 @@ ECG_API(ecg_ecdsa_verify_batch)(ecg_ctx* ctx, ecg_curve curve, size_t n, const u
   op.ostride = 1;
   return run_batch(ctx, op, n);
 }
+// SM2DSA: TU 1 holds sm2; the public entry (TU 0) forwards there like every other sm2 call
+ECG_API(ecg_sm2dsa_verify_batch)(ecg_ctx* ctx, size_t n, const uint8_t* e32, const uint8_t* sig64, const uint8_t* Q_xy, uint8_t* valid) {
+  if (!ctx) return ECG_EINVAL;
 #if ECG_TU == 0
-
-
-#endif  // ECG_TU == 0
+  return ecg_tu1_ecg_sm2dsa_verify_batch(ctx, n, e32, sig64, Q_xy, valid);
+#elif ECG_TU == 1
+  if (n == 0) return ECG_OK;
+  if (!e32 || !sig64 || !Q_xy || !valid) {
+    ctx->err = "ecg_sm2dsa_verify_batch: null pointer";
+    return ECG_EINVAL;
+  }
+  BatchOp op;
+  op.kind = BatchOp::ECDSA;
+  op.curve = ECG_SM2;
+  op.fop = 2;
+  op.kstride = 32;
+  op.pstride = op.xstride = 64;
+  op.k = e32;
+  op.p = sig64;
+  op.x = Q_xy;
+  op.out = valid;
+  op.ostride = 1;
+  return run_batch(ctx, op, n);
+#else
+  return ECG_EINVAL;
+#endif
+}
 
 ECG_API(ecg_batch_normalize)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* xyz, uint8_t* out_xy,
                                           uint8_t* out_inf) {

@@ -52,7 +52,7 @@ EXPORTS = [
     "ecg_kernel_launches", "ecg_version", "ecg_timing_enable", "ecg_timing_read",
     "ecg_schnorr_verify_batch", "ecg_ecdsa_verify_batch", "ecg_decompress_batch",
     "ecg_batch_normalize_hom", "ecg_mul_batch_x", "ecg_field_sqrt_batch",
-    "ecg_hash_to_curve_batch", "ecg_hash_to_scalar_batch",
+    "ecg_hash_to_curve_batch", "ecg_hash_to_scalar_batch", "ecg_sm2dsa_verify_batch",
 ]
 
 
@@ -122,6 +122,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.ecg_schnorr_verify_batch.restype = ctypes.c_int
     lib.ecg_ecdsa_verify_batch.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p, ctypes.c_int, u8p]
     lib.ecg_ecdsa_verify_batch.restype = ctypes.c_int
+    lib.ecg_sm2dsa_verify_batch.argtypes = [vp, sz, u8p, u8p, u8p, u8p]
+    lib.ecg_sm2dsa_verify_batch.restype = ctypes.c_int
     lib.ecg_decompress_batch.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p, u8p]
     lib.ecg_decompress_batch.restype = ctypes.c_int
     lib.ecg_batch_normalize_hom.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p]
@@ -381,6 +383,16 @@ class Engine:
         Q_xy = _u8(Q_xy, 2 * fb * n, "Q_xy")
         valid = np.zeros(n, np.uint8)
         self._check(self.lib.ecg_ecdsa_verify_batch(self._ctx, c, n, _ptr(z32), _ptr(sig64), _ptr(Q_xy), 1 if low_s_only else 0, _ptr(valid)))
+        return valid
+
+    def sm2dsa_verify_batch(self, e32, sig64, Q_xy):
+        """SM2DSA verify_prehash over a batch -> uint8 flags: e = SM3(Z_A || M) (32 bytes), signature r || s, public key x || y"""
+        n = np.asarray(e32).size // 32
+        e32 = _u8(e32, 32 * n, "e")
+        sig64 = _u8(sig64, 64 * n, "sig")
+        Q_xy = _u8(Q_xy, 64 * n, "Q_xy")
+        valid = np.zeros(n, np.uint8)
+        self._check(self.lib.ecg_sm2dsa_verify_batch(self._ctx, n, _ptr(e32), _ptr(sig64), _ptr(Q_xy), _ptr(valid)))
         return valid
 
     def decompress_batch(self, curve, sec1_33):

@@ -154,6 +154,16 @@ class Engine {
                                  xy_.data(), low_s_only ? 1 : 0, valid.data()));
     return std::vector<bool>(valid.begin(), valid.end());
   }
+  // sm2::dsa::VerifyingKey::verify_prehash over a batch (sm2/src/dsa/verifying.rs:138-175): e = SM3(Z_A || M) per signature
+  std::vector<bool> sm2dsa_verify_prehash(const std::vector<Bytes32>& e, const std::vector<Sig64>& sig, const std::vector<AffinePoint>& q) {
+    size_t n = check_sizes(e.size(), sig.size());
+    check_sizes(n, q.size());
+    pack(q);
+    std::vector<uint8_t> valid(n);
+    check(ecg_sm2dsa_verify_batch(ctx_, n, reinterpret_cast<const uint8_t*>(e.data()), reinterpret_cast<const uint8_t*>(sig.data()), xy_.data(),
+                                  valid.data()));
+    return std::vector<bool>(valid.begin(), valid.end());
+  }
   // AffinePoint::decompress over a batch (primeorder/src/affine.rs:179-198); ok[i] = false where x is not on the curve
   std::vector<AffinePoint> decompress(const std::vector<Sec1Compressed>& rec, std::vector<bool>* ok = nullptr) {
     size_t n = rec.size();

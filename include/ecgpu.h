@@ -176,12 +176,21 @@ ecg_status ecg_schnorr_verify_batch(ecg_ctx* ctx, size_t n, const uint8_t* pk_x,
 ecg_status ecg_ecdsa_verify_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* z32, const uint8_t* sig64,
                                   const uint8_t* Q_xy, int low_s_only, uint8_t* valid);
 
+/* SM2DSA verify_prehash over a batch (curve sm2 only, so no curve argument): e32 = the 32-byte digest e = SM3(Z_A || M)
+ * the caller computed (Z_A = the identity hash of sm2/src/distid.rs:21-47), sig64 = r || s, Q_xy = the public key.
+ * valid[i] = 1 iff r, s in [1, n-1], t = r + s mod n != 0, Q on the curve and (e + x(s*G + t*Q)) mod n == r.
+ * Replaces sm2::dsa::VerifyingKey::verify_prehash (sm2/src/dsa/verifying.rs:138-175).  The bign signature scheme
+ * (bignp256/src/ecdsa/verifying.rs:92-150) hashes the x coordinate with belt-hash between the group step and the
+ * verdict; its group step R = (s1 + H)*G + (s0 + 2^128)*Q is ecg_mul_gen_add_batch on ECG_BIGNP256. */
+ecg_status ecg_sm2dsa_verify_batch(ecg_ctx* ctx, size_t n, const uint8_t* e32, const uint8_t* sig64, const uint8_t* Q_xy,
+                                   uint8_t* valid);
+
 /* SEC1 compressed point decoding (rank 2 of SURVEY 8(f)): records of 1 + FB bytes (02|03 || x; all zero bytes = the
  * identity; 33 bytes for the 256-bit curves, 49 for the 384-bit ones, 25 for P-192, 67 for P-521).  valid[i] = 0 when the tag is unknown, x >= p, or x^3 + ax + b has no square root; out_xy / out_inf as
  * in ecg_mul_batch.  Replaces AffinePoint::decompress / from_sec1_point over a batch
  * (primeorder/src/affine.rs:179-198, :212-232; k256/src/arithmetic/affine.rs DecompressPoint; sqrt:
- * k256/src/arithmetic/field.rs:200-235, p256/src/arithmetic/field.rs:121-147, p384/src/arithmetic/field.rs sqrt,
- * p521/src/arithmetic/field.rs:386; the primefield-generated fields of sm2 / brainpool / p192 through the same
+ * k256/src/arithmetic/field.rs:200-235, p256/src/arithmetic/field.rs:121-147, p521/src/arithmetic/field.rs:386; the
+ * primefield-generated fields of p384 / sm2 / brainpool / p192, primefield/src/monty.rs:467, through the same
  * (p + 1) / 4 exponent).  ECG_NISTP224 (p = 1 mod 4: Tonelli-Shanks) and ECG_BIGNP256: ECG_EINVAL. */
 ecg_status ecg_decompress_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* sec1_33, uint8_t* out_xy,
                                 uint8_t* out_inf, uint8_t* valid);

@@ -352,6 +352,42 @@ def ecdsa_sign(c: Curve, d: int, z: int, k: int):
     return r, s
 
 
+# ---- SM2DSA (sm2/src/dsa/verifying.rs:138-175, signing.rs:213-260; Z_A: sm2/src/distid.rs:21-47) ------------------------
+def sm2_hash_z(distid: bytes, Q) -> bytes:
+    import hashlib
+    c = CURVES["sm2"]
+    h = hashlib.new("sm3")
+    h.update((8 * len(distid)).to_bytes(2, "big") + distid)
+    for v in (c.a % c.p, c.b, c.gx, c.gy, Q[0], Q[1]):
+        h.update(v.to_bytes(32, "big"))
+    return h.digest()
+
+
+def sm2_hash_msg(distid: bytes, Q, msg: bytes) -> bytes:
+    import hashlib
+    return hashlib.new("sm3", sm2_hash_z(distid, Q) + msg).digest()
+
+
+def sm2dsa_verify(e: int, r: int, s: int, Q) -> bool:
+    c = CURVES["sm2"]
+    n = c.n
+    if not (0 < r < n and 0 < s < n) or Q is None or not on_curve(c, Q):
+        return False
+    t = (r + s) % n
+    if t == 0:
+        return False
+    R = add(c, mul(c, s, G(c)), mul(c, t, Q))
+    return R is not None and (e + R[0]) % n == r
+
+
+def sm2dsa_sign(d: int, e: int, k: int):
+    c = CURVES["sm2"]
+    n = c.n
+    r = (e + mul(c, k, G(c))[0]) % n
+    s = pow(1 + d, -1, n) * (k - r * d) % n
+    return r, s
+
+
 # ---- hash to curve (RFC 9380), the suites the reference implements with SHA-256 -------------------------------------
 # hash2curve/src/group_digest.rs:88-143 (hash_from_bytes / encode_from_bytes / hash_to_scalar),
 # hash2curve/src/hash2field.rs + hash2field/expand_msg/xmd.rs (hash_to_field over expand_message_xmd),

@@ -78,6 +78,8 @@ unsafe extern "C" {
     /// `ecdsa::VerifyingKey::verify_prehash` over a batch (ecdsa.rs:93-121)
     pub fn ecg_ecdsa_verify_batch(ctx: *mut ecg_ctx, curve: i32, n: usize, z32: *const u8, sig64: *const u8, q_xy: *const u8,
                                   low_s_only: i32, valid: *mut u8) -> i32;
+    /// `sm2::dsa::VerifyingKey::verify_prehash` over a batch (sm2/src/dsa/verifying.rs:138-175)
+    pub fn ecg_sm2dsa_verify_batch(ctx: *mut ecg_ctx, n: usize, e32: *const u8, sig64: *const u8, q_xy: *const u8, valid: *mut u8) -> i32;
     /// `AffinePoint::decompress` over a batch (primeorder/src/affine.rs:179-198)
     pub fn ecg_decompress_batch(ctx: *mut ecg_ctx, curve: i32, n: usize, sec1_33: *const u8, out_xy: *mut u8,
                                 out_inf: *mut u8, valid: *mut u8) -> i32;
@@ -288,6 +290,16 @@ impl GpuEngine {
             ecg_ecdsa_verify_batch(self.ctx, self.curve, n, z.as_ptr().cast(), sig.as_ptr().cast(), q_xy.as_ptr().cast(), low_s_only as i32,
                                    valid.as_mut_ptr())
         };
+        self.check(rc).map(|_| valid.into_iter().map(|v| v != 0).collect())
+    }
+
+    /// SM2DSA `verify_prehash` over a batch: `e` = SM3(Z_A || M) per signature (`VerifyingKey::hash_msg`).
+    pub fn sm2dsa_verify_batch(&mut self, e: &[Bytes32], sig: &[[u8; 64]], q_xy: &[PointXY]) -> Result<Vec<bool>, GpuError> {
+        let n = e.len();
+        assert!(sig.len() == n && q_xy.len() == n);
+        let mut valid = vec![0u8; n];
+        // SAFETY: as above.
+        let rc = unsafe { ecg_sm2dsa_verify_batch(self.ctx, n, e.as_ptr().cast(), sig.as_ptr().cast(), q_xy.as_ptr().cast(), valid.as_mut_ptr()) };
         self.check(rc).map(|_| valid.into_iter().map(|v| v != 0).collect())
     }
 

@@ -922,3 +922,15 @@ extern "C" int simk_field_sqrt_generic(int curve, size_t n, const uint8_t* a, ui
   SIM_FOR_GENERIC(curve, sim_launch(n, 128, [&] { field_sqrt_generic_kernel<CV, SqrtExp<CV>::T>(n, a, out, is_square, status, 0); }));
   return 0;
 }
+
+// ecg_sm2dsa_verify_batch: SM2DSA front end -> s*G + t*Q -> verdict
+extern "C" int simk_sm2dsa_verify(size_t n, const uint8_t* e, const uint8_t* sig, const uint8_t* q, const uint32_t* table, uint8_t* valid) {
+  typedef CurveSm2 C;
+  constexpr size_t FB = C::F::FB;
+  std::vector<uint8_t> vp(2 * FB * n), va(FB * n), vb(FB * n), vok(n), vxy(2 * FB * n), vinf(n);
+  uint32_t status[2] = {0, 0xFFFFFFFFu};
+  sim_launch(n, 128, [&] { sm2dsa_prep_kernel<C>(sig, q, n, vp.data(), va.data(), vb.data(), vok.data()); });
+  simk_mga_generic<C>(n, va.data(), vb.data(), vp.data(), nullptr, table, vxy.data(), vinf.data(), status);
+  sim_launch(n, 256, [&] { sm2dsa_check_kernel<C>(e, sig, vxy.data(), vinf.data(), vok.data(), n, valid); });
+  return (int)status[0];
+}
