@@ -763,7 +763,67 @@ ECG_DEV void sqrt_candidate_generic(typename F::FeT& r, const typename F::FeT& a
   }
   r = acc;
 }
-// records: tag (02 / 03; 00 with an all-zero x = the identity) || x, 1 + FB bytes, big-endian (SEC1 2.3.4)
+template <int V>
+struct ILog2 {
+  static constexpr int value = 1 + ILog2<(V >> 1)>::value;
+};
+template <>
+struct ILog2<1> {
+  static constexpr int value = 0;
+};
+// Tonelli-Shanks for a field with p = 1 (mod 4), p - 1 = 2^S (2^K - 1) (P-224: S = 96, K = 128).  Either root may come out:
+// the caller checks r^2 == a and (decompression) picks the root by parity, so only "a root when one exists" matters.
+// Variable time in a — these are public encodings.
+template <class F, class E>
+ECG_DEV void sqrt_candidate_ts(typename F::FeT& r, const typename F::FeT& a) {
+  typedef typename F::FeT Fe;
+  constexpr int NL = F::NL;
+  Fe one, w, t, c, b;
+  F::set_one(one);
+  auto is_one = [&](const Fe& v) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int i = 0; i < NL; i++) d |= v.v[i] ^ one.v[i];
+    return d == 0;
+  };
+  // w = a^(2^(K-1) - 1): x_{2m} = x_m^(2^m) * x_m, x_{2m+1} = x_{2m}^2 * a, over the bits of K - 1 from the top
+  w = a;
+  int m = 1;
+#pragma unroll 1
+  for (int bit = ILog2<E::TS_QBITS - 1>::value - 1; bit >= 0; bit--) {
+    F::sqr_n(t, w, m);
+    F::mul(w, t, w);
+    m *= 2;
+    if (((E::TS_QBITS - 1) >> bit) & 1) {
+      F::sqr(w, w);
+      F::mul(w, w, a);
+      m++;
+    }
+  }
+  F::mul(r, a, w);  // a^((Q+1)/2)
+  F::mul(t, r, w);  // a^Q
+#pragma unroll
+  for (int i = 0; i < NL; i++) c.v[i] = E::TS_ZQ(i);
+  int M = E::TS_S;
+#pragma unroll 1
+  while (!is_one(t)) {
+    if (F::is_zero(t)) return;  // a = 0: r = 0 already
+    int i = 0;
+    b = t;
+#pragma unroll 1
+    while (i < M && !is_one(b)) {
+      F::sqr(b, b);
+      i++;
+    }
+    if (i == M) return;  // a is not a square; the caller's r^2 == a check fails
+    F::sqr_n(b, c, M - i - 1);
+    F::mul(r, r, b);
+    F::sqr(c, b);
+    F::mul(t, t, c);
+    M = i;
+  }
+}
+// records: tag (02 / 03; 00 with an all-zero x = the identity) || x, 1 + FB bytes, x in the curve's FieldBytes order (SEC1 2.3.4)
 template <class C, class E>
 ECG_KERNEL(128)
     decompress_generic_kernel(const uint8_t* __restrict__ sec1, size_t n, uint8_t* __restrict__ out_xy, uint8_t* __restrict__ out_inf,
@@ -776,7 +836,13 @@ ECG_KERNEL(128)
   const uint8_t* rec = sec1 + (size_t)(FB + 1) * idx;
   const uint8_t tag = rec[0];
   Fe xc;
-  load_be_bytes<NL, FB>(xc.v, rec + 1);  // the x bytes are not word-aligned
+  if constexpr (F::LE) {  // bign-curve256v1: FieldBytes are little-endian (from_repr reads them so inside decompress, too)
+#pragma unroll
+    for (int i = 0; i < NL; i++)
+      xc.v[i] = (uint32_t)rec[1 + 4 * i] | ((uint32_t)rec[2 + 4 * i] << 8) | ((uint32_t)rec[3 + 4 * i] << 16) | ((uint32_t)rec[4 + 4 * i] << 24);
+  } else {
+    load_be_bytes<NL, FB>(xc.v, rec + 1);  // the x bytes are not word-aligned
+  }
   uint32_t any = 0;
 #pragma unroll
   for (int i = 0; i < NL; i++) any |= xc.v[i];
@@ -800,7 +866,10 @@ ECG_KERNEL(128)
     }
     C::b_internal(b);
     F::add(rhs, rhs, b);
-    sqrt_candidate_generic<F, E>(y, rhs);
+    if constexpr (E::HAS_SQRT_EXP)
+      sqrt_candidate_generic<F, E>(y, rhs);
+    else
+      sqrt_candidate_ts<F, E>(y, rhs);
     F::sqr(chk, y);
     F::sub(chk, chk, rhs);
     ok = F::is_zero(chk);

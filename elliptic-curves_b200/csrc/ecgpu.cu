@@ -1180,9 +1180,8 @@ ECG_API(ecg_decompress_batch)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uin
   if (!ctx) return ECG_EINVAL;
   ECG_FORWARD(ecg_decompress_batch, ctx, curve, n, sec1_33, out_xy, out_inf, valid);
   if (n == 0) return ECG_OK;
-  // p = 1 (mod 4) for P-224 (no single-exponentiation square root); bign-curve256v1 has no SEC1 form (little-endian records)
-  if (!sec1_33 || !out_xy || !out_inf || !valid || !curve_ok(curve) || curve == ECG_NISTP224 || curve == ECG_BIGNP256) {
-    ctx->err = "ecg_decompress_batch: null pointer or a curve without SEC1 decompression here";
+  if (!sec1_33 || !out_xy || !out_inf || !valid || !curve_ok(curve)) {
+    ctx->err = "ecg_decompress_batch: null pointer or unknown curve";
     return ECG_EINVAL;
   }
   BatchOp op;

@@ -52,9 +52,10 @@ typedef enum {
  * Every curve is served by the hot-path entries (mul_batch[_x], mul_gen_batch, lincomb[_partial], point_sum,
  * batch_normalize[_hom], field_op_batch) and by mul_gen_add_batch; ecdsa_verify_batch serves every curve the reference
  * defines ECDSA for (all but sm2 and bign-curve256v1, whose signature schemes differ); hash to curve the four curves with
- * an RFC 9380 suite in the reference; SEC1 decompression and the field square root every curve with p = 3 (mod 4), i.e. one
- * exponentiation by (p + 1) / 4 (all but P-224; decompression also refuses bign-curve256v1, whose SEC1 form is not
- * pinned by a reference vector); BIP340 is secp256k1's alone.  What a curve does not serve answers ECG_EINVAL. */
+ * an RFC 9380 suite in the reference; SEC1 decompression every curve (one exponentiation by (p + 1) / 4 where p = 3 mod 4,
+ * Tonelli-Shanks for P-224); the field square root every curve but P-224 (where the reference's root is the one its
+ * external bignum crate's Tonelli-Shanks happens to return); BIP340 is secp256k1's alone and SM2DSA sm2's.  What a curve
+ * does not serve answers ECG_EINVAL. */
 typedef enum {
   ECG_SECP256K1 = 0,
   ECG_NISTP256 = 1,
@@ -191,7 +192,9 @@ ecg_status ecg_sm2dsa_verify_batch(ecg_ctx* ctx, size_t n, const uint8_t* e32, c
  * (primeorder/src/affine.rs:179-198, :212-232; k256/src/arithmetic/affine.rs DecompressPoint; sqrt:
  * k256/src/arithmetic/field.rs:200-235, p256/src/arithmetic/field.rs:121-147, p521/src/arithmetic/field.rs:386; the
  * primefield-generated fields of p384 / sm2 / brainpool / p192, primefield/src/monty.rs:467, through the same
- * (p + 1) / 4 exponent).  ECG_NISTP224 (p = 1 mod 4: Tonelli-Shanks) and ECG_BIGNP256: ECG_EINVAL. */
+ * (p + 1) / 4 exponent; P-224, p = 1 mod 4, through Tonelli-Shanks — decompress selects the root by the tag's parity, so
+ * the result does not depend on which root the square root finds).  The x bytes are the curve's FieldBytes, i.e.
+ * little-endian for bign-curve256v1, as from_repr reads them inside decompress. */
 ecg_status ecg_decompress_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* sec1_33, uint8_t* out_xy,
                                 uint8_t* out_inf, uint8_t* valid);
 

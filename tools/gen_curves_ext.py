@@ -138,6 +138,16 @@ def main():
             else:
                 out.append("  static constexpr bool HAS_SQRT_EXP = false;  // p = 1 (mod 4): no single-exponentiation square root\n")
                 out.append(accessor("PP14", 0, nl))
+                # Tonelli-Shanks constants: p - 1 = 2^S * Q, Q odd; z = the smallest quadratic non-residue; ZQ = z^Q (Montgomery form)
+                S_, Q_ = 0, p - 1
+                while Q_ % 2 == 0:
+                    S_, Q_ = S_ + 1, Q_ // 2
+                z = 2
+                while pow(z, (p - 1) // 2, p) != p - 1:
+                    z += 1
+                assert Q_ == (1 << Q_.bit_length()) - 1, "the addition chain in sqrt_candidate_ts assumes Q = 2^k - 1"
+                out.append("  static constexpr int TS_S = %d;      // p - 1 = 2^%d * (2^%d - 1)\n  static constexpr int TS_QBITS = %d;\n" % (S_, S_, Q_.bit_length(), Q_.bit_length()))
+                out.append(accessor("TS_ZQ", pow(z, Q_, p) * R % p, nl).replace("{ return", "{  // %d^Q * R mod p, %d the smallest non-residue\n    return" % (z, z)))
             out.append("};\n")
             out.append("ECG_XCONSTANT uint32_t %s_P[%d] = %s;\n" % (field.upper(), nl, carr(p, nl)))
         if generic_a:
