@@ -337,9 +337,20 @@ class Engine:
     def hash_to_curve(self, curve, msgs, dst: bytes, nonuniform: bool = False):
         """GroupDigest::hash_from_bytes / encode_from_bytes over a batch of messages (hash2curve/src/group_digest.rs:88-118)
         -> (xy n x 64, inf)"""
-        c = CURVE_IDS[curve]
-        n = len(msgs)
         data, offs = self._pack_messages(msgs)
+        return self.hash_to_curve_packed(curve, data, offs, dst, nonuniform)
+
+    def hash_to_curve_packed(self, curve, data, offsets, dst: bytes, nonuniform: bool = False):
+        """the same over messages already laid out as the C ABI takes them: `data` = the messages back to back (uint8),
+        `offsets` = n + 1 uint64 byte offsets (message i = data[offsets[i]:offsets[i + 1]])"""
+        c = CURVE_IDS[curve]
+        offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = offs.size - 1
+        if n < 0 or (n >= 0 and offs.size and int(offs[-1]) > np.asarray(data).size):
+            raise ValueError("offsets: n + 1 ascending byte offsets into data")
+        data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+        if data.size == 0:
+            data = np.zeros(1, np.uint8)
         d = np.frombuffer(bytes(dst), np.uint8).copy() if len(dst) else np.zeros(1, np.uint8)
         fb = FBYTES[c]
         out_xy = np.empty(2 * fb * n, np.uint8)
