@@ -480,6 +480,111 @@ ECG_KERNEL(256)
   valid[idx] = (ok[idx] && !rinf[idx] && same) ? 1 : 0;
 }
 
+// Public-key recovery (ecdsa_core::VerifyingKey::recover_from_prehash, the Ethereum `ecrecover` shape; k256/src/ecdsa.rs:45-88,
+// vectors :182-262): R = decompress(r [+ n if recid bit 1], y odd = recid bit 0); Q = r^-1 (s R - z G) = u1*G + u2*R with
+// u1 = -z r^-1, u2 = s r^-1.  One inversion mod n per thread slice (Montgomery's trick over the r_i); scr: 8 * n words.
+// recid: one byte per signature, RecoveryId::to_byte (0..3).
+template <class C>
+ECG_KERNEL(128)
+    ecdsa_recover_prep_kernel(const uint8_t* __restrict__ zb, const uint8_t* __restrict__ sig, const uint8_t* __restrict__ recid, size_t n,
+                              int low_s_only, uint32_t* __restrict__ scr, uint8_t* __restrict__ pxy, uint8_t* __restrict__ a_out,
+                              uint8_t* __restrict__ b_out, uint8_t* __restrict__ ok_out) {
+  typedef typename C::F F;
+  typedef FnMont<C> N;
+  size_t T = (size_t)gridDim.x * blockDim.x;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  uint32_t acc[8], rm[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = C::N_ONE()[i];
+  size_t last = t;
+  for (size_t idx = t; idx < n; idx += T) {
+    uint32_t r[8], sv[8], x[8];
+    load_be32(r, sig + 64 * idx);
+    load_be32(sv, sig + 64 * idx + 32);
+    const uint32_t id = recid[idx];
+    bool ok = id < 4 && lt8(r, C::N()) && !N::is_zero(r) && lt8(sv, C::N()) && !N::is_zero(sv);
+    if (ok && low_s_only) {  // the closing verify_prehash of a NORMALIZE_S curve refuses s > n/2
+      uint32_t twice[8];
+      uint32_t c = add8(twice, sv, sv);
+      ok = !c && lt8(twice, C::N());
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = r[i];
+    if (id & 2u) {  // is_x_reduced: the x coordinate of R was r + n (checked_add: no wrap past 2^256; decompress refuses x >= p)
+      uint32_t c = add8(x, r, C::N());
+      ok = ok && !c;
+    }
+    Aff R;
+    ok = ok && sec1_decompress<C>(R, x, id & 1u);
+    Fe cx, cy;
+    if (!ok) C::generator(R);
+    F::to_canonical(cx, R.x);
+    F::to_canonical(cy, R.y);
+    store_be32(pxy + 64 * idx, cx.v);
+    store_be32(pxy + 64 * idx + 32, cy.v);
+    ok_out[idx] = ok ? 1 : 0;
+    if (!ok) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) r[i] = (i == 0);
+    }
+    N::to_mont(rm, r);
+    soa_store<8>(scr, n, idx, acc, 0);
+    N::mul(acc, acc, rm);
+    last = idx;
+  }
+  uint32_t inv[8];
+  N::inv(inv, acc);
+  for (size_t idx = last;; idx -= T) {
+    uint32_t r[8], sv[8], z[8], pre[8], w[8], u1[8], u2[8];
+    bool ok = ok_out[idx] != 0;
+    load_be32(r, sig + 64 * idx);
+    load_be32(sv, sig + 64 * idx + 32);
+    load_be32(z, zb + 32 * idx);
+    if (!ok) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) r[i] = (i == 0);
+    }
+    N::to_mont(rm, r);
+    soa_load<8>(pre, scr, n, idx, 0);
+    N::mul(w, inv, pre);  // w = r^-1 (Montgomery form)
+    N::mul(inv, inv, rm);
+    N::cond_sub_n(z, N::ge_n(z));
+    N::mul(u1, z, w);  // z r^-1, then negated mod n
+    N::mul(u2, sv, w);
+    if (!N::is_zero(u1)) {
+      uint32_t neg[8];
+      sub8(neg, C::N(), u1);
+#pragma unroll
+      for (int i = 0; i < 8; i++) u1[i] = neg[i];
+    }
+    if (!ok) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        u1[i] = (i == 0);
+        u2[i] = (i == 0);
+      }
+    }
+    store_scalar_be(a_out + 32 * idx, u1);
+    store_scalar_be(b_out + 32 * idx, u2);
+    if (idx < T) break;
+  }
+}
+// after the normalisation wrote x || y and the identity flag: valid = front end ok and Q != O (VerifyingKey::from_affine);
+// the flag array becomes the verdict, refused records come back as 64 zero bytes
+template <int ECG_ONCE = 0>  // a template only so that several translation units may define it
+ECG_KERNEL(256)
+    ecdsa_recover_finish_kernel(uint8_t* __restrict__ out_xy, uint8_t* __restrict__ inf_to_valid, const uint8_t* __restrict__ ok, size_t n) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  bool v = ok[idx] && !inf_to_valid[idx];
+  if (!v) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) reinterpret_cast<uint32_t*>(out_xy + 64 * idx)[i] = 0;
+  }
+  inf_to_valid[idx] = v ? 1 : 0;
+}
+
 // ---- the same two entries for every other curve with ECDSA in the reference (p192, p224, p384, p521, brainpoolP256r1/t1,
 // brainpoolP384r1/t1: */src/ecdsa.rs) — generic twins over the field policy's limb count, arithmetic mod n through
 // ScalarField<C>::T (the Montgomery policy of ecg_fe_mont.cuh instantiated over the group order) ----------------------

@@ -734,7 +734,7 @@ static ecg_status ensure_fb_table(ecg_ctx* ctx, DevState& d, ecg_curve curve) {
 // What one chunk does is the only thing that differs between ecg_mul_batch, ecg_mul_gen_batch, ecg_mul_gen_add_batch,
 // ecg_batch_normalize and ecg_field_op_batch:
 struct BatchOp {
-  enum Kind { MUL, MULGEN, MULGENADD, NORMALIZE, FIELD, SCHNORR, ECDSA, DECOMPRESS, FSQRT } kind;
+  enum Kind { MUL, MULGEN, MULGENADD, NORMALIZE, FIELD, SCHNORR, ECDSA, DECOMPRESS, FSQRT, RECOVER } kind;
   ecg_curve curve;
   int fop = 0;  // field op, the ECDSA low-S flag, or NORMALIZE's "homogeneous input" flag
   bool x_only = false;  // MUL: write x coordinates only (ostride 32)
@@ -852,8 +852,8 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
     LAUNCHED(ctx);
     return copy_back(ctx, L, off, cnt, op.out, op.ostride, op.oinf, dp);
   }
-  if (op.kind == BatchOp::SCHNORR || op.kind == BatchOp::ECDSA) {
-    // front end -> (a, b, P) -> a*G + b*P -> affine -> verdict, all on the device
+  if (op.kind == BatchOp::SCHNORR || op.kind == BatchOp::ECDSA || op.kind == BatchOp::RECOVER) {
+    // front end -> (a, b, P) -> a*G + b*P -> affine -> verdict (or, for key recovery, the point itself), all on the device
     ST_TRY(ensure(ctx, L, B_V1, cnt * 64));
     ST_TRY(ensure(ctx, L, B_V2, cnt * 32));
     ST_TRY(ensure(ctx, L, B_V3, cnt * 32));
@@ -868,6 +868,13 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
     const bool k1c = op.curve == ECG_SECP256K1;
     if (op.kind == BatchOp::SCHNORR) {
       schnorr_prep_kernel<<<grid_for(cnt, 128), 128, 0, L.s()>>>(dp.k, dp.a, dp.p, cnt, vp, va, vb, vok);
+    } else if (op.kind == BatchOp::RECOVER) {
+      ST_TRY(ensure(ctx, L, B_SCR, cnt * 32));
+      size_t want_threads = std::max<size_t>((cnt + 31) / 32, std::min<size_t>(cnt, (size_t)d.sm_count * 128));
+      if (k1c)
+        ecdsa_recover_prep_kernel<CurveK256><<<grid_for(want_threads, 128), 128, 0, L.s()>>>(dp.k, dp.p, dp.inf, cnt, op.fop, (uint32_t*)L.buf[B_SCR], vp, va, vb, vok);
+      else
+        ecdsa_recover_prep_kernel<CurveP256><<<grid_for(want_threads, 128), 128, 0, L.s()>>>(dp.k, dp.p, dp.inf, cnt, op.fop, (uint32_t*)L.buf[B_SCR], vp, va, vb, vok);
     } else {
       ST_TRY(ensure(ctx, L, B_SCR, cnt * 32));
       size_t want_threads = std::max<size_t>((cnt + 31) / 32, std::min<size_t>(cnt, (size_t)d.sm_count * 128));
@@ -886,6 +893,12 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
           va, vb, vp, nullptr, cnt, d.fb_table[op.curve], vj, (uint32_t*)L.buf[B_TAB], L.status, off);
     LAUNCHED(ctx);
     DOM_END(ctx, L);
+    if (op.kind == BatchOp::RECOVER) {  // the recovered key goes out as x || y; the identity-flag array becomes the verdict
+      ST_TRY(launch_norm(ctx, d, L, op.curve, cnt, vj, dp.out, dp.oinf));
+      ecdsa_recover_finish_kernel<><<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.out, dp.oinf, vok, cnt);
+      LAUNCHED(ctx);
+      return copy_back(ctx, L, off, cnt, op.out, op.ostride, op.oinf, dp);
+    }
     ST_TRY(launch_norm(ctx, d, L, op.curve, cnt, vj, vxy, vinf));
     if (op.kind == BatchOp::SCHNORR)
       schnorr_check_kernel<<<grid_for(cnt, 256), 256, 0, L.s()>>>(dp.p, vxy, vinf, vok, cnt, dp.out);
@@ -995,7 +1008,7 @@ static std::vector<Shard> chunk_schedule(size_t cnt, size_t wave) {
 static ecg_status run_batch_inner(ecg_ctx* ctx, const BatchOp& op, size_t n) {
   std::vector<Shard> shards = make_shards(n, ctx->devs.size());
   bool need_table = (op.kind == BatchOp::MULGEN && !(ctx->flags & ECG_FLAG_CONSTTIME)) || op.kind == BatchOp::MULGENADD ||
-                    op.kind == BatchOp::SCHNORR || op.kind == BatchOp::ECDSA;
+                    op.kind == BatchOp::SCHNORR || op.kind == BatchOp::ECDSA || op.kind == BatchOp::RECOVER;
   for (size_t i = 0; i < ctx->devs.size(); i++) {
     if (shards[i].cnt == 0) continue;
     DevState& d = ctx->devs[i];
@@ -1240,6 +1253,31 @@ ECG_API(ecg_ecdsa_verify_batch)(ecg_ctx* ctx, ecg_curve curve, size_t n, const u
   op.ostride = 1;
   return run_batch(ctx, op, n);
 }
+#if ECG_TU == 0
+ECG_API(ecg_ecdsa_recover_batch)(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* z32, const uint8_t* sig64, const uint8_t* recid,
+                                 int low_s_only, uint8_t* out_xy, uint8_t* valid) {
+  if (!ctx) return ECG_EINVAL;
+  if (n == 0) return ECG_OK;
+  if (!z32 || !sig64 || !recid || !out_xy || !valid || !curve_256(curve)) {
+    ctx->err = "ecg_ecdsa_recover_batch: null pointer, or a curve other than secp256k1 / P-256";
+    return ECG_EINVAL;
+  }
+  BatchOp op;
+  op.kind = BatchOp::RECOVER;
+  op.curve = curve;
+  op.fop = low_s_only ? 1 : 0;
+  op.kstride = 32;
+  op.pstride = 64;
+  op.k = z32;
+  op.p = sig64;
+  op.inf = recid;
+  op.out = out_xy;
+  op.ostride = 64;
+  op.oinf = valid;
+  return run_batch(ctx, op, n);
+}
+#endif
+
 // SM2DSA: TU 1 holds sm2; the public entry (TU 0) forwards there like every other sm2 call
 ECG_API(ecg_sm2dsa_verify_batch)(ecg_ctx* ctx, size_t n, const uint8_t* e32, const uint8_t* sig64, const uint8_t* Q_xy, uint8_t* valid) {
   if (!ctx) return ECG_EINVAL;

@@ -52,7 +52,7 @@ EXPORTS = [
     "ecg_kernel_launches", "ecg_version", "ecg_timing_enable", "ecg_timing_read",
     "ecg_schnorr_verify_batch", "ecg_ecdsa_verify_batch", "ecg_decompress_batch",
     "ecg_batch_normalize_hom", "ecg_mul_batch_x", "ecg_field_sqrt_batch",
-    "ecg_hash_to_curve_batch", "ecg_hash_to_scalar_batch", "ecg_sm2dsa_verify_batch",
+    "ecg_hash_to_curve_batch", "ecg_hash_to_scalar_batch", "ecg_sm2dsa_verify_batch", "ecg_ecdsa_recover_batch",
 ]
 
 
@@ -123,6 +123,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.ecg_ecdsa_verify_batch.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p, ctypes.c_int, u8p]
     lib.ecg_ecdsa_verify_batch.restype = ctypes.c_int
     lib.ecg_sm2dsa_verify_batch.argtypes = [vp, sz, u8p, u8p, u8p, u8p]
+    lib.ecg_ecdsa_recover_batch.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p, ctypes.c_int, u8p, u8p]
+    lib.ecg_ecdsa_recover_batch.restype = ctypes.c_int
     lib.ecg_sm2dsa_verify_batch.restype = ctypes.c_int
     lib.ecg_decompress_batch.argtypes = [vp, ctypes.c_int, sz, u8p, u8p, u8p, u8p]
     lib.ecg_decompress_batch.restype = ctypes.c_int
@@ -395,6 +397,20 @@ class Engine:
         valid = np.zeros(n, np.uint8)
         self._check(self.lib.ecg_ecdsa_verify_batch(self._ctx, c, n, _ptr(z32), _ptr(sig64), _ptr(Q_xy), 1 if low_s_only else 0, _ptr(valid)))
         return valid
+
+    def ecdsa_recover_batch(self, curve, z32, sig64, recid, low_s_only=False):
+        """VerifyingKey::recover_from_prehash over a batch (secp256k1 / P-256) -> (Q_xy n x 64, valid): prehash, r || s, one
+        RecoveryId byte (bit 0: y of R odd, bit 1: x of R = r + n) per signature"""
+        c = CURVE_IDS[curve]
+        n = np.asarray(recid).size
+        z32 = _u8(z32, 32 * n, "z")
+        sig64 = _u8(sig64, 64 * n, "sig")
+        recid = _u8(recid, n, "recid")
+        out_xy = np.empty(64 * n, np.uint8)
+        valid = np.zeros(n, np.uint8)
+        self._check(self.lib.ecg_ecdsa_recover_batch(self._ctx, c, n, _ptr(z32), _ptr(sig64), _ptr(recid), 1 if low_s_only else 0,
+                                                     _ptr(out_xy), _ptr(valid)))
+        return out_xy.reshape(n, 64), valid
 
     def sm2dsa_verify_batch(self, e32, sig64, Q_xy):
         """SM2DSA verify_prehash over a batch -> uint8 flags: e = SM3(Z_A || M) (32 bytes), signature r || s, public key x || y"""

@@ -154,6 +154,18 @@ class Engine {
                                  xy_.data(), low_s_only ? 1 : 0, valid.data()));
     return std::vector<bool>(valid.begin(), valid.end());
   }
+  // ecdsa::VerifyingKey::recover_from_prehash over a batch (k256/src/ecdsa.rs:45-88): recid = RecoveryId::to_byte per signature;
+  // ok[i] = false (and an all-zero point) where recovery fails
+  std::vector<AffinePoint> ecdsa_recover_prehash(const std::vector<Bytes32>& z, const std::vector<Sig64>& sig, const std::vector<uint8_t>& recid,
+                                                 bool low_s_only, std::vector<bool>* ok = nullptr) {
+    size_t n = check_sizes(z.size(), sig.size());
+    check_sizes(n, recid.size());
+    std::vector<uint8_t> out(64 * n), valid(n), noinf(n, 0);
+    check(ecg_ecdsa_recover_batch(ctx_, curve_, n, reinterpret_cast<const uint8_t*>(z.data()), reinterpret_cast<const uint8_t*>(sig.data()),
+                                  recid.data(), low_s_only ? 1 : 0, out.data(), valid.data()));
+    if (ok) ok->assign(valid.begin(), valid.end());
+    return unpack(out, noinf);
+  }
   // sm2::dsa::VerifyingKey::verify_prehash over a batch (sm2/src/dsa/verifying.rs:138-175): e = SM3(Z_A || M) per signature
   std::vector<bool> sm2dsa_verify_prehash(const std::vector<Bytes32>& e, const std::vector<Sig64>& sig, const std::vector<AffinePoint>& q) {
     size_t n = check_sizes(e.size(), sig.size());

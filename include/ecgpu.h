@@ -177,6 +177,16 @@ ecg_status ecg_schnorr_verify_batch(ecg_ctx* ctx, size_t n, const uint8_t* pk_x,
 ecg_status ecg_ecdsa_verify_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* z32, const uint8_t* sig64,
                                   const uint8_t* Q_xy, int low_s_only, uint8_t* valid);
 
+/* Public-key recovery over a batch (secp256k1 — the Ethereum ecrecover shape — and P-256): z32 = the prehash, sig64 = r || s,
+ * recid = one byte per signature (RecoveryId::to_byte: bit 0 = y of R is odd, bit 1 = x of R was reduced, i.e. x = r + n).
+ * R = decompress(x, y parity); Q = u1*G + u2*R with u1 = -z r^-1, u2 = s r^-1 (mod n).  valid[i] = 1 and out_xy = Q.x || Q.y
+ * when 0 < r, s < n, recid < 4, x < p has a point and Q != O (then the closing verify_prehash of the reference holds by
+ * construction; low_s_only = EcdsaCurve::NORMALIZE_S refuses s > n/2 as that verification does on secp256k1); otherwise
+ * valid[i] = 0 and 64 zero bytes.  Replaces ecdsa_core::VerifyingKey::recover_from_prehash / recover_from_digest as k256 and
+ * p256 re-export it (k256/src/ecdsa.rs:45-88; vectors :182-262). */
+ecg_status ecg_ecdsa_recover_batch(ecg_ctx* ctx, ecg_curve curve, size_t n, const uint8_t* z32, const uint8_t* sig64,
+                                   const uint8_t* recid, int low_s_only, uint8_t* out_xy, uint8_t* valid);
+
 /* SM2DSA verify_prehash over a batch (curve sm2 only, so no curve argument): e32 = the 32-byte digest e = SM3(Z_A || M)
  * the caller computed (Z_A = the identity hash of sm2/src/distid.rs:21-47), sig64 = r || s, Q_xy = the public key.
  * valid[i] = 1 iff r, s in [1, n-1], t = r + s mod n != 0, Q on the curve and (e + x(s*G + t*Q)) mod n == r.

@@ -352,6 +352,30 @@ def ecdsa_sign(c: Curve, d: int, z: int, k: int):
     return r, s
 
 
+def ecdsa_recover(c: Curve, z: int, r: int, s: int, recid: int, low_s_only: bool = False):
+    """ecdsa_core::VerifyingKey::recover_from_prehash (k256/src/ecdsa.rs:45-88 documents it; vectors :182-262): the public key,
+    or None.  recid bit 0 = y of R odd, bit 1 = x of R was r + n."""
+    n, p = c.n, c.p
+    if not (0 < r < n and 0 < s < n) or not 0 <= recid < 4:
+        return None
+    if low_s_only and s > n // 2:
+        return None
+    x = r + (n if recid & 2 else 0)
+    if x >= 1 << (8 * fbytes(c)) or x >= p:
+        return None
+    rhs = (x * x * x + c.a * x + c.b) % p
+    y = pow(rhs, (p + 1) // 4, p)
+    if y * y % p != rhs:
+        return None
+    if (y & 1) != (recid & 1):
+        y = p - y
+    ri = pow(r, -1, n)
+    Q = add(c, mul(c, (-(z % n) * ri) % n, G(c)), mul(c, s * ri % n, (x, y)))
+    if Q is None or not ecdsa_verify(c, z, r, s, Q):
+        return None
+    return Q
+
+
 # ---- SM2DSA (sm2/src/dsa/verifying.rs:138-175, signing.rs:213-260; Z_A: sm2/src/distid.rs:21-47) ------------------------
 def sm2_hash_z(distid: bytes, Q) -> bytes:
     import hashlib

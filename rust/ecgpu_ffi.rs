@@ -78,6 +78,9 @@ unsafe extern "C" {
     /// `ecdsa::VerifyingKey::verify_prehash` over a batch (ecdsa.rs:93-121)
     pub fn ecg_ecdsa_verify_batch(ctx: *mut ecg_ctx, curve: i32, n: usize, z32: *const u8, sig64: *const u8, q_xy: *const u8,
                                   low_s_only: i32, valid: *mut u8) -> i32;
+    /// `ecdsa::VerifyingKey::recover_from_prehash` over a batch (k256/src/ecdsa.rs:45-88), `recid` = `RecoveryId::to_byte`
+    pub fn ecg_ecdsa_recover_batch(ctx: *mut ecg_ctx, curve: i32, n: usize, z32: *const u8, sig64: *const u8, recid: *const u8,
+                                   low_s_only: i32, out_xy: *mut u8, valid: *mut u8) -> i32;
     /// `sm2::dsa::VerifyingKey::verify_prehash` over a batch (sm2/src/dsa/verifying.rs:138-175)
     pub fn ecg_sm2dsa_verify_batch(ctx: *mut ecg_ctx, n: usize, e32: *const u8, sig64: *const u8, q_xy: *const u8, valid: *mut u8) -> i32;
     /// `AffinePoint::decompress` over a batch (primeorder/src/affine.rs:179-198)
@@ -291,6 +294,20 @@ impl GpuEngine {
                                    valid.as_mut_ptr())
         };
         self.check(rc).map(|_| valid.into_iter().map(|v| v != 0).collect())
+    }
+
+    /// `VerifyingKey::recover_from_prehash` over a batch: `None` where the reference returns `Err`.
+    pub fn ecdsa_recover_batch(&mut self, z: &[Bytes32], sig: &[[u8; 64]], recid: &[u8], low_s_only: bool) -> Result<Vec<Option<PointXY>>, GpuError> {
+        let n = z.len();
+        assert!(sig.len() == n && recid.len() == n);
+        let mut out = vec![[0u8; 64]; n];
+        let mut valid = vec![0u8; n];
+        // SAFETY: as above.
+        let rc = unsafe {
+            ecg_ecdsa_recover_batch(self.ctx, self.curve, n, z.as_ptr().cast(), sig.as_ptr().cast(), recid.as_ptr(), low_s_only as i32,
+                                    out.as_mut_ptr().cast(), valid.as_mut_ptr())
+        };
+        self.check(rc).map(|_| out.into_iter().zip(valid).map(|(q, v)| if v != 0 { Some(q) } else { None }).collect())
     }
 
     /// SM2DSA `verify_prehash` over a batch: `e` = SM3(Z_A || M) per signature (`VerifyingKey::hash_msg`).

@@ -934,3 +934,22 @@ extern "C" int simk_sm2dsa_verify(size_t n, const uint8_t* e, const uint8_t* sig
   sim_launch(n, 256, [&] { sm2dsa_check_kernel<C>(e, sig, vxy.data(), vinf.data(), vok.data(), n, valid); });
   return (int)status[0];
 }
+
+// ecg_ecdsa_recover_batch: prep (decompress R, batched r^-1) -> u1*G + u2*R -> affine -> key + verdict
+template <class C, bool IS_K256>
+static int simk_recover(size_t n, const uint8_t* z, const uint8_t* sig, const uint8_t* recid, int low_s, const uint32_t* table, uint8_t* out_xy,
+                        uint8_t* valid) {
+  std::vector<uint32_t> scr(8 * n + 8);
+  std::vector<uint8_t> vp(64 * n), va(32 * n), vb(32 * n), vok(n);
+  uint32_t status[2] = {0, 0xFFFFFFFFu};
+  size_t threads = (n + 31) / 32;
+  sim_launch(threads, 128, [&] { ecdsa_recover_prep_kernel<C>(z, sig, recid, n, low_s, scr.data(), vp.data(), va.data(), vb.data(), vok.data()); });
+  simk_mga<C, IS_K256>(n, va.data(), vb.data(), vp.data(), nullptr, table, out_xy, valid, status);
+  sim_launch(n, 256, [&] { ecdsa_recover_finish_kernel<>(out_xy, valid, vok.data(), n); });
+  return (int)status[0];
+}
+extern "C" int simk_ecdsa_recover_batch(int curve, size_t n, const uint8_t* z, const uint8_t* sig, const uint8_t* recid, int low_s,
+                                        const uint32_t* table, uint8_t* out_xy, uint8_t* valid) {
+  return curve == 0 ? simk_recover<CurveK256, true>(n, z, sig, recid, low_s, table, out_xy, valid)
+                    : simk_recover<CurveP256, false>(n, z, sig, recid, low_s, table, out_xy, valid);
+}

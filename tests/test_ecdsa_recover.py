@@ -1,0 +1,182 @@
+"""ECDSA public-key recovery over a batch (the Ethereum `ecrecover` shape): ecdsa_core::VerifyingKey::recover_from_prehash as
+k256 / p256 re-export it (k256/src/ecdsa.rs:45-88) — R = decompress(r [+ n], parity), Q = r^-1 (s R - z G), i.e. SEC1
+decompression feeding a*G + b*P (rank 1).
+
+Pinned to the reference's own vectors: RECOVERY_TEST_VECTORS (k256/src/ecdsa.rs:190-211, SHA-256 of "example message", recovery
+ids 0 and 1) and the Ethereum end-to-end example (:229-261: Keccak-256 digest, signature bytes, recovery id 0, key = d*G), then every
+valid Wycheproof signature of both curves (the recovery id found with the model; the other three ids must give the model's answer
+too), crafted signatures with the x-reduced bit (x = r + n), and refusals.  CPU: the kernels on the host.  GPU: through the C ABI."""
+import ctypes
+import hashlib
+import random
+
+import numpy as np
+import pytest
+
+import pyref
+from helpers import wycheproof_cases
+from test_sim import sim  # noqa: F401
+from test_sim_kernels import fb_tables  # noqa: F401
+
+CID = {"k256": 0, "p256": 1}
+REF_VECTORS = [   # (compressed public key, message, r || s, recovery id)
+    ("021a7a569e91dbf60581509c7fc946d1003b60c7dee85299538db6353538d59574", b"example message",
+     "ce53abb3721bafc561408ce8ff99c909f7f0b18a2f788649d6470162ab1aa0323971edc523a6d6453f3fb6128d318d9db1a5ff3386feb1047d9816e780039d52", 0),
+    ("036d6caac248af96f6afa7f904f550253a0f3ef3f5aa2fe6838a95b216691468e2", b"example message",
+     "46c05b6368a44b8810d79859441d819b8e7cdc8bfd371e35c53196f4bcacdb5135c7facce2a97b95eacba8a586d87b7958aaf8368ab29cee481f76e871dbd9cb", 1),
+]
+ETH_KEY = 0x4C0883A69102937D6231471B5DBB6204FE5129617082792AE468D01A3F362318
+ETH_MSG = bytes.fromhex("e9808504e3b29200831e848094f0109fc8df283027b6285cc889f5aa624eac1f55843b9aca0080018080")
+ETH_SIG = "c9cf86333bcb065d140032ecaab5d9281bde80f21b9687b3e94161de42d51895727a108a0b8d101465414033c3f705a9c7b826e596766046ee1183dbc8aeaa68"
+
+
+def keccak256(data: bytes) -> bytes:
+    """Keccak-256 with the original 0x01 padding (sha3::Keccak256), for the Ethereum vector; hashlib only has the FIPS 202 padding"""
+    rc, r = [], 1
+    for _ in range(24):
+        v = 0
+        for j in range(7):
+            r = ((r << 1) ^ ((r >> 7) * 0x71)) & 0xFF
+            if r & 2:
+                v ^= 1 << ((1 << j) - 1)
+        rc.append(v)
+    rot = [[0, 36, 3, 41, 18], [1, 44, 10, 45, 2], [62, 6, 43, 15, 61], [28, 55, 25, 21, 56], [27, 20, 39, 8, 14]]
+    m64 = (1 << 64) - 1
+    rol = lambda x, n: ((x << n) | (x >> (64 - n))) & m64 if n else x  # noqa: E731
+    st = [[0] * 5 for _ in range(5)]
+    rate = 136
+    msg = bytearray(data) + b"\x01" + bytes(-(len(data) + 1) % rate)
+    msg[-1] |= 0x80
+    for off in range(0, len(msg), rate):
+        for i in range(rate // 8):
+            st[i % 5][i // 5] ^= int.from_bytes(msg[off + 8 * i:off + 8 * i + 8], "little")
+        for rnd in range(24):
+            c = [st[x][0] ^ st[x][1] ^ st[x][2] ^ st[x][3] ^ st[x][4] for x in range(5)]
+            d = [c[(x - 1) % 5] ^ rol(c[(x + 1) % 5], 1) for x in range(5)]
+            st = [[st[x][y] ^ d[x] for y in range(5)] for x in range(5)]
+            b = [[0] * 5 for _ in range(5)]
+            for x in range(5):
+                for y in range(5):
+                    b[y][(2 * x + 3 * y) % 5] = rol(st[x][y], rot[x][y])
+            st = [[b[x][y] ^ (~b[(x + 1) % 5][y] & m64 & b[(x + 2) % 5][y]) for y in range(5)] for x in range(5)]
+            st[0][0] ^= rc[rnd]
+    return b"".join(st[i % 5][i // 5].to_bytes(8, "little") for i in range(4))
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def cases_for(curve):
+    """[(z bytes, r, s, recid, low_s, expected key | None)]"""
+    c = pyref.CURVES[curve]
+    n = c.n
+    low = curve == "k256"
+    out = []
+    if curve == "k256":
+        for pk, msg, sig, rid in REF_VECTORS:
+            z = hashlib.sha256(msg).digest()
+            r, s = int(sig[:64], 16), int(sig[64:], 16)
+            Q = pyref.ecdsa_recover(c, int.from_bytes(z, "big"), r, s, rid, low)
+            assert Q is not None and (bytes([2 + (Q[1] & 1)]) + Q[0].to_bytes(32, "big")).hex() == pk     # the model on the reference's vectors
+            out.append((z, r, s, rid, low, Q))
+        z = keccak256(ETH_MSG)
+        r, s = int(ETH_SIG[:64], 16), int(ETH_SIG[64:], 16)
+        Q = pyref.ecdsa_recover(c, int.from_bytes(z, "big"), r, s, 0, low)
+        assert Q == pyref.mul(c, ETH_KEY, pyref.G(c))
+        out.append((z, r, s, 0, low, Q))
+    # every valid Wycheproof signature: some recovery id gives back the vector's key; all four ids follow the model
+    valid = [x for x in wycheproof_cases(curve)[0] if x[4]]
+    assert len(valid) > 100
+    for z, r, s, q, _ in valid[::2]:
+        zi = int.from_bytes(z, "big")
+        got = [pyref.ecdsa_recover(c, zi, r, s, rid, low) for rid in range(4)]
+        assert q in got
+        out += [(z, r, s, rid, low, got[rid]) for rid in range(4)]
+    # the x-reduced bit: r small enough that x = r + n < p
+    rng = random.Random(5)
+    found = 0
+    r = 1
+    while found < 6:
+        r += 1
+        s, z = rng.randrange(1, n // 2), rng.randrange(1 << 256)
+        for rid in (2, 3):
+            Q = pyref.ecdsa_recover(c, z, r, s, rid, low)
+            found += Q is not None
+            out.append((z.to_bytes(32, "big"), r, s, rid, low, Q))
+    # refusals: r = 0, s = 0, r = n, s = n, a recovery id out of range, a high s under NORMALIZE_S (and accepted without it)
+    z, r, s, rid, _, Q = out[0] if curve == "k256" else next(x for x in out if x[5] is not None)
+    out += [(z, 0, s, rid, low, None), (z, r, 0, rid, low, None), (z, n, s, rid, low, None), (z, r, n, rid, low, None), (z, r, s, 4, low, None),
+            (z, r, s, 255, low, None)]
+    zi = int.from_bytes(z, "big")
+    out.append((z, r, n - s, rid ^ 1, True, None))
+    out.append((z, r, n - s, rid ^ 1, False, pyref.ecdsa_recover(c, zi, r, n - s, rid ^ 1, False)))
+    assert out[-1][5] == Q                                  # (r, n - s) with the flipped parity recovers the same key
+    return out
+
+
+def pack(cases):
+    Z = np.frombuffer(b"".join(x[0] for x in cases), np.uint8).copy()
+    S = np.frombuffer(b"".join((x[1] % (1 << 256)).to_bytes(32, "big") + (x[2] % (1 << 256)).to_bytes(32, "big") for x in cases), np.uint8).copy()
+    R = np.array([x[3] for x in cases], np.uint8)
+    return Z, S, R
+
+
+def check(cases, xy, valid):
+    xy = np.asarray(xy).reshape(-1, 64)
+    for i, x in enumerate(cases):
+        if x[5] is None:
+            assert not valid[i] and not xy[i].any(), i
+        else:
+            assert valid[i] and (int.from_bytes(xy[i, :32].tobytes(), "big"), int.from_bytes(xy[i, 32:].tobytes(), "big")) == x[5], i
+
+
+def run_groups(cases, fn):
+    """the low-S flag is per call: one call per flag value"""
+    for flag in (False, True):
+        grp = [x for x in cases if x[4] == flag]
+        if grp:
+            Z, S, R = pack(grp)
+            xy, valid = fn(Z, S, R, flag)
+            check(grp, xy, valid)
+
+
+@pytest.mark.parametrize("curve", ["k256", "p256"])
+def test_kernels_on_host(sim, fb_tables, curve):  # noqa: F811
+    cases = cases_for(curve)
+    assert sum(x[5] is not None for x in cases) > 60 and sum(x[5] is None for x in cases) > 20
+
+    def fn(Z, S, R, flag):
+        n = R.size
+        xy, valid = np.full(64 * n, 9, np.uint8), np.full(n, 9, np.uint8)
+        assert sim.simk_ecdsa_recover_batch(CID[curve], ctypes.c_size_t(n), _p(Z), _p(S), _p(R), int(flag), _p(fb_tables[curve]), _p(xy), _p(valid)) == 0
+        return xy, valid
+
+    run_groups(cases, fn)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("curve", ["k256", "p256"])
+def test_gpu_ecdsa_recover(engine, curve):
+    import ecgpu
+
+    c = pyref.CURVES[curve]
+    cases = cases_for(curve)
+    # plus a larger batch of signatures made here: the recovery id from the nonce point, as sign_prehash_recoverable reports it
+    rng = random.Random(17)
+    low = curve == "k256"
+    for _ in range(400):
+        d, k, z = rng.randrange(1, c.n), rng.randrange(1, c.n), rng.randrange(1 << 256)
+        Rp = pyref.mul(c, k, pyref.G(c))
+        r = Rp[0] % c.n
+        s = pow(k, -1, c.n) * (z + r * d) % c.n
+        rid = (Rp[1] & 1) | (2 if Rp[0] >= c.n else 0)
+        if s > c.n // 2:                                   # normalize_s flips the parity bit with it
+            s, rid = c.n - s, rid ^ 1
+        if r and s:
+            cases.append((z.to_bytes(32, "big"), r, s, rid, low, pyref.mul(c, d, pyref.G(c))))
+    run_groups(cases, lambda Z, S, R, flag: engine.ecdsa_recover_batch(curve, Z, S, R, low_s_only=flag))
+    xy, valid = engine.ecdsa_recover_batch(curve, np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(0, np.uint8))
+    assert xy.shape[0] == 0 and valid.size == 0
+    with pytest.raises(ecgpu.EcgError):                    # written for the two 256-bit hot-path curves
+        engine.ecdsa_recover_batch("p384", np.zeros(32, np.uint8), np.zeros(64, np.uint8), np.zeros(1, np.uint8))
