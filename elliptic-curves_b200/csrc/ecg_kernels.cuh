@@ -482,14 +482,48 @@ ECG_KERNEL(256)
 
 // Public-key recovery (ecdsa_core::VerifyingKey::recover_from_prehash, the Ethereum `ecrecover` shape; k256/src/ecdsa.rs:45-88,
 // vectors :182-262): R = decompress(r [+ n if recid bit 1], y odd = recid bit 0); Q = r^-1 (s R - z G) = u1*G + u2*R with
-// u1 = -z r^-1, u2 = s r^-1.  One inversion mod n per thread slice (Montgomery's trick over the r_i); scr: 8 * n words.
-// recid: one byte per signature, RecoveryId::to_byte (0..3).
+// u1 = -z r^-1, u2 = s r^-1.  recid: one byte per signature, RecoveryId::to_byte (0..3).
+// Two front-end kernels: the square root of the decompression is the expensive part and runs one thread per signature;
+// the inversion of the r_i is shared per thread slice (Montgomery's trick) in a second, strided kernel.
 template <class C>
 ECG_KERNEL(128)
-    ecdsa_recover_prep_kernel(const uint8_t* __restrict__ zb, const uint8_t* __restrict__ sig, const uint8_t* __restrict__ recid, size_t n,
-                              int low_s_only, uint32_t* __restrict__ scr, uint8_t* __restrict__ pxy, uint8_t* __restrict__ a_out,
-                              uint8_t* __restrict__ b_out, uint8_t* __restrict__ ok_out) {
+    ecdsa_recover_point_kernel(const uint8_t* __restrict__ sig, const uint8_t* __restrict__ recid, size_t n, int low_s_only,
+                               uint8_t* __restrict__ pxy, uint8_t* __restrict__ ok_out) {
   typedef typename C::F F;
+  typedef FnMont<C> N;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  uint32_t r[8], sv[8], x[8];
+  load_be32(r, sig + 64 * idx);
+  load_be32(sv, sig + 64 * idx + 32);
+  const uint32_t id = recid[idx];
+  bool ok = id < 4 && lt8(r, C::N()) && !N::is_zero(r) && lt8(sv, C::N()) && !N::is_zero(sv);
+  if (ok && low_s_only) {  // the closing verify_prehash of a NORMALIZE_S curve refuses s > n/2
+    uint32_t twice[8];
+    uint32_t c = add8(twice, sv, sv);
+    ok = !c && lt8(twice, C::N());
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) x[i] = r[i];
+  if (id & 2u) {  // is_x_reduced: the x coordinate of R was r + n (checked_add: no wrap past 2^256; decompress refuses x >= p)
+    uint32_t c = add8(x, r, C::N());
+    ok = ok && !c;
+  }
+  Aff R;
+  ok = ok && sec1_decompress<C>(R, x, id & 1u);
+  Fe cx, cy;
+  if (!ok) C::generator(R);  // a harmless stand-in keeps the middle kernel's input checks quiet; the verdict is already 0
+  F::to_canonical(cx, R.x);
+  F::to_canonical(cy, R.y);
+  store_be32(pxy + 64 * idx, cx.v);
+  store_be32(pxy + 64 * idx + 32, cy.v);
+  ok_out[idx] = ok ? 1 : 0;
+}
+// scr: 8 * n words
+template <class C>
+ECG_KERNEL(128)
+    ecdsa_recover_prep_kernel(const uint8_t* __restrict__ zb, const uint8_t* __restrict__ sig, const uint8_t* __restrict__ ok_in, size_t n,
+                              uint32_t* __restrict__ scr, uint8_t* __restrict__ a_out, uint8_t* __restrict__ b_out) {
   typedef FnMont<C> N;
   size_t T = (size_t)gridDim.x * blockDim.x;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -499,32 +533,9 @@ ECG_KERNEL(128)
   for (int i = 0; i < 8; i++) acc[i] = C::N_ONE()[i];
   size_t last = t;
   for (size_t idx = t; idx < n; idx += T) {
-    uint32_t r[8], sv[8], x[8];
+    uint32_t r[8];
     load_be32(r, sig + 64 * idx);
-    load_be32(sv, sig + 64 * idx + 32);
-    const uint32_t id = recid[idx];
-    bool ok = id < 4 && lt8(r, C::N()) && !N::is_zero(r) && lt8(sv, C::N()) && !N::is_zero(sv);
-    if (ok && low_s_only) {  // the closing verify_prehash of a NORMALIZE_S curve refuses s > n/2
-      uint32_t twice[8];
-      uint32_t c = add8(twice, sv, sv);
-      ok = !c && lt8(twice, C::N());
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) x[i] = r[i];
-    if (id & 2u) {  // is_x_reduced: the x coordinate of R was r + n (checked_add: no wrap past 2^256; decompress refuses x >= p)
-      uint32_t c = add8(x, r, C::N());
-      ok = ok && !c;
-    }
-    Aff R;
-    ok = ok && sec1_decompress<C>(R, x, id & 1u);
-    Fe cx, cy;
-    if (!ok) C::generator(R);
-    F::to_canonical(cx, R.x);
-    F::to_canonical(cy, R.y);
-    store_be32(pxy + 64 * idx, cx.v);
-    store_be32(pxy + 64 * idx + 32, cy.v);
-    ok_out[idx] = ok ? 1 : 0;
-    if (!ok) {
+    if (!ok_in[idx]) {
 #pragma unroll
       for (int i = 0; i < 8; i++) r[i] = (i == 0);
     }
@@ -537,7 +548,7 @@ ECG_KERNEL(128)
   N::inv(inv, acc);
   for (size_t idx = last;; idx -= T) {
     uint32_t r[8], sv[8], z[8], pre[8], w[8], u1[8], u2[8];
-    bool ok = ok_out[idx] != 0;
+    bool ok = ok_in[idx] != 0;
     load_be32(r, sig + 64 * idx);
     load_be32(sv, sig + 64 * idx + 32);
     load_be32(z, zb + 32 * idx);

@@ -871,10 +871,14 @@ static ecg_status run_chunk(ecg_ctx* ctx, DevState& d, Lane& L, const BatchOp& o
     } else if (op.kind == BatchOp::RECOVER) {
       ST_TRY(ensure(ctx, L, B_SCR, cnt * 32));
       size_t want_threads = std::max<size_t>((cnt + 31) / 32, std::min<size_t>(cnt, (size_t)d.sm_count * 128));
-      if (k1c)
-        ecdsa_recover_prep_kernel<CurveK256><<<grid_for(want_threads, 128), 128, 0, L.s()>>>(dp.k, dp.p, dp.inf, cnt, op.fop, (uint32_t*)L.buf[B_SCR], vp, va, vb, vok);
-      else
-        ecdsa_recover_prep_kernel<CurveP256><<<grid_for(want_threads, 128), 128, 0, L.s()>>>(dp.k, dp.p, dp.inf, cnt, op.fop, (uint32_t*)L.buf[B_SCR], vp, va, vb, vok);
+      if (k1c) {
+        ecdsa_recover_point_kernel<CurveK256><<<grid_for(cnt, 128), 128, 0, L.s()>>>(dp.p, dp.inf, cnt, op.fop, vp, vok);
+        ecdsa_recover_prep_kernel<CurveK256><<<grid_for(want_threads, 128), 128, 0, L.s()>>>(dp.k, dp.p, vok, cnt, (uint32_t*)L.buf[B_SCR], va, vb);
+      } else {
+        ecdsa_recover_point_kernel<CurveP256><<<grid_for(cnt, 128), 128, 0, L.s()>>>(dp.p, dp.inf, cnt, op.fop, vp, vok);
+        ecdsa_recover_prep_kernel<CurveP256><<<grid_for(want_threads, 128), 128, 0, L.s()>>>(dp.k, dp.p, vok, cnt, (uint32_t*)L.buf[B_SCR], va, vb);
+      }
+      LAUNCHED(ctx);
     } else {
       ST_TRY(ensure(ctx, L, B_SCR, cnt * 32));
       size_t want_threads = std::max<size_t>((cnt + 31) / 32, std::min<size_t>(cnt, (size_t)d.sm_count * 128));

@@ -342,7 +342,7 @@ class Engine:
         data, offs = self._pack_messages(msgs)
         return self.hash_to_curve_packed(curve, data, offs, dst, nonuniform)
 
-    def hash_to_curve_packed(self, curve, data, offsets, dst: bytes, nonuniform: bool = False):
+    def hash_to_curve_packed(self, curve, data, offsets, dst: bytes, nonuniform: bool = False, out_xy=None, out_inf=None):
         """the same over messages already laid out as the C ABI takes them: `data` = the messages back to back (uint8),
         `offsets` = n + 1 uint64 byte offsets (message i = data[offsets[i]:offsets[i + 1]])"""
         c = CURVE_IDS[curve]
@@ -355,8 +355,8 @@ class Engine:
             data = np.zeros(1, np.uint8)
         d = np.frombuffer(bytes(dst), np.uint8).copy() if len(dst) else np.zeros(1, np.uint8)
         fb = FBYTES[c]
-        out_xy = np.empty(2 * fb * n, np.uint8)
-        out_inf = np.empty(n, np.uint8)
+        out_xy = _out(out_xy, 2 * fb * n, "out_xy")
+        out_inf = _out(out_inf, n, "out_inf")
         self._check(self.lib.ecg_hash_to_curve_batch(self._ctx, c, n, _ptr(data), _ptr(offs), _ptr(d), len(dst), 1 if nonuniform else 0,
                                                      _ptr(out_xy), _ptr(out_inf)))
         return out_xy.reshape(n, 2 * fb), out_inf
@@ -398,7 +398,7 @@ class Engine:
         self._check(self.lib.ecg_ecdsa_verify_batch(self._ctx, c, n, _ptr(z32), _ptr(sig64), _ptr(Q_xy), 1 if low_s_only else 0, _ptr(valid)))
         return valid
 
-    def ecdsa_recover_batch(self, curve, z32, sig64, recid, low_s_only=False):
+    def ecdsa_recover_batch(self, curve, z32, sig64, recid, low_s_only=False, out_xy=None, valid=None):
         """VerifyingKey::recover_from_prehash over a batch (secp256k1 / P-256) -> (Q_xy n x 64, valid): prehash, r || s, one
         RecoveryId byte (bit 0: y of R odd, bit 1: x of R = r + n) per signature"""
         c = CURVE_IDS[curve]
@@ -406,8 +406,8 @@ class Engine:
         z32 = _u8(z32, 32 * n, "z")
         sig64 = _u8(sig64, 64 * n, "sig")
         recid = _u8(recid, n, "recid")
-        out_xy = np.empty(64 * n, np.uint8)
-        valid = np.zeros(n, np.uint8)
+        out_xy = _out(out_xy, 64 * n, "out_xy")
+        valid = _out(valid, n, "valid")
         self._check(self.lib.ecg_ecdsa_recover_batch(self._ctx, c, n, _ptr(z32), _ptr(sig64), _ptr(recid), 1 if low_s_only else 0,
                                                      _ptr(out_xy), _ptr(valid)))
         return out_xy.reshape(n, 64), valid

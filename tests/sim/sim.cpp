@@ -943,7 +943,8 @@ static int simk_recover(size_t n, const uint8_t* z, const uint8_t* sig, const ui
   std::vector<uint8_t> vp(64 * n), va(32 * n), vb(32 * n), vok(n);
   uint32_t status[2] = {0, 0xFFFFFFFFu};
   size_t threads = (n + 31) / 32;
-  sim_launch(threads, 128, [&] { ecdsa_recover_prep_kernel<C>(z, sig, recid, n, low_s, scr.data(), vp.data(), va.data(), vb.data(), vok.data()); });
+  sim_launch(n, 128, [&] { ecdsa_recover_point_kernel<C>(sig, recid, n, low_s, vp.data(), vok.data()); });
+  sim_launch(threads, 128, [&] { ecdsa_recover_prep_kernel<C>(z, sig, vok.data(), n, scr.data(), va.data(), vb.data()); });
   simk_mga<C, IS_K256>(n, va.data(), vb.data(), vp.data(), nullptr, table, out_xy, valid, status);
   sim_launch(n, 256, [&] { ecdsa_recover_finish_kernel<>(out_xy, valid, vok.data(), n); });
   return (int)status[0];

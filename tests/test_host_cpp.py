@@ -138,6 +138,15 @@ int main() {
     REQUIRE(ev[0] && !ev[1]);
     auto pv = p1.ecdsa_verify_prehash({h32("@PZ@")}, {h64("@PSIG@")}, {pt("@PQX@", "@PQY@")}, false);
     REQUIRE(pv[0]);
+    // public-key recovery: the FIPS vector's key comes back under its recovery id; an id out of range is refused
+    std::vector<bool> rok;
+    auto rk = k1.ecdsa_recover_prehash({h32("@KZ@"), h32("@KZ@")}, {h64("@KSIG@"), h64("@KSIG@")}, {@KRID@, 4}, false, &rok);
+    REQUIRE(rok[0] && !rok[1] && same(rk[0], pt("@KQX@", "@KQY@")));
+    // SM2DSA: a signature made with the model, and the same signature over another digest
+    Engine s2(ECG_SM2);
+    auto sm = s2.sm2dsa_verify_prehash({h32("@SE@"), h32("@SE2@")}, {h64("@SSIG@"), h64("@SSIG@")},
+                                       {pt("@SQX@", "@SQY@"), pt("@SQX@", "@SQY@")});
+    REQUIRE(sm[0] && !sm[1]);
     std::printf("cpp mirror ok\n");
     return 0;
   } catch (const Error& e) {
@@ -185,6 +194,14 @@ def _full_source():
     rep = {"@BPK@": bip["pk"], "@BMSG@": bip["msg"], "@BMSG2@": bip["msg"][:-2] + "00", "@BSIG@": bip["sig"],
            "@KZ@": z_of(ke), "@KSIG@": ke["r"] + ke["s"], "@KSIG_BAD@": bad, "@KQX@": ke["q_x"], "@KQY@": ke["q_y"],
            "@PZ@": z_of(pe), "@PSIG@": pe["r"] + pe["s"], "@PQX@": pe["q_x"], "@PQY@": pe["q_y"]}
+    kz, kr, ks_ = int(z_of(ke), 16), int(ke["r"], 16), int(ke["s"], 16)
+    kq = (int(ke["q_x"], 16), int(ke["q_y"], 16))
+    rep["@KRID@"] = str(next(i for i in range(4) if pyref.ecdsa_recover(pyref.K256, kz, kr, ks_, i) == kq))
+    sm2 = pyref.CURVES["sm2"]
+    d, e = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF, 0x55AA55AA55AA55AA55AA55AA55AA55AA55AA55AA55AA55AA55AA55AA55AA55AA
+    sr, ss = pyref.sm2dsa_sign(d, e, 0x1F2E3D4C5B6A79880123456789ABCDEF)
+    sq = pyref.mul(sm2, d, pyref.G(sm2))
+    rep.update({"@SE@": _h(e), "@SE2@": _h(e ^ 1), "@SSIG@": _h(sr) + _h(ss), "@SQX@": _h(sq[0]), "@SQY@": _h(sq[1])})
     for k, v in rep.items():
         src = src.replace(k, v)
     return src
