@@ -200,27 +200,28 @@ def test_varbase_kernel_chain(sim, cid):
     assert st[0] == 3 and st[1] == 3
 
 
+_FB_CACHE = {}
+
+
+def ext_fb_table(sim, cid):
+    """the fixed-base table as ensure_fb_table (ecgpu.cu) builds it: entry (i, j) = (2j + 1) 2^(16 i) G, then 2^(32 NL) G, here
+    computed by the C restatement and converted by affine_to_table_kernel; built once per test session (2^15 * 2 NL + 1 points)"""
+    if cid not in _FB_CACHE:
+        c = EXT[cid]
+        nl = (pyref.fbytes(c) + 3) // 4
+        ks = [((2 * j + 1) << (16 * i)) % c.n for i in range(2 * nl) for j in range(1 << 15)] + [(1 << (32 * nl)) % c.n]
+        xy, inf = ecref.mul_gen_batch(c.name, recs(c, ks), nthreads=os.cpu_count() or 4)
+        assert not inf.any()
+        table = np.zeros(len(ks) * 2 * nl, np.uint32)
+        flat = np.ascontiguousarray(xy).reshape(-1)
+        sim.simk_affine_to_table(cid, ctypes.c_size_t(len(ks)), _p(flat), _p(table))
+        _FB_CACHE[cid] = table
+    return _FB_CACHE[cid]
+
+
 @pytest.fixture(scope="module")
 def fb_tables(sim):
-    """fixed-base tables as ensure_fb_table (ecgpu.cu) builds them: entry (i, j) = (2j + 1) 2^(16 i) G, then 2^(32 NL) G,
-    here computed by the C restatement and converted by affine_to_table_kernel"""
-    cache = {}
-
-    def get(cid):
-        if cid not in cache:
-            c = EXT[cid]
-            nb = pyref.fbytes(c)
-            nl = nb // 4
-            ks = [((2 * j + 1) << (16 * i)) % c.n for i in range(2 * nl) for j in range(1 << 15)] + [(1 << (32 * nl)) % c.n]
-            xy, inf = ecref.mul_gen_batch(c.name, recs(c, ks), nthreads=os.cpu_count() or 4)
-            assert not inf.any()
-            table = np.zeros(len(ks) * 2 * nl, np.uint32)
-            flat = np.ascontiguousarray(xy).reshape(-1)
-            sim.simk_affine_to_table(cid, ctypes.c_size_t(len(ks)), _p(flat), _p(table))
-            cache[cid] = table
-        return cache[cid]
-
-    return get
+    return lambda cid: ext_fb_table(sim, cid)
 
 
 @pytest.mark.parametrize("cid", [3, 4, 6, 9])   # one a = -3, one general-a, the little-endian one, the 7-limb one

@@ -17,7 +17,7 @@ import pytest
 import ecref
 import pyref
 from helpers import GOLDEN, wycheproof_cases
-from test_curves_ext import pts, recs, unpack
+from test_curves_ext import ext_fb_table, pts, recs, unpack
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ECDSA_CURVES = ["p384", "bp256r1", "bp256t1", "bp384r1", "bp384t1", "p224", "p192", "p521"]
@@ -85,7 +85,7 @@ def test_model_on_reference_vectors(curve):
     if curve != "p192":
         cases, rejected = wycheproof_cases(curve)
         assert len(cases) > 100 and all(not v["pass"] for v in rejected)
-        for z, r, s, Q, exp in cases:
+        for z, r, s, Q, exp in cases[::3 if curve == "p521" else 2]:      # big-integer model: a sample here, every record on the GPU
             assert pyref.ecdsa_verify(c, int.from_bytes(z, "big"), r, s, Q) == exp
 
 
@@ -97,12 +97,7 @@ def test_kernels_on_host(curve):
     c = pyref.CURVES[curve]
     cid = pyref.CURVE_IDS[curve]
     nb = pyref.fbytes(c)
-    nl = (nb + 3) // 4
-    ks = [((2 * j + 1) << (16 * i)) % c.n for i in range(2 * nl) for j in range(1 << 15)] + [(1 << (32 * nl)) % c.n]
-    xy, inf = ecref.mul_gen_batch(curve, recs(c, ks), nthreads=os.cpu_count() or 4)
-    table = np.zeros(len(ks) * 2 * nl, np.uint32)
-    flat = np.ascontiguousarray(xy).reshape(-1)
-    sim.simk_affine_to_table(cid, ctypes.c_size_t(len(ks)), _p(flat), _p(table))
+    table = ext_fb_table(sim, cid)
     cases = fips_cases(curve) + made_cases(curve, 12, 5)
     if curve == "p224":
         cases += wycheproof_cases(curve)[0][::3]

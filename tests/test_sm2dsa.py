@@ -13,9 +13,8 @@ import random
 import numpy as np
 import pytest
 
-import ecref
 import pyref
-from test_curves_ext import recs
+from test_curves_ext import ext_fb_table, recs
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 C = pyref.CURVES["sm2"]
@@ -92,11 +91,7 @@ def test_kernels_on_host():
     ge.build()
     sim = ctypes.CDLL(os.path.join(HERE, "sim", "libecgsim.so"))
     cid = pyref.CURVE_IDS["sm2"]
-    ks = [((2 * j + 1) << (16 * i)) % C.n for i in range(16) for j in range(1 << 15)] + [(1 << 256) % C.n]
-    xy, inf = ecref.mul_gen_batch("sm2", recs(C, ks), nthreads=os.cpu_count() or 4)
-    table = np.zeros(len(ks) * 16, np.uint32)
-    flat = np.ascontiguousarray(xy).reshape(-1)
-    sim.simk_affine_to_table(cid, ctypes.c_size_t(len(ks)), _p(flat), _p(table))
+    table = ext_fb_table(sim, cid)
     cases = made_cases(8, 3)
     if "sm3" in hashlib.algorithms_available:
         cases.append(ref_case())
