@@ -197,8 +197,8 @@ ecg_status ecg_sm2dsa_verify_batch(ecg_ctx* ctx, size_t n, const uint8_t* e32, c
                                    uint8_t* valid);
 
 /* SEC1 compressed point decoding (rank 2 of SURVEY 8(f)): records of 1 + FB bytes (02|03 || x; all zero bytes = the
- * identity; 33 bytes for the 256-bit curves, 49 for the 384-bit ones, 25 for P-192, 67 for P-521).  valid[i] = 0 when the tag is unknown, x >= p, or x^3 + ax + b has no square root; out_xy / out_inf as
- * in ecg_mul_batch.  Replaces AffinePoint::decompress / from_sec1_point over a batch
+ * identity; 33 bytes for the 256-bit curves, 49 for the 384-bit ones, 29 for P-224, 25 for P-192, 67 for P-521).
+ * valid[i] = 0 when the tag is unknown, x >= p, or x^3 + ax + b has no square root; out_xy / out_inf as in ecg_mul_batch.  Replaces AffinePoint::decompress / from_sec1_point over a batch
  * (primeorder/src/affine.rs:179-198, :212-232; k256/src/arithmetic/affine.rs DecompressPoint; sqrt:
  * k256/src/arithmetic/field.rs:200-235, p256/src/arithmetic/field.rs:121-147, p521/src/arithmetic/field.rs:386; the
  * primefield-generated fields of p384 / sm2 / brainpool / p192, primefield/src/monty.rs:467, through the same
