@@ -128,6 +128,8 @@ def main():
             out.append("struct Mp%s {\n  static constexpr int NL = %d;\n  static constexpr int FB = %d;  // bytes per canonical record\n  static constexpr bool LE = %s;\n"
                        % (field, nl, c.get("fb", 4 * nl), "true" if c["le"] else "false"))
             out.append("  static constexpr uint32_t N0INV = 0x%08Xu;  // -p^-1 mod 2^32\n" % ((-pow(p, -1, 1 << 32)) % (1 << 32)))
+            mers = p.bit_length() if p == (1 << p.bit_length()) - 1 else 0
+            out.append("  static constexpr int MERSENNE = %d;  // B when p = 2^B - 1: the Montgomery reduction is a fold and a rotation (ecg_fe_mont.cuh)\n" % mers)
             out.append(accessor("P", p, nl))
             out.append(accessor("ONE", R % p, nl))
             out.append(accessor("R2", R * R % p, nl))
@@ -184,6 +186,7 @@ def main():
         R = 1 << (32 * nl)
         assert n % 2 == 1 and n < R
         out.append("struct Mn%s {\n  static constexpr int NL = %d;\n  static constexpr int FB = %d;\n  static constexpr bool LE = %s;\n" % (name, nl, fb, "true" if le else "false"))
+        out.append("  static constexpr int MERSENNE = 0;\n")
         out.append("  static constexpr uint32_t N0INV = 0x%08Xu;  // -n^-1 mod 2^32\n" % ((-pow(n, -1, 1 << 32)) % (1 << 32)))
         out.append(accessor("P", n, nl))
         out.append(accessor("ONE", R % n, nl))
