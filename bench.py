@@ -883,6 +883,8 @@ def measure_more_curves(B, steps):
         # multiplier slots executed per pair: M = 2 NL^2 + NL (integrated Montgomery product), S = NL(NL+1)/2 + NL^2 + NL;
         # 32 NL doublings (4M+4S; general a: 5M+6S) + 8 NL + 1 Jacobian additions (12M+4S) + table (1 dbl + 1 madd + 6 add)
         M, S = 2 * nl * nl + nl, nl * (nl + 1) // 2 + nl * nl + nl
+        if c.p == (1 << c.p.bit_length()) - 1:    # P-521: the Mersenne form of the reduction has no products (FpMontT::redc_mersenne)
+            M, S = nl * nl, nl * (nl + 1) // 2
         general_a = (c.a % c.p) != c.p - 3
         dbl = (5 * M + 6 * S) if general_a else (4 * M + 4 * S)
         slots = 32 * nl * dbl + (8 * nl + 1) * (12 * M + 4 * S) + dbl + (8 * M + 3 * S) + 6 * (12 * M + 4 * S)
