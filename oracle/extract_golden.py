@@ -13,6 +13,10 @@ Sources (relative to /root/reference):
   {k256,p256}/src/test_vectors/field.rs:6  DBL_TEST_VECTORS (2^i, 32 B BE)
   {k256,p256}/src/test_vectors/ecdsa.rs    d -> (q_x, q_y) pairs (a k*G fixture each)
   {k256,p256}/benches/point.rs             the criterion bench scalars
+  k256/src/ecdsa.rs:190-211,229-261        RECOVERY_TEST_VECTORS + the Ethereum example (public-key recovery)   -> sig_extras.json
+  sm2/tests/sm2dsa.rs:16-34                the SM2DSA signature vector                                          -> sig_extras.json
+  p384/tests/affine.rs:14-24               (UN)COMPRESSED_BASEPOINT                                             -> sig_extras.json
+  (Wycheproof blobs, BIP340, FIPS ECDSA, hash2curve, the other curves' group vectors: see the functions below)
 """
 import json
 import os
@@ -181,8 +185,48 @@ def h2c_vectors():
     return out
 
 
+def signature_extras():
+    """Vectors of the callers widened in round 2:
+    k256/src/ecdsa.rs:190-211 RECOVERY_TEST_VECTORS (pk, msg, sig, RecoveryId::new(is_y_odd, is_x_reduced)) and :229-261 the
+    Ethereum end-to-end example (signing key, message, signature bytes, recovery id 0);
+    sm2/tests/sm2dsa.rs:16-34 (PUBLIC_KEY, IDENTITY, MSG, SIG: an OpenSSL-made SM2DSA signature);
+    p384/tests/affine.rs:14-24 (UNCOMPRESSED_BASEPOINT / COMPRESSED_BASEPOINT)."""
+    def hx(t):
+        return re.sub(r"\s+", "", t).lower()
+
+    txt = open(f"{REF}/k256/src/ecdsa.rs").read()
+    rec = []
+    for m in re.finditer(r'RecoveryTestVector \{\s*pk: hex!\("([0-9a-fA-F]+)"\),\s*msg: b"([^"]*)",\s*sig: hex!\(\s*"([0-9a-fA-F\s]+)"\s*\),\s*'
+                         r'recid: RecoveryId::new\((true|false), (true|false)\)', txt):
+        rec.append({"pk": m.group(1).lower(), "msg": m.group(2), "sig": hx(m.group(3)),
+                    "recid": (1 if m.group(4) == "true" else 0) | (2 if m.group(5) == "true" else 0)})
+    assert len(rec) == 2
+    eth = txt[txt.index("fn ethereum_end_to_end_example"):]
+    key = re.search(r'SigningKey::from_bytes\(\s*&hex!\("([0-9a-f]+)"\)', eth).group(1)
+    msg = re.search(r'let msg = hex!\(\s*"([0-9a-f]+)"\s*\)', eth).group(1)
+    sig = re.search(r'sig\.to_bytes\(\)\.as_slice\(\),\s*&hex!\(\s*"([0-9a-f]+)"', eth).group(1)
+    rid = int(re.search(r"RecoveryId::from_byte\((\d)\)", eth).group(1))
+    sm = open(f"{REF}/sm2/tests/sm2dsa.rs").read()
+    sm2 = {"public_key": re.search(r'PUBLIC_KEY: \[u8; 65\] = hex!\(\s*"([0-9A-Fa-f]+)"', sm).group(1).lower(),
+           "identity": re.search(r'IDENTITY: &str = "([^"]+)"', sm).group(1),
+           "msg": re.search(r'MSG: &\[u8\] = b"([^"]+)"', sm).group(1),
+           "sig": "".join(h.lower() for h in re.findall(r'"([0-9a-f]{64})"', sm[sm.index("const SIG: [u8; 64]"):sm.index("fn verify_test_vector")]))}
+    assert len(sm2["sig"]) == 128 and len(sm2["public_key"]) == 130
+    af = open(f"{REF}/p384/tests/affine.rs").read()
+    comp = hx(re.search(r'COMPRESSED_BASEPOINT: &\[u8\] = &hex!\(\s*"([0-9a-fA-F\s]+)"', af[af.index("const COMPRESSED_BASEPOINT"):]).group(1))
+    unc = hx(re.search(r'UNCOMPRESSED_BASEPOINT: &\[u8\] = &hex!\(\s*"([0-9a-fA-F\s]+)"', af).group(1))
+    assert len(comp) == 98 and len(unc) == 194
+    return {"reference_commit": "739304e026fdf06cd1a31606e4db487d3f47c5ae",
+            "k256_recovery": rec, "k256_ethereum": {"signing_key": key, "msg_hex": msg, "sig": sig, "recid": rid, "digest": "keccak256"},
+            "sm2dsa": sm2, "p384_compressed_basepoint": comp, "p384_uncompressed_basepoint": unc}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "sig_extras.json"), "w") as f:
+        v = signature_extras()
+        json.dump(v, f, indent=1)
+        print("sig_extras", len(v["k256_recovery"]), "recovery vectors, ethereum example, sm2dsa vector, p384 basepoint encodings")
     for curve in ("k256", "p256", "p224", "p384", "p521"):
         with open(os.path.join(OUT, f"{curve}_wycheproof.json"), "w") as f:
             v = wycheproof(curve)

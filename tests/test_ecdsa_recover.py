@@ -8,26 +8,26 @@ valid Wycheproof signature of both curves (the recovery id found with the model;
 too), crafted signatures with the x-reduced bit (x = r + n), and refusals.  CPU: the kernels on the host.  GPU: through the C ABI."""
 import ctypes
 import hashlib
+import json
+import os
 import random
 
 import numpy as np
 import pytest
 
 import pyref
-from helpers import wycheproof_cases
+from helpers import GOLDEN, wycheproof_cases
 from test_sim import sim  # noqa: F401
 from test_sim_kernels import fb_tables  # noqa: F401
 
 CID = {"k256": 0, "p256": 1}
-REF_VECTORS = [   # (compressed public key, message, r || s, recovery id)
-    ("021a7a569e91dbf60581509c7fc946d1003b60c7dee85299538db6353538d59574", b"example message",
-     "ce53abb3721bafc561408ce8ff99c909f7f0b18a2f788649d6470162ab1aa0323971edc523a6d6453f3fb6128d318d9db1a5ff3386feb1047d9816e780039d52", 0),
-    ("036d6caac248af96f6afa7f904f550253a0f3ef3f5aa2fe6838a95b216691468e2", b"example message",
-     "46c05b6368a44b8810d79859441d819b8e7cdc8bfd371e35c53196f4bcacdb5135c7facce2a97b95eacba8a586d87b7958aaf8368ab29cee481f76e871dbd9cb", 1),
-]
-ETH_KEY = 0x4C0883A69102937D6231471B5DBB6204FE5129617082792AE468D01A3F362318
-ETH_MSG = bytes.fromhex("e9808504e3b29200831e848094f0109fc8df283027b6285cc889f5aa624eac1f55843b9aca0080018080")
-ETH_SIG = "c9cf86333bcb065d140032ecaab5d9281bde80f21b9687b3e94161de42d51895727a108a0b8d101465414033c3f705a9c7b826e596766046ee1183dbc8aeaa68"
+# tests/golden/sig_extras.json <- oracle/extract_golden.py <- k256/src/ecdsa.rs:190-211 (RECOVERY_TEST_VECTORS), :229-261 (Ethereum example)
+_X = json.load(open(os.path.join(GOLDEN, "sig_extras.json")))
+REF_VECTORS = [(v["pk"], v["msg"].encode(), v["sig"], v["recid"]) for v in _X["k256_recovery"]]   # (compressed key, message, r || s, id)
+ETH_KEY = int(_X["k256_ethereum"]["signing_key"], 16)
+ETH_MSG = bytes.fromhex(_X["k256_ethereum"]["msg_hex"])
+ETH_SIG = _X["k256_ethereum"]["sig"]
+ETH_RECID = _X["k256_ethereum"]["recid"]
 
 
 def keccak256(data: bytes) -> bytes:
@@ -82,9 +82,9 @@ def cases_for(curve):
             out.append((z, r, s, rid, low, Q))
         z = keccak256(ETH_MSG)
         r, s = int(ETH_SIG[:64], 16), int(ETH_SIG[64:], 16)
-        Q = pyref.ecdsa_recover(c, int.from_bytes(z, "big"), r, s, 0, low)
+        Q = pyref.ecdsa_recover(c, int.from_bytes(z, "big"), r, s, ETH_RECID, low)
         assert Q == pyref.mul(c, ETH_KEY, pyref.G(c))
-        out.append((z, r, s, 0, low, Q))
+        out.append((z, r, s, ETH_RECID, low, Q))
     # every valid Wycheproof signature: some recovery id gives back the vector's key; all four ids follow the model
     valid = [x for x in wycheproof_cases(curve)[0] if x[4]]
     assert len(valid) > 100

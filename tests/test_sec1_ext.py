@@ -5,6 +5,7 @@ reference with p = 3 (mod 4) — all but P-224 — that is one exponentiation by
 bign-curve256v1 records carry x in its little-endian FieldBytes (from_repr inside decompress).
 CPU: the kernels on the host; GPU: through the C ABI.  Expected values: the big-integer model."""
 import ctypes
+import json
 import os
 import random
 
@@ -17,7 +18,9 @@ from test_curves_ext import recs
 HERE = os.path.dirname(os.path.abspath(__file__))
 CURVES = ["p384", "sm2", "bp256r1", "bp256t1", "bignp256", "bp384r1", "bp384t1", "p224", "p192", "p521"]
 # p384/tests/affine.rs:21-24 (COMPRESSED_BASEPOINT); the identity is FB + 1 zero bytes (:71-77)
-P384_COMPRESSED_BASEPOINT = "03aa87ca22be8b05378eb1c71ef320ad746e1d3b628ba79b9859f741e082542a385502f25dbf55296c3a545e3872760ab7"
+_X = json.load(open(os.path.join(HERE, "golden", "sig_extras.json")))     # <- oracle/extract_golden.py
+P384_COMPRESSED_BASEPOINT = _X["p384_compressed_basepoint"]
+assert _X["p384_uncompressed_basepoint"] == "04" + "%096x%096x" % pyref.G(pyref.CURVES["p384"])
 SQRT_CURVES = [c for c in CURVES if c != "p224"]
 
 

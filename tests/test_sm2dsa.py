@@ -7,6 +7,7 @@ signatures made here with the model, each with the corruptions the reference's p
 tests/dsa_extended.rs:41-56: every signature byte flipped).  CPU: the kernels on the host.  GPU: through the C ABI."""
 import ctypes
 import hashlib
+import json
 import os
 import random
 
@@ -18,10 +19,12 @@ from test_curves_ext import ext_fb_table, recs
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 C = pyref.CURVES["sm2"]
-REF_Q = (0x08D77AE04C01CC4C1104360DD8AF6B6F7DF334283D7C1A6AFD5652407B87BEE5, 0x014E2A57C36C150D16324DC664E31E6432359609C4E79847A5B161C8C7364C8A)
-REF_ID, REF_MSG = b"example@rustcrypto.org", b"testing"
-REF_R = 0xD1DCCCEDD9FB785E0F67C16B7C52901625C0B69DE9BCA2144ACC7BE713CAD2FC
-REF_S = 0xF7D1EAE6E3A157B36C65F672F738CA8B46298BF149A6510072C431B49CD88B1C
+# tests/golden/sig_extras.json <- oracle/extract_golden.py <- sm2/tests/sm2dsa.rs:16-34 (PUBLIC_KEY, IDENTITY, MSG, SIG)
+_X = json.load(open(os.path.join(HERE, "golden", "sig_extras.json")))["sm2dsa"]
+assert _X["public_key"][:2] == "04"
+REF_Q = (int(_X["public_key"][2:66], 16), int(_X["public_key"][66:], 16))
+REF_ID, REF_MSG = _X["identity"].encode(), _X["msg"].encode()
+REF_R, REF_S = int(_X["sig"][:64], 16), int(_X["sig"][64:], 16)
 
 needs_sm3 = pytest.mark.skipif("sm3" not in hashlib.algorithms_available, reason="hashlib without SM3")
 
