@@ -136,7 +136,10 @@ def test_field_policy_on_host(sim, cid):
         assert sim.sim_ext_fe_op(cid, o, rec(c, a), rec(c, b), out) == 0
         return pyref.dec_fe(c, out.raw)
 
-    vals = [0, 1, 2, 3, p - 1, p - 2, (p + 1) // 2, (p - 1) // 2, 2**(8 * nb - 8) % p] + [rng.randrange(p) for _ in range(60)]
+    top = 1 << (p.bit_length() - 1)
+    # the last four: bit patterns around the fold / rotation boundaries of the Mersenne reduction (P-521: 23-bit rotation)
+    vals = [0, 1, 2, 3, p - 1, p - 2, (p + 1) // 2, (p - 1) // 2, 2**(8 * nb - 8) % p, (1 << 23) - 1, p - (1 << 23), top, top - 1] + \
+           [rng.randrange(p) for _ in range(60)]
     for a in vals:
         for b in rng.sample(vals, 5):
             assert op(0, a, b) == (a + b) % p
